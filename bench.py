@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- cells assembled/s (K+f, FP64, 3-D hex) on N B200s, one JSON line on stdout.
+
+Workload at N=1: BASELINE.json configs[1] = heat equation, scalar Q1 on generate_grid(Hexahedron,(200,200,200)),
+nodes perturbed deterministically so that cells are not congruent, K and f assembled
+in FP64 (zero-fill + gather + geometry + element + scatter).  A "step" is one full assembly.
+
+  value        device-resident throughput: cells / s with grid, dofs, pattern and map already in HBM
+  e2e          same metric through the host-buffer C-ABI path: per step the node coordinates are copied
+               host(pinned)->device and nzval + f are copied device->host(pinned)
+  roofline     dominant kernel (fused cell kernel) against the measured HBM peak, algorithmic bytes per cell
+               from SURVEY.md section 8d / DESIGN.md (B_min = 314 B/cell for this config); the FP64 view
+               (F_min = 4.3 kFLOP/cell against an FMA microbenchmark on the same device) is reported beside it
+  cpu_baseline the oracle's C restatement of the reference loop (oracle/cpu_assemble.c) on the host cores, on a
+               bounded sample of the same workload
+`--impl reference` times that CPU restatement alone (the reference is Julia; no Julia toolchain exists in the
+image or on the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (celltype, nel, order, vdim, qr_order, element, B_min bytes/cell, F_min flop/cell)
+    "c2": dict(cell="hex", nel=(200, 200, 200), order=1, vdim=1, qr=2, element="heat", bmin=314.0, fmin=4.3e3,
+               label="heat Q1 hex 200^3 (BASELINE.json configs[1]), perturbed nodes"),
+    "c2s": dict(cell="hex", nel=(64, 64, 64), order=1, vdim=1, qr=2, element="heat", bmin=314.0, fmin=4.3e3,
+                label="heat Q1 hex 64^3 (reduced size, debugging only)"),
+    "c5": dict(cell="hex", nel=(128, 128, 128), order=1, vdim=3, qr=2, element="elasticity", bmin=2060.0, fmin=15.5e3,
+               label="linear elasticity Q1^3 hex 128^3 (per-GPU block of BASELINE.json configs[4])"),
+    "c3": dict(cell="hex", nel=(48, 48, 48), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
+               label="linear elasticity Q2^3 hex 48^3 (BASELINE.json configs[2] at 1/8 size)"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_problem(cfg, nel):
+    import oracle as O
+    shape = "hexahedron"
+    og = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * 3, (1,) * 3, 0.2)
+    ip = O.Lagrange(shape, cfg["order"])
+    ip = ip ** cfg["vdim"] if cfg["vdim"] > 1 else ip
+    dh = O.DofHandler(og).add("u", ip).close()
+    cv = O.CellValues(O.QuadratureRule(shape, cfg["qr"]), ip)
+    return og, dh, cv
+
+
+def cpu_baseline(cfg, sample_nel, reps=3, threads=0):
+    """Time the C restatement of the reference loop on a bounded sample of the workload (all host cores)."""
+    import numpy as np
+    import oracle as O
+    from oracle import cport
+    og, dh, cv = oracle_problem(cfg, sample_nel)
+    K = O.allocate_matrix(dh)
+    f = np.zeros(dh.ndofs)
+    if cfg["element"] == "heat":
+        params = {"k": 1.0, "source": 1.0}
+    else:
+        lam, mu = O.lame(200e9, 0.3)
+        params = {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}
+    nthreads = threads or (os.cpu_count() or 1)
+    cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)   # warm-up
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": og.ncells / best, "unit": "cells/s", "cores": nthreads, "kind": "port",
+            "sample": f"{'x'.join(map(str, sample_nel))} cells of the same workload (C restatement of the reference loop, "
+                      f"OpenMP atomic scatter, best of {reps}); the reference is Julia and cannot run here"}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU algorithm (oracle C port) on the host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
+    import numpy as np
+    import oracle as O
+    from oracle import cport
+    og, dh, cv = oracle_problem(cfg, sample)
+    K = O.allocate_matrix(dh)
+    f = np.zeros(dh.ndofs)
+    if cfg["element"] == "heat":
+        params = {"k": 1.0, "source": 1.0}
+    else:
+        lam, mu = O.lame(200e9, 0.3)
+        params = {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}
+    nthreads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    value = og.ncells * args.steps / dt
+    sample_txt = f"{'x'.join(map(str, sample))} cells per step of the same workload"
+    line = {
+        "impl": "reference", "metric": "cells assembled/sec (K+f, FP64, 3D hex)", "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["label"], "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": nthreads, "kind": "port", "sample": sample_txt +
+                         "; C restatement of the reference's threaded atomic loop (the reference is Julia, no toolchain here)"},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import numpy as np
+    import torch
+    import ferrite_b200 as fb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    ctx = fb.default_context(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+
+    # ---- set-up (not timed): grid, dofs, pattern, map all resident in HBM ------------------------------
+    t_setup = time.perf_counter()
+    nel = cfg["nel"]
+    g = fb.generate_grid(fb.Hexahedron, nel).perturb(0.2)
+    ip = fb.Lagrange(fb.RefHexahedron, cfg["order"]) ** cfg["vdim"]
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, cfg["qr"]), ip)
+    if cfg["element"] == "heat":
+        elem = fb.HeatElement(1.0, 1.0)
+    else:
+        elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+    a = fb.start_assemble(K, f, scatter=args.scatter)
+    a.variant = args.variant
+    fb.assemble_(a, elem, cv)
+    ctx.synchronize()
+    t_setup = time.perf_counter() - t_setup
+    ncells = g.ncells
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        fb.assemble_(a, elem, cv)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fb.assemble_(a, elem, cv)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ctx.synchronize()
+    # size-independent checks on the full-size result (Laplace: sum(f) = |Omega| * source; K row sums = 0)
+    checks = {}
+    if cfg["element"] == "heat":
+        checks["sum_f_minus_volume"] = abs(float(f.sum()) - 8.0)
+        checks["sum_K"] = abs(float(K.nzval.sum())) / float(K.nzval.abs().max())
+
+    # ---- dominant kernel alone (no zero fill) for the roofline -----------------------------------------------
+    a_nz = fb.start_assemble(K, f, fillzero=False, scatter=args.scatter)
+    a_nz.variant = args.variant
+    a_nz._h = a._h          # reuse the same native assembler (map)
+    kreps = max(3, min(args.steps, 10))
+    fb.assemble_(a_nz, elem, cv)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(kreps):
+        fb.assemble_(a_nz, elem, cv)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / kreps
+    a_nz._h = {}
+
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = ncells * world * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end through host buffers ------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        xyz_host = torch.from_numpy(g.nodes).pin_memory()
+        nz_host = torch.empty(K.nnz, dtype=torch.float64).pin_memory()
+        f_host = torch.empty(dh.ndofs, dtype=torch.float64).pin_memory()
+        nz_np, f_np = nz_host.numpy(), f_host.numpy()
+        a_h = fb.start_assemble(K, None, scatter=args.scatter)
+        a_h.variant = args.variant
+        a_h._h = a._h
+        esteps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            g.upload_coordinates_async(xyz_host)
+            fb.assemble_host(a_h, elem, cv, nz_np, f_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            g.upload_coordinates_async(xyz_host)          # H2D: this step's input
+            fb.assemble_host(a_h, elem, cv, nz_np, f_np)  # assemble + D2H of nzval and f (synchronises)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        a_h._h = {}
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": ncells * world * esteps / dt, "unit": "cells/s", "h2d_bytes_per_step": int(g.nnodes * g.sdim * 8),
+               "d2h_bytes_per_step": int((K.nnz + dh.ndofs) * 8), "steps": esteps,
+               "checksum_ok": bool(abs(float(f_host.sum()) - float(f.sum())) <= 1e-9 * max(1.0, abs(float(f.sum()))))}
+
+    if rank != 0:
+        return
+    hbm_peak, peak_src = load_peaks()
+    fp64_peak = ctx.measure_fp64_peak()
+    cells_per_s_kernel = ncells / (kernel_ms * 1e-3)
+    achieved = cfg["bmin"] * cells_per_s_kernel / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.config)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms, "bytes_per_cell": cfg["bmin"],
+                "fp64": {"achieved_tflops": cfg["fmin"] * cells_per_s_kernel / 1e12, "peak_tflops": fp64_peak,
+                         "frac": cfg["fmin"] * cells_per_s_kernel / 1e12 / fp64_peak if fp64_peak else None,
+                         "flop_per_cell": cfg["fmin"], "peak_source": "FMA microbenchmark in this run"}}
+    line = {
+        "metric": "cells assembled/sec (K+f, FP64, 3D hex)", "value": value, "unit": "cells/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": cfg["label"], "cells": ncells, "ndofs": dh.ndofs, "nnz": K.nnz, "scatter": args.scatter,
+                   "l2": "inputs+outputs (>= 3 GB) exceed the 126 MB L2; no flush needed", "setup_s": round(t_setup, 2),
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (partitioned path: see DESIGN.md)"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "checks": checks,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
+        line["cpu_baseline"] = cpu_baseline(cfg, sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,579 @@
+"""Host-side mirror of the Ferrite.jl API for the assembly path, on top of the C ABI.
+
+Names follow the reference (Julia `f!` is spelled `f_` here): generate_grid, DofHandler / add_ /
+close_, CellValues, QuadratureRule, Lagrange, allocate_matrix, start_assemble / assemble_,
+ConstraintHandler / Dirichlet / update_ / apply_ / apply_zero_.  Everything that computes runs in
+libferrite_b200.so on the GPU; torch is used only to own device memory and the CUDA stream.
+
+Differences from the reference that a user must know:
+  * the element routine is chosen from a menu (HeatElement, MassElement, ElasticityElement,
+    NeoHookeElement) instead of being user code -- `assemble_(assembler, element, cv)` performs the whole
+    `for cell in CellIterator(dh)` loop of the reference in one call;
+  * matrices live on the device (`B200Matrix`): `K.colptr` / `K.rowval` are the reference's 1-based
+    Int64 arrays, `K.nzval` a float64 CUDA tensor; `K.tocsc()` downloads a scipy matrix.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import FB2Error, DetJNotPositive, MissingPatternEntry  # noqa: F401
+
+# reference shapes / cell types --------------------------------------------------------------------
+Line, Triangle, Quadrilateral, Tetrahedron, Hexahedron = L.LINE, L.TRIANGLE, L.QUADRILATERAL, L.TETRAHEDRON, L.HEXAHEDRON
+RefLine, RefTriangle, RefQuadrilateral, RefTetrahedron, RefHexahedron = Line, Triangle, Quadrilateral, Tetrahedron, Hexahedron
+_RDIM = {Line: 1, Triangle: 2, Quadrilateral: 2, Tetrahedron: 3, Hexahedron: 3}
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _chain(obj, attr):
+    """obj.<attr> and all of its ancestors (dh -> grid -> ctx)."""
+    out = []
+    p = getattr(obj, attr, None)
+    while p is not None:
+        out.append(p)
+        p = getattr(p, "dh", None) or getattr(p, "grid", None) or getattr(p, "ctx", None)
+    return out or [None]
+
+
+def _destroy(obj, fn, parents=()):
+    """Destroy a native handle unless one of its parents is already gone (the cyclic GC may finalise
+    objects in any order at interpreter exit; the native child dereferences its parent)."""
+    try:
+        h = getattr(obj, "h", None)
+        if not h:
+            return
+        for p in parents:
+            if p is None or not getattr(p, "h", None):
+                obj.h = None
+                return
+        getattr(L.lib, fn)(h)
+        obj.h = None
+    except Exception:
+        pass
+
+
+class Context:
+    """One CUDA device + stream.  `Context(-1)` is host-only (grid / dof / constraint set-up logic)."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        self.h = C.c_void_p()
+        L.call("fb2_ctx_create", int(device), C.byref(self.h))
+        self.device = int(device)
+        if device >= 0 and use_torch_stream:
+            torch = _torch()
+            torch.cuda.set_device(device)
+            stream = torch.cuda.current_stream(device)
+            L.call("fb2_ctx_set_stream", self.h, C.c_void_p(stream.cuda_stream))
+            self._stream = stream
+
+    def synchronize(self):
+        L.call("fb2_ctx_synchronize", self.h)
+
+    @property
+    def launch_count(self):
+        n = C.c_int64()
+        L.call("fb2_ctx_launch_count", self.h, C.byref(n))
+        return n.value
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        L.call("fb2_measure_fp64_peak", self.h, C.byref(t))
+        return t.value
+
+    def zeros(self, n):
+        torch = _torch()
+        return torch.zeros(int(n), dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def __del__(self):
+        _destroy(self, "fb2_ctx_destroy", ())
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---- interpolation / quadrature descriptors ---------------------------------------------------------
+class Lagrange:
+    """Lagrange{refshape, order}(); `ip ** vdim` is the reference's `ip^vdim`."""
+
+    def __init__(self, refshape, order, vdim=1):
+        self.refshape, self.order, self.vdim = refshape, int(order), int(vdim)
+
+    def __pow__(self, vdim):
+        return Lagrange(self.refshape, self.order, int(vdim))
+
+
+class QuadratureRule:
+    """QuadratureRule{refshape}(order) with the reference's default rule for the shape."""
+
+    def __init__(self, refshape, order):
+        self.refshape, self.order = refshape, int(order)
+
+
+# ---- grid ---------------------------------------------------------------------------------------------
+class Grid:
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, handle
+        ct, nc, nn, nnpc, sdim = C.c_int(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+        L.call("fb2_grid_info", self.h, C.byref(ct), C.byref(nc), C.byref(nn), C.byref(nnpc), C.byref(sdim))
+        self.celltype, self.ncells, self.nnodes, self.nnpc, self.sdim = ct.value, nc.value, nn.value, nnpc.value, sdim.value
+
+    @classmethod
+    def from_arrays(cls, celltype, cells, nodes, ctx=None):
+        """Grid(cells, nodes): cells (ncells, nnpc) 1-based node ids, nodes (nnodes, sdim)."""
+        ctx = ctx or default_context()
+        cells, nodes = _i64(cells), _f64(nodes)
+        h = C.c_void_p()
+        L.call("fb2_grid_from_host", ctx.h, celltype, cells.shape[0], nodes.shape[0], nodes.shape[1],
+               _ptr(cells, C.c_int64), _ptr(nodes, C.c_double), C.byref(h))
+        return cls(ctx, h)
+
+    @property
+    def cells(self):
+        out = np.empty((self.ncells, self.nnpc), dtype=np.int64)
+        L.call("fb2_grid_export", self.h, _ptr(out, C.c_int64), None)
+        return out
+
+    @property
+    def nodes(self):
+        out = np.empty((self.nnodes, self.sdim), dtype=np.float64)
+        L.call("fb2_grid_export", self.h, None, _ptr(out, C.c_double))
+        return out
+
+    def set_coordinates(self, nodes):
+        nodes = _f64(nodes)
+        assert nodes.shape == (self.nnodes, self.sdim)
+        L.call("fb2_grid_set_coordinates", self.h, _ptr(nodes, C.c_double))
+
+    def upload_coordinates_async(self, host_tensor):
+        """Stream-ordered device-only coordinate update from a (pinned) torch/numpy host buffer (nnodes, sdim)."""
+        ptr = host_tensor.data_ptr() if hasattr(host_tensor, "data_ptr") else host_tensor.ctypes.data
+        L.call("fb2_grid_upload_coordinates_async", self.h, C.c_void_p(ptr))
+
+    def perturb(self, amplitude=0.2):
+        L.call("fb2_grid_perturb", self.h, float(amplitude))
+        return self
+
+    def __del__(self):
+        _destroy(self, "fb2_grid_destroy", (getattr(self, "ctx", None),))
+
+
+def generate_grid(celltype, nel, left=None, right=None, ctx=None):
+    ctx = ctx or default_context()
+    nel = _i64(nel)
+    lp = _ptr(_f64(left), C.c_double) if left is not None else None
+    rp = _ptr(_f64(right), C.c_double) if right is not None else None
+    h = C.c_void_p()
+    L.call("fb2_grid_generate", ctx.h, celltype, _ptr(nel, C.c_int64), lp, rp, C.byref(h))
+    return Grid(ctx, h)
+
+
+def getfacetset(grid, name):
+    n = C.c_int64()
+    L.call("fb2_grid_facetset", grid.h, name.encode(), C.byref(n), None)
+    out = np.empty((n.value, 2), dtype=np.int64)
+    L.call("fb2_grid_facetset", grid.h, name.encode(), C.byref(n), _ptr(out, C.c_int64))
+    return out
+
+
+# ---- DofHandler -----------------------------------------------------------------------------------------
+class DofHandler:
+    def __init__(self, grid):
+        self.grid = grid
+        self.field_names, self.field_ips = [], []
+        self.h = None
+
+    def _fields(self):
+        arr = (L.Field * len(self.field_ips))()
+        for k, ip in enumerate(self.field_ips):
+            arr[k].order, arr[k].vdim = ip.order, ip.vdim
+        return arr
+
+    def _info(self):
+        nd, ndpc, nf = C.c_int64(), C.c_int(), C.c_int()
+        L.call("fb2_dh_info", self.h, C.byref(nd), C.byref(ndpc), C.byref(nf))
+        self.ndofs, self.ndofs_per_cell = nd.value, ndpc.value
+
+    @classmethod
+    def from_arrays(cls, grid, fields, ndofs, cell_dofs):
+        """Adopt the reference's own numbering: cell_dofs (ncells, ndofs_per_cell) 1-based."""
+        dh = cls(grid)
+        for name, ip in fields:
+            add_(dh, name, ip)
+        cd = _i64(cell_dofs)
+        dh.h = C.c_void_p()
+        L.call("fb2_dh_from_host", grid.h, len(dh.field_ips), dh._fields(), int(ndofs), cd.shape[1],
+               _ptr(cd, C.c_int64), C.byref(dh.h))
+        dh._info()
+        return dh
+
+    @property
+    def cell_dofs(self):
+        out = np.empty((self.grid.ncells, self.ndofs_per_cell), dtype=np.int64)
+        L.call("fb2_dh_export", self.h, _ptr(out, C.c_int64))
+        return out
+
+    def __del__(self):
+        _destroy(self, "fb2_dh_destroy", _chain(self, "grid"))
+
+
+def add_(obj, *args):
+    """add!(dh, name, ip)  or  add!(ch, dbc)"""
+    if isinstance(obj, DofHandler):
+        name, ip = args
+        assert obj.h is None, "DofHandler already closed"
+        assert ip.refshape == obj.grid.celltype
+        obj.field_names.append(name)
+        obj.field_ips.append(ip)
+        return obj
+    if isinstance(obj, ConstraintHandler):
+        return obj._add(args[0])
+    raise TypeError(type(obj))
+
+
+def close_(obj):
+    """close!(dh) / close!(ch)"""
+    if isinstance(obj, DofHandler):
+        obj.h = C.c_void_p()
+        L.call("fb2_dh_close", obj.grid.h, len(obj.field_ips), obj._fields(), C.byref(obj.h))
+        obj._info()
+        return obj
+    if isinstance(obj, ConstraintHandler):
+        return obj._close()
+    raise TypeError(type(obj))
+
+
+def ndofs(dh):
+    return dh.ndofs
+
+
+def ndofs_per_cell(dh):
+    return dh.ndofs_per_cell
+
+
+def celldofs(dh, i):
+    """celldofs(dh, i), i 1-based"""
+    return dh.cell_dofs[i - 1]
+
+
+def dof_range(dh, name):
+    a, b = C.c_int(), C.c_int()
+    L.call("fb2_dh_dof_range", dh.h, dh.field_names.index(name), C.byref(a), C.byref(b))
+    return range(a.value, b.value + 1)
+
+
+# ---- matrix -----------------------------------------------------------------------------------------------
+class B200Matrix:
+    """Device-resident SparseMatrixCSC{Float64,Int}: pattern handle + nzval CUDA tensor."""
+
+    def __init__(self, dh, handle):
+        self.dh, self.h = dh, handle
+        n, nnz = C.c_int64(), C.c_int64()
+        L.call("fb2_pattern_info", self.h, C.byref(n), C.byref(nnz))
+        self.n, self.nnz = n.value, nnz.value
+        self.nzval = dh.grid.ctx.zeros(self.nnz)
+        self._colptr = self._rowval = None
+
+    def _export(self):
+        if self._colptr is None:
+            self._colptr = np.empty(self.n + 1, dtype=np.int64)
+            self._rowval = np.empty(self.nnz, dtype=np.int64)
+            L.call("fb2_pattern_export", self.h, _ptr(self._colptr, C.c_int64), _ptr(self._rowval, C.c_int64))
+
+    @property
+    def colptr(self):
+        self._export()
+        return self._colptr
+
+    @property
+    def rowval(self):
+        self._export()
+        return self._rowval
+
+    def tocsc(self):
+        import scipy.sparse as sp
+        self.dh.grid.ctx.synchronize()
+        return sp.csc_matrix((self.nzval.cpu().numpy(), self.rowval - 1, self.colptr - 1), shape=(self.n, self.n))
+
+    def __del__(self):
+        _destroy(self, "fb2_pattern_destroy", _chain(self, "dh"))
+
+
+def allocate_matrix(dh, colptr=None, rowval=None):
+    """allocate_matrix(dh) (pattern built on the device); with colptr/rowval: adopt the reference's pattern."""
+    h = C.c_void_p()
+    if colptr is None:
+        L.call("fb2_pattern_create", dh.h, C.byref(h))
+    else:
+        cp, rv = _i64(colptr), _i64(rowval)
+        L.call("fb2_pattern_from_host", dh.h, _ptr(cp, C.c_int64), _ptr(rv, C.c_int64), C.byref(h))
+    return B200Matrix(dh, h)
+
+
+# ---- CellValues ----------------------------------------------------------------------------------------------
+class CellValues:
+    """CellValues(qr, ip[, ip_geo])"""
+
+    def __init__(self, qr, ip, ip_geo=None, ctx=None, tables=None):
+        self.ctx = ctx or default_context()
+        self.qr, self.ip = qr, ip
+        self.h = C.c_void_p()
+        if tables is None:
+            geo_order = ip_geo.order if ip_geo is not None else 1
+            L.call("fb2_cellvalues_create", self.ctx.h, ip.refshape, qr.order, ip.order, ip.vdim, geo_order, C.byref(self.h))
+        else:  # arrays-in: N (nq,n), dNdxi (nq,n,rdim), M (nq,ngeo), dMdxi (nq,ngeo,rdim), w (nq)
+            N, dN, M, dM, w = (_f64(t) for t in tables)
+            L.call("fb2_cellvalues_from_tables", self.ctx.h, ip.refshape, N.shape[0], N.shape[1], ip.vdim, M.shape[1],
+                   _ptr(N, C.c_double), _ptr(dN, C.c_double), _ptr(M, C.c_double), _ptr(dM, C.c_double),
+                   _ptr(w, C.c_double), C.byref(self.h))
+        nq, nb, vd, ng, rd = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.call("fb2_cellvalues_info", self.h, C.byref(nq), C.byref(nb), C.byref(vd), C.byref(ng), C.byref(rd))
+        self.nq, self.nbase_scalar, self.vdim, self.ngeo, self.rdim = nq.value, nb.value, vd.value, ng.value, rd.value
+
+    def tables(self):
+        N = np.empty((self.nq, self.nbase_scalar))
+        dN = np.empty((self.nq, self.nbase_scalar, self.rdim))
+        M = np.empty((self.nq, self.ngeo))
+        dM = np.empty((self.nq, self.ngeo, self.rdim))
+        w = np.empty(self.nq)
+        pts = np.empty((self.nq, self.rdim))
+        L.call("fb2_cellvalues_export", self.h, _ptr(N, C.c_double), _ptr(dN, C.c_double), _ptr(M, C.c_double),
+               _ptr(dM, C.c_double), _ptr(w, C.c_double), _ptr(pts, C.c_double))
+        return dict(N=N, dNdxi=dN, M=M, dMdxi=dM, w=w, points=pts)
+
+    def __del__(self):
+        _destroy(self, "fb2_cellvalues_destroy", (getattr(self, "ctx", None),))
+
+
+# ---- element menu -----------------------------------------------------------------------------------------------
+class HeatElement:
+    """Ke = int k grad(Ni).grad(Nj), fe = int source Ni  (heat_equation.jl:143-164)"""
+    elem_id = L.ELEM_HEAT
+
+    def __init__(self, k=1.0, source=1.0):
+        self.params = L.HeatParams(float(k), float(source))
+
+
+class MassElement:
+    elem_id = L.ELEM_MASS
+
+    def __init__(self, rho=1.0):
+        self.params = L.MassParams(float(rho))
+
+
+class ElasticityElement:
+    """Ke = int eps_i : C : eps_j with isotropic C(lambda, mu), fe = int Ni . b  (threaded_assembly.jl:105-119)"""
+    elem_id = L.ELEM_ELASTICITY
+
+    def __init__(self, lam=None, mu=None, b=(0.0, 0.0, 0.0), E=None, nu=None):
+        if lam is None:
+            lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+            mu = E / (2 * (1 + nu))
+        b = tuple(b) + (0.0,) * (3 - len(b))
+        self.params = L.ElasticityParams(float(lam), float(mu), (C.c_double * 3)(*b))
+
+
+class NeoHookeElement(ElasticityElement):
+    """tangent + residual of the compressible Neo-Hooke model (hyperelasticity.jl:162-176,241-276)"""
+    elem_id = L.ELEM_NEOHOOKE
+
+
+# ---- assembler ------------------------------------------------------------------------------------------------------
+class Assembler:
+    def __init__(self, K, f, fillzero=True, scatter="atomic"):
+        self.K, self.f = K, f
+        self.fillzero = fillzero
+        self.scatter = scatter
+        self.variant = 0
+        self._h = {}
+
+    def _handle(self, cv):
+        key = id(cv)
+        if key not in self._h:
+            h = C.c_void_p()
+            L.call("fb2_assembler_create", self.K.dh.h, self.K.h, cv.h if cv is not None else None, C.byref(h))
+            self._h[key] = (h, cv)
+        return self._h[key][0]
+
+    def _opts(self):
+        return L.AsmOpts(1 if self.fillzero else 0, L.SCATTER_COLORED if self.scatter == "colored" else L.SCATTER_ATOMIC,
+                         self.variant, 0)
+
+    def coloring(self, cv=None):
+        h = self._handle(cv)
+        nc = C.c_int()
+        col = np.empty(self.K.dh.grid.ncells, dtype=np.int32)
+        L.call("fb2_assembler_coloring", h, C.byref(nc), _ptr(col, C.c_int32))
+        return nc.value, col
+
+    def __del__(self):
+        try:
+            alive = all(getattr(p, "h", None) for p in [self.K] + _chain(self.K, "dh"))
+            for h, _ in self._h.values():
+                if alive:
+                    L.lib.fb2_assembler_destroy(h)
+            self._h = {}
+        except Exception:
+            pass
+
+
+def start_assemble(K, f=None, fillzero=True, scatter="atomic"):
+    """start_assemble(K, f; fillzero) -- the zero fill happens inside the next assemble_ call."""
+    return Assembler(K, f, fillzero, scatter)
+
+
+def assemble_(assembler, element, cv, u=None):
+    """The whole `for cell in CellIterator(dh): reinit!, element routine, assemble!` loop on the GPU."""
+    h = assembler._handle(cv)
+    opts = assembler._opts()
+    f = assembler.f
+    L.call("fb2_assemble", h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
+           C.c_void_p(u.data_ptr()) if u is not None else None,
+           C.c_void_p(assembler.K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
+    return assembler
+
+
+def assemble_host(assembler, element, cv, nzval, f=None, u=None):
+    """Same loop through host buffers (numpy float64): nzval/f are filled like SparseMatrixCSC.nzval / f."""
+    h = assembler._handle(cv)
+    opts = assembler._opts()
+    L.call("fb2_assemble_host", h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
+           _ptr(u, C.c_double) if u is not None else None, _ptr(nzval, C.c_double),
+           _ptr(f, C.c_double) if f is not None else None, C.byref(opts))
+
+
+def scatter_(assembler, Ke, fe=None):
+    """assemble!(assembler, dofs, Ke, fe) for all cells at once from precomputed element matrices:
+    Ke (ncells, n, n) with Ke[c, i, j], fe (ncells, n)."""
+    h = assembler._handle(None)
+    opts = assembler._opts()
+    Kc = _f64(np.transpose(np.asarray(Ke), (0, 2, 1)))   # -> per cell column-major
+    fp = _ptr(_f64(fe), C.c_double) if fe is not None else None
+    f = assembler.f
+    L.call("fb2_scatter_host", h, _ptr(Kc, C.c_double), fp, C.c_void_p(assembler.K.nzval.data_ptr()),
+           C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
+
+
+def finish_assemble(assembler):
+    assembler.K.dh.grid.ctx.synchronize()
+    return assembler.K, assembler.f
+
+
+# ---- constraints ---------------------------------------------------------------------------------------------------------
+class Dirichlet:
+    """Dirichlet(field, set, f, components): set = getfacetset(...) pairs (kind 'facet'/'face'/'edge'/'vertex')
+    or node ids (kind 'node'); f(x, t) -> value(s)."""
+
+    def __init__(self, field, entities, f, components=None, kind="facet"):
+        self.field, self.f, self.kind = field, f, kind
+        self.entities = _i64(entities)
+        self.components = None if components is None else [int(c) for c in np.atleast_1d(components)]
+
+
+_KIND = {"facet": L.BC_FACET, "face": L.BC_FACE, "edge": L.BC_EDGE, "vertex": L.BC_VERTEX, "node": L.BC_NODE}
+
+
+class ConstraintHandler:
+    def __init__(self, dh):
+        self.dh = dh
+        self.h = C.c_void_p()
+        L.call("fb2_ch_create", dh.h, C.byref(self.h))
+        self.dbcs = []
+        self.closed = False
+
+    @classmethod
+    def from_arrays(cls, dh, prescribed_dofs, inhomogeneities):
+        ch = cls.__new__(cls)
+        ch.dh, ch.dbcs, ch.closed = dh, [], True
+        ch.h = C.c_void_p()
+        p, v = _i64(prescribed_dofs), _f64(inhomogeneities)
+        L.call("fb2_ch_from_host", dh.h, len(p), _ptr(p, C.c_int64), _ptr(v, C.c_double), C.byref(ch.h))
+        return ch
+
+    def _add(self, dbc):
+        comps = dbc.components or []
+        carr = (C.c_int * max(len(comps), 1))(*comps)
+        ibc = C.c_int()
+        n = dbc.entities.shape[0]
+        L.call("fb2_ch_add_dirichlet", self.h, self.dh.field_names.index(dbc.field), _KIND[dbc.kind], n,
+               _ptr(dbc.entities, C.c_int64), len(comps), carr, C.byref(ibc))
+        ncomp = len(comps) if comps else self.dh.field_ips[self.dh.field_names.index(dbc.field)].vdim
+        self.dbcs.append((ibc.value, dbc, ncomp))
+        return self
+
+    def _close(self):
+        L.call("fb2_ch_close", self.h)
+        self.closed = True
+        update_(self, 0.0)
+        return self
+
+    @property
+    def prescribed_dofs(self):
+        n = C.c_int64()
+        L.call("fb2_ch_info", self.h, C.byref(n))
+        out = np.empty(n.value, dtype=np.int64)
+        L.call("fb2_ch_export", self.h, _ptr(out, C.c_int64), None)
+        return out
+
+    @property
+    def inhomogeneities(self):
+        n = C.c_int64()
+        L.call("fb2_ch_info", self.h, C.byref(n))
+        out = np.empty(n.value, dtype=np.float64)
+        L.call("fb2_ch_export", self.h, None, _ptr(out, C.c_double))
+        return out
+
+    def __del__(self):
+        _destroy(self, "fb2_ch_destroy", _chain(self, "dh"))
+
+
+def update_(ch, t=0.0):
+    """update!(ch, t): evaluate every Dirichlet function at its dof locations (in the reference's order)."""
+    sdim = ch.dh.grid.sdim
+    for ibc, dbc, ncomp in ch.dbcs:
+        n = C.c_int64()
+        L.call("fb2_ch_bc_points", ch.h, ibc, C.byref(n), None)
+        x = np.empty((n.value, sdim))
+        L.call("fb2_ch_bc_points", ch.h, ibc, C.byref(n), _ptr(x, C.c_double))
+        vals = np.empty((n.value, ncomp))
+        for k in range(n.value):
+            vals[k] = np.atleast_1d(dbc.f(x[k], t))
+        L.call("fb2_ch_bc_set_values", ch.h, ibc, n.value, _ptr(vals, C.c_double))
+
+
+def apply_(K, f=None, ch=None, applyzero=False):
+    """apply!(K, f, ch) / apply!(u, ch) (first argument a CUDA tensor)."""
+    if not isinstance(K, B200Matrix):   # apply!(u, ch)
+        u, ch = K, f if ch is None else ch
+        L.call("fb2_apply_vector", ch.h, C.c_void_p(u.data_ptr()), 1 if applyzero else 0)
+        return None
+    m = C.c_double()
+    L.call("fb2_apply", ch.h, K.h, C.c_void_p(K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None,
+           1 if applyzero else 0, C.byref(m))
+    return m.value
+
+
+def apply_zero_(K, f=None, ch=None):
+    return apply_(K, f, ch, applyzero=True)

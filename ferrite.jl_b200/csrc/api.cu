@@ -1,0 +1,302 @@
+// Context, CellValues and assembler entry points of the C ABI (see include/ferrite_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.h"
+
+static thread_local char g_err[1024] = "";
+
+void fb2_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fb2_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char* fb2_version(void) { return "ferrite_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* fb2_last_error(void) { return g_err; }
+
+// ---- context -------------------------------------------------------------------------------------
+extern "C" int fb2_ctx_create(int device, fb2_ctx** out) {
+    FB2_CHECK(out, FB2_ERR_BAD_ARG, "fb2_ctx_create: null output pointer");
+    if (device == -1) {  // host-only context: grid / dof / constraint set-up logic without a device
+        fb2_ctx* ctx = new fb2_ctx();
+        ctx->device = -1;
+        ctx->own_stream = false;
+        *out = ctx;
+        return FB2_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fb2_fail(FB2_ERR_CUDA, "no usable CUDA device (%s); libferrite_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    FB2_CHECK(device >= 0 && device < ndev, FB2_ERR_BAD_ARG, "fb2_ctx_create: device %d out of range (0..%d)", device, ndev - 1);
+    FB2_CUDA(cudaSetDevice(device));
+    fb2_ctx* ctx = new fb2_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    FB2_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    FB2_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    FB2_CUDA(cudaMalloc(&ctx->d_errflag, 2 * sizeof(int)));
+    FB2_CUDA(cudaMemset(ctx->d_errflag, 0, 2 * sizeof(int)));
+    FB2_CUDA(cudaMallocHost(&ctx->h_errflag, 2 * sizeof(int)));
+    *out = ctx;
+    return FB2_OK;
+}
+
+extern "C" int fb2_comm_destroy(fb2_ctx* ctx);
+
+extern "C" int fb2_ctx_destroy(fb2_ctx* ctx) {
+    if (!ctx) return FB2_OK;
+    if (ctx->device < 0) { delete ctx; return FB2_OK; }
+    cudaSetDevice(ctx->device);
+    fb2_comm_destroy(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->d_errflag);
+    cudaFreeHost(ctx->h_errflag);
+    delete ctx;
+    return FB2_OK;
+}
+
+extern "C" int fb2_ctx_synchronize(fb2_ctx* ctx) {
+    FB2_CHECK(ctx, FB2_ERR_BAD_ARG, "fb2_ctx_synchronize: null context");
+    if (ctx->device < 0) return FB2_OK;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    return fb2_check_device_error(ctx);  // synchronises the stream and surfaces kernel-side errors
+}
+
+extern "C" int fb2_ctx_set_stream(fb2_ctx* ctx, void* cuda_stream) {
+    FB2_CHECK(ctx, FB2_ERR_BAD_ARG, "fb2_ctx_set_stream: null context");
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return FB2_OK;
+}
+
+extern "C" int fb2_ctx_launch_count(fb2_ctx* ctx, int64_t* out) {
+    FB2_CHECK(ctx && out, FB2_ERR_BAD_ARG, "fb2_ctx_launch_count: null argument");
+    *out = ctx->launches;
+    return FB2_OK;
+}
+
+extern "C" int fb2_device_alloc(fb2_ctx* ctx, size_t nbytes, void** dev_ptr) {
+    FB2_CHECK(ctx && dev_ptr, FB2_ERR_BAD_ARG, "fb2_device_alloc: null argument");
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaMalloc(dev_ptr, nbytes ? nbytes : 8));
+    return FB2_OK;
+}
+
+extern "C" int fb2_device_free(fb2_ctx* ctx, void* dev_ptr) {
+    FB2_CHECK(ctx, FB2_ERR_BAD_ARG, "fb2_device_free: null context");
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    FB2_CUDA(cudaFree(dev_ptr));
+    return FB2_OK;
+}
+
+extern "C" int fb2_memcpy_h2d(fb2_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes) {
+    FB2_CHECK(ctx && dst_dev && src_host, FB2_ERR_BAD_ARG, "fb2_memcpy_h2d: null argument");
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FB2_OK;
+}
+
+extern "C" int fb2_memcpy_d2h(fb2_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes) {
+    FB2_CHECK(ctx && dst_host && src_dev, FB2_ERR_BAD_ARG, "fb2_memcpy_d2h: null argument");
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return fb2_check_device_error(ctx);
+}
+
+// ---- CellValues -------------------------------------------------------------------------------------
+static int celltype_rdim(int ct) {
+    const RefShapeInfo* rs = fb2_refshape(ct);
+    return rs ? rs->rdim : 0;
+}
+
+extern "C" int fb2_cellvalues_create(fb2_ctx* ctx, int celltype, int qr_order, int ip_order, int vdim, int geo_order, fb2_cv** out) {
+    FB2_CHECK(ctx && out, FB2_ERR_BAD_ARG, "fb2_cellvalues_create: null argument");
+    LagrangeInfo ip, geo;
+    FB2_CHECK(fb2_lagrange(celltype, ip_order, &ip), FB2_ERR_UNSUPPORTED, "CellValues: Lagrange order %d on cell type %d not supported", ip_order, celltype);
+    FB2_CHECK(fb2_lagrange(celltype, geo_order, &geo), FB2_ERR_UNSUPPORTED, "CellValues: geometric order %d not supported", geo_order);
+    FB2_CHECK(vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "CellValues: vdim must be 1..3");
+    fb2_cv* cv = new fb2_cv();
+    cv->ctx = ctx;
+    cv->celltype = celltype;
+    cv->rdim = ip.rdim;
+    cv->nb = ip.nbase;
+    cv->vdim = vdim;
+    cv->ngeo = geo.nbase;
+    cv->ip_order = ip_order;
+    cv->geo_order = geo_order;
+    cv->qr_order = qr_order;
+    if (!fb2_quadrature(celltype, qr_order, &cv->w, &cv->pts)) {
+        delete cv;
+        return fb2_fail(FB2_ERR_UNSUPPORTED, "QuadratureRule of order %d on cell type %d not supported", qr_order, celltype);
+    }
+    cv->nq = (int)cv->w.size();
+    const int rd = cv->rdim;
+    cv->N.resize((size_t)cv->nq * cv->nb);
+    cv->dN.resize((size_t)cv->nq * cv->nb * rd);
+    cv->M.resize((size_t)cv->nq * cv->ngeo);
+    cv->dM.resize((size_t)cv->nq * cv->ngeo * rd);
+    for (int q = 0; q < cv->nq; ++q) {
+        fb2_lagrange_eval(ip, &cv->pts[(size_t)q * rd], &cv->N[(size_t)q * cv->nb], &cv->dN[(size_t)q * cv->nb * rd]);
+        fb2_lagrange_eval(geo, &cv->pts[(size_t)q * rd], &cv->M[(size_t)q * cv->ngeo], &cv->dM[(size_t)q * cv->ngeo * rd]);
+    }
+    *out = cv;
+    return FB2_OK;
+}
+
+extern "C" int fb2_cellvalues_from_tables(fb2_ctx* ctx, int celltype, int nq, int n, int vdim, int ngeo, const double* N,
+                                          const double* dNdxi, const double* M, const double* dMdxi, const double* w, fb2_cv** out) {
+    FB2_CHECK(ctx && N && dNdxi && M && dMdxi && w && out, FB2_ERR_BAD_ARG, "fb2_cellvalues_from_tables: null argument");
+    const int rd = celltype_rdim(celltype);
+    FB2_CHECK(rd > 0, FB2_ERR_BAD_ARG, "fb2_cellvalues_from_tables: unknown cell type %d", celltype);
+    FB2_CHECK(nq >= 1 && n >= 1 && ngeo >= 1 && vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "fb2_cellvalues_from_tables: bad sizes");
+    fb2_cv* cv = new fb2_cv();
+    cv->ctx = ctx;
+    cv->celltype = celltype;
+    cv->rdim = rd;
+    cv->nq = nq;
+    cv->nb = n;
+    cv->vdim = vdim;
+    cv->ngeo = ngeo;
+    cv->w.assign(w, w + nq);
+    cv->pts.assign((size_t)nq * rd, 0.0);
+    cv->N.resize((size_t)nq * n);
+    cv->dN.resize((size_t)nq * n * rd);
+    cv->M.resize((size_t)nq * ngeo);
+    cv->dM.resize((size_t)nq * ngeo * rd);
+    // inputs are column-major Julia arrays: N[i, q], dNdxi[d, i, q] -> exactly the q-major layout used here
+    memcpy(cv->N.data(), N, cv->N.size() * sizeof(double));
+    memcpy(cv->dN.data(), dNdxi, cv->dN.size() * sizeof(double));
+    memcpy(cv->M.data(), M, cv->M.size() * sizeof(double));
+    memcpy(cv->dM.data(), dMdxi, cv->dM.size() * sizeof(double));
+    *out = cv;
+    return FB2_OK;
+}
+
+extern "C" int fb2_cellvalues_info(fb2_cv* cv, int* nq, int* nbase_scalar, int* vdim, int* ngeo, int* rdim) {
+    FB2_CHECK(cv, FB2_ERR_BAD_ARG, "fb2_cellvalues_info: null handle");
+    if (nq) *nq = cv->nq;
+    if (nbase_scalar) *nbase_scalar = cv->nb;
+    if (vdim) *vdim = cv->vdim;
+    if (ngeo) *ngeo = cv->ngeo;
+    if (rdim) *rdim = cv->rdim;
+    return FB2_OK;
+}
+
+extern "C" int fb2_cellvalues_export(fb2_cv* cv, double* N, double* dNdxi, double* M, double* dMdxi, double* w, double* points) {
+    FB2_CHECK(cv, FB2_ERR_BAD_ARG, "fb2_cellvalues_export: null handle");
+    if (N) memcpy(N, cv->N.data(), cv->N.size() * sizeof(double));
+    if (dNdxi) memcpy(dNdxi, cv->dN.data(), cv->dN.size() * sizeof(double));
+    if (M) memcpy(M, cv->M.data(), cv->M.size() * sizeof(double));
+    if (dMdxi) memcpy(dMdxi, cv->dM.data(), cv->dM.size() * sizeof(double));
+    if (w) memcpy(w, cv->w.data(), cv->w.size() * sizeof(double));
+    if (points) memcpy(points, cv->pts.data(), cv->pts.size() * sizeof(double));
+    return FB2_OK;
+}
+
+extern "C" int fb2_cellvalues_destroy(fb2_cv* cv) {
+    if (!cv) return FB2_OK;
+    if (cv->ctx && cv->ctx->const_tables_owner == cv) cv->ctx->const_tables_owner = nullptr;
+    delete cv;
+    return FB2_OK;
+}
+
+// ---- assembler -----------------------------------------------------------------------------------------
+extern "C" int fb2_assembler_create(fb2_dh* dh, fb2_pattern* p, fb2_cv* cv, fb2_assembler** out) {
+    FB2_CHECK(dh && p && out, FB2_ERR_BAD_ARG, "fb2_assembler_create: null argument");
+    FB2_CHECK(p->dh == dh || p->n == dh->ndofs, FB2_ERR_BAD_ARG, "fb2_assembler_create: pattern does not belong to this DofHandler");
+    FB2_NEED_DEVICE(dh->grid->ctx);
+    if (cv) {
+        FB2_CHECK(cv->celltype == dh->grid->celltype, FB2_ERR_BAD_ARG, "fb2_assembler_create: CellValues are for another cell type");
+        FB2_CHECK(cv->nb * cv->vdim == dh->ndpc, FB2_ERR_UNSUPPORTED,
+                  "fb2_assembler_create: the element must cover all %d dofs of a cell (CellValues has %d)", dh->ndpc, cv->nb * cv->vdim);
+        FB2_CHECK(cv->ngeo == dh->grid->nnpc, FB2_ERR_BAD_ARG, "fb2_assembler_create: geometric interpolation has %d nodes, cells have %d", cv->ngeo, dh->grid->nnpc);
+        FB2_CHECK(cv->rdim == dh->grid->sdim, FB2_ERR_UNSUPPORTED, "embedded elements (rdim %d in sdim %d) are not supported", cv->rdim, dh->grid->sdim);
+    }
+    fb2_assembler* a = new fb2_assembler();
+    a->dh = dh;
+    a->pat = p;
+    a->cv = cv;
+    a->n = dh->ndpc;
+    int rc = fb2_map_build(a);
+    if (rc != FB2_OK) { fb2_assembler_destroy(a); return rc; }
+    *out = a;
+    return FB2_OK;
+}
+
+extern "C" int fb2_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
+                            double* nzval_dev, double* f_dev, const fb2_asm_opts* opts) {
+    FB2_CHECK(a && nzval_dev, FB2_ERR_BAD_ARG, "fb2_assemble: null argument");
+    FB2_CHECK(a->cv, FB2_ERR_BAD_ARG, "fb2_assemble: this assembler was created without CellValues (scatter-only)");
+    return fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, opts);
+}
+
+extern "C" int fb2_assemble_host(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_host,
+                                 double* nzval_host, double* f_host, const fb2_asm_opts* opts) {
+    FB2_CHECK(a && nzval_host, FB2_ERR_BAD_ARG, "fb2_assemble_host: null argument");
+    FB2_CHECK(a->cv, FB2_ERR_BAD_ARG, "fb2_assemble_host: this assembler was created without CellValues (scatter-only)");
+    fb2_ctx* ctx = a->dh->grid->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const size_t nnz = (size_t)a->pat->nnz, n = (size_t)a->dh->ndofs;
+    if (!a->d_nzval) FB2_CUDA(cudaMalloc(&a->d_nzval, nnz * sizeof(double)));
+    if (!a->d_f) FB2_CUDA(cudaMalloc(&a->d_f, n * sizeof(double)));
+    if (u_host) {
+        if (!a->d_u) FB2_CUDA(cudaMalloc(&a->d_u, n * sizeof(double)));
+        FB2_CUDA(cudaMemcpyAsync(a->d_u, u_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+    if (opts) o = *opts;
+    if (!o.fillzero) {  // accumulate onto the caller's current values
+        FB2_CUDA(cudaMemcpyAsync(a->d_nzval, nzval_host, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (f_host) FB2_CUDA(cudaMemcpyAsync(a->d_f, f_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    FB2_TRY(fb2_launch_assemble(a, element, params, params_bytes, u_host ? a->d_u : nullptr, a->d_nzval, f_host ? a->d_f : nullptr, &o));
+    FB2_CUDA(cudaMemcpyAsync(nzval_host, a->d_nzval, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (f_host) FB2_CUDA(cudaMemcpyAsync(f_host, a->d_f, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return fb2_check_device_error(ctx);
+}
+
+extern "C" int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color) {
+    FB2_CHECK(a, FB2_ERR_BAD_ARG, "fb2_assembler_coloring: null handle");
+    FB2_TRY(fb2_coloring_build(a));
+    if (ncolors) *ncolors = a->ncolors;
+    if (cell_color) memcpy(cell_color, a->cell_color.data(), a->cell_color.size() * sizeof(int32_t));
+    return FB2_OK;
+}
+
+extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
+    if (!a) return FB2_OK;
+    cudaSetDevice(a->dh->grid->ctx->device);
+    cudaFree(a->d_map);
+    cudaFree(a->d_color_cells);
+    cudaFree(a->d_cells);
+    cudaFree(a->d_nzval);
+    cudaFree(a->d_f);
+    cudaFree(a->d_u);
+    delete a;
+    return FB2_OK;
+}

@@ -1,0 +1,326 @@
+// Host side of the assembly path: table upload, kernel selection, launches, colouring, scatter-only.
+//
+// fb2_assemble = start_assemble (zero fill, src/assembler.jl:287-291 + src/arrayutils.jl:118-152) followed by
+// one fused kernel per launch (or one per colour) that covers the reference's whole cell loop; see
+// assemble_kernels.cuh for the kernels and DESIGN.md for the per-kernel byte / flop accounting.
+#include <algorithm>
+#include <cstring>
+
+#include "assemble_kernels.cuh"
+
+namespace {
+
+int upload_tables(fb2_assembler* a, AsmArgs* A) {
+    fb2_cv* cv = a->cv;
+    fb2_ctx* ctx = cv->ctx;
+    const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
+    A->nq = nq;
+    A->o_w = 0;
+    A->o_N = A->o_w + nq;
+    A->o_dN = A->o_N + nq * nb;
+    A->o_M = A->o_dN + nq * nb * rd;
+    A->o_dM = A->o_M + nq * ng;
+    const int total = A->o_dM + nq * ng * rd;
+    FB2_CHECK(total <= FB2_TAB_MAX, FB2_ERR_UNSUPPORTED, "CellValues tables need %d doubles of constant memory (max %d)", total, FB2_TAB_MAX);
+    if (ctx->const_tables_owner != cv) {
+        std::vector<double> h(total);
+        memcpy(h.data() + A->o_w, cv->w.data(), sizeof(double) * nq);
+        memcpy(h.data() + A->o_N, cv->N.data(), sizeof(double) * nq * nb);
+        memcpy(h.data() + A->o_dN, cv->dN.data(), sizeof(double) * nq * nb * rd);
+        memcpy(h.data() + A->o_M, cv->M.data(), sizeof(double) * nq * ng);
+        memcpy(h.data() + A->o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
+        // synchronous w.r.t. the host buffer; ordered on the stream w.r.t. earlier kernels
+        FB2_CUDA(cudaMemcpyToSymbolAsync(c_tab, h.data(), sizeof(double) * total, 0, cudaMemcpyHostToDevice, ctx->stream));
+        FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->const_tables_owner = cv;
+    }
+    return FB2_OK;
+}
+
+template <int DIM, int NGEO, int NB, int NQ, int ELEM>
+int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
+    const int bs = 128;
+    const unsigned grid = (unsigned)((A.ncount + bs - 1) / bs);
+    if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true><<<grid, bs, 0, ctx->stream>>>(A);
+    else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, false><<<grid, bs, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+template <int DIM, int NGEO, int NBS, int VDIM, int ELEM>
+int launch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
+    constexpr int TB = TileOf<NBS>::TB;
+    constexpr int NT = (NBS + TB - 1) / TB;
+    const size_t per_cell = (size_t)fb2_blocks_smem_per_cell<DIM, NBS, ELEM>(A.nq) * sizeof(double);
+    int cells = 32;
+    while (cells > 1 && per_cell * cells > 100 * 1024) cells >>= 1;
+    const size_t smem = per_cell * cells;
+    FB2_CHECK(smem <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", per_cell);
+    int work = std::max(A.nq * cells, NBS * NT * cells);
+    int bs = std::min(256, (work + 31) / 32 * 32);
+    const unsigned grid = (unsigned)((A.ncount + cells - 1) / cells);
+    if (atomic) {
+        auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, true>;
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, bs, smem, ctx->stream>>>(A, cells);
+    } else {
+        auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, false>;
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, bs, smem, ctx->stream>>>(A, cells);
+    }
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+// shape dispatch helpers -------------------------------------------------------------------------
+template <int ELEM, int VDIM_IS_DIM>
+int dispatch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
+#define CASE(CT, DIM, NGEO, NBS)                                                                  \
+    if (celltype == CT && nbs == NBS) {                                                           \
+        if (VDIM_IS_DIM) { if (vdim == DIM) return launch_blocks<DIM, NGEO, NBS, DIM, ELEM>(ctx, A, atomic); } \
+        else { if (vdim == 1) return launch_blocks<DIM, NGEO, NBS, 1, ELEM>(ctx, A, atomic); }    \
+    }
+    CASE(FB2_TRIANGLE, 2, 3, 3)
+    CASE(FB2_TRIANGLE, 2, 3, 6)
+    CASE(FB2_QUADRILATERAL, 2, 4, 4)
+    CASE(FB2_QUADRILATERAL, 2, 4, 9)
+    CASE(FB2_TETRAHEDRON, 3, 4, 4)
+    CASE(FB2_TETRAHEDRON, 3, 4, 10)
+    CASE(FB2_HEXAHEDRON, 3, 8, 8)
+    CASE(FB2_HEXAHEDRON, 3, 8, 27)
+#undef CASE
+    return fb2_fail(FB2_ERR_UNSUPPORTED, "no kernel for cell type %d with %d scalar basis functions and vdim %d", celltype, nbs, vdim);
+}
+
+int dispatch_neohooke(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
+    if (vdim == 3) {
+        if (celltype == FB2_TETRAHEDRON && nbs == 4) return launch_blocks<3, 4, 4, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
+        if (celltype == FB2_TETRAHEDRON && nbs == 10) return launch_blocks<3, 4, 10, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
+        if (celltype == FB2_HEXAHEDRON && nbs == 8) return launch_blocks<3, 8, 8, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
+        if (celltype == FB2_HEXAHEDRON && nbs == 27) return launch_blocks<3, 8, 27, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
+    }
+    return fb2_fail(FB2_ERR_UNSUPPORTED, "Neo-Hooke needs a 3-D cell with a 3-component field");
+}
+
+template <int ELEM>
+bool try_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nb, int nq, int* rc) {
+#define CASE(CT, DIM, NGEO, NB, NQ)                                              \
+    if (celltype == CT && nb == NB && nq == NQ) {                                \
+        *rc = launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic);            \
+        return true;                                                             \
+    }
+    CASE(FB2_QUADRILATERAL, 2, 4, 4, 4)
+    CASE(FB2_HEXAHEDRON, 3, 8, 8, 8)
+    CASE(FB2_TRIANGLE, 2, 3, 3, 1)
+    CASE(FB2_TRIANGLE, 2, 3, 3, 3)
+    CASE(FB2_TRIANGLE, 2, 3, 6, 3)
+    CASE(FB2_TETRAHEDRON, 3, 4, 4, 1)
+    CASE(FB2_TETRAHEDRON, 3, 4, 4, 4)
+    CASE(FB2_TETRAHEDRON, 3, 4, 10, 4)
+#undef CASE
+    return false;
+}
+
+__global__ void k_scatter_batch(const double* __restrict__ Ke, const double* __restrict__ fe, const int32_t* __restrict__ cell_dofs,
+                                const int64_t* __restrict__ colptr, const uint16_t* __restrict__ map, int64_t ncells,
+                                int64_t ncells_pad, int n, double* __restrict__ nzval, double* __restrict__ f, int* errflag) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)n * n;
+    if (t < per * ncells) {
+        int64_t c = t % ncells;
+        int e = (int)(t / ncells);
+        int j = e / n;
+        double v = Ke[(size_t)c * per + e];
+        if (v != 0.0) {
+            unsigned off = map[(size_t)e * ncells_pad + c];
+            if (off == 0xFFFFu) fb2_flag_error(errflag, FB2_ERR_MISSING_PATTERN_ENTRY, c);
+            else atomicAdd(nzval + colptr[cell_dofs[(size_t)j * ncells_pad + c]] + off, v);
+        }
+    }
+    if (f != nullptr && fe != nullptr && t < (int64_t)n * ncells) {
+        int64_t c = t % ncells;
+        int i = (int)(t / ncells);
+        atomicAdd(f + cell_dofs[(size_t)i * ncells_pad + c], fe[(size_t)c * n + i]);
+    }
+}
+
+}  // namespace
+
+int fb2_check_device_error(fb2_ctx* ctx) {
+    FB2_CUDA(cudaMemcpyAsync(ctx->h_errflag, ctx->d_errflag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int code = ctx->h_errflag[0], cell = ctx->h_errflag[1];
+    if (code == 0) return FB2_OK;
+    FB2_CUDA(cudaMemsetAsync(ctx->d_errflag, 0, 2 * sizeof(int), ctx->stream));
+    if (code == FB2_ERR_DETJ_NOT_POSITIVE)
+        return fb2_fail(code, "det(J) is not positive in cell %d (1-based); check the node ordering of the cell", cell + 1);
+    if (code == FB2_ERR_MISSING_PATTERN_ENTRY)
+        return fb2_fail(code, "a non-zero element matrix entry of cell %d (1-based) is missing in the sparsity pattern", cell + 1);
+    return fb2_fail(FB2_ERR_INTERNAL, "device error flag %d in cell %d", code, cell + 1);
+}
+
+int fb2_coloring_build(fb2_assembler* a) {
+    // Greedy colouring: no two cells of one colour share a node (src/Grid/coloring.jl:108-160).  The colours
+    // need not equal the reference's, only be valid; cells keep ascending order inside each colour.
+    if (a->ncolors > 0) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    const int64_t nc = g->ncells;
+    const int nnpc = g->nnpc;
+    std::vector<uint64_t> mask_lo((size_t)g->nnodes, 0), mask_hi((size_t)g->nnodes, 0);
+    a->cell_color.assign((size_t)nc, 0);
+    int ncol = 0;
+    for (int64_t c = 0; c < nc; ++c) {
+        const int64_t* cell = &g->cells[(size_t)c * nnpc];
+        uint64_t lo = 0, hi = 0;
+        for (int k = 0; k < nnpc; ++k) { lo |= mask_lo[cell[k] - 1]; hi |= mask_hi[cell[k] - 1]; }
+        int col = -1;
+        if (~lo) col = __builtin_ctzll(~lo);
+        else if (~hi) col = 64 + __builtin_ctzll(~hi);
+        FB2_CHECK(col >= 0, FB2_ERR_UNSUPPORTED, "colouring needs more than 128 colours");
+        a->cell_color[c] = col;
+        ncol = std::max(ncol, col + 1);
+        for (int k = 0; k < nnpc; ++k) {
+            if (col < 64) mask_lo[cell[k] - 1] |= 1ull << col;
+            else mask_hi[cell[k] - 1] |= 1ull << (col - 64);
+        }
+    }
+    a->ncolors = ncol;
+    a->color_ptr.assign(ncol + 1, 0);
+    for (int64_t c = 0; c < nc; ++c) a->color_ptr[a->cell_color[c] + 1]++;
+    for (int k = 0; k < ncol; ++k) a->color_ptr[k + 1] += a->color_ptr[k];
+    std::vector<int32_t> order((size_t)nc);
+    std::vector<int64_t> cur(a->color_ptr.begin(), a->color_ptr.end() - 1);
+    for (int64_t c = 0; c < nc; ++c) order[cur[a->cell_color[c]]++] = (int32_t)c;
+    FB2_CUDA(cudaSetDevice(g->ctx->device));
+    FB2_CUDA(cudaMalloc(&a->d_color_cells, (size_t)nc * sizeof(int32_t)));
+    FB2_CUDA(cudaMemcpy(a->d_color_cells, order.data(), (size_t)nc * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return FB2_OK;
+}
+
+static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, int variant) {
+    fb2_cv* cv = a->cv;
+    fb2_ctx* ctx = cv->ctx;
+    const int ct = cv->celltype, nbs = cv->nb, vdim = cv->vdim;
+    int rc = FB2_OK;
+    switch (element) {
+        case FB2_ELEM_HEAT:
+            FB2_CHECK(vdim == 1, FB2_ERR_BAD_ARG, "the heat element needs a scalar field");
+            if (variant == 0 && try_scalar<FB2_ELEM_HEAT>(ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            return dispatch_blocks<FB2_ELEM_HEAT, 0>(ctx, A, atomic, ct, nbs, vdim);
+        case FB2_ELEM_MASS:
+            FB2_CHECK(vdim == 1, FB2_ERR_UNSUPPORTED, "the mass element is implemented for scalar fields");
+            if (variant == 0 && try_scalar<FB2_ELEM_MASS>(ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            return dispatch_blocks<FB2_ELEM_MASS, 0>(ctx, A, atomic, ct, nbs, vdim);
+        case FB2_ELEM_ELASTICITY:
+            return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(ctx, A, atomic, ct, nbs, vdim);
+        case FB2_ELEM_NEOHOOKE:
+            FB2_CHECK(A.u != nullptr, FB2_ERR_BAD_ARG, "the Neo-Hooke element needs the current solution u");
+            return dispatch_neohooke(ctx, A, atomic, ct, nbs, vdim);
+    }
+    return fb2_fail(FB2_ERR_BAD_ARG, "unknown element id %d", element);
+}
+
+int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
+                        double* nzval_dev, double* f_dev, const fb2_asm_opts* opts) {
+    fb2_dh* dh = a->dh;
+    fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+    if (opts) o = *opts;
+    AsmArgs A;
+    memset(&A, 0, sizeof(A));
+    FB2_TRY(upload_tables(a, &A));
+    A.conn = g->d_conn;
+    A.xyz = g->d_xyz;
+    A.cell_dofs = dh->d_cell_dofs;
+    A.colptr = a->pat->d_colptr;
+    A.map = a->d_map;
+    A.ncells_pad = g->ncells_pad;
+    A.nzval = nzval_dev;
+    A.f = f_dev;
+    A.u = u_dev;
+    A.errflag = ctx->d_errflag;
+    switch (element) {
+        case FB2_ELEM_HEAT: {
+            fb2_heat_params p = {1.0, 1.0};
+            if (params) { FB2_CHECK(params_bytes == sizeof(p), FB2_ERR_BAD_ARG, "heat params: expected %zu bytes", sizeof(p)); memcpy(&p, params, sizeof(p)); }
+            A.p[0] = p.k; A.p[1] = p.source;
+            break;
+        }
+        case FB2_ELEM_MASS: {
+            fb2_mass_params p = {1.0};
+            if (params) { FB2_CHECK(params_bytes == sizeof(p), FB2_ERR_BAD_ARG, "mass params: expected %zu bytes", sizeof(p)); memcpy(&p, params, sizeof(p)); }
+            A.p[0] = p.rho; A.p[1] = 0.0;
+            break;
+        }
+        case FB2_ELEM_ELASTICITY:
+        case FB2_ELEM_NEOHOOKE: {
+            fb2_elasticity_params p;
+            FB2_CHECK(params && params_bytes == sizeof(p), FB2_ERR_BAD_ARG, "elasticity params: expected %zu bytes", sizeof(p));
+            memcpy(&p, params, sizeof(p));
+            A.p[0] = p.lambda; A.p[1] = p.mu; A.p[2] = p.b[0]; A.p[3] = p.b[1]; A.p[4] = p.b[2];
+            break;
+        }
+        default: return fb2_fail(FB2_ERR_BAD_ARG, "unknown element id %d", element);
+    }
+    if (o.fillzero) {
+        FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+        if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)dh->ndofs * sizeof(double), ctx->stream));
+        ctx->launches += f_dev ? 2 : 1;
+    }
+    if (o.scatter_mode == FB2_SCATTER_COLORED) {
+        FB2_CHECK(a->d_cells == nullptr, FB2_ERR_UNSUPPORTED, "coloured scatter on a partitioned assembler is not supported");
+        FB2_TRY(fb2_coloring_build(a));
+        for (int c = 0; c < a->ncolors; ++c) {
+            A.cells = a->d_color_cells + a->color_ptr[c];
+            A.ncount = a->color_ptr[c + 1] - a->color_ptr[c];
+            if (A.ncount == 0) continue;
+            FB2_TRY(launch_one(a, A, element, false, o.variant));
+        }
+        return FB2_OK;
+    }
+    A.cells = a->d_cells;
+    A.ncount = a->d_cells ? a->ncells_active : g->ncells;
+    if (A.ncount == 0) return FB2_OK;
+    return launch_one(a, A, element, true, o.variant);
+}
+
+extern "C" int fb2_scatter_host(fb2_assembler* a, const double* Ke, const double* fe, double* nzval_dev, double* f_dev,
+                                const fb2_asm_opts* opts) {
+    FB2_CHECK(a && Ke && nzval_dev, FB2_ERR_BAD_ARG, "fb2_scatter_host: null argument");
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+    if (opts) o = *opts;
+    const int n = a->n;
+    const size_t nk = (size_t)n * n * g->ncells, nf = (size_t)n * g->ncells;
+    double *d_Ke = nullptr, *d_fe = nullptr;
+    FB2_CUDA(cudaMalloc(&d_Ke, nk * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d_Ke, Ke, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && fe && f_dev) {
+        e = cudaMalloc(&d_fe, nf * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_fe, fe, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e == cudaSuccess && o.fillzero) {
+        e = cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream);
+        if (e == cudaSuccess && f_dev) e = cudaMemsetAsync(f_dev, 0, (size_t)a->dh->ndofs * sizeof(double), ctx->stream);
+    }
+    if (e == cudaSuccess) {
+        const int64_t total = (int64_t)n * n * g->ncells;
+        k_scatter_batch<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_Ke, d_fe, a->dh->d_cell_dofs, a->pat->d_colptr,
+                                                                               a->d_map, g->ncells, g->ncells_pad, n, nzval_dev,
+                                                                               f_dev, ctx->d_errflag);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    int rc = FB2_OK;
+    if (e != cudaSuccess) rc = fb2_fail(FB2_ERR_CUDA, "fb2_scatter_host: %s", cudaGetErrorString(e));
+    else rc = fb2_check_device_error(ctx);
+    cudaFree(d_Ke);
+    cudaFree(d_fe);
+    return rc;
+}

@@ -1,0 +1,204 @@
+// Internal definitions shared by the translation units of libferrite_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/ferrite_b200.h"
+
+// ---- error handling ---------------------------------------------------------------------
+void fb2_set_error(const char* fmt, ...);
+int fb2_fail(int code, const char* fmt, ...);
+
+#define FB2_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            return fb2_fail(e__ == cudaErrorMemoryAllocation ? FB2_ERR_OOM : FB2_ERR_CUDA,      \
+                            "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,  \
+                            __LINE__);                                                          \
+        }                                                                                       \
+    } while (0)
+
+#define FB2_CHECK(cond, code, ...)                  \
+    do {                                            \
+        if (!(cond)) return fb2_fail(code, __VA_ARGS__); \
+    } while (0)
+
+#define FB2_NEED_DEVICE(ctx)                                                                      \
+    do {                                                                                          \
+        if ((ctx)->device < 0)                                                                    \
+            return fb2_fail(FB2_ERR_CUDA, "%s needs a CUDA device but the context is host-only; " \
+                            "libferrite_b200 has no CPU fallback", __func__);                     \
+    } while (0)
+
+#define FB2_TRY(call)                 \
+    do {                              \
+        int rc__ = (call);            \
+        if (rc__ != FB2_OK) return rc__; \
+    } while (0)
+
+// ---- reference-shape / interpolation tables (tables.cpp) -----------------------------------
+struct RefShapeInfo {
+    int celltype;
+    int rdim;
+    int nvertices;
+    int nedges;
+    int nfaces;
+    int edges[12][2];      // 0-based local vertex ids
+    int faces[6][4];       // 0-based, -1 padded
+    int face_nverts[6];
+    int face_edges[6][4];  // edge numbers (0-based) around each face
+};
+const RefShapeInfo* fb2_refshape(int celltype);
+
+struct LagrangeInfo {
+    int celltype;
+    int order;
+    int nbase;
+    int rdim;
+    double refcoords[27][3];
+    int nvertexdofs;  // per vertex (0 or 1)
+    int nedgedofs;    // interior dofs per edge
+    int nfacedofs;    // interior dofs per face
+    int nvolumedofs;
+    int edge_first;   // 0-based index of the first edge-interior dof
+    int face_first;
+    int vol_first;
+};
+// returns false if (celltype, order) is outside the supported menu
+bool fb2_lagrange(int celltype, int order, LagrangeInfo* out);
+// N[n], dN[n][rdim] at xi
+void fb2_lagrange_eval(const LagrangeInfo& ip, const double* xi, double* N, double* dN);
+// local dof lists (0-based scalar basis indices) of boundary entities: kind = FB2_BC_FACET/FACE/EDGE/VERTEX
+std::vector<std::vector<int>> fb2_boundarydof_indices(const LagrangeInfo& ip, int kind);
+// quadrature: default rule of the reference per shape; points are nq x rdim
+bool fb2_quadrature(int celltype, int order, std::vector<double>* w, std::vector<double>* pts);
+
+// ---- objects --------------------------------------------------------------------------------
+struct fb2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    int64_t launches = 0;
+    int* d_errflag = nullptr;   // [0] = code, [1] = cell id
+    int* h_errflag = nullptr;   // pinned
+    const void* const_tables_owner = nullptr;  // fb2_cv whose tables are currently in __constant__ memory
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+struct fb2_grid {
+    fb2_ctx* ctx = nullptr;
+    int celltype = 0;
+    int64_t ncells = 0, nnodes = 0;
+    int nnpc = 0, sdim = 0;
+    std::vector<int64_t> cells;   // nnpc x ncells, 1-based
+    std::vector<double> xyz;      // sdim x nnodes
+    std::map<std::string, std::vector<int64_t>> facetsets;  // flattened (cell, facet) pairs, 1-based, sorted
+    bool generated = false;
+    int64_t nel[3] = {1, 1, 1};
+    double left[3] = {0, 0, 0}, right[3] = {0, 0, 0};
+    // device
+    int64_t ncells_pad = 0;       // multiple of 32
+    int32_t* d_conn = nullptr;    // SoA [nnpc][ncells_pad], 0-based node ids
+    double* d_xyz = nullptr;      // [nnodes][xstride]
+    double* d_xyz_stage = nullptr;  // staging buffer of fb2_grid_upload_coordinates_async
+    int xstride = 0;              // 4 for sdim 3, 2 for sdim 2, 1 for sdim 1
+};
+int fb2_grid_upload(fb2_grid* g);
+int fb2_grid_upload_xyz(fb2_grid* g);
+
+struct fb2_dh {
+    fb2_grid* grid = nullptr;
+    std::vector<fb2_field> fields;
+    std::vector<LagrangeInfo> ips;
+    int64_t ndofs = 0;
+    int ndpc = 0;
+    std::vector<int32_t> cell_dofs;  // host, ndpc x ncells, 0-based
+    int32_t* d_cell_dofs = nullptr;  // SoA [ndpc][ncells_pad], 0-based
+    int field_offset(int f) const {
+        int o = 0;
+        for (int i = 0; i < f; ++i) o += ips[i].nbase * fields[i].vdim;
+        return o;
+    }
+};
+
+struct fb2_pattern {
+    fb2_dh* dh = nullptr;
+    int64_t n = 0, nnz = 0;
+    int64_t* d_colptr = nullptr;   // [n+1], 0-based offsets
+    int32_t* d_rowval = nullptr;   // [nnz], 0-based
+    int64_t* d_diag = nullptr;     // [n] position of the diagonal entry, -1 if absent
+    bool structurally_symmetric = false;
+    int max_col_len = 0;
+};
+
+struct fb2_cv {
+    fb2_ctx* ctx = nullptr;
+    int celltype = 0;
+    int rdim = 0, nq = 0, nb = 0, vdim = 1, ngeo = 0;
+    int ip_order = 0, geo_order = 0, qr_order = 0;
+    // host tables, q-major: N[q][i], dN[q][i][d], M[q][j], dM[q][j][d], w[q], pts[q][d]
+    std::vector<double> N, dN, M, dM, w, pts;
+    double* d_tables = nullptr;   // packed [w | N | dN | M | dM] on the device
+    size_t tables_count = 0;
+};
+
+struct fb2_part;
+
+struct fb2_assembler {
+    fb2_dh* dh = nullptr;
+    fb2_pattern* pat = nullptr;
+    fb2_cv* cv = nullptr;
+    int n = 0;                     // dofs per cell covered by the element (= ndpc)
+    uint16_t* d_map = nullptr;     // [n*n][ncells_pad]: offset of row dof_i inside column dof_j, e = j*n + i
+    // colouring (lazy)
+    int ncolors = 0;
+    std::vector<int32_t> cell_color;
+    std::vector<int64_t> color_ptr;      // [ncolors+1]
+    int32_t* d_color_cells = nullptr;    // cells sorted by colour
+    // cell subset (partitioned assembly); nullptr = all cells
+    int32_t* d_cells = nullptr;
+    int64_t ncells_active = 0;
+    // scratch for the host-buffer entry point
+    double* d_nzval = nullptr;
+    double* d_f = nullptr;
+    double* d_u = nullptr;
+};
+
+struct DirichletBC {
+    int field = 0, kind = 0;
+    std::vector<int> comps;                // 1-based
+    std::vector<int64_t> entities;         // flattened pairs or node ids (1-based)
+    std::vector<double> points;            // sdim x npoints (evaluation order of update!)
+    std::vector<int64_t> point_dofs;       // ncomp x npoints global dofs (0-based)
+};
+
+struct fb2_ch {
+    fb2_dh* dh = nullptr;
+    bool closed = false;
+    std::vector<DirichletBC> bcs;
+    std::vector<int64_t> insertion;          // prescribed dofs in insertion order (0-based)
+    std::vector<int64_t> prescribed;         // sorted, 0-based
+    std::vector<double> inhom;
+    std::vector<int32_t> dofmap;             // dof -> index in prescribed (or -1), built at close
+    int32_t* d_prescribed = nullptr;
+    double* d_inhom = nullptr;
+    uint8_t* d_isconstrained = nullptr;
+    double* d_scratch = nullptr;             // reduction scratch
+    bool inhom_dirty = true;
+};
+
+// ---- device-side helpers implemented in .cu files ------------------------------------------
+int fb2_pattern_build_device(fb2_pattern* p);
+int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
+int fb2_map_build(fb2_assembler* a);
+int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
+                        double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
+int fb2_check_device_error(fb2_ctx* ctx);
+int fb2_coloring_build(fb2_assembler* a);

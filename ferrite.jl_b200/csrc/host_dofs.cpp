@@ -1,0 +1,197 @@
+// DofHandler: dof distribution (host, bit-identical to the reference) + SoA upload.
+//
+// Replaces close!(dh) of the reference for one SubDofHandler covering the grid:
+// src/Dofs/DofHandler.jl:493-569 (__close!), :576-676 (_close_subdofhandler!), :685-713
+// (_distribute_dofs_for_cell!), :715-738 (add_vertex_dofs), :746-759 (get_or_create_dofs!),
+// :761-794 (face / edge / volume dofs), :854-857 (sortedge), :1043-1057 (sortface_fast: a face is
+// keyed by its three smallest node ids).  One counter, cells ascending, fields in add! order, per field
+// vertices -> edge interiors -> face interiors -> cell interior; vdim copies of a scalar dof are
+// consecutive.  Orders 1-2 never permute entity dofs (src/interpolations.jl:577-579).
+#include <algorithm>
+#include <cstring>
+#include <unordered_map>
+
+#include "common.h"
+
+struct Key3 {
+    int32_t a, b, c;
+    bool operator==(const Key3& o) const { return a == o.a && b == o.b && c == o.c; }
+};
+struct Key3Hash {
+    size_t operator()(const Key3& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.a * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)(uint32_t)k.b + 0x7F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+        h = (h ^ (h >> 29)) + (uint64_t)(uint32_t)k.c * 0x94D049BB133111EBull;
+        return (size_t)(h ^ (h >> 32));
+    }
+};
+
+static int upload_cell_dofs(fb2_dh* dh) {
+    fb2_grid* g = dh->grid;
+    if (g->ctx->device < 0) return FB2_OK;  // host-only context
+    FB2_CUDA(cudaSetDevice(g->ctx->device));
+    std::vector<int32_t> soa((size_t)dh->ndpc * g->ncells_pad);
+    for (int i = 0; i < dh->ndpc; ++i) {
+        int32_t* dst = soa.data() + (size_t)i * g->ncells_pad;
+        for (int64_t c = 0; c < g->ncells; ++c) dst[c] = dh->cell_dofs[(size_t)c * dh->ndpc + i];
+        for (int64_t c = g->ncells; c < g->ncells_pad; ++c) dst[c] = dst[g->ncells - 1];
+    }
+    FB2_CUDA(cudaMalloc(&dh->d_cell_dofs, soa.size() * sizeof(int32_t)));
+    FB2_CUDA(cudaMemcpy(dh->d_cell_dofs, soa.data(), soa.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return FB2_OK;
+}
+
+static int init_fields(fb2_dh* dh, fb2_grid* grid, int nfields, const fb2_field* fields) {
+    FB2_CHECK(nfields >= 1 && nfields <= 8, FB2_ERR_BAD_ARG, "DofHandler: need 1..8 fields");
+    dh->grid = grid;
+    dh->ndpc = 0;
+    for (int f = 0; f < nfields; ++f) {
+        LagrangeInfo ip;
+        FB2_CHECK(fb2_lagrange(grid->celltype, fields[f].order, &ip), FB2_ERR_UNSUPPORTED,
+                  "DofHandler: Lagrange order %d not supported on cell type %d", fields[f].order, grid->celltype);
+        FB2_CHECK(fields[f].vdim >= 1 && fields[f].vdim <= 3, FB2_ERR_BAD_ARG, "DofHandler: vdim must be 1..3");
+        dh->fields.push_back(fields[f]);
+        dh->ips.push_back(ip);
+        dh->ndpc += ip.nbase * fields[f].vdim;
+    }
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_close(fb2_grid* grid, int nfields, const fb2_field* fields, fb2_dh** out) {
+    FB2_CHECK(grid && fields && out, FB2_ERR_BAD_ARG, "fb2_dh_close: null argument");
+    fb2_dh* dh = new fb2_dh();
+    int rc = init_fields(dh, grid, nfields, fields);
+    if (rc != FB2_OK) { delete dh; return rc; }
+    const RefShapeInfo* rs = fb2_refshape(grid->celltype);
+    const int64_t ncells = grid->ncells;
+    const int nnpc = grid->nnpc;
+    dh->cell_dofs.resize((size_t)ncells * dh->ndpc);
+
+    std::vector<std::vector<int32_t>> vertexdict(nfields);
+    std::vector<std::unordered_map<uint64_t, int32_t>> edgedict(nfields);
+    std::vector<std::unordered_map<Key3, int32_t, Key3Hash>> facedict(nfields);
+    for (int f = 0; f < nfields; ++f) {
+        vertexdict[f].assign((size_t)grid->nnodes, -1);
+        if (dh->ips[f].nedgedofs > 0) edgedict[f].reserve((size_t)ncells * 2);
+        if (dh->ips[f].nfacedofs > 0) facedict[f].reserve((size_t)ncells * (rs->rdim == 3 ? 2 : 1));
+    }
+    int64_t nextdof = 0;  // 0-based
+    for (int64_t ci = 0; ci < ncells; ++ci) {
+        const int64_t* cell = &grid->cells[(size_t)ci * nnpc];
+        int32_t* row = &dh->cell_dofs[(size_t)ci * dh->ndpc];
+        int col = 0;
+        for (int f = 0; f < nfields; ++f) {
+            const LagrangeInfo& ip = dh->ips[f];
+            const int nc = dh->fields[f].vdim;
+            // vertices
+            if (ip.nvertexdofs > 0)
+                for (int vi = 0; vi < rs->nvertices; ++vi) {
+                    int64_t v = cell[vi] - 1;
+                    int32_t first = vertexdict[f][v];
+                    if (first < 0) {
+                        first = (int32_t)nextdof;
+                        vertexdict[f][v] = first;
+                        nextdof += (int64_t)ip.nvertexdofs * nc;
+                    }
+                    for (int t = 0; t < ip.nvertexdofs * nc; ++t) row[col++] = first + t;
+                }
+            // edge interiors
+            if (ip.nedgedofs > 0)
+                for (int ei = 0; ei < rs->nedges; ++ei) {
+                    uint64_t a = (uint64_t)cell[rs->edges[ei][0]], b = (uint64_t)cell[rs->edges[ei][1]];
+                    uint64_t key = a < b ? (a << 32) | b : (b << 32) | a;
+                    auto ins = edgedict[f].emplace(key, (int32_t)nextdof);
+                    if (ins.second) nextdof += (int64_t)ip.nedgedofs * nc;
+                    int32_t first = ins.first->second;
+                    for (int t = 0; t < ip.nedgedofs * nc; ++t) row[col++] = first + t;
+                }
+            // face interiors
+            if (ip.nfacedofs > 0)
+                for (int fi = 0; fi < rs->nfaces; ++fi) {
+                    int32_t ids[4];
+                    int nfv = rs->face_nverts[fi];
+                    for (int k = 0; k < nfv; ++k) ids[k] = (int32_t)cell[rs->faces[fi][k]];
+                    for (int x = 1; x < nfv; ++x)  // insertion sort of <= 4 ids
+                        for (int y = x; y > 0 && ids[y] < ids[y - 1]; --y) std::swap(ids[y], ids[y - 1]);
+                    Key3 key{ids[0], ids[1], ids[2]};
+                    auto ins = facedict[f].emplace(key, (int32_t)nextdof);
+                    if (ins.second) nextdof += (int64_t)ip.nfacedofs * nc;
+                    int32_t first = ins.first->second;
+                    for (int t = 0; t < ip.nfacedofs * nc; ++t) row[col++] = first + t;
+                }
+            // cell interior
+            for (int t = 0; t < ip.nvolumedofs * nc; ++t) row[col++] = (int32_t)nextdof++;
+            if (nextdof >= (int64_t)2147483647) { delete dh; return fb2_fail(FB2_ERR_UNSUPPORTED, "more than 2^31-1 dofs per device"); }
+        }
+        if (col != dh->ndpc) {
+            const int expected = dh->ndpc;
+            delete dh;
+            return fb2_fail(FB2_ERR_INTERNAL, "dof distribution produced %d dofs per cell, expected %d", col, expected);
+        }
+    }
+    dh->ndofs = nextdof;
+    rc = upload_cell_dofs(dh);
+    if (rc != FB2_OK) { delete dh; return rc; }
+    *out = dh;
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fields, int64_t ndofs, int ndofs_per_cell,
+                                const int64_t* cell_dofs, fb2_dh** out) {
+    FB2_CHECK(grid && fields && cell_dofs && out, FB2_ERR_BAD_ARG, "fb2_dh_from_host: null argument");
+    FB2_CHECK(ndofs > 0 && ndofs < (int64_t)2147483647, FB2_ERR_UNSUPPORTED, "ndofs must be in 1..2^31-2");
+    fb2_dh* dh = new fb2_dh();
+    int rc = init_fields(dh, grid, nfields, fields);
+    if (rc != FB2_OK) { delete dh; return rc; }
+    if (dh->ndpc != ndofs_per_cell) {
+        const int have = dh->ndpc;
+        delete dh;
+        return fb2_fail(FB2_ERR_BAD_ARG, "fb2_dh_from_host: fields give %d dofs per cell, caller says %d", have, ndofs_per_cell);
+    }
+    dh->ndofs = ndofs;
+    size_t tot = (size_t)grid->ncells * dh->ndpc;
+    dh->cell_dofs.resize(tot);
+    for (size_t i = 0; i < tot; ++i) {
+        if (cell_dofs[i] < 1 || cell_dofs[i] > ndofs) {
+            delete dh;
+            return fb2_fail(FB2_ERR_BAD_ARG, "fb2_dh_from_host: dof %lld out of range 1..%lld", (long long)cell_dofs[i], (long long)ndofs);
+        }
+        dh->cell_dofs[i] = (int32_t)(cell_dofs[i] - 1);
+    }
+    rc = upload_cell_dofs(dh);
+    if (rc != FB2_OK) { delete dh; return rc; }
+    *out = dh;
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_info(fb2_dh* dh, int64_t* ndofs, int* ndofs_per_cell, int* nfields) {
+    FB2_CHECK(dh, FB2_ERR_BAD_ARG, "fb2_dh_info: null handle");
+    if (ndofs) *ndofs = dh->ndofs;
+    if (ndofs_per_cell) *ndofs_per_cell = dh->ndpc;
+    if (nfields) *nfields = (int)dh->fields.size();
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_export(fb2_dh* dh, int64_t* cell_dofs) {
+    FB2_CHECK(dh && cell_dofs, FB2_ERR_BAD_ARG, "fb2_dh_export: null argument");
+    for (size_t i = 0; i < dh->cell_dofs.size(); ++i) cell_dofs[i] = (int64_t)dh->cell_dofs[i] + 1;
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_dof_range(fb2_dh* dh, int field, int* first, int* last) {
+    FB2_CHECK(dh && field >= 0 && field < (int)dh->fields.size(), FB2_ERR_BAD_ARG, "fb2_dh_dof_range: bad field index");
+    int off = dh->field_offset(field);
+    if (first) *first = off + 1;
+    if (last) *last = off + dh->ips[field].nbase * dh->fields[field].vdim;
+    return FB2_OK;
+}
+
+extern "C" int fb2_dh_destroy(fb2_dh* dh) {
+    if (!dh) return FB2_OK;
+    if (dh->grid->ctx->device >= 0) {
+        cudaSetDevice(dh->grid->ctx->device);
+        cudaFree(dh->d_cell_dofs);
+    }
+    delete dh;
+    return FB2_OK;
+}

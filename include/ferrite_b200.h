@@ -1,0 +1,253 @@
+/*
+ * libferrite_b200.so -- C ABI of the B200-native global FE assembly path.
+ *
+ * The reference (Ferrite.jl, pure Julia) has no FFI; its extension points for a
+ * custom matrix/assembler back-end are the generic functions listed in
+ * docs/src/devdocs/assembly.md:18-51.  Each entry point below names the
+ * reference interface it replaces (path:line under the reference tree).  A Julia
+ * shim binds these with `ccall`; the Python mirror in
+ * ferrite.jl_b200/ binds them with ctypes.
+ *
+ * Conventions
+ *   - every function returns an int status (FB2_OK == 0); no C++ exception crosses
+ *     the boundary; fb2_last_error() returns the message of the last failure on
+ *     the calling thread.
+ *   - all index arrays that cross the boundary are 1-based int64 exactly as the
+ *     reference stores them (cell node ids, cell_dofs, colptr, rowval,
+ *     prescribed_dofs); floating point is double.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - handles are opaque, created and destroyed by the library.  A context is bound
+ *     to one CUDA device and one stream; calls on one context are not re-entrant
+ *     (like the reference's per-task assemblers, src/assembler.jl:273-276).
+ *   - there is no CPU fallback: every compute entry point fails with
+ *     FB2_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef FERRITE_B200_H
+#define FERRITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ----------------------------------------------------------------- */
+enum {
+    FB2_OK = 0,
+    FB2_ERR_BAD_ARG = 1,
+    FB2_ERR_CUDA = 2,
+    FB2_ERR_OOM = 3,
+    FB2_ERR_DETJ_NOT_POSITIVE = 4,     /* throw_detJ_not_pos, src/FEValues/common_values.jl:5 */
+    FB2_ERR_MISSING_PATTERN_ENTRY = 5, /* _missing_sparsity_pattern_error, src/assembler.jl:459-467 */
+    FB2_ERR_UNSUPPORTED = 6,
+    FB2_ERR_NCCL = 7,
+    FB2_ERR_INTERNAL = 8
+};
+
+/* ---- enums ------------------------------------------------------------------------ */
+/* cell types (src/Grid/grid.jl:282-338): Line, Triangle, Quadrilateral, Tetrahedron, Hexahedron */
+enum { FB2_LINE = 1, FB2_TRIANGLE = 2, FB2_QUADRILATERAL = 3, FB2_TETRAHEDRON = 4, FB2_HEXAHEDRON = 5 };
+
+/* element-routine menu (the reference's element routine is user Julia code; these are the
+ * tutorial kernels) */
+enum {
+    FB2_ELEM_HEAT = 1,       /* Ke = int k grad(Ni).grad(Nj), fe = int s Ni; heat_equation.jl:143-164 */
+    FB2_ELEM_MASS = 2,       /* Ke = int rho Ni.Nj, fe = 0 */
+    FB2_ELEM_ELASTICITY = 3, /* Ke = int eps_i:C:eps_j (isotropic C), fe = int Ni.b; threaded_assembly.jl:105-119 */
+    FB2_ELEM_NEOHOOKE = 4    /* tangent + residual of Psi = mu/2(Ic-3-2lnJ)+lam/2(J-1)^2; hyperelasticity.jl:162-176,241-276 */
+};
+
+/* scatter strategies (src/assembler.jl:174-231 `atomic` flag; threaded_assembly.jl:232-265 colouring) */
+enum { FB2_SCATTER_ATOMIC = 0, FB2_SCATTER_COLORED = 1 };
+
+/* boundary entity kinds of a Dirichlet set (FacetIndex/FaceIndex/EdgeIndex/VertexIndex, node set) */
+enum { FB2_BC_FACET = 0, FB2_BC_FACE = 1, FB2_BC_EDGE = 2, FB2_BC_VERTEX = 3, FB2_BC_NODE = 4 };
+
+/* ---- POD parameter structs -------------------------------------------------------- */
+typedef struct { int order; int vdim; } fb2_field; /* Lagrange{refshape(cell), order}()^vdim, add!(dh, name, ip) src/Dofs/DofHandler.jl:420-439 */
+
+typedef struct { double k; double source; } fb2_heat_params;
+typedef struct { double rho; } fb2_mass_params;
+typedef struct { double lambda; double mu; double b[3]; } fb2_elasticity_params; /* also for FB2_ELEM_NEOHOOKE */
+
+typedef struct {
+    int fillzero;     /* start_assemble(K, f; fillzero) src/assembler.jl:287-291 */
+    int scatter_mode; /* FB2_SCATTER_* */
+    int variant;      /* 0 = default kernel for the element; >0 selects an alternative implementation (benchmarks) */
+    int reserved;
+} fb2_asm_opts;
+
+typedef struct fb2_ctx fb2_ctx;
+typedef struct fb2_grid fb2_grid;
+typedef struct fb2_dh fb2_dh;
+typedef struct fb2_pattern fb2_pattern;
+typedef struct fb2_cv fb2_cv;
+typedef struct fb2_assembler fb2_assembler;
+typedef struct fb2_ch fb2_ch;
+
+/* ---- context ---------------------------------------------------------------------- */
+const char* fb2_version(void);
+const char* fb2_last_error(void);
+int fb2_ctx_create(int device, fb2_ctx** out);
+int fb2_ctx_destroy(fb2_ctx* ctx);
+int fb2_ctx_synchronize(fb2_ctx* ctx);
+/* run all subsequent work of this context on an existing CUDA stream (cudaStream_t as void*) */
+int fb2_ctx_set_stream(fb2_ctx* ctx, void* cuda_stream);
+/* number of kernels this context has launched so far (bench.py `gpu_launches`) */
+int fb2_ctx_launch_count(fb2_ctx* ctx, int64_t* out);
+/* device memory owned by the library on behalf of the caller (nzval, f, u ...) */
+int fb2_device_alloc(fb2_ctx* ctx, size_t nbytes, void** dev_ptr);
+int fb2_device_free(fb2_ctx* ctx, void* dev_ptr);
+int fb2_memcpy_h2d(fb2_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
+int fb2_memcpy_d2h(fb2_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes);
+/* dependent-chain-free FP64 FMA microbenchmark on the context's device: measured roofline denominator
+ * for the FP64-bound kernels (TFLOP/s) */
+int fb2_measure_fp64_peak(fb2_ctx* ctx, double* tflops);
+
+/* ---- grid: Grid / generate_grid ---------------------------------------------------- */
+/* Grid(cells, nodes), src/Grid/grid.jl:385-393.  cells: nnpc x ncells column-major (= Julia
+ * Vector{Hexahedron}), 1-based node ids; xyz: sdim x nnodes (= Vector{Node{sdim,Float64}}). */
+int fb2_grid_from_host(fb2_ctx* ctx, int celltype, int64_t ncells, int64_t nnodes, int sdim,
+                       const int64_t* cells, const double* xyz, fb2_grid** out);
+/* generate_grid(CellType, nel, left, right), src/Grid/grid_generators.jl:8-37 (Line), :78-112
+ * (Quadrilateral), :383-417 (Triangle), :159-203 (Hexahedron), :474-537 (Tetrahedron); node
+ * coordinates as _generate_nodes :550-578.  Also creates the named facet sets. */
+int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel, const double* left,
+                      const double* right, fb2_grid** out);
+/* deterministic interior-node perturbation x += amplitude*h*(hash(node)-1/2) of a generated
+ * grid (cf. perturb_standard_grid!, test/test_utils.jl:282); synthetic benchmark input only */
+int fb2_grid_perturb(fb2_grid* grid, double amplitude);
+/* replace the node coordinates (sdim x nnodes, host) on the host copy and on the device */
+int fb2_grid_set_coordinates(fb2_grid* grid, const double* xyz);
+/* device-only, stream-ordered coordinate update from (ideally pinned) host memory: the per-step input of
+ * the end-to-end path (moving meshes).  The host copy used by Dirichlet set-up is not touched. */
+int fb2_grid_upload_coordinates_async(fb2_grid* grid, const double* xyz_host);
+int fb2_grid_info(fb2_grid* grid, int* celltype, int64_t* ncells, int64_t* nnodes, int* nnpc, int* sdim);
+int fb2_grid_export(fb2_grid* grid, int64_t* cells, double* xyz);
+/* getfacetset(grid, name): pairs = 2 x n (cell, local facet), sorted; pass pairs = NULL to query n */
+int fb2_grid_facetset(fb2_grid* grid, const char* name, int64_t* n, int64_t* pairs);
+int fb2_grid_destroy(fb2_grid* grid);
+
+/* ---- DofHandler: add! / close! / celldofs / ndofs ------------------------------------- */
+/* DofHandler(grid); add!(dh, :f_k, Lagrange{..,order}()^vdim) for each field; close!(dh):
+ * src/Dofs/DofHandler.jl:169,420-439,474-569,576-794.  The numbering is bit-identical to the reference. */
+int fb2_dh_close(fb2_grid* grid, int nfields, const fb2_field* fields, fb2_dh** out);
+/* arrays-in mode: adopt the reference's own dh.cell_dofs (ndofs_per_cell x ncells, 1-based),
+ * src/Dofs/DofHandler.jl:126-131 */
+int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fields, int64_t ndofs,
+                     int ndofs_per_cell, const int64_t* cell_dofs, fb2_dh** out);
+int fb2_dh_info(fb2_dh* dh, int64_t* ndofs, int* ndofs_per_cell, int* nfields);
+/* celldofs!(dofs, dh, i) for all cells: ndofs_per_cell x ncells, 1-based (src/Dofs/DofHandler.jl:248-253) */
+int fb2_dh_export(fb2_dh* dh, int64_t* cell_dofs);
+/* dof_range(dh, field): 1-based inclusive range of local dofs (src/Dofs/DofHandler.jl:1173-1187) */
+int fb2_dh_dof_range(fb2_dh* dh, int field, int* first, int* last);
+int fb2_dh_destroy(fb2_dh* dh);
+
+/* ---- sparsity pattern: allocate_matrix ------------------------------------------------ */
+/* allocate_matrix(dh) -> SparseMatrixCSC pattern, built on the device:
+ * src/Dofs/sparsity_pattern.jl:628-645,370-398,1136-1249,951-991.  colptr/rowval are bit-identical. */
+int fb2_pattern_create(fb2_dh* dh, fb2_pattern** out);
+/* arrays-in mode: adopt K.colptr (n+1) / K.rowval (nnz), 1-based */
+int fb2_pattern_from_host(fb2_dh* dh, const int64_t* colptr, const int64_t* rowval, fb2_pattern** out);
+int fb2_pattern_info(fb2_pattern* p, int64_t* n, int64_t* nnz);
+int fb2_pattern_export(fb2_pattern* p, int64_t* colptr, int64_t* rowval);
+int fb2_pattern_destroy(fb2_pattern* p);
+
+/* ---- CellValues ------------------------------------------------------------------------- */
+/* CellValues(QuadratureRule{refshape}(qr_order), Lagrange{refshape,ip_order}()^vdim, Lagrange{refshape,geo_order}()):
+ * src/FEValues/CellValues.jl:57-83; quadrature src/Quadrature/quadrature.jl:64-138 (default rule per shape) */
+int fb2_cellvalues_create(fb2_ctx* ctx, int celltype, int qr_order, int ip_order, int vdim, int geo_order, fb2_cv** out);
+/* arrays-in mode: the reference's own tables.  N: n x nq, dNdxi: rdim x n x nq, M: ngeo x nq,
+ * dMdxi: rdim x ngeo x nq (column-major, i.e. cv.fun_values.Nxi/dNdxi FunctionValues.jl:46-49,
+ * cv.geo_mapping.M/dMdxi GeometryMapping.jl:38-39), w: nq (cv.qr.weights) */
+int fb2_cellvalues_from_tables(fb2_ctx* ctx, int celltype, int nq, int n, int vdim, int ngeo, const double* N,
+                               const double* dNdxi, const double* M, const double* dMdxi, const double* w, fb2_cv** out);
+int fb2_cellvalues_info(fb2_cv* cv, int* nq, int* nbase_scalar, int* vdim, int* ngeo, int* rdim);
+int fb2_cellvalues_export(fb2_cv* cv, double* N, double* dNdxi, double* M, double* dMdxi, double* w, double* points);
+int fb2_cellvalues_destroy(fb2_cv* cv);
+
+/* ---- assembler: start_assemble / assemble! / finish_assemble ---------------------------- */
+/* start_assemble(K, f) (src/assembler.jl:287-291) for the whole cell loop: builds the
+ * cell-local -> nzval index map (replaces the per-cell sort + merge walk of _assemble_inner!,
+ * src/assembler.jl:347-457) and, for FB2_SCATTER_COLORED, create_coloring (src/Grid/coloring.jl:308-317). */
+int fb2_assembler_create(fb2_dh* dh, fb2_pattern* p, fb2_cv* cv, fb2_assembler** out);
+/* the whole `for cell in CellIterator(dh) ... assemble!(assembler, celldofs(cell), Ke, fe)` loop
+ * (docs/src/literate-tutorials/heat_equation.jl:181-204; src/iterators.jl:72-93; src/FEValues/CellValues.jl:122-140)
+ * nzval_dev (nnz) and f_dev (ndofs, nullable) are device pointers; u_dev (ndofs, nullable) is the
+ * current solution for nonlinear elements. */
+int fb2_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
+                 double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
+/* same call with HOST buffers: uploads u (if any), assembles into library-owned device buffers and
+ * downloads nzval/f into the caller's SparseMatrixCSC.nzval / f vectors */
+int fb2_assemble_host(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_host,
+                      double* nzval_host, double* f_host, const fb2_asm_opts* opts);
+/* create_coloring(grid): number of colours and, optionally, the colour of every cell (0-based colour ids) */
+int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color);
+/* scatter-only entry: assemble!(assembler, dofs, Ke, fe) for a batch of precomputed element matrices
+ * (Ke: n x n x ncells column-major, fe: n x ncells, host) -- src/assembler.jl:322-331 */
+int fb2_scatter_host(fb2_assembler* a, const double* Ke, const double* fe, double* nzval_dev, double* f_dev,
+                     const fb2_asm_opts* opts);
+int fb2_assembler_destroy(fb2_assembler* a);
+
+/* ---- ConstraintHandler: Dirichlet / close! / update! / apply! ---------------------------- */
+int fb2_ch_create(fb2_dh* dh, fb2_ch** out);
+/* add!(ch, Dirichlet(field, set, f, components)): src/Dofs/ConstraintHandler.jl:965-1008,404-493.
+ * entities: 2 x n (cell, local entity) for FB2_BC_FACET/FACE/EDGE/VERTEX, or n node ids for FB2_BC_NODE;
+ * components: 1-based, sorted; ncomponents = 0 means all. Returns the index of the condition in *ibc. */
+int fb2_ch_add_dirichlet(fb2_ch* ch, int field, int kind, int64_t n, const int64_t* entities, int ncomponents,
+                         const int* components, int* ibc);
+/* close!(ch): src/Dofs/ConstraintHandler.jl:303-361 (sorts prescribed dofs, builds isconstrained) */
+int fb2_ch_close(fb2_ch* ch);
+/* arrays-in mode: adopt a closed reference ConstraintHandler (ch.prescribed_dofs sorted, ch.inhomogeneities),
+ * src/Dofs/ConstraintHandler.jl:160-162 */
+int fb2_ch_from_host(fb2_dh* dh, int64_t n, const int64_t* prescribed_dofs, const double* inhomogeneities, fb2_ch** out);
+/* update!(ch, t) (src/Dofs/ConstraintHandler.jl:504-580) is split around the user's Julia function f(x,t):
+ * fb2_ch_bc_points returns the dof locations x (sdim x npoints) of condition ibc in the reference's
+ * evaluation order (BCValues, src/FEValues/FacetValues.jl:185-236); the caller evaluates f and hands the
+ * values (ncomponents x npoints) to fb2_ch_bc_set_values. */
+int fb2_ch_bc_points(fb2_ch* ch, int ibc, int64_t* npoints, double* x);
+int fb2_ch_bc_set_values(fb2_ch* ch, int ibc, int64_t npoints, const double* values);
+int fb2_ch_info(fb2_ch* ch, int64_t* nprescribed);
+int fb2_ch_export(fb2_ch* ch, int64_t* prescribed_dofs, double* inhomogeneities);
+/* apply!(K, f, ch) / apply_zero!(K, f, ch): src/Dofs/ConstraintHandler.jl:710-740,755-768,931-958.
+ * f_dev may be NULL (apply!(K, ch)). *meandiag (nullable) receives the mean |diagonal| used. */
+int fb2_apply(fb2_ch* ch, fb2_pattern* p, double* nzval_dev, double* f_dev, int applyzero, double* meandiag);
+/* apply!(u, ch) / apply_zero!(u, ch): src/Dofs/ConstraintHandler.jl:686-700 */
+int fb2_apply_vector(fb2_ch* ch, double* u_dev, int applyzero);
+int fb2_ch_destroy(fb2_ch* ch);
+
+/* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
+typedef struct fb2_part fb2_part;
+/* Partition the cells of `grid` into nparts blocks (structured generate_grid input: px*py*pz blocks;
+ * otherwise contiguous cell ranges) and describe rank `rank`: its cells, the dofs it owns (lowest rank
+ * touching a dof owns it) and the interface columns it must exchange.  Host logic only. */
+int fb2_partition_create(fb2_dh* dh, fb2_pattern* p, int nparts, int rank, fb2_part** out);
+int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncols_owned, int64_t* nnz_send, int64_t* nnz_recv);
+/* cell ids (0-based) of this rank, for tests */
+int fb2_partition_cells(fb2_part* part, int64_t* cells);
+/* per-peer exchange plan: number of nz values (and f values) sent to / received from `peer` */
+int fb2_partition_peer_counts(fb2_part* part, int peer, int64_t* nz_send, int64_t* f_send, int64_t* nz_recv, int64_t* f_recv);
+/* restrict an assembler to the cells of this partition */
+int fb2_assembler_set_partition(fb2_assembler* a, fb2_part* part);
+/* pack the partial sums this rank holds for columns owned by `peer` into send_dev (nz values then f values) */
+int fb2_partition_pack(fb2_part* part, int peer, const double* nzval_dev, const double* f_dev, double* send_dev);
+/* add the partial sums received from `peer` into the owned columns */
+int fb2_partition_unpack_add(fb2_part* part, int peer, const double* recv_dev, double* nzval_dev, double* f_dev);
+/* zero every entry of nzval/f this rank does not own (after the exchange the owned part is final) */
+int fb2_partition_mask_unowned(fb2_part* part, double* nzval_dev, double* f_dev);
+int fb2_partition_destroy(fb2_part* part);
+
+/* NCCL exchange driven by the library: unique id bootstrap is done by the caller (e.g. broadcast over
+ * torch.distributed); afterwards fb2_assemble_distributed = assemble local cells + pack + grouped
+ * ncclSend/ncclRecv + unpack-add on the context's stream. */
+int fb2_comm_unique_id(void* id128 /* 128 bytes out */);
+int fb2_comm_init_rank(fb2_ctx* ctx, const void* id128, int nranks, int rank);
+int fb2_comm_destroy(fb2_ctx* ctx);
+int fb2_assemble_distributed(fb2_assembler* a, fb2_part* part, int element, const void* params, size_t params_bytes,
+                             const double* u_dev, double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERRITE_B200_H */

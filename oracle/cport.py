@@ -1,0 +1,101 @@
+"""Build + call the C restatement of the reference loop (oracle/cpu_assemble.c).
+
+TEST INFRASTRUCTURE ONLY (tests, smoke, and the cpu_baseline / --impl reference legs of bench.py).
+The shared object is compiled with -march=native, so it is rebuilt whenever the host CPU differs from
+the one it was built on (the GPU box is not the build container).
+"""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "cpu_assemble.c")
+_lib = None
+
+
+def _cpu_tag():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force=False):
+    """Compile oracle/cpu_assemble.c -> oracle/_build/liboracle_cpu.so (or a temp dir if not writable)."""
+    out_dir = os.path.join(_HERE, "_build")
+    so = os.path.join(out_dir, "liboracle_cpu.so")
+    tag = os.path.join(out_dir, "cpu.tag")
+    if not force and os.path.exists(so) and os.path.exists(tag) and open(tag).read() == _cpu_tag():
+        return so
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        test = os.path.join(out_dir, ".w")
+        open(test, "w").close()
+        os.remove(test)
+    except OSError:
+        out_dir = tempfile.mkdtemp(prefix="oracle_cpu_")
+        so = os.path.join(out_dir, "liboracle_cpu.so")
+        tag = os.path.join(out_dir, "cpu.tag")
+    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", so, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    with open(tag, "w") as fh:
+        fh.write(_cpu_tag())
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_assemble.restype = C.c_int64
+        _lib.oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+def max_threads():
+    return lib().oracle_max_threads()
+
+
+def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0):
+    """Same contract as oracle.assemble_global, executed by the C port with `nthreads` OpenMP threads."""
+    grid = dh.grid
+    n = dh.ndofs_per_cell
+    assert n == cv.nbase
+    if element == "heat":
+        p = dict(k=1.0, source=1.0)
+        p.update(params or {})
+        eid, pv = 1, np.array([p["k"], p["source"]])
+    elif element == "elasticity":
+        b = list((params or {}).get("b") or (0.0,) * cv.vdim) + [0.0, 0.0, 0.0]
+        eid, pv = 3, np.array([params["lambda"], params["mu"]] + b[:3])
+    else:
+        raise ValueError(element)
+    cells = np.ascontiguousarray(grid.cells, dtype=np.int64)
+    xyz = np.ascontiguousarray(grid.nodes, dtype=np.float64)
+    cd = np.ascontiguousarray(dh.cell_dofs, dtype=np.int64)
+    N = np.ascontiguousarray(cv.N)
+    dN = np.ascontiguousarray(cv.dNdxi)
+    dM = np.ascontiguousarray(cv.dMdxi)
+    w = np.ascontiguousarray(cv.w)
+    K.nzval[:] = 0.0
+    if f is not None:
+        f[:] = 0.0
+
+    def ptr(a, t):
+        return a.ctypes.data_as(C.POINTER(t))
+    bad = lib().oracle_assemble(
+        C.c_int(eid), C.c_int(grid.sdim), C.c_int(cells.shape[1]), C.c_int(cv.base.nbase), C.c_int(cv.vdim), C.c_int(cv.nq),
+        C.c_int64(grid.ncells), ptr(cells, C.c_int64), ptr(xyz, C.c_double), ptr(cd, C.c_int64),
+        ptr(K.colptr, C.c_int64), ptr(K.rowval, C.c_int64), ptr(N, C.c_double), ptr(dN, C.c_double), ptr(dM, C.c_double),
+        ptr(w, C.c_double), ptr(pv, C.c_double), ptr(K.nzval, C.c_double),
+        ptr(f, C.c_double) if f is not None else None, C.c_int(nthreads))
+    if bad:
+        raise ArithmeticError(f"det(J) is not positive in cell {bad}")
+    return K, f

@@ -47,12 +47,13 @@ def allocate_matrix(dh, chunk=1 << 22):
     n = dh.ndofs
     cd = dh.cell_dofs - 1
     ncells, ndpc = cd.shape
-    uniq = np.arange(n, dtype=np.int64) * n + np.arange(n, dtype=np.int64)   # diagonal
+    parts = [np.arange(n, dtype=np.int64) * n + np.arange(n, dtype=np.int64)]   # diagonal
     per = max(1, chunk // (ndpc * ndpc))
     for s in range(0, ncells, per):
         c = cd[s:s + per]
         keys = (c[:, None, :] * n + c[:, :, None]).ravel()   # col*n + row
-        uniq = np.union1d(uniq, keys)
+        parts.append(np.unique(keys))
+    uniq = np.unique(np.concatenate(parts))
     cols = uniq // n
     rows = uniq % n
     colptr = np.zeros(n + 1, dtype=np.int64)

@@ -1,0 +1,217 @@
+"""CPU-side tests of the C ABI (no GPU): the library loads, exports every declared symbol, fails loudly
+without a device, and its host logic (grid generation, dof numbering, Dirichlet set-up, quadrature and
+shape tables) is bit-identical to the oracle / the reference's literal goldens."""
+import numpy as np
+import pytest
+
+import ferrite_b200 as fb
+import oracle as O
+
+SHAPE = {fb.Line: "line", fb.Triangle: "triangle", fb.Quadrilateral: "quadrilateral",
+         fb.Tetrahedron: "tetrahedron", fb.Hexahedron: "hexahedron"}
+
+
+@pytest.fixture(scope="module")
+def hctx():
+    return fb.Context(-1)
+
+
+def test_library_exports_every_declared_symbol():
+    syms = fb.declared_symbols()
+    assert len(syms) >= 60
+    missing = [s for s in syms if not hasattr(fb.lib, s)]
+    assert missing == []
+
+
+def test_no_cpu_fallback(hctx):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(fb.FB2Error) as e:
+        fb.Context(0, use_torch_stream=False)
+    assert "no CPU fallback" in str(e.value)
+    g = fb.generate_grid(fb.Quadrilateral, (2, 2), ctx=hctx)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefQuadrilateral, 1)))
+    with pytest.raises(fb.FB2Error) as e:
+        fb.allocate_matrix(dh)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("ct,nel,left,right", [
+    (fb.Line, (5,), None, None),
+    (fb.Quadrilateral, (4, 3), None, None),
+    (fb.Quadrilateral, (7, 5), (0.0, -2.0), (3.0, 0.5)),
+    (fb.Triangle, (3, 4), None, None),
+    (fb.Hexahedron, (3, 2, 4), None, None),
+    (fb.Hexahedron, (5, 4, 3), (0.1, 0.2, 0.3), (1.7, 0.9, 2.2)),
+    (fb.Tetrahedron, (2, 3, 2), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)),
+])
+def test_generate_grid_matches_oracle(hctx, ct, nel, left, right):
+    g = fb.generate_grid(ct, nel, left, right, ctx=hctx)
+    og = O.generate_grid(SHAPE[ct], nel, left, right)
+    assert np.array_equal(g.cells, og.cells)
+    assert np.array_equal(g.nodes, og.nodes)          # same formula, same operation order: bit-identical
+    for name, pairs in og.facetsets.items():
+        assert np.array_equal(fb.getfacetset(g, name), pairs), name
+
+
+def test_perturb_matches_oracle(hctx):
+    nel, left, right = (4, 3, 5), (0.0, 0.0, 0.0), (1.0, 2.0, 3.0)
+    g = fb.generate_grid(fb.Hexahedron, nel, left, right, ctx=hctx).perturb(0.2)
+    og = O.perturb_grid(O.generate_grid("hexahedron", nel, left, right), nel, left, right, 0.2)
+    assert np.array_equal(g.nodes, og.nodes)
+    assert not np.array_equal(og.nodes, O.generate_grid("hexahedron", nel, left, right).nodes)
+
+
+FIELDSETS = [
+    (fb.Quadrilateral, (5, 4), [("u", 1, 1)]),
+    (fb.Quadrilateral, (5, 4), [("u", 2, 1)]),
+    (fb.Quadrilateral, (3, 3), [("v", 2, 2), ("s", 1, 1)]),
+    (fb.Triangle, (4, 3), [("u", 2, 2), ("p", 1, 1)]),
+    (fb.Hexahedron, (3, 3, 2), [("u", 1, 1)]),
+    (fb.Hexahedron, (3, 2, 2), [("u", 1, 3)]),
+    (fb.Hexahedron, (3, 2, 3), [("u", 2, 3)]),
+    (fb.Hexahedron, (2, 2, 2), [("u", 2, 3), ("p", 1, 1)]),
+    (fb.Tetrahedron, (2, 2, 3), [("u", 1, 3)]),
+    (fb.Tetrahedron, (3, 2, 2), [("u", 2, 3)]),
+    (fb.Tetrahedron, (2, 2, 2), [("u", 2, 3), ("p", 1, 1)]),
+]
+
+
+def _both_dh(hctx, ct, nel, fields):
+    g = fb.generate_grid(ct, nel, ctx=hctx)
+    dh = fb.DofHandler(g)
+    og = O.generate_grid(SHAPE[ct], nel)
+    odh = O.DofHandler(og)
+    for name, order, vdim in fields:
+        fb.add_(dh, name, fb.Lagrange(ct, order) ** vdim)
+        odh.add(name, O.Lagrange(SHAPE[ct], order) ** vdim if vdim > 1 else O.Lagrange(SHAPE[ct], order))
+    fb.close_(dh)
+    odh.close()
+    return g, dh, og, odh
+
+
+@pytest.mark.parametrize("ct,nel,fields", FIELDSETS)
+def test_dof_numbering_bit_exact(hctx, ct, nel, fields):
+    g, dh, og, odh = _both_dh(hctx, ct, nel, fields)
+    assert dh.ndofs == odh.ndofs
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    for name, _, _ in fields:
+        r = fb.dof_range(dh, name)
+        assert (r[0], r[-1]) == odh.dof_range(name)
+
+
+def test_dof_goldens_through_cabi(hctx):
+    # test/test_dofs.jl:95-126 (shell quads) and :235-257 (two fields on 2x1 quads)
+    nodes = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [2, 0, 0], [2, 2, 0]], dtype=float)
+    g = fb.Grid.from_arrays(fb.Quadrilateral, [(1, 2, 3, 4), (2, 5, 6, 3)], nodes, ctx=hctx)
+    q1, q2 = fb.Lagrange(fb.RefQuadrilateral, 1), fb.Lagrange(fb.RefQuadrilateral, 2)
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "u", q1 ** 3), "th", q1 ** 3))
+    assert list(fb.celldofs(dh, 1)) == list(range(1, 25))
+    assert list(fb.celldofs(dh, 2)) == [4, 5, 6, 25, 26, 27, 28, 29, 30, 7, 8, 9, 16, 17, 18, 31, 32, 33, 34, 35, 36, 19, 20, 21]
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "u", q2), "th", q2))
+    assert list(fb.celldofs(dh, 1)) == list(range(1, 19))
+    assert list(fb.celldofs(dh, 2)) == [2, 19, 20, 3, 21, 22, 23, 6, 24, 11, 25, 26, 12, 27, 28, 29, 15, 30]
+    # edge bc on the shell: test/test_constraints.jl:175-200
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("th", [(1, 1), (2, 1)], lambda x, t: 0.0, [1], kind="edge"))
+    fb.close_(ch)
+    assert list(ch.prescribed_dofs) == [10, 11, 14, 25, 27]
+
+    g = fb.generate_grid(fb.Quadrilateral, (2, 1), ctx=hctx)
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "v", q1 ** 2), "s", q1))
+    assert list(fb.celldofs(dh, 1)) == list(range(1, 13))
+    assert list(fb.celldofs(dh, 2)) == [3, 4, 13, 14, 15, 16, 5, 6, 10, 17, 18, 11]
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("v", fb.getfacetset(g, "left"), lambda x, t: 0, [2]))
+    fb.add_(ch, fb.Dirichlet("s", fb.getfacetset(g, "left"), lambda x, t: 0))
+    fb.close_(ch)
+    assert list(ch.prescribed_dofs) == [2, 8, 9, 12]
+
+
+def test_constraint_goldens_through_cabi(hctx):
+    # test/test_constraints.jl:84-101 (node sets) and :155-172 (edge set on a hex)
+    g = fb.generate_grid(fb.Triangle, (1, 1), ctx=hctx)
+    nodeset = [i + 1 for i, x in enumerate(g.nodes) if x[1] == -1 or x[0] == -1]
+    p1 = fb.Lagrange(fb.RefTriangle, 1)
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "u", p1 ** 2), "p", p1))
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", nodeset, lambda x, t: x, [1, 2], kind="node"))
+    fb.add_(ch, fb.Dirichlet("p", nodeset, lambda x, t: 0, 1, kind="node"))
+    fb.close_(ch)
+    assert list(ch.prescribed_dofs) == list(range(1, 10))
+    assert list(ch.inhomogeneities) == [-1, -1, 1, -1, -1, 1, 0, 0, 0]
+
+    g = fb.generate_grid(fb.Hexahedron, (1, 1, 1), ctx=hctx)
+    h1 = fb.Lagrange(fb.RefHexahedron, 1)
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "u", h1 ** 3), "p", h1))
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", [(1, 4)], lambda x, t: x, [1, 2, 3], kind="edge"))
+    fb.close_(ch)
+    assert list(ch.prescribed_dofs) == [1, 2, 3, 10, 11, 12]
+    assert list(ch.inhomogeneities) == [-1.0, -1.0, -1.0, -1.0, 1.0, -1.0]
+
+
+@pytest.mark.parametrize("ct,nel,fields", [f for f in FIELDSETS if f[0] != fb.Line])
+def test_dirichlet_matches_oracle(hctx, ct, nel, fields):
+    g, dh, og, odh = _both_dh(hctx, ct, nel, fields)
+    ch, och = fb.ConstraintHandler(dh), O.ConstraintHandler(odh)
+    names = sorted(og.facetsets)
+    name, order, vdim = fields[0]
+
+    def f1(x, t):
+        return [np.sin(x[0] + 0.3 * k) + t + x[-1] for k in range(vdim)]
+
+    def f2(x, t):
+        return 0.25 * x[0] - x[1]
+    fb.add_(ch, fb.Dirichlet(name, fb.getfacetset(g, names[0]), f1))
+    och.add(O.Dirichlet(name, og.facetsets[names[0]], f1))
+    # overlapping second condition on one component: later conditions override earlier ones
+    both = np.concatenate([og.facetsets[names[0]][:2], og.facetsets[names[1]]])
+    fb.add_(ch, fb.Dirichlet(name, both, f2, [1]))
+    och.add(O.Dirichlet(name, both, f2, [1]))
+    fb.close_(ch)
+    och.close()
+    assert np.array_equal(ch.prescribed_dofs, och.prescribed_dofs)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+    fb.update_(ch, 1.5)
+    och.update(1.5)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+
+
+@pytest.mark.parametrize("ct,qo,io,vdim", [
+    (fb.Quadrilateral, 2, 1, 1), (fb.Quadrilateral, 3, 2, 2), (fb.Triangle, 2, 2, 1), (fb.Triangle, 1, 1, 2),
+    (fb.Hexahedron, 2, 1, 1), (fb.Hexahedron, 3, 2, 3), (fb.Tetrahedron, 2, 1, 3), (fb.Tetrahedron, 4, 2, 3),
+    (fb.Tetrahedron, 3, 2, 1), (fb.Hexahedron, 4, 2, 1),
+])
+def test_cellvalues_tables_match_oracle(hctx, ct, qo, io, vdim):
+    cv = fb.CellValues(fb.QuadratureRule(ct, qo), fb.Lagrange(ct, io) ** vdim, ctx=hctx)
+    t = cv.tables()
+    oip = O.Lagrange(SHAPE[ct], io)
+    ocv = O.CellValues(O.QuadratureRule(SHAPE[ct], qo), oip ** vdim if vdim > 1 else oip)
+    assert cv.nq == ocv.nq and cv.nbase_scalar == oip.nbase
+    # Gauss points come from two independent generators (Newton vs numpy's eigen-solve): ~1 ulp apart
+    assert np.allclose(t["w"], ocv.w, rtol=1e-14, atol=0)
+    assert np.allclose(t["points"], ocv.qr.points, rtol=1e-14, atol=1e-16)
+    assert np.allclose(t["N"], ocv.N, rtol=1e-13, atol=1e-15)
+    assert np.allclose(t["dNdxi"], ocv.dNdxi, rtol=1e-13, atol=1e-15)
+    assert np.allclose(t["M"], ocv.M, rtol=1e-13, atol=1e-15)
+    assert np.allclose(t["dMdxi"], ocv.dMdxi, rtol=1e-13, atol=1e-15)
+
+
+def test_bad_arguments_are_reported(hctx):
+    with pytest.raises(fb.FB2Error):
+        fb.generate_grid(fb.Quadrilateral, (0, 2), ctx=hctx)
+    with pytest.raises(fb.FB2Error):
+        fb.Grid.from_arrays(fb.Quadrilateral, [(1, 2, 3, 9)], np.zeros((4, 2)), ctx=hctx)
+    g = fb.generate_grid(fb.Quadrilateral, (2, 2), ctx=hctx)
+    with pytest.raises(fb.FB2Error):
+        fb.getfacetset(g, "nope")
+    with pytest.raises(fb.FB2Error):
+        fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefQuadrilateral, 3)))
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefQuadrilateral, 1) ** 2))
+    ch = fb.ConstraintHandler(dh)
+    with pytest.raises(fb.FB2Error):
+        fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: 0, [3]))
+    with pytest.raises(fb.FB2Error):
+        fb.ConstraintHandler.from_arrays(dh, [3, 2], [0.0, 0.0])

@@ -1,0 +1,434 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): dof numbering, colptr and rowval bit-exact; nzval / f within 1e-12
+relative in FP64 (atomic summation order).  Entry-wise relative error is ill-defined where K is
+analytically zero (e.g. edge-adjacent entries of the trilinear Laplacian), so the entry-wise check is
+|a-b| <= RTOL*max(|a|,|b|) + RTOL*max|a| and the norm-wise error is checked as well.
+"""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import ferrite_b200 as fb
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+SHAPE = {fb.Triangle: "triangle", fb.Quadrilateral: "quadrilateral", fb.Tetrahedron: "tetrahedron",
+         fb.Hexahedron: "hexahedron", fb.Line: "line"}
+
+
+def close(a, b, rtol=RTOL):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.abs(b).max() if b.size else 0.0
+    ok = np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(a), np.abs(b)) + rtol * scale)
+    nrm = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+    return bool(ok and nrm <= rtol), nrm
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return fb.default_context(0)
+
+
+def build(ct, nel, order, vdim, qr_order, perturb=True, left=None, right=None):
+    dim = len(nel)
+    left = left if left is not None else (-1.0,) * dim
+    right = right if right is not None else (1.0,) * dim
+    g = fb.generate_grid(ct, nel, left, right)
+    og = O.generate_grid(SHAPE[ct], nel, left, right)
+    if perturb:
+        g.perturb(0.2)
+        O.perturb_grid(og, nel, left, right, 0.2)
+    ip = fb.Lagrange(ct, order) ** vdim
+    oip = O.Lagrange(SHAPE[ct], order)
+    oip = oip ** vdim if vdim > 1 else oip
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    odh = O.DofHandler(og).add("u", oip).close()
+    cv = fb.CellValues(fb.QuadratureRule(ct, qr_order), ip)
+    ocv = O.CellValues(O.QuadratureRule(SHAPE[ct], qr_order), oip)
+    return g, og, dh, odh, cv, ocv
+
+
+def test_pattern_bit_exact_many(ctx):
+    cases = [
+        (fb.Quadrilateral, (7, 5), 1, 1), (fb.Quadrilateral, (5, 4), 2, 2), (fb.Triangle, (6, 5), 2, 1),
+        (fb.Hexahedron, (5, 4, 3), 1, 1), (fb.Hexahedron, (4, 3, 3), 1, 3), (fb.Hexahedron, (3, 3, 2), 2, 3),
+        (fb.Tetrahedron, (3, 3, 2), 1, 3), (fb.Tetrahedron, (3, 2, 2), 2, 3), (fb.Line, (9,), 2, 1),
+    ]
+    for ct, nel, order, vdim in cases:
+        g = fb.generate_grid(ct, nel)
+        dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, order) ** vdim))
+        K = fb.allocate_matrix(dh)
+        og = O.generate_grid(SHAPE[ct], nel)
+        oip = O.Lagrange(SHAPE[ct], order)
+        odh = O.DofHandler(og).add("u", oip ** vdim if vdim > 1 else oip).close()
+        oK = O.allocate_matrix(odh)
+        assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+        assert K.nnz == oK.nnz, (ct, nel, order, vdim)
+        assert np.array_equal(K.colptr, oK.colptr)
+        assert np.array_equal(K.rowval, oK.rowval)
+
+
+def test_pattern_two_fields_and_from_host(ctx):
+    g = fb.generate_grid(fb.Hexahedron, (3, 2, 2))
+    h1, h2 = fb.Lagrange(fb.RefHexahedron, 1), fb.Lagrange(fb.RefHexahedron, 2)
+    dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "u", h2 ** 3), "p", h1))
+    K = fb.allocate_matrix(dh)
+    og = O.generate_grid("hexahedron", (3, 2, 2))
+    odh = O.DofHandler(og).add("u", O.Lagrange("hexahedron", 2) ** 3).add("p", O.Lagrange("hexahedron", 1)).close()
+    oK = O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    # arrays-in mode round trip
+    K2 = fb.allocate_matrix(dh, oK.colptr, oK.rowval)
+    assert np.array_equal(K2.colptr, oK.colptr) and np.array_equal(K2.rowval, oK.rowval)
+    with pytest.raises(fb.FB2Error):
+        fb.allocate_matrix(dh, oK.colptr, oK.rowval[::-1].copy())
+
+
+ASSEMBLY_CASES = [
+    # (celltype, nel, order, vdim, qr_order, element, oracle params, fb element)
+    ("quad-q1-heat", fb.Quadrilateral, (13, 9), 1, 1, 2, "heat", {"k": 1.3, "source": 0.7}),
+    ("quad-q2-heat", fb.Quadrilateral, (7, 6), 2, 1, 3, "heat", {"k": 1.0, "source": 1.0}),
+    ("tri-p1-heat", fb.Triangle, (9, 8), 1, 1, 1, "heat", {}),
+    ("tri-p2-heat", fb.Triangle, (8, 7), 2, 1, 2, "heat", {}),
+    ("hex-q1-heat", fb.Hexahedron, (9, 8, 7), 1, 1, 2, "heat", {"k": 2.0, "source": 3.0}),
+    ("hex-q2-heat", fb.Hexahedron, (4, 3, 3), 2, 1, 3, "heat", {}),
+    ("tet-p1-heat", fb.Tetrahedron, (4, 4, 3), 1, 1, 2, "heat", {}),
+    ("tet-p2-heat", fb.Tetrahedron, (3, 3, 3), 2, 1, 2, "heat", {}),
+    ("tet-p2-heat-q3", fb.Tetrahedron, (3, 2, 3), 2, 1, 3, "heat", {}),
+    ("hex-q1-mass", fb.Hexahedron, (5, 4, 4), 1, 1, 2, "mass", {"rho": 2.5}),
+    ("quad-q2-mass", fb.Quadrilateral, (5, 5), 2, 1, 3, "mass", {"rho": 1.0}),
+    ("quad-q1-elast", fb.Quadrilateral, (8, 7), 1, 2, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, -1.0)}),
+    ("tri-p2-elast", fb.Triangle, (6, 5), 2, 2, 2, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.5, -1.0)}),
+    ("hex-q1-elast", fb.Hexahedron, (6, 5, 4), 1, 3, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}),
+    ("hex-q2-elast", fb.Hexahedron, (3, 3, 2), 2, 3, 3, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}),
+    ("tet-p1-elast", fb.Tetrahedron, (3, 3, 3), 1, 3, 1, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+    ("tet-p2-elast", fb.Tetrahedron, (3, 2, 2), 2, 3, 4, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+    ("tet-p1-neohooke", fb.Tetrahedron, (3, 3, 3), 1, 3, 1, "neohooke", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+    ("tet-p2-neohooke", fb.Tetrahedron, (3, 2, 2), 2, 3, 4, "neohooke", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+    ("hex-q1-neohooke", fb.Hexahedron, (4, 3, 3), 1, 3, 2, "neohooke", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+]
+
+
+def make_element(kind, p):
+    if kind == "heat":
+        return fb.HeatElement(**p), dict(k=p.get("k", 1.0), source=p.get("source", 1.0))
+    if kind == "mass":
+        return fb.MassElement(**p), dict(p)
+    lam, mu = O.lame(p["E"], p["nu"])
+    cls = fb.ElasticityElement if kind == "elasticity" else fb.NeoHookeElement
+    return cls(lam=lam, mu=mu, b=p["b"]), {"lambda": lam, "mu": mu, "b": p["b"]}
+
+
+def displacement(og, odh, vdim):
+    """Deterministic smooth state u = 0.05 sin(pi x)-type field evaluated at the dofs (config 4)."""
+    u = np.zeros(odh.ndofs)
+    base = odh.field_ips[0].base
+    geo = O.Lagrange(og.shape, 1)
+    for ci in range(og.ncells):
+        xc = og.nodes[og.cells[ci] - 1]
+        for a in range(base.nbase):
+            M, _ = geo.value_and_gradient(base.refcoords[a])
+            x = M @ xc
+            for c in range(vdim):
+                u[odh.cell_dofs[ci, a * vdim + c] - 1] = 0.05 * np.sin(np.pi * x[c] + 0.3 * c) * np.cos(0.5 * x[(c + 1) % len(x)])
+    return u
+
+
+@pytest.mark.parametrize("case", ASSEMBLY_CASES, ids=[c[0] for c in ASSEMBLY_CASES])
+@pytest.mark.parametrize("scatter", ["atomic", "colored"])
+def test_assembly_matches_oracle(ctx, case, scatter):
+    _, ct, nel, order, vdim, qo, kind, p = case
+    left = (0.0,) * len(nel) if kind == "neohooke" else None
+    right = (1.0,) * len(nel) if kind == "neohooke" else None
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo, True, left, right)
+    elem, op = make_element(kind, p)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    u = ou = None
+    if kind == "neohooke":
+        import torch
+        ou = displacement(og, odh, vdim)
+        u = torch.from_numpy(ou).to(f.device)
+    O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
+    variants = [0, 1] if kind in ("heat", "mass") else [0]
+    for variant in variants:
+        a = fb.start_assemble(K, f, scatter=scatter)
+        a.variant = variant
+        K.nzval.fill_(123.0)      # start_assemble must zero-fill
+        f.fill_(-7.0)
+        fb.assemble_(a, elem, cv, u=u)
+        fb.finish_assemble(a)
+        ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+        assert ok, f"nzval mismatch (variant {variant}): norm-wise {nrm:.3e}"
+        if kind != "mass":
+            ok, nrm = close(f.cpu().numpy(), of)
+            assert ok, f"f mismatch (variant {variant}): norm-wise {nrm:.3e}"
+
+
+def test_colored_is_bitwise_reproducible_and_coloring_valid(ctx):
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (7, 6, 5), 1, 1, 2)
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    a = fb.start_assemble(K, f, scatter="colored")
+    ncol, col = a.coloring(cv)
+    assert 8 <= ncol <= 16
+    # validity: no two cells of one colour share a node (src/Grid/coloring.jl)
+    cells = g.cells
+    for c in range(ncol):
+        nodes = cells[col == c].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
+    runs = []
+    for _ in range(3):
+        fb.assemble_(a, fb.HeatElement(), cv)
+        fb.finish_assemble(a)
+        runs.append((K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()))
+    assert all(np.array_equal(runs[0][0], r[0]) and np.array_equal(runs[0][1], r[1]) for r in runs[1:])
+
+
+def test_fillzero_false_accumulates(ctx):
+    g, og, dh, odh, cv, ocv = build(fb.Quadrilateral, (6, 5), 1, 1, 2)
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, fb.HeatElement(), cv)
+    once = K.nzval.clone()
+    a2 = fb.start_assemble(K, f, fillzero=False)
+    fb.assemble_(a2, fb.HeatElement(), cv)
+    fb.finish_assemble(a2)
+    assert np.allclose(K.nzval.cpu().numpy(), 2 * once.cpu().numpy(), rtol=1e-14)
+
+
+def test_host_buffer_entry_point(ctx):
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (6, 5, 4), 1, 1, 2)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    of = np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, "heat")
+    nz = np.full(K.nnz, 9.0)
+    fh = np.full(dh.ndofs, 9.0)
+    a = fb.start_assemble(K, None)
+    fb.assemble_host(a, fb.HeatElement(), cv, nz, fh)
+    assert close(nz, oK.nzval)[0] and close(fh, of)[0]
+
+
+def test_arrays_in_mode_matches_native(ctx):
+    """Arrays-in entry mode: grid, cell_dofs, pattern, tables and constraints supplied by the caller
+    (here: by the oracle standing in for Ferrite.jl) give the same matrix as the native mode."""
+    nel = (5, 4, 3)
+    og = O.perturb_grid(O.generate_grid("hexahedron", nel), nel, (-1,) * 3, (1,) * 3, 0.2)
+    oip = O.Lagrange("hexahedron", 1) ** 3
+    odh = O.DofHandler(og).add("u", oip).close()
+    oK = O.allocate_matrix(odh)
+    ocv = O.CellValues(O.QuadratureRule("hexahedron", 2), oip)
+    g = fb.Grid.from_arrays(fb.Hexahedron, og.cells, og.nodes)
+    ip = fb.Lagrange(fb.RefHexahedron, 1) ** 3
+    dh = fb.DofHandler.from_arrays(g, [("u", ip)], odh.ndofs, odh.cell_dofs)
+    K = fb.allocate_matrix(dh, oK.colptr, oK.rowval)
+    cv = fb.CellValues(None, ip, tables=(ocv.N, ocv.dNdxi, ocv.M, ocv.dMdxi, ocv.w))
+    f = ctx.zeros(dh.ndofs)
+    lam, mu = O.lame(200e9, 0.3)
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, fb.ElasticityElement(lam=lam, mu=mu, b=(0, 0, -1.0)), cv)
+    fb.finish_assemble(a)
+    of = np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, "elasticity", {"lambda": lam, "mu": mu, "b": (0, 0, -1.0)})
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0]
+    assert close(f.cpu().numpy(), of)[0]
+    # constraints adopted from arrays + apply on a pattern that is not flagged structurally symmetric
+    och = O.ConstraintHandler(odh)
+    och.add(O.Dirichlet("u", og.facetsets["left"], lambda x, t: (0.0, 0.0, 0.0)))
+    och.add(O.Dirichlet("u", og.facetsets["right"], lambda x, t: (0.0, 0.0, 0.01 * x[1]), [1, 2, 3]))
+    och.close()
+    ch = fb.ConstraintHandler.from_arrays(dh, och.prescribed_dofs, och.inhomogeneities)
+    m = fb.apply_(K, f, ch)
+    om = och.apply(oK, of)
+    assert abs(m - om) <= 1e-13 * abs(om)
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0]
+    assert close(f.cpu().numpy(), of)[0]
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,p", [
+    (fb.Quadrilateral, (9, 8), 1, 1, 2, "heat", {}),
+    (fb.Hexahedron, (5, 4, 4), 1, 3, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}),
+    (fb.Hexahedron, (3, 2, 2), 2, 3, 3, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}),
+    (fb.Tetrahedron, (3, 3, 2), 2, 1, 2, "heat", {}),
+])
+@pytest.mark.parametrize("applyzero", [False, True])
+def test_apply_dirichlet_matches_oracle(ctx, ct, nel, order, vdim, qo, kind, p, applyzero):
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    elem, op = make_element(kind, p)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    fb.assemble_(fb.start_assemble(K, f), elem, cv)
+    O.assemble_global(odh, ocv, oK, of, kind, op)
+
+    def val(x, t):
+        return [0.01 * x[1] + 0.02 * k + t for k in range(vdim)] if vdim > 1 else 0.3 * x[0] - x[1]
+    ch, och = fb.ConstraintHandler(dh), O.ConstraintHandler(odh)
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: [0.0] * vdim if vdim > 1 else 0.0))
+    och.add(O.Dirichlet("u", og.facetsets["left"], lambda x, t: [0.0] * vdim if vdim > 1 else 0.0))
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "right"), val))
+    och.add(O.Dirichlet("u", og.facetsets["right"], val))
+    fb.close_(ch)
+    och.close()
+    fb.update_(ch, 0.5)
+    och.update(0.5)
+    assert np.array_equal(ch.prescribed_dofs, och.prescribed_dofs)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+    m = fb.apply_(K, f, ch, applyzero=applyzero)
+    om = och.apply(oK, of, applyzero=applyzero)
+    assert abs(m - om) <= 1e-13 * abs(om)
+    ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+    assert ok, nrm
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, nrm
+    # apply!(u, ch)
+    u = ctx.zeros(dh.ndofs)
+    fb.apply_(u, ch)
+    ou = och.apply_vec(np.zeros(odh.ndofs))
+    assert np.array_equal(u.cpu().numpy(), ou)
+
+
+def test_kat_assemble_and_apply_literal(ctx):
+    # test/test_assembler_extensions.jl:44-86 through the scatter-only entry point
+    g = fb.generate_grid(fb.Line, (2,))
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefLine, 1)))
+    K = fb.allocate_matrix(dh)
+    assert list(K.colptr) == [1, 3, 6, 8] and list(K.rowval) == [1, 2, 1, 2, 3, 2, 3]
+    f = ctx.zeros(3)
+    ke = np.array([[-1.0, 1.0], [2.0, -1.0]])
+    fe = np.array([1.0, 2.0])
+    # the reference test scatters cell 2 with dofs [3, 2]; our cell_dofs are [2, 3] -> permute ke/fe accordingly
+    P = np.array([1, 0])
+    a = fb.start_assemble(K, f)
+    fb.scatter_(a, np.stack([ke, ke[np.ix_(P, P)]]), np.stack([fe, fe[P]]))
+    fb.finish_assemble(a)
+    assert np.allclose(K.tocsc().toarray(), [[-1, 1, 0], [2, -2, 2], [0, 1, -1]], rtol=1e-15)
+    assert np.allclose(f.cpu().numpy(), [1.0, 4.0, 1.0], rtol=1e-15)
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: 1))
+    fb.close_(ch)
+    fb.apply_(K, f, ch)
+    assert np.allclose(K.tocsc().toarray(), [[4 / 3, 0, 0], [0, -2, 2], [0, 1, -1]], rtol=1e-15)
+    assert np.allclose(f.cpu().numpy(), [4 / 3, 2.0, 1.0], rtol=1e-15)
+
+
+def test_scatter_fake_element_golden(ctx):
+    # test/test_assemble.jl:304-357: Ke[i,j] = sin(d_i d_j / 100), fe[i] = cos(d_i) on Q2 10x10 quads
+    g = fb.generate_grid(fb.Quadrilateral, (10, 10))
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefQuadrilateral, 2)))
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    cd = dh.cell_dofs.astype(np.float64)
+    Ke = np.sin(cd[:, :, None] * cd[:, None, :] / 100)
+    fe = np.cos(cd)
+    a = fb.start_assemble(K, f)
+    fb.scatter_(a, Ke, fe)
+    fb.finish_assemble(a)
+    og = O.generate_grid("quadrilateral", (10, 10))
+    odh = O.DofHandler(og).add("u", O.Lagrange("quadrilateral", 2)).close()
+    oK = O.allocate_matrix(odh)
+    of = np.zeros(odh.ndofs)
+    for c in range(og.ncells):
+        O.assemble_cell(oK, of, odh.cell_dofs[c], Ke[c], fe[c])
+    assert np.allclose(K.nzval.cpu().numpy(), oK.nzval, rtol=1e-14, atol=0)     # the reference's own tolerance
+    assert np.allclose(f.cpu().numpy(), of, rtol=1e-14, atol=1e-14)
+
+
+def test_missing_entry_and_zero_skip(ctx):
+    # test/test_assemble.jl:171-214: zeros aimed at missing entries are skipped, non-zeros are an error
+    g = fb.generate_grid(fb.Line, (3,))
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefLine, 1)))
+    # a pattern without the off-diagonal couplings
+    n = dh.ndofs
+    K = fb.allocate_matrix(dh, np.arange(1, n + 2), np.arange(1, n + 1))
+    a = fb.start_assemble(K, None)
+    Ke = np.zeros((3, 2, 2))
+    Ke[:, 0, 0] = Ke[:, 1, 1] = 1.0
+    fb.scatter_(a, Ke)
+    assert np.allclose(K.nzval.cpu().numpy(), [1, 2, 2, 1])
+    Ke[1, 0, 1] = 5.0
+    with pytest.raises(fb.MissingPatternEntry):
+        fb.scatter_(a, Ke)
+
+
+def test_detj_not_positive_is_reported(ctx):
+    og = O.generate_grid("hexahedron", (3, 3, 3))
+    cells = og.cells.copy()
+    cells[7] = cells[7][[1, 0, 3, 2, 5, 4, 7, 6]]      # mirror one cell -> negative Jacobian
+    g = fb.Grid.from_arrays(fb.Hexahedron, cells, og.nodes)
+    ip = fb.Lagrange(fb.RefHexahedron, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    K = fb.allocate_matrix(dh)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, 2), ip)
+    a = fb.start_assemble(K, ctx.zeros(dh.ndofs))
+    fb.assemble_(a, fb.HeatElement(), cv)
+    with pytest.raises(fb.DetJNotPositive) as e:
+        fb.finish_assemble(a)
+    assert "cell 8" in str(e.value)
+
+
+def test_goldens_through_the_gpu_path(ctx):
+    # docs/src/topics/assembly.md:348-356
+    g = fb.generate_grid(fb.Triangle, (100, 100))
+    ip = fb.Lagrange(fb.RefTriangle, 2)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    assert dh.ndofs == 40401
+    K = fb.allocate_matrix(dh)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefTriangle, 2), ip)
+    fb.assemble_(fb.start_assemble(K, None), fb.HeatElement(), cv)
+    ref = 1138.8803468514259
+    assert abs(float(K.nzval.norm()) - ref) / ref < 1e-13
+    # docs/src/literate-tutorials/heat_equation.jl:59-114,181-234
+    g = fb.generate_grid(fb.Quadrilateral, (20, 20))
+    ip = fb.Lagrange(fb.RefQuadrilateral, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip)
+    ch = fb.ConstraintHandler(dh)
+    boundary = np.concatenate([fb.getfacetset(g, k) for k in ("left", "right", "top", "bottom")])
+    fb.add_(ch, fb.Dirichlet("u", boundary, lambda x, t: 0))
+    fb.close_(ch)
+    fb.assemble_(fb.start_assemble(K, f), fb.HeatElement(), cv)
+    fb.apply_(K, f, ch)
+    u = spla.spsolve(K.tocsc(), f.cpu().numpy())
+    ref = 3.307743912641305
+    assert abs(np.linalg.norm(u) - ref) / ref < 1e-12
+
+
+def test_full_size_properties_c2_scaled(ctx):
+    """Size-independent properties at a large size the oracle cannot reach quickly: Laplace rows sum to
+    zero, sum(f) = vol(Omega), K symmetric (config 2 at 96^3; bench.py checks the same at 200^3)."""
+    import torch
+    n = 96
+    g = fb.generate_grid(fb.Hexahedron, (n, n, n)).perturb(0.2)
+    ip = fb.Lagrange(fb.RefHexahedron, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    assert dh.ndofs == (n + 1) ** 3
+    K = fb.allocate_matrix(dh)
+    assert K.nnz == (3 * n + 1) ** 3
+    f = ctx.zeros(dh.ndofs)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, 2), ip)
+    fb.assemble_(fb.start_assemble(K, f), fb.HeatElement(), cv)
+    fb.finish_assemble(fb.start_assemble(K, f))
+    assert abs(float(f.sum()) - 8.0) < 1e-11
+    rows = torch.from_numpy(K.rowval - 1).to(f.device)
+    rowsum = torch.zeros_like(f).index_add_(0, rows, K.nzval)
+    assert float(rowsum.abs().max()) < 1e-12 * float(K.nzval.abs().max()) * 27
+    # symmetry via x^T K y == y^T K x on random vectors
+    cols = torch.repeat_interleave(torch.arange(K.n, device=f.device), torch.from_numpy(np.diff(K.colptr)).to(f.device))
+    gen = torch.Generator(device=f.device).manual_seed(0)
+    x = torch.rand(K.n, dtype=torch.float64, device=f.device, generator=gen)
+    y = torch.rand(K.n, dtype=torch.float64, device=f.device, generator=gen)
+    xKy = float((x[rows] * K.nzval * y[cols]).sum())
+    yKx = float((y[rows] * K.nzval * x[cols]).sum())
+    assert abs(xKy - yKx) <= 1e-11 * abs(xKy)

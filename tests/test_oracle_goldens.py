@@ -231,3 +231,24 @@ def test_neohooke_tangent_is_derivative_of_residual():
         gm = O.element_neohooke(cv, x, p, u - du)[1]
         assert np.allclose((gp - gm)[0] / (2 * h), ke[0, :, j], rtol=1e-6, atol=1e-8)
     assert np.allclose(ke, np.swapaxes(ke, 1, 2), atol=1e-12)
+
+
+def test_c_port_matches_numpy_oracle():
+    # the C restatement (bench cpu_baseline) against the numpy oracle, heat + elasticity, 1 and 4 threads
+    from oracle import cport
+    nel = (6, 5, 4)
+    for vdim, elem, params in [(1, "heat", {"k": 1.5, "source": 0.5}),
+                               (3, "elasticity", dict(zip(("lambda", "mu"), O.lame(200e9, 0.3)), b=(0.0, 0.0, -1.0)))]:
+        grid = O.perturb_grid(O.generate_grid("hexahedron", nel), nel, (-1,) * 3, (1,) * 3, 0.2)
+        ip = O.Lagrange("hexahedron", 1)
+        ip = ip ** vdim if vdim > 1 else ip
+        dh = O.DofHandler(grid).add("u", ip).close()
+        cv = O.CellValues(O.QuadratureRule("hexahedron", 2), ip)
+        K1, f1 = O.allocate_matrix(dh), np.zeros(dh.ndofs)
+        O.assemble_global(dh, cv, K1, f1, elem, params)
+        for nt in (1, 4):
+            K2, f2 = O.allocate_matrix(dh), np.zeros(dh.ndofs)
+            cport.assemble(dh, cv, K2, f2, elem, params, nthreads=nt)
+            scale = np.abs(K1.nzval).max()
+            assert np.all(np.abs(K2.nzval - K1.nzval) <= 1e-13 * scale)
+            assert np.all(np.abs(f2 - f1) <= 1e-13 * max(np.abs(f1).max(), 1e-300))
