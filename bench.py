@@ -269,6 +269,8 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps
     a_nz._h = {}
+    fb.assemble_(a, elem, cv)       # restore K, f (the accumulating launches above added on top)
+    ctx.synchronize()
 
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)

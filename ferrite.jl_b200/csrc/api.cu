@@ -292,6 +292,7 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     if (!a) return FB2_OK;
     cudaSetDevice(a->dh->grid->ctx->device);
     cudaFree(a->d_map);
+    cudaFree(a->d_map8);
     cudaFree(a->d_color_cells);
     cudaFree(a->d_cells);
     cudaFree(a->d_nzval);

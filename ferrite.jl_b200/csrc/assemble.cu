@@ -105,10 +105,12 @@ int dispatch_neohooke(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype,
 }
 
 template <int ELEM>
-bool try_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nb, int nq, int* rc) {
+bool try_scalar(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int celltype, int nb, int nq, int* rc) {
 #define CASE(CT, DIM, NGEO, NB, NQ)                                              \
     if (celltype == CT && nb == NB && nq == NQ) {                                \
-        *rc = launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic);            \
+        *rc = fb2_map_build_packed(a);                                           \
+        A.map8 = reinterpret_cast<const uint4*>(a->d_map8);                      \
+        if (*rc == FB2_OK) *rc = launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic); \
         return true;                                                             \
     }
     CASE(FB2_QUADRILATERAL, 2, 4, 4, 4)
@@ -207,11 +209,11 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
     switch (element) {
         case FB2_ELEM_HEAT:
             FB2_CHECK(vdim == 1, FB2_ERR_BAD_ARG, "the heat element needs a scalar field");
-            if (variant == 0 && try_scalar<FB2_ELEM_HEAT>(ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            if (variant == 0 && try_scalar<FB2_ELEM_HEAT>(a, ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_HEAT, 0>(ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_MASS:
             FB2_CHECK(vdim == 1, FB2_ERR_UNSUPPORTED, "the mass element is implemented for scalar fields");
-            if (variant == 0 && try_scalar<FB2_ELEM_MASS>(ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            if (variant == 0 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_MASS, 0>(ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY:
             return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(ctx, A, atomic, ct, nbs, vdim);
@@ -238,6 +240,7 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     A.cell_dofs = dh->d_cell_dofs;
     A.colptr = a->pat->d_colptr;
     A.map = a->d_map;
+    A.map8 = reinterpret_cast<const uint4*>(a->d_map8);
     A.ncells_pad = g->ncells_pad;
     A.nzval = nzval_dev;
     A.f = f_dev;

@@ -28,6 +28,7 @@ struct AsmArgs {
     const int32_t* cell_dofs;
     const int64_t* colptr;
     const uint16_t* map;
+    const uint4* map8;     // packed offsets for k_cell_scalar
     const int32_t* cells;  // optional indirection (colour / partition subset)
     int64_t ncount;        // number of cells handled by this launch
     int64_t ncells_pad;
@@ -103,12 +104,15 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
     const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
     const int64_t np = A.ncells_pad;
 
+    int node[NGEO];
+#pragma unroll
+    for (int j = 0; j < NGEO; ++j) node[j] = __ldg(A.conn + (size_t)j * np + cell);
+    int dof[NB];   // loaded early: the dependent colptr loads can then be issued right after the quadrature loop
+#pragma unroll
+    for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
     double x[NGEO][DIM];
 #pragma unroll
-    for (int j = 0; j < NGEO; ++j) {
-        int node = __ldg(A.conn + (size_t)j * np + cell);
-        fb2_load_x<DIM>(A.xyz, node, x[j]);
-    }
+    for (int j = 0; j < NGEO; ++j) fb2_load_x<DIM>(A.xyz, node[j], x[j]);
     constexpr int NSYM = NB * (NB + 1) / 2;
     double Ke[NSYM];
     double fe[NB];
@@ -180,20 +184,27 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
     }
     const double kscale = A.p[0];  // heat: conductivity k; mass: rho
     const double fscale = A.p[1];  // heat: source
-    int dof[NB];
+    // Scatter.  All index loads (column bases, packed offsets) are issued as one batch before the first RED:
+    // interleaving them with the atomics serialises 64 memory round trips per cell (profiles/r1 notes).
+    int64_t base[NB];
 #pragma unroll
-    for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
+    for (int j = 0; j < NB; ++j) base[j] = __ldg(A.colptr + dof[j]);
+    constexpr int NCH = (NB * NB + 7) / 8;
+    uint4 mp[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) mp[k] = __ldg(A.map8 + (size_t)k * np + cell);
     bool missing = false;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-        const int64_t base = __ldg(A.colptr + dof[j]);
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const double v = kscale * (i <= j ? Ke[j * (j + 1) / 2 + i] : Ke[i * (i + 1) / 2 + j]);
-            const unsigned off = __ldg(A.map + (size_t)(j * NB + i) * np + cell);
+            const int e = j * NB + i;
+            const unsigned w32 = (e & 7) < 2 ? mp[e >> 3].x : ((e & 7) < 4 ? mp[e >> 3].y : ((e & 7) < 6 ? mp[e >> 3].z : mp[e >> 3].w));
+            const unsigned off = (e & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
             if (v != 0.0) {
                 if (off == 0xFFFFu) missing = true;
-                else fb2_add<ATOMIC>(A.nzval + base + off, v);
+                else fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
             }
         }
     }
@@ -454,19 +465,25 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             if (b0 + t < NBS) {
+                // batch the index loads of this node block before its REDs (loads interleaved with atomics
+                // are serialised by the compiler: one memory round trip per entry)
+                int64_t base[VDIM];
+                unsigned off[VDIM][VDIM];
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
                     const int jl = (b0 + t) * VDIM + d;
-                    const int dj = __ldg(A.cell_dofs + (size_t)jl * np + cell);
-                    const int64_t base = __ldg(A.colptr + dj);
+                    base[d] = __ldg(A.colptr + __ldg(A.cell_dofs + (size_t)jl * np + cell));
+#pragma unroll
+                    for (int c = 0; c < VDIM; ++c) off[d][c] = __ldg(A.map + (size_t)(jl * N + a * VDIM + c) * np + cell);
+                }
+#pragma unroll
+                for (int d = 0; d < VDIM; ++d) {
 #pragma unroll
                     for (int c = 0; c < VDIM; ++c) {
-                        const int il = a * VDIM + c;
                         const double v = kscale * acc[t][c][d];
-                        const unsigned off = __ldg(A.map + (size_t)(jl * N + il) * np + cell);
                         if (v != 0.0) {
-                            if (off == 0xFFFFu) missing = true;
-                            else fb2_add<ATOMIC>(A.nzval + base + off, v);
+                            if (off[d][c] == 0xFFFFu) missing = true;
+                            else fb2_add<ATOMIC>(A.nzval + base[d] + off[d][c], v);
                         }
                     }
                 }

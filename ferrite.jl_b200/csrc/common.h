@@ -157,6 +157,7 @@ struct fb2_assembler {
     fb2_cv* cv = nullptr;
     int n = 0;                     // dofs per cell covered by the element (= ndpc)
     uint16_t* d_map = nullptr;     // [n*n][ncells_pad]: offset of row dof_i inside column dof_j, e = j*n + i
+    uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     // colouring (lazy)
     int ncolors = 0;
     std::vector<int32_t> cell_color;
@@ -198,6 +199,7 @@ struct fb2_ch {
 int fb2_pattern_build_device(fb2_pattern* p);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
 int fb2_map_build(fb2_assembler* a);
+int fb2_map_build_packed(fb2_assembler* a);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 int fb2_check_device_error(fb2_ctx* ctx);

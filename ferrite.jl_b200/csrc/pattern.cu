@@ -145,6 +145,20 @@ __global__ void k_build_map(const int32_t* __restrict__ cell_dofs, int64_t ncell
     map[t] = off;
 }
 
+// Packed variant for the thread-per-cell kernels: 8 offsets per 16-byte chunk, chunk k of cell c at
+// map8[k * ncells_pad + c] (one coalesced LDG.128 per chunk and warp).
+__global__ void k_pack_map(const uint16_t* __restrict__ map, int64_t ncells_pad, int nn, int nchunks, uint16_t* __restrict__ map8) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nchunks * 8 * ncells_pad;
+    if (t >= total) return;
+    int s = (int)(t & 7);
+    int64_t r = t >> 3;
+    int64_t c = r % ncells_pad;
+    int k = (int)(r / ncells_pad);
+    int e = k * 8 + s;
+    map8[t] = e < nn ? map[(size_t)e * ncells_pad + c] : (uint16_t)0xFFFF;
+}
+
 __global__ void k_to_onebased64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) out[t] = (int64_t)in[t] + 1;
@@ -382,6 +396,21 @@ extern "C" int fb2_pattern_destroy(fb2_pattern* p) {
     cudaFree(p->d_rowval);
     cudaFree(p->d_diag);
     delete p;
+    return FB2_OK;
+}
+
+int fb2_map_build_packed(fb2_assembler* a) {
+    if (a->d_map8) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int nn = a->n * a->n, nchunks = (nn + 7) / 8;
+    const int64_t total = (int64_t)nchunks * 8 * g->ncells_pad;
+    FB2_CUDA(cudaMalloc(&a->d_map8, total * sizeof(uint16_t)));
+    k_pack_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells_pad, nn, nchunks, a->d_map8);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
     return FB2_OK;
 }
 
