@@ -132,7 +132,25 @@ _PROTOS = {
     "fb2_apply": [_p, _p, _p, _p, C.c_int, _dp],
     "fb2_apply_vector": [_p, _p, C.c_int],
     "fb2_ch_destroy": [_p],
+    "fb2_partition_create": [_p, C.c_int, C.c_int, _ip, _pp],
+    "fb2_partition_info": [_p, _i64p, _i64p, _i64p, _i64p, _i64p],
+    "fb2_partition_export": [_p, _i64p, C.POINTER(C.c_uint8), _i64p, _i64p, _i32p],
+    "fb2_partition_local_grid": [_p, _p, _pp],
+    "fb2_partition_local_dh": [_p, _p, _pp],
+    "fb2_partition_peer_counts": [_p, C.c_int, _i64p, _i64p, _i64p, _i64p],
+    "fb2_partition_peer_lists": [_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p],
+    "fb2_partition_bind": [_p, _p],
+    "fb2_partition_pack": [_p, C.c_int, _p, _p, _p],
+    "fb2_partition_unpack_add": [_p, C.c_int, _p, _p, _p],
+    "fb2_partition_mask_unowned": [_p, _p, _p],
+    "fb2_partition_destroy": [_p],
+    "fb2_comm_unique_id": [_p],
+    "fb2_comm_init_rank": [_p, _p, C.c_int, C.c_int],
+    "fb2_comm_destroy": [_p],
+    "fb2_partition_exchange": [_p, _p, _p],
+    "fb2_assemble_distributed": [_p, _p, C.c_int, C.c_int, _p, C.c_size_t, _p, _p, _p, C.POINTER(AsmOpts)],
 }
+DIST_EXCHANGE, DIST_HALO, DIST_OWN_ONLY = 0, 1, 2
 
 lib.fb2_version.restype = C.c_char_p
 lib.fb2_version.argtypes = []

@@ -577,3 +577,105 @@ def apply_(K, f=None, ch=None, applyzero=False):
 
 def apply_zero_(K, f=None, ch=None):
     return apply_(K, f, ch, applyzero=True)
+
+
+# ---- partitioned multi-GPU assembly (no counterpart in the reference) ---------------------------------------------
+class Partition:
+    """Rank `rank` of `nparts` of a global DofHandler: own + halo cells as a local problem, column ownership and
+    per-peer interface exchange lists (see csrc/partition.cu).  `gdh` may live on a host-only context."""
+
+    def __init__(self, gdh, nparts, rank, dims=None):
+        self.gdh, self.nparts, self.rank = gdh, int(nparts), int(rank)
+        self.h = C.c_void_p()
+        darr = (C.c_int * 3)(*(list(dims) + [1, 1, 1])[:3]) if dims is not None else None
+        L.call("fb2_partition_create", gdh.h, self.nparts, self.rank, darr, C.byref(self.h))
+        v = [C.c_int64() for _ in range(5)]
+        L.call("fb2_partition_info", self.h, *[C.byref(x) for x in v])
+        self.ncells_local, self.ncells_own, self.nnodes_local, self.ndofs_local, self.ndofs_owned = (x.value for x in v)
+        self.cells_global = np.empty(self.ncells_local, dtype=np.int64)
+        self.cell_is_own = np.empty(self.ncells_local, dtype=np.uint8)
+        self.l2g_node = np.empty(self.nnodes_local, dtype=np.int64)
+        self.l2g_dof = np.empty(self.ndofs_local, dtype=np.int64)
+        self.dof_owner = np.empty(self.ndofs_local, dtype=np.int32)
+        L.call("fb2_partition_export", self.h, _ptr(self.cells_global, C.c_int64), _ptr(self.cell_is_own, C.c_uint8),
+               _ptr(self.l2g_node, C.c_int64), _ptr(self.l2g_dof, C.c_int64), _ptr(self.dof_owner, C.c_int32))
+        self._asm = None
+
+    def local_problem(self, ctx):
+        """(grid, dh) of the local sub-problem on `ctx` (local numbering)."""
+        gh, dhh = C.c_void_p(), C.c_void_p()
+        L.call("fb2_partition_local_grid", self.h, ctx.h, C.byref(gh))
+        grid = Grid(ctx, gh)
+        L.call("fb2_partition_local_dh", self.h, grid.h, C.byref(dhh))
+        dh = DofHandler(grid)
+        dh.field_names, dh.field_ips = list(self.gdh.field_names), list(self.gdh.field_ips)
+        dh.h = dhh
+        dh._info()
+        return grid, dh
+
+    def peer_counts(self, peer):
+        v = [C.c_int64() for _ in range(4)]
+        L.call("fb2_partition_peer_counts", self.h, int(peer), *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)      # nz_send, f_send, nz_recv, f_recv
+
+    def peer_lists(self, peer):
+        ns, fs, nr, fr = self.peer_counts(peer)
+        a = [np.empty(n, dtype=np.int32) for n in (ns, ns, nr, nr, fs, fr)]
+        L.call("fb2_partition_peer_lists", self.h, int(peer), *[_ptr(x, C.c_int32) for x in a])
+        return dict(send_rows=a[0], send_cols=a[1], recv_rows=a[2], recv_cols=a[3], send_f=a[4], recv_f=a[5])
+
+    def bind(self, assembler, cv):
+        self._asm = assembler
+        self._cv = cv
+        L.call("fb2_partition_bind", self.h, assembler._handle(cv))
+
+    def pack(self, peer, K, f, out):
+        L.call("fb2_partition_pack", self.h, int(peer), C.c_void_p(K.nzval.data_ptr()),
+               C.c_void_p(f.data_ptr()) if f is not None else None, C.c_void_p(out.data_ptr()))
+
+    def unpack_add(self, peer, buf, K, f):
+        L.call("fb2_partition_unpack_add", self.h, int(peer), C.c_void_p(buf.data_ptr()), C.c_void_p(K.nzval.data_ptr()),
+               C.c_void_p(f.data_ptr()) if f is not None else None)
+
+    def mask_unowned(self, K, f):
+        L.call("fb2_partition_mask_unowned", self.h, C.c_void_p(K.nzval.data_ptr()),
+               C.c_void_p(f.data_ptr()) if f is not None else None)
+
+    def assemble_(self, element, mode="exchange", u=None):
+        """assemble! for this rank: mode 'exchange' (own cells + NCCL interface exchange, needs comm_init) or
+        'halo' (own + halo cells, no communication); the local K / f then hold the final owned columns / dofs."""
+        a = self._asm
+        opts = a._opts()
+        L.call("fb2_assemble_distributed", a._handle(self._cv), self.h,
+               {"halo": L.DIST_HALO, "exchange": L.DIST_EXCHANGE, "own": L.DIST_OWN_ONLY}[mode],
+               element.elem_id, C.byref(element.params), C.sizeof(element.params),
+               C.c_void_p(u.data_ptr()) if u is not None else None, C.c_void_p(a.K.nzval.data_ptr()),
+               C.c_void_p(a.f.data_ptr()) if a.f is not None else None, C.byref(opts))
+
+    def owned_triplets(self, K, f=None):
+        """Owned columns of the local matrix as global (row, col, value) triplets (1-based) + owned f entries."""
+        K.dh.grid.ctx.synchronize()
+        colptr, rowval = K.colptr - 1, K.rowval - 1
+        nz = K.nzval.cpu().numpy()
+        cols = np.repeat(np.arange(K.n), np.diff(colptr))
+        sel = self.dof_owner[cols] == self.rank
+        out = (self.l2g_dof[rowval[sel]], self.l2g_dof[cols[sel]], nz[sel])
+        if f is None:
+            return out
+        own = self.dof_owner == self.rank
+        return out + (self.l2g_dof[own], f.cpu().numpy()[own])
+
+    def __del__(self):
+        _destroy(self, "fb2_partition_destroy", _chain(self, "gdh"))
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    L.call("fb2_comm_unique_id", buf)
+    return bytes(buf)
+
+
+def comm_init(ctx, unique_id, nranks, rank):
+    """ncclCommInitRank for the library's own transport; `unique_id` = bytes from comm_unique_id() on rank 0."""
+    buf = (C.c_char * 128).from_buffer_copy(unique_id)
+    L.call("fb2_comm_init_rank", ctx.h, buf, int(nranks), int(rank))

@@ -52,6 +52,24 @@ __device__ __forceinline__ void fb2_add(double* p, double v) {
     else *p += v;
 }
 
+// Volatile read-only loads: ptxas keeps them in program order ahead of the REDs that follow, so a batch of
+// index loads is in flight together instead of one memory round trip per scattered entry.
+__device__ __forceinline__ int fb2_ldv_s32(const int32_t* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned fb2_ldv_u16(const uint16_t* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int64_t fb2_ldv_s64(const int64_t* p) {
+    int64_t v;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
 template <int DIM>
 __device__ __forceinline__ void fb2_load_x(const double* __restrict__ xyz, int node, double* x) {
     if (DIM == 3) {
@@ -113,6 +131,22 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
     double x[NGEO][DIM];
 #pragma unroll
     for (int j = 0; j < NGEO; ++j) fb2_load_x<DIM>(A.xyz, node[j], x[j]);
+    // Stage the scatter indices (packed uint16 offsets, column bases) into shared memory with cp.async now;
+    // they land while the quadrature loop runs.  Plain loads placed here are sunk by ptxas next to the
+    // REDs (one exposed memory round trip per 8 entries, profiles/r1 notes); cp.async cannot be sunk.
+    constexpr int NCH = (NB * NB + 7) / 8;
+    __shared__ uint4 s_map[NCH][128];
+    __shared__ int64_t s_base[NB][128];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_map[k][threadIdx.x]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(A.map8 + (size_t)k * np + cell) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_base[j][threadIdx.x]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(A.colptr + dof[j]) : "memory");
+    }
     constexpr int NSYM = NB * (NB + 1) / 2;
     double Ke[NSYM];
     double fe[NB];
@@ -178,6 +212,7 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
             }
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     if (bad) {
         fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
         return;
@@ -186,13 +221,14 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
     const double fscale = A.p[1];  // heat: source
     // Scatter.  All index loads (column bases, packed offsets) are issued as one batch before the first RED:
     // interleaving them with the atomics serialises 64 memory round trips per cell (profiles/r1 notes).
+    // They were staged into shared memory with cp.async before the quadrature loop (see above).
+    asm volatile("cp.async.wait_all;" ::: "memory");
     int64_t base[NB];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) base[j] = __ldg(A.colptr + dof[j]);
-    constexpr int NCH = (NB * NB + 7) / 8;
+    for (int j = 0; j < NB; ++j) base[j] = s_base[j][threadIdx.x];
     uint4 mp[NCH];
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) mp[k] = __ldg(A.map8 + (size_t)k * np + cell);
+    for (int k = 0; k < NCH; ++k) mp[k] = s_map[k][threadIdx.x];
     bool missing = false;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -469,13 +505,16 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
                 // are serialised by the compiler: one memory round trip per entry)
                 int64_t base[VDIM];
                 unsigned off[VDIM][VDIM];
+                int dj[VDIM];
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
                     const int jl = (b0 + t) * VDIM + d;
-                    base[d] = __ldg(A.colptr + __ldg(A.cell_dofs + (size_t)jl * np + cell));
+                    dj[d] = fb2_ldv_s32(A.cell_dofs + (size_t)jl * np + cell);
 #pragma unroll
-                    for (int c = 0; c < VDIM; ++c) off[d][c] = __ldg(A.map + (size_t)(jl * N + a * VDIM + c) * np + cell);
+                    for (int c = 0; c < VDIM; ++c) off[d][c] = fb2_ldv_u16(A.map + (size_t)(jl * N + a * VDIM + c) * np + cell);
                 }
+#pragma unroll
+                for (int d = 0; d < VDIM; ++d) base[d] = fb2_ldv_s64(A.colptr + dj[d]);
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
 #pragma unroll

@@ -1,21 +1,520 @@
-// Partitioned multi-GPU assembly (placeholder until the partition plan lands).
+// Partitioned multi-GPU assembly.  New capability: the reference is single-process; the
+// parity oracle for this path is the reference's serial global K, f.
+//
+// One process per GPU.  Every rank knows the global grid + DofHandler (host side, reference numbering) and builds:
+//   * its cells: structured blocks px*py*pz for generate_grid input, contiguous ranges otherwise;
+//   * dof/column ownership: the lowest rank among the cells touching a dof owns it;
+//   * a LOCAL problem = own cells + halo cells (every cell touching an owned dof), with local node / dof numbering
+//     (ascending global ids), so the ordinary single-GPU pattern / map / kernels run unchanged on it and the local
+//     pattern of an owned column holds all of the column's global rows;
+//   * per peer, the interface exchange lists.  K is CSC, so "interface-row contributions" are exchanged by column:
+//     rank r sends, for every column j owned by peer o, the partial sums K[i, j] it produced from its own cells
+//     (i in the dofs of r's own cells containing j); both sides derive the identical (j, i)-sorted list from the
+//     global numbering, so only values travel.
+// Two strategies: FB2_DIST_EXCHANGE assembles own cells and exchanges interface columns (NCCL grouped send/recv);
+// FB2_DIST_HALO assembles own + halo cells redundantly and needs no communication at all.  Afterwards every rank
+// holds the final values of its owned columns / dofs; everything it does not own is zeroed.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "common.h"
 
-struct fb2_part { int dummy; };
+struct PeerPlan {
+    std::vector<int32_t> send_rows, send_cols, recv_rows, recv_cols;  // local dof ids, sorted by global (col, row)
+    std::vector<int32_t> send_f, recv_f;                              // local dof ids, sorted by global id
+    int64_t* d_send_pos = nullptr;
+    int64_t* d_recv_pos = nullptr;
+    int32_t* d_send_f = nullptr;
+    int32_t* d_recv_f = nullptr;
+    double* d_sendbuf = nullptr;
+    double* d_recvbuf = nullptr;
+};
 
-#define FB2_NYI(name) return fb2_fail(FB2_ERR_UNSUPPORTED, name ": not implemented yet")
+struct fb2_part {
+    fb2_dh* gdh = nullptr;
+    int nparts = 1, rank = 0;
+    int dims[3] = {1, 1, 1};
+    std::vector<int64_t> cells_global;   // local cells (own + halo), ascending global id (0-based)
+    std::vector<uint8_t> cell_is_own;
+    std::vector<int64_t> l2g_node, l2g_dof;  // 0-based global ids, ascending
+    std::vector<int32_t> dof_owner;          // per local dof
+    std::vector<int64_t> lcells;             // nnpc x nlocal, 1-based local node ids
+    std::vector<double> lxyz;                // sdim x nlocal_nodes
+    std::vector<int64_t> lcell_dofs;         // ndpc x nlocal, 1-based local dofs
+    std::vector<PeerPlan> peers;
+    int64_t ndofs_owned = 0, ncells_own = 0;
+    // device binding
+    fb2_assembler* bound = nullptr;
+    int32_t* d_own_cells = nullptr;
+    uint8_t* d_col_owned = nullptr;
+};
 
-extern "C" int fb2_partition_create(fb2_dh*, fb2_pattern*, int, int, fb2_part**) { FB2_NYI("fb2_partition_create"); }
-extern "C" int fb2_partition_info(fb2_part*, int64_t*, int64_t*, int64_t*, int64_t*) { FB2_NYI("fb2_partition_info"); }
-extern "C" int fb2_partition_cells(fb2_part*, int64_t*) { FB2_NYI("fb2_partition_cells"); }
-extern "C" int fb2_partition_peer_counts(fb2_part*, int, int64_t*, int64_t*, int64_t*, int64_t*) { FB2_NYI("fb2_partition_peer_counts"); }
-extern "C" int fb2_assembler_set_partition(fb2_assembler*, fb2_part*) { FB2_NYI("fb2_assembler_set_partition"); }
-extern "C" int fb2_partition_pack(fb2_part*, int, const double*, const double*, double*) { FB2_NYI("fb2_partition_pack"); }
-extern "C" int fb2_partition_unpack_add(fb2_part*, int, const double*, double*, double*) { FB2_NYI("fb2_partition_unpack_add"); }
-extern "C" int fb2_partition_mask_unowned(fb2_part*, double*, double*) { FB2_NYI("fb2_partition_mask_unowned"); }
-extern "C" int fb2_partition_destroy(fb2_part*) { return FB2_OK; }
-extern "C" int fb2_comm_unique_id(void*) { FB2_NYI("fb2_comm_unique_id"); }
-extern "C" int fb2_comm_init_rank(fb2_ctx*, const void*, int, int) { FB2_NYI("fb2_comm_init_rank"); }
-extern "C" int fb2_comm_destroy(fb2_ctx*) { return FB2_OK; }
-extern "C" int fb2_assemble_distributed(fb2_assembler*, fb2_part*, int, const void*, size_t, const double*, double*, double*,
-                                        const fb2_asm_opts*) { FB2_NYI("fb2_assemble_distributed"); }
+namespace {
+
+void default_dims(int nparts, const int64_t* nel, int dim, int* dims) {
+    dims[0] = dims[1] = dims[2] = 1;
+    int n = nparts;
+    for (int p = 2; n > 1;) {
+        if (n % p) { ++p; continue; }
+        // give the factor to the direction with the most cells per block
+        int best = 0;
+        double bv = -1;
+        for (int d = 0; d < dim; ++d) {
+            double v = (double)nel[d] / dims[d];
+            if (v > bv) { bv = v; best = d; }
+        }
+        dims[best] *= p;
+        n /= p;
+    }
+}
+
+inline int block_of(int64_t i, int64_t n, int p) {
+    // balanced split: block b covers [floor(b*n/p), floor((b+1)*n/p))
+    int b = (int)((i * p) / n);
+    while (b + 1 < p && ((int64_t)(b + 1) * n) / p <= i) ++b;
+    while (b > 0 && ((int64_t)b * n) / p > i) --b;
+    return b;
+}
+
+__global__ void k_lookup_pos(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols, int64_t n,
+                             const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t* __restrict__ pos) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int r = rows[t], c = cols[t];
+    int64_t lo = colptr[c], hi = colptr[c + 1], p = -1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        int rr = rowval[mid];
+        if (rr == r) { p = mid; break; }
+        if (rr < r) lo = mid + 1; else hi = mid;
+    }
+    pos[t] = p;
+}
+
+__global__ void k_pack(const int64_t* __restrict__ pos, int64_t nnz, const int32_t* __restrict__ fd, int64_t nf,
+                       const double* __restrict__ nzval, const double* __restrict__ f, double* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) out[t] = nzval[pos[t]];
+    else if (t < nnz + nf) out[t] = f ? f[fd[t - nnz]] : 0.0;
+}
+
+__global__ void k_unpack_add(const int64_t* __restrict__ pos, int64_t nnz, const int32_t* __restrict__ fd, int64_t nf,
+                             const double* __restrict__ in, double* __restrict__ nzval, double* __restrict__ f) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nnz) nzval[pos[t]] += in[t];               // positions are unique within one peer list
+    else if (t < nnz + nf && f) f[fd[t - nnz]] += in[t];
+}
+
+__global__ void k_mask_unowned(const uint8_t* __restrict__ owned, int64_t n, const int64_t* __restrict__ colptr,
+                               double* __restrict__ nzval, double* __restrict__ f) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n || owned[w]) return;
+    for (int64_t k = colptr[w] + lane; k < colptr[w + 1]; k += 32) nzval[k] = 0.0;
+    if (lane == 0 && f) f[w] = 0.0;
+}
+
+inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+extern "C" int fb2_partition_create(fb2_dh* gdh, int nparts, int rank, const int* dims_in, fb2_part** out) {
+    FB2_CHECK(gdh && out, FB2_ERR_BAD_ARG, "fb2_partition_create: null argument");
+    FB2_CHECK(nparts >= 1 && rank >= 0 && rank < nparts, FB2_ERR_BAD_ARG, "fb2_partition_create: bad nparts/rank");
+    fb2_grid* g = gdh->grid;
+    const int64_t ncells = g->ncells;
+    const int nnpc = g->nnpc, ndpc = gdh->ndpc, sdim = g->sdim;
+    fb2_part* P = new fb2_part();
+    P->gdh = gdh;
+    P->nparts = nparts;
+    P->rank = rank;
+    // ---- cell -> rank --------------------------------------------------------------------------------------
+    std::vector<int32_t> owner((size_t)ncells);
+    if (g->generated && g->celltype != FB2_LINE) {
+        const int dim = g->sdim;
+        if (dims_in) { for (int d = 0; d < 3; ++d) P->dims[d] = d < dim ? dims_in[d] : 1; }
+        else default_dims(nparts, g->nel, dim, P->dims);
+        if ((int64_t)P->dims[0] * P->dims[1] * P->dims[2] != nparts) {
+            delete P;
+            return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create: block layout does not multiply to nparts");
+        }
+        const int64_t nx = g->nel[0], ny = g->nel[1], nz = dim > 2 ? g->nel[2] : 1;
+        const int per = (g->celltype == FB2_TRIANGLE) ? 2 : (g->celltype == FB2_TETRAHEDRON ? 6 : 1);
+        for (int64_t c = 0; c < ncells; ++c) {
+            int64_t cube = c / per;
+            int64_t i = cube % nx, j = (cube / nx) % ny, k = cube / (nx * ny);
+            int b = block_of(i, nx, P->dims[0]) + P->dims[0] * (block_of(j, ny, P->dims[1]) + P->dims[1] * (dim > 2 ? block_of(k, nz, P->dims[2]) : 0));
+            owner[c] = b;
+        }
+    } else {
+        P->dims[0] = nparts;
+        for (int64_t c = 0; c < ncells; ++c) owner[c] = block_of(c, ncells, nparts);
+    }
+    // ---- dof -> rank: lowest rank among the cells touching the dof ---------------------------------------------
+    std::vector<int32_t> gdof_owner((size_t)gdh->ndofs, nparts);
+    for (int64_t c = 0; c < ncells; ++c) {
+        const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
+        const int32_t o = owner[c];
+        for (int i = 0; i < ndpc; ++i)
+            if (o < gdof_owner[cd[i]]) gdof_owner[cd[i]] = o;
+    }
+    // ---- local cells: own + every cell touching an owned dof -----------------------------------------------------
+    for (int64_t c = 0; c < ncells; ++c) {
+        bool own = owner[c] == rank, touch = false;
+        if (!own) {
+            const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
+            for (int i = 0; i < ndpc && !touch; ++i) touch = gdof_owner[cd[i]] == rank;
+        }
+        if (own || touch) {
+            P->cells_global.push_back(c);
+            P->cell_is_own.push_back(own ? 1 : 0);
+            P->ncells_own += own ? 1 : 0;
+        }
+    }
+    const int64_t nl = (int64_t)P->cells_global.size();
+    if (nl == 0) { delete P; return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create: rank %d owns no cells", rank); }
+    // ---- local numbering (ascending global ids) ---------------------------------------------------------------------
+    std::vector<int32_t> g2l_node((size_t)g->nnodes, -1), g2l_dof((size_t)gdh->ndofs, -1);
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        for (int k = 0; k < nnpc; ++k) g2l_node[g->cells[(size_t)c * nnpc + k] - 1] = 0;
+        for (int i = 0; i < ndpc; ++i) g2l_dof[gdh->cell_dofs[(size_t)c * ndpc + i]] = 0;
+    }
+    for (int64_t n = 0; n < g->nnodes; ++n)
+        if (g2l_node[n] == 0) { g2l_node[n] = (int32_t)P->l2g_node.size(); P->l2g_node.push_back(n); }
+    for (int64_t d = 0; d < gdh->ndofs; ++d)
+        if (g2l_dof[d] == 0) {
+            g2l_dof[d] = (int32_t)P->l2g_dof.size();
+            P->l2g_dof.push_back(d);
+            P->dof_owner.push_back(gdof_owner[d]);
+            P->ndofs_owned += gdof_owner[d] == rank ? 1 : 0;
+        }
+    P->lcells.resize((size_t)nl * nnpc);
+    P->lcell_dofs.resize((size_t)nl * ndpc);
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        for (int k = 0; k < nnpc; ++k) P->lcells[(size_t)l * nnpc + k] = g2l_node[g->cells[(size_t)c * nnpc + k] - 1] + 1;
+        for (int i = 0; i < ndpc; ++i) P->lcell_dofs[(size_t)l * ndpc + i] = g2l_dof[gdh->cell_dofs[(size_t)c * ndpc + i]] + 1;
+    }
+    P->lxyz.resize(P->l2g_node.size() * sdim);
+    for (size_t n = 0; n < P->l2g_node.size(); ++n)
+        for (int d = 0; d < sdim; ++d) P->lxyz[n * sdim + d] = g->xyz[(size_t)P->l2g_node[n] * sdim + d];
+    // ---- exchange lists -----------------------------------------------------------------------------------------------
+    P->peers.resize(nparts);
+    std::vector<std::vector<uint64_t>> send_k(nparts), recv_k(nparts), send_fk(nparts), recv_fk(nparts);
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
+        if (P->cell_is_own[l]) {
+            for (int j = 0; j < ndpc; ++j) {
+                const int o = gdof_owner[cd[j]];
+                if (o == rank) continue;
+                send_fk[o].push_back((uint64_t)cd[j]);
+                for (int i = 0; i < ndpc; ++i) send_k[o].push_back(((uint64_t)cd[j] << 32) | (uint32_t)cd[i]);
+            }
+        } else {
+            const int s = owner[c];
+            for (int j = 0; j < ndpc; ++j) {
+                if (gdof_owner[cd[j]] != rank) continue;
+                recv_fk[s].push_back((uint64_t)cd[j]);
+                for (int i = 0; i < ndpc; ++i) recv_k[s].push_back(((uint64_t)cd[j] << 32) | (uint32_t)cd[i]);
+            }
+        }
+    }
+    auto uniq = [](std::vector<uint64_t>& v) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    for (int p = 0; p < nparts; ++p) {
+        uniq(send_k[p]); uniq(recv_k[p]); uniq(send_fk[p]); uniq(recv_fk[p]);
+        PeerPlan& pp = P->peers[p];
+        for (uint64_t k : send_k[p]) { pp.send_cols.push_back(g2l_dof[k >> 32]); pp.send_rows.push_back(g2l_dof[k & 0xffffffffu]); }
+        for (uint64_t k : recv_k[p]) { pp.recv_cols.push_back(g2l_dof[k >> 32]); pp.recv_rows.push_back(g2l_dof[k & 0xffffffffu]); }
+        for (uint64_t k : send_fk[p]) pp.send_f.push_back(g2l_dof[k]);
+        for (uint64_t k : recv_fk[p]) pp.recv_f.push_back(g2l_dof[k]);
+        std::vector<uint64_t>().swap(send_k[p]);
+        std::vector<uint64_t>().swap(recv_k[p]);
+    }
+    *out = P;
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_info(fb2_part* P, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
+                                  int64_t* ndofs_local, int64_t* ndofs_owned) {
+    FB2_CHECK(P, FB2_ERR_BAD_ARG, "fb2_partition_info: null handle");
+    if (ncells_local) *ncells_local = (int64_t)P->cells_global.size();
+    if (ncells_own) *ncells_own = P->ncells_own;
+    if (nnodes_local) *nnodes_local = (int64_t)P->l2g_node.size();
+    if (ndofs_local) *ndofs_local = (int64_t)P->l2g_dof.size();
+    if (ndofs_owned) *ndofs_owned = P->ndofs_owned;
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_export(fb2_part* P, int64_t* cells_global, uint8_t* cell_is_own, int64_t* l2g_node, int64_t* l2g_dof,
+                                    int32_t* dof_owner) {
+    FB2_CHECK(P, FB2_ERR_BAD_ARG, "fb2_partition_export: null handle");
+    if (cells_global) for (size_t i = 0; i < P->cells_global.size(); ++i) cells_global[i] = P->cells_global[i] + 1;
+    if (cell_is_own) memcpy(cell_is_own, P->cell_is_own.data(), P->cell_is_own.size());
+    if (l2g_node) for (size_t i = 0; i < P->l2g_node.size(); ++i) l2g_node[i] = P->l2g_node[i] + 1;
+    if (l2g_dof) for (size_t i = 0; i < P->l2g_dof.size(); ++i) l2g_dof[i] = P->l2g_dof[i] + 1;
+    if (dof_owner) memcpy(dof_owner, P->dof_owner.data(), P->dof_owner.size() * sizeof(int32_t));
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_local_grid(fb2_part* P, fb2_ctx* ctx, fb2_grid** out) {
+    FB2_CHECK(P && ctx && out, FB2_ERR_BAD_ARG, "fb2_partition_local_grid: null argument");
+    fb2_grid* g = P->gdh->grid;
+    return fb2_grid_from_host(ctx, g->celltype, (int64_t)P->cells_global.size(), (int64_t)P->l2g_node.size(), g->sdim,
+                              P->lcells.data(), P->lxyz.data(), out);
+}
+
+extern "C" int fb2_partition_local_dh(fb2_part* P, fb2_grid* local_grid, fb2_dh** out) {
+    FB2_CHECK(P && local_grid && out, FB2_ERR_BAD_ARG, "fb2_partition_local_dh: null argument");
+    return fb2_dh_from_host(local_grid, (int)P->gdh->fields.size(), P->gdh->fields.data(), (int64_t)P->l2g_dof.size(), P->gdh->ndpc,
+                            P->lcell_dofs.data(), out);
+}
+
+extern "C" int fb2_partition_peer_counts(fb2_part* P, int peer, int64_t* nz_send, int64_t* f_send, int64_t* nz_recv, int64_t* f_recv) {
+    FB2_CHECK(P && peer >= 0 && peer < P->nparts, FB2_ERR_BAD_ARG, "fb2_partition_peer_counts: bad argument");
+    const PeerPlan& pp = P->peers[peer];
+    if (nz_send) *nz_send = (int64_t)pp.send_rows.size();
+    if (f_send) *f_send = (int64_t)pp.send_f.size();
+    if (nz_recv) *nz_recv = (int64_t)pp.recv_rows.size();
+    if (f_recv) *f_recv = (int64_t)pp.recv_f.size();
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_peer_lists(fb2_part* P, int peer, int32_t* send_rows, int32_t* send_cols, int32_t* recv_rows,
+                                        int32_t* recv_cols, int32_t* send_f, int32_t* recv_f) {
+    FB2_CHECK(P && peer >= 0 && peer < P->nparts, FB2_ERR_BAD_ARG, "fb2_partition_peer_lists: bad argument");
+    const PeerPlan& pp = P->peers[peer];
+    auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
+    cp(send_rows, pp.send_rows); cp(send_cols, pp.send_cols); cp(recv_rows, pp.recv_rows); cp(recv_cols, pp.recv_cols);
+    cp(send_f, pp.send_f); cp(recv_f, pp.recv_f);
+    return FB2_OK;
+}
+
+static void free_binding(fb2_part* P) {
+    for (PeerPlan& pp : P->peers) {
+        cudaFree(pp.d_send_pos); cudaFree(pp.d_recv_pos); cudaFree(pp.d_send_f); cudaFree(pp.d_recv_f);
+        cudaFree(pp.d_sendbuf); cudaFree(pp.d_recvbuf);
+        pp.d_send_pos = pp.d_recv_pos = nullptr; pp.d_send_f = pp.d_recv_f = nullptr; pp.d_sendbuf = pp.d_recvbuf = nullptr;
+    }
+    cudaFree(P->d_own_cells); cudaFree(P->d_col_owned);
+    P->d_own_cells = nullptr; P->d_col_owned = nullptr;
+    P->bound = nullptr;
+}
+
+// Bind the plan to a local assembler: resolve the exchange lists to positions in the local nzval, upload the
+// own-cell subset and the owned-column mask.
+extern "C" int fb2_partition_bind(fb2_part* P, fb2_assembler* a) {
+    FB2_CHECK(P && a, FB2_ERR_BAD_ARG, "fb2_partition_bind: null argument");
+    fb2_ctx* ctx = a->dh->grid->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(a->dh->ndofs == (int64_t)P->l2g_dof.size() && a->dh->grid->ncells == (int64_t)P->cells_global.size(), FB2_ERR_BAD_ARG,
+              "fb2_partition_bind: the assembler does not belong to this partition's local problem");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    free_binding(P);
+    cudaStream_t st = ctx->stream;
+    for (int p = 0; p < P->nparts; ++p) {
+        PeerPlan& pp = P->peers[p];
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::vector<int32_t>& rows = dir ? pp.recv_rows : pp.send_rows;
+            const std::vector<int32_t>& cols = dir ? pp.recv_cols : pp.send_cols;
+            const std::vector<int32_t>& fl = dir ? pp.recv_f : pp.send_f;
+            const size_t n = rows.size();
+            int64_t** d_pos = dir ? &pp.d_recv_pos : &pp.d_send_pos;
+            int32_t** d_f = dir ? &pp.d_recv_f : &pp.d_send_f;
+            double** d_buf = dir ? &pp.d_recvbuf : &pp.d_sendbuf;
+            if (n + fl.size() == 0) continue;
+            FB2_CUDA(cudaMalloc(d_buf, (n + fl.size()) * sizeof(double)));
+            if (!fl.empty()) {
+                FB2_CUDA(cudaMalloc(d_f, fl.size() * sizeof(int32_t)));
+                FB2_CUDA(cudaMemcpyAsync(*d_f, fl.data(), fl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            }
+            if (n == 0) continue;
+            int32_t *d_r = nullptr, *d_c = nullptr;
+            FB2_CUDA(cudaMalloc(&d_r, n * sizeof(int32_t)));
+            FB2_CUDA(cudaMalloc(&d_c, n * sizeof(int32_t)));
+            FB2_CUDA(cudaMalloc(d_pos, n * sizeof(int64_t)));
+            FB2_CUDA(cudaMemcpyAsync(d_r, rows.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            FB2_CUDA(cudaMemcpyAsync(d_c, cols.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            k_lookup_pos<<<nblk((int64_t)n, 256), 256, 0, st>>>(d_r, d_c, (int64_t)n, a->pat->d_colptr, a->pat->d_rowval, *d_pos);
+            ctx->launches++;
+            // every listed entry must exist in the local pattern
+            std::vector<int64_t> h(n);
+            FB2_CUDA(cudaMemcpyAsync(h.data(), *d_pos, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            FB2_CUDA(cudaStreamSynchronize(st));
+            cudaFree(d_r);
+            cudaFree(d_c);
+            for (size_t t = 0; t < n; ++t)
+                FB2_CHECK(h[t] >= 0, FB2_ERR_INTERNAL, "fb2_partition_bind: exchange entry missing in the local pattern (peer %d)", p);
+        }
+    }
+    std::vector<int32_t> own;
+    for (size_t l = 0; l < P->cell_is_own.size(); ++l)
+        if (P->cell_is_own[l]) own.push_back((int32_t)l);
+    FB2_CUDA(cudaMalloc(&P->d_own_cells, std::max<size_t>(own.size(), 1) * sizeof(int32_t)));
+    FB2_CUDA(cudaMemcpy(P->d_own_cells, own.data(), own.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    std::vector<uint8_t> co(P->dof_owner.size());
+    for (size_t d = 0; d < co.size(); ++d) co[d] = P->dof_owner[d] == P->rank;
+    FB2_CUDA(cudaMalloc(&P->d_col_owned, co.size()));
+    FB2_CUDA(cudaMemcpy(P->d_col_owned, co.data(), co.size(), cudaMemcpyHostToDevice));
+    P->bound = a;
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_pack(fb2_part* P, int peer, const double* nzval_dev, const double* f_dev, double* send_dev) {
+    FB2_CHECK(P && P->bound && peer >= 0 && peer < P->nparts && nzval_dev, FB2_ERR_BAD_ARG, "fb2_partition_pack: bad argument or plan not bound");
+    fb2_ctx* ctx = P->bound->dh->grid->ctx;
+    PeerPlan& pp = P->peers[peer];
+    const int64_t nnz = (int64_t)pp.send_rows.size(), nf = (int64_t)pp.send_f.size();
+    if (nnz + nf == 0) return FB2_OK;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    k_pack<<<nblk(nnz + nf, 256), 256, 0, ctx->stream>>>(pp.d_send_pos, nnz, pp.d_send_f, nf, nzval_dev, f_dev, send_dev ? send_dev : pp.d_sendbuf);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_unpack_add(fb2_part* P, int peer, const double* recv_dev, double* nzval_dev, double* f_dev) {
+    FB2_CHECK(P && P->bound && peer >= 0 && peer < P->nparts && nzval_dev, FB2_ERR_BAD_ARG, "fb2_partition_unpack_add: bad argument or plan not bound");
+    fb2_ctx* ctx = P->bound->dh->grid->ctx;
+    PeerPlan& pp = P->peers[peer];
+    const int64_t nnz = (int64_t)pp.recv_rows.size(), nf = (int64_t)pp.recv_f.size();
+    if (nnz + nf == 0) return FB2_OK;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    k_unpack_add<<<nblk(nnz + nf, 256), 256, 0, ctx->stream>>>(pp.d_recv_pos, nnz, pp.d_recv_f, nf, recv_dev ? recv_dev : pp.d_recvbuf, nzval_dev, f_dev);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_mask_unowned(fb2_part* P, double* nzval_dev, double* f_dev) {
+    FB2_CHECK(P && P->bound && nzval_dev, FB2_ERR_BAD_ARG, "fb2_partition_mask_unowned: bad argument or plan not bound");
+    fb2_ctx* ctx = P->bound->dh->grid->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t)P->l2g_dof.size();
+    k_mask_unowned<<<nblk(n * 32, 256), 256, 0, ctx->stream>>>(P->d_col_owned, n, P->bound->pat->d_colptr, nzval_dev, f_dev);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+extern "C" int fb2_partition_destroy(fb2_part* P) {
+    if (!P) return FB2_OK;
+    if (P->bound) { cudaSetDevice(P->bound->dh->grid->ctx->device); free_binding(P); }
+    delete P;
+    return FB2_OK;
+}
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------------------------------
+// libnccl.so.2 is dlopen'ed instead of linked: inside a PyTorch process the already loaded (bundled) NCCL is reused,
+// a Julia / C host gets the system library; only the stable point-to-point subset of the API is used.
+namespace {
+struct NcclApi {
+    struct Id128 { char b[128]; };  // ncclUniqueId, passed by value
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.handle) return FB2_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    FB2_CHECK(h, FB2_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    g_nccl.handle = h;
+#define SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); FB2_CHECK(g_nccl.field, FB2_ERR_NCCL, "libnccl: missing symbol %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return FB2_OK;
+}
+#define FB2_NCCL(call)                                                                                      \
+    do {                                                                                                    \
+        int r__ = (call);                                                                                   \
+        if (r__ != 0) return fb2_fail(FB2_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));   \
+    } while (0)
+}  // namespace
+
+extern "C" int fb2_comm_unique_id(void* id128) {
+    FB2_CHECK(id128, FB2_ERR_BAD_ARG, "fb2_comm_unique_id: null argument");
+    FB2_TRY(nccl_load());
+    FB2_NCCL(g_nccl.GetUniqueId(id128));
+    return FB2_OK;
+}
+
+extern "C" int fb2_comm_init_rank(fb2_ctx* ctx, const void* id128, int nranks, int rank) {
+    FB2_CHECK(ctx && id128, FB2_ERR_BAD_ARG, "fb2_comm_init_rank: null argument");
+    FB2_NEED_DEVICE(ctx);
+    FB2_TRY(nccl_load());
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    NcclApi::Id128 id;
+    memcpy(id.b, id128, 128);
+    FB2_NCCL(g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return FB2_OK;
+}
+
+extern "C" int fb2_comm_destroy(fb2_ctx* ctx) {
+    if (ctx && ctx->nccl_comm && g_nccl.handle) {
+        g_nccl.CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return FB2_OK;
+}
+
+// pack everything, one grouped send/recv with every peer, unpack-add everything (all on the context's stream)
+extern "C" int fb2_partition_exchange(fb2_part* P, double* nzval_dev, double* f_dev) {
+    FB2_CHECK(P && P->bound && nzval_dev, FB2_ERR_BAD_ARG, "fb2_partition_exchange: bad argument or plan not bound");
+    fb2_ctx* ctx = P->bound->dh->grid->ctx;
+    FB2_CHECK(ctx->nccl_comm, FB2_ERR_NCCL, "fb2_partition_exchange: call fb2_comm_init_rank first");
+    FB2_CHECK(ctx->nranks == P->nparts && ctx->rank == P->rank, FB2_ERR_BAD_ARG, "fb2_partition_exchange: communicator and partition disagree");
+    for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_pack(P, p, nzval_dev, f_dev, nullptr));
+    FB2_NCCL(g_nccl.GroupStart());
+    for (int p = 0; p < P->nparts; ++p) {
+        PeerPlan& pp = P->peers[p];
+        const size_t ns = pp.send_rows.size() + pp.send_f.size(), nr = pp.recv_rows.size() + pp.recv_f.size();
+        if (ns) FB2_NCCL(g_nccl.Send(pp.d_sendbuf, ns, /*ncclFloat64*/ 8, p, ctx->nccl_comm, ctx->stream));
+        if (nr) FB2_NCCL(g_nccl.Recv(pp.d_recvbuf, nr, /*ncclFloat64*/ 8, p, ctx->nccl_comm, ctx->stream));
+    }
+    FB2_NCCL(g_nccl.GroupEnd());
+    for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_unpack_add(P, p, nullptr, nzval_dev, f_dev));
+    return FB2_OK;
+}
+
+extern "C" int fb2_assemble_distributed(fb2_assembler* a, fb2_part* P, int mode, int element, const void* params, size_t params_bytes,
+                                        const double* u_dev, double* nzval_dev, double* f_dev, const fb2_asm_opts* opts) {
+    FB2_CHECK(a && P && nzval_dev, FB2_ERR_BAD_ARG, "fb2_assemble_distributed: null argument");
+    FB2_CHECK(P->bound == a, FB2_ERR_BAD_ARG, "fb2_assemble_distributed: bind the partition to this assembler first");
+    FB2_CHECK(mode == FB2_DIST_EXCHANGE || mode == FB2_DIST_HALO || mode == FB2_DIST_OWN_ONLY, FB2_ERR_BAD_ARG,
+              "fb2_assemble_distributed: unknown mode %d", mode);
+    if (mode != FB2_DIST_HALO) {
+        a->d_cells = P->d_own_cells;
+        a->ncells_active = P->ncells_own;
+    }
+    int rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, opts);
+    a->d_cells = nullptr;
+    a->ncells_active = 0;
+    FB2_TRY(rc);
+    if (mode == FB2_DIST_OWN_ONLY) return FB2_OK;  // the host drives pack / transport / unpack_add / mask itself
+    if (mode == FB2_DIST_EXCHANGE && P->nparts > 1) FB2_TRY(fb2_partition_exchange(P, nzval_dev, f_dev));
+    return fb2_partition_mask_unowned(P, nzval_dev, f_dev);
+}

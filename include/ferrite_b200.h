@@ -219,32 +219,51 @@ int fb2_ch_destroy(fb2_ch* ch);
 
 /* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
 typedef struct fb2_part fb2_part;
-/* Partition the cells of `grid` into nparts blocks (structured generate_grid input: px*py*pz blocks;
- * otherwise contiguous cell ranges) and describe rank `rank`: its cells, the dofs it owns (lowest rank
- * touching a dof owns it) and the interface columns it must exchange.  Host logic only. */
-int fb2_partition_create(fb2_dh* dh, fb2_pattern* p, int nparts, int rank, fb2_part** out);
-int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncols_owned, int64_t* nnz_send, int64_t* nnz_recv);
-/* cell ids (0-based) of this rank, for tests */
-int fb2_partition_cells(fb2_part* part, int64_t* cells);
+enum { FB2_DIST_EXCHANGE = 0, /* assemble own cells, exchange interface columns over NCCL */
+       FB2_DIST_HALO = 1,     /* assemble own + halo cells redundantly, no communication */
+       FB2_DIST_OWN_ONLY = 2  /* assemble own cells only; the host drives pack / transport / unpack_add / mask */ };
+/* Host logic only (works on a host-only context).  `dh` is the GLOBAL DofHandler in the reference's numbering.
+ * Cells go to ranks as px*py*pz blocks for generate_grid input (dims, nullable = automatic) or as contiguous
+ * ranges otherwise; a dof (= matrix column) is owned by the lowest rank among the cells touching it.  Rank
+ * `rank` gets a local problem = own cells + halo cells (every cell touching an owned dof), local node / dof
+ * numbering by ascending global id, and per-peer exchange lists. */
+int fb2_partition_create(fb2_dh* dh, int nparts, int rank, const int* dims, fb2_part** out);
+int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
+                       int64_t* ndofs_local, int64_t* ndofs_owned);
+/* global ids (1-based) of the local cells / nodes / dofs, own-cell flags, owner rank of each local dof */
+int fb2_partition_export(fb2_part* part, int64_t* cells_global, uint8_t* cell_is_own, int64_t* l2g_node,
+                         int64_t* l2g_dof, int32_t* dof_owner);
+/* the local sub-grid / DofHandler of this rank on context `ctx` (a device, or host-only for tests) */
+int fb2_partition_local_grid(fb2_part* part, fb2_ctx* ctx, fb2_grid** out);
+int fb2_partition_local_dh(fb2_part* part, fb2_grid* local_grid, fb2_dh** out);
 /* per-peer exchange plan: number of nz values (and f values) sent to / received from `peer` */
 int fb2_partition_peer_counts(fb2_part* part, int peer, int64_t* nz_send, int64_t* f_send, int64_t* nz_recv, int64_t* f_recv);
-/* restrict an assembler to the cells of this partition */
-int fb2_assembler_set_partition(fb2_assembler* a, fb2_part* part);
-/* pack the partial sums this rank holds for columns owned by `peer` into send_dev (nz values then f values) */
+/* the lists themselves as local 0-based dof ids (row, col), sorted by global (col, row); for tests and for hosts
+ * that drive the transport themselves */
+int fb2_partition_peer_lists(fb2_part* part, int peer, int32_t* send_rows, int32_t* send_cols, int32_t* recv_rows,
+                             int32_t* recv_cols, int32_t* send_f, int32_t* recv_f);
+/* device: resolve the lists to positions in the local nzval of assembler `a` (local pattern), upload the own-cell
+ * subset and the owned-column mask */
+int fb2_partition_bind(fb2_part* part, fb2_assembler* a);
+/* pack the partial sums this rank holds for columns owned by `peer` (nz values, then f values) into send_dev
+ * (NULL = the plan's internal buffer) */
 int fb2_partition_pack(fb2_part* part, int peer, const double* nzval_dev, const double* f_dev, double* send_dev);
-/* add the partial sums received from `peer` into the owned columns */
+/* add the partial sums received from `peer` (recv_dev, NULL = internal buffer) into the owned columns */
 int fb2_partition_unpack_add(fb2_part* part, int peer, const double* recv_dev, double* nzval_dev, double* f_dev);
-/* zero every entry of nzval/f this rank does not own (after the exchange the owned part is final) */
+/* zero every column of nzval / entry of f this rank does not own (the owned part is then final) */
 int fb2_partition_mask_unowned(fb2_part* part, double* nzval_dev, double* f_dev);
 int fb2_partition_destroy(fb2_part* part);
 
-/* NCCL exchange driven by the library: unique id bootstrap is done by the caller (e.g. broadcast over
- * torch.distributed); afterwards fb2_assemble_distributed = assemble local cells + pack + grouped
- * ncclSend/ncclRecv + unpack-add on the context's stream. */
+/* NCCL transport inside the library (libnccl.so.2 is resolved with dlopen at run time).  The 128-byte unique id is
+ * created on one rank and distributed by the caller (e.g. a torch.distributed / MPI broadcast). */
 int fb2_comm_unique_id(void* id128 /* 128 bytes out */);
 int fb2_comm_init_rank(fb2_ctx* ctx, const void* id128, int nranks, int rank);
 int fb2_comm_destroy(fb2_ctx* ctx);
-int fb2_assemble_distributed(fb2_assembler* a, fb2_part* part, int element, const void* params, size_t params_bytes,
+/* pack for all peers, one grouped ncclSend/ncclRecv, unpack-add; stream-ordered on the context's stream */
+int fb2_partition_exchange(fb2_part* part, double* nzval_dev, double* f_dev);
+/* assemble! for a partition: FB2_DIST_EXCHANGE = own cells + fb2_partition_exchange, FB2_DIST_HALO = own + halo
+ * cells; then mask what is not owned.  nzval_dev / f_dev are the LOCAL matrix / vector of this rank. */
+int fb2_assemble_distributed(fb2_assembler* a, fb2_part* part, int mode, int element, const void* params, size_t params_bytes,
                              const double* u_dev, double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 
 #ifdef __cplusplus
