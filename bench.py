@@ -173,6 +173,19 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def block_dims(n):
+    """px, py, pz with px*py*pz == n, as cubic as possible (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2)."""
+    dims = [1, 1, 1]
+    p = 2
+    while n > 1:
+        if n % p:
+            p += 1
+            continue
+        dims[dims.index(min(dims))] *= p
+        n //= p
+    return tuple(sorted(dims, reverse=True))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +195,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "colored"])
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--dist-mode", default="exchange", choices=["exchange", "halo"],
+                    help="N>1: own cells + NCCL interface exchange, or own+halo cells without communication")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -197,6 +212,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
@@ -207,31 +223,69 @@ def main():
     # ---- set-up (not timed): grid, dofs, pattern, map all resident in HBM ------------------------------
     t_setup = time.perf_counter()
     nel = cfg["nel"]
-    g = fb.generate_grid(fb.Hexahedron, nel).perturb(0.2)
     ip = fb.Lagrange(fb.RefHexahedron, cfg["order"]) ** cfg["vdim"]
-    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, cfg["qr"]), ip)
+    elem = fb.HeatElement(1.0, 1.0) if cfg["element"] == "heat" else fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+    part = None
+    if world == 1:
+        g = fb.generate_grid(fb.Hexahedron, nel).perturb(0.2)
+        dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+        ncells_total, volume = g.ncells, 8.0
+    else:
+        # weak scaling: every GPU owns one block of `nel` cells of a px*py*pz times larger box; every rank derives
+        # the global numbering (host), its own + halo cells and the interface exchange lists
+        dims = block_dims(world)
+        gnel = tuple(n * d for n, d in zip(nel, dims))
+        hctx = fb.Context(-1)
+        gg = fb.generate_grid(fb.Hexahedron, gnel, tuple(-float(d) for d in dims), tuple(float(d) for d in dims), ctx=hctx).perturb(0.2)
+        gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+        part = fb.Partition(gdh, world, rank, dims)
+        g, dh = part.local_problem(ctx)
+        ncells_total, volume = gg.ncells, 8.0 * world
     K = fb.allocate_matrix(dh)
     f = ctx.zeros(dh.ndofs)
-    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, cfg["qr"]), ip)
-    if cfg["element"] == "heat":
-        elem = fb.HeatElement(1.0, 1.0)
-    else:
-        elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
     a = fb.start_assemble(K, f, scatter=args.scatter)
     a.variant = args.variant
-    fb.assemble_(a, elem, cv)
+    if part is not None:
+        part.bind(a, cv)
+        if args.dist_mode == "exchange":
+            ids = [fb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            fb.comm_init(ctx, ids[0], world, rank)
+
+    def step(asm):
+        if part is None:
+            fb.assemble_(asm, elem, cv)
+        else:
+            part._asm = asm
+            part.assemble_(elem, mode=args.dist_mode)
+
+    step(a)
     ctx.synchronize()
     t_setup = time.perf_counter() - t_setup
-    ncells = g.ncells
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ---- device-resident timing ---------------------------------------------------------------------------
     for _ in range(args.warmup):
-        fb.assemble_(a, elem, cv)
+        step(a)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -241,20 +295,22 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        fb.assemble_(a, elem, cv)
+        step(a)
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
     ctx.synchronize()
-    # size-independent checks on the full-size result (Laplace: sum(f) = |Omega| * source; K row sums = 0)
+    value = ncells_total * args.steps / (ms * 1e-3)
+    # size-independent checks on the full-size result (Laplace: sum(f) = |Omega| * source, sum(K) = 0); with N > 1
+    # every rank holds its owned columns / dofs only, so the sums over ranks must give the global totals
     checks = {}
     if cfg["element"] == "heat":
-        checks["sum_f_minus_volume"] = abs(float(f.sum()) - 8.0)
-        checks["sum_K"] = abs(float(K.nzval.sum())) / float(K.nzval.abs().max())
+        checks["sum_f_minus_volume"] = abs(sum_over_ranks(float(f.sum())) - volume)
+        checks["sum_K"] = abs(sum_over_ranks(float(K.nzval.sum()))) / max_over_ranks(float(K.nzval.abs().max()))
 
-    # ---- dominant kernel alone (no zero fill) for the roofline -----------------------------------------------
+    # ---- dominant kernel alone (no zero fill, no exchange) for the roofline -----------------------------------
     a_nz = fb.start_assemble(K, f, fillzero=False, scatter=args.scatter)
     a_nz.variant = args.variant
     a_nz._h = a._h          # reuse the same native assembler (map)
@@ -269,14 +325,9 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps
     a_nz._h = {}
-    fb.assemble_(a, elem, cv)       # restore K, f (the accumulating launches above added on top)
+    step(a)       # restore K, f (the accumulating launches above added on top)
     ctx.synchronize()
-
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = ncells * world * args.steps / (ms * 1e-3)
+    fsum_dev = float(f.sum())
 
     # ---- end-to-end through host buffers ------------------------------------------------------------------------
     e2e = None
@@ -285,34 +336,42 @@ def main():
         nz_host = torch.empty(K.nnz, dtype=torch.float64).pin_memory()
         f_host = torch.empty(dh.ndofs, dtype=torch.float64).pin_memory()
         nz_np, f_np = nz_host.numpy(), f_host.numpy()
-        a_h = fb.start_assemble(K, None, scatter=args.scatter)
+        a_h = fb.start_assemble(K, f if part is not None else None, scatter=args.scatter)
         a_h.variant = args.variant
         a_h._h = a._h
         esteps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            g.upload_coordinates_async(xyz_host)              # H2D: this step's input
+            if part is None:
+                fb.assemble_host(a_h, elem, cv, nz_np, f_np)  # assemble + D2H of nzval and f (synchronises)
+            else:
+                step(a_h)
+                nz_host.copy_(K.nzval, non_blocking=True)     # D2H of this rank's owned columns / dofs
+                f_host.copy_(f, non_blocking=True)
+                torch.cuda.synchronize()
         for _ in range(2):
-            g.upload_coordinates_async(xyz_host)
-            fb.assemble_host(a_h, elem, cv, nz_np, f_np)
+            e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(esteps):
-            g.upload_coordinates_async(xyz_host)          # H2D: this step's input
-            fb.assemble_host(a_h, elem, cv, nz_np, f_np)  # assemble + D2H of nzval and f (synchronises)
+            e2e_step()
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = max_over_ranks(time.perf_counter() - t0)
         a_h._h = {}
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": ncells * world * esteps / dt, "unit": "cells/s", "h2d_bytes_per_step": int(g.nnodes * g.sdim * 8),
-               "d2h_bytes_per_step": int((K.nnz + dh.ndofs) * 8), "steps": esteps,
-               "checksum_ok": bool(abs(float(f_host.sum()) - float(f.sum())) <= 1e-9 * max(1.0, abs(float(f.sum()))))}
+        e2e = {"value": ncells_total * esteps / dt, "unit": "cells/s",
+               "h2d_bytes_per_step": int(sum_over_ranks(float(g.nnodes * g.sdim * 8))),
+               "d2h_bytes_per_step": int(sum_over_ranks(float((K.nnz + dh.ndofs) * 8))), "steps": esteps,
+               "checksum_ok": bool(abs(float(f_host.sum()) - fsum_dev) <= 1e-9 * max(1.0, abs(fsum_dev)))}
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     hbm_peak, peak_src = load_peaks()
     fp64_peak = ctx.measure_fp64_peak()
-    cells_per_s_kernel = ncells / (kernel_ms * 1e-3)
+    cells_per_s_kernel = g.ncells / (kernel_ms * 1e-3)
     achieved = cfg["bmin"] * cells_per_s_kernel / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -320,16 +379,24 @@ def main():
         traffic = json.load(open(tp)).get(args.config)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms, "bytes_per_cell": cfg["bmin"],
+                "kernel_cells": g.ncells,
                 "fp64": {"achieved_tflops": cfg["fmin"] * cells_per_s_kernel / 1e12, "peak_tflops": fp64_peak,
                          "frac": cfg["fmin"] * cells_per_s_kernel / 1e12 / fp64_peak if fp64_peak else None,
                          "flop_per_cell": cfg["fmin"], "peak_source": "FMA microbenchmark in this run"}}
+    if world == 1:
+        par = "1 GPU"
+    else:
+        par = (f"{world} ranks, {'x'.join(map(str, dims))} blocks of {'x'.join(map(str, nel))} cells; "
+               + ("own cells + NCCL exchange of interface columns" if args.dist_mode == "exchange"
+                  else "own + halo cells, no communication"))
     line = {
         "metric": "cells assembled/sec (K+f, FP64, 3D hex)", "value": value, "unit": "cells/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["label"], "cells": ncells, "ndofs": dh.ndofs, "nnz": K.nnz, "scatter": args.scatter,
-                   "l2": "inputs+outputs (>= 3 GB) exceed the 126 MB L2; no flush needed", "setup_s": round(t_setup, 2),
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (partitioned path: see DESIGN.md)"},
+        "config": {"workload": cfg["label"] + ("" if world == 1 else f" per GPU, {ncells_total} cells in total"),
+                   "cells": ncells_total, "ndofs_rank0": dh.ndofs, "nnz_rank0": K.nnz, "scatter": args.scatter,
+                   "l2": "inputs+outputs (>= 3 GB per GPU) exceed the 126 MB L2; no flush needed", "setup_s": round(t_setup, 2),
+                   "parallelism": par},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "checks": checks,
     }
     if e2e:
@@ -339,6 +406,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline(cfg, sample)
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

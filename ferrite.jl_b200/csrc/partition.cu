@@ -47,6 +47,7 @@ struct fb2_part {
     int64_t ndofs_owned = 0, ncells_own = 0;
     // device binding
     fb2_assembler* bound = nullptr;
+    int bound_device = -1;
     int32_t* d_own_cells = nullptr;
     uint8_t* d_col_owned = nullptr;
 };
@@ -363,6 +364,7 @@ extern "C" int fb2_partition_bind(fb2_part* P, fb2_assembler* a) {
     FB2_CUDA(cudaMalloc(&P->d_col_owned, co.size()));
     FB2_CUDA(cudaMemcpy(P->d_col_owned, co.data(), co.size(), cudaMemcpyHostToDevice));
     P->bound = a;
+    P->bound_device = ctx->device;
     return FB2_OK;
 }
 
@@ -405,7 +407,8 @@ extern "C" int fb2_partition_mask_unowned(fb2_part* P, double* nzval_dev, double
 
 extern "C" int fb2_partition_destroy(fb2_part* P) {
     if (!P) return FB2_OK;
-    if (P->bound) { cudaSetDevice(P->bound->dh->grid->ctx->device); free_binding(P); }
+    // the bound assembler may already be gone (host languages finalise in any order): use the saved device id
+    if (P->bound) { cudaSetDevice(P->bound_device); free_binding(P); }
     delete P;
     return FB2_OK;
 }

@@ -1,0 +1,167 @@
+# FerriteB200.jl -- thin Julia shim over libferrite_b200.so (the C ABI in include/ferrite_b200.h).
+#
+# NOT EXECUTED in this repository's CI: neither the build container nor the GPU box has a Julia toolchain.
+# It is the binding a Ferrite.jl maintainer would add; it overloads the reference's documented extension points
+# (docs/src/devdocs/assembly.md:18-51): allocate_matrix, start_assemble, assemble!, finish_assemble, apply!.
+# The executed mirror of the same calls is ferrite.jl_b200/api.py (ctypes); tests/ drive the library through it.
+module FerriteB200
+
+using Ferrite
+using SparseArrays
+
+const LIB = get(ENV, "FERRITE_B200_LIB", "libferrite_b200")
+
+struct FB2Error <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:fb2_last_error, LIB), Cstring, ()))
+    rc == 4 && throw(ArgumentError(msg))      # FB2_ERR_DETJ_NOT_POSITIVE <-> throw_detJ_not_pos (common_values.jl:5)
+    rc == 5 && throw(ErrorException(msg))     # FB2_ERR_MISSING_PATTERN_ENTRY <-> assembler.jl:459-467
+    throw(FB2Error(rc, msg))
+end
+
+macro fb2(f, argtypes, args...)
+    return :(check(ccall(($(QuoteNode(f)), LIB), Cint, $(esc(argtypes)), $(map(esc, args)...))))
+end
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        @fb2 fb2_ctx_create (Cint, Ptr{Ptr{Cvoid}}) device r
+        return finalizer(c -> ccall((:fb2_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), new(r[]))
+    end
+end
+
+const CELLTYPE = Dict(Line => 1, Triangle => 2, Quadrilateral => 3, Tetrahedron => 4, Hexahedron => 5)
+
+struct fb2_field
+    order::Cint
+    vdim::Cint
+end
+
+# ---- arrays-in mode: keep Ferrite for set-up, hand its arrays to the device ----------------------------------------
+"""
+    DeviceProblem(ctx, dh, cv)
+
+Uploads `dh.grid`, `dh.cell_dofs` (src/Dofs/DofHandler.jl:126-131) and the tables of `cv`
+(cv.fun_values.Nξ/dNdξ FunctionValues.jl:46-49, cv.geo_mapping.M/dMdξ GeometryMapping.jl:38-39, cv.qr.weights).
+For vector interpolations pass the CellValues of the scalar base interpolation; `vdim` is taken from `dh`.
+"""
+mutable struct DeviceProblem
+    ctx::Context
+    grid::Ptr{Cvoid}
+    dh::Ptr{Cvoid}
+    cv::Ptr{Cvoid}
+    ndofs::Int
+end
+
+function DeviceProblem(ctx::Context, dh::DofHandler{sdim}, cv::CellValues, vdim::Integer = 1) where {sdim}
+    grid = dh.grid
+    CT = getcelltype(grid)
+    cells = reinterpret(reshape, Int, grid.cells)             # nnpc x ncells, 1-based (Vector{Hexahedron} is isbits)
+    xyz = reinterpret(reshape, Float64, grid.nodes)           # sdim x nnodes
+    g = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve cells xyz begin
+        @fb2 fb2_grid_from_host (Ptr{Cvoid}, Cint, Int64, Int64, Cint, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) ctx.h CELLTYPE[CT] getncells(grid) getnnodes(grid) sdim cells xyz g
+    end
+    ip = Ferrite.getfieldinterpolation(dh.subdofhandlers[1], 1)
+    fields = [fb2_field(Ferrite.getorder(ip), vdim)]
+    d = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve fields begin
+        @fb2 fb2_dh_from_host (Ptr{Cvoid}, Cint, Ptr{fb2_field}, Int64, Cint, Ptr{Int64}, Ptr{Ptr{Cvoid}}) g[] 1 fields ndofs(dh) ndofs_per_cell(dh) dh.cell_dofs d
+    end
+    N = cv.fun_values.Nξ                                       # n x nq
+    dN = reinterpret(reshape, Float64, cv.fun_values.dNdξ)     # rdim x n x nq
+    M = cv.geo_mapping.M
+    dM = reinterpret(reshape, Float64, cv.geo_mapping.dMdξ)
+    w = cv.qr.weights
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve N dN M dM w begin
+        @fb2 fb2_cellvalues_from_tables (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) ctx.h CELLTYPE[CT] length(w) size(N, 1) vdim size(M, 1) N dN M dM w c
+    end
+    return DeviceProblem(ctx, g[], d[], c[], ndofs(dh))
+end
+
+# ---- matrix type: plugs into allocate_matrix / start_assemble / assemble! / apply! -----------------------------------
+"""
+    B200Matrix <: AbstractSparseMatrix
+
+`K.host::SparseMatrixCSC{Float64,Int}` carries colptr/rowval (bit-identical to `allocate_matrix(dh)`); the values
+live on the device until `finish_assemble` / `download!` copies them into `K.host.nzval`.
+"""
+mutable struct B200Matrix
+    prob::DeviceProblem
+    pattern::Ptr{Cvoid}
+    assembler::Ptr{Cvoid}
+    host::SparseMatrixCSC{Float64, Int}
+    f::Vector{Float64}
+end
+
+# allocate_matrix(::Type{B200Matrix}, dh) -- src/Dofs/sparsity_pattern.jl:628-645
+function Ferrite.allocate_matrix(::Type{B200Matrix}, prob::DeviceProblem)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_pattern_create (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) prob.dh p          # pattern built on the device
+    n = Ref{Int64}(0); nnz = Ref{Int64}(0)
+    @fb2 fb2_pattern_info (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}) p[] n nnz
+    colptr = Vector{Int}(undef, n[] + 1); rowval = Vector{Int}(undef, nnz[])
+    @fb2 fb2_pattern_export (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}) p[] colptr rowval
+    a = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_assembler_create (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) prob.dh p[] prob.cv a
+    return B200Matrix(prob, p[], a[], SparseMatrixCSC(n[], n[], colptr, rowval, zeros(nnz[])), zeros(n[]))
+end
+
+# element menu (the reference's element routine is user code; see DESIGN.md section 1)
+struct HeatElement;       k::Float64; source::Float64; end
+struct ElasticityElement; lambda::Float64; mu::Float64; b::NTuple{3, Float64}; end
+elem_id(::HeatElement) = Cint(1)
+elem_id(::ElasticityElement) = Cint(3)
+
+struct fb2_asm_opts
+    fillzero::Cint
+    scatter_mode::Cint
+    variant::Cint
+    reserved::Cint
+end
+
+struct B200Assembler <: Ferrite.AbstractAssembler
+    K::B200Matrix
+    fillzero::Bool
+end
+
+# start_assemble(K, f; fillzero) -- src/assembler.jl:287-291
+Ferrite.start_assemble(K::B200Matrix; fillzero::Bool = true) = B200Assembler(K, fillzero)
+
+"""
+    assemble!(assembler, element)
+
+The whole `for cell in CellIterator(dh) ... assemble!(assembler, celldofs(cell), Ke, fe)` loop
+(heat_equation.jl:181-204) in one call; results land in `K.host.nzval` and `K.f`.
+"""
+function Ferrite.assemble!(a::B200Assembler, element; u::Union{Nothing, Vector{Float64}} = nothing)
+    K = a.K
+    opts = Ref(fb2_asm_opts(a.fillzero, 0, 0, 0))
+    params = Ref(element)
+    GC.@preserve params opts begin
+        @fb2 fb2_assemble_host (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{fb2_asm_opts}) K.assembler elem_id(element) params sizeof(element) (u === nothing ? C_NULL : pointer(u)) K.host.nzval K.f opts
+    end
+    return a
+end
+
+Ferrite.finish_assemble(a::B200Assembler) = (a.K.host, a.K.f)
+
+# apply!(K, f, ch) -- src/Dofs/ConstraintHandler.jl:710-740; the closed reference ConstraintHandler is adopted as arrays
+function Ferrite.apply!(K::B200Matrix, ch::ConstraintHandler, nzval_dev::Ptr{Float64}, f_dev::Ptr{Float64}; applyzero::Bool = false)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_ch_from_host (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) K.prob.dh length(ch.prescribed_dofs) ch.prescribed_dofs ch.inhomogeneities c
+    m = Ref{Float64}(0.0)
+    @fb2 fb2_apply (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}) c[] K.pattern nzval_dev f_dev applyzero m
+    ccall((:fb2_ch_destroy, LIB), Cint, (Ptr{Cvoid},), c[])
+    return m[]
+end
+
+end # module
