@@ -214,6 +214,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout; stdout carries exactly one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))

@@ -104,13 +104,39 @@ int dispatch_neohooke(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype,
     return fb2_fail(FB2_ERR_UNSUPPORTED, "Neo-Hooke needs a 3-D cell with a 3-component field");
 }
 
+// tile kernel (tiles.cu): whole grid, atomic mode only; falls back to the per-cell kernel when no schedule exists
+template <int DIM, int NGEO, int NB, int NQ, int ELEM>
+int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate) {
+    constexpr int NSYM = NB * (NB + 1) / 2;
+    constexpr int TC = (NSYM + NB) <= 44 ? 256 : 128;
+    if (atomic && variant == 0 && A.cells == nullptr && a->dh->grid->ncells >= 4 * TC) {
+        FB2_TRY(fb2_tiles_build(a, TC));
+        if (a->tiles) {
+            const TileSchedule* S = a->tiles;
+            TileArgs T{S->d_conn, S->d_ncells, S->d_cell_ids, S->d_col_ptr, S->d_col_dof, S->d_ent_ptr, S->d_ent_rec,
+                       S->d_ent_srcend, S->d_src_ptr, S->d_src, S->max_cols, accumulate};
+            const size_t smem = (size_t)(NSYM + NB) * TC * sizeof(double) + (size_t)S->max_cols * (sizeof(int64_t) + sizeof(int32_t));
+            if (smem <= 227 * 1024) {
+                auto k = k_tile_scalar<DIM, NGEO, NB, NQ, ELEM, TC>;
+                FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k<<<(unsigned)S->ntiles, 128, smem, ctx->stream>>>(A, T);
+                ctx->launches++;
+                FB2_CUDA(cudaGetLastError());
+                return FB2_OK;
+            }
+        }
+    }
+    FB2_TRY(fb2_map_build_packed(a));
+    A.map8 = reinterpret_cast<const uint4*>(a->d_map8);
+    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic);
+}
+
 template <int ELEM>
-bool try_scalar(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int celltype, int nb, int nq, int* rc) {
+bool try_scalar(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate, int celltype, int nb,
+                int nq, int* rc) {
 #define CASE(CT, DIM, NGEO, NB, NQ)                                              \
     if (celltype == CT && nb == NB && nq == NQ) {                                \
-        *rc = fb2_map_build_packed(a);                                           \
-        A.map8 = reinterpret_cast<const uint4*>(a->d_map8);                      \
-        if (*rc == FB2_OK) *rc = launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic); \
+        *rc = launch_tiles_or_cells<DIM, NGEO, NB, NQ, ELEM>(a, ctx, A, atomic, variant, accumulate); \
         return true;                                                             \
     }
     CASE(FB2_QUADRILATERAL, 2, 4, 4, 4)
@@ -201,7 +227,7 @@ int fb2_coloring_build(fb2_assembler* a) {
     return FB2_OK;
 }
 
-static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, int variant) {
+static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, int variant, int accumulate) {
     fb2_cv* cv = a->cv;
     fb2_ctx* ctx = cv->ctx;
     const int ct = cv->celltype, nbs = cv->nb, vdim = cv->vdim;
@@ -209,11 +235,11 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
     switch (element) {
         case FB2_ELEM_HEAT:
             FB2_CHECK(vdim == 1, FB2_ERR_BAD_ARG, "the heat element needs a scalar field");
-            if (variant == 0 && try_scalar<FB2_ELEM_HEAT>(a, ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            if (variant != 1 && try_scalar<FB2_ELEM_HEAT>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_HEAT, 0>(ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_MASS:
             FB2_CHECK(vdim == 1, FB2_ERR_UNSUPPORTED, "the mass element is implemented for scalar fields");
-            if (variant == 0 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, ct, nbs, cv->nq, &rc)) return rc;
+            if (variant != 1 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_MASS, 0>(ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY:
             return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(ctx, A, atomic, ct, nbs, vdim);
@@ -281,14 +307,14 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
             A.cells = a->d_color_cells + a->color_ptr[c];
             A.ncount = a->color_ptr[c + 1] - a->color_ptr[c];
             if (A.ncount == 0) continue;
-            FB2_TRY(launch_one(a, A, element, false, o.variant));
+            FB2_TRY(launch_one(a, A, element, false, o.variant, !o.fillzero));
         }
         return FB2_OK;
     }
     A.cells = a->d_cells;
     A.ncount = a->d_cells ? a->ncells_active : g->ncells;
     if (A.ncount == 0) return FB2_OK;
-    return launch_one(a, A, element, true, o.variant);
+    return launch_one(a, A, element, true, o.variant, !o.fillzero);
 }
 
 extern "C" int fb2_scatter_host(fb2_assembler* a, const double* Ke, const double* fe, double* nzval_dev, double* f_dev,

@@ -112,44 +112,13 @@ __device__ __forceinline__ double fb2_det_inv(const double (&J)[DIM][DIM], doubl
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
-// ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC>
-__global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= A.ncount) return;
-    const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
-    const int64_t np = A.ncells_pad;
-
-    int node[NGEO];
-#pragma unroll
-    for (int j = 0; j < NGEO; ++j) node[j] = __ldg(A.conn + (size_t)j * np + cell);
-    int dof[NB];   // loaded early: the dependent colptr loads can then be issued right after the quadrature loop
-#pragma unroll
-    for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
-    double x[NGEO][DIM];
-#pragma unroll
-    for (int j = 0; j < NGEO; ++j) fb2_load_x<DIM>(A.xyz, node[j], x[j]);
-    // Stage the scatter indices (packed uint16 offsets, column bases) into shared memory with cp.async now;
-    // they land while the quadrature loop runs.  Plain loads placed here are sunk by ptxas next to the
-    // REDs (one exposed memory round trip per 8 entries, profiles/r1 notes); cp.async cannot be sunk.
-    constexpr int NCH = (NB * NB + 7) / 8;
-    __shared__ uint4 s_map[NCH][128];
-    __shared__ int64_t s_base[NB][128];
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_map[k][threadIdx.x]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(A.map8 + (size_t)k * np + cell) : "memory");
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_base[j][threadIdx.x]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(A.colptr + dof[j]) : "memory");
-    }
+// Element integration shared by the thread-per-cell kernels: per quadrature point J = sum_j x_j (x) dM_j/dxi, det > 0,
+// dOmega = det*w, dNdx = dNdxi . inv(J); upper triangle of Ke (packed: (i,j), i <= j at j(j+1)/2 + i) and fe in registers.
+// Returns true if some det(J) was not positive.
+template <int DIM, int NGEO, int NB, int NQ, int ELEM>
+__device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const double (&x)[NGEO][DIM],
+                                                   double (&Ke)[NB * (NB + 1) / 2], double (&fe)[NB]) {
     constexpr int NSYM = NB * (NB + 1) / 2;
-    double Ke[NSYM];
-    double fe[NB];
 #pragma unroll
     for (int i = 0; i < NSYM; ++i) Ke[i] = 0.0;
 #pragma unroll
@@ -212,6 +181,48 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
             }
         }
     }
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
+// ------------------------------------------------------------------------------------------------
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC>
+__global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= A.ncount) return;
+    const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
+    const int64_t np = A.ncells_pad;
+
+    int node[NGEO];
+#pragma unroll
+    for (int j = 0; j < NGEO; ++j) node[j] = __ldg(A.conn + (size_t)j * np + cell);
+    int dof[NB];   // loaded early: the dependent colptr loads can then be issued right after the quadrature loop
+#pragma unroll
+    for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
+    double x[NGEO][DIM];
+#pragma unroll
+    for (int j = 0; j < NGEO; ++j) fb2_load_x<DIM>(A.xyz, node[j], x[j]);
+    // Stage the scatter indices (packed uint16 offsets, column bases) into shared memory with cp.async now;
+    // they land while the quadrature loop runs.  Plain loads placed here are sunk by ptxas next to the
+    // REDs (one exposed memory round trip per 8 entries, profiles/r1 notes); cp.async cannot be sunk.
+    constexpr int NCH = (NB * NB + 7) / 8;
+    __shared__ uint4 s_map[NCH][128];
+    __shared__ int64_t s_base[NB][128];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_map[k][threadIdx.x]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(A.map8 + (size_t)k * np + cell) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_base[j][threadIdx.x]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(A.colptr + dof[j]) : "memory");
+    }
+    constexpr int NSYM = NB * (NB + 1) / 2;
+    double Ke[NSYM];
+    double fe[NB];
+    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM>(A, x, Ke, fe);
     asm volatile("cp.async.wait_all;" ::: "memory");
     if (bad) {
         fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
@@ -249,6 +260,94 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
         for (int i = 0; i < NB; ++i) fb2_add<ATOMIC>(A.f + dof[i], fscale * fe[i]);
     }
     if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_tile_scalar: CTA per tile of TC cells (tiles.cu).  Phase 1: every thread integrates TC/128 cells and parks
+// Ke (upper triangle) and fe in shared memory, slot-major with the cell index fastest (conflict-free).  Phase 2:
+// thread per distinct output entry of the tile: sum the scheduled shared-memory slots in fixed order, write the
+// entry once -- plain store when the column is complete inside the tile, one RED otherwise.  Consecutive entries
+// of a column are consecutive in CSC, so the writes of a warp coalesce.
+// ------------------------------------------------------------------------------------------------
+struct TileArgs {
+    const int32_t* conn;
+    const int32_t* ncells;
+    const int32_t* cell_ids;
+    const int64_t* col_ptr;
+    const int32_t* col_dof;
+    const int64_t* ent_ptr;
+    const uint32_t* ent_rec;
+    const uint16_t* ent_srcend;
+    const int64_t* src_ptr;
+    const uint16_t* src;
+    int max_cols;
+    int accumulate;  // 1: add onto existing values (fillzero = false)
+};
+
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, int TC>
+__global__ void __launch_bounds__(128, 2) k_tile_scalar(const AsmArgs A, const TileArgs T) {
+    extern __shared__ double sm[];                      // [NSYM + NB][TC] element values
+    constexpr int NSYM = NB * (NB + 1) / 2;
+    int64_t* s_colbase = reinterpret_cast<int64_t*>(sm + (size_t)(NSYM + NB) * TC);  // [max_cols]
+    int32_t* s_coldof = reinterpret_cast<int32_t*>(s_colbase + T.max_cols);           // [max_cols]
+    const int64_t tile = blockIdx.x;
+    const int ncell = __ldg(T.ncells + tile);
+    const int64_t c0 = __ldg(T.col_ptr + tile);
+    const int ncols = (int)(__ldg(T.col_ptr + tile + 1) - c0);
+    for (int c = threadIdx.x; c < ncols; c += 128) {
+        const int32_t d = __ldg(T.col_dof + c0 + c);
+        s_coldof[c] = d;
+        s_colbase[c] = __ldg(A.colptr + (d & 0x7fffffff));
+    }
+    const double kscale = A.p[0], fscale = A.p[1];
+#pragma unroll 1
+    for (int cl = threadIdx.x; cl < TC; cl += 128) {
+        if (cl < ncell) {
+            double x[NGEO][DIM];
+#pragma unroll
+            for (int j = 0; j < NGEO; ++j) {
+                const int node = __ldg(T.conn + ((size_t)tile * NGEO + j) * TC + cl);
+                fb2_load_x<DIM>(A.xyz, node, x[j]);
+            }
+            double Ke[NSYM];
+            double fe[NB];
+            const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM>(A, x, Ke, fe);
+            if (bad) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, __ldg(T.cell_ids + (size_t)tile * TC + cl));
+#pragma unroll
+            for (int s = 0; s < NSYM; ++s) sm[s * TC + cl] = kscale * Ke[s];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) sm[(NSYM + i) * TC + cl] = fscale * fe[i];
+        }
+    }
+    __syncthreads();
+    const int64_t e0 = __ldg(T.ent_ptr + tile);
+    const int ne = (int)(__ldg(T.ent_ptr + tile + 1) - e0);
+    const uint16_t* src = T.src + __ldg(T.src_ptr + tile);
+    const bool want_f = A.f != nullptr && ELEM == FB2_ELEM_HEAT;
+    for (int e = threadIdx.x; e < ne; e += 128) {
+        const uint32_t rec = __ldg(T.ent_rec + e0 + e);
+        const int send = __ldg(T.ent_srcend + e0 + e);
+        const int sbeg = e ? (int)__ldg(T.ent_srcend + e0 + e - 1) : 0;
+        double sum = 0.0;
+        for (int s = sbeg; s < send; ++s) sum += sm[__ldg(src + s)];
+        const int col = rec >> 16;
+        const unsigned k = rec & 0xFFFFu;
+        const int32_t d = s_coldof[col];
+        const bool complete = d < 0;
+        double* dst;
+        if (k == 0xFFFFu) {
+            if (!want_f) continue;
+            dst = A.f + (d & 0x7fffffff);
+        } else {
+            dst = A.nzval + s_colbase[col] + k;
+        }
+        if (complete) {
+            if (T.accumulate) *dst += sum;   // nobody else touches a complete column
+            else *dst = sum;
+        } else if (sum != 0.0) {
+            atomicAdd(dst, sum);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

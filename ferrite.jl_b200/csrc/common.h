@@ -151,7 +151,29 @@ struct fb2_cv {
 
 struct fb2_part;
 
+// Tile schedule of the scalar thread-per-cell kernels (tiles.cu)
+struct TileSchedule {
+    int TC = 0;               // cells per tile
+    int64_t ntiles = 0;
+    int nslots = 0;           // NSYM + NB shared-memory slots per cell
+    int max_cols = 0;         // max tile-local columns
+    int64_t nentries = 0;
+    int32_t* d_conn = nullptr;        // [ntiles][nnpc][TC] node ids, tile-ordered SoA (padded with the last cell)
+    int32_t* d_ncells = nullptr;      // [ntiles]
+    int32_t* d_cell_ids = nullptr;    // [ntiles][TC] grid cell id (error reporting)
+    int64_t* d_col_ptr = nullptr;     // [ntiles+1]
+    int32_t* d_col_dof = nullptr;     // global dof of each tile-local column; bit 31 = complete
+    int64_t* d_ent_ptr = nullptr;     // [ntiles+1]
+    uint32_t* d_ent_rec = nullptr;    // (tile-local column << 16) | offset in the global column; 0xFFFF = f entry
+    uint16_t* d_ent_srcend = nullptr; // cumulative number of sources inside the tile
+    int64_t* d_src_ptr = nullptr;     // [ntiles+1]
+    uint16_t* d_src = nullptr;        // shared-memory slot index: slot * TC + cell_local
+};
+void fb2_tiles_free(TileSchedule* S);
+
 struct fb2_assembler {
+    TileSchedule* tiles = nullptr;
+    bool tiles_failed = false;
     fb2_dh* dh = nullptr;
     fb2_pattern* pat = nullptr;
     fb2_cv* cv = nullptr;
@@ -200,6 +222,7 @@ int fb2_pattern_build_device(fb2_pattern* p);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
 int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);
+int fb2_tiles_build(fb2_assembler* a, int TC);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 int fb2_check_device_error(fb2_ctx* ctx);

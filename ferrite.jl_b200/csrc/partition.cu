@@ -49,7 +49,8 @@ struct fb2_part {
     fb2_assembler* bound = nullptr;
     int bound_device = -1;
     int32_t* d_own_cells = nullptr;
-    uint8_t* d_col_owned = nullptr;
+    int32_t* d_col_owned = nullptr;   // list of local columns owned by other ranks
+    int64_t n_unowned = 0;
 };
 
 namespace {
@@ -108,13 +109,14 @@ __global__ void k_unpack_add(const int64_t* __restrict__ pos, int64_t nnz, const
     else if (t < nnz + nf && f) f[fd[t - nnz]] += in[t];
 }
 
-__global__ void k_mask_unowned(const uint8_t* __restrict__ owned, int64_t n, const int64_t* __restrict__ colptr,
+__global__ void k_mask_unowned(const int32_t* __restrict__ unowned, int64_t n, const int64_t* __restrict__ colptr,
                                double* __restrict__ nzval, double* __restrict__ f) {
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (w >= n || owned[w]) return;
-    for (int64_t k = colptr[w] + lane; k < colptr[w + 1]; k += 32) nzval[k] = 0.0;
-    if (lane == 0 && f) f[w] = 0.0;
+    if (w >= n) return;
+    const int c = unowned[w];
+    for (int64_t k = colptr[c] + lane; k < colptr[c + 1]; k += 32) nzval[k] = 0.0;
+    if (lane == 0 && f) f[c] = 0.0;
 }
 
 inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
@@ -359,10 +361,13 @@ extern "C" int fb2_partition_bind(fb2_part* P, fb2_assembler* a) {
         if (P->cell_is_own[l]) own.push_back((int32_t)l);
     FB2_CUDA(cudaMalloc(&P->d_own_cells, std::max<size_t>(own.size(), 1) * sizeof(int32_t)));
     FB2_CUDA(cudaMemcpy(P->d_own_cells, own.data(), own.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    std::vector<uint8_t> co(P->dof_owner.size());
-    for (size_t d = 0; d < co.size(); ++d) co[d] = P->dof_owner[d] == P->rank;
-    FB2_CUDA(cudaMalloc(&P->d_col_owned, co.size()));
-    FB2_CUDA(cudaMemcpy(P->d_col_owned, co.data(), co.size(), cudaMemcpyHostToDevice));
+    // list of the local columns this rank does NOT own (only these are visited by the mask kernel)
+    std::vector<int32_t> unowned;
+    for (size_t d = 0; d < P->dof_owner.size(); ++d)
+        if (P->dof_owner[d] != P->rank) unowned.push_back((int32_t)d);
+    P->n_unowned = (int64_t)unowned.size();
+    FB2_CUDA(cudaMalloc(&P->d_col_owned, std::max<size_t>(unowned.size(), 1) * sizeof(int32_t)));
+    FB2_CUDA(cudaMemcpy(P->d_col_owned, unowned.data(), unowned.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     P->bound = a;
     P->bound_device = ctx->device;
     return FB2_OK;
@@ -398,7 +403,8 @@ extern "C" int fb2_partition_mask_unowned(fb2_part* P, double* nzval_dev, double
     FB2_CHECK(P && P->bound && nzval_dev, FB2_ERR_BAD_ARG, "fb2_partition_mask_unowned: bad argument or plan not bound");
     fb2_ctx* ctx = P->bound->dh->grid->ctx;
     FB2_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = (int64_t)P->l2g_dof.size();
+    const int64_t n = P->n_unowned;
+    if (n == 0) return FB2_OK;
     k_mask_unowned<<<nblk(n * 32, 256), 256, 0, ctx->stream>>>(P->d_col_owned, n, P->bound->pat->d_colptr, nzval_dev, f_dev);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());

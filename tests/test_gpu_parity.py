@@ -98,6 +98,13 @@ ASSEMBLY_CASES = [
     ("tet-p1-heat", fb.Tetrahedron, (4, 4, 3), 1, 1, 2, "heat", {}),
     ("tet-p2-heat", fb.Tetrahedron, (3, 3, 3), 2, 1, 2, "heat", {}),
     ("tet-p2-heat-q3", fb.Tetrahedron, (3, 2, 3), 2, 1, 3, "heat", {}),
+    # sizes above the tile-kernel threshold (k_tile_scalar: Morton tiles, shared-memory aggregation)
+    ("hex-q1-heat-tiles", fb.Hexahedron, (17, 13, 11), 1, 1, 2, "heat", {"k": 2.0, "source": 3.0}),
+    ("quad-q1-heat-tiles", fb.Quadrilateral, (53, 41), 1, 1, 2, "heat", {"k": 1.3, "source": 0.7}),
+    ("tri-p2-heat-tiles", fb.Triangle, (31, 27), 2, 1, 2, "heat", {}),
+    ("tet-p2-heat-tiles", fb.Tetrahedron, (7, 6, 5), 2, 1, 2, "heat", {}),
+    ("tet-p1-heat-tiles", fb.Tetrahedron, (8, 7, 6), 1, 1, 2, "heat", {}),
+    ("hex-q1-mass-tiles", fb.Hexahedron, (13, 12, 11), 1, 1, 2, "mass", {"rho": 2.5}),
     ("hex-q1-mass", fb.Hexahedron, (5, 4, 4), 1, 1, 2, "mass", {"rho": 2.5}),
     ("quad-q2-mass", fb.Quadrilateral, (5, 5), 2, 1, 3, "mass", {"rho": 1.0}),
     ("quad-q1-elast", fb.Quadrilateral, (8, 7), 1, 2, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, -1.0)}),
@@ -156,7 +163,7 @@ def test_assembly_matches_oracle(ctx, case, scatter):
         ou = displacement(og, odh, vdim)
         u = torch.from_numpy(ou).to(f.device)
     O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
-    variants = [0, 1] if kind in ("heat", "mass") else [0]
+    variants = [0, 1, 2] if kind in ("heat", "mass") else [0]   # 0 tiles/default, 1 block kernel, 2 per-cell kernel
     for variant in variants:
         a = fb.start_assemble(K, f, scatter=scatter)
         a.variant = variant
@@ -191,8 +198,9 @@ def test_colored_is_bitwise_reproducible_and_coloring_valid(ctx):
     assert all(np.array_equal(runs[0][0], r[0]) and np.array_equal(runs[0][1], r[1]) for r in runs[1:])
 
 
-def test_fillzero_false_accumulates(ctx):
-    g, og, dh, odh, cv, ocv = build(fb.Quadrilateral, (6, 5), 1, 1, 2)
+@pytest.mark.parametrize("nel", [(6, 5), (41, 33)])      # per-cell kernel / tile kernel
+def test_fillzero_false_accumulates(ctx, nel):
+    g, og, dh, odh, cv, ocv = build(fb.Quadrilateral, nel, 1, 1, 2)
     K = fb.allocate_matrix(dh)
     f = ctx.zeros(dh.ndofs)
     a = fb.start_assemble(K, f)
@@ -360,8 +368,9 @@ def test_missing_entry_and_zero_skip(ctx):
         fb.scatter_(a, Ke)
 
 
-def test_detj_not_positive_is_reported(ctx):
-    og = O.generate_grid("hexahedron", (3, 3, 3))
+@pytest.mark.parametrize("nel", [(3, 3, 3), (12, 10, 9)])   # per-cell kernel / tile kernel
+def test_detj_not_positive_is_reported(ctx, nel):
+    og = O.generate_grid("hexahedron", nel)
     cells = og.cells.copy()
     cells[7] = cells[7][[1, 0, 3, 2, 5, 4, 7, 6]]      # mirror one cell -> negative Jacobian
     g = fb.Grid.from_arrays(fb.Hexahedron, cells, og.nodes)
