@@ -293,6 +293,7 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     cudaSetDevice(a->dh->grid->ctx->device);
     cudaFree(a->d_map);
     cudaFree(a->d_map8);
+    cudaFree(a->d_mapc);
     fb2_tiles_free(a->tiles);
     cudaFree(a->d_color_cells);
     cudaFree(a->d_cells);

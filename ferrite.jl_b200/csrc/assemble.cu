@@ -38,10 +38,14 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
 }
 
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
-int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
+int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0) {
     const int bs = 128;
     const unsigned grid = (unsigned)((A.ncount + bs - 1) / bs);
-    if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true><<<grid, bs, 0, ctx->stream>>>(A);
+    // NQ >= 8: keep the quadrature loop rolled (code fits the instruction cache; 4 % faster on Q1 hex); variant 2
+    // selects the fully unrolled body for comparison
+    constexpr bool ROLL = NQ >= 8;
+    if (atomic && variant == 2) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, false><<<grid, bs, 0, ctx->stream>>>(A);
+    else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);
     else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, false><<<grid, bs, 0, ctx->stream>>>(A);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
@@ -49,25 +53,28 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
 }
 
 template <int DIM, int NGEO, int NBS, int VDIM, int ELEM>
-int launch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
+int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     constexpr int TB = TileOf<NBS>::TB;
     constexpr int NT = (NBS + TB - 1) / TB;
-    const size_t per_cell = (size_t)fb2_blocks_smem_per_cell<DIM, NBS, ELEM>(A.nq) * sizeof(double);
-    int cells = 32;
-    while (cells > 1 && per_cell * cells > 100 * 1024) cells >>= 1;
-    const size_t smem = per_cell * cells;
-    FB2_CHECK(smem <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", per_cell);
-    int work = std::max(A.nq * cells, NBS * NT * cells);
-    int bs = std::min(256, (work + 31) / 32 * 32);
+    constexpr int N = NBS * VDIM;
+    FB2_TRY(fb2_map_build_cellmajor(a));
+    A.mapc = a->d_mapc;
+    // cells per CTA: enough rows to fill the block, shared memory small enough for >= 2 CTAs per SM when possible
+    int cells = 16;
+    while (cells > 1 && (fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells).total > 100 * 1024 || cells * N * NT > 768)) cells >>= 1;
+    const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells);
+    FB2_CHECK(L.total <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", L.total);
+    const int work = std::max(A.nq * cells, N * NT * cells);
+    const int bs = std::min(384, (work + 31) / 32 * 32);
     const unsigned grid = (unsigned)((A.ncount + cells - 1) / cells);
     if (atomic) {
         auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, true>;
-        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, bs, smem, ctx->stream>>>(A, cells);
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        k<<<grid, bs, L.total, ctx->stream>>>(A, cells);
     } else {
         auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, false>;
-        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, bs, smem, ctx->stream>>>(A, cells);
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+        k<<<grid, bs, L.total, ctx->stream>>>(A, cells);
     }
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
@@ -76,11 +83,11 @@ int launch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic) {
 
 // shape dispatch helpers -------------------------------------------------------------------------
 template <int ELEM, int VDIM_IS_DIM>
-int dispatch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
+int dispatch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
 #define CASE(CT, DIM, NGEO, NBS)                                                                  \
     if (celltype == CT && nbs == NBS) {                                                           \
-        if (VDIM_IS_DIM) { if (vdim == DIM) return launch_blocks<DIM, NGEO, NBS, DIM, ELEM>(ctx, A, atomic); } \
-        else { if (vdim == 1) return launch_blocks<DIM, NGEO, NBS, 1, ELEM>(ctx, A, atomic); }    \
+        if (VDIM_IS_DIM) { if (vdim == DIM) return launch_blocks<DIM, NGEO, NBS, DIM, ELEM>(a, ctx, A, atomic); } \
+        else { if (vdim == 1) return launch_blocks<DIM, NGEO, NBS, 1, ELEM>(a, ctx, A, atomic); }    \
     }
     CASE(FB2_TRIANGLE, 2, 3, 3)
     CASE(FB2_TRIANGLE, 2, 3, 6)
@@ -94,12 +101,12 @@ int dispatch_blocks(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, i
     return fb2_fail(FB2_ERR_UNSUPPORTED, "no kernel for cell type %d with %d scalar basis functions and vdim %d", celltype, nbs, vdim);
 }
 
-int dispatch_neohooke(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
+int dispatch_neohooke(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int celltype, int nbs, int vdim) {
     if (vdim == 3) {
-        if (celltype == FB2_TETRAHEDRON && nbs == 4) return launch_blocks<3, 4, 4, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
-        if (celltype == FB2_TETRAHEDRON && nbs == 10) return launch_blocks<3, 4, 10, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
-        if (celltype == FB2_HEXAHEDRON && nbs == 8) return launch_blocks<3, 8, 8, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
-        if (celltype == FB2_HEXAHEDRON && nbs == 27) return launch_blocks<3, 8, 27, 3, FB2_ELEM_NEOHOOKE>(ctx, A, atomic);
+        if (celltype == FB2_TETRAHEDRON && nbs == 4) return launch_blocks<3, 4, 4, 3, FB2_ELEM_NEOHOOKE>(a, ctx, A, atomic);
+        if (celltype == FB2_TETRAHEDRON && nbs == 10) return launch_blocks<3, 4, 10, 3, FB2_ELEM_NEOHOOKE>(a, ctx, A, atomic);
+        if (celltype == FB2_HEXAHEDRON && nbs == 8) return launch_blocks<3, 8, 8, 3, FB2_ELEM_NEOHOOKE>(a, ctx, A, atomic);
+        if (celltype == FB2_HEXAHEDRON && nbs == 27) return launch_blocks<3, 8, 27, 3, FB2_ELEM_NEOHOOKE>(a, ctx, A, atomic);
     }
     return fb2_fail(FB2_ERR_UNSUPPORTED, "Neo-Hooke needs a 3-D cell with a 3-component field");
 }
@@ -108,18 +115,21 @@ int dispatch_neohooke(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int celltype,
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
 int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate) {
     constexpr int NSYM = NB * (NB + 1) / 2;
-    constexpr int TC = (NSYM + NB) <= 44 ? 256 : 128;
-    if (atomic && variant == 0 && A.cells == nullptr && a->dh->grid->ncells >= 4 * TC) {
+    constexpr int TC = (NSYM + NB) <= 44 ? 128 : 64;   // one cell per thread; two CTAs per SM overlap their phases
+    // The tile kernel is opt-in (variant 5): on B200 it is slower than the per-cell kernel for Q1 hex (phase 2 costs as
+    // many instructions as it saves in L2 traffic); kept because it removes 80 % of the RED traffic.
+    if (atomic && variant == 5 && A.cells == nullptr && a->dh->grid->ncells >= 8 * TC) {
         FB2_TRY(fb2_tiles_build(a, TC));
         if (a->tiles) {
             const TileSchedule* S = a->tiles;
-            TileArgs T{S->d_conn, S->d_ncells, S->d_cell_ids, S->d_col_ptr, S->d_col_dof, S->d_ent_ptr, S->d_ent_rec,
-                       S->d_ent_srcend, S->d_src_ptr, S->d_src, S->max_cols, accumulate};
-            const size_t smem = (size_t)(NSYM + NB) * TC * sizeof(double) + (size_t)S->max_cols * (sizeof(int64_t) + sizeof(int32_t));
+            TileArgs T{S->d_conn, S->d_ncells, S->d_cell_ids, S->d_tile_base, S->d_ent_ptr, S->d_rec, S->d_src_ptr, S->d_src,
+                       S->max_ent, S->max_src, accumulate};
+            const size_t smem = (size_t)(NSYM + NB) * TC * sizeof(double) + (size_t)S->max_ent * sizeof(uint2) +
+                                (size_t)S->max_src * sizeof(uint16_t);
             if (smem <= 227 * 1024) {
-                auto k = k_tile_scalar<DIM, NGEO, NB, NQ, ELEM, TC>;
+                auto k = k_tile_scalar<DIM, NGEO, NB, NQ, ELEM, TC, 2>;
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k<<<(unsigned)S->ntiles, 128, smem, ctx->stream>>>(A, T);
+                k<<<(unsigned)S->ntiles, TC, smem, ctx->stream>>>(A, T);
                 ctx->launches++;
                 FB2_CUDA(cudaGetLastError());
                 return FB2_OK;
@@ -128,7 +138,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     }
     FB2_TRY(fb2_map_build_packed(a));
     A.map8 = reinterpret_cast<const uint4*>(a->d_map8);
-    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic);
+    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic, variant);
 }
 
 template <int ELEM>
@@ -236,16 +246,16 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
         case FB2_ELEM_HEAT:
             FB2_CHECK(vdim == 1, FB2_ERR_BAD_ARG, "the heat element needs a scalar field");
             if (variant != 1 && try_scalar<FB2_ELEM_HEAT>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
-            return dispatch_blocks<FB2_ELEM_HEAT, 0>(ctx, A, atomic, ct, nbs, vdim);
+            return dispatch_blocks<FB2_ELEM_HEAT, 0>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_MASS:
             FB2_CHECK(vdim == 1, FB2_ERR_UNSUPPORTED, "the mass element is implemented for scalar fields");
             if (variant != 1 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
-            return dispatch_blocks<FB2_ELEM_MASS, 0>(ctx, A, atomic, ct, nbs, vdim);
+            return dispatch_blocks<FB2_ELEM_MASS, 0>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY:
-            return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(ctx, A, atomic, ct, nbs, vdim);
+            return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_NEOHOOKE:
             FB2_CHECK(A.u != nullptr, FB2_ERR_BAD_ARG, "the Neo-Hooke element needs the current solution u");
-            return dispatch_neohooke(ctx, A, atomic, ct, nbs, vdim);
+            return dispatch_neohooke(a, ctx, A, atomic, ct, nbs, vdim);
     }
     return fb2_fail(FB2_ERR_BAD_ARG, "unknown element id %d", element);
 }

@@ -29,6 +29,7 @@ struct AsmArgs {
     const int64_t* colptr;
     const uint16_t* map;
     const uint4* map8;     // packed offsets for k_cell_scalar
+    const uint16_t* mapc;  // cell-major offsets for k_cell_blocks: [cell][mapstride], entry jl * n + il
     const int32_t* cells;  // optional indirection (colour / partition subset)
     int64_t ncount;        // number of cells handled by this launch
     int64_t ncells_pad;
@@ -115,7 +116,7 @@ __device__ __forceinline__ double fb2_det_inv(const double (&J)[DIM][DIM], doubl
 // Element integration shared by the thread-per-cell kernels: per quadrature point J = sum_j x_j (x) dM_j/dxi, det > 0,
 // dOmega = det*w, dNdx = dNdxi . inv(J); upper triangle of Ke (packed: (i,j), i <= j at j(j+1)/2 + i) and fe in registers.
 // Returns true if some det(J) was not positive.
-template <int DIM, int NGEO, int NB, int NQ, int ELEM>
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ROLLQ = false>
 __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const double (&x)[NGEO][DIM],
                                                    double (&Ke)[NB * (NB + 1) / 2], double (&fe)[NB]) {
     constexpr int NSYM = NB * (NB + 1) / 2;
@@ -129,7 +130,9 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
     const double* tdN = c_tab + A.o_dN;
     const double* tdM = c_tab + A.o_dM;
     bool bad = false;
-#pragma unroll
+    // ROLLQ keeps the quadrature loop rolled: 1/NQ of the code size (the unrolled Q1-hex body is ~70 KB of SASS, more
+    // than the 32 KB instruction cache level shared by the SM's warps)
+#pragma unroll(ROLLQ ? 1 : NQ)
     for (int q = 0; q < NQ; ++q) {
         double J[DIM][DIM];
 #pragma unroll
@@ -187,8 +190,8 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 // k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC>
-__global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false>
+__global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= A.ncount) return;
     const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(128) k_cell_scalar(const AsmArgs A) {
     constexpr int NSYM = NB * (NB + 1) / 2;
     double Ke[NSYM];
     double fe[NB];
-    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM>(A, x, Ke, fe);
+    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ>(A, x, Ke, fe);
     asm volatile("cp.async.wait_all;" ::: "memory");
     if (bad) {
         fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
@@ -273,35 +276,39 @@ struct TileArgs {
     const int32_t* conn;
     const int32_t* ncells;
     const int32_t* cell_ids;
-    const int64_t* col_ptr;
-    const int32_t* col_dof;
+    const int64_t* tile_base;
     const int64_t* ent_ptr;
-    const uint32_t* ent_rec;
-    const uint16_t* ent_srcend;
+    const uint2* rec;
     const int64_t* src_ptr;
     const uint16_t* src;
-    int max_cols;
+    int max_ent, max_src;
     int accumulate;  // 1: add onto existing values (fillzero = false)
 };
 
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, int TC>
-__global__ void __launch_bounds__(128, 2) k_tile_scalar(const AsmArgs A, const TileArgs T) {
-    extern __shared__ double sm[];                      // [NSYM + NB][TC] element values
+__device__ __forceinline__ void fb2_cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, int TC, int MB = 2>
+__global__ void __launch_bounds__(TC, MB) k_tile_scalar(const AsmArgs A, const TileArgs T) {
+    extern __shared__ double sm[];                      // [NSYM + NB][TC] element values, then the staged schedule
     constexpr int NSYM = NB * (NB + 1) / 2;
-    int64_t* s_colbase = reinterpret_cast<int64_t*>(sm + (size_t)(NSYM + NB) * TC);  // [max_cols]
-    int32_t* s_coldof = reinterpret_cast<int32_t*>(s_colbase + T.max_cols);           // [max_cols]
+    uint2* s_rec = reinterpret_cast<uint2*>(sm + (size_t)(NSYM + NB) * TC);   // [max_ent]
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(s_rec + T.max_ent);          // [max_src]
     const int64_t tile = blockIdx.x;
     const int ncell = __ldg(T.ncells + tile);
-    const int64_t c0 = __ldg(T.col_ptr + tile);
-    const int ncols = (int)(__ldg(T.col_ptr + tile + 1) - c0);
-    for (int c = threadIdx.x; c < ncols; c += 128) {
-        const int32_t d = __ldg(T.col_dof + c0 + c);
-        s_coldof[c] = d;
-        s_colbase[c] = __ldg(A.colptr + (d & 0x7fffffff));
-    }
+    const int64_t e0 = __ldg(T.ent_ptr + tile);
+    const int ne = (int)(__ldg(T.ent_ptr + tile + 1) - e0);
+    const int64_t s0 = __ldg(T.src_ptr + tile);
+    const int ns = (int)(__ldg(T.src_ptr + tile + 1) - s0);
+    // stage the tile's schedule into shared memory; it lands while the element matrices are integrated
+    // (segments are padded to multiples of 8 entries, so every chunk is 16-byte aligned)
+    for (int i = threadIdx.x; i < ne / 2; i += TC) fb2_cp_async16(s_rec + 2 * i, T.rec + e0 + 2 * i);
+    for (int i = threadIdx.x; i < ns / 8; i += TC) fb2_cp_async16(s_src + 8 * i, T.src + s0 + 8 * i);
     const double kscale = A.p[0], fscale = A.p[1];
-#pragma unroll 1
-    for (int cl = threadIdx.x; cl < TC; cl += 128) {
+    {
+        const int cl = threadIdx.x;
         if (cl < ncell) {
             double x[NGEO][DIM];
 #pragma unroll
@@ -319,76 +326,132 @@ __global__ void __launch_bounds__(128, 2) k_tile_scalar(const AsmArgs A, const T
             for (int i = 0; i < NB; ++i) sm[(NSYM + i) * TC + cl] = fscale * fe[i];
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    const int64_t e0 = __ldg(T.ent_ptr + tile);
-    const int ne = (int)(__ldg(T.ent_ptr + tile + 1) - e0);
-    const uint16_t* src = T.src + __ldg(T.src_ptr + tile);
     const bool want_f = A.f != nullptr && ELEM == FB2_ELEM_HEAT;
-    for (int e = threadIdx.x; e < ne; e += 128) {
-        const uint32_t rec = __ldg(T.ent_rec + e0 + e);
-        const int send = __ldg(T.ent_srcend + e0 + e);
-        const int sbeg = e ? (int)__ldg(T.ent_srcend + e0 + e - 1) : 0;
-        double sum = 0.0;
-        for (int s = sbeg; s < send; ++s) sum += sm[__ldg(src + s)];
-        const int col = rec >> 16;
-        const unsigned k = rec & 0xFFFFu;
-        const int32_t d = s_coldof[col];
-        const bool complete = d < 0;
-        double* dst;
-        if (k == 0xFFFFu) {
-            if (!want_f) continue;
-            dst = A.f + (d & 0x7fffffff);
-        } else {
-            dst = A.nzval + s_colbase[col] + k;
+    double* const nzbase = A.nzval + __ldg(T.tile_base + tile);
+    // two entries per thread and iteration: two independent shared-memory gather chains in flight
+    for (int eb = threadIdx.x; eb < ne; eb += 2 * TC) {
+        const uint2 r0 = s_rec[eb];
+        const bool has1 = eb + TC < ne;
+        const uint2 r1 = has1 ? s_rec[eb + TC] : make_uint2(0xFFFFFFFFu, 0u);
+        const int b0 = r0.y & 0xFFFFu, n0 = r0.y >> 16;
+        const int b1 = r1.y & 0xFFFFu, n1 = r1.y >> 16;
+        double sum0 = 0.0, sum1 = 0.0;
+        const int nmin = min(n0, n1);
+        int s = 0;
+        for (; s < nmin; ++s) {
+            const double v0 = sm[s_src[b0 + s]];
+            const double v1 = sm[s_src[b1 + s]];
+            sum0 += v0;
+            sum1 += v1;
         }
-        if (complete) {
-            if (T.accumulate) *dst += sum;   // nobody else touches a complete column
-            else *dst = sum;
-        } else if (sum != 0.0) {
-            atomicAdd(dst, sum);
+        for (int q = s; q < n0; ++q) sum0 += sm[s_src[b0 + q]];
+        for (int q = s; q < n1; ++q) sum1 += sm[s_src[b1 + q]];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned x = u ? r1.x : r0.x;
+            const double sum = u ? sum1 : sum0;
+            if (x == 0xFFFFFFFFu) continue;
+            double* dst;
+            if (x & 0x40000000u) {
+                if (!want_f) continue;
+                dst = A.f + (x & 0x3fffffffu);
+            } else {
+                dst = nzbase + (x & 0x3fffffffu);
+            }
+            if (x & 0x80000000u) {
+                if (T.accumulate) *dst += sum;   // nobody else touches a complete column
+                else *dst = sum;
+            } else if (sum != 0.0) {
+                atomicAdd(dst, sum);
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_cell_blocks: CTA per batch of CELLS cells.
+// k_cell_blocks: CTA per batch of CELLS cells (vector fields, higher order, Neo-Hooke).
+//   phase A : thread per (cell, qp): J, det > 0, J^-1, dOmega and the physical gradients of all scalar basis functions
+//             go to shared memory ([q][cell][a][d]); Neo-Hooke also stages P*dOmega and dP/dF*dOmega.
+//   staging : the cell's scatter indices are brought on chip once: its block of the cell-major uint16 offset map with
+//             cp.async (contiguous bytes), column bases colptr[dof_j] and the dofs themselves.
+//   phase B : thread per (cell, local row r = (a, c), tile of TB column nodes): integrates its TB*VDIM entries of row
+//             r in registers (low register count => several CTAs per SM hide the latencies) and scatters them.  The
+//             lanes of a warp hold CONSECUTIVE rows of one cell; rows (a, 0..VDIM-1) are adjacent in a CSC column, so
+//             the REDs of one instruction share 32-byte sectors (about 2.4x fewer L2 atomic sectors than one RED per
+//             (a, b) block and lane).
 // ------------------------------------------------------------------------------------------------
 template <int NBS>
 struct TileOf {
     static constexpr int TB = (NBS <= 8) ? NBS : (NBS == 10 ? 10 : 9);
 };
 
-// doubles of shared memory per cell
-template <int DIM, int NBS, int ELEM>
-__host__ __device__ constexpr int fb2_blocks_smem_per_cell(int nq) {
-    return nq * (NBS * DIM + 1) + (ELEM == FB2_ELEM_NEOHOOKE ? nq * 90 : 0);
+struct BlockSmem {
+    size_t g, dO, A, P, base, dof, map, total;   // byte offsets
+    int mapstride;                               // uint16 entries per cell in the staged map (multiple of 8)
+};
+
+template <int DIM, int NBS, int VDIM, int ELEM>
+__host__ __device__ inline BlockSmem fb2_blocks_smem(int nq, int cells) {
+    constexpr int N = NBS * VDIM;
+    BlockSmem L;
+    size_t o = 0;
+    L.g = o; o += sizeof(double) * (size_t)nq * cells * NBS * DIM;
+    L.dO = o; o += sizeof(double) * (size_t)nq * cells;
+    L.A = o; o += (ELEM == FB2_ELEM_NEOHOOKE ? sizeof(double) * (size_t)nq * cells * 81 : 0);
+    L.P = o; o += (ELEM == FB2_ELEM_NEOHOOKE ? sizeof(double) * (size_t)nq * cells * 9 : 0);
+    L.base = o; o += sizeof(int64_t) * (size_t)cells * N;
+    L.dof = o; o += sizeof(int32_t) * (size_t)cells * N;
+    o = (o + 15) / 16 * 16;
+    L.mapstride = (N * N + 7) / 8 * 8;
+    L.map = o; o += sizeof(uint16_t) * (size_t)cells * L.mapstride;
+    L.total = o;
+    return L;
 }
 
 template <int DIM, int NGEO, int NBS, int VDIM, int ELEM, bool ATOMIC>
-__global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int CELLS) {
-    extern __shared__ double sm[];
+__global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int CELLS) {
+    extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int TB = TileOf<NBS>::TB;
     constexpr int NT = (NBS + TB - 1) / TB;
     constexpr int N = NBS * VDIM;
     const int NQ = A.nq;
     const int64_t np = A.ncells_pad;
-    double* s_g = sm;                                   // [NQ][NBS][DIM][CELLS]
-    double* s_dO = s_g + (size_t)NQ * NBS * DIM * CELLS;  // [NQ][CELLS]
-    double* s_A = s_dO + (size_t)NQ * CELLS;              // neohooke: [NQ][81][CELLS] dP/dF * dO
-    double* s_P = s_A + (ELEM == FB2_ELEM_NEOHOOKE ? (size_t)NQ * 81 * CELLS : 0);  // [NQ][9][CELLS] P * dO
+    const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(NQ, CELLS);
+    double* s_g = reinterpret_cast<double*>(smraw + L.g);        // [NQ][CELLS][NBS][DIM]
+    double* s_dO = reinterpret_cast<double*>(smraw + L.dO);      // [NQ][CELLS]
+    double* s_A = reinterpret_cast<double*>(smraw + L.A);        // neo-hooke [NQ][CELLS][81]
+    double* s_P = reinterpret_cast<double*>(smraw + L.P);        // neo-hooke [NQ][CELLS][9]
+    int64_t* s_base = reinterpret_cast<int64_t*>(smraw + L.base);  // [CELLS][N]
+    int32_t* s_dof = reinterpret_cast<int32_t*>(smraw + L.dof);    // [CELLS][N]
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(smraw + L.map);  // [CELLS][mapstride]
     const int64_t cell0 = (int64_t)blockIdx.x * CELLS;
+    const int ncl = (int)min((int64_t)CELLS, A.ncount - cell0);
 
     const double* tw = c_tab + A.o_w;
     const double* tN = c_tab + A.o_N;
     const double* tdN = c_tab + A.o_dN;
     const double* tdM = c_tab + A.o_dM;
 
+    // ---- staging of the scatter indices (asynchronous; consumed after phase B's integration) --------------------
+    for (int i = threadIdx.x; i < ncl * (L.mapstride / 8); i += blockDim.x) {
+        const int cl = i / (L.mapstride / 8), ch = i - cl * (L.mapstride / 8);
+        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        fb2_cp_async16(s_map + (size_t)cl * L.mapstride + ch * 8, A.mapc + (size_t)cell * L.mapstride + ch * 8);
+    }
+    for (int i = threadIdx.x; i < ncl * N; i += blockDim.x) {
+        const int cl = i / N, jl = i - cl * N;
+        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        const int d = __ldg(A.cell_dofs + (size_t)jl * np + cell);
+        s_dof[i] = d;
+        s_base[i] = __ldg(A.colptr + d);
+    }
+
     // ---- phase A: geometry (+ material state) per (qp, cell) --------------------------------------
-    for (int item = threadIdx.x; item < NQ * CELLS; item += blockDim.x) {
-        const int q = item / CELLS, cl = item - q * CELLS;
-        const int64_t idx = cell0 + cl;
-        if (idx >= A.ncount) continue;
-        const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
+    for (int item = threadIdx.x; item < NQ * ncl; item += blockDim.x) {
+        const int q = item / ncl, cl = item - q * ncl;
+        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
         double J[DIM][DIM];
 #pragma unroll
         for (int a = 0; a < DIM; ++a)
@@ -410,6 +473,7 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
         const double dO = det * tw[q];
         s_dO[q * CELLS + cl] = dO;
         double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
         for (int i = 0; i < NBS; ++i) {
             double g[DIM];
 #pragma unroll
@@ -418,7 +482,7 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
 #pragma unroll
                 for (int a = 0; a < DIM; ++a) s = fma(tdN[(q * NBS + i) * DIM + a], Ji[a][b], s);
                 g[b] = s;
-                s_g[((size_t)(q * NBS + i) * DIM + b) * CELLS + cl] = s;
+                gq[i * DIM + b] = s;
             }
             if (ELEM == FB2_ELEM_NEOHOOKE) {
 #pragma unroll
@@ -446,24 +510,20 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
 #pragma unroll
                 for (int j = 0; j < 3; ++j) S[i][j] = mu * ((i == j ? 1.0 : 0.0) - Ci[i][j]) + cS * Ci[i][j];
             const double c1 = (mu - cS) * 0.5, c2 = lam * (2.0 * Jd - 1.0) * (Jd * 0.5);
-            // P = F S
+            double* Pq = s_P + ((size_t)q * CELLS + cl) * 9;
+            double* Aq = s_A + ((size_t)q * CELLS + cl) * 81;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    double pij = F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j];
-                    s_P[((size_t)q * 9 + i * 3 + j) * CELLS + cl] = pij * dO;
-                }
-            // dP_ij/dF_mn = delta_im S_jn + 2 F_ia dSdC_ajkn F_mk,
-            // dSdC_ajkn = c1 (Ci_ak Ci_nj + Ci_an Ci_kj) + c2 Ci_aj Ci_kn
-            // => F_ia dSdC_ajkn F_mk = c1 (G_ik' ... ) ; evaluate with FCi = F Ci (3x3): FCi_ik = F_ia Ci_ak
-            double FCi[3][3];
+                for (int j = 0; j < 3; ++j) Pq[i * 3 + j] = (F[i][0] * S[0][j] + F[i][1] * S[1][j] + F[i][2] * S[2][j]) * dO;
+            // dP_ij/dF_mn = delta_im S_jn + 2 F_ia dSdC_ajkn F_mk with
+            // dSdC_ajkn = c1 (Ci_ak Ci_nj + Ci_an Ci_kj) + c2 Ci_aj Ci_kn; with FCi = F Ci and W = FCi F^T:
+            // F_ia Ci_ak Ci_nj F_mk = W_im Ci_nj, F_ia Ci_an Ci_kj F_mk = FCi_in FCi_mj, F_ia Ci_aj Ci_kn F_mk = FCi_ij FCi_mn
+            double FCi[3][3], W[3][3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) FCi[i][k] = F[i][0] * Ci[0][k] + F[i][1] * Ci[1][k] + F[i][2] * Ci[2][k];
-            // W_im = F_ia Ci_ak F_mk = (FCi F^T)_im
-            double W[3][3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -476,153 +536,129 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
                     for (int m = 0; m < 3; ++m)
 #pragma unroll
                         for (int n = 0; n < 3; ++n) {
-                            // F_ia Ci_ak Ci_nj F_mk = W_im Ci_nj ; F_ia Ci_an Ci_kj F_mk = FCi_in FCi_mj ; F_ia Ci_aj Ci_kn F_mk = FCi_ij FCi_mn
                             double t = c1 * (W[i][m] * Ci[n][j] + FCi[i][n] * FCi[m][j]) + c2 * FCi[i][j] * FCi[m][n];
-                            double v = (i == m ? S[j][n] : 0.0) + 2.0 * t;
-                            s_A[((size_t)q * 81 + ((i * 3 + j) * 3 + m) * 3 + n) * CELLS + cl] = v * dO;
+                            Aq[((i * 3 + j) * 3 + m) * 3 + n] = ((i == m ? S[j][n] : 0.0) + 2.0 * t) * dO;
                         }
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
-    // ---- phase B: integrate node blocks and scatter ------------------------------------------------
-    const int nitems = NBS * NT * CELLS;
+    // ---- phase B: integrate one row of Ke per thread and scatter ---------------------------------------
+    const int nitems = ncl * NT * N;
     for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
-        const int cl = item % CELLS;
-        const int r = item / CELLS;
-        const int bt = r % NT, a = r / NT;
-        const int64_t idx = cell0 + cl;
-        if (idx >= A.ncount) continue;
-        const int64_t cell = A.cells ? (int64_t)A.cells[idx] : idx;
+        const int r = item % N;              // local row, fastest => lanes hold consecutive rows of one cell
+        const int rest = item / N;
+        const int bt = rest % NT, cl = rest / NT;
+        const int a = r / VDIM, c = r - a * VDIM;
+        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
         const int b0 = bt * TB;
-        double acc[TB][VDIM][VDIM];
+        double acc[TB][VDIM];
 #pragma unroll
         for (int t = 0; t < TB; ++t)
 #pragma unroll
-            for (int c = 0; c < VDIM; ++c)
-#pragma unroll
-                for (int d = 0; d < VDIM; ++d) acc[t][c][d] = 0.0;
-        double fa[VDIM];
-#pragma unroll
-        for (int c = 0; c < VDIM; ++c) fa[c] = 0.0;
+            for (int d = 0; d < VDIM; ++d) acc[t][d] = 0.0;
+        double fa = 0.0;
 
         for (int q = 0; q < NQ; ++q) {
             const double dO = s_dO[q * CELLS + cl];
+            const double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
             double ga[DIM];
 #pragma unroll
-            for (int b = 0; b < DIM; ++b) ga[b] = s_g[((size_t)(q * NBS + a) * DIM + b) * CELLS + cl];
+            for (int b = 0; b < DIM; ++b) ga[b] = gq[a * DIM + b];
             const double Na = tN[q * NBS + a];
             if (ELEM == FB2_ELEM_HEAT) {
-                fa[0] = fma(Na, dO, fa[0]);
+                fa = fma(Na, dO, fa);
 #pragma unroll
                 for (int b = 0; b < DIM; ++b) ga[b] *= dO;
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
-                        double s = acc[t][0][0];
+                        double s = acc[t][0];
 #pragma unroll
-                        for (int b = 0; b < DIM; ++b) s = fma(ga[b], s_g[((size_t)(q * NBS + b0 + t) * DIM + b) * CELLS + cl], s);
-                        acc[t][0][0] = s;
+                        for (int b = 0; b < DIM; ++b) s = fma(ga[b], gq[(b0 + t) * DIM + b], s);
+                        acc[t][0] = s;
                     }
                 }
             } else if (ELEM == FB2_ELEM_MASS) {
                 const double ns = Na * dO;
 #pragma unroll
                 for (int t = 0; t < TB; ++t)
-                    if (b0 + t < NBS) acc[t][0][0] = fma(ns, tN[q * NBS + b0 + t], acc[t][0][0]);
+                    if (b0 + t < NBS) acc[t][0] = fma(ns, tN[q * NBS + b0 + t], acc[t][0]);
             } else if (ELEM == FB2_ELEM_ELASTICITY) {
                 const double lam = A.p[0] * dO, mu = A.p[1] * dO;
-#pragma unroll
-                for (int c = 0; c < VDIM; ++c) fa[c] = fma(Na * dO, A.p[2 + c], fa[c]);
+                fa = fma(Na * dO, A.p[2 + c], fa);
+                const double gac = (c == 0 ? ga[0] : (c == 1 ? ga[1] : ga[DIM - 1]));
+                const double lgac = lam * gac;
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
                         double gb[DIM];
 #pragma unroll
-                        for (int b = 0; b < DIM; ++b) gb[b] = s_g[((size_t)(q * NBS + b0 + t) * DIM + b) * CELLS + cl];
+                        for (int b = 0; b < DIM; ++b) gb[b] = gq[(b0 + t) * DIM + b];
                         double dot = 0.0;
 #pragma unroll
                         for (int b = 0; b < DIM; ++b) dot = fma(ga[b], gb[b], dot);
-                        const double mdot = mu * dot;
+                        const double gbc = (c == 0 ? gb[0] : (c == 1 ? gb[1] : gb[DIM - 1]));
+                        const double mgbc = mu * gbc, mdot = mu * dot;
 #pragma unroll
-                        for (int c = 0; c < VDIM; ++c)
-#pragma unroll
-                            for (int d = 0; d < VDIM; ++d) {
-                                double v = fma(lam * ga[c], gb[d], mu * ga[d] * gb[c]);
-                                if (c == d) v += mdot;
-                                acc[t][c][d] += v;
-                            }
+                        for (int d = 0; d < VDIM; ++d) {
+                            // K[(a,c),(b,d)] += lam g_a[c] g_b[d] + mu (g_a[d] g_b[c] + delta_cd g_a.g_b)
+                            double v = fma(lgac, gb[d], mgbc * ga[d]);
+                            acc[t][d] += (d == c) ? v + mdot : v;
+                        }
                     }
                 }
-            } else {  // neo-hooke: block(a,b)[c][d] = sum_{j,n} ga[j] A[c][j][d][n] gb[n]
-                double h[3][3][3];
+            } else {  // neo-hooke: K[(a,c),(b,d)] = sum_{j,n} ga[j] A[c][j][d][n] gb[n]
+                const double* Aq = s_A + ((size_t)q * CELLS + cl) * 81;
+                const double* Pq = s_P + ((size_t)q * CELLS + cl) * 9;
+                double h[3][3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d)
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+                    for (int n = 0; n < 3; ++n) {
+                        double s = 0.0;
 #pragma unroll
-                        for (int n = 0; n < 3; ++n) {
-                            double s = 0.0;
+                        for (int j = 0; j < 3; ++j) s = fma(ga[j], Aq[((c * 3 + j) * 3 + d) * 3 + n], s);
+                        h[d][n] = s;
+                    }
+                double s = fa;
 #pragma unroll
-                            for (int j = 0; j < 3; ++j)
-                                s = fma(ga[j], s_A[((size_t)q * 81 + ((c * 3 + j) * 3 + d) * 3 + n) * CELLS + cl], s);
-                            h[c][d][n] = s;
-                        }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double s = fa[c];
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) s = fma(ga[j], s_P[((size_t)q * 9 + c * 3 + j) * CELLS + cl], s);
-                    fa[c] = fma(-Na * dO, A.p[2 + c], s);
-                }
+                for (int j = 0; j < 3; ++j) s = fma(ga[j], Pq[c * 3 + j], s);
+                fa = fma(-Na * dO, A.p[2 + c], s);
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
                         double gb[3];
 #pragma unroll
-                        for (int b = 0; b < 3; ++b) gb[b] = s_g[((size_t)(q * NBS + b0 + t) * 3 + b) * CELLS + cl];
+                        for (int b = 0; b < 3; ++b) gb[b] = gq[(b0 + t) * 3 + b];
 #pragma unroll
-                        for (int c = 0; c < 3; ++c)
+                        for (int d = 0; d < 3; ++d) {
+                            double v = acc[t][d];
 #pragma unroll
-                            for (int d = 0; d < 3; ++d) {
-                                double s = acc[t][c][d];
-#pragma unroll
-                                for (int n = 0; n < 3; ++n) s = fma(h[c][d][n], gb[n], s);
-                                acc[t][c][d] = s;
-                            }
+                            for (int n = 0; n < 3; ++n) v = fma(h[d][n], gb[n], v);
+                            acc[t][d] = v;
+                        }
                     }
                 }
             }
         }
-        // scatter the row block (a, :) x tile columns
+        // scatter row r: column bases and offsets come from shared memory (staged above)
         const double kscale = (ELEM == FB2_ELEM_HEAT || ELEM == FB2_ELEM_MASS) ? A.p[0] : 1.0;
+        const uint16_t* mrow = s_map + (size_t)cl * L.mapstride + r;   // offset of row r in column jl at mrow[jl * N]
+        const int64_t* brow = s_base + (size_t)cl * N;
         bool missing = false;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             if (b0 + t < NBS) {
-                // batch the index loads of this node block before its REDs (loads interleaved with atomics
-                // are serialised by the compiler: one memory round trip per entry)
-                int64_t base[VDIM];
-                unsigned off[VDIM][VDIM];
-                int dj[VDIM];
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
                     const int jl = (b0 + t) * VDIM + d;
-                    dj[d] = fb2_ldv_s32(A.cell_dofs + (size_t)jl * np + cell);
-#pragma unroll
-                    for (int c = 0; c < VDIM; ++c) off[d][c] = fb2_ldv_u16(A.map + (size_t)(jl * N + a * VDIM + c) * np + cell);
-                }
-#pragma unroll
-                for (int d = 0; d < VDIM; ++d) base[d] = fb2_ldv_s64(A.colptr + dj[d]);
-#pragma unroll
-                for (int d = 0; d < VDIM; ++d) {
-#pragma unroll
-                    for (int c = 0; c < VDIM; ++c) {
-                        const double v = kscale * acc[t][c][d];
-                        if (v != 0.0) {
-                            if (off[d][c] == 0xFFFFu) missing = true;
-                            else fb2_add<ATOMIC>(A.nzval + base[d] + off[d][c], v);
-                        }
+                    const double v = kscale * acc[t][d];
+                    const unsigned off = mrow[jl * N];
+                    if (v != 0.0) {
+                        if (off == 0xFFFFu) missing = true;
+                        else fb2_add<ATOMIC>(A.nzval + brow[jl] + off, v);
                     }
                 }
             }
@@ -630,11 +666,7 @@ __global__ void __launch_bounds__(256) k_cell_blocks(const AsmArgs A, const int 
         if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
         if (bt == 0 && A.f != nullptr && ELEM != FB2_ELEM_MASS) {
             const double fscale = ELEM == FB2_ELEM_HEAT ? A.p[1] : 1.0;
-#pragma unroll
-            for (int c = 0; c < VDIM; ++c) {
-                const int di = __ldg(A.cell_dofs + (size_t)(a * VDIM + c) * np + cell);
-                fb2_add<ATOMIC>(A.f + di, fscale * fa[c]);
-            }
+            fb2_add<ATOMIC>(A.f + s_dof[cl * N + r], fscale * fa);
         }
     }
 }

@@ -156,16 +156,14 @@ struct TileSchedule {
     int TC = 0;               // cells per tile
     int64_t ntiles = 0;
     int nslots = 0;           // NSYM + NB shared-memory slots per cell
-    int max_cols = 0;         // max tile-local columns
+    int max_ent = 0, max_src = 0;  // max (padded) entries / sources of a tile: shared-memory staging sizes
     int64_t nentries = 0;
     int32_t* d_conn = nullptr;        // [ntiles][nnpc][TC] node ids, tile-ordered SoA (padded with the last cell)
     int32_t* d_ncells = nullptr;      // [ntiles]
     int32_t* d_cell_ids = nullptr;    // [ntiles][TC] grid cell id (error reporting)
-    int64_t* d_col_ptr = nullptr;     // [ntiles+1]
-    int32_t* d_col_dof = nullptr;     // global dof of each tile-local column; bit 31 = complete
+    int64_t* d_tile_base = nullptr;   // [ntiles] smallest nzval position touched by the tile
     int64_t* d_ent_ptr = nullptr;     // [ntiles+1]
-    uint32_t* d_ent_rec = nullptr;    // (tile-local column << 16) | offset in the global column; 0xFFFF = f entry
-    uint16_t* d_ent_srcend = nullptr; // cumulative number of sources inside the tile
+    uint2* d_rec = nullptr;           // per entry {target | flags, first source | nsources << 16}, see tiles.cu
     int64_t* d_src_ptr = nullptr;     // [ntiles+1]
     uint16_t* d_src = nullptr;        // shared-memory slot index: slot * TC + cell_local
 };
@@ -179,6 +177,7 @@ struct fb2_assembler {
     fb2_cv* cv = nullptr;
     int n = 0;                     // dofs per cell covered by the element (= ndpc)
     uint16_t* d_map = nullptr;     // [n*n][ncells_pad]: offset of row dof_i inside column dof_j, e = j*n + i
+    uint16_t* d_mapc = nullptr;    // cell-major copy for k_cell_blocks: [ncells][ceil8(n*n)] (lazy)
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     // colouring (lazy)
     int ncolors = 0;
@@ -222,6 +221,7 @@ int fb2_pattern_build_device(fb2_pattern* p);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
 int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);
+int fb2_map_build_cellmajor(fb2_assembler* a);
 int fb2_tiles_build(fb2_assembler* a, int TC);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);

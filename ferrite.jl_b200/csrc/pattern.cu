@@ -159,6 +159,17 @@ __global__ void k_pack_map(const uint16_t* __restrict__ map, int64_t ncells_pad,
     map8[t] = e < nn ? map[(size_t)e * ncells_pad + c] : (uint16_t)0xFFFF;
 }
 
+// Cell-major variant for k_cell_blocks: the n*n offsets of one cell are contiguous (padded to a multiple of 8
+// entries), so a CTA stages a cell's block with 16-byte cp.async copies.
+__global__ void k_cellmajor_map(const uint16_t* __restrict__ map, int64_t ncells, int64_t ncells_pad, int nn, int stride,
+                                uint16_t* __restrict__ mapc) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells * stride) return;
+    int64_t c = t / stride;
+    int e = (int)(t - c * stride);
+    mapc[t] = e < nn ? map[(size_t)e * ncells_pad + c] : (uint16_t)0xFFFF;
+}
+
 __global__ void k_to_onebased64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) out[t] = (int64_t)in[t] + 1;
@@ -408,6 +419,21 @@ int fb2_map_build_packed(fb2_assembler* a) {
     const int64_t total = (int64_t)nchunks * 8 * g->ncells_pad;
     FB2_CUDA(cudaMalloc(&a->d_map8, total * sizeof(uint16_t)));
     k_pack_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells_pad, nn, nchunks, a->d_map8);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FB2_OK;
+}
+
+int fb2_map_build_cellmajor(fb2_assembler* a) {
+    if (a->d_mapc) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int nn = a->n * a->n, stride = (nn + 7) / 8 * 8;
+    const int64_t total = g->ncells * stride;
+    FB2_CUDA(cudaMalloc(&a->d_mapc, total * sizeof(uint16_t)));
+    k_cellmajor_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells, g->ncells_pad, nn, stride, a->d_mapc);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     FB2_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -30,34 +30,70 @@ struct TileHost {
     std::vector<int32_t> col_dof;      // bit 31 = complete
     std::vector<uint32_t> ent_col;     // tile-local column of each entry
     std::vector<int32_t> ent_row;      // global row dof, or -1 for the f entry of the column
-    std::vector<uint16_t> ent_srcend;
+    std::vector<uint16_t> ent_srcend;  // first source of the entry
+    std::vector<uint16_t> ent_nsrc;    // number of sources
     std::vector<uint16_t> src;
 };
 
-// resolve (column dof, row dof) -> offset k of the row inside the column; CTA per tile
+// Resolve every entry (column dof, row dof) to its position in nzval and pack the kernel's records; CTA per tile.
+// Record = uint2 { x = target | flags, y = first source | (number of sources << 16) } with
+//   nzval entry: x = (position - tile_base[t])          (30 bits)   | bit 31 if the column is complete in the tile
+//   f entry:     x = dof                                (30 bits)   | bit 30 | bit 31 if complete
+//   padding:     x = 0xFFFFFFFF
+// status[0] counts entries missing in the pattern, status[1] offsets that do not fit 30 bits.
 __global__ void k_resolve_entries(const int64_t* __restrict__ ent_ptr, const int64_t* __restrict__ col_ptr,
                                   const int32_t* __restrict__ col_dof, const uint32_t* __restrict__ ent_col,
-                                  const int32_t* __restrict__ ent_row, const int64_t* __restrict__ colptr,
-                                  const int32_t* __restrict__ rowval, uint32_t* __restrict__ ent_rec, int* __restrict__ nmissing) {
+                                  const int32_t* __restrict__ ent_row, const uint16_t* __restrict__ ent_srcbeg,
+                                  const uint16_t* __restrict__ ent_nsrc,
+                                  const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
+                                  int64_t* __restrict__ pos_tmp, int64_t* __restrict__ tile_base, uint2* __restrict__ rec,
+                                  int* __restrict__ status) {
     const int64_t t = blockIdx.x;
     const int64_t e0 = ent_ptr[t], e1 = ent_ptr[t + 1], c0 = col_ptr[t];
+    __shared__ unsigned long long s_min;
+    if (threadIdx.x == 0) s_min = ~0ull;
+    __syncthreads();
+    unsigned long long mymin = ~0ull;
     for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const uint32_t cl = ent_col[e];
         const int32_t row = ent_row[e];
-        uint32_t k = 0xFFFFu;
-        if (row >= 0) {
+        int64_t p = -1;
+        if (cl != 0xFFFFu && row >= 0) {
             const int32_t j = col_dof[c0 + cl] & 0x7fffffff;
-            int64_t b = colptr[j], lo = b, hi = colptr[j + 1];
-            k = 0xFFFEu;  // "missing"
+            int64_t lo = colptr[j], hi = colptr[j + 1];
             while (lo < hi) {
                 int64_t mid = (lo + hi) >> 1;
                 int32_t r = rowval[mid];
-                if (r == row) { k = (uint32_t)(mid - b); break; }
+                if (r == row) { p = mid; break; }
                 if (r < row) lo = mid + 1; else hi = mid;
             }
-            if (k == 0xFFFEu) atomicAdd(nmissing, 1);
+            if (p < 0) atomicAdd(&status[0], 1);
+            else mymin = min(mymin, (unsigned long long)p);
         }
-        ent_rec[e] = (cl << 16) | k;
+        pos_tmp[e] = p;
+    }
+    atomicMin(&s_min, mymin);
+    __syncthreads();
+    const int64_t base = s_min == ~0ull ? 0 : (int64_t)s_min;
+    if (threadIdx.x == 0) tile_base[t] = base;
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const uint32_t cl = ent_col[e];
+        uint2 r;
+        r.x = 0xFFFFFFFFu;
+        r.y = (unsigned)ent_srcbeg[e] | ((unsigned)ent_nsrc[e] << 16);
+        if (cl != 0xFFFFu) {
+            const int32_t cd = col_dof[c0 + cl];
+            const unsigned complete = cd < 0 ? 0x80000000u : 0u;
+            if (ent_row[e] < 0) {
+                r.x = (unsigned)(cd & 0x3fffffff) | 0x40000000u | complete;
+                if ((cd & 0x7fffffff) >= 0x40000000) atomicAdd(&status[1], 1);
+            } else {
+                const int64_t rel = pos_tmp[e] - base;
+                if (rel < 0 || rel >= 0x40000000ll) atomicAdd(&status[1], 1);
+                r.x = (unsigned)(rel & 0x3fffffff) | complete;
+            }
+        }
+        rec[e] = r;
     }
 }
 
@@ -72,8 +108,8 @@ int upload(T** d, const std::vector<T>& h) {
 
 void fb2_tiles_free(TileSchedule* S) {
     if (!S) return;
-    cudaFree(S->d_conn); cudaFree(S->d_ncells); cudaFree(S->d_cell_ids); cudaFree(S->d_col_ptr); cudaFree(S->d_col_dof);
-    cudaFree(S->d_ent_ptr); cudaFree(S->d_ent_rec); cudaFree(S->d_ent_srcend); cudaFree(S->d_src_ptr); cudaFree(S->d_src);
+    cudaFree(S->d_conn); cudaFree(S->d_ncells); cudaFree(S->d_cell_ids); cudaFree(S->d_tile_base);
+    cudaFree(S->d_ent_ptr); cudaFree(S->d_rec); cudaFree(S->d_src_ptr); cudaFree(S->d_src);
     delete S;
 }
 
@@ -121,14 +157,14 @@ int fb2_tiles_build(fb2_assembler* a, int TC) {
     // ---- per-tile schedules ---------------------------------------------------------------------------------------------------
     std::vector<TileHost> tiles((size_t)ntiles);
     std::vector<int32_t> h_conn((size_t)ntiles * nnpc * TC), h_ncells((size_t)ntiles), h_cell_ids((size_t)ntiles * TC);
-    int max_cols = 0;
+    int max_cols = 0, max_ent = 0, max_src = 0;
     bool overflow = false;
 #pragma omp parallel
     {
         std::vector<int32_t> cols;
         std::vector<std::pair<uint64_t, uint16_t>> pairs;
         std::vector<int32_t> incount;
-#pragma omp for schedule(dynamic, 16) reduction(max : max_cols)
+#pragma omp for schedule(dynamic, 16) reduction(max : max_cols, max_ent, max_src)
         for (int64_t t = 0; t < ntiles; ++t) {
             const int64_t c0 = t * TC, nc = std::min<int64_t>(TC, ncells - c0);
             h_ncells[t] = (int32_t)nc;
@@ -174,16 +210,42 @@ int fb2_tiles_build(fb2_assembler* a, int TC) {
             }
             std::sort(pairs.begin(), pairs.end());
             T.src.reserve(pairs.size());
+            std::vector<uint32_t> e_col;
+            std::vector<int32_t> e_row;
+            std::vector<uint16_t> e_beg, e_n;
             for (size_t i = 0; i < pairs.size(); ++i) {
                 if (i == 0 || pairs[i].first != pairs[i - 1].first) {
-                    if (i) T.ent_srcend.push_back((uint16_t)i);
-                    T.ent_col.push_back((uint32_t)(pairs[i].first >> 32));
+                    e_col.push_back((uint32_t)(pairs[i].first >> 32));
                     const uint32_t r = (uint32_t)(pairs[i].first & 0xFFFFFFFFull);
-                    T.ent_row.push_back(r == 0xFFFFFFFFu ? -1 : (int32_t)r);
+                    e_row.push_back(r == 0xFFFFFFFFu ? -1 : (int32_t)r);
+                    e_beg.push_back((uint16_t)i);
+                    e_n.push_back(0);
                 }
+                e_n.back()++;
                 T.src.push_back(pairs[i].second);
             }
-            T.ent_srcend.push_back((uint16_t)pairs.size());
+            // Order the entries by their number of sources (descending, stable): the lanes of a warp then run the same
+            // gather length (no SIMT divergence in phase 2).  Neighbouring entries of one class still share sectors often.
+            std::vector<int> perm(e_col.size());
+            for (size_t i = 0; i < perm.size(); ++i) perm[i] = (int)i;
+            std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return e_n[x] > e_n[y]; });
+            for (int i : perm) {
+                T.ent_col.push_back(e_col[i]);
+                T.ent_row.push_back(e_row[i]);
+                T.ent_srcend.push_back(e_beg[i]);   // first source
+                T.ent_nsrc.push_back(e_n[i]);
+            }
+            // pad to multiples of 8 so that every per-tile segment starts 16-byte aligned (cp.async staging);
+            // padding entries carry the skip marker (column 0xFFFF) and no sources
+            while (T.ent_col.size() % 8) {
+                T.ent_col.push_back(0xFFFFu);
+                T.ent_row.push_back(-1);
+                T.ent_srcend.push_back(0);
+                T.ent_nsrc.push_back(0);
+            }
+            while (T.src.size() % 8) T.src.push_back(0);
+            max_ent = std::max(max_ent, (int)T.ent_col.size());
+            max_src = std::max(max_src, (int)T.src.size());
         }
     }
     if (overflow) { a->tiles_failed = true; return FB2_OK; }
@@ -197,7 +259,7 @@ int fb2_tiles_build(fb2_assembler* a, int TC) {
     }
     std::vector<int32_t> col_dof((size_t)col_ptr[ntiles]), ent_row((size_t)ent_ptr[ntiles]);
     std::vector<uint32_t> ent_col((size_t)ent_ptr[ntiles]);
-    std::vector<uint16_t> ent_srcend((size_t)ent_ptr[ntiles]), src((size_t)src_ptr[ntiles]);
+    std::vector<uint16_t> ent_srcend((size_t)ent_ptr[ntiles]), ent_nsrc((size_t)ent_ptr[ntiles]), src((size_t)src_ptr[ntiles]);
 #pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < ntiles; ++t) {
         const TileHost& T = tiles[t];
@@ -205,6 +267,7 @@ int fb2_tiles_build(fb2_assembler* a, int TC) {
         std::copy(T.ent_col.begin(), T.ent_col.end(), ent_col.begin() + ent_ptr[t]);
         std::copy(T.ent_row.begin(), T.ent_row.end(), ent_row.begin() + ent_ptr[t]);
         std::copy(T.ent_srcend.begin(), T.ent_srcend.end(), ent_srcend.begin() + ent_ptr[t]);
+        std::copy(T.ent_nsrc.begin(), T.ent_nsrc.end(), ent_nsrc.begin() + ent_ptr[t]);
         std::copy(T.src.begin(), T.src.end(), src.begin() + src_ptr[t]);
     }
     std::vector<TileHost>().swap(tiles);
@@ -213,36 +276,50 @@ int fb2_tiles_build(fb2_assembler* a, int TC) {
     S->TC = TC;
     S->ntiles = ntiles;
     S->nslots = nsym + nb;
-    S->max_cols = max_cols;
+    S->max_ent = max_ent;
+    S->max_src = max_src;
     S->nentries = ent_ptr[ntiles];
+    // temporaries of the resolve pass
+    int64_t *d_col_ptr = nullptr, *d_pos = nullptr;
+    int32_t *d_col_dof = nullptr, *d_ent_row = nullptr;
     uint32_t* d_ent_col = nullptr;
-    int32_t* d_ent_row = nullptr;
-    int* d_missing = nullptr;
+    uint16_t *d_srcend = nullptr, *d_nsrc = nullptr;
+    int* d_status = nullptr;
     int rc = FB2_OK;
+    auto free_tmp = [&]() {
+        cudaFree(d_col_ptr); cudaFree(d_pos); cudaFree(d_col_dof); cudaFree(d_ent_row); cudaFree(d_ent_col); cudaFree(d_srcend);
+        cudaFree(d_nsrc); cudaFree(d_status);
+        d_col_ptr = d_pos = nullptr; d_col_dof = d_ent_row = nullptr; d_ent_col = nullptr; d_srcend = nullptr; d_nsrc = nullptr; d_status = nullptr;
+    };
     auto fail = [&](int code) {
-        cudaFree(d_ent_col); cudaFree(d_ent_row); cudaFree(d_missing);
+        free_tmp();
         fb2_tiles_free(S);
         return code;
     };
     if ((rc = upload(&S->d_conn, h_conn)) || (rc = upload(&S->d_ncells, h_ncells)) || (rc = upload(&S->d_cell_ids, h_cell_ids)) ||
-        (rc = upload(&S->d_col_ptr, col_ptr)) || (rc = upload(&S->d_col_dof, col_dof)) || (rc = upload(&S->d_ent_ptr, ent_ptr)) ||
-        (rc = upload(&S->d_ent_srcend, ent_srcend)) || (rc = upload(&S->d_src_ptr, src_ptr)) || (rc = upload(&S->d_src, src)) ||
+        (rc = upload(&S->d_ent_ptr, ent_ptr)) || (rc = upload(&S->d_src_ptr, src_ptr)) || (rc = upload(&S->d_src, src)) ||
+        (rc = upload(&d_col_ptr, col_ptr)) || (rc = upload(&d_col_dof, col_dof)) || (rc = upload(&d_srcend, ent_srcend)) || (rc = upload(&d_nsrc, ent_nsrc)) ||
         (rc = upload(&d_ent_col, ent_col)) || (rc = upload(&d_ent_row, ent_row)))
         return fail(rc);
-    cudaError_t e = cudaMalloc(&S->d_ent_rec, std::max<size_t>(ent_col.size(), 1) * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_missing, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_missing, 0, sizeof(int), ctx->stream);
+    const size_t ne = std::max<size_t>(ent_col.size(), 1);
+    cudaError_t e = cudaMalloc(&S->d_rec, ne * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&S->d_tile_base, (size_t)ntiles * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_pos, ne * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_status, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 2 * sizeof(int), ctx->stream);
     if (e != cudaSuccess) return fail(fb2_fail(FB2_ERR_OOM, "tile schedule: %s", cudaGetErrorString(e)));
-    k_resolve_entries<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(S->d_ent_ptr, S->d_col_ptr, S->d_col_dof, d_ent_col, d_ent_row,
-                                                               a->pat->d_colptr, a->pat->d_rowval, S->d_ent_rec, d_missing);
+    k_resolve_entries<<<(unsigned)ntiles, 256, 0, ctx->stream>>>(S->d_ent_ptr, d_col_ptr, d_col_dof, d_ent_col, d_ent_row, d_srcend, d_nsrc,
+                                                               a->pat->d_colptr, a->pat->d_rowval, d_pos, S->d_tile_base, S->d_rec,
+                                                               d_status);
     ctx->launches++;
-    int missing = 0;
-    e = cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    int status[2] = {0, 0};
+    e = cudaMemcpyAsync(status, d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_ent_col); cudaFree(d_ent_row); cudaFree(d_missing);
-    d_ent_col = nullptr; d_ent_row = nullptr; d_missing = nullptr;
+    free_tmp();
     if (e != cudaSuccess) return fail(fb2_fail(FB2_ERR_CUDA, "tile schedule: %s", cudaGetErrorString(e)));
-    if (missing > 0) {  // the pattern lacks entries: keep the per-cell kernel, which implements the zero-skip semantics
+    if (status[0] > 0 || status[1] > 0) {
+        // the pattern lacks entries (the per-cell kernel implements the zero-skip semantics) or a tile spans more
+        // than 2^30 nzval positions: keep the per-cell kernel
         fb2_tiles_free(S);
         a->tiles_failed = true;
         return FB2_OK;

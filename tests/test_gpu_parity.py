@@ -163,7 +163,7 @@ def test_assembly_matches_oracle(ctx, case, scatter):
         ou = displacement(og, odh, vdim)
         u = torch.from_numpy(ou).to(f.device)
     O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
-    variants = [0, 1, 2] if kind in ("heat", "mass") else [0]   # 0 tiles/default, 1 block kernel, 2 per-cell kernel
+    variants = [0, 1, 2, 5] if kind in ("heat", "mass") else [0]   # 0 per-cell kernel, 1 block kernel, 2 unrolled, 5 tile kernel
     for variant in variants:
         a = fb.start_assemble(K, f, scatter=scatter)
         a.variant = variant
@@ -204,9 +204,11 @@ def test_fillzero_false_accumulates(ctx, nel):
     K = fb.allocate_matrix(dh)
     f = ctx.zeros(dh.ndofs)
     a = fb.start_assemble(K, f)
+    a.variant = 5 if nel[0] > 10 else 0
     fb.assemble_(a, fb.HeatElement(), cv)
     once = K.nzval.clone()
     a2 = fb.start_assemble(K, f, fillzero=False)
+    a2.variant = a.variant
     fb.assemble_(a2, fb.HeatElement(), cv)
     fb.finish_assemble(a2)
     assert np.allclose(K.nzval.cpu().numpy(), 2 * once.cpu().numpy(), rtol=1e-14)
@@ -379,6 +381,7 @@ def test_detj_not_positive_is_reported(ctx, nel):
     K = fb.allocate_matrix(dh)
     cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, 2), ip)
     a = fb.start_assemble(K, ctx.zeros(dh.ndofs))
+    a.variant = 5 if nel[0] > 10 else 0
     fb.assemble_(a, fb.HeatElement(), cv)
     with pytest.raises(fb.DetJNotPositive) as e:
         fb.finish_assemble(a)
