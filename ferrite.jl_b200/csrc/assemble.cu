@@ -54,18 +54,17 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0) 
 
 template <int DIM, int NGEO, int NBS, int VDIM, int ELEM>
 int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
-    constexpr int TB = TileOf<NBS>::TB;
+    constexpr int TB = TileOf<NBS, VDIM>::TB;
     constexpr int NT = (NBS + TB - 1) / TB;
-    constexpr int N = NBS * VDIM;
     FB2_TRY(fb2_map_build_cellmajor(a));
     A.mapc = a->d_mapc;
-    // cells per CTA: enough rows to fill the block, shared memory small enough for >= 2 CTAs per SM when possible
-    int cells = 16;
-    while (cells > 1 && (fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells).total > 100 * 1024 || cells * N * NT > 768)) cells >>= 1;
+    // cells per CTA: as many as give <= 256 phase-B rows (one row of Ke per thread); ~100 registers per thread then
+    // allow 2-3 CTAs per SM, which is what hides the shared-memory and FP64 latencies
+    int cells = std::max(1, 256 / (NBS * NT));
+    while (cells > 1 && fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells).total > 100 * 1024) --cells;
     const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells);
     FB2_CHECK(L.total <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", L.total);
-    const int work = std::max(A.nq * cells, N * NT * cells);
-    const int bs = std::min(384, (work + 31) / 32 * 32);
+    const int bs = std::min(256, (NBS * NT * cells + 31) / 32 * 32);
     const unsigned grid = (unsigned)((A.ncount + cells - 1) / cells);
     if (atomic) {
         auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, true>;

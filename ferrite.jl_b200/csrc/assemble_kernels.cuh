@@ -382,14 +382,17 @@ __global__ void __launch_bounds__(TC, MB) k_tile_scalar(const AsmArgs A, const T
 //             the REDs of one instruction share 32-byte sectors (about 2.4x fewer L2 atomic sectors than one RED per
 //             (a, b) block and lane).
 // ------------------------------------------------------------------------------------------------
-template <int NBS>
+template <int NBS, int VDIM>
 struct TileOf {
-    static constexpr int TB = (NBS <= 8) ? NBS : (NBS == 10 ? 10 : 9);
+    // column nodes per phase-B thread: keeps the accumulators (TB * VDIM^2 doubles) around 30-40 registers pairs
+    static constexpr int TB = VDIM == 1 ? ((NBS <= 8) ? NBS : (NBS == 10 ? 10 : 9))
+                            : VDIM == 2 ? NBS
+                                        : (NBS == 27 ? 3 : (NBS == 10 ? 5 : 4));
 };
 
 struct BlockSmem {
-    size_t g, dO, A, P, base, dof, map, total;   // byte offsets
-    int mapstride;                               // uint16 entries per cell in the staged map (multiple of 8)
+    size_t g, dO, Ji, A, P, base, dof, map, total;   // byte offsets
+    int mapstride;                                   // uint16 entries per cell in the staged map (multiple of 8)
 };
 
 template <int DIM, int NBS, int VDIM, int ELEM>
@@ -399,6 +402,7 @@ __host__ __device__ inline BlockSmem fb2_blocks_smem(int nq, int cells) {
     size_t o = 0;
     L.g = o; o += sizeof(double) * (size_t)nq * cells * NBS * DIM;
     L.dO = o; o += sizeof(double) * (size_t)nq * cells;
+    L.Ji = o; o += sizeof(double) * (size_t)nq * cells * DIM * DIM;
     L.A = o; o += (ELEM == FB2_ELEM_NEOHOOKE ? sizeof(double) * (size_t)nq * cells * 81 : 0);
     L.P = o; o += (ELEM == FB2_ELEM_NEOHOOKE ? sizeof(double) * (size_t)nq * cells * 9 : 0);
     L.base = o; o += sizeof(int64_t) * (size_t)cells * N;
@@ -411,9 +415,9 @@ __host__ __device__ inline BlockSmem fb2_blocks_smem(int nq, int cells) {
 }
 
 template <int DIM, int NGEO, int NBS, int VDIM, int ELEM, bool ATOMIC>
-__global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int CELLS) {
+__global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const int CELLS) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    constexpr int TB = TileOf<NBS>::TB;
+    constexpr int TB = TileOf<NBS, VDIM>::TB;
     constexpr int NT = (NBS + TB - 1) / TB;
     constexpr int N = NBS * VDIM;
     const int NQ = A.nq;
@@ -421,6 +425,7 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
     const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(NQ, CELLS);
     double* s_g = reinterpret_cast<double*>(smraw + L.g);        // [NQ][CELLS][NBS][DIM]
     double* s_dO = reinterpret_cast<double*>(smraw + L.dO);      // [NQ][CELLS]
+    double* s_Ji = reinterpret_cast<double*>(smraw + L.Ji);      // [NQ][CELLS][DIM][DIM]
     double* s_A = reinterpret_cast<double*>(smraw + L.A);        // neo-hooke [NQ][CELLS][81]
     double* s_P = reinterpret_cast<double*>(smraw + L.P);        // neo-hooke [NQ][CELLS][9]
     int64_t* s_base = reinterpret_cast<int64_t*>(smraw + L.base);  // [CELLS][N]
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
     const double* tdN = c_tab + A.o_dN;
     const double* tdM = c_tab + A.o_dM;
 
-    // ---- staging of the scatter indices (asynchronous; consumed after phase B's integration) --------------------
+    // ---- staging of the scatter indices (asynchronous; consumed by the scatter at the end of phase B) --------------
     for (int i = threadIdx.x; i < ncl * (L.mapstride / 8); i += blockDim.x) {
         const int cl = i / (L.mapstride / 8), ch = i - cl * (L.mapstride / 8);
         const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
         s_base[i] = __ldg(A.colptr + d);
     }
 
-    // ---- phase A: geometry (+ material state) per (qp, cell) --------------------------------------
+    // ---- phase A1: per (qp, cell): J, det > 0, J^-1, dOmega ---------------------------------------------------------
     for (int item = threadIdx.x; item < NQ * ncl; item += blockDim.x) {
         const int q = item / ncl, cl = item - q * ncl;
         const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
@@ -470,30 +475,45 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
         double Ji[DIM][DIM];
         const double det = fb2_det_inv<DIM>(J, Ji);
         if (!(det > 0.0)) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
-        const double dO = det * tw[q];
-        s_dO[q * CELLS + cl] = dO;
-        double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
-        for (int i = 0; i < NBS; ++i) {
-            double g[DIM];
+        s_dO[q * CELLS + cl] = det * tw[q];
+        double* Jq = s_Ji + ((size_t)q * CELLS + cl) * DIM * DIM;
 #pragma unroll
-            for (int b = 0; b < DIM; ++b) {
-                double s = 0.0;
+        for (int a = 0; a < DIM; ++a)
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) s = fma(tdN[(q * NBS + i) * DIM + a], Ji[a][b], s);
-                g[b] = s;
-                gq[i * DIM + b] = s;
-            }
-            if (ELEM == FB2_ELEM_NEOHOOKE) {
+            for (int b = 0; b < DIM; ++b) Jq[a * DIM + b] = Ji[a][b];
+    }
+    __syncthreads();
+    // ---- phase A2: per (qp, cell, basis function): dNdx = dNdxi . J^-1 ------------------------------------------------
+    for (int item = threadIdx.x; item < NQ * ncl * NBS; item += blockDim.x) {
+        const int i = item % NBS;
+        const int rest = item / NBS;
+        const int cl = rest % ncl, q = rest / ncl;
+        const double* Jq = s_Ji + ((size_t)q * CELLS + cl) * DIM * DIM;
+        double* gq = s_g + (((size_t)q * CELLS + cl) * NBS + i) * DIM;
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) s = fma(tdN[(q * NBS + i) * DIM + a], Jq[a * DIM + b], s);
+            gq[b] = s;
+        }
+    }
+    if (ELEM == FB2_ELEM_NEOHOOKE) {
+        __syncthreads();
+        // ---- phase A3 (Neo-Hooke): per (qp, cell): F = I + sum_a u_a (x) g_a, S, dS/dC -> P dOmega, dP/dF dOmega --------
+        for (int item = threadIdx.x; item < NQ * ncl; item += blockDim.x) {
+            const int q = item / ncl, cl = item - q * ncl;
+            const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+            const double dO = s_dO[q * CELLS + cl];
+            const double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
+            double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            for (int i = 0; i < NBS; ++i)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const double uc = __ldg(A.u + __ldg(A.cell_dofs + (size_t)(i * 3 + c) * np + cell));
+                    const double uc = __ldg(A.u + s_dof[cl * N + i * 3 + c]);
 #pragma unroll
-                    for (int b = 0; b < DIM; ++b) F[c][b] = fma(uc, g[b], F[c][b]);
+                    for (int b = 0; b < 3; ++b) F[c][b] = fma(uc, gq[i * 3 + b], F[c][b]);
                 }
-            }
-        }
-        if (ELEM == FB2_ELEM_NEOHOOKE) {
             const double lam = A.p[0], mu = A.p[1];
             double C[3][3], Ci[3][3];
 #pragma unroll
@@ -544,88 +564,89 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
-    // ---- phase B: integrate one row of Ke per thread and scatter ---------------------------------------
-    const int nitems = ncl * NT * N;
+    // ---- phase B: thread per (cell, row node a, tile of TB column nodes) ---------------------------------------------
+    // Elasticity: only G_ab = sum_q dOmega g_a (x) g_b is accumulated (9 FMA per qp and node pair); the block is
+    // K_ab = lam G_ab + mu G_ab^T + mu tr(G_ab) I  (from lam g_a[c] g_b[d] + mu (g_a[d] g_b[c] + delta_cd g_a.g_b)).
+    const int nitems = ncl * NT * NBS;
     for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
-        const int r = item % N;              // local row, fastest => lanes hold consecutive rows of one cell
-        const int rest = item / N;
+        const int a = item % NBS;            // row node fastest
+        const int rest = item / NBS;
         const int bt = rest % NT, cl = rest / NT;
-        const int a = r / VDIM, c = r - a * VDIM;
         const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
         const int b0 = bt * TB;
-        double acc[TB][VDIM];
+        double acc[TB][VDIM][VDIM];
 #pragma unroll
         for (int t = 0; t < TB; ++t)
 #pragma unroll
-            for (int d = 0; d < VDIM; ++d) acc[t][d] = 0.0;
-        double fa = 0.0;
+            for (int c = 0; c < VDIM; ++c)
+#pragma unroll
+                for (int d = 0; d < VDIM; ++d) acc[t][c][d] = 0.0;
+        double fa[VDIM];
+#pragma unroll
+        for (int c = 0; c < VDIM; ++c) fa[c] = 0.0;
 
         for (int q = 0; q < NQ; ++q) {
             const double dO = s_dO[q * CELLS + cl];
             const double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
             double ga[DIM];
 #pragma unroll
-            for (int b = 0; b < DIM; ++b) ga[b] = gq[a * DIM + b];
-            const double Na = tN[q * NBS + a];
+            for (int b = 0; b < DIM; ++b) ga[b] = gq[a * DIM + b] * dO;      // dOmega folded into g_a
+            const double Na = tN[q * NBS + a] * dO;
             if (ELEM == FB2_ELEM_HEAT) {
-                fa = fma(Na, dO, fa);
-#pragma unroll
-                for (int b = 0; b < DIM; ++b) ga[b] *= dO;
+                fa[0] += Na;
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
-                        double s = acc[t][0];
+                        double s = acc[t][0][0];
 #pragma unroll
                         for (int b = 0; b < DIM; ++b) s = fma(ga[b], gq[(b0 + t) * DIM + b], s);
-                        acc[t][0] = s;
+                        acc[t][0][0] = s;
                     }
                 }
             } else if (ELEM == FB2_ELEM_MASS) {
-                const double ns = Na * dO;
 #pragma unroll
                 for (int t = 0; t < TB; ++t)
-                    if (b0 + t < NBS) acc[t][0] = fma(ns, tN[q * NBS + b0 + t], acc[t][0]);
+                    if (b0 + t < NBS) acc[t][0][0] = fma(Na, tN[q * NBS + b0 + t], acc[t][0][0]);
             } else if (ELEM == FB2_ELEM_ELASTICITY) {
-                const double lam = A.p[0] * dO, mu = A.p[1] * dO;
-                fa = fma(Na * dO, A.p[2 + c], fa);
-                const double gac = (c == 0 ? ga[0] : (c == 1 ? ga[1] : ga[DIM - 1]));
-                const double lgac = lam * gac;
+#pragma unroll
+                for (int c = 0; c < VDIM; ++c) fa[c] = fma(Na, A.p[2 + c], fa[c]);
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
                         double gb[DIM];
 #pragma unroll
                         for (int b = 0; b < DIM; ++b) gb[b] = gq[(b0 + t) * DIM + b];
-                        double dot = 0.0;
 #pragma unroll
-                        for (int b = 0; b < DIM; ++b) dot = fma(ga[b], gb[b], dot);
-                        const double gbc = (c == 0 ? gb[0] : (c == 1 ? gb[1] : gb[DIM - 1]));
-                        const double mgbc = mu * gbc, mdot = mu * dot;
+                        for (int c = 0; c < VDIM; ++c)
 #pragma unroll
-                        for (int d = 0; d < VDIM; ++d) {
-                            // K[(a,c),(b,d)] += lam g_a[c] g_b[d] + mu (g_a[d] g_b[c] + delta_cd g_a.g_b)
-                            double v = fma(lgac, gb[d], mgbc * ga[d]);
-                            acc[t][d] += (d == c) ? v + mdot : v;
-                        }
+                            for (int d = 0; d < VDIM; ++d) acc[t][c][d] = fma(ga[c], gb[d], acc[t][c][d]);
                     }
                 }
-            } else {  // neo-hooke: K[(a,c),(b,d)] = sum_{j,n} ga[j] A[c][j][d][n] gb[n]
+            } else {  // neo-hooke: K_ab[c][d] = sum_{j,n} ga[j] A[c][j][d][n] gb[n]   (dOmega is inside A and P)
                 const double* Aq = s_A + ((size_t)q * CELLS + cl) * 81;
                 const double* Pq = s_P + ((size_t)q * CELLS + cl) * 9;
-                double h[3][3];
+                double gr[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d)
+                for (int b = 0; b < 3; ++b) gr[b] = gq[a * 3 + b];
+                double h[3][3][3];
 #pragma unroll
-                    for (int n = 0; n < 3; ++n) {
-                        double s = 0.0;
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) s = fma(ga[j], Aq[((c * 3 + j) * 3 + d) * 3 + n], s);
-                        h[d][n] = s;
-                    }
-                double s = fa;
+                    for (int d = 0; d < 3; ++d)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) s = fma(ga[j], Pq[c * 3 + j], s);
-                fa = fma(-Na * dO, A.p[2 + c], s);
+                        for (int n = 0; n < 3; ++n) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) s = fma(gr[j], Aq[((c * 3 + j) * 3 + d) * 3 + n], s);
+                            h[c][d][n] = s;
+                        }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double s = fa[c];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) s = fma(gr[j], Pq[c * 3 + j], s);
+                    fa[c] = fma(-Na, A.p[2 + c], s);
+                }
 #pragma unroll
                 for (int t = 0; t < TB; ++t) {
                     if (b0 + t < NBS) {
@@ -633,32 +654,45 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
 #pragma unroll
                         for (int b = 0; b < 3; ++b) gb[b] = gq[(b0 + t) * 3 + b];
 #pragma unroll
-                        for (int d = 0; d < 3; ++d) {
-                            double v = acc[t][d];
+                        for (int c = 0; c < 3; ++c)
 #pragma unroll
-                            for (int n = 0; n < 3; ++n) v = fma(h[d][n], gb[n], v);
-                            acc[t][d] = v;
-                        }
+                            for (int d = 0; d < 3; ++d) {
+                                double v = acc[t][c][d];
+#pragma unroll
+                                for (int n = 0; n < 3; ++n) v = fma(h[c][d][n], gb[n], v);
+                                acc[t][c][d] = v;
+                            }
                     }
                 }
             }
         }
-        // scatter row r: column bases and offsets come from shared memory (staged above)
+        // scatter the node blocks (a, b0..b0+TB-1): column bases and offsets come from shared memory
         const double kscale = (ELEM == FB2_ELEM_HEAT || ELEM == FB2_ELEM_MASS) ? A.p[0] : 1.0;
-        const uint16_t* mrow = s_map + (size_t)cl * L.mapstride + r;   // offset of row r in column jl at mrow[jl * N]
-        const int64_t* brow = s_base + (size_t)cl * N;
+        const uint16_t* mcell = s_map + (size_t)cl * L.mapstride;
+        const int64_t* bcell = s_base + (size_t)cl * N;
         bool missing = false;
 #pragma unroll
         for (int t = 0; t < TB; ++t) {
             if (b0 + t < NBS) {
+                double tr = 0.0;
+                if (ELEM == FB2_ELEM_ELASTICITY) {
+#pragma unroll
+                    for (int c = 0; c < VDIM; ++c) tr += acc[t][c][c];
+                }
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
                     const int jl = (b0 + t) * VDIM + d;
-                    const double v = kscale * acc[t][d];
-                    const unsigned off = mrow[jl * N];
-                    if (v != 0.0) {
-                        if (off == 0xFFFFu) missing = true;
-                        else fb2_add<ATOMIC>(A.nzval + brow[jl] + off, v);
+                    const int64_t base = bcell[jl];
+#pragma unroll
+                    for (int c = 0; c < VDIM; ++c) {
+                        double v;
+                        if (ELEM == FB2_ELEM_ELASTICITY) v = A.p[0] * acc[t][c][d] + A.p[1] * (acc[t][d][c] + (c == d ? tr : 0.0));
+                        else v = kscale * acc[t][c][d];
+                        const unsigned off = mcell[jl * N + a * VDIM + c];
+                        if (v != 0.0) {
+                            if (off == 0xFFFFu) missing = true;
+                            else fb2_add<ATOMIC>(A.nzval + base + off, v);
+                        }
                     }
                 }
             }
@@ -666,7 +700,8 @@ __global__ void __launch_bounds__(384) k_cell_blocks(const AsmArgs A, const int 
         if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
         if (bt == 0 && A.f != nullptr && ELEM != FB2_ELEM_MASS) {
             const double fscale = ELEM == FB2_ELEM_HEAT ? A.p[1] : 1.0;
-            fb2_add<ATOMIC>(A.f + s_dof[cl * N + r], fscale * fa);
+#pragma unroll
+            for (int c = 0; c < VDIM; ++c) fb2_add<ATOMIC>(A.f + s_dof[cl * N + a * VDIM + c], fscale * fa[c]);
         }
     }
 }
