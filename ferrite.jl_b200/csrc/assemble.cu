@@ -38,13 +38,16 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
 }
 
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
-int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0) {
+int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, bool unchecked = false) {
     const int bs = 128;
     const unsigned grid = (unsigned)((A.ncount + bs - 1) / bs);
     // NQ >= 8: keep the quadrature loop rolled (code fits the instruction cache; 4 % faster on Q1 hex); variant 2
     // selects the fully unrolled body for comparison
     constexpr bool ROLL = NQ >= 8;
     if (atomic && variant == 2) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, false><<<grid, bs, 0, ctx->stream>>>(A);
+    // variant 4: branch-free scatter for complete maps; measured slower on Q1 hex (2.98 vs 2.86 ms: the kernel is bound
+    // by L2 atomic throughput, not by instruction issue), so the checked scatter stays the default
+    else if (atomic && unchecked && variant == 4) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, false><<<grid, bs, 0, ctx->stream>>>(A);
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);
     else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, false><<<grid, bs, 0, ctx->stream>>>(A);
     ctx->launches++;
@@ -58,13 +61,21 @@ int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     constexpr int NT = (NBS + TB - 1) / TB;
     FB2_TRY(fb2_map_build_cellmajor(a));
     A.mapc = a->d_mapc;
-    // cells per CTA: as many as give <= 256 phase-B rows (one row of Ke per thread); ~100 registers per thread then
-    // allow 2-3 CTAs per SM, which is what hides the shared-memory and FP64 latencies
-    int cells = std::max(1, 256 / (NBS * NT));
-    while (cells > 1 && fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells).total > 100 * 1024) --cells;
+    // cells per CTA: phase-B items (row node x column tile) are looped over 256 threads; take as many cells as fit in
+    // ~100 KB of shared memory (two CTAs per SM overlap one CTA's geometry phase / barriers with the other's phase B),
+    // preferring a count whose item total fills the last loop iteration
+    const int per_cell = NBS * NT;
+    int cells = 1, best_eff = 0;
+    for (int c = 1; c <= 32; ++c) {
+        if (fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, c).total > 100 * 1024) break;
+        const int items = c * per_cell, slots = (items + 255) / 256 * 256;
+        const int eff = items * 1000 / slots;
+        if (eff >= best_eff || items <= 256) { best_eff = std::max(eff, best_eff); cells = c; }
+        if (items >= 1024) break;
+    }
     const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells);
     FB2_CHECK(L.total <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", L.total);
-    const int bs = std::min(256, (NBS * NT * cells + 31) / 32 * 32);
+    const int bs = std::min(256, (per_cell * cells + 31) / 32 * 32);
     const unsigned grid = (unsigned)((A.ncount + cells - 1) / cells);
     if (atomic) {
         auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, true>;
@@ -137,7 +148,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     }
     FB2_TRY(fb2_map_build_packed(a));
     A.map8 = reinterpret_cast<const uint4*>(a->d_map8);
-    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic, variant);
+    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic, variant, a->map_complete);
 }
 
 template <int ELEM>

@@ -190,7 +190,7 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 // k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false>
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true>
 __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= A.ncount) return;
@@ -252,9 +252,13 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
             const int e = j * NB + i;
             const unsigned w32 = (e & 7) < 2 ? mp[e >> 3].x : ((e & 7) < 4 ? mp[e >> 3].y : ((e & 7) < 6 ? mp[e >> 3].z : mp[e >> 3].w));
             const unsigned off = (e & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
-            if (v != 0.0) {
-                if (off == 0xFFFFu) missing = true;
-                else fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
+            if (CHECK) {   // zero values are skipped; a non-zero aimed at a missing entry is an error
+                if (v != 0.0) {
+                    if (off == 0xFFFFu) missing = true;
+                    else fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
+                }
+            } else {       // complete map: adding an exact zero has no effect, no branches needed
+                fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
             }
         }
     }
@@ -388,10 +392,15 @@ struct TileOf {
     static constexpr int TB = VDIM == 1 ? ((NBS <= 8) ? NBS : (NBS == 10 ? 10 : 9))
                             : VDIM == 2 ? NBS
                                         : (NBS == 27 ? 3 : (NBS == 10 ? 5 : 4));
+    // Optional transposed scatter (off): the element matrices of the CTA's cells go through shared memory so that
+    // the lanes of a warp add CONSECUTIVE rows of one column (rows (a, 0..VDIM-1) are adjacent in a CSC column and
+    // share 32-byte sectors).  Measured on Q1^3 hex elasticity (profiles/r01_prof_c5_r1f.txt): RED sectors 1100 M ->
+    // 522 M, lts throughput 49 % -> 27 %, but +40 % instructions and an extra barrier: 7.2 ms -> 8.1 ms, so it stays off.
+    static constexpr bool TRANSPOSE = false;
 };
 
 struct BlockSmem {
-    size_t g, dO, Ji, A, P, base, dof, map, total;   // byte offsets
+    size_t g, dO, Ji, A, P, base, dof, map, K, total;   // byte offsets
     int mapstride;                                   // uint16 entries per cell in the staged map (multiple of 8)
 };
 
@@ -410,6 +419,8 @@ __host__ __device__ inline BlockSmem fb2_blocks_smem(int nq, int cells) {
     o = (o + 15) / 16 * 16;
     L.mapstride = (N * N + 7) / 8 * 8;
     L.map = o; o += sizeof(uint16_t) * (size_t)cells * L.mapstride;
+    o = (o + 15) / 16 * 16;
+    L.K = o; o += (TileOf<NBS, VDIM>::TRANSPOSE ? sizeof(double) * (size_t)cells * N * N : 0);
     L.total = o;
     return L;
 }
@@ -431,6 +442,8 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
     int64_t* s_base = reinterpret_cast<int64_t*>(smraw + L.base);  // [CELLS][N]
     int32_t* s_dof = reinterpret_cast<int32_t*>(smraw + L.dof);    // [CELLS][N]
     uint16_t* s_map = reinterpret_cast<uint16_t*>(smraw + L.map);  // [CELLS][mapstride]
+    double* s_K = reinterpret_cast<double*>(smraw + L.K);          // TRANSPOSE: [CELLS][N * N], entry jl * N + il
+    constexpr bool TRANSPOSE = TileOf<NBS, VDIM>::TRANSPOSE;
     const int64_t cell0 = (int64_t)blockIdx.x * CELLS;
     const int ncl = (int)min((int64_t)CELLS, A.ncount - cell0);
 
@@ -585,6 +598,7 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
 #pragma unroll
         for (int c = 0; c < VDIM; ++c) fa[c] = 0.0;
 
+#pragma unroll 2
         for (int q = 0; q < NQ; ++q) {
             const double dO = s_dO[q * CELLS + cl];
             const double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
@@ -688,10 +702,14 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
                         double v;
                         if (ELEM == FB2_ELEM_ELASTICITY) v = A.p[0] * acc[t][c][d] + A.p[1] * (acc[t][d][c] + (c == d ? tr : 0.0));
                         else v = kscale * acc[t][c][d];
-                        const unsigned off = mcell[jl * N + a * VDIM + c];
-                        if (v != 0.0) {
-                            if (off == 0xFFFFu) missing = true;
-                            else fb2_add<ATOMIC>(A.nzval + base + off, v);
+                        if (TRANSPOSE) {
+                            s_K[(size_t)cl * N * N + jl * N + a * VDIM + c] = v;
+                        } else {
+                            const unsigned off = mcell[jl * N + a * VDIM + c];
+                            if (v != 0.0) {
+                                if (off == 0xFFFFu) missing = true;
+                                else fb2_add<ATOMIC>(A.nzval + base + off, v);
+                            }
                         }
                     }
                 }
@@ -702,6 +720,18 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
             const double fscale = ELEM == FB2_ELEM_HEAT ? A.p[1] : 1.0;
 #pragma unroll
             for (int c = 0; c < VDIM; ++c) fb2_add<ATOMIC>(A.f + s_dof[cl * N + a * VDIM + c], fscale * fa[c]);
+        }
+    }
+    if (TRANSPOSE) {
+        __syncthreads();
+        for (int e2 = threadIdx.x; e2 < ncl * N * N; e2 += blockDim.x) {
+            const int cl = e2 / (N * N), e = e2 - cl * (N * N);   // e = jl * N + il: lanes walk down the rows of a column
+            const double v = s_K[e2];
+            if (v != 0.0) {
+                const unsigned off = s_map[(size_t)cl * L.mapstride + e];
+                if (off == 0xFFFFu) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl);
+                else fb2_add<ATOMIC>(A.nzval + s_base[cl * N + e / N] + off, v);
+            }
         }
     }
 }

@@ -172,6 +172,7 @@ void fb2_tiles_free(TileSchedule* S);
 struct fb2_assembler {
     TileSchedule* tiles = nullptr;
     bool tiles_failed = false;
+    bool map_complete = false;     // every (cell, i, j) has a pattern entry: unchecked scatter allowed
     fb2_dh* dh = nullptr;
     fb2_pattern* pat = nullptr;
     fb2_cv* cv = nullptr;

@@ -125,7 +125,7 @@ __global__ void k_find_diag(const int64_t* __restrict__ colptr, const int32_t* _
 
 __global__ void k_build_map(const int32_t* __restrict__ cell_dofs, int64_t ncells, int64_t ncells_pad, int n,
                             const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval,
-                            uint16_t* __restrict__ map) {
+                            uint16_t* __restrict__ map, int* __restrict__ nmissing) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)n * n * ncells_pad;
     if (t >= total) return;
@@ -143,6 +143,7 @@ __global__ void k_build_map(const int32_t* __restrict__ cell_dofs, int64_t ncell
         if (r < di) lo = mid + 1; else hi = mid;
     }
     map[t] = off;
+    if (off == 0xFFFF) atomicAdd(nmissing, 1);   // (cell, i, j) has no entry in the pattern
 }
 
 // Packed variant for the thread-per-cell kernels: 8 offsets per 16-byte chunk, chunk k of cell c at
@@ -448,10 +449,20 @@ int fb2_map_build(fb2_assembler* a) {
     const int n = a->n;
     const int64_t total = (int64_t)n * n * g->ncells_pad;
     FB2_CUDA(cudaMalloc(&a->d_map, total * sizeof(uint16_t)));
+    int* d_missing = nullptr;
+    FB2_CUDA(cudaMalloc(&d_missing, sizeof(int)));
+    FB2_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), ctx->stream));
     k_build_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(dh->d_cell_dofs, g->ncells, g->ncells_pad, n, a->pat->d_colptr,
-                                                              a->pat->d_rowval, a->d_map);
+                                                              a->pat->d_rowval, a->d_map, d_missing);
     ctx->launches++;
-    FB2_CUDA(cudaGetLastError());
-    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    int missing = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_missing);
+    FB2_CHECK(e == cudaSuccess, FB2_ERR_CUDA, "fb2_map_build: %s", cudaGetErrorString(e));
+    // patterns built by fb2_pattern_create contain every (i, j) of every cell: the kernels then scatter without
+    // the per-entry zero / missing checks of assemble! (src/assembler.jl:376-457)
+    a->map_complete = missing == 0;
     return FB2_OK;
 }
