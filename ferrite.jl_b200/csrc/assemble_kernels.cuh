@@ -31,6 +31,8 @@ struct AsmArgs {
     const uint4* map8;     // packed offsets for k_cell_scalar
     const uint16_t* mapc;  // cell-major offsets for k_cell_blocks: [cell][mapstride], entry jl * n + il
     const int32_t* cells;  // optional indirection (colour / partition subset)
+    const int32_t* wfirst; // optional warp list of k_cell_scalar: first cell of every warp (4 consecutive warps = 4 grid rows)
+    const uint8_t* wcount; //   and its number of cells (<= 32)
     int64_t ncount;        // number of cells handled by this launch
     int64_t ncells_pad;
     double* nzval;
@@ -192,12 +194,21 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true>
 __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // lanes past the end stay alive (they redo the last cell and write nothing): the face merge below shuffles
-    // across the whole warp
-    bool active = idx < A.ncount;
-    const int64_t idc = active ? idx : A.ncount - 1;
-    const int64_t cell = A.cells ? (int64_t)A.cells[idc] : idc;
+    // lanes past the end stay alive (they redo a valid cell and write nothing): the face merges below shuffle across
+    // the whole warp and synchronise the CTA
+    bool active;
+    int64_t cell;
+    if (A.wfirst) {   // warp list: warp w covers cells [wfirst[w], wfirst[w] + wcount[w])
+        const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31, cnt = A.wcount[w];
+        active = lane < cnt;
+        cell = (int64_t)A.wfirst[w] + (active ? lane : 0);
+    } else {
+        const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        active = idx < A.ncount;
+        const int64_t idc = active ? idx : A.ncount - 1;
+        cell = A.cells ? (int64_t)A.cells[idc] : idc;
+    }
     const int64_t np = A.ncells_pad;
 
     int node[NGEO];
@@ -236,16 +247,73 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     }
     const double kscale = A.p[0];  // heat: conductivity k; mass: rho
     const double fscale = A.p[1];  // heat: source
-    // Face merge (Q1 quadrilateral / hexahedron, atomic mode): if the cell of the previous lane shares this cell's
-    // "left" face (its local nodes R = {1,2[,5,6]} are this cell's L = {0,3[,4,7]}, compared by dof id, so any mesh
-    // ordering qualifies), the previous lane's face block is added here through warp shuffles and the previous lane
-    // skips those REDs: 25 % fewer L2 atomics on grids whose cells are stored in rows (the kernel is bound by L2
-    // atomic sector throughput, profiles/r01_prof_c2_r1c.txt).
-    constexpr bool MERGE = ATOMIC && ((DIM == 3 && NB == 8 && NGEO == 8) || (DIM == 2 && NB == 4 && NGEO == 4));
-    constexpr int NF = DIM == 3 ? 4 : 2;
-    constexpr int RF[4] = {1, 2, 5, 6}, LF[4] = {0, 3, 4, 7};
-    bool next_takes = false;   // the next lane consumes my R-face block
-    if (MERGE) {
+    // Face merges (Q1 quadrilateral / hexahedron, atomic mode).  A cell hands the block of Ke / fe that belongs to a
+    // face shared with a neighbouring cell to that neighbour and zeroes it (zeros are skipped by the scatter), so the
+    // neighbour adds both contributions with ONE RED per entry.  Faces are matched by dof id, so any mesh ordering
+    // qualifies; on grids stored in rows the previous lane is the x-neighbour and, with the warp list (4 consecutive
+    // grid rows per CTA), the previous warp holds the y-neighbours.  The kernel is bound by L2 atomic sector
+    // throughput (profiles/r01_prof_c2_r1c.txt): x-merge alone removes 25 % of the REDs (2.86 -> 2.41 ms on C2).
+    constexpr bool MERGE = ATOMIC && CHECK && ((DIM == 3 && NB == 8 && NGEO == 8) || (DIM == 2 && NB == 4 && NGEO == 4));
+    constexpr int NF = DIM == 3 ? 4 : 2;                       // nodes per face
+    constexpr int RF[4] = {1, 2, 5, 6}, LF[4] = {0, 3, 4, 7};   // right face of the left cell <-> left face of this cell
+    constexpr int TF[4] = {3, 2, 7, 6}, BF[4] = {0, 1, 4, 5};   // top face of the lower cell  <-> bottom face of this cell
+    constexpr int NPAIR = NF * (NF + 1) / 2;
+    if (MERGE && A.wfirst != nullptr) {   // ---- y-merge through shared memory (uniform branch) ----
+        __shared__ double s_T[NPAIR + NF][128];
+        __shared__ int s_Tdof[NF][128];
+        __shared__ unsigned char s_act[128], s_taken[128];
+        const int t = threadIdx.x;
+        {
+            int pi = 0;
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+                for (int p = 0; p <= q; ++p) {
+                    const int i0 = TF[p] < TF[q] ? TF[p] : TF[q], j0 = TF[p] < TF[q] ? TF[q] : TF[p];
+                    s_T[pi++][t] = Ke[j0 * (j0 + 1) / 2 + i0];
+                }
+#pragma unroll
+            for (int k = 0; k < NF; ++k) {
+                s_T[NPAIR + k][t] = fe[TF[k]];
+                s_Tdof[k][t] = dof[TF[k]];
+            }
+            s_act[t] = active;
+            s_taken[t] = 0;
+        }
+        __syncthreads();
+        if (t >= 32) {
+            const int lo = t - 32;
+            bool ym = active && s_act[lo];
+#pragma unroll
+            for (int k = 0; k < NF; ++k) ym = ym & (s_Tdof[k][lo] == dof[BF[k]]);
+            if (ym) {
+                int pi = 0;
+#pragma unroll
+                for (int q = 0; q < NF; ++q)
+#pragma unroll
+                    for (int p = 0; p <= q; ++p) {
+                        const int i0 = BF[p] < BF[q] ? BF[p] : BF[q], j0 = BF[p] < BF[q] ? BF[q] : BF[p];
+                        Ke[j0 * (j0 + 1) / 2 + i0] += s_T[pi++][lo];
+                    }
+#pragma unroll
+                for (int k = 0; k < NF; ++k) fe[BF[k]] += s_T[NPAIR + k][lo];
+                s_taken[lo] = 1;
+            }
+        }
+        __syncthreads();
+        if (s_taken[t]) {   // the cell above took my top-face block
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+                for (int p = 0; p <= q; ++p) {
+                    const int i0 = TF[p] < TF[q] ? TF[p] : TF[q], j0 = TF[p] < TF[q] ? TF[q] : TF[p];
+                    Ke[j0 * (j0 + 1) / 2 + i0] = 0.0;
+                }
+#pragma unroll
+            for (int k = 0; k < NF; ++k) fe[TF[k]] = 0.0;
+        }
+    }
+    if (MERGE) {   // ---- x-merge through warp shuffles ----
         const unsigned full = 0xffffffffu;
         const int lane = threadIdx.x & 31;
         bool match = lane > 0;
@@ -256,20 +324,24 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
         }
         const bool prev_active = __shfl_up_sync(full, (int)active, 1) != 0;
         match = match & prev_active & active;
+        const bool nm = __shfl_down_sync(full, (int)match, 1) != 0;
+        const bool next_takes = nm & (lane < 31);   // the next lane consumes my right-face block
 #pragma unroll
         for (int q = 0; q < NF; ++q)
 #pragma unroll
             for (int p = 0; p <= q; ++p) {
-                const double recv = __shfl_up_sync(full, Ke[RF[q] * (RF[q] + 1) / 2 + RF[p]], 1);
+                const double mine = Ke[RF[q] * (RF[q] + 1) / 2 + RF[p]];
+                const double recv = __shfl_up_sync(full, mine, 1);
+                if (next_takes) Ke[RF[q] * (RF[q] + 1) / 2 + RF[p]] = 0.0;
                 if (match) Ke[LF[q] * (LF[q] + 1) / 2 + LF[p]] += recv;
             }
 #pragma unroll
         for (int k = 0; k < NF; ++k) {
-            const double recv = __shfl_up_sync(full, fe[RF[k]], 1);
+            const double mine = fe[RF[k]];
+            const double recv = __shfl_up_sync(full, mine, 1);
+            if (next_takes) fe[RF[k]] = 0.0;
             if (match) fe[LF[k]] += recv;
         }
-        const bool nm = __shfl_down_sync(full, (int)match, 1) != 0;
-        next_takes = nm & (lane < 31);
     }
     // Scatter.  All index loads (column bases, packed offsets) are issued as one batch before the first RED:
     // interleaving them with the atomics serialises 64 memory round trips per cell (profiles/r1 notes).
@@ -290,9 +362,7 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
             const int e = j * NB + i;
             const unsigned w32 = (e & 7) < 2 ? mp[e >> 3].x : ((e & 7) < 4 ? mp[e >> 3].y : ((e & 7) < 6 ? mp[e >> 3].z : mp[e >> 3].w));
             const unsigned off = (e & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
-            const bool in_rface = MERGE && (i == RF[0] || i == RF[1] || (NF == 4 && (i == RF[2] || i == RF[3]))) &&
-                                      (j == RF[0] || j == RF[1] || (NF == 4 && (j == RF[2] || j == RF[3])));
-            if (!active || (in_rface && next_takes)) continue;
+            if (!active) continue;
             if (CHECK) {   // zero values are skipped; a non-zero aimed at a missing entry is an error
                 if (v != 0.0) {
                     if (off == 0xFFFFu) missing = true;
@@ -305,11 +375,8 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     }
     if (A.f != nullptr && ELEM == FB2_ELEM_HEAT && active) {
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const bool in_rface = MERGE && (i == RF[0] || i == RF[1] || (NF == 4 && (i == RF[2] || i == RF[3])));
-            if (in_rface && next_takes) continue;
-            fb2_add<ATOMIC>(A.f + dof[i], fscale * fe[i]);
-        }
+        for (int i = 0; i < NB; ++i)
+            if (!MERGE || fe[i] != 0.0) fb2_add<ATOMIC>(A.f + dof[i], fscale * fe[i]);
     }
     if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
 }

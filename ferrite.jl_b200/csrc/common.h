@@ -172,6 +172,9 @@ void fb2_tiles_free(TileSchedule* S);
 struct fb2_assembler {
     TileSchedule* tiles = nullptr;
     bool tiles_failed = false;
+    int32_t* d_wfirst = nullptr;   // warp list of k_cell_scalar (lazy): first cell of every warp, 4 warps = 4 grid rows
+    uint8_t* d_wcount = nullptr;   //   number of cells of the warp (0 for padding warps)
+    int64_t nwarps = 0;
     bool map_complete = false;     // every (cell, i, j) has a pattern entry: unchecked scatter allowed
     fb2_dh* dh = nullptr;
     fb2_pattern* pat = nullptr;
@@ -224,6 +227,7 @@ int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);
 int fb2_map_build_cellmajor(fb2_assembler* a);
 int fb2_tiles_build(fb2_assembler* a, int TC);
+int fb2_warplist_build(fb2_assembler* a);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 int fb2_check_device_error(fb2_ctx* ctx);
