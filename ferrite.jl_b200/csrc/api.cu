@@ -221,6 +221,7 @@ extern "C" int fb2_cellvalues_export(fb2_cv* cv, double* N, double* dNdxi, doubl
 extern "C" int fb2_cellvalues_destroy(fb2_cv* cv) {
     if (!cv) return FB2_OK;
     if (cv->ctx && cv->ctx->const_tables_owner == cv) cv->ctx->const_tables_owner = nullptr;
+    if (cv->d_tables) cudaFree(cv->d_tables);
     delete cv;
     return FB2_OK;
 }

@@ -22,7 +22,7 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
     A->o_dM = A->o_M + nq * ng;
     const int total = A->o_dM + nq * ng * rd;
     FB2_CHECK(total <= FB2_TAB_MAX, FB2_ERR_UNSUPPORTED, "CellValues tables need %d doubles of constant memory (max %d)", total, FB2_TAB_MAX);
-    if (ctx->const_tables_owner != cv) {
+    if (ctx->const_tables_owner != cv || cv->d_tables == nullptr) {
         std::vector<double> h(total);
         memcpy(h.data() + A->o_w, cv->w.data(), sizeof(double) * nq);
         memcpy(h.data() + A->o_N, cv->N.data(), sizeof(double) * nq * nb);
@@ -33,7 +33,13 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
         FB2_CUDA(cudaMemcpyToSymbolAsync(c_tab, h.data(), sizeof(double) * total, 0, cudaMemcpyHostToDevice, ctx->stream));
         FB2_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->const_tables_owner = cv;
+        if (cv->d_tables == nullptr) {   // global copy: the CTA kernels index the tables per lane, which a constant bank serialises
+            FB2_CUDA(cudaMalloc(&cv->d_tables, sizeof(double) * total));
+            FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), sizeof(double) * total, cudaMemcpyHostToDevice));
+            cv->tables_count = total;
+        }
     }
+    A->tab = cv->d_tables;
     return FB2_OK;
 }
 
@@ -88,6 +94,47 @@ int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     }
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+// isotropic elasticity on the FP64 tensor cores (k_cell_syrk)
+template <int DIM, int NGEO, int NBS>
+int launch_syrk(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
+    using S = SyrkOf<NBS, DIM>;
+    FB2_TRY(fb2_map_build_cellmajor(a));
+    A.mapc = a->d_mapc;
+    const SyrkSmem L = fb2_syrk_smem<NBS, DIM>(A.nq);
+    const size_t smem = L.cell * S::CELLS;
+    FB2_CHECK(smem <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory", smem);
+    const unsigned grid = (unsigned)((A.ncount + S::CELLS - 1) / S::CELLS);
+    if (atomic) {
+        auto k = k_cell_syrk<DIM, NGEO, NBS, true>;
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, S::NTHR, smem, ctx->stream>>>(A);
+    } else {
+        auto k = k_cell_syrk<DIM, NGEO, NBS, false>;
+        FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, S::NTHR, smem, ctx->stream>>>(A);
+    }
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+int dispatch_syrk(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int celltype, int nbs, int vdim, bool* handled) {
+    *handled = true;
+#define CASE(CT, DIM, NGEO, NBS) \
+    if (celltype == CT && nbs == NBS && vdim == DIM) return launch_syrk<DIM, NGEO, NBS>(a, ctx, A, atomic);
+    CASE(FB2_TRIANGLE, 2, 3, 3)
+    CASE(FB2_TRIANGLE, 2, 3, 6)
+    CASE(FB2_QUADRILATERAL, 2, 4, 4)
+    CASE(FB2_QUADRILATERAL, 2, 4, 9)
+    CASE(FB2_TETRAHEDRON, 3, 4, 4)
+    CASE(FB2_TETRAHEDRON, 3, 4, 10)
+    CASE(FB2_HEXAHEDRON, 3, 8, 8)
+    CASE(FB2_HEXAHEDRON, 3, 8, 27)
+#undef CASE
+    *handled = false;
     return FB2_OK;
 }
 
@@ -312,6 +359,11 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
             if (variant != 1 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_MASS, 0>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY:
+            if (variant != 1) {   // variant 1: the DFMA block kernel
+                bool handled = false;
+                rc = dispatch_syrk(a, ctx, A, atomic, ct, nbs, vdim, &handled);
+                if (handled) return rc;
+            }
             return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_NEOHOOKE:
             FB2_CHECK(A.u != nullptr, FB2_ERR_BAD_ARG, "the Neo-Hooke element needs the current solution u");

@@ -41,7 +41,8 @@ struct AsmArgs {
     int* errflag;
     double p[6];  // element parameters
     int nq;
-    // table offsets into c_tab (in doubles)
+    const double* tab;     // the c_tab contents in global memory (per-lane indexed reads)
+    // table offsets into c_tab / tab (in doubles)
     int o_w, o_N, o_dN, o_M, o_dM;
 };
 
@@ -559,10 +560,11 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
     const int64_t cell0 = (int64_t)blockIdx.x * CELLS;
     const int ncl = (int)min((int64_t)CELLS, A.ncount - cell0);
 
-    const double* tw = c_tab + A.o_w;
-    const double* tN = c_tab + A.o_N;
-    const double* tdN = c_tab + A.o_dN;
-    const double* tdM = c_tab + A.o_dM;
+    // tables from global memory (L1-resident): the indices below differ per lane, which the constant bank would serialise
+    const double* __restrict__ tw = A.tab + A.o_w;
+    const double* __restrict__ tN = A.tab + A.o_N;
+    const double* __restrict__ tdN = A.tab + A.o_dN;
+    const double* __restrict__ tdM = A.tab + A.o_dM;
 
     // ---- staging of the scatter indices (asynchronous; consumed by the scatter at the end of phase B) --------------
     for (int i = threadIdx.x; i < ncl * (L.mapstride / 8); i += blockDim.x) {
@@ -846,4 +848,251 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_cell_syrk: isotropic elasticity (VDIM == DIM) on the FP64 tensor cores.
+//
+// With X[q][(a,c)] = d phi_a / d x_c at quadrature point q (a row per point, a column per local dof) the node-pair sums
+// of k_cell_blocks are one symmetric rank-NQ update per cell,
+//     G = X^T diag(dOmega) X          (N x N, N = NBS * DIM),
+// and Ke[(a,c),(b,d)] = lam G[(a,c),(b,d)] + mu G[(a,d),(b,c)] + delta_cd mu sum_k G[(a,k),(b,k)].
+// G is computed in 8 x 8 tiles with mma.sync.m8n8k4.f64 (DMMA): one warp instruction is 256 FMAs, so the instruction
+// stream of the contraction shrinks 8x against the DFMA version, which was issue/latency bound (19 % of the FP64 peak on
+// Q2 hexahedra).  Only the upper-triangular tiles are computed, accumulators stay in registers, and the result goes to
+// shared memory (mirrored) so that the scatter walks down the rows of a column with consecutive lanes: consecutive rows
+// of a CSC column share 32-byte sectors, which is what the L2 atomic units are bound by.
+//
+// Work split (WPC = warps per cell): elements with N < 48 are handled by ONE warp per cell (four independent warps per
+// CTA, __syncwarp only: no CTA barrier, the phases of different warps interleave and hide each other's latency); Q2
+// hexahedra (N = 81, 66 tiles) use one CTA of 8 warps per cell, tile t going to warp t mod 8.  The tile loop is unrolled
+// at compile time, so tile coordinates and accumulator slots are immediates.
+template <int NBS, int DIM>
+struct SyrkOf {
+    static constexpr int N = NBS * DIM;
+    static constexpr int NTI = (N + 7) / 8;                             // 8-wide tile rows / columns
+    static constexpr int NP = (NTI * 8) % 16 == 0 ? NTI * 8 + 8 : NTI * 8;  // row stride of X (doubles), = 8 mod 16: the four
+                                                                        // quadrature rows of a fragment load hit disjoint banks
+    static constexpr int NG = N % 2 == 0 ? N + 1 : N;                   // row stride of G: odd -> column walks are conflict-free
+    static constexpr int NTU = NTI * (NTI + 1) / 2;                     // upper-triangular tiles per cell
+    static constexpr int WPC = N >= 48 ? 8 : 1;                         // warps per cell
+    static constexpr int NTHR = WPC == 1 ? 128 : 32 * WPC;              // threads per CTA
+    static constexpr int CELLS = WPC == 1 ? 4 : 1;                      // cells per CTA
+    static constexpr int TPW = (NTU + WPC - 1) / WPC;                   // tiles (accumulator pairs) per warp
+};
+
+struct SyrkSmem {
+    size_t X, dO, G, base, dof, map, cell;  // byte offsets inside a cell's region, and its size; J^-1 of phase A aliases G
+    int nqp, mapstride;
+};
+
+template <int NBS, int DIM>
+__host__ __device__ inline SyrkSmem fb2_syrk_smem(int nq) {
+    using S = SyrkOf<NBS, DIM>;
+    SyrkSmem L;
+    L.nqp = (nq + 3) / 4 * 4;
+    size_t o = 0;
+    L.X = o; o += sizeof(double) * (size_t)L.nqp * S::NP;
+    L.dO = o; o += sizeof(double) * (size_t)L.nqp;
+    const size_t gbytes = sizeof(double) * (size_t)S::N * S::NG;
+    const size_t jbytes = sizeof(double) * (size_t)nq * DIM * DIM;
+    L.G = o; o += gbytes > jbytes ? gbytes : jbytes;
+    L.base = o; o += sizeof(int64_t) * (size_t)S::N;
+    L.dof = o; o += sizeof(int32_t) * (size_t)S::N;
+    o = (o + 15) / 16 * 16;
+    L.mapstride = (S::N * S::N + 7) / 8 * 8;
+    // one CTA per cell (WPC > 1): the staged scatter indices reuse the X buffer after the contraction, which brings
+    // Q2 hexahedra from 86 KB to 73 KB per CTA = three CTAs per SM
+    if (S::WPC > 1 && sizeof(uint16_t) * (size_t)L.mapstride <= sizeof(double) * (size_t)L.nqp * S::NP) L.map = L.X;
+    else { L.map = o; o += sizeof(uint16_t) * (size_t)L.mapstride; }
+    L.cell = (o + 15) / 16 * 16;
+    return L;
+}
+
+__device__ __forceinline__ void fb2_dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int DIM, int NGEO, int NBS, bool ATOMIC>
+__global__ void __launch_bounds__(SyrkOf<NBS, DIM>::NTHR) k_cell_syrk(const AsmArgs A) {
+    using S = SyrkOf<NBS, DIM>;
+    constexpr int N = S::N, NP = S::NP, NG = S::NG, NTI = S::NTI, TPW = S::TPW, WPC = S::WPC;
+    constexpr int GS = 32 * WPC;             // threads working on one cell
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int NQ = A.nq;
+    const int64_t np = A.ncells_pad;
+    const SyrkSmem L = fb2_syrk_smem<NBS, DIM>(NQ);
+    const int NQP = L.nqp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gt = WPC == 1 ? lane : (int)threadIdx.x;   // thread index inside the cell's group
+    const int64_t ci = WPC == 1 ? (int64_t)blockIdx.x * S::CELLS + warp : (int64_t)blockIdx.x;
+    if (ci >= A.ncount) return;              // a whole group leaves together
+    const int64_t cell = A.cells ? (int64_t)A.cells[ci] : ci;
+    unsigned char* smc = smraw + (WPC == 1 ? (size_t)warp * L.cell : 0);
+    double* s_X = reinterpret_cast<double*>(smc + L.X);          // [NQP][NP]
+    double* s_dO = reinterpret_cast<double*>(smc + L.dO);        // [NQP]
+    double* s_G = reinterpret_cast<double*>(smc + L.G);          // [N][NG]
+    double* s_Ji = s_G;                                          // [NQ][DIM*DIM] (phase A only)
+    int64_t* s_base = reinterpret_cast<int64_t*>(smc + L.base);  // [N]
+    int32_t* s_dof = reinterpret_cast<int32_t*>(smc + L.dof);    // [N]
+    uint16_t* s_map = reinterpret_cast<uint16_t*>(smc + L.map);  // [mapstride]
+    // tables from global memory (L1-resident): the indices below differ per lane, which the constant bank would serialise
+    const double* __restrict__ tw = A.tab + A.o_w;
+    const double* __restrict__ tN = A.tab + A.o_N;
+    const double* __restrict__ tdN = A.tab + A.o_dN;
+    const double* __restrict__ tdM = A.tab + A.o_dM;
+#define FB2_GROUP_SYNC() do { if (WPC == 1) __syncwarp(); else __syncthreads(); } while (0)
+
+    // scatter indices: asynchronous staging, consumed after the contraction.  When they share the X buffer they are
+    // only pulled into L2 here and staged once X is dead.
+    const bool late_map = L.map == L.X;
+    if (late_map) {
+        for (int i = gt; i < L.mapstride / 64; i += GS)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.mapc + (size_t)cell * L.mapstride + i * 64));
+    } else {
+        for (int i = gt; i < L.mapstride / 8; i += GS) fb2_cp_async16(s_map + i * 8, A.mapc + (size_t)cell * L.mapstride + i * 8);
+    }
+    for (int i = gt; i < N; i += GS) {
+        const int d = __ldg(A.cell_dofs + (size_t)i * np + cell);
+        s_dof[i] = d;
+        s_base[i] = __ldg(A.colptr + d);
+    }
+    // quadrature rows NQ..NQP-1 are padding of the k dimension: zero.  Padding columns are left
+    // uninitialised: they only reach G entries with a row or column >= N, which are never read
+    for (int i = gt; i < (NQP - NQ) * NP; i += GS) s_X[NQ * NP + i] = 0.0;
+    for (int i = gt; i < NQP - NQ; i += GS) s_dO[NQ + i] = 0.0;
+    // node coordinates (the X buffer is free until phase A2)
+    double* s_x = s_X;                                           // [NGEO][DIM]
+    for (int j = gt; j < NGEO; j += GS) {
+        const int node = __ldg(A.conn + (size_t)j * np + cell);
+        double xj[DIM];
+        fb2_load_x<DIM>(A.xyz, node, xj);
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) s_x[j * DIM + a] = xj[a];
+    }
+    FB2_GROUP_SYNC();
+    // ---- phase A1: thread per (qp, a, b): J_ab = sum_j x_j[a] dM_j/dxi_b ------------------------------------------------
+    for (int item = gt; item < NQ * DIM * DIM; item += GS) {
+        const int q = item / (DIM * DIM), ab = item - q * DIM * DIM;
+        const int a = ab / DIM, b = ab - a * DIM;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NGEO; ++j) s = fma(s_x[j * DIM + a], tdM[(q * NGEO + j) * DIM + b], s);
+        s_Ji[item] = s;
+    }
+    FB2_GROUP_SYNC();
+    // ---- thread per qp: det > 0, J^-1 (in place), dOmega ------------------------------------------------------------------
+    for (int q = gt; q < NQ; q += GS) {
+        double J[DIM][DIM], Ji[DIM][DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = 0; b < DIM; ++b) J[a][b] = s_Ji[q * DIM * DIM + a * DIM + b];
+        const double det = fb2_det_inv<DIM>(J, Ji);
+        if (!(det > 0.0)) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
+        s_dO[q] = det * tw[q];
+#pragma unroll
+        for (int a = 0; a < DIM; ++a)
+#pragma unroll
+            for (int b = 0; b < DIM; ++b) s_Ji[q * DIM * DIM + a * DIM + b] = Ji[a][b];
+    }
+    FB2_GROUP_SYNC();
+    // ---- phase A2: X[q][(i, b)] = dN_i/dxi . J^-1 ---------------------------------------------------------------------
+    for (int item = gt; item < NQ * NBS; item += GS) {
+        const int q = item / NBS, i = item - q * NBS;
+        const double* Jq = s_Ji + q * DIM * DIM;
+#pragma unroll
+        for (int b = 0; b < DIM; ++b) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) s = fma(tdN[(q * NBS + i) * DIM + a], Jq[a * DIM + b], s);
+            s_X[q * NP + i * DIM + b] = s;
+        }
+    }
+    FB2_GROUP_SYNC();
+
+    // ---- contraction: G tiles on the tensor cores -------------------------------------------------------------------------
+    const int kr = lane & 3, mc = lane >> 2;   // fragment coordinates: A[mc][kr], B[kr][mc], C[mc][2 kr + {0,1}]
+    double acc[TPW][2];
+#pragma unroll
+    for (int s = 0; s < TPW; ++s) acc[s][0] = acc[s][1] = 0.0;
+    // one specialised copy of the loop per warp of the group (W is a compile-time constant inside): a warp issues only
+    // its own tiles' fragment loads and DMMAs, and the branch is warp-uniform
+#pragma unroll
+    for (int W = 0; W < WPC; ++W) {
+        if (WPC > 1 && warp != W) continue;
+        for (int ks = 0; ks < NQP / 4; ++ks) {
+            const double w = s_dO[4 * ks + kr];
+            const double* xrow = s_X + (4 * ks + kr) * NP + mc;
+            double xb[NTI], xw[NTI];
+#pragma unroll
+            for (int t = 0; t < NTI; ++t) { xb[t] = xrow[8 * t]; xw[t] = xb[t] * w; }
+            int t = 0;
+#pragma unroll
+            for (int ti = 0; ti < NTI; ++ti)
+#pragma unroll
+                for (int tj = ti; tj < NTI; ++tj, ++t)
+                    if (t % WPC == W) fb2_dmma884(acc[t / WPC], xw[ti], xb[tj]);
+        }
+        // G (and its mirror image) to shared memory; J^-1 aliased this buffer, the group is past phase A2
+        int t = 0;
+#pragma unroll
+        for (int ti = 0; ti < NTI; ++ti)
+#pragma unroll
+            for (int tj = ti; tj < NTI; ++tj, ++t)
+                if (t % WPC == W) {
+                    const int r = 8 * ti + mc, c0 = 8 * tj + 2 * kr;
+                    const double v0 = acc[t / WPC][0], v1 = acc[t / WPC][1];
+                    if (r < N) {
+                        if (c0 < N) s_G[r * NG + c0] = v0;
+                        if (c0 + 1 < N) s_G[r * NG + c0 + 1] = v1;
+                        if (ti != tj) {
+                            if (c0 < N) s_G[c0 * NG + r] = v0;
+                            if (c0 + 1 < N) s_G[(c0 + 1) * NG + r] = v1;
+                        }
+                    }
+                }
+    }
+    if (late_map) {
+        FB2_GROUP_SYNC();   // every warp is done reading X
+        for (int i = gt; i < L.mapstride / 8; i += GS) fb2_cp_async16(s_map + i * 8, A.mapc + (size_t)cell * L.mapstride + i * 8);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    FB2_GROUP_SYNC();
+
+    // ---- scatter: a thread owns row il = (a, c) and walks over the columns (b, d); the groups of N consecutive threads
+    // take every (GS / N)-th column node.  G is symmetric, so G[(b,.)][(a,.)] is read: consecutive lanes, consecutive words.
+    constexpr int NGRP = GS / N;
+    const int grp = gt / N, il = gt - grp * N;
+    if (grp < NGRP) {
+        const double lam = A.p[0], mu = A.p[1];
+        const int a = il / DIM, c = il - a * DIM;
+        bool missing = false;
+        for (int b = grp; b < NBS; b += NGRP) {
+            const double* Gb = s_G + (b * DIM) * NG;       // rows (b, 0..DIM-1)
+            double tr = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) tr += Gb[k * NG + a * DIM + k];
+            const double* Gbc = Gb + c * NG + a * DIM;     // G[(b,c)][(a,.)]
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const int jl = b * DIM + d;
+                double v = lam * Gb[d * NG + il] + mu * Gbc[d];
+                if (c == d) v = fma(mu, tr, v);
+                const unsigned off = s_map[jl * N + il];
+                if (v != 0.0) {
+                    if (off == 0xFFFFu) missing = true;
+                    else fb2_add<ATOMIC>(A.nzval + s_base[jl] + off, v);
+                }
+            }
+        }
+        if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
+        if (A.f != nullptr && grp == 0) {
+            double s = 0.0;
+            for (int q = 0; q < NQ; ++q) s = fma(tN[q * NBS + a], s_dO[q], s);
+            fb2_add<ATOMIC>(A.f + s_dof[il], s * A.p[2 + c]);
+        }
+    }
+#undef FB2_GROUP_SYNC
 }
