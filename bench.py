@@ -213,8 +213,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL's version banner) go to stderr meanwhile
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout; stdout carries exactly one JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -310,6 +314,17 @@ def main():
     if cfg["element"] == "heat":
         checks["sum_f_minus_volume"] = abs(sum_over_ranks(float(f.sum())) - volume)
         checks["sum_K"] = abs(sum_over_ranks(float(K.nzval.sum()))) / max_over_ranks(float(K.nzval.abs().max()))
+    if part is not None:
+        # the exchange path and the communication-free halo path must give the same owned columns
+        ref_nz, ref_f = K.nzval.clone(), f.clone()
+        part.assemble_(elem, mode="halo" if args.dist_mode == "exchange" else "exchange")
+        ctx.synchronize()
+        scale = max_over_ranks(float(ref_nz.abs().max()))
+        checks["exchange_vs_halo_maxdiff_rel"] = max_over_ranks(float((K.nzval - ref_nz).abs().max())) / scale
+        checks["exchange_vs_halo_f_maxdiff"] = max_over_ranks(float((f - ref_f).abs().max()))
+        del ref_nz, ref_f
+        step(a)
+        ctx.synchronize()
 
     # ---- dominant kernel alone (no zero fill, no exchange) for the roofline -----------------------------------
     a_nz = fb.start_assemble(K, f, fillzero=False, scatter=args.scatter)
@@ -405,7 +420,9 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
         line["cpu_baseline"] = cpu_baseline(cfg, sample)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -175,7 +175,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     constexpr int TC = (NSYM + NB) <= 44 ? 128 : 64;   // one cell per thread; two CTAs per SM overlap their phases
     // The tile kernel is opt-in (variant 5): on B200 it is slower than the per-cell kernel for Q1 hex (phase 2 costs as
     // many instructions as it saves in L2 traffic); kept because it removes 80 % of the RED traffic.
-    if (atomic && variant == 5 && A.cells == nullptr && a->dh->grid->ncells >= 8 * TC) {
+    if (atomic && variant == 5 && A.cells == nullptr && A.ncount == a->dh->grid->ncells && a->dh->grid->ncells >= 8 * TC) {
         FB2_TRY(fb2_tiles_build(a, TC));
         if (a->tiles) {
             const TileSchedule* S = a->tiles;
@@ -198,7 +198,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     // variant 6: launch over the warp list, which adds the y-merge through shared memory.  Measured on C2 it removes a
     // further ~20 % of the REDs but costs two CTA barriers and 12 % padding lanes (200 = 6*32 + 8): 2.78 ms vs 2.41 ms
     // with the x-merge alone, so it is not the default.
-    if (atomic && A.cells == nullptr && variant == 6) {
+    if (atomic && A.cells == nullptr && A.ncount == a->dh->grid->ncells && variant == 6) {
         FB2_TRY(fb2_warplist_build(a));
         A.wfirst = a->d_wfirst;
         A.wcount = a->d_wcount;
@@ -423,7 +423,7 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
         ctx->launches += f_dev ? 2 : 1;
     }
     if (o.scatter_mode == FB2_SCATTER_COLORED) {
-        FB2_CHECK(a->d_cells == nullptr, FB2_ERR_UNSUPPORTED, "coloured scatter on a partitioned assembler is not supported");
+        FB2_CHECK(a->d_cells == nullptr && a->ncells_active == 0, FB2_ERR_UNSUPPORTED, "coloured scatter on a partitioned assembler is not supported");
         FB2_TRY(fb2_coloring_build(a));
         for (int c = 0; c < a->ncolors; ++c) {
             A.cells = a->d_color_cells + a->color_ptr[c];
@@ -434,7 +434,9 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
         return FB2_OK;
     }
     A.cells = a->d_cells;
-    A.ncount = a->d_cells ? a->ncells_active : g->ncells;
+    const bool subset = a->d_cells != nullptr || a->ncells_active > 0;
+    A.cell_first = subset && !a->d_cells ? a->cell_first : 0;
+    A.ncount = subset ? a->ncells_active : g->ncells;
     if (A.ncount == 0) return FB2_OK;
     return launch_one(a, A, element, true, o.variant, !o.fillzero);
 }

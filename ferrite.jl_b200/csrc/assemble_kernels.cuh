@@ -30,7 +30,8 @@ struct AsmArgs {
     const uint16_t* map;
     const uint4* map8;     // packed offsets for k_cell_scalar
     const uint16_t* mapc;  // cell-major offsets for k_cell_blocks: [cell][mapstride], entry jl * n + il
-    const int32_t* cells;  // optional indirection (colour / partition subset)
+    const int32_t* cells;  // optional indirection (colour subset)
+    int64_t cell_first;    // without a list the launch covers cells [cell_first, cell_first + ncount)
     const int32_t* wfirst; // optional warp list of k_cell_scalar: first cell of every warp (4 consecutive warps = 4 grid rows)
     const uint8_t* wcount; //   and its number of cells (<= 32)
     int64_t ncount;        // number of cells handled by this launch
@@ -45,6 +46,10 @@ struct AsmArgs {
     // table offsets into c_tab / tab (in doubles)
     int o_w, o_N, o_dN, o_M, o_dM;
 };
+
+__device__ __forceinline__ int64_t fb2_cell_of(const AsmArgs& A, int64_t i) {
+    return A.cells ? (int64_t)A.cells[i] : A.cell_first + i;
+}
 
 __device__ __forceinline__ void fb2_flag_error(int* errflag, int code, int64_t cell) {
     if (atomicCAS(&errflag[0], 0, code) == 0) errflag[1] = (int)cell;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
         const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         active = idx < A.ncount;
         const int64_t idc = active ? idx : A.ncount - 1;
-        cell = A.cells ? (int64_t)A.cells[idc] : idc;
+        cell = fb2_cell_of(A, idc);
     }
     const int64_t np = A.ncells_pad;
 
@@ -569,12 +574,12 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
     // ---- staging of the scatter indices (asynchronous; consumed by the scatter at the end of phase B) --------------
     for (int i = threadIdx.x; i < ncl * (L.mapstride / 8); i += blockDim.x) {
         const int cl = i / (L.mapstride / 8), ch = i - cl * (L.mapstride / 8);
-        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        const int64_t cell = fb2_cell_of(A, cell0 + cl);
         fb2_cp_async16(s_map + (size_t)cl * L.mapstride + ch * 8, A.mapc + (size_t)cell * L.mapstride + ch * 8);
     }
     for (int i = threadIdx.x; i < ncl * N; i += blockDim.x) {
         const int cl = i / N, jl = i - cl * N;
-        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        const int64_t cell = fb2_cell_of(A, cell0 + cl);
         const int d = __ldg(A.cell_dofs + (size_t)jl * np + cell);
         s_dof[i] = d;
         s_base[i] = __ldg(A.colptr + d);
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
     // ---- phase A1: per (qp, cell): J, det > 0, J^-1, dOmega ---------------------------------------------------------
     for (int item = threadIdx.x; item < NQ * ncl; item += blockDim.x) {
         const int q = item / ncl, cl = item - q * ncl;
-        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        const int64_t cell = fb2_cell_of(A, cell0 + cl);
         double J[DIM][DIM];
 #pragma unroll
         for (int a = 0; a < DIM; ++a)
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
         // ---- phase A3 (Neo-Hooke): per (qp, cell): F = I + sum_a u_a (x) g_a, S, dS/dC -> P dOmega, dP/dF dOmega --------
         for (int item = threadIdx.x; item < NQ * ncl; item += blockDim.x) {
             const int q = item / ncl, cl = item - q * ncl;
-            const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+            const int64_t cell = fb2_cell_of(A, cell0 + cl);
             const double dO = s_dO[q * CELLS + cl];
             const double* gq = s_g + ((size_t)q * CELLS + cl) * NBS * DIM;
             double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -699,7 +704,7 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
         const int a = item % NBS;            // row node fastest
         const int rest = item / NBS;
         const int bt = rest % NT, cl = rest / NT;
-        const int64_t cell = A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl;
+        const int64_t cell = fb2_cell_of(A, cell0 + cl);
         const int b0 = bt * TB;
         double acc[TB][VDIM][VDIM];
 #pragma unroll
@@ -843,7 +848,7 @@ __global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const i
             const double v = s_K[e2];
             if (v != 0.0) {
                 const unsigned off = s_map[(size_t)cl * L.mapstride + e];
-                if (off == 0xFFFFu) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, A.cells ? (int64_t)A.cells[cell0 + cl] : cell0 + cl);
+                if (off == 0xFFFFu) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, fb2_cell_of(A, cell0 + cl));
                 else fb2_add<ATOMIC>(A.nzval + s_base[cl * N + e / N] + off, v);
             }
         }
@@ -928,7 +933,7 @@ __global__ void __launch_bounds__(SyrkOf<NBS, DIM>::NTHR) k_cell_syrk(const AsmA
     const int gt = WPC == 1 ? lane : (int)threadIdx.x;   // thread index inside the cell's group
     const int64_t ci = WPC == 1 ? (int64_t)blockIdx.x * S::CELLS + warp : (int64_t)blockIdx.x;
     if (ci >= A.ncount) return;              // a whole group leaves together
-    const int64_t cell = A.cells ? (int64_t)A.cells[ci] : ci;
+    const int64_t cell = fb2_cell_of(A, ci);
     unsigned char* smc = smraw + (WPC == 1 ? (size_t)warp * L.cell : 0);
     double* s_X = reinterpret_cast<double*>(smc + L.X);          // [NQP][NP]
     double* s_dO = reinterpret_cast<double*>(smc + L.dO);        // [NQP]

@@ -188,8 +188,10 @@ struct fb2_assembler {
     std::vector<int32_t> cell_color;
     std::vector<int64_t> color_ptr;      // [ncolors+1]
     int32_t* d_color_cells = nullptr;    // cells sorted by colour
-    // cell subset (partitioned assembly); nullptr = all cells
+    // cell subset (partitioned assembly): an index list, or the range [cell_first, cell_first + ncells_active) when
+    // d_cells is null and ncells_active > 0; otherwise all cells
     int32_t* d_cells = nullptr;
+    int64_t cell_first = 0;
     int64_t ncells_active = 0;
     // scratch for the host-buffer entry point
     double* d_nzval = nullptr;

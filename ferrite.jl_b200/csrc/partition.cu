@@ -48,9 +48,13 @@ struct fb2_part {
     // device binding
     fb2_assembler* bound = nullptr;
     int bound_device = -1;
-    int32_t* d_own_cells = nullptr;
     int32_t* d_col_owned = nullptr;   // list of local columns owned by other ranks
     int64_t n_unowned = 0;
+    // local cells [0, n_iface) are the own cells touching an exchanged dof, [n_iface, ncells_own) the other own cells;
+    // the interface exchange runs on a second stream while the interior cells are assembled
+    int64_t n_iface = 0;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_iface = nullptr, ev_done = nullptr;
 };
 
 namespace {
@@ -163,22 +167,42 @@ extern "C" int fb2_partition_create(fb2_dh* gdh, int nparts, int rank, const int
         for (int i = 0; i < ndpc; ++i)
             if (o < gdof_owner[cd[i]]) gdof_owner[cd[i]] = o;
     }
-    // ---- local cells: own + every cell touching an owned dof -----------------------------------------------------
+    // ---- local cells: own + every cell touching an owned dof ------------------------------------------------------
+    // Order: [own cells touching an exchanged dof | other own cells | halo cells], each by ascending global id.  A dof is
+    // exchanged when cells of more than one rank touch it.  Contiguous ranges let the kernels run without an index list,
+    // and the interface cells can be assembled first so that their exchange overlaps the interior.
+    std::vector<int32_t> gdof_maxowner((size_t)gdh->ndofs, -1);
     for (int64_t c = 0; c < ncells; ++c) {
-        bool own = owner[c] == rank, touch = false;
-        if (!own) {
+        const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
+        const int32_t o = owner[c];
+        for (int i = 0; i < ndpc; ++i)
+            if (o > gdof_maxowner[cd[i]]) gdof_maxowner[cd[i]] = o;
+    }
+    {
+        std::vector<int64_t> iface, inner, halo;
+        for (int64_t c = 0; c < ncells; ++c) {
             const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
-            for (int i = 0; i < ndpc && !touch; ++i) touch = gdof_owner[cd[i]] == rank;
+            if (owner[c] == rank) {
+                bool x = false;
+                for (int i = 0; i < ndpc && !x; ++i) x = gdof_owner[cd[i]] != gdof_maxowner[cd[i]];
+                (x ? iface : inner).push_back(c);
+            } else {
+                bool touch = false;
+                for (int i = 0; i < ndpc && !touch; ++i) touch = gdof_owner[cd[i]] == rank;
+                if (touch) halo.push_back(c);
+            }
         }
-        if (own || touch) {
-            P->cells_global.push_back(c);
-            P->cell_is_own.push_back(own ? 1 : 0);
-            P->ncells_own += own ? 1 : 0;
-        }
+        P->n_iface = (int64_t)iface.size();
+        P->ncells_own = (int64_t)(iface.size() + inner.size());
+        P->cells_global = iface;
+        P->cells_global.insert(P->cells_global.end(), inner.begin(), inner.end());
+        P->cells_global.insert(P->cells_global.end(), halo.begin(), halo.end());
+        P->cell_is_own.assign(P->cells_global.size(), 0);
+        std::fill(P->cell_is_own.begin(), P->cell_is_own.begin() + P->ncells_own, 1);
     }
     const int64_t nl = (int64_t)P->cells_global.size();
     if (nl == 0) { delete P; return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create: rank %d owns no cells", rank); }
-    // ---- local numbering (ascending global ids) ---------------------------------------------------------------------
+    // ---- local node / dof numbering (ascending global ids) ---------------------------------------------------------------------
     std::vector<int32_t> g2l_node((size_t)g->nnodes, -1), g2l_dof((size_t)gdh->ndofs, -1);
     for (int64_t l = 0; l < nl; ++l) {
         const int64_t c = P->cells_global[l];
@@ -305,8 +329,12 @@ static void free_binding(fb2_part* P) {
         cudaFree(pp.d_sendbuf); cudaFree(pp.d_recvbuf);
         pp.d_send_pos = pp.d_recv_pos = nullptr; pp.d_send_f = pp.d_recv_f = nullptr; pp.d_sendbuf = pp.d_recvbuf = nullptr;
     }
-    cudaFree(P->d_own_cells); cudaFree(P->d_col_owned);
-    P->d_own_cells = nullptr; P->d_col_owned = nullptr;
+    cudaFree(P->d_col_owned);
+    P->d_col_owned = nullptr;
+    if (P->xstream) cudaStreamDestroy(P->xstream);
+    if (P->ev_iface) cudaEventDestroy(P->ev_iface);
+    if (P->ev_done) cudaEventDestroy(P->ev_done);
+    P->xstream = nullptr; P->ev_iface = P->ev_done = nullptr;
     P->bound = nullptr;
 }
 
@@ -356,11 +384,11 @@ extern "C" int fb2_partition_bind(fb2_part* P, fb2_assembler* a) {
                 FB2_CHECK(h[t] >= 0, FB2_ERR_INTERNAL, "fb2_partition_bind: exchange entry missing in the local pattern (peer %d)", p);
         }
     }
-    std::vector<int32_t> own;
-    for (size_t l = 0; l < P->cell_is_own.size(); ++l)
-        if (P->cell_is_own[l]) own.push_back((int32_t)l);
-    FB2_CUDA(cudaMalloc(&P->d_own_cells, std::max<size_t>(own.size(), 1) * sizeof(int32_t)));
-    FB2_CUDA(cudaMemcpy(P->d_own_cells, own.data(), own.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    int lo_prio = 0, hi_prio = 0;
+    FB2_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    FB2_CUDA(cudaStreamCreateWithPriority(&P->xstream, cudaStreamNonBlocking, hi_prio));
+    FB2_CUDA(cudaEventCreateWithFlags(&P->ev_iface, cudaEventDisableTiming));
+    FB2_CUDA(cudaEventCreateWithFlags(&P->ev_done, cudaEventDisableTiming));
     // list of the local columns this rank does NOT own (only these are visited by the mask kernel)
     std::vector<int32_t> unowned;
     for (size_t d = 0; d < P->dof_owner.size(); ++d)
@@ -515,12 +543,43 @@ extern "C" int fb2_assemble_distributed(fb2_assembler* a, fb2_part* P, int mode,
     FB2_CHECK(P->bound == a, FB2_ERR_BAD_ARG, "fb2_assemble_distributed: bind the partition to this assembler first");
     FB2_CHECK(mode == FB2_DIST_EXCHANGE || mode == FB2_DIST_HALO || mode == FB2_DIST_OWN_ONLY, FB2_ERR_BAD_ARG,
               "fb2_assemble_distributed: unknown mode %d", mode);
-    if (mode != FB2_DIST_HALO) {
-        a->d_cells = P->d_own_cells;
+    fb2_ctx* ctx = a->dh->grid->ctx;
+    if (mode == FB2_DIST_EXCHANGE && P->nparts > 1 && P->n_iface > 0 && P->n_iface < P->ncells_own && ctx->nccl_comm) {
+        // interface cells first; their exchange (pack, NCCL send/recv, unpack, mask) runs on the second stream while the
+        // interior cells are assembled.  Interior cells touch no entry of an exchanged row or column, so the two never
+        // write the same address.
+        fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+        if (opts) o = *opts;
+        FB2_CHECK(o.scatter_mode == FB2_SCATTER_ATOMIC, FB2_ERR_UNSUPPORTED, "coloured scatter on a partitioned assembler is not supported");
+        a->cell_first = 0;
+        a->ncells_active = P->n_iface;
+        int rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, &o);
+        if (rc == FB2_OK) {
+            cudaEventRecord(P->ev_iface, ctx->stream);
+            cudaStreamWaitEvent(P->xstream, P->ev_iface, 0);
+            a->cell_first = P->n_iface;
+            a->ncells_active = P->ncells_own - P->n_iface;
+            o.fillzero = 0;
+            rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, &o);
+        }
+        a->cell_first = 0;
+        a->ncells_active = 0;
+        FB2_TRY(rc);
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = P->xstream;
+        rc = fb2_partition_exchange(P, nzval_dev, f_dev);
+        if (rc == FB2_OK) rc = fb2_partition_mask_unowned(P, nzval_dev, f_dev);
+        ctx->stream = main_stream;
+        FB2_TRY(rc);
+        FB2_CUDA(cudaEventRecord(P->ev_done, P->xstream));
+        FB2_CUDA(cudaStreamWaitEvent(ctx->stream, P->ev_done, 0));
+        return FB2_OK;
+    }
+    if (mode != FB2_DIST_HALO) {   // own cells = local cells [0, ncells_own)
+        a->cell_first = 0;
         a->ncells_active = P->ncells_own;
     }
     int rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, opts);
-    a->d_cells = nullptr;
     a->ncells_active = 0;
     FB2_TRY(rc);
     if (mode == FB2_DIST_OWN_ONLY) return FB2_OK;  // the host drives pack / transport / unpack_add / mask itself

@@ -226,7 +226,9 @@ enum { FB2_DIST_EXCHANGE = 0, /* assemble own cells, exchange interface columns 
  * Cells go to ranks as px*py*pz blocks for generate_grid input (dims, nullable = automatic) or as contiguous
  * ranges otherwise; a dof (= matrix column) is owned by the lowest rank among the cells touching it.  Rank
  * `rank` gets a local problem = own cells + halo cells (every cell touching an owned dof), local node / dof
- * numbering by ascending global id, and per-peer exchange lists. */
+ * numbering by ascending global id, and per-peer exchange lists.  Local cells are ordered [own cells touching
+ * a dof shared with another rank | other own cells | halo cells], each group by ascending global id, so that
+ * every group is a contiguous range and the interface exchange can overlap the interior cells. */
 int fb2_partition_create(fb2_dh* dh, int nparts, int rank, const int* dims, fb2_part** out);
 int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
                        int64_t* ndofs_local, int64_t* ndofs_owned);

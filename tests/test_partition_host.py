@@ -133,7 +133,11 @@ def test_local_problem_reproduces_global_numbering():
         assert np.array_equal(p.l2g_node[lg.cells - 1], gcells[p.cells_global - 1])
         assert np.array_equal(lg.nodes, gnodes[p.l2g_node - 1])
         assert np.array_equal(p.l2g_dof[ldh.cell_dofs - 1], gcd[p.cells_global - 1])
-        assert np.all(np.diff(p.l2g_dof) > 0) and np.all(np.diff(p.cells_global) > 0)
+        assert np.all(np.diff(p.l2g_dof) > 0)
+        # local cells: [own, interface | own, interior | halo], each ascending; own cells first
+        nown = int(p.cell_is_own.sum())
+        assert np.all(p.cell_is_own[:nown] == 1) and np.all(p.cell_is_own[nown:] == 0)
+        assert np.all(np.diff(p.cells_global[nown:]) > 0) and len(np.unique(p.cells_global)) == len(p.cells_global)
 
 
 def _free_port():
