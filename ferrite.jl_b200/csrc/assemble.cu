@@ -54,6 +54,8 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, 
     // variant 4: branch-free scatter for complete maps; measured slower on Q1 hex (2.98 vs 2.86 ms: the kernel is bound
     // by L2 atomic throughput, not by instruction issue), so the checked scatter stays the default
     else if (atomic && unchecked && variant == 4) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, false><<<grid, bs, 0, ctx->stream>>>(A);
+    // variant 7: without the lane-parity sector pairing of the scatter (A/B measurement)
+    else if (atomic && variant == 7) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, false><<<grid, bs, 0, ctx->stream>>>(A);
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);
     else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, false><<<grid, bs, 0, ctx->stream>>>(A);
     ctx->launches++;

@@ -198,7 +198,7 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 // k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true>
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true, bool PAIRX = true>
 __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     // lanes past the end stay alive (they redo a valid cell and write nothing): the face merges below shuffle across
     // the whole warp and synchronise the CTA
@@ -360,22 +360,35 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
 #pragma unroll
     for (int k = 0; k < NCH; ++k) mp[k] = s_map[k][threadIdx.x];
     bool missing = false;
+    // Sector pairing (Q1 quadrilateral / hexahedron): local nodes j and j^1 are x-mates, so column j of an even lane
+    // and column j^1 of the next (odd) lane are the same matrix column when j lies on the shared face, and their rows
+    // i are x-neighbours = adjacent entries of that CSC column.  Odd lanes therefore walk the columns in the order
+    // j^1: the two REDs of a lane pair fall into one 32-byte sector three times out of four.  The values stay in
+    // registers (compile-time indices), only selected by lane parity.
+    constexpr bool PAIR = MERGE && PAIRX;
+    const bool odd = PAIR && (threadIdx.x & 1);
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            const double v = kscale * (i <= j ? Ke[j * (j + 1) / 2 + i] : Ke[i * (i + 1) / 2 + j]);
-            const int e = j * NB + i;
-            const unsigned w32 = (e & 7) < 2 ? mp[e >> 3].x : ((e & 7) < 4 ? mp[e >> 3].y : ((e & 7) < 6 ? mp[e >> 3].z : mp[e >> 3].w));
+            const int jo = PAIR ? (j ^ 1) : j;
+            const double ve = i <= j ? Ke[j * (j + 1) / 2 + i] : Ke[i * (i + 1) / 2 + j];
+            const double vo = i <= jo ? Ke[jo * (jo + 1) / 2 + i] : Ke[i * (i + 1) / 2 + jo];
+            const double v = kscale * (odd ? vo : ve);
+            const int e = j * NB + i, eo = jo * NB + i;   // e and eo differ by NB = 8: same slot of the packed word
+            const unsigned we = (e & 7) < 2 ? mp[e >> 3].x : ((e & 7) < 4 ? mp[e >> 3].y : ((e & 7) < 6 ? mp[e >> 3].z : mp[e >> 3].w));
+            const unsigned wo = (eo & 7) < 2 ? mp[eo >> 3].x : ((eo & 7) < 4 ? mp[eo >> 3].y : ((eo & 7) < 6 ? mp[eo >> 3].z : mp[eo >> 3].w));
+            const unsigned w32 = odd ? wo : we;
             const unsigned off = (e & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
+            const int64_t bj = odd ? base[jo] : base[j];
             if (!active) continue;
             if (CHECK) {   // zero values are skipped; a non-zero aimed at a missing entry is an error
                 if (v != 0.0) {
                     if (off == 0xFFFFu) missing = true;
-                    else fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
+                    else fb2_add<ATOMIC>(A.nzval + bj + off, v);
                 }
             } else {       // complete map: adding an exact zero has no effect, no branches needed
-                fb2_add<ATOMIC>(A.nzval + base[j] + off, v);
+                fb2_add<ATOMIC>(A.nzval + bj + off, v);
             }
         }
     }
