@@ -115,6 +115,13 @@ _PROTOS = {
     "fb2_cellvalues_info": [_p, _ip, _ip, _ip, _ip, _ip],
     "fb2_cellvalues_export": [_p, _dp, _dp, _dp, _dp, _dp, _dp],
     "fb2_cellvalues_destroy": [_p],
+    "fb2_facetvalues_create": [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp],
+    "fb2_facetvalues_info": [_p, _ip, _ip, _ip, _ip, _ip],
+    "fb2_facetvalues_export": [_p, _dp, _dp, _dp],
+    "fb2_facetvalues_destroy": [_p],
+    "fb2_facetset_create": [_p, _i64p, C.c_int64, _pp],
+    "fb2_facetset_destroy": [_p],
+    "fb2_assemble_facets": [_p, _p, _p, C.c_int, _dp, C.c_int, _p],
     "fb2_assembler_create": [_p, _p, _p, _pp],
     "fb2_assemble": [_p, C.c_int, _p, C.c_size_t, _p, _p, _p, C.POINTER(AsmOpts)],
     "fb2_assemble_host": [_p, C.c_int, _p, C.c_size_t, _dp, _dp, _dp, C.POINTER(AsmOpts)],
@@ -151,6 +158,7 @@ _PROTOS = {
     "fb2_assemble_distributed": [_p, _p, C.c_int, C.c_int, _p, C.c_size_t, _p, _p, _p, C.POINTER(AsmOpts)],
 }
 DIST_EXCHANGE, DIST_HALO, DIST_OWN_ONLY = 0, 1, 2
+FACET_FLUX, FACET_TRACTION, FACET_NORMAL_TRACTION = 1, 2, 3
 
 lib.fb2_version.restype = C.c_char_p
 lib.fb2_version.argtypes = []

@@ -367,6 +367,63 @@ class CellValues:
         _destroy(self, "fb2_cellvalues_destroy", (getattr(self, "ctx", None),))
 
 
+# ---- FacetValues and the Neumann / traction facet loop ---------------------------------------------------
+class FacetQuadratureRule:
+    """FacetQuadratureRule{refshape}(order) (src/Quadrature/quadrature.jl:205-238)"""
+
+    def __init__(self, refshape, order):
+        self.refshape, self.order = refshape, int(order)
+
+
+class FacetValues:
+    """FacetValues(fqr, ip[, ip_geo]) (src/FEValues/FacetValues.jl:39-88)"""
+
+    def __init__(self, fqr, ip, ip_geo=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.fqr, self.ip = fqr, ip
+        self.h = C.c_void_p()
+        geo_order = ip_geo.order if ip_geo is not None else 1
+        L.call("fb2_facetvalues_create", self.ctx.h, ip.refshape, fqr.order, ip.order, ip.vdim, geo_order, C.byref(self.h))
+        nf, nq, nb, vd, rd = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.call("fb2_facetvalues_info", self.h, C.byref(nf), C.byref(nq), C.byref(nb), C.byref(vd), C.byref(rd))
+        self.nfacets, self.nq, self.nbase_scalar, self.vdim, self.rdim = nf.value, nq.value, nb.value, vd.value, rd.value
+
+    def tables(self):
+        w = np.empty((self.nfacets, self.nq))
+        pts = np.empty((self.nfacets, self.nq, self.rdim))
+        N = np.empty((self.nfacets, self.nq, self.nbase_scalar))
+        L.call("fb2_facetvalues_export", self.h, _ptr(w, C.c_double), _ptr(pts, C.c_double), _ptr(N, C.c_double))
+        return dict(w=w, points=pts, N=N)
+
+    def __del__(self):
+        _destroy(self, "fb2_facetvalues_destroy", (getattr(self, "ctx", None),))
+
+
+class FacetSet:
+    """A set of FacetIndex (cell, local facet) pairs, 1-based: getfacetset(grid, name) or a union of several."""
+
+    def __init__(self, grid, pairs):
+        self.grid = grid
+        self.pairs = _i64(np.asarray(pairs).reshape(-1, 2))
+        self.h = C.c_void_p()
+        L.call("fb2_facetset_create", grid.h, _ptr(self.pairs, C.c_int64), self.pairs.shape[0], C.byref(self.h))
+
+    def __del__(self):
+        _destroy(self, "fb2_facetset_destroy", (getattr(self, "grid", None),))
+
+
+def assemble_facets_(f, dh, fv, facetset, kind, params):
+    """The facet loop `for (cell, facet) in set: reinit!(fv, cell, facet); ...; assemble!(f, celldofs, fe)`
+    (hyperelasticity.jl:278-291).  kind: 'flux' (params q), 'traction' (params t[vdim]) or 'normal_traction' (params p:
+    fe += p n N dGamma; the tutorial's `ge[i] -= (dui . tn n) dGamma` is p = -tn).  f: device vector (torch / pointer)."""
+    if not isinstance(facetset, FacetSet):
+        facetset = FacetSet(dh.grid, facetset)
+    k = {"flux": L.FACET_FLUX, "traction": L.FACET_TRACTION, "normal_traction": L.FACET_NORMAL_TRACTION}[kind]
+    p = _f64(np.atleast_1d(np.asarray(params, dtype=np.float64)))
+    L.call("fb2_assemble_facets", dh.h, fv.h, facetset.h, k, _ptr(p, C.c_double), int(p.size), C.c_void_p(f.data_ptr()))
+    return f
+
+
 # ---- element menu -----------------------------------------------------------------------------------------------
 class HeatElement:
     """Ke = int k grad(Ni).grad(Nj), fe = int source Ni  (heat_equation.jl:143-164)"""

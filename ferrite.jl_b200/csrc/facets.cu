@@ -1,0 +1,326 @@
+// FacetValues and the Neumann / traction facet loop.
+//
+// Reference: FacetQuadratureRule src/Quadrature/quadrature.jl:205-238 (create_facet_quad_rule
+// src/FEValues/facet_integrals.jl:39-47), facet_to_element_transformation / weighted_normal
+// src/FEValues/facet_integrals.jl:102-239, reinit!(fv, cell, x, facet) src/FEValues/FacetValues.jl:128-154, and the
+// traction loop of docs/src/literate-tutorials/hyperelasticity.jl:278-291 with assemble!(f, dofs, fe)
+// src/assembler.jl:338-345.
+#include <cmath>
+#include <cstring>
+
+#include "common.h"
+
+struct fb2_fv {
+    fb2_ctx* ctx = nullptr;
+    int celltype = 0, rdim = 0, nfacets = 0, nq = 0, nb = 0, vdim = 1, ngeo = 0;
+    // host tables, facet-major then q-major: w[f][q], N[f][q][i], dM[f][q][j][d], pts[f][q][d]
+    std::vector<double> w, N, dM, pts;
+    double* d_tab = nullptr;   // [w | N | dM] on the device
+};
+
+struct fb2_fset {
+    fb2_grid* grid = nullptr;
+    int64_t n = 0;
+    std::vector<int64_t> pairs;     // (cell, facet) 1-based, as given
+    int32_t* d_cell = nullptr;      // 0-based
+    int8_t* d_facet = nullptr;      // 0-based
+};
+
+namespace {
+
+int facet_celltype(int celltype) {
+    switch (celltype) {
+        case FB2_TRIANGLE: case FB2_QUADRILATERAL: return FB2_LINE;
+        case FB2_TETRAHEDRON: return FB2_TRIANGLE;
+        case FB2_HEXAHEDRON: return FB2_QUADRILATERAL;
+    }
+    return 0;
+}
+
+// facet: 0-based; p: point of the facet's reference shape; out: point of the cell's reference shape
+void facet_to_element(int celltype, int facet, const double* p, double* out) {
+    const double x = p[0], y = p[1];
+    switch (celltype) {
+        case FB2_QUADRILATERAL: {
+            const double t[4][2] = {{x, -1.0}, {1.0, x}, {-x, 1.0}, {-1.0, -x}};
+            out[0] = t[facet][0]; out[1] = t[facet][1];
+            break;
+        }
+        case FB2_TRIANGLE: {
+            const double s = (x + 1.0) / 2;
+            const double t[3][2] = {{1.0 - s, s}, {0.0, 1.0 - s}, {s, 0.0}};
+            out[0] = t[facet][0]; out[1] = t[facet][1];
+            break;
+        }
+        case FB2_HEXAHEDRON: {
+            const double t[6][3] = {{y, x, -1.0}, {x, -1.0, y}, {1.0, x, y}, {-x, 1.0, y}, {-1.0, y, x}, {x, y, 1.0}};
+            for (int d = 0; d < 3; ++d) out[d] = t[facet][d];
+            break;
+        }
+        case FB2_TETRAHEDRON: {
+            const double z = 1.0 - x - y;
+            const double t[4][3] = {{z, y, 0.0}, {y, 0.0, z}, {x, y, z}, {0.0, z, y}};
+            for (int d = 0; d < 3; ++d) out[d] = t[facet][d];
+            break;
+        }
+    }
+}
+
+struct FacetArgs {
+    const int32_t* conn;
+    const double* xyz;
+    const int32_t* cell_dofs;
+    int64_t ncells_pad;
+    const int32_t* cell;
+    const int8_t* facet;
+    int64_t n;
+    const double* tab;
+    int o_w, o_N, o_dM;
+    int celltype, nq, nb, vdim, ngeo, xstride;
+    int kind;
+    double p[3];
+    double* f;
+    int* errflag;
+};
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// J stored [a][b] = d x_a / d xi_b; returns the weighted normal of local facet `facet` (0-based)
+template <int DIM>
+__device__ void weighted_normal(int celltype, int facet, const double (&J)[DIM][DIM], double (&wn)[DIM]) {
+    if (DIM == 2) {
+        if (celltype == FB2_QUADRILATERAL) {
+            const double s = facet < 2 ? 1.0 : -1.0;
+            const int c = facet & 1;   // facets 1,3 use column 1; facets 2,4 column 2
+            wn[0] = s * J[1][c];
+            wn[1] = -s * J[0][c];
+        } else {
+            if (facet == 0) { wn[0] = -(J[1][0] - J[1][1]); wn[1] = J[0][0] - J[0][1]; }
+            else if (facet == 1) { wn[0] = -J[1][1]; wn[1] = J[0][1]; }
+            else { wn[0] = J[1][0]; wn[1] = -J[0][0]; }
+        }
+    } else {
+        double a[3], b[3];
+        int ia, ib;
+        if (celltype == FB2_HEXAHEDRON) {
+            const int A[6] = {1, 0, 1, 2, 2, 0}, B[6] = {0, 2, 2, 0, 1, 1};
+            ia = A[facet]; ib = B[facet];
+            for (int d = 0; d < 3; ++d) { a[d] = J[d][ia]; b[d] = J[d][ib]; }
+        } else if (facet == 2) {
+            for (int d = 0; d < 3; ++d) { a[d] = J[d][0] - J[d][2]; b[d] = J[d][1] - J[d][2]; }
+        } else {
+            const int A[4] = {1, 0, 0, 2}, B[4] = {0, 2, 0, 1};
+            ia = A[facet]; ib = B[facet];
+            for (int d = 0; d < 3; ++d) { a[d] = J[d][ia]; b[d] = J[d][ib]; }
+        }
+        double c[3];
+        cross3(a, b, c);
+        for (int d = 0; d < 3; ++d) wn[d] = c[d];
+    }
+}
+
+// thread per (cell, facet) pair: per facet quadrature point J, weighted normal, |wn| > 0, dGamma; fe goes straight
+// into f with FP64 REDs (a facet set is a surface: O(ncells^(2/3)) pairs, not a hot loop)
+template <int DIM>
+__global__ void k_facets(const FacetArgs A) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.n) return;
+    const int64_t cell = A.cell[t];
+    const int facet = A.facet[t];
+    double x[8][DIM];
+    for (int j = 0; j < A.ngeo; ++j) {
+        const int node = A.conn[(size_t)j * A.ncells_pad + cell];
+        for (int a = 0; a < DIM; ++a) x[j][a] = A.xyz[(size_t)node * A.xstride + a];
+    }
+    const double* tw = A.tab + A.o_w + (size_t)facet * A.nq;
+    const double* tN = A.tab + A.o_N + (size_t)facet * A.nq * A.nb;
+    const double* tdM = A.tab + A.o_dM + (size_t)facet * A.nq * A.ngeo * DIM;
+    for (int q = 0; q < A.nq; ++q) {
+        double J[DIM][DIM];
+        for (int a = 0; a < DIM; ++a)
+            for (int b = 0; b < DIM; ++b) J[a][b] = 0.0;
+        for (int j = 0; j < A.ngeo; ++j)
+            for (int a = 0; a < DIM; ++a)
+                for (int b = 0; b < DIM; ++b) J[a][b] = fma(x[j][a], tdM[(q * A.ngeo + j) * DIM + b], J[a][b]);
+        double wn[DIM];
+        weighted_normal<DIM>(A.celltype, facet, J, wn);
+        double det = 0.0;
+        for (int a = 0; a < DIM; ++a) det += wn[a] * wn[a];
+        det = sqrt(det);
+        if (!(det > 0.0)) {
+            if (atomicCAS(&A.errflag[0], 0, FB2_ERR_DETJ_NOT_POSITIVE) == 0) A.errflag[1] = (int)cell;
+            return;
+        }
+        const double dG = det * tw[q];
+        double tr[3] = {0.0, 0.0, 0.0};   // traction (or scalar flux in tr[0]) at this point
+        if (A.kind == FB2_FACET_FLUX) tr[0] = A.p[0];
+        else if (A.kind == FB2_FACET_TRACTION) { for (int c = 0; c < A.vdim; ++c) tr[c] = A.p[c]; }
+        else { for (int c = 0; c < DIM; ++c) tr[c] = A.p[0] * (wn[c] / det); }
+        for (int i = 0; i < A.nb; ++i) {
+            const double Ni = tN[q * A.nb + i];
+            if (Ni == 0.0) continue;
+            for (int c = 0; c < A.vdim; ++c) {
+                const int dof = A.cell_dofs[(size_t)(i * A.vdim + c) * A.ncells_pad + cell];
+                atomicAdd(A.f + dof, Ni * tr[c] * dG);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int fb2_facetvalues_create(fb2_ctx* ctx, int celltype, int qr_order, int ip_order, int vdim, int geo_order, fb2_fv** out) {
+    FB2_CHECK(ctx && out, FB2_ERR_BAD_ARG, "fb2_facetvalues_create: null argument");
+    LagrangeInfo ip, geo;
+    FB2_CHECK(fb2_lagrange(celltype, ip_order, &ip), FB2_ERR_UNSUPPORTED, "FacetValues: Lagrange order %d on cell type %d not supported", ip_order, celltype);
+    FB2_CHECK(fb2_lagrange(celltype, geo_order, &geo), FB2_ERR_UNSUPPORTED, "FacetValues: geometric order %d not supported", geo_order);
+    FB2_CHECK(vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "FacetValues: vdim must be 1..3");
+    const int fct = facet_celltype(celltype);
+    FB2_CHECK(fct != 0, FB2_ERR_UNSUPPORTED, "FacetValues: cell type %d has no facet rule here", celltype);
+    const RefShapeInfo* rs = fb2_refshape(celltype);
+    std::vector<double> w, p;
+    FB2_CHECK(fb2_quadrature(fct, qr_order, &w, &p), FB2_ERR_UNSUPPORTED, "FacetQuadratureRule of order %d on cell type %d not supported", qr_order, celltype);
+    fb2_fv* fv = new fb2_fv();
+    fv->ctx = ctx;
+    fv->celltype = celltype;
+    fv->rdim = ip.rdim;
+    fv->nfacets = rs->rdim == 2 ? rs->nedges : rs->nfaces;
+    fv->nq = (int)w.size();
+    fv->nb = ip.nbase;
+    fv->vdim = vdim;
+    fv->ngeo = geo.nbase;
+    const int rd = ip.rdim, frd = rd - 1, nf = fv->nfacets, nq = fv->nq;
+    fv->w.resize((size_t)nf * nq);
+    fv->pts.resize((size_t)nf * nq * rd);
+    fv->N.resize((size_t)nf * nq * fv->nb);
+    fv->dM.resize((size_t)nf * nq * fv->ngeo * rd);
+    std::vector<double> dN((size_t)fv->nb * rd), M((size_t)fv->ngeo);
+    for (int f = 0; f < nf; ++f)
+        for (int q = 0; q < nq; ++q) {
+            // the triangle's edges are parametrised over (0,1): half the line weights (quadrature.jl:231-232)
+            fv->w[(size_t)f * nq + q] = celltype == FB2_TRIANGLE ? w[q] / 2 : w[q];
+            double fp[2] = {p[(size_t)q * frd], frd > 1 ? p[(size_t)q * frd + 1] : 0.0};
+            double* xi = &fv->pts[((size_t)f * nq + q) * rd];
+            facet_to_element(celltype, f, fp, xi);
+            fb2_lagrange_eval(ip, xi, &fv->N[((size_t)f * nq + q) * fv->nb], dN.data());
+            fb2_lagrange_eval(geo, xi, M.data(), &fv->dM[((size_t)f * nq + q) * fv->ngeo * rd]);
+        }
+    *out = fv;
+    return FB2_OK;
+}
+
+extern "C" int fb2_facetvalues_info(fb2_fv* fv, int* nfacets, int* nq, int* nbase_scalar, int* vdim, int* rdim) {
+    FB2_CHECK(fv, FB2_ERR_BAD_ARG, "fb2_facetvalues_info: null handle");
+    if (nfacets) *nfacets = fv->nfacets;
+    if (nq) *nq = fv->nq;
+    if (nbase_scalar) *nbase_scalar = fv->nb;
+    if (vdim) *vdim = fv->vdim;
+    if (rdim) *rdim = fv->rdim;
+    return FB2_OK;
+}
+
+extern "C" int fb2_facetvalues_export(fb2_fv* fv, double* w, double* points, double* N) {
+    FB2_CHECK(fv, FB2_ERR_BAD_ARG, "fb2_facetvalues_export: null handle");
+    if (w) memcpy(w, fv->w.data(), fv->w.size() * sizeof(double));
+    if (points) memcpy(points, fv->pts.data(), fv->pts.size() * sizeof(double));
+    if (N) memcpy(N, fv->N.data(), fv->N.size() * sizeof(double));
+    return FB2_OK;
+}
+
+extern "C" int fb2_facetvalues_destroy(fb2_fv* fv) {
+    if (!fv) return FB2_OK;
+    if (fv->d_tab) cudaFree(fv->d_tab);
+    delete fv;
+    return FB2_OK;
+}
+
+extern "C" int fb2_facetset_create(fb2_grid* g, const int64_t* pairs, int64_t n, fb2_fset** out) {
+    FB2_CHECK(g && out && (pairs || n == 0) && n >= 0, FB2_ERR_BAD_ARG, "fb2_facetset_create: bad argument");
+    const RefShapeInfo* rs = fb2_refshape(g->celltype);
+    const int nf = rs->rdim == 1 ? 2 : (rs->rdim == 2 ? rs->nedges : rs->nfaces);
+    for (int64_t k = 0; k < n; ++k) {
+        FB2_CHECK(pairs[2 * k] >= 1 && pairs[2 * k] <= g->ncells && pairs[2 * k + 1] >= 1 && pairs[2 * k + 1] <= nf, FB2_ERR_BAD_ARG,
+                  "fb2_facetset_create: (cell %lld, facet %lld) out of range", (long long)pairs[2 * k], (long long)pairs[2 * k + 1]);
+    }
+    fb2_fset* s = new fb2_fset();
+    s->grid = g;
+    s->n = n;
+    s->pairs.assign(pairs, pairs + 2 * n);
+    *out = s;
+    return FB2_OK;
+}
+
+extern "C" int fb2_facetset_destroy(fb2_fset* s) {
+    if (!s) return FB2_OK;
+    if (s->d_cell) cudaFree(s->d_cell);
+    if (s->d_facet) cudaFree(s->d_facet);
+    delete s;
+    return FB2_OK;
+}
+
+extern "C" int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int kind, const double* params, int nparams, double* f_dev) {
+    FB2_CHECK(dh && fv && set && f_dev, FB2_ERR_BAD_ARG, "fb2_assemble_facets: null argument");
+    fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(set->grid == g, FB2_ERR_BAD_ARG, "fb2_assemble_facets: the facet set belongs to another grid");
+    FB2_CHECK(fv->celltype == g->celltype && fv->rdim == g->sdim, FB2_ERR_BAD_ARG, "fb2_assemble_facets: FacetValues do not match the grid");
+    FB2_CHECK(fv->ngeo == g->nnpc && fv->ngeo <= 8, FB2_ERR_UNSUPPORTED, "fb2_assemble_facets: geometric interpolation must match the cell's nodes");
+    FB2_CHECK(dh->fields.size() == 1 && dh->ndpc == fv->nb * fv->vdim, FB2_ERR_BAD_ARG, "fb2_assemble_facets: FacetValues must cover the (single) field");
+    FB2_CHECK(kind == FB2_FACET_FLUX || kind == FB2_FACET_TRACTION || kind == FB2_FACET_NORMAL_TRACTION, FB2_ERR_BAD_ARG,
+              "fb2_assemble_facets: unknown kind %d", kind);
+    const int need = kind == FB2_FACET_TRACTION ? fv->vdim : 1;
+    FB2_CHECK(params && nparams == need, FB2_ERR_BAD_ARG, "fb2_assemble_facets: kind %d takes %d parameter(s)", kind, need);
+    FB2_CHECK(kind != FB2_FACET_FLUX || fv->vdim == 1, FB2_ERR_BAD_ARG, "fb2_assemble_facets: a flux needs a scalar field");
+    FB2_CHECK(kind != FB2_FACET_NORMAL_TRACTION || fv->vdim == fv->rdim, FB2_ERR_BAD_ARG, "fb2_assemble_facets: a normal traction needs vdim == dim");
+    if (set->n == 0) return FB2_OK;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FacetArgs A;
+    memset(&A, 0, sizeof(A));
+    const int nf = fv->nfacets, nq = fv->nq, rd = fv->rdim;
+    A.o_w = 0;
+    A.o_N = nf * nq;
+    A.o_dM = A.o_N + nf * nq * fv->nb;
+    if (!fv->d_tab) {
+        std::vector<double> h((size_t)A.o_dM + (size_t)nf * nq * fv->ngeo * rd);
+        memcpy(h.data() + A.o_w, fv->w.data(), fv->w.size() * sizeof(double));
+        memcpy(h.data() + A.o_N, fv->N.data(), fv->N.size() * sizeof(double));
+        memcpy(h.data() + A.o_dM, fv->dM.data(), fv->dM.size() * sizeof(double));
+        FB2_CUDA(cudaMalloc(&fv->d_tab, h.size() * sizeof(double)));
+        FB2_CUDA(cudaMemcpy(fv->d_tab, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (!set->d_cell) {
+        std::vector<int32_t> c((size_t)set->n);
+        std::vector<int8_t> f((size_t)set->n);
+        for (int64_t k = 0; k < set->n; ++k) { c[k] = (int32_t)(set->pairs[2 * k] - 1); f[k] = (int8_t)(set->pairs[2 * k + 1] - 1); }
+        FB2_CUDA(cudaMalloc(&set->d_cell, c.size() * sizeof(int32_t)));
+        FB2_CUDA(cudaMalloc(&set->d_facet, f.size() * sizeof(int8_t)));
+        FB2_CUDA(cudaMemcpy(set->d_cell, c.data(), c.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        FB2_CUDA(cudaMemcpy(set->d_facet, f.data(), f.size() * sizeof(int8_t), cudaMemcpyHostToDevice));
+    }
+    A.conn = g->d_conn;
+    A.xyz = g->d_xyz;
+    A.cell_dofs = dh->d_cell_dofs;
+    A.ncells_pad = g->ncells_pad;
+    A.cell = set->d_cell;
+    A.facet = set->d_facet;
+    A.n = set->n;
+    A.tab = fv->d_tab;
+    A.celltype = g->celltype;
+    A.nq = nq; A.nb = fv->nb; A.vdim = fv->vdim; A.ngeo = fv->ngeo; A.xstride = g->xstride;
+    A.kind = kind;
+    for (int k = 0; k < nparams && k < 3; ++k) A.p[k] = params[k];
+    A.f = f_dev;
+    A.errflag = ctx->d_errflag;
+    const unsigned grid = (unsigned)((set->n + 127) / 128);
+    if (rd == 2) k_facets<2><<<grid, 128, 0, ctx->stream>>>(A);
+    else if (rd == 3) k_facets<3><<<grid, 128, 0, ctx->stream>>>(A);
+    else return fb2_fail(FB2_ERR_UNSUPPORTED, "fb2_assemble_facets: 1-D cells are not supported");
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}

@@ -164,4 +164,24 @@ function Ferrite.apply!(K::B200Matrix, ch::ConstraintHandler, nzval_dev::Ptr{Flo
     return m[]
 end
 
+# ---- Neumann / traction facet loop (hyperelasticity.jl:278-291) ------------------------------------------------------
+# `facetset` is a reference facet set (OrderedSet{FacetIndex}); kind: 1 flux (params q), 2 traction (params t),
+# 3 normal traction (params p: fe += p n N dGamma; the tutorial's `ge[i] -= (dui . tn n) dGamma` is p = -tn).
+# f_dev is the device residual / load vector the volume assembly wrote.
+function assemble_facets!(f_dev::Ptr{Float64}, prob::DeviceProblem, celltype::Integer, ip_order::Int, vdim::Int, qr_order::Int,
+        facetset, kind::Integer, params::Vector{Float64})
+    pairs = Matrix{Int64}(undef, 2, length(facetset))
+    for (k, fi) in enumerate(facetset)
+        pairs[1, k], pairs[2, k] = fi[1], fi[2]
+    end
+    fv = Ref{Ptr{Cvoid}}(C_NULL)
+    set = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_facetvalues_create (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, Ptr{Ptr{Cvoid}}) prob.ctx.h celltype qr_order ip_order vdim 1 fv
+    @fb2 fb2_facetset_create (Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Ptr{Cvoid}}) prob.grid pairs size(pairs, 2) set
+    @fb2 fb2_assemble_facets (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Cint, Ptr{Float64}) prob.dh fv[] set[] kind params length(params) f_dev
+    ccall((:fb2_facetset_destroy, LIB), Cint, (Ptr{Cvoid},), set[])
+    ccall((:fb2_facetvalues_destroy, LIB), Cint, (Ptr{Cvoid},), fv[])
+    return f_dev
+end
+
 end # module

@@ -217,6 +217,30 @@ int fb2_apply(fb2_ch* ch, fb2_pattern* p, double* nzval_dev, double* f_dev, int 
 int fb2_apply_vector(fb2_ch* ch, double* u_dev, int applyzero);
 int fb2_ch_destroy(fb2_ch* ch);
 
+/* ---- FacetValues and the Neumann / traction facet loop ------------------------ */
+typedef struct fb2_fv fb2_fv;
+typedef struct fb2_fset fb2_fset;
+/* FacetValues(FacetQuadratureRule{refshape}(qr_order), Lagrange{refshape,ip_order}()^vdim):
+ * src/FEValues/FacetValues.jl:39-88; FacetQuadratureRule src/Quadrature/quadrature.jl:205-238 with
+ * facet_to_element_transformation src/FEValues/facet_integrals.jl:102-217 */
+int fb2_facetvalues_create(fb2_ctx* ctx, int celltype, int qr_order, int ip_order, int vdim, int geo_order, fb2_fv** out);
+int fb2_facetvalues_info(fb2_fv* fv, int* nfacets, int* nq, int* nbase_scalar, int* vdim, int* rdim);
+/* tables per local facet: w nq x nfacets, points rdim x nq x nfacets (cell reference coordinates), N n x nq x nfacets
+ * (column-major); any pointer may be NULL */
+int fb2_facetvalues_export(fb2_fv* fv, double* w, double* points, double* N);
+int fb2_facetvalues_destroy(fb2_fv* fv);
+/* a FacetIndex set, e.g. getfacetset(grid, "top") or a union: pairs = 2 x n (cell, local facet), 1-based */
+int fb2_facetset_create(fb2_grid* grid, const int64_t* pairs, int64_t n, fb2_fset** out);
+int fb2_facetset_destroy(fb2_fset* set);
+enum { FB2_FACET_FLUX = 1,            /* scalar field: fe[i] += q N_i dGamma; params = {q} */
+       FB2_FACET_TRACTION = 2,        /* fe[(i,c)] += t_c N_i dGamma; params = t[vdim] */
+       FB2_FACET_NORMAL_TRACTION = 3  /* fe[(i,c)] += p n_c N_i dGamma, n = outward unit normal; params = {p}
+                                         (hyperelasticity.jl:278-291 is p = -tn) */ };
+/* for (cell, facet) in set: reinit!(fv, cell, facet) (src/FEValues/FacetValues.jl:128-154: J, weighted_normal
+ * src/FEValues/facet_integrals.jl:122-239, detJ = |weighted normal| > 0, dGamma = detJ w); integrate fe;
+ * assemble!(f, celldofs(cell), fe) (src/assembler.jl:338-345).  Adds onto f_dev (no zero fill). */
+int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int kind, const double* params, int nparams, double* f_dev);
+
 /* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
 typedef struct fb2_part fb2_part;
 enum { FB2_DIST_EXCHANGE = 0, /* assemble own cells, exchange interface columns over NCCL */

@@ -15,6 +15,8 @@ values instead -- see `tests/test_oracle_goldens.py`:
   * literal celldofs vectors   test/test_dofs.jl:71-126,256-257
   * literal prescribed_dofs / inhomogeneities   test/test_constraints.jl:100-101,171-172, test/test_dofs.jl:257
   * 3-dof assemble!+apply! KAT   test/test_assembler_extensions.jl:69-86
+  * hyperelasticity tutorial norm(u) = 4.761404305083876   docs/src/literate-tutorials/hyperelasticity.jl:442
+    (Neo-Hooke tangent/residual + facet traction + inhomogeneous Dirichlet + apply_zero!)
 Third-party arithmetic not vendored under the reference tree: Tensors.jl 1.17.1
 (det/inv/otimes closed forms, restated here), ForwardDiff 1.4.1 (shape-function
 gradients; restated as analytic derivatives), SparseArrays 1.12 (CSC layout).
@@ -28,3 +30,4 @@ from .pattern import *        # noqa: F401,F403
 from .element import *        # noqa: F401,F403
 from .assemble import *       # noqa: F401,F403
 from .constraints import *    # noqa: F401,F403
+from .facets import *         # noqa: F401,F403

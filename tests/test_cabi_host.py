@@ -199,6 +199,24 @@ def test_cellvalues_tables_match_oracle(hctx, ct, qo, io, vdim):
     assert np.allclose(t["dMdxi"], ocv.dMdxi, rtol=1e-13, atol=1e-15)
 
 
+@pytest.mark.parametrize("ct,qo,io,vdim", [
+    (fb.Quadrilateral, 2, 1, 1), (fb.Quadrilateral, 3, 2, 2), (fb.Triangle, 2, 2, 1), (fb.Triangle, 1, 1, 2),
+    (fb.Hexahedron, 2, 1, 3), (fb.Hexahedron, 3, 2, 1), (fb.Tetrahedron, 1, 1, 3), (fb.Tetrahedron, 3, 2, 3),
+])
+def test_facetvalues_tables_match_oracle(hctx, ct, qo, io, vdim):
+    # FacetQuadratureRule + facet_to_element_transformation (src/Quadrature/quadrature.jl:205-238,
+    # src/FEValues/facet_integrals.jl:102-217)
+    fv = fb.FacetValues(fb.FacetQuadratureRule(ct, qo), fb.Lagrange(ct, io) ** vdim, ctx=hctx)
+    t = fv.tables()
+    oip = O.Lagrange(SHAPE[ct], io)
+    ofv = O.FacetValues(O.FacetQuadratureRule(SHAPE[ct], qo), oip ** vdim if vdim > 1 else oip)
+    assert fv.nfacets == ofv.fqr.nfacets and fv.nq == ofv.w.shape[1] and fv.nbase_scalar == oip.nbase
+    assert np.allclose(t["w"], ofv.w, rtol=1e-14, atol=0)
+    opts = np.array([r.points for r in ofv.fqr.rules])
+    assert np.allclose(t["points"], opts, rtol=1e-14, atol=1e-15)
+    assert np.allclose(t["N"], ofv.N, rtol=1e-13, atol=1e-15)
+
+
 def test_bad_arguments_are_reported(hctx):
     with pytest.raises(fb.FB2Error):
         fb.generate_grid(fb.Quadrilateral, (0, 2), ctx=hctx)

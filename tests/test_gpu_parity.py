@@ -507,3 +507,77 @@ def test_partitioned_assembly_matches_serial_oracle(ctx, mode, ct, nel, order, v
     fg[fd - 1] = fv
     ok, nrm = close(fg, of)
     assert ok, nrm
+
+
+# ---- facet loop: FacetValues + Neumann / traction term ------------------------------------------------
+@pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,params,sets", [
+    (fb.Hexahedron, (4, 3, 3), 1, 3, 2, "normal_traction", -0.1, ("top", "bottom", "front", "back")),
+    (fb.Hexahedron, (3, 3, 2), 2, 3, 3, "traction", (0.3, -0.2, 0.7), ("right", "top")),
+    (fb.Hexahedron, (3, 3, 3), 2, 1, 2, "flux", 2.5, ("left", "right", "top", "bottom", "front", "back")),
+    (fb.Tetrahedron, (3, 3, 3), 1, 3, 1, "normal_traction", 0.4, ("top", "bottom", "front", "back", "left", "right")),
+    (fb.Tetrahedron, (2, 3, 2), 2, 3, 3, "traction", (1.0, 2.0, -1.0), ("left", "back")),
+    (fb.Quadrilateral, (5, 4), 2, 2, 3, "normal_traction", 1.5, ("left", "right", "top", "bottom")),
+    (fb.Triangle, (4, 5), 2, 1, 2, "flux", -1.0, ("top", "left")),
+    (fb.Triangle, (4, 3), 1, 2, 2, "traction", (0.5, 0.25), ("bottom", "right")),
+])
+def test_facet_loop_matches_oracle(ctx, ct, nel, order, vdim, qo, kind, params, sets):
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    ip, oip = cv.ip, ocv.ip
+    fv = fb.FacetValues(fb.FacetQuadratureRule(ct, qo), ip)
+    ofv = O.FacetValues(O.FacetQuadratureRule(SHAPE[ct], qo), oip)
+    pairs = np.concatenate([fb.getfacetset(g, s) for s in sets])
+    opairs = np.concatenate([np.asarray(og.facetsets[s]).reshape(-1, 2) for s in sets])
+    assert np.array_equal(pairs, opairs)
+    f = ctx.zeros(dh.ndofs)
+    f += 1.0   # the facet loop adds onto f
+    fb.assemble_facets_(f, dh, fv, pairs, kind, params)
+    ctx.synchronize()
+    of = np.ones(odh.ndofs)
+    O.assemble_facets(odh, ofv, of, opairs, kind, params)
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, nrm
+
+
+def test_hyperelasticity_tutorial_golden_through_the_gpu_path(ctx):
+    # docs/src/literate-tutorials/hyperelasticity.jl:241-291,329-442: norm(u) == 4.761404305083876
+    # K and g (Neo-Hooke volume terms + facet traction) and apply_zero! on the device, linear solves on the host
+    import torch
+    N, Lx = 10, 1.0
+    g = fb.generate_grid(fb.Tetrahedron, (N, N, N), (0.0, 0.0, 0.0), (Lx, Lx, Lx))
+    ip = fb.Lagrange(fb.RefTetrahedron, 1) ** 3
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefTetrahedron, 1), ip)
+    fv = fb.FacetValues(fb.FacetQuadratureRule(fb.RefTetrahedron, 1), ip)
+    th = np.pi / 3
+
+    def rotation(x, t):
+        return t * np.array([0.0, Lx / 2 - x[1] + (x[1] - Lx / 2) * np.cos(th) - (x[2] - Lx / 2) * np.sin(th),
+                             Lx / 2 - x[2] + (x[1] - Lx / 2) * np.sin(th) + (x[2] - Lx / 2) * np.cos(th)])
+
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "right"), lambda x, t: [0.0, 0.0, 0.0], [1, 2, 3]))
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), rotation, [1, 2, 3]))
+    fb.close_(ch)
+    fb.update_(ch, 0.5)
+    gamma_n = fb.FacetSet(g, np.concatenate([fb.getfacetset(g, k) for k in ("top", "bottom", "front", "back")]))
+    E, nu = 10.0, 0.3
+    elem = fb.NeoHookeElement(lam=E * nu / ((1 + nu) * (1 - 2 * nu)), mu=E / (2 * (1 + nu)), b=(0.0, -0.5, 0.0))
+    K = fb.allocate_matrix(dh)
+    res = ctx.zeros(dh.ndofs)
+    un = ctx.zeros(dh.ndofs)
+    fb.apply_(un, ch)
+    du = ctx.zeros(dh.ndofs)
+    for it in range(31):
+        u = un + du
+        fb.assemble_(fb.start_assemble(K, res), elem, cv, u=u)
+        fb.assemble_facets_(res, dh, fv, gamma_n, "normal_traction", -0.1)
+        fb.apply_zero_(K, res, ch)
+        if float(res.norm()) < 1e-8:
+            break
+        ddu = torch.from_numpy(spla.spsolve(K.tocsc(), res.cpu().numpy())).to(res.device)
+        fb.apply_(ddu, ch, applyzero=True)
+        du -= ddu
+    else:
+        raise AssertionError("Newton did not converge")
+    ref = 4.761404305083876
+    assert abs(float(u.norm()) - ref) / ref < 1e-7, float(u.norm())
