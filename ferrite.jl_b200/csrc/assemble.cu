@@ -54,6 +54,17 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, 
     // variant 4: branch-free scatter for complete maps; measured slower on Q1 hex (2.98 vs 2.86 ms: the kernel is bound
     // by L2 atomic throughput, not by instruction issue), so the checked scatter stays the default
     else if (atomic && unchecked && variant == 4) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, false><<<grid, bs, 0, ctx->stream>>>(A);
+    // variant 8: warp-specialised compute / scatter groups (Q1 quadrilaterals and hexahedra)
+    else if (atomic && variant == 8 && A.wfirst == nullptr && ((DIM == 3 && NB == 8 && NGEO == 8) || (DIM == 2 && NB == 4 && NGEO == 4))) {
+        if constexpr ((DIM == 3 && NB == 8 && NGEO == 8) || (DIM == 2 && NB == 4 && NGEO == 4)) {
+            auto k = unchecked ? k_cell_scalar_ws<DIM, NGEO, NB, NQ, ELEM, ROLL, false> : k_cell_scalar_ws<DIM, NGEO, NB, NQ, ELEM, ROLL, true>;
+            const size_t smem = WsSmem<NB>::total;
+            FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t nbatch = (A.ncount + 127) / 128;
+            const unsigned g2 = (unsigned)std::min<int64_t>(nbatch, 2 * (int64_t)ctx->sm_count);
+            k<<<g2, 256, smem, ctx->stream>>>(A, nbatch);
+        }
+    }
     // variant 7: without the lane-parity sector pairing of the scatter (A/B measurement)
     else if (atomic && variant == 7) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, false><<<grid, bs, 0, ctx->stream>>>(A);
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);

@@ -55,6 +55,11 @@ __device__ __forceinline__ void fb2_flag_error(int* errflag, int code, int64_t c
     if (atomicCAS(&errflag[0], 0, code) == 0) errflag[1] = (int)cell;
 }
 
+__device__ __forceinline__ void fb2_cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
 template <bool ATOMIC>
 __device__ __forceinline__ void fb2_add(double* p, double v) {
     if (ATOMIC) atomicAdd(p, v);  // result unused -> RED.E.ADD.F64
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
             for (int k = 0; k < NF; ++k) fe[TF[k]] = 0.0;
         }
     }
+    bool next_takes_x = false;
     if (MERGE) {   // ---- x-merge through warp shuffles ----
         const unsigned full = 0xffffffffu;
         const int lane = threadIdx.x & 31;
@@ -332,6 +338,7 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
         match = match & prev_active & active;
         const bool nm = __shfl_down_sync(full, (int)match, 1) != 0;
         const bool next_takes = nm & (lane < 31);   // the next lane consumes my right-face block
+        next_takes_x = next_takes;
 #pragma unroll
         for (int q = 0; q < NF; ++q)
 #pragma unroll
@@ -387,8 +394,10 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
                     if (off == 0xFFFFu) missing = true;
                     else fb2_add<ATOMIC>(A.nzval + bj + off, v);
                 }
-            } else {       // complete map: adding an exact zero has no effect, no branches needed
-                fb2_add<ATOMIC>(A.nzval + bj + off, v);
+            } else {       // complete map: straight-line code; only the blocks handed to the x-neighbour are skipped
+                const bool iR = (i & 1) != ((i >> 1) & 1);
+                const bool jR = odd ? ((jo & 1) != ((jo >> 1) & 1)) : ((j & 1) != ((j >> 1) & 1));
+                if (!(MERGE && iR && jR && next_takes_x)) fb2_add<ATOMIC>(A.nzval + bj + off, v);
             }
         }
     }
@@ -398,6 +407,163 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
             if (!MERGE || fe[i] != 0.0) fb2_add<ATOMIC>(A.f + dof[i], fscale * fe[i]);
     }
     if (missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_cell_scalar_ws: warp-specialised version of k_cell_scalar for Q1 quadrilaterals / hexahedra (atomic mode).
+//
+// k_cell_scalar needs 216 registers per thread for the element integration, i.e. two warps per scheduler, and every
+// warp alternates between an FP64-bound phase (integration) and an L2-bound phase (scatter): the FP64 pipe idles while
+// both warps of a scheduler scatter (52 % pipe utilisation, profiles/r01_prof_c2_r1h.txt).  Here a CTA has two warp
+// groups with their own register budgets (setmaxnreg): the COMPUTE group (216 registers) gathers and integrates batches
+// of 128 cells and parks Ke (upper triangle) + fe in a double-buffered shared-memory stage; the SCATTER group
+// (40 registers) stages the scatter indices of the same cells with cp.async while the batch is integrated, then does
+// the face merge (the x-neighbour's block is read from the stage, no shuffles), the sector-paired REDs and the load
+// vector.  Named barriers FULL[s] / EMPTY[s] hand the stages back and forth.  CTAs are persistent over batches.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fb2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void fb2_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int NB>
+struct WsSmem {
+    static constexpr int NSYM = NB * (NB + 1) / 2, NV = NSYM + NB, NCH = (NB * NB + 7) / 8;
+    static constexpr size_t val = 0;                                              // double [2][NV][128]
+    static constexpr size_t map = val + sizeof(double) * 2 * NV * 128;            // uint4  [NCH][128]
+    static constexpr size_t base = map + sizeof(uint4) * NCH * 128;               // int64  [NB][128]
+    static constexpr size_t total = base + sizeof(int64_t) * NB * 128;
+};
+
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ROLLQ, bool CHECK>
+__global__ void __launch_bounds__(256, 2) k_cell_scalar_ws(const AsmArgs A, const int64_t nbatch) {
+    using SM = WsSmem<NB>;
+    constexpr int NSYM = SM::NSYM, NV = SM::NV, NCH = SM::NCH;
+    constexpr bool MERGE = (DIM == 3 && NB == 8 && NGEO == 8) || (DIM == 2 && NB == 4 && NGEO == 4);
+    constexpr int NF = DIM == 3 ? 4 : 2;
+    constexpr int RF[4] = {1, 2, 5, 6}, LF[4] = {0, 3, 4, 7};   // x = 1 face / x = 0 face; x-mates are j ^ 1
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double* s_val = reinterpret_cast<double*>(smraw + SM::val);
+    uint4* s_map = reinterpret_cast<uint4*>(smraw + SM::map);
+    int64_t* s_base = reinterpret_cast<int64_t*>(smraw + SM::base);
+    const int wg = threadIdx.x >> 7, t = threadIdx.x & 127;
+    const int64_t np = A.ncells_pad;
+    enum { BAR_FULL = 1, BAR_EMPTY = 3 };
+
+    if (wg == 0) {
+        // ================= compute group =================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        const double kscale = A.p[0], fscale = A.p[1];
+        int k = 0;
+        for (int64_t b = blockIdx.x; b < nbatch; b += gridDim.x, ++k) {
+            const int s = k & 1;
+            const int64_t idx = b * 128 + t;
+            const bool active = idx < A.ncount;
+            const int64_t cell = fb2_cell_of(A, active ? idx : A.ncount - 1);
+            double x[NGEO][DIM];
+#pragma unroll
+            for (int j = 0; j < NGEO; ++j) {
+                const int node = __ldg(A.conn + (size_t)j * np + cell);
+                fb2_load_x<DIM>(A.xyz, node, x[j]);
+            }
+            double Ke[NSYM];
+            double fe[NB];
+            const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ>(A, x, Ke, fe);
+            if (bad && active) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
+            const bool drop = bad || !active;   // zeros are skipped by the scatter group
+            if (k >= 2) fb2_bar_sync(BAR_EMPTY + s, 256);     // the scatter group has released this stage
+            double* st = s_val + (size_t)s * NV * 128 + t;
+#pragma unroll
+            for (int e = 0; e < NSYM; ++e) st[e * 128] = drop ? 0.0 : kscale * Ke[e];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) st[(NSYM + i) * 128] = (ELEM == FB2_ELEM_HEAT && !drop) ? fscale * fe[i] : 0.0;
+            fb2_bar_arrive(BAR_FULL + s, 256);
+        }
+    } else {
+        // ================= scatter group =================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int lane = t & 31;
+        const bool odd = MERGE && (t & 1);
+        int k = 0;
+        for (int64_t b = blockIdx.x; b < nbatch; b += gridDim.x, ++k) {
+            const int s = k & 1;
+            const int64_t idx = b * 128 + t;
+            const bool active = idx < A.ncount;
+            const int64_t cell = fb2_cell_of(A, active ? idx : A.ncount - 1);
+            int dof[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) fb2_cp_async16(&s_map[c * 128 + t], A.map8 + (size_t)c * np + cell);
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_base[j * 128 + t]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(A.colptr + dof[j]) : "memory");
+            }
+            // face match with the previous / next lane (dof ids; any mesh ordering qualifies)
+            bool match = false, next_takes = false;
+            if (MERGE) {
+                const unsigned full = 0xffffffffu;
+                match = lane > 0;
+#pragma unroll
+                for (int q = 0; q < NF; ++q) {
+                    const int pd = __shfl_up_sync(full, dof[RF[q]], 1);
+                    match = match & (pd == dof[LF[q]]);
+                }
+                const bool prev_active = __shfl_up_sync(full, (int)active, 1) != 0;
+                match = match & prev_active & active;
+                next_takes = (__shfl_down_sync(full, (int)match, 1) != 0) & (lane < 31);
+            }
+            fb2_bar_sync(BAR_FULL + s, 256);                  // the batch's Ke / fe are in stage s
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const double* st = s_val + (size_t)s * NV * 128 + t;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        // sector pairing: odd lanes walk the columns in the order j ^ 1 (see k_cell_scalar)
+                        const int jo = MERGE ? (j ^ 1) : j;
+                        const int se = i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j;
+                        const int so = i <= jo ? jo * (jo + 1) / 2 + i : i * (i + 1) / 2 + jo;
+                        const int im = i ^ 1, jme = j ^ 1, jmo = jo ^ 1;   // x-mates: the neighbour's local ids of the same nodes
+                        const int sme = im <= jme ? jme * (jme + 1) / 2 + im : im * (im + 1) / 2 + jme;
+                        const int smo = im <= jmo ? jmo * (jmo + 1) / 2 + im : im * (im + 1) / 2 + jmo;
+                        const bool iL = (i & 1) == ((i >> 1) & 1);          // local nodes 0,3,4,7 lie on x = 0
+                        const bool jLe = (j & 1) == ((j >> 1) & 1), jLo = (jo & 1) == ((jo >> 1) & 1);
+                        const bool jL = odd ? jLo : jLe;
+                        double v = st[(odd ? so : se) * 128];
+                        if (MERGE) {
+                            if (iL && jL && match) v += st[(odd ? smo : sme) * 128 - 1];   // left neighbour's x = 1 face block
+                            if (!iL && !jL && next_takes) v = 0.0;                            // the right neighbour adds mine
+                        }
+                        const int e = (odd ? jo : j) * NB + i;
+                        const unsigned off = reinterpret_cast<const uint16_t*>(s_map)[((e >> 3) * 128 + t) * 8 + (e & 7)];
+                        double* dst = A.nzval + s_base[(odd ? jo : j) * 128 + t] + off;
+                        if (CHECK) {   // zero values are skipped; a non-zero aimed at a missing entry is an error
+                            if (v != 0.0) {
+                                if (off == 0xFFFFu) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
+                                else atomicAdd(dst, v);
+                            }
+                        } else {       // complete map: straight-line code, only the blocks handed to the neighbour are skipped
+                            if (!(MERGE && !iL && !jL && next_takes)) atomicAdd(dst, v);
+                        }
+                    }
+                }
+                if (A.f != nullptr && ELEM == FB2_ELEM_HEAT) {
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const bool iL = (i & 1) == ((i >> 1) & 1);
+                        double v = st[(NSYM + i) * 128];
+                        if (MERGE) {
+                            if (iL && match) v += st[(NSYM + (i ^ 1)) * 128 - 1];
+                            if (!iL && next_takes) v = 0.0;
+                        }
+                        if (v != 0.0) atomicAdd(A.f + dof[i], v);
+                    }
+                }
+            }
+            if (b + 2 * (int64_t)gridDim.x < nbatch) fb2_bar_arrive(BAR_EMPTY + s, 256);   // the compute group waits for it at k + 2
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -419,11 +585,6 @@ struct TileArgs {
     int max_ent, max_src;
     int accumulate;  // 1: add onto existing values (fillzero = false)
 };
-
-__device__ __forceinline__ void fb2_cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
-}
 
 template <int DIM, int NGEO, int NB, int NQ, int ELEM, int TC, int MB = 2>
 __global__ void __launch_bounds__(TC, MB) k_tile_scalar(const AsmArgs A, const TileArgs T) {
