@@ -380,6 +380,25 @@ def main():
                "d2h_bytes_per_step": int(sum_over_ranks(float((K.nnz + dh.ndofs) * 8))), "steps": esteps,
                "checksum_ok": bool(abs(float(f_host.sum()) - fsum_dev) <= 1e-9 * max(1.0, abs(fsum_dev)))}
 
+    # ---- the consumer of K: y = K x on the assembled matrix, an HBM-bound gather ------------------------
+    spmv = None
+    if world == 1:
+        xv = torch.ones(K.n, dtype=torch.float64, device=dev)
+        yv = torch.empty_like(xv)
+        fb.spmv(K, xv, transpose=True, out=yv)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(10):
+            fb.spmv(K, xv, transpose=True, out=yv)
+        s1.record()
+        torch.cuda.synchronize()
+        spmv_ms = s0.elapsed_time(s1) / 10
+        spmv_bytes = K.nnz * 12 + K.n * (8 + 8 + 8)       # nzval + rowval, colptr, x once, y
+        spmv = {"ms": spmv_ms, "GB/s": spmv_bytes / spmv_ms / 1e6, "bytes": spmv_bytes,
+                "rowsum_check": float(yv.abs().max()) / float(K.nzval.abs().max()) if cfg["element"] == "heat" else None}
+        del xv, yv
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -417,6 +436,9 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if spmv:
+        spmv["frac_of_hbm_peak"] = spmv["GB/s"] / hbm_peak
+        line["spmv"] = spmv
     if not args.no_cpu_baseline and world == 1:
         sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
         line["cpu_baseline"] = cpu_baseline(cfg, sample)

@@ -122,6 +122,9 @@ _PROTOS = {
     "fb2_facetset_create": [_p, _i64p, C.c_int64, _pp],
     "fb2_facetset_destroy": [_p],
     "fb2_assemble_facets": [_p, _p, _p, C.c_int, _dp, C.c_int, _p],
+    "fb2_spmv": [_p, _p, _p, _p, C.c_int],
+    "fb2_csr_values": [_p, _p, _p],
+    "fb2_cg": [_p, _p, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _ip, _dp],
     "fb2_assembler_create": [_p, _p, _p, _pp],
     "fb2_assemble": [_p, C.c_int, _p, C.c_size_t, _p, _p, _p, C.POINTER(AsmOpts)],
     "fb2_assemble_host": [_p, C.c_int, _p, C.c_size_t, _dp, _dp, _dp, C.POINTER(AsmOpts)],

@@ -636,6 +636,32 @@ def apply_zero_(K, f=None, ch=None):
     return apply_(K, f, ch, applyzero=True)
 
 
+# ---- the step after the path: SpMV / CSR values / CG on the device -------------------------------------------------
+def spmv(K, x, transpose=False, out=None):
+    """y = K x (or K' x) with K's values where the assembly left them (CUDA tensors in, CUDA tensor out)."""
+    y = out if out is not None else K.dh.grid.ctx.zeros(K.n)
+    L.call("fb2_spmv", K.h, C.c_void_p(K.nzval.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), 1 if transpose else 0)
+    return y
+
+
+def csr_values(K):
+    """nzval of K in CSR order; with rowptr = K.colptr and colval = K.rowval (structurally symmetric patterns)."""
+    out = K.dh.grid.ctx.zeros(K.nnz)
+    L.call("fb2_csr_values", K.h, C.c_void_p(K.nzval.data_ptr()), C.c_void_p(out.data_ptr()))
+    return out
+
+
+def cg_(x, K, b, reltol=None, abstol=0.0, maxiter=None, jacobi=False, symmetric=True):
+    """IterativeSolvers.cg!(x, K, b; reltol = sqrt(eps), abstol = 0, maxiter = n) on the device.
+    Returns (iterations, final residual norm); x is updated in place."""
+    reltol = float(np.sqrt(np.finfo(np.float64).eps)) if reltol is None else float(reltol)
+    maxiter = K.n if maxiter is None else int(maxiter)
+    it, rn = C.c_int(), C.c_double()
+    L.call("fb2_cg", K.h, C.c_void_p(K.nzval.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()),
+           reltol, float(abstol), maxiter, 1 if jacobi else 0, 1 if symmetric else 0, C.byref(it), C.byref(rn))
+    return it.value, rn.value
+
+
 # ---- partitioned multi-GPU assembly (no counterpart in the reference) ---------------------------------------------
 class Partition:
     """Rank `rank` of `nparts` of a global DofHandler: own + halo cells as a local problem, column ownership and

@@ -136,6 +136,11 @@ struct fb2_pattern {
     int64_t* d_diag = nullptr;     // [n] position of the diagonal entry, -1 if absent
     bool structurally_symmetric = false;
     int max_col_len = 0;
+    // solver support (solver.cu, lazy): position of the transposed entry (j,i) for every stored (i,j); -1 if absent
+    int64_t* d_tperm = nullptr;
+    int tperm_state = 0;           // 0 not built, 1 built and complete (structurally symmetric), 2 built with gaps
+    double* d_work = nullptr;      // CG work vectors
+    size_t work_count = 0;
 };
 
 struct fb2_cv {

@@ -407,6 +407,8 @@ extern "C" int fb2_pattern_destroy(fb2_pattern* p) {
     cudaFree(p->d_colptr);
     cudaFree(p->d_rowval);
     cudaFree(p->d_diag);
+    cudaFree(p->d_tperm);
+    cudaFree(p->d_work);
     delete p;
     return FB2_OK;
 }

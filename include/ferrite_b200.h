@@ -241,6 +241,22 @@ enum { FB2_FACET_FLUX = 1,            /* scalar field: fe[i] += q N_i dGamma; pa
  * assemble!(f, celldofs(cell), fe) (src/assembler.jl:338-345).  Adds onto f_dev (no zero fill). */
 int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int kind, const double* params, int nparams, double* f_dev);
 
+/* ---- the step after the path: CSR view, SpMV, conjugate gradients on the device ---------------- */
+/* y = K x (transpose = 0) or y = K^T x (transpose = 1) with K = (pattern, nzval_dev) in CSC.  Both are gathers with a
+ * fixed summation order (K x goes through the transpose permutation of a structurally symmetric pattern; other
+ * patterns fall back to a column scatter with FP64 atomics).  x_dev and y_dev must not alias. */
+int fb2_spmv(fb2_pattern* p, const double* nzval_dev, const double* x_dev, double* y_dev, int transpose);
+/* CSR values of a structurally symmetric pattern (every pattern of allocate_matrix is): with rowptr = colptr and
+ * colval = rowval, nzval_csr[k] = K[row(k), colval[k]].  Counterpart of assembling into SparseMatrixCSR,
+ * ext/FerriteSparseMatrixCSR.jl:9-95. */
+int fb2_csr_values(fb2_pattern* p, const double* nzval_csc_dev, double* nzval_csr_dev);
+/* x_dev holds the initial guess and receives the solution of K x = b.  Stops when ||r|| <= max(reltol ||r0||, abstol)
+ * or after maxiter iterations (the stopping rule of IterativeSolvers.cg!, hyperelasticity.jl:418).  jacobi != 0:
+ * diagonal preconditioner.  symmetric != 0: K is symmetric in value and K^T p is used for K p (cheapest).
+ * iters / resnorm (nullable) receive the iteration count and the final residual norm. */
+int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_dev, double* x_dev, double reltol, double abstol,
+           int maxiter, int jacobi, int symmetric, int* iters, double* resnorm);
+
 /* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
 typedef struct fb2_part fb2_part;
 enum { FB2_DIST_EXCHANGE = 0, /* assemble own cells, exchange interface columns over NCCL */

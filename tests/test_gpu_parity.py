@@ -581,3 +581,113 @@ def test_hyperelasticity_tutorial_golden_through_the_gpu_path(ctx):
         raise AssertionError("Newton did not converge")
     ref = 4.761404305083876
     assert abs(float(u.norm()) - ref) / ref < 1e-7, float(u.norm())
+
+
+# ---- the step after the path: SpMV, CSR values, CG on the device ------------------------------------
+@pytest.mark.parametrize("ct,nel,order,vdim", [
+    (fb.Hexahedron, (6, 5, 4), 1, 1), (fb.Hexahedron, (3, 3, 2), 2, 3), (fb.Tetrahedron, (3, 3, 3), 2, 1),
+    (fb.Quadrilateral, (9, 7), 2, 2), (fb.Triangle, (8, 8), 1, 1), (fb.Hexahedron, (4, 4, 4), 1, 3),
+])
+def test_spmv_and_csr_values_match_scipy(ctx, ct, nel, order, vdim):
+    import torch
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, 2)
+    K = fb.allocate_matrix(dh)
+    rng = np.random.default_rng(5)
+    K.nzval.copy_(torch.from_numpy(rng.standard_normal(K.nnz)))     # non-symmetric values on the symmetric pattern
+    x = torch.from_numpy(rng.standard_normal(K.n)).to(K.nzval.device)
+    A = K.tocsc()
+    y = fb.spmv(K, x).cpu().numpy()
+    yt = fb.spmv(K, x, transpose=True).cpu().numpy()
+    xr = x.cpu().numpy()
+    assert close(y, A @ xr, 1e-13)[0]
+    assert close(yt, A.T @ xr, 1e-13)[0]
+    csr = A.tocsr()
+    csr.sort_indices()
+    assert np.array_equal(csr.indptr, K.colptr - 1) and np.array_equal(csr.indices, K.rowval - 1)   # rowptr = colptr, colval = rowval
+    assert np.array_equal(fb.csr_values(K).cpu().numpy(), csr.data)
+
+
+def test_spmv_on_a_non_symmetric_pattern(ctx):
+    import torch
+    g = fb.generate_grid(fb.Line, (4,))
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefLine, 1)))
+    n = dh.ndofs
+    # upper bidiagonal pattern: entries (j-1, j) and (j, j)
+    colptr = np.concatenate([[1], 1 + np.cumsum([1] + [2] * (n - 1))])
+    rowval = np.concatenate([[1]] + [[j, j + 1] for j in range(1, n)])
+    K = fb.allocate_matrix(dh, colptr, rowval)
+    K.nzval.copy_(torch.arange(1.0, K.nnz + 1, dtype=torch.float64))
+    x = torch.arange(1.0, n + 1, dtype=torch.float64, device=K.nzval.device)
+    A = K.tocsc()
+    assert close(fb.spmv(K, x).cpu().numpy(), A @ x.cpu().numpy(), 1e-14)[0]
+    assert close(fb.spmv(K, x, transpose=True).cpu().numpy(), A.T @ x.cpu().numpy(), 1e-14)[0]
+    with pytest.raises(fb.FB2Error):
+        fb.csr_values(K)
+
+
+def test_cg_solves_the_heat_tutorial(ctx):
+    # heat_equation.jl:59-114,181-234 with the linear solve on the device: norm(u) == 3.307743912641305
+    g = fb.generate_grid(fb.Quadrilateral, (20, 20))
+    ip = fb.Lagrange(fb.RefQuadrilateral, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip)
+    ch = fb.ConstraintHandler(dh)
+    boundary = np.concatenate([fb.getfacetset(g, k) for k in ("left", "right", "top", "bottom")])
+    fb.add_(ch, fb.Dirichlet("u", boundary, lambda x, t: 0))
+    fb.close_(ch)
+    fb.assemble_(fb.start_assemble(K, f), fb.HeatElement(), cv)
+    fb.apply_(K, f, ch)
+    for jacobi in (False, True):
+        u = ctx.zeros(dh.ndofs)
+        it, rn = fb.cg_(u, K, f, reltol=1e-13, jacobi=jacobi)
+        assert 0 < it < dh.ndofs and rn <= 1e-13 * float(f.norm()) * 1.01
+        ref = 3.307743912641305
+        assert abs(float(u.norm()) - ref) / ref < 1e-11
+    uref = spla.spsolve(K.tocsc(), f.cpu().numpy())
+    assert close(u.cpu().numpy(), uref, 1e-10)[0]
+
+
+def test_hyperelasticity_newton_cg_entirely_on_the_device(ctx):
+    # hyperelasticity.jl:393-431: assemble, apply_zero!, cg!(ddu, K, g; maxiter = 1000), all on the device
+    N, Lx = 10, 1.0
+    g = fb.generate_grid(fb.Tetrahedron, (N, N, N), (0.0, 0.0, 0.0), (Lx, Lx, Lx))
+    ip = fb.Lagrange(fb.RefTetrahedron, 1) ** 3
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefTetrahedron, 1), ip)
+    fv = fb.FacetValues(fb.FacetQuadratureRule(fb.RefTetrahedron, 1), ip)
+    th = np.pi / 3
+
+    def rotation(x, t):
+        return t * np.array([0.0, Lx / 2 - x[1] + (x[1] - Lx / 2) * np.cos(th) - (x[2] - Lx / 2) * np.sin(th),
+                             Lx / 2 - x[2] + (x[1] - Lx / 2) * np.sin(th) + (x[2] - Lx / 2) * np.cos(th)])
+
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "right"), lambda x, t: [0.0, 0.0, 0.0], [1, 2, 3]))
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), rotation, [1, 2, 3]))
+    fb.close_(ch)
+    fb.update_(ch, 0.5)
+    gamma_n = fb.FacetSet(g, np.concatenate([fb.getfacetset(g, k) for k in ("top", "bottom", "front", "back")]))
+    E, nu = 10.0, 0.3
+    elem = fb.NeoHookeElement(lam=E * nu / ((1 + nu) * (1 - 2 * nu)), mu=E / (2 * (1 + nu)), b=(0.0, -0.5, 0.0))
+    K = fb.allocate_matrix(dh)
+    res = ctx.zeros(dh.ndofs)
+    un = ctx.zeros(dh.ndofs)
+    fb.apply_(un, ch)
+    du = ctx.zeros(dh.ndofs)
+    for it in range(31):
+        u = un + du
+        fb.assemble_(fb.start_assemble(K, res), elem, cv, u=u)
+        fb.assemble_facets_(res, dh, fv, gamma_n, "normal_traction", -0.1)
+        fb.apply_zero_(K, res, ch)
+        if float(res.norm()) < 1e-8:
+            break
+        ddu = ctx.zeros(dh.ndofs)
+        fb.cg_(ddu, K, res, maxiter=1000)          # the tutorial's call: reltol = sqrt(eps)
+        fb.apply_(ddu, ch, applyzero=True)
+        du -= ddu
+    else:
+        raise AssertionError("Newton did not converge")
+    ref = 4.761404305083876
+    assert abs(float(u.norm()) - ref) / ref < 1e-7, float(u.norm())
