@@ -8,6 +8,7 @@
 // rowval); y = K x uses the transpose permutation (CSR values of a structurally symmetric pattern are
 // csc[perm[k]] with rowptr = colptr, colval = rowval), also a gather: no atomics, deterministic summation order.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -48,6 +49,7 @@ __global__ void k_spmv_gather(const int64_t* __restrict__ colptr, const int32_t*
     double s = 0.0;
     if (col < n) {
         const int64_t k1 = colptr[col + 1];
+#pragma unroll 4
         for (int64_t k = colptr[col] + sub; k < k1; k += TPC) {
             const double v = USE_PERM ? nzval[perm[k]] : nzval[k];
             s = fma(v, x[rowval[k]], s);
@@ -204,11 +206,14 @@ int launch_gather(fb2_pattern* p, const double* nzval, const double* x, double* 
     fb2_ctx* ctx = p->dh->grid->ctx;
     const int64_t n = p->n;
     if (n == 0) return FB2_OK;
-    const double avg = (double)p->nnz / (double)n;
-    if (avg <= 6) k_spmv_gather<2, USE_PERM><<<nblk(n * 2, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
-    else if (avg <= 12) k_spmv_gather<4, USE_PERM><<<nblk(n * 4, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
-    else if (avg <= 40) k_spmv_gather<8, USE_PERM><<<nblk(n * 8, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
-    else if (avg <= 100) k_spmv_gather<16, USE_PERM><<<nblk(n * 16, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
+    double avg = (double)p->nnz / (double)n;
+    // threads per column ~ column length / 12: few threads with four unrolled, independent (rowval -> x) load chains each
+    // measured best on B200 (Q1 hex, 27 entries per column: 2 threads 5.46 TB/s, 4: 5.32, 8: 3.6-4.1, 16: 2.7, 32: 1.7)
+    if (const char* e = getenv("FB2_SPMV_TPC")) avg = atoi(e) == 2 ? 1 : atoi(e) == 4 ? 40 : atoi(e) == 8 ? 80 : atoi(e) == 16 ? 200 : 1000;   // tuning override
+    if (avg <= 36) k_spmv_gather<2, USE_PERM><<<nblk(n * 2, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
+    else if (avg <= 72) k_spmv_gather<4, USE_PERM><<<nblk(n * 4, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
+    else if (avg <= 144) k_spmv_gather<8, USE_PERM><<<nblk(n * 8, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
+    else if (avg <= 288) k_spmv_gather<16, USE_PERM><<<nblk(n * 16, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
     else k_spmv_gather<32, USE_PERM><<<nblk(n * 32, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, p->d_tperm, nzval, x, y, n);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
