@@ -65,6 +65,10 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, 
             k<<<g2, 256, smem, ctx->stream>>>(A, nbatch);
         }
     }
+    // variant 9: node coordinates in shared memory instead of 48 registers, 3 CTAs per SM (168 registers, 120 B of
+    // spills).  C2: 2.34 ms vs 2.30 ms -- 50 % more resident warps buy nothing, so the kernel is not bound by per-warp
+    // latency but by the FP64 pipe and the L2 atomic path taking turns (4 CTAs at 128 registers: 4.7 ms, spills).
+    else if (atomic && variant == 9) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 3, ROLL, true, true, true><<<grid, bs, 0, ctx->stream>>>(A);
     // variant 7: without the lane-parity sector pairing of the scatter (A/B measurement)
     else if (atomic && variant == 7) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, false><<<grid, bs, 0, ctx->stream>>>(A);
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);

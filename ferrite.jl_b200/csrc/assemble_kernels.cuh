@@ -129,9 +129,11 @@ __device__ __forceinline__ double fb2_det_inv(const double (&J)[DIM][DIM], doubl
 // Element integration shared by the thread-per-cell kernels: per quadrature point J = sum_j x_j (x) dM_j/dxi, det > 0,
 // dOmega = det*w, dNdx = dNdxi . inv(J); upper triangle of Ke (packed: (i,j), i <= j at j(j+1)/2 + i) and fe in registers.
 // Returns true if some det(J) was not positive.
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ROLLQ = false>
+// xs != nullptr: the coordinates are read from shared memory (xs[(j * DIM + a) * 128], the thread's own column) at
+// every quadrature point instead of living in 2 * NGEO * DIM registers.
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ROLLQ = false, bool XSMEM = false>
 __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const double (&x)[NGEO][DIM],
-                                                   double (&Ke)[NB * (NB + 1) / 2], double (&fe)[NB]) {
+                                                   double (&Ke)[NB * (NB + 1) / 2], double (&fe)[NB], const double* xs = nullptr) {
     constexpr int NSYM = NB * (NB + 1) / 2;
 #pragma unroll
     for (int i = 0; i < NSYM; ++i) Ke[i] = 0.0;
@@ -157,7 +159,7 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 #pragma unroll
             for (int a = 0; a < DIM; ++a)
 #pragma unroll
-                for (int b = 0; b < DIM; ++b) J[a][b] = fma(x[j][a], tdM[(q * NGEO + j) * DIM + b], J[a][b]);
+                for (int b = 0; b < DIM; ++b) J[a][b] = fma(XSMEM ? xs[(j * DIM + a) * 128] : x[j][a], tdM[(q * NGEO + j) * DIM + b], J[a][b]);
         double Ji[DIM][DIM];
         double det = fb2_det_inv<DIM>(J, Ji);
         bad |= !(det > 0.0);
@@ -203,7 +205,7 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 // k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true, bool PAIRX = true>
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true, bool PAIRX = true, bool XSMEM = false>
 __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     // lanes past the end stay alive (they redo a valid cell and write nothing): the face merges below shuffle across
     // the whole warp and synchronise the CTA
@@ -229,8 +231,15 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) dof[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
     double x[NGEO][DIM];
+    __shared__ double s_x[XSMEM ? NGEO * DIM : 1][128];
 #pragma unroll
-    for (int j = 0; j < NGEO; ++j) fb2_load_x<DIM>(A.xyz, node[j], x[j]);
+    for (int j = 0; j < NGEO; ++j) {
+        fb2_load_x<DIM>(A.xyz, node[j], x[j]);
+        if (XSMEM) {
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) s_x[j * DIM + a][threadIdx.x] = x[j][a];
+        }
+    }
     // Stage the scatter indices (packed uint16 offsets, column bases) into shared memory with cp.async now;
     // they land while the quadrature loop runs.  Plain loads placed here are sunk by ptxas next to the
     // REDs (one exposed memory round trip per 8 entries, profiles/r1 notes); cp.async cannot be sunk.
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     constexpr int NSYM = NB * (NB + 1) / 2;
     double Ke[NSYM];
     double fe[NB];
-    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ>(A, x, Ke, fe);
+    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ, XSMEM>(A, x, Ke, fe, &s_x[0][threadIdx.x]);
     asm volatile("cp.async.wait_all;" ::: "memory");
     if (bad && active) {
         fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
@@ -269,10 +278,11 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     constexpr int RF[4] = {1, 2, 5, 6}, LF[4] = {0, 3, 4, 7};   // right face of the left cell <-> left face of this cell
     constexpr int TF[4] = {3, 2, 7, 6}, BF[4] = {0, 1, 4, 5};   // top face of the lower cell  <-> bottom face of this cell
     constexpr int NPAIR = NF * (NF + 1) / 2;
-    if (MERGE && A.wfirst != nullptr) {   // ---- y-merge through shared memory (uniform branch) ----
-        __shared__ double s_T[NPAIR + NF][128];
-        __shared__ int s_Tdof[NF][128];
-        __shared__ unsigned char s_act[128], s_taken[128];
+    if (MERGE && !XSMEM && A.wfirst != nullptr) {   // ---- y-merge through shared memory (uniform branch) ----
+        constexpr int YW = XSMEM ? 1 : 128;             // (no static shared memory for it in the XSMEM instantiations)
+        __shared__ double s_T[NPAIR + NF][YW];
+        __shared__ int s_Tdof[NF][YW];
+        __shared__ unsigned char s_act[YW], s_taken[YW];
         const int t = threadIdx.x;
         {
             int pi = 0;
