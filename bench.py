@@ -367,11 +367,15 @@ def main():
         a_h._h = a._h
         esteps = max(2, min(args.steps, 5))
 
+        xyz_np = xyz_host.numpy()
+
         def e2e_step():
-            g.upload_coordinates_async(xyz_host)              # H2D: this step's input
             if part is None:
-                fb.assemble_host(a_h, elem, cv, nz_np, f_np)  # assemble + D2H of nzval and f (synchronises)
+                # H2D of this step's coordinates, assembly and D2H of nzval + f, pipelined over 8 slabs of cells
+                # (synchronises before returning)
+                fb.assemble_host_streamed(a_h, elem, cv, nz_np, f_np, xyz=xyz_np)
             else:
+                g.upload_coordinates_async(xyz_host)          # H2D: this step's input
                 step(a_h)
                 nz_host.copy_(K.nzval, non_blocking=True)     # D2H of this rank's owned columns / dofs
                 f_host.copy_(f, non_blocking=True)

@@ -128,6 +128,7 @@ _PROTOS = {
     "fb2_assembler_create": [_p, _p, _p, _pp],
     "fb2_assemble": [_p, C.c_int, _p, C.c_size_t, _p, _p, _p, C.POINTER(AsmOpts)],
     "fb2_assemble_host": [_p, C.c_int, _p, C.c_size_t, _dp, _dp, _dp, C.POINTER(AsmOpts)],
+    "fb2_assemble_host_streamed": [_p, C.c_int, _p, C.c_size_t, _dp, _dp, _dp, _dp, C.POINTER(AsmOpts)],
     "fb2_assembler_coloring": [_p, _ip, _i32p],
     "fb2_scatter_host": [_p, _dp, _dp, _p, _p, C.POINTER(AsmOpts)],
     "fb2_assembler_destroy": [_p],

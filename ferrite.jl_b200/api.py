@@ -521,6 +521,16 @@ def assemble_host(assembler, element, cv, nzval, f=None, u=None):
            _ptr(f, C.c_double) if f is not None else None, C.byref(opts))
 
 
+def assemble_host_streamed(assembler, element, cv, nzval, f=None, u=None, xyz=None):
+    """assemble_host with the copies pipelined against the assembly (slabs of cells): xyz (nnodes, sdim) host coordinates
+    of this step (optional), nzval / f host outputs.  Pinned buffers let the copies overlap."""
+    h = assembler._handle(cv)
+    opts = assembler._opts()
+    L.call("fb2_assemble_host_streamed", h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
+           _ptr(xyz, C.c_double) if xyz is not None else None, _ptr(u, C.c_double) if u is not None else None,
+           _ptr(nzval, C.c_double), _ptr(f, C.c_double) if f is not None else None, C.byref(opts))
+
+
 def scatter_(assembler, Ke, fe=None):
     """assemble!(assembler, dofs, Ke, fe) for all cells at once from precomputed element matrices:
     Ke (ncells, n, n) with Ke[c, i, j], fe (ncells, n)."""

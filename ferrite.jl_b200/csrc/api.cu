@@ -3,6 +3,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "common.h"
 
 static thread_local char g_err[1024] = "";
@@ -64,6 +66,9 @@ extern "C" int fb2_ctx_destroy(fb2_ctx* ctx) {
     fb2_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->ev_ready) for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     cudaFree(ctx->d_errflag);
     cudaFreeHost(ctx->h_errflag);
     delete ctx;
@@ -278,6 +283,130 @@ extern "C" int fb2_assemble_host(fb2_assembler* a, int element, const void* para
     FB2_TRY(fb2_launch_assemble(a, element, params, params_bytes, u_host ? a->d_u : nullptr, a->d_nzval, f_host ? a->d_f : nullptr, &o));
     FB2_CUDA(cudaMemcpyAsync(nzval_host, a->d_nzval, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (f_host) FB2_CUDA(cudaMemcpyAsync(f_host, a->d_f, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return fb2_check_device_error(ctx);
+}
+
+// Streamed variant of fb2_assemble_host: the cells are cut into slabs (contiguous ranges in cell order); the
+// coordinates a slab needs are uploaded while the previous slab is assembled, and the matrix columns no later slab
+// touches are downloaded while the following slabs are assembled.  With the reference's cell / dof numbering (both
+// follow the grid sweep) every slab completes a contiguous block of columns; for an arbitrary numbering the schedule
+// degenerates to upload-all / assemble / download-all, which is still correct.
+__global__ void k_repack_xyz_range(const double* __restrict__ src, int64_t node0, int64_t node1, int sdim, int xstride, double* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + node0 * xstride;
+    if (t >= node1 * xstride) return;
+    const int64_t node = t / xstride;
+    const int d = (int)(t - node * xstride);
+    dst[t] = d < sdim ? src[node * sdim + d] : 0.0;
+}
+
+static int build_slab_schedule(fb2_assembler* a, int nslabs) {
+    if (!a->slab_cell.empty()) return FB2_OK;
+    fb2_dh* dh = a->dh;
+    fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    const int64_t nc = g->ncells;
+    const int nnpc = g->nnpc, ndpc = dh->ndpc;
+    std::vector<int64_t> cell(nslabs + 1), node(nslabs + 1, 0), col(nslabs + 1, 0);
+    for (int k = 0; k <= nslabs; ++k) cell[k] = std::min<int64_t>(nc, ((nc * k / nslabs) + 127) / 128 * 128);
+    cell[nslabs] = nc;
+    // nodes needed by slabs <= k: 1 + the largest node id touched so far
+    int64_t mx = 0;
+    for (int k = 0; k < nslabs; ++k) {
+        for (int64_t c = cell[k]; c < cell[k + 1]; ++c)
+            for (int j = 0; j < nnpc; ++j) mx = std::max<int64_t>(mx, g->cells[(size_t)c * nnpc + j]);   // 1-based = count
+        node[k + 1] = mx;
+    }
+    node[nslabs] = g->nnodes;
+    // columns complete after slab k: every column below the smallest dof touched by a later slab
+    int64_t mn = dh->ndofs;
+    col[nslabs] = dh->ndofs;
+    for (int k = nslabs - 1; k >= 1; --k) {
+        for (int64_t c = cell[k]; c < cell[k + 1]; ++c)
+            for (int i = 0; i < ndpc; ++i) mn = std::min<int64_t>(mn, dh->cell_dofs[(size_t)c * ndpc + i]);
+        col[k] = mn;
+    }
+    col[0] = 0;
+    std::vector<int64_t> pos(nslabs + 1);
+    for (int k = 0; k <= nslabs; ++k)
+        FB2_CUDA(cudaMemcpyAsync(&pos[k], a->pat->d_colptr + col[k], sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    a->slab_cell = cell; a->slab_node = node; a->slab_col = col; a->slab_pos = pos;
+    return FB2_OK;
+}
+
+extern "C" int fb2_assemble_host_streamed(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* xyz_host,
+                                          const double* u_host, double* nzval_host, double* f_host, const fb2_asm_opts* opts) {
+    FB2_CHECK(a && nzval_host, FB2_ERR_BAD_ARG, "fb2_assemble_host_streamed: null argument");
+    FB2_CHECK(a->cv, FB2_ERR_BAD_ARG, "fb2_assemble_host_streamed: this assembler was created without CellValues (scatter-only)");
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+    if (opts) o = *opts;
+    FB2_CHECK(o.fillzero && o.scatter_mode == FB2_SCATTER_ATOMIC && a->d_cells == nullptr && a->ncells_active == 0, FB2_ERR_UNSUPPORTED,
+              "fb2_assemble_host_streamed: needs fillzero, the atomic scatter and an unpartitioned assembler");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    int NS = 8;
+    if (const char* e = getenv("FB2_HOST_SLABS")) NS = std::max(1, std::min(20, atoi(e)));   // tuning override
+    if ((int)a->slab_cell.size() != NS + 1) a->slab_cell.clear();
+    const size_t nnz = (size_t)a->pat->nnz, n = (size_t)a->dh->ndofs;
+    if (!a->d_nzval) FB2_CUDA(cudaMalloc(&a->d_nzval, nnz * sizeof(double)));
+    if (!a->d_f) FB2_CUDA(cudaMalloc(&a->d_f, n * sizeof(double)));
+    if (!ctx->h2d_stream) FB2_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) FB2_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_ready) {
+        for (cudaEvent_t& e : ctx->ev_pool) FB2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_ready = true;
+    }
+    FB2_TRY(build_slab_schedule(a, NS));
+    cudaStream_t sm = ctx->stream, sh = ctx->h2d_stream, sd = ctx->d2h_stream;
+    cudaEvent_t* ev = ctx->ev_pool;   // [0] start, [1..NS] uploads, [NS+1..2NS] kernels, [2NS+1] downloads done
+    FB2_CUDA(cudaEventRecord(ev[0], sm));
+    FB2_CUDA(cudaStreamWaitEvent(sh, ev[0], 0));
+    FB2_CUDA(cudaStreamWaitEvent(sd, ev[0], 0));
+    if (u_host) {
+        if (!a->d_u) FB2_CUDA(cudaMalloc(&a->d_u, n * sizeof(double)));
+        FB2_CUDA(cudaMemcpyAsync(a->d_u, u_host, n * sizeof(double), cudaMemcpyHostToDevice, sm));
+    }
+    FB2_CUDA(cudaMemsetAsync(a->d_nzval, 0, nnz * sizeof(double), sm));
+    if (f_host) FB2_CUDA(cudaMemsetAsync(a->d_f, 0, n * sizeof(double), sm));
+    ctx->launches += f_host ? 2 : 1;
+    if (xyz_host) {
+        const size_t tot = (size_t)g->nnodes * g->sdim;
+        if (!g->d_xyz_stage) FB2_CUDA(cudaMalloc(&g->d_xyz_stage, tot * sizeof(double)));
+        for (int k = 0; k < NS; ++k) {
+            const int64_t n0 = a->slab_node[k], n1 = a->slab_node[k + 1];
+            if (n1 > n0) {
+                FB2_CUDA(cudaMemcpyAsync(g->d_xyz_stage + n0 * g->sdim, xyz_host + n0 * g->sdim, (size_t)(n1 - n0) * g->sdim * sizeof(double),
+                                         cudaMemcpyHostToDevice, sh));
+                const int64_t cnt = (n1 - n0) * g->xstride;
+                k_repack_xyz_range<<<(unsigned)((cnt + 255) / 256), 256, 0, sh>>>(g->d_xyz_stage, n0, n1, g->sdim, g->xstride, g->d_xyz);
+                ctx->launches++;
+            }
+            FB2_CUDA(cudaEventRecord(ev[1 + k], sh));
+        }
+    }
+    o.fillzero = 0;
+    int rc = FB2_OK;
+    for (int k = 0; k < NS && rc == FB2_OK; ++k) {
+        if (xyz_host) FB2_CUDA(cudaStreamWaitEvent(sm, ev[1 + k], 0));
+        a->cell_first = a->slab_cell[k];
+        a->ncells_active = a->slab_cell[k + 1] - a->slab_cell[k];
+        if (a->ncells_active > 0)
+            rc = fb2_launch_assemble(a, element, params, params_bytes, u_host ? a->d_u : nullptr, a->d_nzval, f_host ? a->d_f : nullptr, &o);
+        if (rc != FB2_OK) break;
+        FB2_CUDA(cudaEventRecord(ev[1 + NS + k], sm));
+        FB2_CUDA(cudaStreamWaitEvent(sd, ev[1 + NS + k], 0));
+        const int64_t p0 = a->slab_pos[k], p1 = a->slab_pos[k + 1], c0 = a->slab_col[k], c1 = a->slab_col[k + 1];
+        if (p1 > p0) FB2_CUDA(cudaMemcpyAsync(nzval_host + p0, a->d_nzval + p0, (size_t)(p1 - p0) * sizeof(double), cudaMemcpyDeviceToHost, sd));
+        if (f_host && c1 > c0) FB2_CUDA(cudaMemcpyAsync(f_host + c0, a->d_f + c0, (size_t)(c1 - c0) * sizeof(double), cudaMemcpyDeviceToHost, sd));
+    }
+    a->cell_first = 0;
+    a->ncells_active = 0;
+    cudaEventRecord(ev[2 * NS + 1], sd);
+    cudaStreamWaitEvent(sm, ev[2 * NS + 1], 0);
+    cudaStreamWaitEvent(sm, ev[NS], 0);   // (uploads that no slab waited for)
+    FB2_TRY(rc);
     return fb2_check_device_error(ctx);
 }
 

@@ -90,6 +90,10 @@ struct fb2_ctx {
     const void* const_tables_owner = nullptr;  // fb2_cv whose tables are currently in __constant__ memory
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // copy streams + events of the streamed host-buffer entry point (lazy)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_pool[64] = {};
+    bool ev_ready = false;
 };
 
 struct fb2_grid {
@@ -198,6 +202,8 @@ struct fb2_assembler {
     int32_t* d_cells = nullptr;
     int64_t cell_first = 0;
     int64_t ncells_active = 0;
+    // slab schedule of the streamed host-buffer entry point (lazy): cell range, nodes needed so far, columns complete
+    std::vector<int64_t> slab_cell, slab_node, slab_col, slab_pos;
     // scratch for the host-buffer entry point
     double* d_nzval = nullptr;
     double* d_f = nullptr;

@@ -182,6 +182,12 @@ int fb2_assemble(fb2_assembler* a, int element, const void* params, size_t param
  * downloads nzval/f into the caller's SparseMatrixCSC.nzval / f vectors */
 int fb2_assemble_host(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_host,
                       double* nzval_host, double* f_host, const fb2_asm_opts* opts);
+/* Same result, pipelined: cells are assembled in slabs; the node coordinates (xyz_host, sdim x nnodes like
+ * Vector{Vec}, nullable = keep the coordinates on the device) of the next slab go up and the matrix columns
+ * completed by the previous slabs come down while a slab is assembled.  Needs fillzero and the atomic scatter.
+ * Host buffers should be pinned (cudaHostRegister / CUDA.pin) for the copies to overlap. */
+int fb2_assemble_host_streamed(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* xyz_host,
+                               const double* u_host, double* nzval_host, double* f_host, const fb2_asm_opts* opts);
 /* create_coloring(grid): number of colours and, optionally, the colour of every cell (0-based colour ids) */
 int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color);
 /* scatter-only entry: assemble!(assembler, dofs, Ke, fe) for a batch of precomputed element matrices

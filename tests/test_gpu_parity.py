@@ -691,3 +691,30 @@ def test_hyperelasticity_newton_cg_entirely_on_the_device(ctx):
         raise AssertionError("Newton did not converge")
     ref = 4.761404305083876
     assert abs(float(u.norm()) - ref) / ref < 1e-7, float(u.norm())
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,kind", [
+    (fb.Hexahedron, (13, 11, 9), 1, 1, "heat"), (fb.Hexahedron, (5, 4, 6), 1, 3, "elasticity"),
+    (fb.Quadrilateral, (40, 33), 2, 1, "heat"), (fb.Tetrahedron, (4, 4, 5), 2, 3, "neohooke"),
+])
+def test_streamed_host_path_matches_plain_host_path(ctx, ct, nel, order, vdim, kind):
+    # fb2_assemble_host_streamed (slabs of cells, pipelined copies) == fb2_assemble_host, also after moving the nodes
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, 2 if order == 1 else 3)
+    lam, mu = O.lame(10.0, 0.3)
+    elem = {"heat": fb.HeatElement(1.3, 0.7), "elasticity": fb.ElasticityElement(lam=lam, mu=mu, b=(0.1, 0.2, -1.0)),
+            "neohooke": fb.NeoHookeElement(lam=lam, mu=mu, b=(0.0, -0.5, 0.0))}[kind]
+    K = fb.allocate_matrix(dh)
+    u = 0.01 * np.sin(np.arange(dh.ndofs, dtype=np.float64)) if kind == "neohooke" else None
+    nz1, f1 = np.empty(K.nnz), np.empty(dh.ndofs)
+    nz2, f2 = np.full(K.nnz, np.nan), np.full(dh.ndofs, np.nan)
+    a = fb.start_assemble(K, None)
+    fb.assemble_host(a, elem, cv, nz1, f1, u=u)
+    fb.assemble_host_streamed(a, elem, cv, nz2, f2, u=u)
+    assert np.array_equal(np.isnan(nz2), np.zeros(K.nnz, bool))
+    assert close(nz2, nz1, 1e-13)[0] and close(f2, f1, 1e-13)[0]
+    # new coordinates travel with the call
+    xyz = np.ascontiguousarray(g.nodes * 1.25)
+    fb.assemble_host_streamed(a, elem, cv, nz2, f2, u=u, xyz=xyz)
+    g.upload_coordinates_async(xyz)
+    fb.assemble_host(a, elem, cv, nz1, f1, u=u)
+    assert close(nz2, nz1, 1e-13)[0] and close(f2, f1, 1e-13)[0]
