@@ -204,6 +204,9 @@ struct fb2_assembler {
     int64_t ncells_active = 0;
     // slab schedule of the streamed host-buffer entry point (lazy): cell range, nodes needed so far, columns complete
     std::vector<int64_t> slab_cell, slab_node, slab_col, slab_pos;
+    // zero-fill schedule of the device path (lazy): cell ranges and the nzval prefix each range needs zeroed
+    std::vector<int64_t> zf_cell, zf_pos;
+    int zf_state = 0;   // 0 not built, 1 usable, 2 not worthwhile (numbering does not follow the cell order)
     // scratch for the host-buffer entry point
     double* d_nzval = nullptr;
     double* d_f = nullptr;

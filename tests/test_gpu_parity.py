@@ -163,7 +163,7 @@ def test_assembly_matches_oracle(ctx, case, scatter):
         ou = displacement(og, odh, vdim)
         u = torch.from_numpy(ou).to(f.device)
     O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
-    variants = [0, 1, 2, 5, 6, 7, 8, 9] if kind in ("heat", "mass") else [0]   # 0 per-cell kernel (x face merge), 1 block kernel, 2 unrolled, 5 tile kernel, 6 x+y face merge
+    variants = [0, 1, 2, 5, 6, 7, 8, 9, 12] if kind in ("heat", "mass") else [0]   # 0 per-cell kernel (x face merge), 1 block kernel, 2 unrolled, 5 tile kernel, 6 x+y face merge
     for variant in variants:
         a = fb.start_assemble(K, f, scatter=scatter)
         a.variant = variant
