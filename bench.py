@@ -38,6 +38,9 @@ CONFIGS = {
                label="linear elasticity Q1^3 hex 128^3 (per-GPU block of BASELINE.json configs[4])"),
     "c3": dict(cell="hex", nel=(48, 48, 48), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
                label="linear elasticity Q2^3 hex 48^3 (BASELINE.json configs[2] at 1/8 size)"),
+    "c4": dict(cell="tet", nel=(48, 48, 48), order=2, vdim=3, qr=4, element="neohooke", bmin=7.0e3, fmin=0.25e6,
+               label="Neo-Hooke tangent + residual, P2^3 tetrahedra, generate_grid(Tetrahedron, 48^3) = 663552 cells "
+                     "(BASELINE.json configs[3]); bytes/flops per cell are estimates (30x30 Ke, 11-point rule)"),
     "c3full": dict(cell="hex", nel=(96, 96, 96), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
                    label="linear elasticity Q2^3 hex 96^3 (BASELINE.json configs[2], full size: nnz = 4.09e9 > 2^32)"),
 }
@@ -230,12 +233,19 @@ def main():
     # ---- set-up (not timed): grid, dofs, pattern, map all resident in HBM ------------------------------
     t_setup = time.perf_counter()
     nel = cfg["nel"]
-    ip = fb.Lagrange(fb.RefHexahedron, cfg["order"]) ** cfg["vdim"]
-    cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, cfg["qr"]), ip)
-    elem = fb.HeatElement(1.0, 1.0) if cfg["element"] == "heat" else fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+    ct = fb.Tetrahedron if cfg["cell"] == "tet" else fb.Hexahedron
+    ip = fb.Lagrange(ct, cfg["order"]) ** cfg["vdim"]
+    cv = fb.CellValues(fb.QuadratureRule(ct, cfg["qr"]), ip)
+    if cfg["element"] == "heat":
+        elem = fb.HeatElement(1.0, 1.0)
+    elif cfg["element"] == "elasticity":
+        elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+    else:
+        elem = fb.NeoHookeElement(E=10.0, nu=0.3, b=(0.0, -0.5, 0.0))      # hyperelasticity.jl:334-338
+    u_state = None
     part = None
     if world == 1:
-        g = fb.generate_grid(fb.Hexahedron, nel).perturb(0.2)
+        g = fb.generate_grid(ct, nel).perturb(0.2)
         dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
         ncells_total, volume = g.ncells, 8.0
     else:
@@ -251,6 +261,9 @@ def main():
         ncells_total, volume = gg.ncells, 8.0 * world
     K = fb.allocate_matrix(dh)
     f = ctx.zeros(dh.ndofs)
+    if cfg["element"] == "neohooke":
+        # a deterministic small displacement state (|grad u| ~ 0.03, det F > 0); the work per cell does not depend on it
+        u_state = (1e-3 * torch.sin(0.37 * torch.arange(dh.ndofs, dtype=torch.float64))).to(dev)
     a = fb.start_assemble(K, f, scatter=args.scatter)
     a.variant = args.variant
     if part is not None:
@@ -262,7 +275,7 @@ def main():
 
     def step(asm):
         if part is None:
-            fb.assemble_(asm, elem, cv)
+            fb.assemble_(asm, elem, cv, u=u_state)
         else:
             part._asm = asm
             part.assemble_(elem, mode=args.dist_mode)
@@ -324,6 +337,23 @@ def main():
         checks["K_times_translation_rel"] = float(yv.abs().max()) / float(K.nzval.abs().max())
         checks["sum_fz_plus_volume"] = abs(float(f[2::3].sum()) + volume)
         del tvec, yv
+    apply_info = None
+    if cfg["element"] == "elasticity" and world == 1:
+        # BASELINE.json configs[2] "... with Dirichlet apply!": u = 0 on "left", a smooth non-zero field on "right"
+        ch = fb.ConstraintHandler(dh)
+        fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: [0.0, 0.0, 0.0], [1, 2, 3]))
+        fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "right"), lambda x, t: [0.0, 0.0, 0.01 * x[1]], [1, 2, 3]))
+        fb.close_(ch)
+        fb.update_(ch, 0.0)
+        ctx.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        fb.apply_(K, f, ch)
+        a1.record()
+        torch.cuda.synchronize()
+        apply_info = {"ms": a0.elapsed_time(a1), "prescribed_dofs": int(len(ch.prescribed_dofs))}
+        step(a)            # restore the unconstrained K, f for the remaining measurements
+        ctx.synchronize()
     if part is not None:
         # the exchange path and the communication-free halo path must give the same owned columns
         ref_nz, ref_f = K.nzval.clone(), f.clone()
@@ -341,12 +371,12 @@ def main():
     a_nz.variant = args.variant
     a_nz._h = a._h          # reuse the same native assembler (map)
     kreps = max(3, min(args.steps, 10))
-    fb.assemble_(a_nz, elem, cv)
+    fb.assemble_(a_nz, elem, cv, u=u_state)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(kreps):
-        fb.assemble_(a_nz, elem, cv)
+        fb.assemble_(a_nz, elem, cv, u=u_state)
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps
@@ -368,12 +398,13 @@ def main():
         esteps = max(2, min(args.steps, 5))
 
         xyz_np = xyz_host.numpy()
+        u_np = u_state.cpu().numpy() if u_state is not None else None
 
         def e2e_step():
             if part is None:
                 # H2D of this step's coordinates, assembly and D2H of nzval + f, pipelined over 8 slabs of cells
                 # (synchronises before returning)
-                fb.assemble_host_streamed(a_h, elem, cv, nz_np, f_np, xyz=xyz_np)
+                fb.assemble_host_streamed(a_h, elem, cv, nz_np, f_np, xyz=xyz_np, u=u_np)
             else:
                 g.upload_coordinates_async(xyz_host)          # H2D: this step's input
                 step(a_h)
@@ -450,6 +481,8 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+    if apply_info:
+        line["apply"] = apply_info
     if spmv:
         spmv["frac_of_hbm_peak"] = spmv["GB/s"] / hbm_peak
         line["spmv"] = spmv

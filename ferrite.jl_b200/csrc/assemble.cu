@@ -98,7 +98,7 @@ int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     }
     const BlockSmem L = fb2_blocks_smem<DIM, NBS, VDIM, ELEM>(A.nq, cells);
     FB2_CHECK(L.total <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory per cell", L.total);
-    const int bs = std::min(256, (per_cell * cells + 31) / 32 * 32);
+    const int bs = std::min(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, (per_cell * cells + 31) / 32 * 32);
     const unsigned grid = (unsigned)((A.ncount + cells - 1) / cells);
     if (atomic) {
         auto k = k_cell_blocks<DIM, NGEO, NBS, VDIM, ELEM, true>;
@@ -441,7 +441,7 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     // kernel down by more than the 0.25 ms they hide, and four launches have four tails.
     constexpr int ZS = 4;
     const bool whole_grid = a->d_cells == nullptr && a->ncells_active == 0;
-    if (o.fillzero && o.scatter_mode == FB2_SCATTER_ATOMIC && whole_grid && g->ncells >= (1 << 20) && o.variant == 12 && a->zf_state != 2) {
+    if (o.fillzero && o.scatter_mode == FB2_SCATTER_ATOMIC && whole_grid && g->ncells >= 1024 && o.variant == 12 && a->zf_state != 2) {
         if (a->zf_state == 0) {
             const int64_t nc = g->ncells;
             const int ndpc = dh->ndpc;

@@ -727,8 +727,10 @@ __host__ __device__ inline BlockSmem fb2_blocks_smem(int nq, int cells) {
     return L;
 }
 
+// Neo-Hooke keeps 27 + TB * 9 doubles live in phase B: under a 128-register cap it spills (the C4 profile showed 3.1 G L2
+// sectors of local-memory traffic, long-scoreboard stalls on every DFMA), so it runs with at most 192 threads per CTA = a cap of 168 registers.
 template <int DIM, int NGEO, int NBS, int VDIM, int ELEM, bool ATOMIC>
-__global__ void __launch_bounds__(256, 2) k_cell_blocks(const AsmArgs A, const int CELLS) {
+__global__ void __launch_bounds__(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, 2) k_cell_blocks(const AsmArgs A, const int CELLS) {
     extern __shared__ __align__(16) unsigned char smraw[];
     constexpr int TB = TileOf<NBS, VDIM>::TB;
     constexpr int NT = (NBS + TB - 1) / TB;
