@@ -1001,7 +1001,11 @@ __global__ void __launch_bounds__(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, 2) k_ce
 #pragma unroll
                 for (int d = 0; d < VDIM; ++d) {
                     const int jl = (b0 + t) * VDIM + d;
-                    const int64_t base = bcell[jl];
+                    const int64_t base = *reinterpret_cast<const volatile int64_t*>(&bcell[jl]);
+                    // volatile: read before the zero tests instead of one exposed shared-memory round trip per RED
+                    unsigned offs[VDIM];
+#pragma unroll
+                    for (int c = 0; c < VDIM; ++c) offs[c] = *reinterpret_cast<const volatile uint16_t*>(&mcell[jl * N + a * VDIM + c]);
 #pragma unroll
                     for (int c = 0; c < VDIM; ++c) {
                         double v;
@@ -1010,7 +1014,7 @@ __global__ void __launch_bounds__(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, 2) k_ce
                         if (TRANSPOSE) {
                             s_K[(size_t)cl * N * N + jl * N + a * VDIM + c] = v;
                         } else {
-                            const unsigned off = mcell[jl * N + a * VDIM + c];
+                            const unsigned off = offs[c];
                             if (v != 0.0) {
                                 if (off == 0xFFFFu) missing = true;
                                 else fb2_add<ATOMIC>(A.nzval + base + off, v);
@@ -1259,22 +1263,29 @@ __global__ void __launch_bounds__(SyrkOf<NBS, DIM>::NTHR) k_cell_syrk(const AsmA
     if (grp < NGRP) {
         const double lam = A.p[0], mu = A.p[1];
         const int a = il / DIM, c = il - a * DIM;
-        bool missing = false;
+        int missing = 0;
         for (int b = grp; b < NBS; b += NGRP) {
             const double* Gb = s_G + (b * DIM) * NG;       // rows (b, 0..DIM-1)
+            // the offsets and column bases of the DIM entries are read up front through volatile pointers: left to the
+            // compiler they sink behind the zero test of each value, one exposed shared-memory round trip per RED
+            unsigned offs[DIM];
+            int64_t bases[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                offs[d] = *reinterpret_cast<const volatile uint16_t*>(&s_map[(b * DIM + d) * N + il]);
+                bases[d] = *reinterpret_cast<const volatile int64_t*>(&s_base[b * DIM + d]);
+            }
             double tr = 0.0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) tr += Gb[k * NG + a * DIM + k];
             const double* Gbc = Gb + c * NG + a * DIM;     // G[(b,c)][(a,.)]
 #pragma unroll
             for (int d = 0; d < DIM; ++d) {
-                const int jl = b * DIM + d;
                 double v = lam * Gb[d * NG + il] + mu * Gbc[d];
                 if (c == d) v = fma(mu, tr, v);
-                const unsigned off = s_map[jl * N + il];
                 if (v != 0.0) {
-                    if (off == 0xFFFFu) missing = true;
-                    else fb2_add<ATOMIC>(A.nzval + s_base[jl] + off, v);
+                    if (offs[d] == 0xFFFFu) missing = 1;
+                    else fb2_add<ATOMIC>(A.nzval + bases[d] + offs[d], v);
                 }
             }
         }
