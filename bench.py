@@ -328,7 +328,7 @@ def main():
     checks = {}
     if cfg["element"] == "heat":
         checks["sum_f_minus_volume"] = abs(sum_over_ranks(float(f.sum())) - volume)
-        checks["sum_K"] = abs(sum_over_ranks(float(K.nzval.sum()))) / max_over_ranks(float(K.nzval.abs().max()))
+        checks["sum_K"] = abs(sum_over_ranks(float(K.nzval.sum()))) / max(max_over_ranks(float(K.nzval.abs().max())), 1e-300)
     if cfg["element"] == "elasticity" and world == 1:
         # rigid-body translation is in the null space of K (K symmetric: K't = Kt), and sum(f_z) = -|Omega| for b = (0,0,-1)
         tvec = torch.zeros(K.n, dtype=torch.float64, device=dev)

@@ -69,6 +69,13 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, 
     // spills).  C2: 2.34 ms vs 2.30 ms -- 50 % more resident warps buy nothing, so the kernel is not bound by per-warp
     // latency but by the FP64 pipe and the L2 atomic path taking turns (4 CTAs at 128 registers: 4.7 ms, spills).
     else if (atomic && variant == 9) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 3, ROLL, true, true, true><<<grid, bs, 0, ctx->stream>>>(A);
+    // variants 20 / 21 (measurement only, results are wrong): integration without scatter / scatter without integration
+    else if (atomic && (variant == 20 || variant == 21) && DIM == 3 && NB == 8 && NGEO == 8 && ELEM == FB2_ELEM_HEAT) {
+        if constexpr (DIM == 3 && NB == 8 && NGEO == 8 && ELEM == FB2_ELEM_HEAT) {
+            if (variant == 20) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, true, false, 1><<<grid, bs, 0, ctx->stream>>>(A);
+            else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, true, false, 2><<<grid, bs, 0, ctx->stream>>>(A);
+        }
+    }
     // variant 7: without the lane-parity sector pairing of the scatter (A/B measurement)
     else if (atomic && variant == 7) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL, true, false><<<grid, bs, 0, ctx->stream>>>(A);
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);

@@ -205,7 +205,8 @@ __device__ __forceinline__ bool fb2_scalar_element(const AsmArgs& A, const doubl
 // ------------------------------------------------------------------------------------------------
 // k_cell_scalar: thread per cell, scalar field.  ELEM: FB2_ELEM_HEAT or FB2_ELEM_MASS.
 // ------------------------------------------------------------------------------------------------
-template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true, bool PAIRX = true, bool XSMEM = false>
+// DEBUGMODE (measurement only, wrong results): 1 = integrate but never scatter, 2 = scatter without integrating
+template <int DIM, int NGEO, int NB, int NQ, int ELEM, bool ATOMIC, int MB = 1, bool ROLLQ = false, bool CHECK = true, bool PAIRX = true, bool XSMEM = false, int DEBUGMODE = 0>
 __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     // lanes past the end stay alive (they redo a valid cell and write nothing): the face merges below shuffle across
     // the whole warp and synchronise the CTA
@@ -259,7 +260,16 @@ __global__ void __launch_bounds__(128, MB) k_cell_scalar(const AsmArgs A) {
     constexpr int NSYM = NB * (NB + 1) / 2;
     double Ke[NSYM];
     double fe[NB];
-    const bool bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ, XSMEM>(A, x, Ke, fe, &s_x[0][threadIdx.x]);
+    bool bad = false;
+    if (DEBUGMODE == 2) {
+#pragma unroll
+        for (int e = 0; e < NSYM; ++e) Ke[e] = x[e % NGEO][0] + (double)e;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) fe[i] = x[i % NGEO][DIM - 1];
+    } else {
+        bad = fb2_scalar_element<DIM, NGEO, NB, NQ, ELEM, ROLLQ, XSMEM>(A, x, Ke, fe, &s_x[0][threadIdx.x]);
+    }
+    if (DEBUGMODE == 1 && !(Ke[0] == 123.456)) active = false;   // never true: the integration stays, the scatter goes
     asm volatile("cp.async.wait_all;" ::: "memory");
     if (bad && active) {
         fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
