@@ -370,7 +370,6 @@ extern "C" int fb2_assemble_host_streamed(fb2_assembler* a, int element, const v
     }
     FB2_CUDA(cudaMemsetAsync(a->d_nzval, 0, nnz * sizeof(double), sm));
     if (f_host) FB2_CUDA(cudaMemsetAsync(a->d_f, 0, n * sizeof(double), sm));
-    ctx->launches += f_host ? 2 : 1;
     if (xyz_host) {
         const size_t tot = (size_t)g->nnodes * g->sdim;
         if (!g->d_xyz_stage) FB2_CUDA(cudaMalloc(&g->d_xyz_stage, tot * sizeof(double)));

@@ -486,7 +486,6 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
                 if (p1 > p0) FB2_CUDA(cudaMemsetAsync(nzval_dev + p0, 0, (size_t)(p1 - p0) * sizeof(double), aux));
                 FB2_CUDA(cudaEventRecord(ev[1 + k], aux));
             }
-            ctx->launches += (f_dev ? 1 : 0) + ZS;
             A.cells = nullptr;
             int rc = FB2_OK;
             for (int k = 0; k < ZS && rc == FB2_OK; ++k) {
@@ -501,7 +500,6 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     if (o.fillzero) {
         FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
         if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)dh->ndofs * sizeof(double), ctx->stream));
-        ctx->launches += f_dev ? 2 : 1;
     }
     if (o.scatter_mode == FB2_SCATTER_COLORED) {
         FB2_CHECK(a->d_cells == nullptr && a->ncells_active == 0, FB2_ERR_UNSUPPORTED, "coloured scatter on a partitioned assembler is not supported");

@@ -234,7 +234,7 @@ extern "C" int fb2_spmv(fb2_pattern* p, const double* nzval_dev, const double* x
     // not structurally symmetric: column scatter with FP64 atomics
     FB2_CUDA(cudaMemsetAsync(y_dev, 0, (size_t)p->n * sizeof(double), ctx->stream));
     if (p->n > 0) k_spmv_scatter<<<nblk(p->n * 32, 256), 256, 0, ctx->stream>>>(p->d_colptr, p->d_rowval, nzval_dev, x_dev, y_dev, p->n);
-    ctx->launches += 2;
+    ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;
 }
