@@ -74,7 +74,11 @@ typedef struct { double lambda; double mu; double b[3]; } fb2_elasticity_params;
 typedef struct {
     int fillzero;     /* start_assemble(K, f; fillzero) src/assembler.jl:287-291 */
     int scatter_mode; /* FB2_SCATTER_* */
-    int variant;      /* 0 = default kernel for the element; >0 selects an alternative implementation (benchmarks) */
+    int variant;      /* 0 = default kernel for the element.  >0 = measured alternatives, all parity-tested:
+                         1 DFMA block kernel, 2 unrolled quadrature loop, 4 branch-free scatter, 5 tile kernel,
+                         6 x+y face merge, 7 no sector pairing, 8 warp-specialised groups, 9 coordinates in shared
+                         memory, 12 zero fill overlapped with the assembly; 20 / 21 are measurement-only (wrong results):
+                         integration without scatter / scatter without integration */
     int reserved;
 } fb2_asm_opts;
 
