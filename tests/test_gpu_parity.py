@@ -718,3 +718,46 @@ def test_streamed_host_path_matches_plain_host_path(ctx, ct, nel, order, vdim, k
     g.upload_coordinates_async(xyz)
     fb.assemble_host(a, elem, cv, nz1, f1, u=u)
     assert close(nz2, nz1, 1e-13)[0] and close(f2, f1, 1e-13)[0]
+
+
+# ---- property test: random small problems on the device against the oracle ------------------------------------------
+from hypothesis import HealthCheck, given, settings, strategies as hst  # noqa: E402
+
+
+@hst.composite
+def _random_case(draw):
+    ct = draw(hst.sampled_from([fb.Triangle, fb.Quadrilateral, fb.Tetrahedron, fb.Hexahedron]))
+    dim = 2 if ct in (fb.Triangle, fb.Quadrilateral) else 3
+    nel = tuple(draw(hst.integers(1, 5 if dim == 3 else 9)) for _ in range(dim))
+    order = draw(hst.integers(1, 2))
+    kind = draw(hst.sampled_from(["heat", "mass", "elasticity"] + (["neohooke"] if dim == 3 else [])))
+    vdim = 1 if kind in ("heat", "mass") else dim
+    qo = draw(hst.integers(max(1, order), 3 if ct == fb.Triangle else 4)) if kind != "neohooke" else 2
+    scatter = draw(hst.sampled_from(["atomic", "colored"]))
+    return ct, nel, order, vdim, qo, kind, scatter
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(_random_case())
+def test_random_small_problems_match_oracle(ctx, case):
+    import torch
+    ct, nel, order, vdim, qo, kind, scatter = case
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    p = {"heat": {"k": 1.7, "source": 0.3}, "mass": {"rho": 2.5}}.get(kind, {"E": 10.0, "nu": 0.3, "b": (0.1, -0.5, 0.2)[:3]})
+    elem, op = make_element(kind, p)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    u = ou = None
+    if kind == "neohooke":
+        ou = 0.2 * displacement(og, odh, vdim)
+        u = torch.from_numpy(ou).to(f.device)
+    fb.assemble_(fb.start_assemble(K, f, scatter=scatter), elem, cv, u=u)
+    ctx.synchronize()
+    O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
+    ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+    assert ok, (case, nrm)
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, (case, nrm)

@@ -1,0 +1,71 @@
+"""Property tests (hypothesis) of the host logic through the C ABI, CPU only: random cell types, sizes and field
+combinations must give the oracle's dof numbering bit for bit, every dof must be owned exactly once by a partition, and
+the exchange lists of two ranks must mirror each other."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import ferrite_b200 as fb
+import oracle as O
+
+SHAPE = {fb.Line: "line", fb.Triangle: "triangle", fb.Quadrilateral: "quadrilateral",
+         fb.Tetrahedron: "tetrahedron", fb.Hexahedron: "hexahedron"}
+DIM = {fb.Line: 1, fb.Triangle: 2, fb.Quadrilateral: 2, fb.Tetrahedron: 3, fb.Hexahedron: 3}
+HCTX = fb.Context(-1)
+
+celltypes = st.sampled_from([fb.Line, fb.Triangle, fb.Quadrilateral, fb.Tetrahedron, fb.Hexahedron])
+field = st.tuples(st.integers(1, 2), st.integers(1, 3))          # (order, vdim)
+
+
+@st.composite
+def problems(draw, max_fields=3):
+    ct = draw(celltypes)
+    nel = tuple(draw(st.integers(1, 4 if DIM[ct] == 3 else 6)) for _ in range(DIM[ct]))
+    fields = draw(st.lists(field, min_size=1, max_size=max_fields))
+    return ct, nel, fields
+
+
+def build(ct, nel, fields):
+    g = fb.generate_grid(ct, nel, ctx=HCTX)
+    dh = fb.DofHandler(g)
+    og = O.generate_grid(SHAPE[ct], nel)
+    odh = O.DofHandler(og)
+    for k, (order, vdim) in enumerate(fields):
+        fb.add_(dh, f"f{k}", fb.Lagrange(ct, order) ** vdim)
+        oip = O.Lagrange(SHAPE[ct], order)
+        odh.add(f"f{k}", oip ** vdim if vdim > 1 else oip)
+    return g, fb.close_(dh), og, odh.close()
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(problems())
+def test_random_dof_numbering_is_bit_exact(p):
+    ct, nel, fields = p
+    g, dh, og, odh = build(ct, nel, fields)
+    assert np.array_equal(g.cells, og.cells) and np.array_equal(g.nodes, og.nodes)
+    assert dh.ndofs == odh.ndofs
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(problems(max_fields=1), st.integers(2, 5))
+def test_random_partitions_own_every_dof_once_and_mirror_their_lists(p, nparts):
+    ct, nel, fields = p
+    g, dh, og, odh = build(ct, nel, fields)
+    if g.ncells < nparts or ct == fb.Line:
+        return
+    try:
+        parts = [fb.Partition(dh, nparts, r) for r in range(nparts)]
+    except fb.FB2Error:
+        return                      # some rank owns no cells for this tiny grid: reported, not silently wrong
+    owned = np.concatenate([pt.l2g_dof[pt.dof_owner == pt.rank] for pt in parts])
+    assert len(owned) == dh.ndofs == len(np.unique(owned))
+    own_cells = np.concatenate([pt.cells_global[pt.cell_is_own == 1] for pt in parts])
+    assert len(own_cells) == g.ncells == len(np.unique(own_cells))
+    for a in range(nparts):
+        for b in range(nparts):
+            if a == b:
+                continue
+            ns, nfs, _, _ = parts[a].peer_counts(b)
+            _, _, nr, nfr = parts[b].peer_counts(a)
+            assert (ns, nfs) == (nr, nfr)          # what a sends to b is what b expects from a
