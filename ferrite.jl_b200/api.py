@@ -102,7 +102,8 @@ class Context:
         return torch.zeros(int(n), dtype=torch.float64, device=f"cuda:{self.device}")
 
     def __del__(self):
-        _destroy(self, "fb2_ctx_destroy", ())
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_ctx_destroy", ())
 
 
 _default_ctx = {}
@@ -177,7 +178,8 @@ class Grid:
         return self
 
     def __del__(self):
-        _destroy(self, "fb2_grid_destroy", (getattr(self, "ctx", None),))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_grid_destroy", (getattr(self, "ctx", None),))
 
 
 def generate_grid(celltype, nel, left=None, right=None, ctx=None):
@@ -236,7 +238,8 @@ class DofHandler:
         return out
 
     def __del__(self):
-        _destroy(self, "fb2_dh_destroy", _chain(self, "grid"))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_dh_destroy", _chain(self, "grid"))
 
 
 def add_(obj, *args):
@@ -318,7 +321,8 @@ class B200Matrix:
         return sp.csc_matrix((self.nzval.cpu().numpy(), self.rowval - 1, self.colptr - 1), shape=(self.n, self.n))
 
     def __del__(self):
-        _destroy(self, "fb2_pattern_destroy", _chain(self, "dh"))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_pattern_destroy", _chain(self, "dh"))
 
 
 def allocate_matrix(dh, colptr=None, rowval=None):
@@ -364,7 +368,8 @@ class CellValues:
         return dict(N=N, dNdxi=dN, M=M, dMdxi=dM, w=w, points=pts)
 
     def __del__(self):
-        _destroy(self, "fb2_cellvalues_destroy", (getattr(self, "ctx", None),))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_cellvalues_destroy", (getattr(self, "ctx", None),))
 
 
 # ---- FacetValues and the Neumann / traction facet loop ---------------------------------------------------
@@ -396,7 +401,8 @@ class FacetValues:
         return dict(w=w, points=pts, N=N)
 
     def __del__(self):
-        _destroy(self, "fb2_facetvalues_destroy", (getattr(self, "ctx", None),))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_facetvalues_destroy", (getattr(self, "ctx", None),))
 
 
 class FacetSet:
@@ -409,7 +415,8 @@ class FacetSet:
         L.call("fb2_facetset_create", grid.h, _ptr(self.pairs, C.c_int64), self.pairs.shape[0], C.byref(self.h))
 
     def __del__(self):
-        _destroy(self, "fb2_facetset_destroy", (getattr(self, "grid", None),))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_facetset_destroy", (getattr(self, "grid", None),))
 
 
 def assemble_facets_(f, dh, fv, facetset, kind, params):
@@ -613,7 +620,8 @@ class ConstraintHandler:
         return out
 
     def __del__(self):
-        _destroy(self, "fb2_ch_destroy", _chain(self, "dh"))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_ch_destroy", _chain(self, "dh"))
 
 
 def update_(ch, t=0.0):
@@ -759,7 +767,8 @@ class Partition:
         return out + (self.l2g_dof[own], f.cpu().numpy()[own])
 
     def __del__(self):
-        _destroy(self, "fb2_partition_destroy", _chain(self, "gdh"))
+        if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            _destroy(self, "fb2_partition_destroy", _chain(self, "gdh"))
 
 
 def comm_unique_id():
