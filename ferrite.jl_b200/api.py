@@ -372,6 +372,21 @@ class CellValues:
             _destroy(self, "fb2_cellvalues_destroy", (getattr(self, "ctx", None),))
 
 
+def reinit_(cv, grid, cells=None):
+    """reinit!(cv, cell) for a batch of cells (1-based ids; None = all): returns CUDA tensors
+    dNdx (n, nq, nbase, dim) and detJdV (n, nq) -- shape_gradient(cv, q, i) and getdetJdV(cv, q) of every cell."""
+    torch = _torch()
+    n = grid.ncells if cells is None else len(cells)
+    dev = f"cuda:{grid.ctx.device}"
+    dNdx = torch.empty((n, cv.nq, cv.nbase_scalar, cv.rdim), dtype=torch.float64, device=dev)
+    dO = torch.empty((n, cv.nq), dtype=torch.float64, device=dev)
+    ids = None if cells is None else _i64(cells)
+    L.call("fb2_reinit_cells", cv.h, grid.h, _ptr(ids, C.c_int64) if ids is not None else None, n,
+           C.c_void_p(dNdx.data_ptr()), C.c_void_p(dO.data_ptr()))
+    grid.ctx.synchronize()
+    return dNdx, dO
+
+
 # ---- FacetValues and the Neumann / traction facet loop ---------------------------------------------------
 class FacetQuadratureRule:
     """FacetQuadratureRule{refshape}(order) (src/Quadrature/quadrature.jl:205-238)"""

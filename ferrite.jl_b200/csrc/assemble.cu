@@ -21,7 +21,9 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
     A->o_M = A->o_dN + nq * nb * rd;
     A->o_dM = A->o_M + nq * ng;
     const int total = A->o_dM + nq * ng * rd;
-    FB2_CHECK(total <= FB2_TAB_MAX, FB2_ERR_UNSUPPORTED, "CellValues tables need %d doubles of constant memory (max %d)", total, FB2_TAB_MAX);
+    // tables larger than the constant bank (e.g. Q2 hexahedra with a 4x4x4 rule) are served from the global copy alone:
+    // only the thread-per-cell kernels read c_tab, and those shapes are handled by the CTA kernels anyway
+    A->const_ok = total <= FB2_TAB_MAX;
     if (ctx->const_tables_owner != cv || cv->d_tables == nullptr) {
         std::vector<double> h(total);
         memcpy(h.data() + A->o_w, cv->w.data(), sizeof(double) * nq);
@@ -30,9 +32,11 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
         memcpy(h.data() + A->o_M, cv->M.data(), sizeof(double) * nq * ng);
         memcpy(h.data() + A->o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
         // synchronous w.r.t. the host buffer; ordered on the stream w.r.t. earlier kernels
-        FB2_CUDA(cudaMemcpyToSymbolAsync(c_tab, h.data(), sizeof(double) * total, 0, cudaMemcpyHostToDevice, ctx->stream));
-        FB2_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->const_tables_owner = cv;
+        if (A->const_ok) {
+            FB2_CUDA(cudaMemcpyToSymbolAsync(c_tab, h.data(), sizeof(double) * total, 0, cudaMemcpyHostToDevice, ctx->stream));
+            FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+            ctx->const_tables_owner = cv;
+        }
         if (cv->d_tables == nullptr) {   // global copy: the CTA kernels index the tables per lane, which a constant bank serialises
             FB2_CUDA(cudaMalloc(&cv->d_tables, sizeof(double) * total));
             FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), sizeof(double) * total, cudaMemcpyHostToDevice));
@@ -234,6 +238,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
 template <int ELEM>
 bool try_scalar(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate, int celltype, int nb,
                 int nq, int* rc) {
+    if (!A.const_ok) return false;   // the thread-per-cell kernels need the tables in the constant bank
 #define CASE(CT, DIM, NGEO, NB, NQ)                                              \
     if (celltype == CT && nb == NB && nq == NQ) {                                \
         *rc = launch_tiles_or_cells<DIM, NGEO, NB, NQ, ELEM>(a, ctx, A, atomic, variant, accumulate); \

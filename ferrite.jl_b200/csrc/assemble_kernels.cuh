@@ -43,6 +43,7 @@ struct AsmArgs {
     double p[6];  // element parameters
     int nq;
     const double* tab;     // the c_tab contents in global memory (per-lane indexed reads)
+    bool const_ok;         // the tables fit (and are) in c_tab
     // table offsets into c_tab / tab (in doubles)
     int o_w, o_N, o_dN, o_M, o_dM;
 };

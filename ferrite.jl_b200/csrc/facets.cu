@@ -324,3 +324,93 @@ extern "C" int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int ki
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;
 }
+
+// ---- reinit!(cv, cell) as a stand-alone operation (post-processing, user code outside the fused loop) ---------------------
+// src/FEValues/CellValues.jl:122-140: per quadrature point J = sum_j x_j (x) dM_j/dxi, detJ > 0, detJdV = detJ w,
+// dNdx = dNdxi . inv(J).  Thread per (cell, quadrature point); outputs in the reference's array layout:
+// dNdx[cell][q][i][d] (= cv.fun_values.dNdx[i, q] per cell), detJdV[cell][q].
+namespace {
+template <int DIM>
+__global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* __restrict__ xyz, int64_t ncells_pad, int xstride,
+                               const int64_t* __restrict__ cells, int64_t n, const double* __restrict__ tab, int o_w, int o_dN, int o_dM,
+                               int nq, int nb, int ngeo, double* __restrict__ dNdx, double* __restrict__ detJdV, int* errflag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nq) return;
+    const int64_t k = t / nq;
+    const int q = (int)(t - k * nq);
+    const int64_t cell = cells ? cells[k] - 1 : k;
+    double J[DIM][DIM];
+    for (int a = 0; a < DIM; ++a)
+        for (int b = 0; b < DIM; ++b) J[a][b] = 0.0;
+    for (int j = 0; j < ngeo; ++j) {
+        const int node = conn[(size_t)j * ncells_pad + cell];
+        for (int a = 0; a < DIM; ++a)
+            for (int b = 0; b < DIM; ++b) J[a][b] = fma(xyz[(size_t)node * xstride + a], tab[o_dM + (q * ngeo + j) * DIM + b], J[a][b]);
+    }
+    double det, Ji[DIM][DIM];
+    if (DIM == 1) { det = J[0][0]; Ji[0][0] = 1.0 / det; }
+    else if (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double r = 1.0 / det;
+        Ji[0][0] = J[1][1] * r; Ji[0][1 % DIM] = -J[0][1 % DIM] * r; Ji[1 % DIM][0] = -J[1 % DIM][0] * r; Ji[1 % DIM][1 % DIM] = J[0][0] * r;
+    } else {
+        const int X = 0, Y = 1 % DIM, Z = 2 % DIM;
+        const double c00 = J[Y][Y] * J[Z][Z] - J[Y][Z] * J[Z][Y], c01 = J[Y][X] * J[Z][Z] - J[Y][Z] * J[Z][X], c02 = J[Y][X] * J[Z][Y] - J[Y][Y] * J[Z][X];
+        det = J[X][X] * c00 - J[X][Y] * c01 + J[X][Z] * c02;
+        const double r = 1.0 / det;
+        Ji[X][X] = c00 * r;  Ji[X][Y] = -(J[X][Y] * J[Z][Z] - J[X][Z] * J[Z][Y]) * r;  Ji[X][Z] = (J[X][Y] * J[Y][Z] - J[X][Z] * J[Y][Y]) * r;
+        Ji[Y][X] = -c01 * r; Ji[Y][Y] = (J[X][X] * J[Z][Z] - J[X][Z] * J[Z][X]) * r;   Ji[Y][Z] = -(J[X][X] * J[Y][Z] - J[X][Z] * J[Y][X]) * r;
+        Ji[Z][X] = c02 * r;  Ji[Z][Y] = -(J[X][X] * J[Z][Y] - J[X][Y] * J[Z][X]) * r;  Ji[Z][Z] = (J[X][X] * J[Y][Y] - J[X][Y] * J[Y][X]) * r;
+    }
+    if (!(det > 0.0)) {
+        if (atomicCAS(&errflag[0], 0, FB2_ERR_DETJ_NOT_POSITIVE) == 0) errflag[1] = (int)cell;
+        return;
+    }
+    detJdV[t] = det * tab[o_w + q];
+    double* out = dNdx + (size_t)t * nb * DIM;
+    for (int i = 0; i < nb; ++i)
+        for (int b = 0; b < DIM; ++b) {
+            double s = 0.0;
+            for (int a = 0; a < DIM; ++a) s = fma(tab[o_dN + (q * nb + i) * DIM + a], Ji[a][b], s);
+            out[i * DIM + b] = s;
+        }
+}
+}  // namespace
+
+extern "C" int fb2_reinit_cells(fb2_cv* cv, fb2_grid* g, const int64_t* cells, int64_t n, double* dNdx_dev, double* detJdV_dev) {
+    FB2_CHECK(cv && g && dNdx_dev && detJdV_dev && n >= 0, FB2_ERR_BAD_ARG, "fb2_reinit_cells: bad argument");
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(cv->celltype == g->celltype && cv->rdim == g->sdim && cv->ngeo == g->nnpc, FB2_ERR_BAD_ARG, "fb2_reinit_cells: CellValues do not match the grid");
+    if (cells) for (int64_t k = 0; k < n; ++k) FB2_CHECK(cells[k] >= 1 && cells[k] <= g->ncells, FB2_ERR_BAD_ARG, "fb2_reinit_cells: cell %lld out of range", (long long)cells[k]);
+    else FB2_CHECK(n <= g->ncells, FB2_ERR_BAD_ARG, "fb2_reinit_cells: more cells than the grid has");
+    if (n == 0) return FB2_OK;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
+    const int o_w = 0, o_N = nq, o_dN = o_N + nq * nb, o_M = o_dN + nq * nb * rd, o_dM = o_M + nq * ng;
+    if (!cv->d_tables) {
+        std::vector<double> h((size_t)o_dM + (size_t)nq * ng * rd);
+        memcpy(h.data() + o_w, cv->w.data(), sizeof(double) * nq);
+        memcpy(h.data() + o_N, cv->N.data(), sizeof(double) * nq * nb);
+        memcpy(h.data() + o_dN, cv->dN.data(), sizeof(double) * nq * nb * rd);
+        memcpy(h.data() + o_M, cv->M.data(), sizeof(double) * nq * ng);
+        memcpy(h.data() + o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
+        FB2_CUDA(cudaMalloc(&cv->d_tables, h.size() * sizeof(double)));
+        FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        cv->tables_count = h.size();
+    }
+    int64_t* d_cells = nullptr;
+    if (cells) {
+        FB2_CUDA(cudaMalloc(&d_cells, n * sizeof(int64_t)));
+        FB2_CUDA(cudaMemcpyAsync(d_cells, cells, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const unsigned grid = (unsigned)((n * nq + 127) / 128);
+    if (rd == 1) k_reinit_cells<1><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, g->ncells_pad, g->xstride, d_cells, n, cv->d_tables, o_w, o_dN, o_dM, nq, nb, ng, dNdx_dev, detJdV_dev, ctx->d_errflag);
+    else if (rd == 2) k_reinit_cells<2><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, g->ncells_pad, g->xstride, d_cells, n, cv->d_tables, o_w, o_dN, o_dM, nq, nb, ng, dNdx_dev, detJdV_dev, ctx->d_errflag);
+    else k_reinit_cells<3><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, g->ncells_pad, g->xstride, d_cells, n, cv->d_tables, o_w, o_dN, o_dM, nq, nb, ng, dNdx_dev, detJdV_dev, ctx->d_errflag);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (d_cells) { cudaStreamSynchronize(ctx->stream); cudaFree(d_cells); }
+    FB2_CUDA(e);
+    return FB2_OK;
+}

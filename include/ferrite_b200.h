@@ -227,6 +227,11 @@ int fb2_apply(fb2_ch* ch, fb2_pattern* p, double* nzval_dev, double* f_dev, int 
 int fb2_apply_vector(fb2_ch* ch, double* u_dev, int applyzero);
 int fb2_ch_destroy(fb2_ch* ch);
 
+/* reinit!(cv, cell) for a batch of cells outside the fused loop (post-processing): src/FEValues/CellValues.jl:122-140.
+ * cells: n 1-based cell ids (NULL = cells 1..n).  Outputs on the device, the reference's per-cell arrays back to back:
+ * dNdx[cell][q][i][d] (rdim x n x nq per cell, column-major = cv.fun_values.dNdx) and detJdV[cell][q]. */
+int fb2_reinit_cells(fb2_cv* cv, fb2_grid* grid, const int64_t* cells, int64_t n, double* dNdx_dev, double* detJdV_dev);
+
 /* ---- FacetValues and the Neumann / traction facet loop ------------------------ */
 typedef struct fb2_fv fb2_fv;
 typedef struct fb2_fset fb2_fset;

@@ -37,7 +37,7 @@ def build(ct, nel, fields):
     return g, fb.close_(dh), og, odh.close()
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(problems())
 def test_random_dof_numbering_is_bit_exact(p):
     ct, nel, fields = p
@@ -47,7 +47,7 @@ def test_random_dof_numbering_is_bit_exact(p):
     assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(problems(max_fields=1), st.integers(2, 5))
 def test_random_partitions_own_every_dof_once_and_mirror_their_lists(p, nparts):
     ct, nel, fields = p
