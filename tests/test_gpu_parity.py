@@ -5,6 +5,8 @@ relative in FP64 (atomic summation order).  Entry-wise relative error is ill-def
 analytically zero (e.g. edge-adjacent entries of the trilinear Laplacian), so the entry-wise check is
 |a-b| <= RTOL*max(|a|,|b|) + RTOL*max|a| and the norm-wise error is checked as well.
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
@@ -737,7 +739,11 @@ def _random_case(draw):
     return ct, nel, order, vdim, qo, kind, scatter
 
 
-@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+_PROP_N = int(os.environ.get("FB2_PROP_EXAMPLES", "0"))      # > 0: a longer, randomly seeded exploration run
+
+
+@settings(max_examples=_PROP_N or 40, deadline=None, derandomize=_PROP_N == 0,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(_random_case())
 def test_random_small_problems_match_oracle(ctx, case):
     import torch
