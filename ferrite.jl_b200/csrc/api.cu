@@ -423,6 +423,8 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     cudaFree(a->d_map);
     cudaFree(a->d_map8);
     cudaFree(a->d_mapc);
+    cudaFree(a->d_dofc);
+    cudaFree(a->d_basec);
     cudaFree(a->d_wfirst);
     cudaFree(a->d_wcount);
     fb2_tiles_free(a->tiles);

@@ -95,6 +95,8 @@ int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     constexpr int NT = (NBS + TB - 1) / TB;
     FB2_TRY(fb2_map_build_cellmajor(a));
     A.mapc = a->d_mapc;
+    A.dofc = a->d_dofc;
+    A.basec = a->d_basec;
     // cells per CTA: phase-B items (row node x column tile) are looped over 256 threads; take as many cells as fit in
     // ~100 KB of shared memory (two CTAs per SM overlap one CTA's geometry phase / barriers with the other's phase B),
     // preferring a count whose item total fills the last loop iteration
@@ -131,6 +133,8 @@ int launch_syrk(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
     using S = SyrkOf<NBS, DIM>;
     FB2_TRY(fb2_map_build_cellmajor(a));
     A.mapc = a->d_mapc;
+    A.dofc = a->d_dofc;
+    A.basec = a->d_basec;
     const SyrkSmem L = fb2_syrk_smem<NBS, DIM>(A.nq);
     const size_t smem = L.cell * S::CELLS;
     FB2_CHECK(smem <= 227 * 1024, FB2_ERR_UNSUPPORTED, "element needs %zu bytes of shared memory", smem);

@@ -30,6 +30,8 @@ struct AsmArgs {
     const uint16_t* map;
     const uint4* map8;     // packed offsets for k_cell_scalar
     const uint16_t* mapc;  // cell-major offsets for k_cell_blocks: [cell][mapstride], entry jl * n + il
+    const int32_t* dofc;   // cell-major dofs for the CTA kernels: [cell][n]
+    const int64_t* basec;  //   and colptr[dof]: [cell][n]
     const int32_t* cells;  // optional indirection (colour subset)
     int64_t cell_first;    // without a list the launch covers cells [cell_first, cell_first + ncount)
     const int32_t* wfirst; // optional warp list of k_cell_scalar: first cell of every warp (4 consecutive warps = 4 grid rows)
@@ -777,9 +779,8 @@ __global__ void __launch_bounds__(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, 2) k_ce
     for (int i = threadIdx.x; i < ncl * N; i += blockDim.x) {
         const int cl = i / N, jl = i - cl * N;
         const int64_t cell = fb2_cell_of(A, cell0 + cl);
-        const int d = __ldg(A.cell_dofs + (size_t)jl * np + cell);
-        s_dof[i] = d;
-        s_base[i] = __ldg(A.colptr + d);
+        s_dof[i] = __ldg(A.dofc + (size_t)cell * N + jl);   // cell-major: one contiguous run per cell, no dependent gather
+        s_base[i] = __ldg(A.basec + (size_t)cell * N + jl);
     }
 
     // ---- phase A1: per (qp, cell): J, det > 0, J^-1, dOmega ---------------------------------------------------------
@@ -1160,9 +1161,8 @@ __global__ void __launch_bounds__(SyrkOf<NBS, DIM>::NTHR) k_cell_syrk(const AsmA
         for (int i = gt; i < L.mapstride / 8; i += GS) fb2_cp_async16(s_map + i * 8, A.mapc + (size_t)cell * L.mapstride + i * 8);
     }
     for (int i = gt; i < N; i += GS) {
-        const int d = __ldg(A.cell_dofs + (size_t)i * np + cell);
-        s_dof[i] = d;
-        s_base[i] = __ldg(A.colptr + d);
+        s_dof[i] = __ldg(A.dofc + (size_t)cell * N + i);   // cell-major: one contiguous run per cell, no dependent gather
+        s_base[i] = __ldg(A.basec + (size_t)cell * N + i);
     }
     // quadrature rows NQ..NQP-1 are padding of the k dimension: zero.  Padding columns are left
     // uninitialised: they only reach G entries with a row or column >= N, which are never read

@@ -191,6 +191,8 @@ struct fb2_assembler {
     int n = 0;                     // dofs per cell covered by the element (= ndpc)
     uint16_t* d_map = nullptr;     // [n*n][ncells_pad]: offset of row dof_i inside column dof_j, e = j*n + i
     uint16_t* d_mapc = nullptr;    // cell-major copy for k_cell_blocks: [ncells][ceil8(n*n)] (lazy)
+    int32_t* d_dofc = nullptr;     // cell-major dofs for the CTA kernels: [ncells][n] (built with d_mapc)
+    int64_t* d_basec = nullptr;    //   and their column bases colptr[dof]
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     // colouring (lazy)
     int ncolors = 0;

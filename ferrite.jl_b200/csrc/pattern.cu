@@ -171,6 +171,19 @@ __global__ void k_cellmajor_map(const uint16_t* __restrict__ map, int64_t ncells
     mapc[t] = e < nn ? map[(size_t)e * ncells_pad + c] : (uint16_t)0xFFFF;
 }
 
+// cell-major dofs for the CTA kernels: a warp reads the n dofs of its cell as one contiguous run instead of n SoA rows
+// and their column bases colptr[dof], so that the kernels do not chain a gather behind the dof load
+__global__ void k_cellmajor_dofs(const int32_t* __restrict__ cell_dofs, int64_t ncells, int64_t ncells_pad, int n,
+                                 const int64_t* __restrict__ colptr, int32_t* __restrict__ dofc, int64_t* __restrict__ basec) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells * n) return;
+    int64_t c = t / n;
+    int i = (int)(t - c * n);
+    const int d = cell_dofs[(size_t)i * ncells_pad + c];
+    dofc[t] = d;
+    basec[t] = colptr[d];
+}
+
 __global__ void k_to_onebased64(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) out[t] = (int64_t)in[t] + 1;
@@ -437,7 +450,11 @@ int fb2_map_build_cellmajor(fb2_assembler* a) {
     const int64_t total = g->ncells * stride;
     FB2_CUDA(cudaMalloc(&a->d_mapc, total * sizeof(uint16_t)));
     k_cellmajor_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells, g->ncells_pad, nn, stride, a->d_mapc);
-    ctx->launches++;
+    FB2_CUDA(cudaMalloc(&a->d_dofc, (size_t)g->ncells * a->n * sizeof(int32_t)));
+    FB2_CUDA(cudaMalloc(&a->d_basec, (size_t)g->ncells * a->n * sizeof(int64_t)));
+    k_cellmajor_dofs<<<nblocks(g->ncells * a->n, 256), 256, 0, ctx->stream>>>(a->dh->d_cell_dofs, g->ncells, g->ncells_pad, a->n,
+                                                                               a->pat->d_colptr, a->d_dofc, a->d_basec);
+    ctx->launches += 2;
     FB2_CUDA(cudaGetLastError());
     FB2_CUDA(cudaStreamSynchronize(ctx->stream));
     return FB2_OK;
