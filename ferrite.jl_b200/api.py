@@ -387,6 +387,20 @@ def reinit_(cv, grid, cells=None):
     return dNdx, dO
 
 
+def function_values_(cv, dh, u, gradients=True):
+    """function_value(cv, q, ue) and function_gradient(cv, q, ue) at every quadrature point of every cell:
+    CUDA tensors (ncells, nq, vdim) and (ncells, nq, vdim, dim)."""
+    torch = _torch()
+    g = dh.grid
+    dev = f"cuda:{g.ctx.device}"
+    vals = torch.empty((g.ncells, cv.nq, cv.vdim), dtype=torch.float64, device=dev)
+    grads = torch.empty((g.ncells, cv.nq, cv.vdim, cv.rdim), dtype=torch.float64, device=dev) if gradients else None
+    L.call("fb2_function_values", cv.h, dh.h, C.c_void_p(u.data_ptr()), C.c_void_p(vals.data_ptr()),
+           C.c_void_p(grads.data_ptr()) if grads is not None else None)
+    g.ctx.synchronize()
+    return (vals, grads) if gradients else vals
+
+
 # ---- FacetValues and the Neumann / traction facet loop ---------------------------------------------------
 class FacetQuadratureRule:
     """FacetQuadratureRule{refshape}(order) (src/Quadrature/quadrature.jl:205-238)"""

@@ -330,29 +330,25 @@ extern "C" int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int ki
 // dNdx = dNdxi . inv(J).  Thread per (cell, quadrature point); outputs in the reference's array layout:
 // dNdx[cell][q][i][d] (= cv.fun_values.dNdx[i, q] per cell), detJdV[cell][q].
 namespace {
+// J = sum_j x_j (x) dM_j/dxi at quadrature point q of `cell`; returns det(J) and the inverse
 template <int DIM>
-__global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* __restrict__ xyz, int64_t ncells_pad, int xstride,
-                               const int64_t* __restrict__ cells, int64_t n, const double* __restrict__ tab, int o_w, int o_dN, int o_dM,
-                               int nq, int nb, int ngeo, double* __restrict__ dNdx, double* __restrict__ detJdV, int* errflag) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * nq) return;
-    const int64_t k = t / nq;
-    const int q = (int)(t - k * nq);
-    const int64_t cell = cells ? cells[k] - 1 : k;
+__device__ double cell_jacobian_inverse(const int32_t* __restrict__ conn, const double* __restrict__ xyz, int64_t ncells_pad, int xstride,
+                                        int64_t cell, const double* __restrict__ tdM, int q, int ngeo, double (&Ji)[DIM][DIM]) {
     double J[DIM][DIM];
     for (int a = 0; a < DIM; ++a)
         for (int b = 0; b < DIM; ++b) J[a][b] = 0.0;
     for (int j = 0; j < ngeo; ++j) {
         const int node = conn[(size_t)j * ncells_pad + cell];
         for (int a = 0; a < DIM; ++a)
-            for (int b = 0; b < DIM; ++b) J[a][b] = fma(xyz[(size_t)node * xstride + a], tab[o_dM + (q * ngeo + j) * DIM + b], J[a][b]);
+            for (int b = 0; b < DIM; ++b) J[a][b] = fma(xyz[(size_t)node * xstride + a], tdM[(q * ngeo + j) * DIM + b], J[a][b]);
     }
-    double det, Ji[DIM][DIM];
+    double det;
     if (DIM == 1) { det = J[0][0]; Ji[0][0] = 1.0 / det; }
     else if (DIM == 2) {
-        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const int Y = 1 % DIM;
+        det = J[0][0] * J[Y][Y] - J[0][Y] * J[Y][0];
         const double r = 1.0 / det;
-        Ji[0][0] = J[1][1] * r; Ji[0][1 % DIM] = -J[0][1 % DIM] * r; Ji[1 % DIM][0] = -J[1 % DIM][0] * r; Ji[1 % DIM][1 % DIM] = J[0][0] * r;
+        Ji[0][0] = J[Y][Y] * r; Ji[0][Y] = -J[0][Y] * r; Ji[Y][0] = -J[Y][0] * r; Ji[Y][Y] = J[0][0] * r;
     } else {
         const int X = 0, Y = 1 % DIM, Z = 2 % DIM;
         const double c00 = J[Y][Y] * J[Z][Z] - J[Y][Z] * J[Z][Y], c01 = J[Y][X] * J[Z][Z] - J[Y][Z] * J[Z][X], c02 = J[Y][X] * J[Z][Y] - J[Y][Y] * J[Z][X];
@@ -362,6 +358,20 @@ __global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* _
         Ji[Y][X] = -c01 * r; Ji[Y][Y] = (J[X][X] * J[Z][Z] - J[X][Z] * J[Z][X]) * r;   Ji[Y][Z] = -(J[X][X] * J[Y][Z] - J[X][Z] * J[Y][X]) * r;
         Ji[Z][X] = c02 * r;  Ji[Z][Y] = -(J[X][X] * J[Z][Y] - J[X][Y] * J[Z][X]) * r;  Ji[Z][Z] = (J[X][X] * J[Y][Y] - J[X][Y] * J[Y][X]) * r;
     }
+    return det;
+}
+
+template <int DIM>
+__global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* __restrict__ xyz, int64_t ncells_pad, int xstride,
+                               const int64_t* __restrict__ cells, int64_t n, const double* __restrict__ tab, int o_w, int o_dN, int o_dM,
+                               int nq, int nb, int ngeo, double* __restrict__ dNdx, double* __restrict__ detJdV, int* errflag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nq) return;
+    const int64_t k = t / nq;
+    const int q = (int)(t - k * nq);
+    const int64_t cell = cells ? cells[k] - 1 : k;
+    double Ji[DIM][DIM];
+    const double det = cell_jacobian_inverse<DIM>(conn, xyz, ncells_pad, xstride, cell, tab + o_dM, q, ngeo, Ji);
     if (!(det > 0.0)) {
         if (atomicCAS(&errflag[0], 0, FB2_ERR_DETJ_NOT_POSITIVE) == 0) errflag[1] = (int)cell;
         return;
@@ -374,6 +384,46 @@ __global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* _
             for (int a = 0; a < DIM; ++a) s = fma(tab[o_dN + (q * nb + i) * DIM + a], Ji[a][b], s);
             out[i * DIM + b] = s;
         }
+}
+
+// function_value / function_gradient of a dof vector at every quadrature point of every cell
+// (src/FEValues/common_values.jl:177-227): val[c] = sum_a N_a u_(a,c), grad[c][d] = sum_a u_(a,c) dN_a/dx_d
+template <int DIM>
+__global__ void k_function_values(const int32_t* __restrict__ conn, const double* __restrict__ xyz, const int32_t* __restrict__ cell_dofs,
+                                  int64_t ncells_pad, int xstride, int64_t n, const double* __restrict__ tab, int o_N, int o_dN, int o_dM,
+                                  int nq, int nb, int vdim, int ngeo, const double* __restrict__ u, double* __restrict__ vals,
+                                  double* __restrict__ grads, int* errflag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nq) return;
+    const int64_t cell = t / nq;
+    const int q = (int)(t - cell * nq);
+    double Ji[DIM][DIM];
+    const double det = cell_jacobian_inverse<DIM>(conn, xyz, ncells_pad, xstride, cell, tab + o_dM, q, ngeo, Ji);
+    if (!(det > 0.0)) {
+        if (atomicCAS(&errflag[0], 0, FB2_ERR_DETJ_NOT_POSITIVE) == 0) errflag[1] = (int)cell;
+        return;
+    }
+    double v[3] = {0.0, 0.0, 0.0}, gr[3][DIM];
+    for (int c = 0; c < 3; ++c)
+        for (int d = 0; d < DIM; ++d) gr[c][d] = 0.0;
+    for (int a = 0; a < nb; ++a) {
+        double g[DIM];
+        for (int b = 0; b < DIM; ++b) {
+            double s = 0.0;
+            for (int k = 0; k < DIM; ++k) s = fma(tab[o_dN + (q * nb + a) * DIM + k], Ji[k][b], s);
+            g[b] = s;
+        }
+        const double Na = tab[o_N + q * nb + a];
+        for (int c = 0; c < vdim; ++c) {
+            const double uc = u[cell_dofs[(size_t)(a * vdim + c) * ncells_pad + cell]];
+            v[c] = fma(Na, uc, v[c]);
+            for (int d = 0; d < DIM; ++d) gr[c][d] = fma(uc, g[d], gr[c][d]);
+        }
+    }
+    for (int c = 0; c < vdim; ++c) {
+        if (vals) vals[(size_t)t * vdim + c] = v[c];
+        if (grads) for (int d = 0; d < DIM; ++d) grads[((size_t)t * vdim + c) * DIM + d] = gr[c][d];
+    }
 }
 }  // namespace
 
@@ -412,5 +462,42 @@ extern "C" int fb2_reinit_cells(fb2_cv* cv, fb2_grid* g, const int64_t* cells, i
     cudaError_t e = cudaGetLastError();
     if (d_cells) { cudaStreamSynchronize(ctx->stream); cudaFree(d_cells); }
     FB2_CUDA(e);
+    return FB2_OK;
+}
+
+static int ensure_cv_tables(fb2_cv* cv) {
+    if (cv->d_tables) return FB2_OK;
+    const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
+    const int o_N = nq, o_dN = o_N + nq * nb, o_M = o_dN + nq * nb * rd, o_dM = o_M + nq * ng;
+    std::vector<double> h((size_t)o_dM + (size_t)nq * ng * rd);
+    memcpy(h.data(), cv->w.data(), sizeof(double) * nq);
+    memcpy(h.data() + o_N, cv->N.data(), sizeof(double) * nq * nb);
+    memcpy(h.data() + o_dN, cv->dN.data(), sizeof(double) * nq * nb * rd);
+    memcpy(h.data() + o_M, cv->M.data(), sizeof(double) * nq * ng);
+    memcpy(h.data() + o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
+    FB2_CUDA(cudaMalloc(&cv->d_tables, h.size() * sizeof(double)));
+    FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cv->tables_count = h.size();
+    return FB2_OK;
+}
+
+extern "C" int fb2_function_values(fb2_cv* cv, fb2_dh* dh, const double* u_dev, double* values_dev, double* gradients_dev) {
+    FB2_CHECK(cv && dh && u_dev && (values_dev || gradients_dev), FB2_ERR_BAD_ARG, "fb2_function_values: bad argument");
+    fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(cv->celltype == g->celltype && cv->rdim == g->sdim && cv->ngeo == g->nnpc, FB2_ERR_BAD_ARG, "fb2_function_values: CellValues do not match the grid");
+    FB2_CHECK(dh->fields.size() == 1 && dh->ndpc == cv->nb * cv->vdim, FB2_ERR_BAD_ARG, "fb2_function_values: CellValues must cover the (single) field");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_TRY(ensure_cv_tables(cv));
+    const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
+    const int o_N = nq, o_dN = o_N + nq * nb, o_M = o_dN + nq * nb * rd, o_dM = o_M + nq * ng;
+    const int64_t n = g->ncells;
+    const unsigned grid = (unsigned)((n * nq + 127) / 128);
+    if (rd == 1) k_function_values<1><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, dh->d_cell_dofs, g->ncells_pad, g->xstride, n, cv->d_tables, o_N, o_dN, o_dM, nq, nb, cv->vdim, ng, u_dev, values_dev, gradients_dev, ctx->d_errflag);
+    else if (rd == 2) k_function_values<2><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, dh->d_cell_dofs, g->ncells_pad, g->xstride, n, cv->d_tables, o_N, o_dN, o_dM, nq, nb, cv->vdim, ng, u_dev, values_dev, gradients_dev, ctx->d_errflag);
+    else k_function_values<3><<<grid, 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, dh->d_cell_dofs, g->ncells_pad, g->xstride, n, cv->d_tables, o_N, o_dN, o_dM, nq, nb, cv->vdim, ng, u_dev, values_dev, gradients_dev, ctx->d_errflag);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
     return FB2_OK;
 }

@@ -232,6 +232,11 @@ int fb2_ch_destroy(fb2_ch* ch);
  * dNdx[cell][q][i][d] (rdim x n x nq per cell, column-major = cv.fun_values.dNdx) and detJdV[cell][q]. */
 int fb2_reinit_cells(fb2_cv* cv, fb2_grid* grid, const int64_t* cells, int64_t n, double* dNdx_dev, double* detJdV_dev);
 
+/* function_value / function_gradient (src/FEValues/common_values.jl:177-227) of the dof vector u at every quadrature
+ * point of every cell: values[cell][q][c] (vdim x nq per cell) and gradients[cell][q][c][d] (dim x vdim x nq per cell,
+ * column-major); either output may be NULL. */
+int fb2_function_values(fb2_cv* cv, fb2_dh* dh, const double* u_dev, double* values_dev, double* gradients_dev);
+
 /* ---- FacetValues and the Neumann / traction facet loop ------------------------ */
 typedef struct fb2_fv fb2_fv;
 typedef struct fb2_fset fb2_fset;

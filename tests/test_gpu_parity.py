@@ -783,3 +783,22 @@ def test_standalone_reinit_matches_oracle(ctx, ct, nel, order, qo):
     ids = np.array([og.ncells, 1, 2], dtype=np.int64)
     dNdx, dO = fb.reinit_(cv, g, ids)
     assert close(dNdx.cpu().numpy(), odN[ids - 1], 1e-13)[0] and close(dO.cpu().numpy(), odO[ids - 1], 1e-13)[0]
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,qo", [
+    (fb.Hexahedron, (4, 3, 5), 1, 3, 2), (fb.Hexahedron, (3, 3, 2), 2, 1, 3), (fb.Tetrahedron, (3, 2, 2), 2, 3, 4),
+    (fb.Quadrilateral, (6, 5), 2, 2, 3), (fb.Triangle, (5, 4), 1, 1, 2),
+])
+def test_function_values_and_gradients_match_oracle(ctx, ct, nel, order, vdim, qo):
+    # function_value / function_gradient (src/FEValues/common_values.jl:177-227) at every quadrature point
+    import torch
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(odh.ndofs)
+    vals, grads = fb.function_values_(cv, dh, torch.from_numpy(u).to(f"cuda:{ctx.device}"))
+    dNdx, _ = O.reinit(ocv, og.nodes[og.cells - 1])                 # (nc, nq, nb, dim)
+    ue = u[odh.cell_dofs - 1].reshape(og.ncells, -1, vdim)           # (nc, nb, vdim)
+    oval = np.einsum("qa,cav->cqv", ocv.N, ue)
+    ograd = np.einsum("cav,cqad->cqvd", ue, dNdx)
+    assert close(vals.cpu().numpy(), oval, 1e-13)[0]
+    assert close(grads.cpu().numpy(), ograd, 1e-13)[0]
