@@ -802,3 +802,36 @@ def test_function_values_and_gradients_match_oracle(ctx, ct, nel, order, vdim, q
     ograd = np.einsum("cav,cqad->cqvd", ue, dNdx)
     assert close(vals.cpu().numpy(), oval, 1e-13)[0]
     assert close(grads.cpu().numpy(), ograd, 1e-13)[0]
+
+
+@hst.composite
+def _random_facet_case(draw):
+    ct = draw(hst.sampled_from([fb.Triangle, fb.Quadrilateral, fb.Tetrahedron, fb.Hexahedron]))
+    dim = 2 if ct in (fb.Triangle, fb.Quadrilateral) else 3
+    nel = tuple(draw(hst.integers(1, 4 if dim == 3 else 7)) for _ in range(dim))
+    order = draw(hst.integers(1, 2))
+    kind = draw(hst.sampled_from(["flux", "traction", "normal_traction"]))
+    vdim = 1 if kind == "flux" else dim
+    qo = draw(hst.integers(1, 3))
+    names = ["left", "right", "top", "bottom"] + (["front", "back"] if dim == 3 else [])
+    sets = draw(hst.lists(hst.sampled_from(names), min_size=1, max_size=len(names), unique=True))
+    return ct, nel, order, vdim, qo, kind, tuple(sets)
+
+
+@settings(max_examples=_PROP_N or 30, deadline=None, derandomize=_PROP_N == 0,
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(_random_facet_case())
+def test_random_facet_loops_match_oracle(ctx, case):
+    ct, nel, order, vdim, qo, kind, sets = case
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, max(qo, 1))
+    fv = fb.FacetValues(fb.FacetQuadratureRule(ct, qo), cv.ip)
+    ofv = O.FacetValues(O.FacetQuadratureRule(SHAPE[ct], qo), ocv.ip)
+    pairs = np.concatenate([fb.getfacetset(g, s) for s in sets])
+    params = {"flux": 1.75, "traction": (0.3, -0.2, 0.7)[:og.sdim], "normal_traction": -0.4}[kind]
+    f = ctx.zeros(dh.ndofs)
+    fb.assemble_facets_(f, dh, fv, pairs, kind, params)
+    ctx.synchronize()
+    of = np.zeros(odh.ndofs)
+    O.assemble_facets(odh, ofv, of, pairs, kind, params)
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, (case, nrm)
