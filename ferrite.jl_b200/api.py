@@ -714,11 +714,18 @@ class Partition:
     """Rank `rank` of `nparts` of a global DofHandler: own + halo cells as a local problem, column ownership and
     per-peer interface exchange lists (see csrc/partition.cu).  `gdh` may live on a host-only context."""
 
-    def __init__(self, gdh, nparts, rank, dims=None):
+    def __init__(self, gdh, nparts, rank, dims=None, cell_owner=None):
+        """dims: px, py, pz block layout for generate_grid input (None = automatic); cell_owner: any partitioner's
+        cell -> rank array (0-based ranks, e.g. from METIS) instead of the block layout."""
         self.gdh, self.nparts, self.rank = gdh, int(nparts), int(rank)
         self.h = C.c_void_p()
-        darr = (C.c_int * 3)(*(list(dims) + [1, 1, 1])[:3]) if dims is not None else None
-        L.call("fb2_partition_create", gdh.h, self.nparts, self.rank, darr, C.byref(self.h))
+        if cell_owner is not None:
+            own = np.ascontiguousarray(cell_owner, dtype=np.int32)
+            assert own.shape == (gdh.grid.ncells,)
+            L.call("fb2_partition_create_from_owners", gdh.h, self.nparts, self.rank, _ptr(own, C.c_int32), C.byref(self.h))
+        else:
+            darr = (C.c_int * 3)(*(list(dims) + [1, 1, 1])[:3]) if dims is not None else None
+            L.call("fb2_partition_create", gdh.h, self.nparts, self.rank, darr, C.byref(self.h))
         v = [C.c_int64() for _ in range(5)]
         L.call("fb2_partition_info", self.h, *[C.byref(x) for x in v])
         self.ncells_local, self.ncells_own, self.nnodes_local, self.ndofs_local, self.ndofs_owned = (x.value for x in v)

@@ -127,7 +127,19 @@ inline unsigned nblk(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); 
 
 }  // namespace
 
+static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* dims_in, const int32_t* cell_owner, fb2_part** out);
+
 extern "C" int fb2_partition_create(fb2_dh* gdh, int nparts, int rank, const int* dims_in, fb2_part** out) {
+    return partition_create_impl(gdh, nparts, rank, dims_in, nullptr, out);
+}
+
+// any partitioner's result (e.g. METIS_PartMeshDual as in ext/FerriteMetis.jl): cell_owner[c] = rank of cell c (0-based)
+extern "C" int fb2_partition_create_from_owners(fb2_dh* gdh, int nparts, int rank, const int32_t* cell_owner, fb2_part** out) {
+    FB2_CHECK(cell_owner, FB2_ERR_BAD_ARG, "fb2_partition_create_from_owners: null owner array");
+    return partition_create_impl(gdh, nparts, rank, nullptr, cell_owner, out);
+}
+
+static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* dims_in, const int32_t* cell_owner, fb2_part** out) {
     FB2_CHECK(gdh && out, FB2_ERR_BAD_ARG, "fb2_partition_create: null argument");
     FB2_CHECK(nparts >= 1 && rank >= 0 && rank < nparts, FB2_ERR_BAD_ARG, "fb2_partition_create: bad nparts/rank");
     fb2_grid* g = gdh->grid;
@@ -139,7 +151,16 @@ extern "C" int fb2_partition_create(fb2_dh* gdh, int nparts, int rank, const int
     P->rank = rank;
     // ---- cell -> rank --------------------------------------------------------------------------------------
     std::vector<int32_t> owner((size_t)ncells);
-    if (g->generated && g->celltype != FB2_LINE) {
+    if (cell_owner) {
+        P->dims[0] = nparts;
+        for (int64_t c = 0; c < ncells; ++c) {
+            if (cell_owner[c] < 0 || cell_owner[c] >= nparts) {
+                delete P;
+                return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create_from_owners: owner %d of cell %lld is outside 0..%d", cell_owner[c], (long long)c + 1, nparts - 1);
+            }
+            owner[c] = cell_owner[c];
+        }
+    } else if (g->generated && g->celltype != FB2_LINE) {
         const int dim = g->sdim;
         if (dims_in) { for (int d = 0; d < 3; ++d) P->dims[d] = d < dim ? dims_in[d] : 1; }
         else default_dims(nparts, g->nel, dim, P->dims);

@@ -290,6 +290,9 @@ enum { FB2_DIST_EXCHANGE = 0, /* assemble own cells, exchange interface columns 
  * a dof shared with another rank | other own cells | halo cells], each group by ascending global id, so that
  * every group is a contiguous range and the interface exchange can overlap the interior cells. */
 int fb2_partition_create(fb2_dh* dh, int nparts, int rank, const int* dims, fb2_part** out);
+/* same plan from any partitioner's cell -> rank array (ncells entries, 0-based ranks), e.g. METIS_PartMeshDual as used by
+ * ext/FerriteMetis.jl */
+int fb2_partition_create_from_owners(fb2_dh* dh, int nparts, int rank, const int32_t* cell_owner, fb2_part** out);
 int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
                        int64_t* ndofs_local, int64_t* ndofs_owned);
 /* global ids (1-based) of the local cells / nodes / dofs, own-cell flags, owner rank of each local dof */

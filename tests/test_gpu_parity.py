@@ -835,3 +835,58 @@ def test_random_facet_loops_match_oracle(ctx, case):
     O.assemble_facets(odh, ofv, of, pairs, kind, params)
     ok, nrm = close(f.cpu().numpy(), of)
     assert ok, (case, nrm)
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,p,nparts", [
+    (fb.Hexahedron, (5, 4, 3), 1, 1, 2, "heat", {"k": 1.0, "source": 1.0}, 3),
+    (fb.Tetrahedron, (3, 2, 2), 1, 3, 2, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 4),
+])
+def test_partition_from_random_owner_array_matches_serial_oracle(ctx, ct, nel, order, vdim, qo, kind, p, nparts):
+    """A scattered (worst-case) cell -> rank array, as an external partitioner would hand in: gathered owned columns of the
+    emulated ranks == serial oracle."""
+    import torch
+    hctx = fb.Context(-1)
+    gg = fb.generate_grid(ct, nel, ctx=hctx).perturb(0.2)
+    ip = fb.Lagrange(ct, order) ** vdim
+    gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    elem, op = make_element(kind, p)
+    oK = O.allocate_matrix(odh)
+    of = np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, kind, op)
+    owner = np.random.default_rng(3).integers(0, nparts, size=gg.ncells).astype(np.int32)
+    owner[:nparts] = np.arange(nparts)
+    parts = [fb.Partition(gdh, nparts, r, cell_owner=owner) for r in range(nparts)]
+    st = []
+    for pt in parts:
+        lg, ldh = pt.local_problem(ctx)
+        K = fb.allocate_matrix(ldh)
+        f = ctx.zeros(ldh.ndofs)
+        a = fb.start_assemble(K, f)
+        pt.bind(a, cv)
+        pt.assemble_(elem, mode="own")
+        st.append((lg, ldh, K, f, a))
+    for r, pt in enumerate(parts):
+        for o in range(nparts):
+            ns, fs, _, _ = pt.peer_counts(o)
+            if ns + fs == 0:
+                continue
+            buf = torch.empty(ns + fs, dtype=torch.float64, device=st[r][3].device)
+            pt.pack(o, st[r][2], st[r][3], buf)
+            parts[o].unpack_add(r, buf, st[o][2], st[o][3])
+    for r, pt in enumerate(parts):
+        pt.mask_unowned(st[r][2], st[r][3])
+    rows, cols, vals, fd, fv = [], [], [], [], []
+    for r, pt in enumerate(parts):
+        i, j, v, d, x = pt.owned_triplets(st[r][2], st[r][3])
+        rows.append(i); cols.append(j); vals.append(v); fd.append(d); fv.append(x)
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    fd, fv = np.concatenate(fd), np.concatenate(fv)
+    order_ = np.lexsort((rows, cols))
+    assert len(rows) == oK.nnz and np.array_equal(rows[order_], oK.rowval)
+    ok, nrm = close(vals[order_], oK.nzval)
+    assert ok, nrm
+    fg = np.zeros(odh.ndofs)
+    fg[fd - 1] = fv
+    ok, nrm = close(fg, of)
+    assert ok, nrm

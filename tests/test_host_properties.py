@@ -69,3 +69,28 @@ def test_random_partitions_own_every_dof_once_and_mirror_their_lists(p, nparts):
             ns, nfs, _, _ = parts[a].peer_counts(b)
             _, _, nr, nfr = parts[b].peer_counts(a)
             assert (ns, nfs) == (nr, nfr)          # what a sends to b is what b expects from a
+
+
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(problems(max_fields=1), st.integers(2, 4), st.integers(0, 2**31 - 1))
+def test_partitions_from_arbitrary_owner_arrays(p, nparts, seed):
+    # any partitioner's cell -> rank array (METIS in the reference's ext/FerriteMetis.jl) gives a consistent plan
+    ct, nel, fields = p
+    g, dh, og, odh = build(ct, nel, fields)
+    if g.ncells < nparts:
+        return
+    rng = np.random.default_rng(seed)
+    owner = rng.integers(0, nparts, size=g.ncells).astype(np.int32)
+    owner[:nparts] = np.arange(nparts)           # every rank owns at least one cell
+    parts = [fb.Partition(dh, nparts, r, cell_owner=owner) for r in range(nparts)]
+    for r, pt in enumerate(parts):
+        own = np.sort(pt.cells_global[pt.cell_is_own == 1])
+        assert np.array_equal(own, np.flatnonzero(owner == r) + 1)
+    owned = np.concatenate([pt.l2g_dof[pt.dof_owner == pt.rank] for pt in parts])
+    assert len(owned) == dh.ndofs == len(np.unique(owned))
+    for a in range(nparts):
+        for b in range(nparts):
+            if a != b:
+                ns, nfs, _, _ = parts[a].peer_counts(b)
+                _, _, nr, nfr = parts[b].peer_counts(a)
+                assert (ns, nfs) == (nr, nfr)
