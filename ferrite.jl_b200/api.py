@@ -714,12 +714,14 @@ class Partition:
     """Rank `rank` of `nparts` of a global DofHandler: own + halo cells as a local problem, column ownership and
     per-peer interface exchange lists (see csrc/partition.cu).  `gdh` may live on a host-only context."""
 
-    def __init__(self, gdh, nparts, rank, dims=None, cell_owner=None):
+    def __init__(self, gdh, nparts, rank, dims=None, cell_owner=None, metis=False):
         """dims: px, py, pz block layout for generate_grid input (None = automatic); cell_owner: any partitioner's
-        cell -> rank array (0-based ranks, e.g. from METIS) instead of the block layout."""
+        cell -> rank array (0-based ranks) instead of the block layout; metis=True: METIS_PartMeshDual inside the library."""
         self.gdh, self.nparts, self.rank = gdh, int(nparts), int(rank)
         self.h = C.c_void_p()
-        if cell_owner is not None:
+        if metis:
+            L.call("fb2_partition_create_metis", gdh.h, self.nparts, self.rank, C.byref(self.h))
+        elif cell_owner is not None:
             own = np.ascontiguousarray(cell_owner, dtype=np.int32)
             assert own.shape == (gdh.grid.ncells,)
             L.call("fb2_partition_create_from_owners", gdh.h, self.nparts, self.rank, _ptr(own, C.c_int32), C.byref(self.h))

@@ -139,6 +139,40 @@ extern "C" int fb2_partition_create_from_owners(fb2_dh* gdh, int nparts, int ran
     return partition_create_impl(gdh, nparts, rank, nullptr, cell_owner, out);
 }
 
+// METIS from the CUDA toolkit (libmetis_static.a, the copy cuSOLVER ships; built with 64-bit idx_t, verified by a probe):
+// dual-graph partition of the mesh, two cells adjacent when they share a facet's worth of nodes.  Deterministic (default
+// seed), so every rank derives the same cell -> rank array on its own.
+extern "C" int METIS_PartMeshDual(int64_t* ne, int64_t* nn, int64_t* eptr, int64_t* eind, int64_t* vwgt, int64_t* vsize, int64_t* ncommon,
+                                  int64_t* nparts, void* tpwgts, int64_t* options, int64_t* objval, int64_t* epart, int64_t* npart);
+extern "C" int METIS_SetDefaultOptions(int64_t* options);
+
+extern "C" int fb2_partition_create_metis(fb2_dh* gdh, int nparts, int rank, fb2_part** out) {
+    FB2_CHECK(gdh && out, FB2_ERR_BAD_ARG, "fb2_partition_create_metis: null argument");
+    FB2_CHECK(nparts >= 1 && rank >= 0 && rank < nparts, FB2_ERR_BAD_ARG, "fb2_partition_create_metis: bad nparts/rank");
+    fb2_grid* g = gdh->grid;
+    const int64_t nc = g->ncells;
+    std::vector<int32_t> owner((size_t)nc, 0);
+    if (nparts > 1) {
+        const RefShapeInfo* rs = fb2_refshape(g->celltype);
+        const int nv = rs->nvertices;
+        int64_t ne = nc, nn = g->nnodes, ncommon = rs->rdim == 1 ? 1 : (rs->rdim == 2 ? 2 : rs->face_nverts[0]);
+        int64_t np = nparts, objval = 0;
+        std::vector<int64_t> eptr((size_t)nc + 1), eind((size_t)nc * nv), epart((size_t)nc), npart((size_t)nn);
+        for (int64_t c = 0; c < nc; ++c) {
+            eptr[c] = c * nv;
+            for (int k = 0; k < nv; ++k) eind[(size_t)c * nv + k] = g->cells[(size_t)c * g->nnpc + k] - 1;   // vertices only
+        }
+        eptr[nc] = nc * nv;
+        int64_t options[40];
+        METIS_SetDefaultOptions(options);
+        const int rc = METIS_PartMeshDual(&ne, &nn, eptr.data(), eind.data(), nullptr, nullptr, &ncommon, &np, nullptr, options, &objval,
+                                          epart.data(), npart.data());
+        FB2_CHECK(rc == 1, FB2_ERR_INTERNAL, "METIS_PartMeshDual failed with status %d", rc);
+        for (int64_t c = 0; c < nc; ++c) owner[c] = (int32_t)epart[c];
+    }
+    return partition_create_impl(gdh, nparts, rank, nullptr, owner.data(), out);
+}
+
 static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* dims_in, const int32_t* cell_owner, fb2_part** out) {
     FB2_CHECK(gdh && out, FB2_ERR_BAD_ARG, "fb2_partition_create: null argument");
     FB2_CHECK(nparts >= 1 && rank >= 0 && rank < nparts, FB2_ERR_BAD_ARG, "fb2_partition_create: bad nparts/rank");

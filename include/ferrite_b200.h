@@ -293,6 +293,8 @@ int fb2_partition_create(fb2_dh* dh, int nparts, int rank, const int* dims, fb2_
 /* same plan from any partitioner's cell -> rank array (ncells entries, 0-based ranks), e.g. METIS_PartMeshDual as used by
  * ext/FerriteMetis.jl */
 int fb2_partition_create_from_owners(fb2_dh* dh, int nparts, int rank, const int32_t* cell_owner, fb2_part** out);
+/* cell -> rank from METIS_PartMeshDual (the CUDA toolkit's libmetis_static.a, linked statically): general grids */
+int fb2_partition_create_metis(fb2_dh* dh, int nparts, int rank, fb2_part** out);
 int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
                        int64_t* ndofs_local, int64_t* ndofs_owned);
 /* global ids (1-based) of the local cells / nodes / dofs, own-cell flags, owner rank of each local dof */

@@ -841,9 +841,10 @@ def test_random_facet_loops_match_oracle(ctx, case):
     (fb.Hexahedron, (5, 4, 3), 1, 1, 2, "heat", {"k": 1.0, "source": 1.0}, 3),
     (fb.Tetrahedron, (3, 2, 2), 1, 3, 2, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 4),
 ])
-def test_partition_from_random_owner_array_matches_serial_oracle(ctx, ct, nel, order, vdim, qo, kind, p, nparts):
-    """A scattered (worst-case) cell -> rank array, as an external partitioner would hand in: gathered owned columns of the
-    emulated ranks == serial oracle."""
+@pytest.mark.parametrize("how", ["random_owners", "metis"])
+def test_partition_from_random_owner_array_matches_serial_oracle(ctx, ct, nel, order, vdim, qo, kind, p, nparts, how):
+    """A scattered (worst-case) cell -> rank array, as an external partitioner would hand in, and METIS_PartMeshDual
+    inside the library: gathered owned columns of the emulated ranks == serial oracle."""
     import torch
     hctx = fb.Context(-1)
     gg = fb.generate_grid(ct, nel, ctx=hctx).perturb(0.2)
@@ -856,7 +857,10 @@ def test_partition_from_random_owner_array_matches_serial_oracle(ctx, ct, nel, o
     O.assemble_global(odh, ocv, oK, of, kind, op)
     owner = np.random.default_rng(3).integers(0, nparts, size=gg.ncells).astype(np.int32)
     owner[:nparts] = np.arange(nparts)
-    parts = [fb.Partition(gdh, nparts, r, cell_owner=owner) for r in range(nparts)]
+    if how == "metis":
+        parts = [fb.Partition(gdh, nparts, r, metis=True) for r in range(nparts)]
+    else:
+        parts = [fb.Partition(gdh, nparts, r, cell_owner=owner) for r in range(nparts)]
     st = []
     for pt in parts:
         lg, ldh = pt.local_problem(ctx)

@@ -203,3 +203,18 @@ def test_two_rank_exchange_over_gloo():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_metis_partition_covers_the_grid_and_is_balanced():
+    # METIS_PartMeshDual from the CUDA toolkit's libmetis_static.a, computed independently per rank (deterministic)
+    hctx = fb.Context(-1)
+    for ct, nel, nparts in ((fb.Hexahedron, (8, 8, 8), 4), (fb.Tetrahedron, (5, 4, 3), 3), (fb.Quadrilateral, (17, 9), 5), (fb.Triangle, (6, 6), 2)):
+        g = fb.generate_grid(ct, nel, ctx=hctx)
+        dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, 1)))
+        parts = [fb.Partition(dh, nparts, r, metis=True) for r in range(nparts)]
+        own = np.concatenate([p.cells_global[p.cell_is_own == 1] for p in parts])
+        assert len(own) == g.ncells == len(np.unique(own))
+        sizes = np.array([p.ncells_own for p in parts])
+        assert sizes.min() > 0 and sizes.max() <= 1.3 * g.ncells / nparts + 2
+        owned = np.concatenate([p.l2g_dof[p.dof_owner == p.rank] for p in parts])
+        assert len(owned) == dh.ndofs == len(np.unique(owned))
