@@ -46,6 +46,23 @@ CONFIGS = {
 }
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that the pinned host buffers of the
+    end-to-end measurement are first-touched on the GPU's NUMA node (torchrun does not bind ranks)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:            # binding is an optimisation only
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,6 +244,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    bind_to_gpu_numa_node(local_rank)
     ctx = fb.default_context(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
 
