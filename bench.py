@@ -36,6 +36,8 @@ CONFIGS = {
                 label="heat Q1 hex 64^3 (reduced size, debugging only)"),
     "c5": dict(cell="hex", nel=(128, 128, 128), order=1, vdim=3, qr=2, element="elasticity", bmin=2060.0, fmin=15.5e3,
                label="linear elasticity Q1^3 hex 128^3 (per-GPU block of BASELINE.json configs[4])"),
+    "c5full": dict(cell="hex", nel=(160, 160, 160), order=1, vdim=3, qr=2, element="elasticity", bmin=2060.0, fmin=15.5e3,
+                   label="linear elasticity Q1^3 hex, 160^3 cells per GPU (BASELINE.json configs[4]: 320^3 cells on 8 GPUs)"),
     "c3": dict(cell="hex", nel=(48, 48, 48), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
                label="linear elasticity Q2^3 hex 48^3 (BASELINE.json configs[2] at 1/8 size)"),
     "c4": dict(cell="tet", nel=(48, 48, 48), order=2, vdim=3, qr=4, element="neohooke", bmin=7.0e3, fmin=0.25e6,
