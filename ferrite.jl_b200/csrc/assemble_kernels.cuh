@@ -8,14 +8,18 @@
 // through the precomputed uint16 offset map: nzval[colptr[dof_j] + map[i,j]] += Ke[i,j], either with FP64
 // RED atomics (any cell order) or with plain read-modify-write inside one colour.
 //
-// Two kernel families:
-//   k_cell_scalar  -- one thread per cell, Ke (upper triangle) and fe in FP64 registers, quadrature loop
-//                     fully unrolled, reference tables read as constant-bank operands.  Scalar fields with
-//                     few dofs per cell (Q1 quad/hex, P1/P2 simplices).
-//   k_cell_blocks  -- one CTA per batch of cells; phase A (thread per (cell, qp)) stages physical shape
-//                     gradients and dOmega in shared memory (cell index fastest => conflict free), phase B
-//                     (thread per (cell, row node a, tile of column nodes b)) integrates vdim x vdim node
-//                     blocks in registers and scatters them.  Vector fields and higher order.
+// Kernels (DESIGN.md section 4 has the measurements):
+//   k_cell_scalar     -- one thread per cell, Ke (upper triangle) and fe in FP64 registers, reference tables as
+//                        constant-bank operands, scatter indices staged with cp.async, x-face merge through warp
+//                        shuffles and lane-parity sector pairing of the REDs.  Scalar fields with few dofs per cell
+//                        (Q1 quad/hex, P1/P2 simplices).  The default for heat / mass.
+//   k_cell_syrk       -- isotropic elasticity on the FP64 tensor cores: G = X^T diag(dOmega) X per cell with DMMA
+//                        (warp per cell for small elements, an 8-warp CTA per Q2 hexahedron), Ke from G in the scatter.
+//   k_cell_blocks     -- one CTA per batch of cells; phase A stages physical shape gradients and dOmega (Neo-Hooke: P and
+//                        dP/dF) in shared memory, phase B (thread per (cell, row node, tile of column nodes)) integrates
+//                        vdim x vdim node blocks in registers and scatters them.  Neo-Hooke, Q2 scalar fields, variant 1.
+//   k_cell_scalar_ws  -- warp-specialised k_cell_scalar (variant 8), k_tile_scalar -- tile aggregation (variant 5):
+//                        measured alternatives, not defaults.
 #pragma once
 #include "common.h"
 
@@ -67,24 +71,6 @@ template <bool ATOMIC>
 __device__ __forceinline__ void fb2_add(double* p, double v) {
     if (ATOMIC) atomicAdd(p, v);  // result unused -> RED.E.ADD.F64
     else *p += v;
-}
-
-// Volatile read-only loads: ptxas keeps them in program order ahead of the REDs that follow, so a batch of
-// index loads is in flight together instead of one memory round trip per scattered entry.
-__device__ __forceinline__ int fb2_ldv_s32(const int32_t* p) {
-    int v;
-    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ unsigned fb2_ldv_u16(const uint16_t* p) {
-    unsigned short v;
-    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int64_t fb2_ldv_s64(const int64_t* p) {
-    int64_t v;
-    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
 }
 
 template <int DIM>
