@@ -123,15 +123,43 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def SAMPLE(cfg):
+    """bounded CPU sample (cubes per direction) of a configuration"""
+    if cfg["element"] == "neohooke":
+        return (8, 8, 8)
+    return (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
+
+
 def oracle_problem(cfg, nel):
     import oracle as O
-    shape = "hexahedron"
+    shape = "tetrahedron" if cfg.get("cell") == "tet" else "hexahedron"
     og = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * 3, (1,) * 3, 0.2)
     ip = O.Lagrange(shape, cfg["order"])
     ip = ip ** cfg["vdim"] if cfg["vdim"] > 1 else ip
     dh = O.DofHandler(og).add("u", ip).close()
     cv = O.CellValues(O.QuadratureRule(shape, cfg["qr"]), ip)
     return og, dh, cv
+
+
+def cpu_assembler(cfg, dh, cv, K, f):
+    """(callable doing one CPU assembly, threads used, description): the C/OpenMP restatement of the reference loop, or --
+    for Neo-Hooke, which the C port does not cover -- the numpy restatement (one core)."""
+    import numpy as np
+    import oracle as O
+    from oracle import cport
+    if cfg["element"] == "neohooke":
+        E, nu = 10.0, 0.3
+        params = {"mu": E / (2 * (1 + nu)), "lambda": E * nu / ((1 + nu) * (1 - 2 * nu)), "b": (0.0, -0.5, 0.0)}
+        u = 1e-3 * np.sin(0.37 * np.arange(dh.ndofs, dtype=np.float64))
+        return (lambda: O.assemble_global(dh, cv, K, f, "neohooke", params=params, u=u)), 1, "numpy restatement of the reference loop"
+    if cfg["element"] == "heat":
+        params = {"k": 1.0, "source": 1.0}
+    else:
+        lam, mu = O.lame(200e9, 0.3)
+        params = {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}
+    nthreads = os.cpu_count() or 1
+    return (lambda: cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)), nthreads, \
+        "C restatement of the reference's threaded atomic loop"
 
 
 def cpu_baseline(cfg, sample_nel, reps=3, threads=0):
@@ -142,21 +170,16 @@ def cpu_baseline(cfg, sample_nel, reps=3, threads=0):
     og, dh, cv = oracle_problem(cfg, sample_nel)
     K = O.allocate_matrix(dh)
     f = np.zeros(dh.ndofs)
-    if cfg["element"] == "heat":
-        params = {"k": 1.0, "source": 1.0}
-    else:
-        lam, mu = O.lame(200e9, 0.3)
-        params = {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}
-    nthreads = threads or (os.cpu_count() or 1)
-    cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)   # warm-up
+    run, nthreads, what = cpu_assembler(cfg, dh, cv, K, f)
+    run()   # warm-up
     best = float("inf")
     for _ in range(reps):
         t0 = time.perf_counter()
-        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+        run()
         best = min(best, time.perf_counter() - t0)
     return {"value": og.ncells / best, "unit": "cells/s", "cores": nthreads, "kind": "port",
-            "sample": f"{'x'.join(map(str, sample_nel))} cells of the same workload (C restatement of the reference loop, "
-                      f"OpenMP atomic scatter, best of {reps}); the reference is Julia and cannot run here"}
+            "sample": f"{'x'.join(map(str, sample_nel))} cubes of the same workload ({what}, best of {reps}); "
+                      "the reference is Julia and cannot run here"}
 
 
 def run_reference(args, cfg):
@@ -164,24 +187,18 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
+    sample = SAMPLE(cfg)
     import numpy as np
     import oracle as O
-    from oracle import cport
     og, dh, cv = oracle_problem(cfg, sample)
     K = O.allocate_matrix(dh)
     f = np.zeros(dh.ndofs)
-    if cfg["element"] == "heat":
-        params = {"k": 1.0, "source": 1.0}
-    else:
-        lam, mu = O.lame(200e9, 0.3)
-        params = {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}
-    nthreads = os.cpu_count() or 1
+    run, nthreads, what = cpu_assembler(cfg, dh, cv, K, f)
     for _ in range(args.warmup):
-        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+        run()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cport.assemble(dh, cv, K, f, cfg["element"], params, nthreads=nthreads)
+        run()
     dt = time.perf_counter() - t0
     value = og.ncells * args.steps / dt
     sample_txt = f"{'x'.join(map(str, sample))} cells per step of the same workload"
@@ -191,7 +208,7 @@ def run_reference(args, cfg):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["label"], "sample": sample_txt},
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": nthreads, "kind": "port", "sample": sample_txt +
-                         "; C restatement of the reference's threaded atomic loop (the reference is Julia, no toolchain here)"},
+                         f"; {what} (the reference is Julia, no toolchain here)"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -507,8 +524,7 @@ def main():
         spmv["frac_of_hbm_peak"] = spmv["GB/s"] / hbm_peak
         line["spmv"] = spmv
     if not args.no_cpu_baseline and world == 1:
-        sample = (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
-        line["cpu_baseline"] = cpu_baseline(cfg, sample)
+        line["cpu_baseline"] = cpu_baseline(cfg, SAMPLE(cfg))
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
