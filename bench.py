@@ -126,7 +126,7 @@ class ClockSampler:
 def SAMPLE(cfg):
     """bounded CPU sample (cubes per direction) of a configuration"""
     if cfg["element"] == "neohooke":
-        return (8, 8, 8)
+        return (24, 24, 24)
     return (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
 
 
@@ -142,8 +142,7 @@ def oracle_problem(cfg, nel):
 
 
 def cpu_assembler(cfg, dh, cv, K, f):
-    """(callable doing one CPU assembly, threads used, description): the C/OpenMP restatement of the reference loop, or --
-    for Neo-Hooke, which the C port does not cover -- the numpy restatement (one core)."""
+    """(callable doing one CPU assembly, threads used, description): the C/OpenMP restatement of the reference loop."""
     import numpy as np
     import oracle as O
     from oracle import cport
@@ -151,7 +150,9 @@ def cpu_assembler(cfg, dh, cv, K, f):
         E, nu = 10.0, 0.3
         params = {"mu": E / (2 * (1 + nu)), "lambda": E * nu / ((1 + nu) * (1 - 2 * nu)), "b": (0.0, -0.5, 0.0)}
         u = 1e-3 * np.sin(0.37 * np.arange(dh.ndofs, dtype=np.float64))
-        return (lambda: O.assemble_global(dh, cv, K, f, "neohooke", params=params, u=u)), 1, "numpy restatement of the reference loop"
+        nthreads = os.cpu_count() or 1
+        return (lambda: cport.assemble(dh, cv, K, f, "neohooke", params, nthreads=nthreads, u=u)), nthreads, \
+            "C restatement of the reference's threaded atomic loop"
     if cfg["element"] == "heat":
         params = {"k": 1.0, "source": 1.0}
     else:

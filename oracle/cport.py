@@ -63,7 +63,7 @@ def max_threads():
     return lib().oracle_max_threads()
 
 
-def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0):
+def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0, u=None):
     """Same contract as oracle.assemble_global, executed by the C port with `nthreads` OpenMP threads."""
     grid = dh.grid
     n = dh.ndofs_per_cell
@@ -75,8 +75,13 @@ def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0):
     elif element == "elasticity":
         b = list((params or {}).get("b") or (0.0,) * cv.vdim) + [0.0, 0.0, 0.0]
         eid, pv = 3, np.array([params["lambda"], params["mu"]] + b[:3])
+    elif element == "neohooke":
+        assert u is not None and cv.vdim == 3 and grid.sdim == 3
+        b = list((params or {}).get("b") or (0.0,) * 3) + [0.0, 0.0, 0.0]
+        eid, pv = 4, np.array([params["lambda"], params["mu"]] + b[:3])
     else:
         raise ValueError(element)
+    uu = np.ascontiguousarray(u, dtype=np.float64) if u is not None else None
     cells = np.ascontiguousarray(grid.cells, dtype=np.int64)
     xyz = np.ascontiguousarray(grid.nodes, dtype=np.float64)
     cd = np.ascontiguousarray(dh.cell_dofs, dtype=np.int64)
@@ -94,7 +99,7 @@ def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0):
         C.c_int(eid), C.c_int(grid.sdim), C.c_int(cells.shape[1]), C.c_int(cv.base.nbase), C.c_int(cv.vdim), C.c_int(cv.nq),
         C.c_int64(grid.ncells), ptr(cells, C.c_int64), ptr(xyz, C.c_double), ptr(cd, C.c_int64),
         ptr(K.colptr, C.c_int64), ptr(K.rowval, C.c_int64), ptr(N, C.c_double), ptr(dN, C.c_double), ptr(dM, C.c_double),
-        ptr(w, C.c_double), ptr(pv, C.c_double), ptr(K.nzval, C.c_double),
+        ptr(w, C.c_double), ptr(pv, C.c_double), ptr(uu, C.c_double) if uu is not None else None, ptr(K.nzval, C.c_double),
         ptr(f, C.c_double) if f is not None else None, C.c_int(nthreads))
     if bad:
         raise ArithmeticError(f"det(J) is not positive in cell {bad}")

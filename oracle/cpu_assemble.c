@@ -62,7 +62,7 @@ static void sortperm(int n, const int64_t* dofs, int64_t* sorted, int* perm) {
 int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int nq, int64_t ncells, const int64_t* cells,
                         const double* xyz, const int64_t* cell_dofs, const int64_t* colptr, const int64_t* rowval,
                         const double* N, const double* dN, const double* dM, const double* w, const double* params,
-                        double* nzval, double* f, int nthreads) {
+                        const double* u, double* nzval, double* f, int nthreads) {
     const int n = nbs * vdim;
     int64_t bad = 0;
     if (n > MAXN || ngeo > MAXG) return -1;
@@ -113,6 +113,63 @@ int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int n
                             Ke[j * n + i] += params[0] * s * dO;
                         }
                     }
+                } else if (element == 4) {
+                    /* Neo-Hooke tangent + residual, docs/src/literate-tutorials/hyperelasticity.jl:162-176,241-276:
+                       Psi = mu/2 (Ic - 3 - 2 ln J) + lam/2 (J - 1)^2, S and dS/dC in closed form (dim == vdim == 3) */
+                    const double lam = params[0], mu = params[1];
+                    double F[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Cm[9], Ci[9], S[9], P[9], A[81];
+                    for (int a = 0; a < nbs; ++a)
+                        for (int c = 0; c < 3; ++c) {
+                            double uc = u[dofs[a * 3 + c] - 1];
+                            for (int b = 0; b < 3; ++b) F[c * 3 + b] += uc * g[a * 3 + b];
+                        }
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) Cm[i * 3 + j] = F[i] * F[j] + F[3 + i] * F[3 + j] + F[6 + i] * F[6 + j];
+                    double detC = det_inv(3, Cm, Ci);
+                    if (!(detC > 0.0)) {
+#pragma omp critical
+                        if (!bad) bad = ci + 1;
+                    }
+                    double Jd = sqrt(detC), cS = lam * Jd * (Jd - 1.0);
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) S[i * 3 + j] = mu * ((i == j) - Ci[i * 3 + j]) + cS * Ci[i * 3 + j];
+                    double c1 = (mu - cS) * 0.5, c2 = lam * (2.0 * Jd - 1.0) * (Jd * 0.5);
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) P[i * 3 + j] = F[i * 3] * S[j] + F[i * 3 + 1] * S[3 + j] + F[i * 3 + 2] * S[6 + j];
+                    /* dP_ij/dF_mn = delta_im S_jn + 2 F_ia dSdC_ajkn F_mk,
+                       dSdC_ajkn = c1 (Ci_ak Ci_nj + Ci_an Ci_kj) + c2 Ci_aj Ci_kn */
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j)
+                            for (int m = 0; m < 3; ++m)
+                                for (int nn = 0; nn < 3; ++nn) {
+                                    double t = 0;
+                                    for (int a = 0; a < 3; ++a)
+                                        for (int k = 0; k < 3; ++k) {
+                                            double d4 = c1 * (Ci[a * 3 + k] * Ci[nn * 3 + j] + Ci[a * 3 + nn] * Ci[k * 3 + j]) + c2 * Ci[a * 3 + j] * Ci[k * 3 + nn];
+                                            t += F[i * 3 + a] * d4 * F[m * 3 + k];
+                                        }
+                                    A[((i * 3 + j) * 3 + m) * 3 + nn] = (i == m ? S[j * 3 + nn] : 0.0) + 2.0 * t;
+                                }
+                    for (int a = 0; a < nbs; ++a)
+                        for (int c = 0; c < 3; ++c) {
+                            int I = a * 3 + c;
+                            double s = 0;
+                            for (int j = 0; j < 3; ++j) s += g[a * 3 + j] * P[c * 3 + j];
+                            fe[I] += (s - N[q * nbs + a] * params[2 + c]) * dO;
+                            double h[9];   /* hoisted: grad(du_i) : dP/dF */
+                            for (int d = 0; d < 3; ++d)
+                                for (int nn = 0; nn < 3; ++nn) {
+                                    double t = 0;
+                                    for (int j = 0; j < 3; ++j) t += g[a * 3 + j] * A[((c * 3 + j) * 3 + d) * 3 + nn];
+                                    h[d * 3 + nn] = t;
+                                }
+                            for (int b = 0; b < nbs; ++b)
+                                for (int d = 0; d < 3; ++d) {
+                                    double t = 0;
+                                    for (int nn = 0; nn < 3; ++nn) t += h[d * 3 + nn] * g[b * 3 + nn];
+                                    Ke[(b * 3 + d) * n + I] += t * dO;
+                                }
+                        }
                 } else {
                     const double lam = params[0], mu = params[1];
                     for (int a = 0; a < nbs; ++a)

@@ -254,6 +254,25 @@ def test_c_port_matches_numpy_oracle():
             assert np.all(np.abs(f2 - f1) <= 1e-13 * max(np.abs(f1).max(), 1e-300))
 
 
+def test_c_port_neohooke_matches_numpy_oracle():
+    # Neo-Hooke tangent + residual of the C restatement (bench cpu_baseline for the tetrahedral configuration)
+    from oracle import cport
+    lam, mu = O.lame(10.0, 0.3)
+    params = {"lambda": lam, "mu": mu, "b": (0.0, -0.5, 0.1)}
+    for shape, nel, order, qo in (("tetrahedron", (3, 3, 2), 2, 4), ("hexahedron", (3, 2, 2), 1, 2)):
+        grid = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * 3, (1,) * 3, 0.2)
+        ip = O.Lagrange(shape, order) ** 3
+        dh = O.DofHandler(grid).add("u", ip).close()
+        cv = O.CellValues(O.QuadratureRule(shape, qo), ip)
+        u = 0.02 * np.sin(0.7 * np.arange(dh.ndofs))
+        K1, f1 = O.allocate_matrix(dh), np.zeros(dh.ndofs)
+        O.assemble_global(dh, cv, K1, f1, "neohooke", params=params, u=u)
+        K2, f2 = O.allocate_matrix(dh), np.zeros(dh.ndofs)
+        cport.assemble(dh, cv, K2, f2, "neohooke", params, nthreads=3, u=u)
+        assert np.all(np.abs(K2.nzval - K1.nzval) <= 1e-13 * np.abs(K1.nzval).max())
+        assert np.all(np.abs(f2 - f1) <= 1e-13 * np.abs(f1).max())
+
+
 def _hyperelasticity_problem(O_):
     """docs/src/literate-tutorials/hyperelasticity.jl:329-391: grid, values, Dirichlet data, Neumann set"""
     N, L = 10, 1.0
