@@ -184,4 +184,31 @@ function assemble_facets!(f_dev::Ptr{Float64}, prob::DeviceProblem, celltype::In
     return f_dev
 end
 
+# ---- the consumer of K on the device: IterativeSolvers.cg!(x, K, b; ...) (hyperelasticity.jl:418), mul! ------------------
+# nzval_dev / b_dev / x_dev are device pointers (what fb2_assemble wrote); returns (iterations, final residual norm)
+function cg_device!(x_dev::Ptr{Float64}, K::B200Matrix, nzval_dev::Ptr{Float64}, b_dev::Ptr{Float64};
+        reltol::Float64 = sqrt(eps(Float64)), abstol::Float64 = 0.0, maxiter::Int = size(K.host, 1), jacobi::Bool = false)
+    iters = Ref{Cint}(0)
+    res = Ref{Float64}(0.0)
+    @fb2 fb2_cg (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Cint, Ptr{Cint}, Ptr{Float64}) K.pattern nzval_dev b_dev x_dev reltol abstol maxiter jacobi true iters res
+    return Int(iters[]), res[]
+end
+
+function mul_device!(y_dev::Ptr{Float64}, K::B200Matrix, nzval_dev::Ptr{Float64}, x_dev::Ptr{Float64}; transpose::Bool = false)
+    @fb2 fb2_spmv (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint) K.pattern nzval_dev x_dev y_dev transpose
+    return y_dev
+end
+
+# ---- partition plan of rank `rank` of `nparts` (one process per GPU): METIS_PartMeshDual inside the library, or the
+# cell -> rank vector of any partitioner (0-based ranks) -----------------------------------------------------------
+function partition_plan(global_dh_handle::Ptr{Cvoid}, nparts::Integer, rank::Integer; cell_owner::Union{Nothing, Vector{Int32}} = nothing)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    if cell_owner === nothing
+        @fb2 fb2_partition_create_metis (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}) global_dh_handle nparts rank p
+    else
+        @fb2 fb2_partition_create_from_owners (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Ptr{Ptr{Cvoid}}) global_dh_handle nparts rank cell_owner p
+    end
+    return p[]
+end
+
 end # module
