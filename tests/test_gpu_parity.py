@@ -894,3 +894,23 @@ def test_partition_from_random_owner_array_matches_serial_oracle(ctx, ct, nel, o
     fg[fd - 1] = fv
     ok, nrm = close(fg, of)
     assert ok, nrm
+
+
+def test_empty_inputs_are_no_ops(ctx):
+    # empty facet set, empty Dirichlet set, reinit of zero cells: nothing changes, nothing fails
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (2, 2, 2), 1, 1, 2)
+    fv = fb.FacetValues(fb.FacetQuadratureRule(fb.Hexahedron, 2), cv.ip)
+    f = ctx.zeros(dh.ndofs)
+    f += 3.0
+    fb.assemble_facets_(f, dh, fv, np.zeros((0, 2), dtype=np.int64), "flux", 1.0)
+    ctx.synchronize()
+    assert float((f - 3.0).abs().max()) == 0.0
+    dNdx, dO = fb.reinit_(cv, g, np.zeros(0, dtype=np.int64))
+    assert dNdx.shape[0] == 0 and dO.shape[0] == 0
+    K = fb.allocate_matrix(dh)
+    fb.assemble_(fb.start_assemble(K, f), fb.HeatElement(), cv)
+    ref = K.nzval.clone()
+    ch = fb.ConstraintHandler.from_arrays(dh, np.zeros(0, dtype=np.int64), np.zeros(0))
+    fb.apply_(K, f, ch)
+    ctx.synchronize()
+    assert float((K.nzval - ref).abs().max()) == 0.0
