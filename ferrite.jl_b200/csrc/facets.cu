@@ -428,13 +428,14 @@ __global__ void k_function_values(const int32_t* __restrict__ conn, const double
 }  // namespace
 
 extern "C" int fb2_reinit_cells(fb2_cv* cv, fb2_grid* g, const int64_t* cells, int64_t n, double* dNdx_dev, double* detJdV_dev) {
-    FB2_CHECK(cv && g && dNdx_dev && detJdV_dev && n >= 0, FB2_ERR_BAD_ARG, "fb2_reinit_cells: bad argument");
+    FB2_CHECK(cv && g && n >= 0, FB2_ERR_BAD_ARG, "fb2_reinit_cells: bad argument");
+    if (n == 0) return FB2_OK;                       // empty batch: nothing to write (the outputs may be null)
+    FB2_CHECK(dNdx_dev && detJdV_dev, FB2_ERR_BAD_ARG, "fb2_reinit_cells: null output");
     fb2_ctx* ctx = g->ctx;
     FB2_NEED_DEVICE(ctx);
     FB2_CHECK(cv->celltype == g->celltype && cv->rdim == g->sdim && cv->ngeo == g->nnpc, FB2_ERR_BAD_ARG, "fb2_reinit_cells: CellValues do not match the grid");
     if (cells) for (int64_t k = 0; k < n; ++k) FB2_CHECK(cells[k] >= 1 && cells[k] <= g->ncells, FB2_ERR_BAD_ARG, "fb2_reinit_cells: cell %lld out of range", (long long)cells[k]);
     else FB2_CHECK(n <= g->ncells, FB2_ERR_BAD_ARG, "fb2_reinit_cells: more cells than the grid has");
-    if (n == 0) return FB2_OK;
     FB2_CUDA(cudaSetDevice(ctx->device));
     const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
     const int o_w = 0, o_N = nq, o_dN = o_N + nq * nb, o_M = o_dN + nq * nb * rd, o_dM = o_M + nq * ng;
