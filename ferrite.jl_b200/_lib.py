@@ -101,6 +101,8 @@ _PROTOS = {
     "fb2_grid_destroy": [_p],
     "fb2_dh_close": [_p, C.c_int, C.POINTER(Field), _pp],
     "fb2_dh_from_host": [_p, C.c_int, C.POINTER(Field), C.c_int64, C.c_int, _i64p, _pp],
+    "fb2_dh_renumber": [_p, C.c_int, _i64p, C.c_int, _i64p, _i64p],
+    "fb2_ch_renumber": [_p, _i64p],
     "fb2_dh_info": [_p, _i64p, _ip, _ip],
     "fb2_dh_export": [_p, _i64p],
     "fb2_dh_dof_range": [_p, C.c_int, _ip, _ip],
@@ -167,6 +169,7 @@ _PROTOS = {
 }
 DIST_EXCHANGE, DIST_HALO, DIST_OWN_ONLY = 0, 1, 2
 FACET_FLUX, FACET_TRACTION, FACET_NORMAL_TRACTION = 1, 2, 3
+ORDER_PERMUTATION, ORDER_FIELDWISE, ORDER_COMPONENTWISE = 0, 1, 2
 
 lib.fb2_version.restype = C.c_char_p
 lib.fb2_version.argtypes = []

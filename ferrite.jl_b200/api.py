@@ -242,6 +242,38 @@ class DofHandler:
             _destroy(self, "fb2_dh_destroy", _chain(self, "grid"))
 
 
+class DofOrder:
+    """DofOrder.FieldWise([target_blocks]) / DofOrder.ComponentWise([target_blocks]) (src/Dofs/DofRenumbering.jl:1-40)"""
+
+    class FieldWise:
+        kind = L.ORDER_FIELDWISE
+
+        def __init__(self, target_blocks=None):
+            self.target_blocks = None if target_blocks is None else [int(b) for b in target_blocks]
+
+    class ComponentWise(FieldWise):
+        kind = L.ORDER_COMPONENTWISE
+
+
+def renumber_(dh, *args):
+    """renumber!(dh, order) / renumber!(dh, ch, order): order = a permutation vector (1-based, dof i becomes perm[i]),
+    DofOrder.FieldWise(...) or DofOrder.ComponentWise(...).  Returns the permutation that was applied (1-based).
+    Renumber before allocate_matrix / start_assemble: matrices of the old numbering are stale (as in the reference)."""
+    ch, order = (None, args[0]) if len(args) == 1 else args
+    perm_out = np.empty(dh.ndofs, dtype=np.int64)
+    if isinstance(order, DofOrder.FieldWise):
+        tb = None if order.target_blocks is None else _i64(order.target_blocks)
+        L.call("fb2_dh_renumber", dh.h, order.kind, _ptr(tb, C.c_int64) if tb is not None else None,
+               0 if tb is None else len(tb), None, _ptr(perm_out, C.c_int64))
+    else:
+        perm = _i64(order)
+        assert perm.shape == (dh.ndofs,), "input vector is not a permutation of length ndofs(dh)"
+        L.call("fb2_dh_renumber", dh.h, L.ORDER_PERMUTATION, None, 0, _ptr(perm, C.c_int64), _ptr(perm_out, C.c_int64))
+    if ch is not None:
+        L.call("fb2_ch_renumber", ch.h, _ptr(perm_out, C.c_int64))
+    return perm_out
+
+
 def add_(obj, *args):
     """add!(dh, name, ip)  or  add!(ch, dbc)"""
     if isinstance(obj, DofHandler):

@@ -290,6 +290,36 @@ extern "C" int fb2_ch_from_host(fb2_dh* dh, int64_t n, const int64_t* prescribed
     return FB2_OK;
 }
 
+// renumber!(dh, ch, perm), the ConstraintHandler half (src/Dofs/DofRenumbering.jl:92-125): prescribed dofs are mapped through
+// perm (1-based, dof i -> perm[i]) and re-sorted together with their inhomogeneities
+extern "C" int fb2_ch_renumber(fb2_ch* ch, const int64_t* perm) {
+    FB2_CHECK(ch && perm, FB2_ERR_BAD_ARG, "fb2_ch_renumber: null argument");
+    FB2_CHECK(ch->closed, FB2_ERR_BAD_ARG, "fb2_ch_renumber: close the ConstraintHandler first");
+    const int64_t n = ch->dh->ndofs;
+    const size_t np = ch->prescribed.size();
+    std::vector<std::pair<int64_t, double>> pv(np);
+    for (size_t i = 0; i < np; ++i) {
+        const int64_t v = perm[ch->prescribed[i]] - 1;
+        FB2_CHECK(v >= 0 && v < n, FB2_ERR_BAD_ARG, "fb2_ch_renumber: permutation entry out of range");
+        pv[i] = {v, ch->inhom[i]};
+    }
+    std::sort(pv.begin(), pv.end());
+    for (int64_t& d : ch->insertion) d = perm[d] - 1;
+    for (DirichletBC& bc : ch->bcs)
+        for (int64_t& d : bc.point_dofs) d = perm[d] - 1;
+    ch->dofmap.assign((size_t)n, -1);
+    for (size_t i = 0; i < np; ++i) {
+        ch->prescribed[i] = pv[i].first;
+        ch->inhom[i] = pv[i].second;
+        ch->dofmap[pv[i].first] = (int32_t)i;
+    }
+    if (ch->d_prescribed) { cudaFree(ch->d_prescribed); ch->d_prescribed = nullptr; }
+    if (ch->d_inhom) { cudaFree(ch->d_inhom); ch->d_inhom = nullptr; }
+    if (ch->d_isconstrained) { cudaFree(ch->d_isconstrained); ch->d_isconstrained = nullptr; }
+    if (ch->d_scratch) { cudaFree(ch->d_scratch); ch->d_scratch = nullptr; }
+    return finish_close(ch);
+}
+
 extern "C" int fb2_ch_bc_points(fb2_ch* ch, int ibc, int64_t* npoints, double* x) {
     FB2_CHECK(ch && npoints && ibc >= 0 && ibc < (int)ch->bcs.size(), FB2_ERR_BAD_ARG, "fb2_ch_bc_points: bad argument");
     const DirichletBC& bc = ch->bcs[ibc];

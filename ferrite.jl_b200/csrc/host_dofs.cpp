@@ -164,6 +164,72 @@ extern "C" int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fi
     return FB2_OK;
 }
 
+// renumber!(dh, order): src/Dofs/DofRenumbering.jl:79-125 (apply), :167-246 (FieldWise / ComponentWise permutations).
+// kind 0: perm_in (1-based, dof i -> perm_in[i]); 1: FieldWise, 2: ComponentWise with optional target blocks (1-based block
+// per field / per component; nullptr = one block each in declaration order).  The permutation is returned in perm_out
+// (1-based, nullable) so that a ConstraintHandler can follow (fb2_ch_renumber).  Patterns, assemblers and partitions built
+// from the old numbering are stale afterwards, exactly like in the reference.
+extern "C" int fb2_dh_renumber(fb2_dh* dh, int kind, const int64_t* target_blocks, int ntargets, const int64_t* perm_in, int64_t* perm_out) {
+    FB2_CHECK(dh, FB2_ERR_BAD_ARG, "fb2_dh_renumber: null handle");
+    const int64_t n = dh->ndofs;
+    const int64_t nc = dh->grid->ncells;
+    const int ndpc = dh->ndpc;
+    std::vector<int64_t> perm((size_t)n);   // 0-based: old -> new
+    if (kind == 0) {
+        FB2_CHECK(perm_in, FB2_ERR_BAD_ARG, "fb2_dh_renumber: a permutation is required");
+        std::vector<uint8_t> seen((size_t)n, 0);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t v = perm_in[i] - 1;
+            FB2_CHECK(v >= 0 && v < n && !seen[v], FB2_ERR_BAD_ARG, "fb2_dh_renumber: input vector is not a permutation of length ndofs(dh)");
+            seen[v] = 1;
+            perm[i] = v;
+        }
+    } else if (kind == 1 || kind == 2) {
+        // component -> block
+        std::vector<int> fdim, coff(1, 0);
+        for (const fb2_field& f : dh->fields) { fdim.push_back(f.vdim); coff.push_back(coff.back() + f.vdim); }
+        const int ncomp = coff.back(), nfields = (int)fdim.size();
+        std::vector<int> block((size_t)ncomp);
+        if (!target_blocks) {
+            for (int f = 0; f < nfields; ++f)
+                for (int c = 0; c < fdim[f]; ++c) block[coff[f] + c] = kind == 1 ? f : coff[f] + c;
+        } else {
+            FB2_CHECK(ntargets == (kind == 1 ? nfields : ncomp), FB2_ERR_BAD_ARG,
+                      kind == 1 ? "fb2_dh_renumber: length of target block vector does not match number of fields in DofHandler"
+                                : "fb2_dh_renumber: length of target block vector does not match number of components in DofHandler");
+            for (int f = 0; f < nfields; ++f)
+                for (int c = 0; c < fdim[f]; ++c) block[coff[f] + c] = (int)target_blocks[kind == 1 ? f : coff[f] + c] - 1;
+        }
+        int nblocks = 0;
+        for (int b : block) { FB2_CHECK(b >= 0, FB2_ERR_BAD_ARG, "fb2_dh_renumber: target blocks are 1-based"); nblocks = std::max(nblocks, b + 1); }
+        std::vector<uint8_t> used((size_t)nblocks, 0);
+        for (int b : block) used[b] = 1;
+        for (uint8_t u : used) FB2_CHECK(u, FB2_ERR_BAD_ARG, "fb2_dh_renumber: target blocks must be continuous and in the range 1:maxblock");
+        // dof -> block (every dof belongs to exactly one field component)
+        std::vector<int> dofblock((size_t)n, -1);
+        for (int64_t c = 0; c < nc; ++c) {
+            int off = 0;
+            for (int f = 0; f < nfields; ++f) {
+                const int nloc = dh->ips[f].nbase * fdim[f];
+                for (int j = 0; j < nloc; ++j) dofblock[dh->cell_dofs[(size_t)c * ndpc + off + j]] = block[coff[f] + j % fdim[f]];
+                off += nloc;
+            }
+        }
+        // stable: blocks in order, ascending old dof number inside a block
+        std::vector<int64_t> start((size_t)nblocks + 1, 0);
+        for (int64_t d = 0; d < n; ++d) { FB2_CHECK(dofblock[d] >= 0, FB2_ERR_INTERNAL, "fb2_dh_renumber: dof %lld belongs to no cell", (long long)d + 1); start[dofblock[d] + 1]++; }
+        for (int b = 0; b < nblocks; ++b) start[b + 1] += start[b];
+        for (int64_t d = 0; d < n; ++d) perm[d] = start[dofblock[d]]++;
+    } else {
+        return fb2_fail(FB2_ERR_BAD_ARG, "fb2_dh_renumber: unknown order %d", kind);
+    }
+    for (size_t i = 0; i < dh->cell_dofs.size(); ++i) dh->cell_dofs[i] = (int32_t)perm[dh->cell_dofs[i]];
+    if (dh->d_cell_dofs) { cudaFree(dh->d_cell_dofs); dh->d_cell_dofs = nullptr; }
+    FB2_TRY(upload_cell_dofs(dh));
+    if (perm_out) for (int64_t i = 0; i < n; ++i) perm_out[i] = perm[i] + 1;
+    return FB2_OK;
+}
+
 extern "C" int fb2_dh_info(fb2_dh* dh, int64_t* ndofs, int* ndofs_per_cell, int* nfields) {
     FB2_CHECK(dh, FB2_ERR_BAD_ARG, "fb2_dh_info: null handle");
     if (ndofs) *ndofs = dh->ndofs;

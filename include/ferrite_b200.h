@@ -141,6 +141,12 @@ int fb2_dh_close(fb2_grid* grid, int nfields, const fb2_field* fields, fb2_dh** 
  * src/Dofs/DofHandler.jl:126-131 */
 int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fields, int64_t ndofs,
                      int ndofs_per_cell, const int64_t* cell_dofs, fb2_dh** out);
+/* renumber!(dh, order): src/Dofs/DofRenumbering.jl:79-125,167-246.  order: 0 = the permutation perm_in (1-based, dof i
+ * becomes perm_in[i]), FB2_ORDER_FIELDWISE / FB2_ORDER_COMPONENTWISE with optional 1-based target blocks (one per field /
+ * per component; NULL = declaration order).  perm_out (nullable, ndofs entries) receives the permutation for
+ * fb2_ch_renumber.  Renumber before allocate_matrix: patterns and assemblers of the old numbering are stale. */
+enum { FB2_ORDER_PERMUTATION = 0, FB2_ORDER_FIELDWISE = 1, FB2_ORDER_COMPONENTWISE = 2 };
+int fb2_dh_renumber(fb2_dh* dh, int order, const int64_t* target_blocks, int ntargets, const int64_t* perm_in, int64_t* perm_out);
 int fb2_dh_info(fb2_dh* dh, int64_t* ndofs, int* ndofs_per_cell, int* nfields);
 /* celldofs!(dofs, dh, i) for all cells: ndofs_per_cell x ncells, 1-based (src/Dofs/DofHandler.jl:248-253) */
 int fb2_dh_export(fb2_dh* dh, int64_t* cell_dofs);
@@ -218,6 +224,8 @@ int fb2_ch_from_host(fb2_dh* dh, int64_t n, const int64_t* prescribed_dofs, cons
  * values (ncomponents x npoints) to fb2_ch_bc_set_values. */
 int fb2_ch_bc_points(fb2_ch* ch, int ibc, int64_t* npoints, double* x);
 int fb2_ch_bc_set_values(fb2_ch* ch, int ibc, int64_t npoints, const double* values);
+/* renumber!(dh, ch, perm): the ConstraintHandler half, src/Dofs/DofRenumbering.jl:92-125 */
+int fb2_ch_renumber(fb2_ch* ch, const int64_t* perm);
 int fb2_ch_info(fb2_ch* ch, int64_t* nprescribed);
 int fb2_ch_export(fb2_ch* ch, int64_t* prescribed_dofs, double* inhomogeneities);
 /* apply!(K, f, ch) / apply_zero!(K, f, ch): src/Dofs/ConstraintHandler.jl:710-740,755-768,931-958.

@@ -10,7 +10,7 @@ covers the whole grid: `__close!` :493-569, `_close_subdofhandler!` :576-676,
 """
 import numpy as np
 
-__all__ = ["DofHandler"]
+__all__ = ["renumber_permutation", "renumber", "DofHandler"]
 
 
 class DofHandler:
@@ -138,3 +138,54 @@ class DofHandler:
     def celldofs(self, ci):
         """1-based cell index -> dofs (1-based)."""
         return self.cell_dofs[ci - 1]
+
+
+# ---- renumber! --------------------------------------------------------------------------------------------------
+def renumber_permutation(dh, order, target_blocks=None):
+    """compute_renumber_permutation (src/Dofs/DofRenumbering.jl:167-246): order 'fieldwise' | 'componentwise' with
+    optional 1-based target blocks; returns perm (1-based: dof i becomes perm[i-1]).  Stable inside every block."""
+    fdims = [ip.vdim for ip in dh.field_ips]
+    ncomp = sum(fdims)
+    if order == "fieldwise":
+        tb = list(range(1, len(fdims) + 1)) if target_blocks is None else list(target_blocks)
+        if len(tb) != len(fdims):
+            raise ValueError("length of target block vector does not match number of fields and algebraic variables in DofHandler")
+        comp_blocks = [tb[i] for i, d in enumerate(fdims) for _ in range(d)]
+    elif order == "componentwise":
+        comp_blocks = list(range(1, ncomp + 1)) if target_blocks is None else list(target_blocks)
+        if len(comp_blocks) != ncomp:
+            raise ValueError("length of target block vector does not match number of components in DofHandler")
+    else:
+        raise ValueError(order)
+    if sorted(set(comp_blocks)) != list(range(1, max(comp_blocks) + 1)):
+        raise ValueError("target blocks must be continuous and in the range 1:maxblock")
+    nblocks = max(comp_blocks)
+    blocks = [set() for _ in range(nblocks)]
+    offs = np.concatenate([[0], np.cumsum(fdims)])
+    col = 0
+    for fi, ip in enumerate(dh.field_ips):
+        nloc = ip.base.nbase * ip.vdim
+        for j in range(nloc):
+            comp = j % fdims[fi] + offs[fi]
+            blocks[comp_blocks[comp] - 1].update(dh.cell_dofs[:, col + j].tolist())
+        col += nloc
+    iperm = []
+    for b in blocks:
+        iperm.extend(sorted(b))
+    assert len(iperm) == dh.ndofs
+    perm = np.empty(dh.ndofs, dtype=np.int64)
+    perm[np.asarray(iperm) - 1] = np.arange(1, dh.ndofs + 1)
+    return perm
+
+
+def renumber(dh, perm, ch=None):
+    """_renumber!(dh, perm) and _renumber!(ch, perm) (src/Dofs/DofRenumbering.jl:79-125)"""
+    perm = np.asarray(perm, dtype=np.int64)
+    assert sorted(perm.tolist()) == list(range(1, dh.ndofs + 1)), "input vector is not a permutation of length ndofs(dh)"
+    dh.cell_dofs = perm[dh.cell_dofs - 1]
+    if ch is not None:
+        p = perm[np.asarray(ch.prescribed_dofs) - 1]
+        o = np.argsort(p, kind="stable")
+        ch.prescribed_dofs = p[o]
+        ch.inhomogeneities = np.asarray(ch.inhomogeneities)[o]
+    return dh

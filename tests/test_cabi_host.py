@@ -233,3 +233,80 @@ def test_bad_arguments_are_reported(hctx):
         fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: 0, [3]))
     with pytest.raises(fb.FB2Error):
         fb.ConstraintHandler.from_arrays(dh, [3, 2], [0.0, 0.0])
+
+
+def test_renumber_goldens_through_cabi(hctx):
+    # renumber!(dh, ch, order): the reference's literal goldens (test/test_dofs.jl:260-316) and agreement with the oracle
+    from test_oracle_goldens import RENUMBER_GOLDENS
+
+    def make():
+        g = fb.generate_grid(fb.Quadrilateral, (2, 1), ctx=hctx)
+        q1 = fb.Lagrange(fb.RefQuadrilateral, 1)
+        dh = fb.close_(fb.add_(fb.add_(fb.DofHandler(g), "v", q1 ** 2), "s", q1))
+        ch = fb.ConstraintHandler(dh)
+        fb.add_(ch, fb.Dirichlet("v", fb.getfacetset(g, "left"), lambda x, t: 0, [2]))
+        fb.add_(ch, fb.Dirichlet("s", fb.getfacetset(g, "left"), lambda x, t: 0))
+        fb.close_(ch)
+        return dh, ch
+
+    for order, tb, c1, c2, pre in RENUMBER_GOLDENS:
+        dh, ch = make()
+        o = (fb.DofOrder.FieldWise if order == "fieldwise" else fb.DofOrder.ComponentWise)(tb)
+        fb.renumber_(dh, ch, o)
+        cd = dh.cell_dofs
+        assert list(cd[0]) == c1 and list(cd[1]) == c2, order
+        assert list(ch.prescribed_dofs) == pre, order
+    dh, ch = make()
+    cd0, pre0 = dh.cell_dofs.copy(), ch.prescribed_dofs.copy()
+    perm = np.random.default_rng(1).permutation(dh.ndofs) + 1
+    iperm = np.empty_like(perm)
+    iperm[perm - 1] = np.arange(1, dh.ndofs + 1)
+    fb.renumber_(dh, ch, perm)
+    assert not np.array_equal(dh.cell_dofs, cd0)
+    fb.renumber_(dh, ch, iperm)
+    assert np.array_equal(dh.cell_dofs, cd0) and np.array_equal(ch.prescribed_dofs, pre0)
+    with pytest.raises(fb.FB2Error):
+        fb.renumber_(dh, np.ones(dh.ndofs, dtype=np.int64))            # not a permutation
+    with pytest.raises(fb.FB2Error):
+        fb.renumber_(dh, fb.DofOrder.FieldWise([1, 3]))                # blocks must be contiguous 1:maxblock
+
+
+@pytest.mark.parametrize("ct,nel,fields", FIELDSETS)
+def test_renumber_matches_oracle(hctx, ct, nel, fields):
+    for order in ("fieldwise", "componentwise"):
+        g, dh, og, odh = _both_dh(hctx, ct, nel, fields)
+        perm = fb.renumber_(dh, (fb.DofOrder.FieldWise if order == "fieldwise" else fb.DofOrder.ComponentWise)())
+        operm = O.renumber_permutation(odh, order)
+        assert np.array_equal(perm, operm)
+        O.renumber(odh, operm)
+        assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+
+
+@pytest.mark.parametrize("ct,nel,fields", FIELDSETS)
+def test_update_after_renumber_matches_oracle(hctx, ct, nel, fields):
+    # a ConstraintHandler closed before renumber!(dh, ch, perm) must behave like one built from the new numbering
+    g, dh, og, odh = _both_dh(hctx, ct, nel, fields)
+    names = sorted(og.facetsets)
+    name, order, vdim = fields[0]
+
+    def f1(x, t):
+        return [np.sin(x[0] + 0.3 * k) + t + x[-1] for k in range(vdim)]
+
+    def f2(x, t):
+        return 0.25 * x[0] - x[1] + t
+    both = np.concatenate([og.facetsets[names[0]][:2], og.facetsets[names[1]]])
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet(name, fb.getfacetset(g, names[0]), f1))
+    fb.add_(ch, fb.Dirichlet(name, both, f2, [1]))
+    fb.close_(ch)
+    perm = fb.renumber_(dh, ch, np.random.default_rng(11).permutation(dh.ndofs) + 1)
+    O.renumber(odh, perm)
+    och = O.ConstraintHandler(odh)
+    och.add(O.Dirichlet(name, og.facetsets[names[0]], f1))
+    och.add(O.Dirichlet(name, both, f2, [1]))
+    och.close()
+    assert np.array_equal(ch.prescribed_dofs, och.prescribed_dofs)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+    fb.update_(ch, 0.75)
+    och.update(0.75)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)

@@ -914,3 +914,52 @@ def test_empty_inputs_are_no_ops(ctx):
     fb.apply_(K, f, ch)
     ctx.synchronize()
     assert float((K.nzval - ref).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,p", [
+    (fb.Hexahedron, (5, 4, 3), 1, 3, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}),
+    (fb.Hexahedron, (14, 12, 11), 1, 1, 2, "heat", {"k": 2.0, "source": 3.0}),      # tile kernel
+    (fb.Tetrahedron, (3, 3, 2), 2, 3, 4, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, -0.5, 0.0)}),
+])
+@pytest.mark.parametrize("order_kind", ["componentwise", "permutation"])
+def test_renumbered_problem_matches_oracle(ctx, ct, nel, order, vdim, qo, kind, p, order_kind):
+    # renumber!(dh, ch, order) (src/Dofs/DofRenumbering.jl:79-125) followed by pattern, assembly, update! and apply! on the
+    # device; the oracle renumbers its DofHandler first and builds its ConstraintHandler from the new numbering
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    elem, op = make_element(kind, p)
+
+    def val(x, t):
+        return [0.01 * x[1] + 0.02 * k + t for k in range(vdim)] if vdim > 1 else 0.3 * x[0] - x[1] + t
+    ch = fb.ConstraintHandler(dh)
+    fb.add_(ch, fb.Dirichlet("u", fb.getfacetset(g, "left"), val))
+    fb.close_(ch)
+    if order_kind == "componentwise":
+        perm = fb.renumber_(dh, ch, fb.DofOrder.ComponentWise())
+        assert np.array_equal(perm, O.renumber_permutation(odh, "componentwise"))
+    else:
+        perm = fb.renumber_(dh, ch, np.random.default_rng(5).permutation(dh.ndofs) + 1)
+    O.renumber(odh, perm)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    och = O.ConstraintHandler(odh)
+    och.add(O.Dirichlet("u", og.facetsets["left"], val))
+    och.close()
+    fb.update_(ch, 0.25)
+    och.update(0.25)
+    assert np.array_equal(ch.prescribed_dofs, och.prescribed_dofs)
+    assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+    K, oK = fb.allocate_matrix(dh), O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f, of = ctx.zeros(dh.ndofs), np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, kind, op)
+    for scatter in ("atomic", "colored"):
+        fb.assemble_(fb.start_assemble(K, f, scatter=scatter), elem, cv)
+        ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+        assert ok, (scatter, nrm)
+        ok, nrm = close(f.cpu().numpy(), of)
+        assert ok, (scatter, nrm)
+    fb.apply_(K, f, ch)
+    och.apply(oK, of)
+    ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+    assert ok, nrm
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, nrm

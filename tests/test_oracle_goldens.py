@@ -343,3 +343,43 @@ def test_facet_values_areas_and_normals():
                     tot += dG.sum()
                     assert np.allclose(n[..., 0], sign) and np.allclose(n[..., 1:], 0.0)
                 assert abs(tot - area) < 1e-13, (shape, name, tot)
+
+
+def _renumber_testdh():
+    # test/test_dofs.jl:230-246 (testdhch) without the AffineConstraint on dof 13 (out of scope)
+    grid = O.generate_grid("quadrilateral", (2, 1))
+    q1 = O.Lagrange("quadrilateral", 1)
+    dh = O.DofHandler(grid).add("v", q1 ** 2).add("s", q1).close()
+    ch = O.ConstraintHandler(dh)
+    ch.add(O.Dirichlet("v", grid.facetsets["left"], lambda x, t: 0, [2]))
+    ch.add(O.Dirichlet("s", grid.facetsets["left"], lambda x, t: 0))
+    ch.close()
+    return dh, ch
+
+
+RENUMBER_GOLDENS = [
+    # (order, target blocks, celldofs(1), celldofs(2), prescribed dofs without the image of the affine dof 13)
+    # test/test_dofs.jl:260-316
+    ("fieldwise", None, [1, 2, 3, 4, 5, 6, 7, 8, 13, 14, 15, 16], [3, 4, 9, 10, 11, 12, 5, 6, 14, 17, 18, 15], [2, 8, 13, 16]),
+    ("fieldwise", [2, 1], [7, 8, 9, 10, 11, 12, 13, 14, 1, 2, 3, 4], [9, 10, 15, 16, 17, 18, 11, 12, 2, 5, 6, 3], [1, 4, 8, 14]),
+    ("componentwise", None, [1, 7, 2, 8, 3, 9, 4, 10, 13, 14, 15, 16], [2, 8, 5, 11, 6, 12, 3, 9, 14, 17, 18, 15], [7, 10, 13, 16]),
+    ("componentwise", [3, 1, 2], [13, 1, 14, 2, 15, 3, 16, 4, 7, 8, 9, 10], [14, 2, 17, 5, 18, 6, 15, 3, 8, 11, 12, 9], [1, 4, 7, 10]),
+]
+
+
+def test_renumber_goldens():
+    # renumber!(dh, ch, DofOrder.FieldWise / ComponentWise): literal celldofs and prescribed dofs of test/test_dofs.jl:260-316
+    for order, tb, c1, c2, pre in RENUMBER_GOLDENS:
+        dh, ch = _renumber_testdh()
+        O.renumber(dh, O.renumber_permutation(dh, order, tb), ch)
+        assert list(dh.celldofs(1)) == c1 and list(dh.celldofs(2)) == c2, order
+        assert list(ch.prescribed_dofs) == pre, order
+    # roundtrip with an arbitrary permutation and its inverse (test/test_dofs.jl:183-206)
+    dh, ch = _renumber_testdh()
+    cd0, pre0 = dh.cell_dofs.copy(), np.array(ch.prescribed_dofs)
+    perm = np.random.default_rng(0).permutation(dh.ndofs) + 1
+    iperm = np.empty_like(perm)
+    iperm[perm - 1] = np.arange(1, dh.ndofs + 1)
+    O.renumber(dh, perm, ch)
+    O.renumber(dh, iperm, ch)
+    assert np.array_equal(dh.cell_dofs, cd0) and np.array_equal(ch.prescribed_dofs, pre0)
