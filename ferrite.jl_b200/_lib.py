@@ -135,6 +135,14 @@ _PROTOS = {
     "fb2_assemble_host_streamed": [_p, C.c_int, _p, C.c_size_t, _dp, _dp, _dp, _dp, C.POINTER(AsmOpts)],
     "fb2_assembler_coloring": [_p, _ip, _i32p],
     "fb2_scatter_host": [_p, _dp, _dp, _p, _p, C.POINTER(AsmOpts)],
+    "fb2_scatter_device": [_p, _p, _p, _p, _p, C.POINTER(AsmOpts)],
+    "fb2_ea_create": [_p, _p, _pp],
+    "fb2_ea_info": [_p, _i64p, _ip],
+    "fb2_ea_assemble": [_p, C.c_int, _p, C.c_size_t, _p, _p, _p],
+    "fb2_ea_mul": [_p, _p, _p, _p],
+    "fb2_ea_apply_local": [_p, _p, _p, _p, C.c_int],
+    "fb2_apply_assemble": [_p, _p, _p, C.c_int, _p, C.c_size_t, _p, _p, _p, C.c_int, C.POINTER(AsmOpts)],
+    "fb2_ea_destroy": [_p],
     "fb2_assembler_destroy": [_p],
     "fb2_ch_create": [_p, _pp],
     "fb2_ch_add_dirichlet": [_p, C.c_int, C.c_int, C.c_int64, _i64p, C.c_int, _ip, _ip],

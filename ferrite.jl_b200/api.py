@@ -611,6 +611,67 @@ def scatter_(assembler, Ke, fe=None):
            C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
 
 
+def scatter_device_(assembler, Kes, fes=None):
+    """assemble!(assembler, celldofs(cell), Ke, fe) for all cells from device-resident element matrices in the layout of
+    ElementAssembly.assemble (CUDA tensors: Kes[c, j, i] = Ke_c[i, j], fes[c, i])."""
+    h = assembler._handle(None)
+    opts = assembler._opts()
+    f = assembler.f
+    L.call("fb2_scatter_device", h, C.c_void_p(Kes.data_ptr()), C.c_void_p(fes.data_ptr()) if fes is not None else None,
+           C.c_void_p(assembler.K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
+    return assembler
+
+
+class ElementAssembly:
+    """"Element assembly" (docs/src/literate-howto/gpu_assembly.jl:265-304): all element matrices are kept on the device,
+    Kes (ncells, n, n) with Kes[c, j, i] = Ke_c[i, j] (column-major per cell) and fes (ncells, n); `mul` is the
+    matrix-free operator y = sum_e P_e' Ke P_e x, `apply_local_` is apply_local! on every cell."""
+
+    def __init__(self, dh, cv):
+        self.dh, self.cv = dh, cv
+        self.h = C.c_void_p()
+        L.call("fb2_ea_create", dh.h, cv.h, C.byref(self.h))
+        nc, n = C.c_int64(), C.c_int()
+        L.call("fb2_ea_info", self.h, C.byref(nc), C.byref(n))
+        self.ncells, self.n = nc.value, n.value
+
+    def assemble(self, element, u=None, Kes=None, fes=None):
+        ctx = self.dh.grid.ctx
+        if Kes is None:
+            Kes = ctx.zeros(self.ncells * self.n * self.n).view(self.ncells, self.n, self.n)
+        if fes is None:
+            fes = ctx.zeros(self.ncells * self.n).view(self.ncells, self.n)
+        L.call("fb2_ea_assemble", self.h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
+               C.c_void_p(u.data_ptr()) if u is not None else None, C.c_void_p(Kes.data_ptr()), C.c_void_p(fes.data_ptr()))
+        return Kes, fes
+
+    def mul(self, Kes, x, out=None):
+        y = out if out is not None else self.dh.grid.ctx.zeros(self.dh.ndofs)
+        L.call("fb2_ea_mul", self.h, C.c_void_p(Kes.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()))
+        return y
+
+    def apply_local_(self, Kes, fes, ch, applyzero=False):
+        L.call("fb2_ea_apply_local", self.h, ch.h, C.c_void_p(Kes.data_ptr()),
+               C.c_void_p(fes.data_ptr()) if fes is not None else None, 1 if applyzero else 0)
+
+    def __del__(self):
+        if _destroy is not None:
+            _destroy(self, "fb2_ea_destroy", [self.cv] + _chain(self, "dh"))
+
+
+def apply_assemble_(assembler, ch, element, cv, u=None, applyzero=False, ea=None):
+    """The cell loop with apply_assemble!(assembler, ch, celldofs(cell), Ke, fe; apply_zero) in place of assemble!
+    (src/assembler.jl:491-503): the Dirichlet conditions are applied element by element, no global apply! afterwards.
+    `ea`: an ElementAssembly to reuse between calls (its scratch holds all element matrices)."""
+    ea = ea if ea is not None else ElementAssembly(assembler.K.dh, cv)
+    h = assembler._handle(cv)
+    opts = assembler._opts()
+    L.call("fb2_apply_assemble", h, ea.h, ch.h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
+           C.c_void_p(u.data_ptr()) if u is not None else None, C.c_void_p(assembler.K.nzval.data_ptr()),
+           C.c_void_p(assembler.f.data_ptr()), 1 if applyzero else 0, C.byref(opts))
+    return ea
+
+
 def finish_assemble(assembler):
     assembler.K.dh.grid.ctx.synchronize()
     return assembler.K, assembler.f

@@ -529,38 +529,51 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     return launch_one(a, A, element, true, o.variant, !o.fillzero);
 }
 
+// assemble!(a, celldofs(cell), Ke, fe) for every cell from device-resident element matrices (the layout of fb2_ea_assemble:
+// Ke[c*n*n + j*n + i], fe[c*n + i]); src/assembler.jl:322-331,347-457 (zero skip, missing-entry error)
+extern "C" int fb2_scatter_device(fb2_assembler* a, const double* Ke_dev, const double* fe_dev, double* nzval_dev, double* f_dev,
+                                  const fb2_asm_opts* opts) {
+    FB2_CHECK(a && Ke_dev && nzval_dev, FB2_ERR_BAD_ARG, "fb2_scatter_device: null argument");
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+    if (opts) o = *opts;
+    const int n = a->n;
+    if (o.fillzero) {
+        FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+        if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)a->dh->ndofs * sizeof(double), ctx->stream));
+    }
+    const int64_t total = (int64_t)n * n * g->ncells;
+    if (total == 0) return FB2_OK;
+    k_scatter_batch<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(Ke_dev, f_dev ? fe_dev : nullptr, a->dh->d_cell_dofs,
+                                                                           a->pat->d_colptr, a->d_map, g->ncells, g->ncells_pad, n,
+                                                                           nzval_dev, f_dev, ctx->d_errflag);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return fb2_check_device_error(ctx);
+}
+
 extern "C" int fb2_scatter_host(fb2_assembler* a, const double* Ke, const double* fe, double* nzval_dev, double* f_dev,
                                 const fb2_asm_opts* opts) {
     FB2_CHECK(a && Ke && nzval_dev, FB2_ERR_BAD_ARG, "fb2_scatter_host: null argument");
     fb2_grid* g = a->dh->grid;
     fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
     FB2_CUDA(cudaSetDevice(ctx->device));
-    fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
-    if (opts) o = *opts;
     const int n = a->n;
     const size_t nk = (size_t)n * n * g->ncells, nf = (size_t)n * g->ncells;
     double *d_Ke = nullptr, *d_fe = nullptr;
-    FB2_CUDA(cudaMalloc(&d_Ke, nk * sizeof(double)));
+    FB2_CUDA(cudaMalloc(&d_Ke, std::max<size_t>(nk, 1) * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(d_Ke, Ke, nk * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && fe && f_dev) {
-        e = cudaMalloc(&d_fe, nf * sizeof(double));
+        e = cudaMalloc(&d_fe, std::max<size_t>(nf, 1) * sizeof(double));
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_fe, fe, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    }
-    if (e == cudaSuccess && o.fillzero) {
-        e = cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream);
-        if (e == cudaSuccess && f_dev) e = cudaMemsetAsync(f_dev, 0, (size_t)a->dh->ndofs * sizeof(double), ctx->stream);
-    }
-    if (e == cudaSuccess) {
-        const int64_t total = (int64_t)n * n * g->ncells;
-        k_scatter_batch<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(d_Ke, d_fe, a->dh->d_cell_dofs, a->pat->d_colptr,
-                                                                               a->d_map, g->ncells, g->ncells_pad, n, nzval_dev,
-                                                                               f_dev, ctx->d_errflag);
-        ctx->launches++;
-        e = cudaGetLastError();
     }
     int rc = FB2_OK;
     if (e != cudaSuccess) rc = fb2_fail(FB2_ERR_CUDA, "fb2_scatter_host: %s", cudaGetErrorString(e));
-    else rc = fb2_check_device_error(ctx);
+    else rc = fb2_scatter_device(a, d_Ke, d_fe, nzval_dev, f_dev, opts);
     cudaFree(d_Ke);
     cudaFree(d_fe);
     return rc;

@@ -250,3 +250,4 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 int fb2_check_device_error(fb2_ctx* ctx);
 int fb2_coloring_build(fb2_assembler* a);
+int fb2_ch_sync_device(fb2_ch* ch);      // upload the inhomogeneities if update! changed them

@@ -339,6 +339,9 @@ extern "C" int fb2_ch_bc_set_values(fb2_ch* ch, int ibc, int64_t npoints, const 
     return FB2_OK;
 }
 
+// inhomogeneities of the current update! on the device (used by element_assembly.cu)
+int fb2_ch_sync_device(fb2_ch* ch) { return upload_inhom(ch); }
+
 extern "C" int fb2_ch_info(fb2_ch* ch, int64_t* nprescribed) {
     FB2_CHECK(ch, FB2_ERR_BAD_ARG, "fb2_ch_info: null handle");
     if (nprescribed) *nprescribed = (int64_t)(ch->closed ? ch->prescribed.size() : ch->insertion.size());

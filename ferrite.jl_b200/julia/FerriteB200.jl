@@ -199,6 +199,64 @@ function mul_device!(y_dev::Ptr{Float64}, K::B200Matrix, nzval_dev::Ptr{Float64}
     return y_dev
 end
 
+# ---- element assembly (docs/src/literate-howto/gpu_assembly.jl:265-304) and apply_assemble! (src/assembler.jl:491-503) -----
+# Kes_dev (n x n x ncells) / fes_dev (n x ncells) are device buffers of the caller, e.g. CUDA.jl arrays passed as pointers.
+mutable struct ElementAssembly
+    h::Ptr{Cvoid}
+    prob::DeviceProblem
+    function ElementAssembly(prob::DeviceProblem)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        @fb2 fb2_ea_create (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) prob.dh prob.cv r
+        return finalizer(e -> ccall((:fb2_ea_destroy, LIB), Cint, (Ptr{Cvoid},), e.h), new(r[], prob))
+    end
+end
+
+function element_matrices!(Kes_dev::Ptr{Float64}, fes_dev::Ptr{Float64}, ea::ElementAssembly, element; u_dev::Ptr{Float64} = Ptr{Float64}(C_NULL))
+    params = Ref(element)
+    GC.@preserve params begin
+        @fb2 fb2_ea_assemble (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}) ea.h elem_id(element) params sizeof(element) u_dev Kes_dev fes_dev
+    end
+    return Kes_dev, fes_dev
+end
+
+# mul!(y, A, x) of the matrix-free operator (gpu_assembly.jl:287-304)
+function mul_device!(y_dev::Ptr{Float64}, ea::ElementAssembly, Kes_dev::Ptr{Float64}, x_dev::Ptr{Float64})
+    @fb2 fb2_ea_mul (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}) ea.h Kes_dev x_dev y_dev
+    return y_dev
+end
+
+# apply_local!(Ke, fe, celldofs(cell), ch; apply_zero) for every cell (src/Dofs/ConstraintHandler.jl:1750-1822)
+function apply_local_device!(Kes_dev::Ptr{Float64}, fes_dev::Ptr{Float64}, ea::ElementAssembly, ch::ConstraintHandler; apply_zero::Bool = false)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_ch_from_host (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) ea.prob.dh length(ch.prescribed_dofs) ch.prescribed_dofs ch.inhomogeneities c
+    @fb2 fb2_ea_apply_local (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint) ea.h c[] Kes_dev fes_dev apply_zero
+    ccall((:fb2_ch_destroy, LIB), Cint, (Ptr{Cvoid},), c[])
+    return Kes_dev, fes_dev
+end
+
+# assemble!(assembler, celldofs(cell), Ke, fe) for every cell from the stored element matrices
+function scatter_device!(K::B200Matrix, nzval_dev::Ptr{Float64}, f_dev::Ptr{Float64}, Kes_dev::Ptr{Float64}, fes_dev::Ptr{Float64}; fillzero::Bool = true)
+    opts = Ref(fb2_asm_opts(fillzero, 0, 0, 0))
+    GC.@preserve opts begin
+        @fb2 fb2_scatter_device (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{fb2_asm_opts}) K.assembler Kes_dev fes_dev nzval_dev f_dev opts
+    end
+    return nzval_dev, f_dev
+end
+
+# the cell loop with apply_assemble!(assembler, ch, celldofs(cell), Ke, fe; apply_zero) in place of assemble!
+function Ferrite.apply_assemble!(a::B200Assembler, ea::ElementAssembly, ch::ConstraintHandler, element, nzval_dev::Ptr{Float64}, f_dev::Ptr{Float64};
+        u_dev::Ptr{Float64} = Ptr{Float64}(C_NULL), apply_zero::Bool = false)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_ch_from_host (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) ea.prob.dh length(ch.prescribed_dofs) ch.prescribed_dofs ch.inhomogeneities c
+    opts = Ref(fb2_asm_opts(a.fillzero, 0, 0, 0))
+    params = Ref(element)
+    GC.@preserve params opts begin
+        @fb2 fb2_apply_assemble (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{fb2_asm_opts}) a.K.assembler ea.h c[] elem_id(element) params sizeof(element) u_dev nzval_dev f_dev apply_zero opts
+    end
+    ccall((:fb2_ch_destroy, LIB), Cint, (Ptr{Cvoid},), c[])
+    return a
+end
+
 # ---- partition plan of rank `rank` of `nparts` (one process per GPU): METIS_PartMeshDual inside the library, or the
 # cell -> rank vector of any partitioner (0-based ranks) -----------------------------------------------------------
 function partition_plan(global_dh_handle::Ptr{Cvoid}, nparts::Integer, rank::Integer; cell_owner::Union{Nothing, Vector{Int32}} = nothing)

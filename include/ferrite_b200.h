@@ -204,6 +204,9 @@ int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color);
  * (Ke: n x n x ncells column-major, fe: n x ncells, host) -- src/assembler.jl:322-331 */
 int fb2_scatter_host(fb2_assembler* a, const double* Ke, const double* fe, double* nzval_dev, double* f_dev,
                      const fb2_asm_opts* opts);
+/* the same from device-resident element matrices (layout of fb2_ea_assemble) */
+int fb2_scatter_device(fb2_assembler* a, const double* Ke_dev, const double* fe_dev, double* nzval_dev, double* f_dev,
+                       const fb2_asm_opts* opts);
 int fb2_assembler_destroy(fb2_assembler* a);
 
 /* ---- ConstraintHandler: Dirichlet / close! / update! / apply! ---------------------------- */
@@ -284,6 +287,28 @@ int fb2_csr_values(fb2_pattern* p, const double* nzval_csc_dev, double* nzval_cs
  * iters / resnorm (nullable) receive the iteration count and the final residual norm. */
 int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_dev, double* x_dev, double reltol, double abstol,
            int maxiter, int jacobi, int symmetric, int* iters, double* resnorm);
+
+/* ---- element assembly, matrix-free operator, apply_local! / apply_assemble! -------------- */
+/* All element matrices are kept instead of being summed into a CSC (docs/src/literate-howto/gpu_assembly.jl:265-304):
+ * Kes is n x n x ncells (column-major per cell, Kes[c*n*n + j*n + i] = Ke_c[i, j]), fes is n x ncells; both device buffers
+ * owned by the caller.  The same fused kernels as fb2_assemble compute them. */
+typedef struct fb2_ea fb2_ea;
+int fb2_ea_create(fb2_dh* dh, fb2_cv* cv, fb2_ea** out);
+int fb2_ea_info(fb2_ea* ea, int64_t* ncells, int* ndofs_per_cell);
+/* element routine of the kernel menu for every cell; u_dev (global numbering) for FB2_ELEM_NEOHOOKE; fes_dev nullable */
+int fb2_ea_assemble(fb2_ea* ea, int element, const void* params, size_t params_bytes, const double* u_dev, double* Kes_dev,
+                    double* fes_dev);
+/* y = sum_e P_e' Ke P_e x, the operator of gpu_assembly.jl:287-304 (y is overwritten; equals K * x of the assembled matrix) */
+int fb2_ea_mul(fb2_ea* ea, const double* Kes_dev, const double* x_dev, double* y_dev);
+/* apply_local!(Ke, fe, celldofs(cell), ch; apply_zero) for every cell, Dirichlet constraints
+ * (src/Dofs/ConstraintHandler.jl:1750-1822): fe -= v Ke[:, l], rows/columns of prescribed local dofs zeroed, the diagonal
+ * set to meandiag(Ke) and fe[l] = v meandiag(Ke).  fes_dev nullable. */
+int fb2_ea_apply_local(fb2_ea* ea, fb2_ch* ch, double* Kes_dev, double* fes_dev, int applyzero);
+/* apply_assemble!(assembler, ch, celldofs(cell), Ke, fe; apply_zero) for every cell (src/assembler.jl:491-503):
+ * fb2_ea_assemble + fb2_ea_apply_local + fb2_scatter_device into the caller's nzval / f */
+int fb2_apply_assemble(fb2_assembler* a, fb2_ea* ea, fb2_ch* ch, int element, const void* params, size_t params_bytes,
+                       const double* u_dev, double* nzval_dev, double* f_dev, int applyzero, const fb2_asm_opts* opts);
+int fb2_ea_destroy(fb2_ea* ea);
 
 /* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
 typedef struct fb2_part fb2_part;

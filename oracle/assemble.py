@@ -13,7 +13,7 @@ import numpy as np
 
 from .element import ELEMENTS
 
-__all__ = ["start_assemble", "assemble_cell", "assemble_global", "MissingEntryError"]
+__all__ = ["start_assemble", "assemble_cell", "assemble_global", "element_matrices", "ea_mul", "MissingEntryError"]
 
 
 class MissingEntryError(KeyError):
@@ -71,3 +71,28 @@ def assemble_global(dh, cv, K, f, element="heat", params=None, u=None, chunk=409
         if f is not None:
             np.add.at(f, (cd - 1).ravel(), fe.ravel())
     return K, f
+
+
+def element_matrices(dh, cv, element="heat", params=None, u=None, chunk=4096):
+    """Kes (ncells, n, n) and fes (ncells, n): the element routine of every cell, nothing scattered -- the "element
+    assembly" storage of docs/src/literate-howto/gpu_assembly.jl:265-285."""
+    fn = ELEMENTS[element] if isinstance(element, str) else element
+    grid = dh.grid
+    n = dh.ndofs_per_cell
+    Kes = np.zeros((grid.ncells, n, n))
+    fes = np.zeros((grid.ncells, n))
+    for s in range(0, grid.ncells, chunk):
+        sl = slice(s, min(s + chunk, grid.ncells))
+        x = grid.nodes[grid.cells[sl] - 1]
+        ue = None if u is None else u[dh.cell_dofs[sl] - 1]
+        Kes[sl], fes[sl] = fn(cv, x, params, ue)
+    return Kes, fes
+
+
+def ea_mul(dh, Kes, x):
+    """y = sum_e P_e' Ke P_e x in ascending cell order (gpu_assembly.jl:287-304)"""
+    y = np.zeros(dh.ndofs)
+    for c in range(dh.grid.ncells):
+        d = dh.cell_dofs[c] - 1
+        np.add.at(y, d, Kes[c] @ x[d])
+    return y

@@ -14,7 +14,7 @@ import numpy as np
 
 from .interpolations import geometric_interpolation
 
-__all__ = ["Dirichlet", "ConstraintHandler"]
+__all__ = ["Dirichlet", "ConstraintHandler", "apply_local", "apply_assemble"]
 
 
 class Dirichlet:
@@ -167,3 +167,35 @@ class ConstraintHandler:
     def apply_vec(self, u, applyzero=False):
         u[self.prescribed_dofs - 1] = 0.0 if applyzero else self.inhomogeneities
         return u
+
+
+def apply_local(Ke, fe, dofs, ch, applyzero=False):
+    """apply_local!(Ke, fe, global_dofs, ch; apply_zero) for Dirichlet constraints, in place
+    (src/Dofs/ConstraintHandler.jl:1762-1822 `_apply_local!`, steps 1, 2 and 4; step 3 is the affine condensation).
+    dofs 1-based."""
+    n = len(dofs)
+    index = {int(d): i for i, d in enumerate(ch.prescribed_dofs)}
+    local = [(l, index[int(d)]) for l, d in enumerate(dofs) if int(d) in index]
+    if not local:
+        return
+    for l, i in local:
+        v = ch.inhomogeneities[i]
+        if not applyzero and v != 0:
+            for j in range(n):
+                fe[j] -= v * Ke[j, l]
+    m = 0.0
+    for i in range(n):                  # meandiag, :952-958
+        m += abs(Ke[i, i])
+    m /= n
+    for l, i in local:
+        Ke[:, l] = 0.0
+        Ke[l, :] = 0.0
+        Ke[l, l] = m
+        fe[l] = 0.0 if applyzero else ch.inhomogeneities[i] * m
+
+
+def apply_assemble(K, f, ch, dofs, Ke, fe, applyzero=False):
+    """apply_assemble!(assembler, ch, global_dofs, Ke, fe; apply_zero), src/assembler.jl:491-503 (destructive on Ke, fe)"""
+    from .assemble import assemble_cell
+    apply_local(Ke, fe, dofs, ch, applyzero)
+    assemble_cell(K, f, dofs, Ke, fe)

@@ -310,3 +310,13 @@ def test_update_after_renumber_matches_oracle(hctx, ct, nel, fields):
     fb.update_(ch, 0.75)
     och.update(0.75)
     assert np.array_equal(ch.inhomogeneities, och.inhomogeneities)
+
+
+def test_element_assembly_needs_a_device(hctx):
+    # no CPU fallback: the element-assembly entry points refuse a host-only context
+    g = fb.generate_grid(fb.Quadrilateral, (2, 2), ctx=hctx)
+    ip = fb.Lagrange(fb.RefQuadrilateral, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip, ctx=hctx)
+    with pytest.raises(fb.FB2Error):
+        fb.ElementAssembly(dh, cv)

@@ -383,3 +383,46 @@ def test_renumber_goldens():
     O.renumber(dh, perm, ch)
     O.renumber(dh, iperm, ch)
     assert np.array_equal(dh.cell_dofs, cd0) and np.array_equal(ch.prescribed_dofs, pre0)
+
+
+def test_local_application_of_bc_golden():
+    # test/test_constraints.jl:1425-1610 "local application of bc": 5x5 quads, Q1, u(left) = 0, u(right) = 1, element with
+    # conductivity k = cellid and source b = 1/cellid; literal goldens norm(u) = 3.8249286998373586 (apply!) and
+    # 0.06401424182205259 (apply_zero!), and the identities between apply!, apply_assemble! and apply_local! + assemble!
+    grid = O.generate_grid("quadrilateral", (5, 5))
+    ip = O.Lagrange("quadrilateral", 1)
+    dh = O.DofHandler(grid).add("u", ip).close()
+    ch = O.ConstraintHandler(dh)
+    ch.add(O.Dirichlet("u", grid.facetsets["left"], lambda x, t: 0))
+    ch.add(O.Dirichlet("u", grid.facetsets["right"], lambda x, t: 1))
+    ch.close()
+    ch.update(0.0)
+    cv = O.CellValues(O.QuadratureRule("quadrilateral", 2), ip)
+    Kes, fes = O.element_matrices(dh, cv, "heat", {"k": 1.0, "source": 1.0})
+    ids = np.arange(1, grid.ncells + 1, dtype=float)
+    Kes *= ids[:, None, None]
+    fes /= ids[:, None]
+    pd = ch.prescribed_dofs - 1
+    fd = np.setdiff1d(np.arange(dh.ndofs), pd)
+    for azero, golden in ((False, 3.8249286998373586), (True, 0.06401424182205259)):
+        Ks, Kc, Kl = O.allocate_matrix(dh), O.allocate_matrix(dh), O.allocate_matrix(dh)
+        fs, fc, fl = np.zeros(dh.ndofs), np.zeros(dh.ndofs), np.zeros(dh.ndofs)
+        for c in range(grid.ncells):
+            dofs = dh.cell_dofs[c]
+            O.assemble_cell(Ks, fs, dofs, Kes[c], fes[c])
+            O.apply_assemble(Kc, fc, ch, dofs, Kes[c].copy(), fes[c].copy(), applyzero=azero)
+            ke, fe = Kes[c].copy(), fes[c].copy()
+            O.apply_local(ke, fe, dofs, ch, applyzero=azero)
+            O.assemble_cell(Kl, fl, dofs, ke, fe)
+        ch.apply(Ks, fs, applyzero=azero)
+        As, Ac, Al = Ks.toscipy().toarray(), Kc.toscipy().toarray(), Kl.toscipy().toarray()
+        assert np.array_equal(Ac, Al) and np.array_equal(fc, fl)
+        assert np.allclose(As[np.ix_(fd, fd)], Ac[np.ix_(fd, fd)], rtol=1e-13, atol=0)
+        assert np.allclose(fs[fd], fc[fd], rtol=1e-12, atol=1e-14)
+        for A, f in ((As, fs), (Ac, fc)):
+            P = A[np.ix_(pd, pd)]
+            assert np.array_equal(P, np.diag(np.diag(P)))
+            assert np.all(A[np.ix_(pd, fd)] == 0) and np.all(A[np.ix_(fd, pd)] == 0)
+            assert np.allclose(f[pd] / np.diag(P), 0.0 if azero else ch.inhomogeneities, rtol=1e-14, atol=0)
+            u = np.linalg.solve(A, f)
+            assert abs(np.linalg.norm(u) - golden) < 1e-12 * golden, (azero, np.linalg.norm(u))
