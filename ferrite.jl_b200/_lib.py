@@ -142,6 +142,9 @@ _PROTOS = {
     "fb2_ea_mul": [_p, _p, _p, _p],
     "fb2_ea_apply_local": [_p, _p, _p, _p, C.c_int],
     "fb2_apply_assemble": [_p, _p, _p, C.c_int, _p, C.c_size_t, _p, _p, _p, C.c_int, C.POINTER(AsmOpts)],
+    "fb2_ea_diag": [_p, _p, _p],
+    "fb2_ea_rhs": [_p, _p, _p],
+    "fb2_ea_cg": [_p, _p, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, _ip, _dp],
     "fb2_ea_destroy": [_p],
     "fb2_assembler_destroy": [_p],
     "fb2_ch_create": [_p, _pp],

@@ -650,6 +650,26 @@ class ElementAssembly:
         L.call("fb2_ea_mul", self.h, C.c_void_p(Kes.data_ptr()), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()))
         return y
 
+    def diag(self, Kes, out=None):
+        d = out if out is not None else self.dh.grid.ctx.zeros(self.dh.ndofs)
+        L.call("fb2_ea_diag", self.h, C.c_void_p(Kes.data_ptr()), C.c_void_p(d.data_ptr()))
+        return d
+
+    def rhs(self, fes, out=None):
+        """f = sum_e P_e' fe"""
+        f = out if out is not None else self.dh.grid.ctx.zeros(self.dh.ndofs)
+        L.call("fb2_ea_rhs", self.h, C.c_void_p(fes.data_ptr()), C.c_void_p(f.data_ptr()))
+        return f
+
+    def cg_(self, x, Kes, b, reltol=None, abstol=0.0, maxiter=None, jacobi=False):
+        """IterativeSolvers.cg!(x, A, b) with the matrix-free operator A = (this, Kes); returns (iterations, residual norm)."""
+        reltol = float(np.sqrt(np.finfo(np.float64).eps)) if reltol is None else float(reltol)
+        maxiter = self.dh.ndofs if maxiter is None else int(maxiter)
+        it, res = C.c_int(), C.c_double()
+        L.call("fb2_ea_cg", self.h, C.c_void_p(Kes.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(x.data_ptr()), reltol,
+               float(abstol), maxiter, 1 if jacobi else 0, C.byref(it), C.byref(res))
+        return it.value, res.value
+
     def apply_local_(self, Kes, fes, ch, applyzero=False):
         L.call("fb2_ea_apply_local", self.h, ch.h, C.c_void_p(Kes.data_ptr()),
                C.c_void_p(fes.data_ptr()) if fes is not None else None, 1 if applyzero else 0)

@@ -260,26 +260,39 @@ bool try_scalar(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int var
     return false;
 }
 
-__global__ void k_scatter_batch(const double* __restrict__ Ke, const double* __restrict__ fe, const int32_t* __restrict__ cell_dofs,
-                                const int64_t* __restrict__ colptr, const uint16_t* __restrict__ map, int64_t ncells,
-                                int64_t ncells_pad, int n, double* __restrict__ nzval, double* __restrict__ f, int* errflag) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t per = (int64_t)n * n;
-    if (t < per * ncells) {
-        int64_t c = t % ncells;
-        int e = (int)(t / ncells);
-        int j = e / n;
-        double v = Ke[(size_t)c * per + e];
-        if (v != 0.0) {
-            unsigned off = map[(size_t)e * ncells_pad + c];
-            if (off == 0xFFFFu) fb2_flag_error(errflag, FB2_ERR_MISSING_PATTERN_ENTRY, c);
-            else atomicAdd(nzval + colptr[cell_dofs[(size_t)j * ncells_pad + c]] + off, v);
-        }
+// assemble! of stored element matrices.  Ke is cell-major (Ke[c][e], e = j*n + i) while the offset map and the dofs are
+// entry-major SoA ([e][cell]); a CTA therefore takes 32 cells x EC entries, reads the Ke tile with consecutive lanes along e,
+// turns it in shared memory and scatters with consecutive lanes along the cells, so that both sides are coalesced.
+constexpr int SB_EC = 128;   // entries per tile
+__global__ void __launch_bounds__(256) k_scatter_batch(const double* __restrict__ Ke, const double* __restrict__ fe,
+                                                       const int32_t* __restrict__ cell_dofs, const int64_t* __restrict__ colptr,
+                                                       const uint16_t* __restrict__ map, int64_t ncells, int64_t ncells_pad, int n,
+                                                       double* __restrict__ nzval, double* __restrict__ f, int* errflag) {
+    __shared__ double s_v[32][SB_EC + 1];
+    const int per = n * n;
+    const int64_t c0 = (int64_t)blockIdx.x * 32;
+    const int ncl = (int)min((int64_t)32, ncells - c0);
+    const int e0 = blockIdx.y * SB_EC;
+    const int ne = min(SB_EC, per - e0);
+    for (int idx = threadIdx.x; idx < ncl * ne; idx += 256) {
+        const int cl = idx / ne, ee = idx - cl * ne;
+        s_v[cl][ee] = __ldcs(Ke + (size_t)(c0 + cl) * per + e0 + ee);
     }
-    if (f != nullptr && fe != nullptr && t < (int64_t)n * ncells) {
-        int64_t c = t % ncells;
-        int i = (int)(t / ncells);
-        atomicAdd(f + cell_dofs[(size_t)i * ncells_pad + c], fe[(size_t)c * n + i]);
+    __syncthreads();
+    const int cl = threadIdx.x & 31;
+    if (cl < ncl) {
+        const int64_t c = c0 + cl;
+        for (int ee = threadIdx.x >> 5; ee < ne; ee += 8) {
+            const double v = s_v[cl][ee];
+            if (v != 0.0) {
+                const int e = e0 + ee;
+                const unsigned off = map[(size_t)e * ncells_pad + c];
+                if (off == 0xFFFFu) fb2_flag_error(errflag, FB2_ERR_MISSING_PATTERN_ENTRY, c);
+                else atomicAdd(nzval + colptr[cell_dofs[(size_t)(e / n) * ncells_pad + c]] + off, v);
+            }
+        }
+        if (f != nullptr && fe != nullptr && blockIdx.y == 0)
+            for (int i = threadIdx.x >> 5; i < n; i += 8) atomicAdd(f + cell_dofs[(size_t)i * ncells_pad + c], fe[(size_t)c * n + i]);
     }
 }
 
@@ -547,7 +560,8 @@ extern "C" int fb2_scatter_device(fb2_assembler* a, const double* Ke_dev, const 
     }
     const int64_t total = (int64_t)n * n * g->ncells;
     if (total == 0) return FB2_OK;
-    k_scatter_batch<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(Ke_dev, f_dev ? fe_dev : nullptr, a->dh->d_cell_dofs,
+    const dim3 grid((unsigned)((g->ncells + 31) / 32), (unsigned)((n * n + SB_EC - 1) / SB_EC));
+    k_scatter_batch<<<grid, 256, 0, ctx->stream>>>(Ke_dev, f_dev ? fe_dev : nullptr, a->dh->d_cell_dofs,
                                                                            a->pat->d_colptr, a->d_map, g->ncells, g->ncells_pad, n,
                                                                            nzval_dev, f_dev, ctx->d_errflag);
     ctx->launches++;

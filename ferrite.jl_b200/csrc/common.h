@@ -238,6 +238,20 @@ struct fb2_ch {
     bool inhom_dirty = true;
 };
 
+// element assembly (element_assembly.cu)
+struct fb2_ea {
+    fb2_dh* dh = nullptr;          // the caller's DofHandler (borrowed)
+    fb2_cv* cv = nullptr;          // borrowed
+    fb2_dh* bdh = nullptr;         // broken twin
+    fb2_pattern* bpat = nullptr;   // block-diagonal pattern of the twin
+    fb2_assembler* basm = nullptr;
+    int n = 0;                     // dofs per cell
+    double* d_ub = nullptr;        // state in the broken numbering (lazy)
+    double* d_work = nullptr;      // CG work vectors of fb2_ea_cg (lazy)
+    size_t work_count = 0;
+    struct EaSplit* split = nullptr;   // fb2_apply_assemble: boundary-layer problem of the last ConstraintHandler (lazy)
+};
+
 // ---- device-side helpers implemented in .cu files ------------------------------------------
 int fb2_pattern_build_device(fb2_pattern* p);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len

@@ -15,17 +15,6 @@
 
 #include <algorithm>
 
-struct fb2_ea {
-    fb2_dh* dh = nullptr;          // the caller's DofHandler (borrowed)
-    fb2_cv* cv = nullptr;          // borrowed
-    fb2_dh* bdh = nullptr;         // broken twin
-    fb2_pattern* bpat = nullptr;   // block-diagonal pattern of the twin
-    fb2_assembler* basm = nullptr;
-    int n = 0;                     // dofs per cell
-    double* d_ub = nullptr;        // state in the broken numbering (lazy)
-    struct EaSplit* split = nullptr;   // fb2_apply_assemble: boundary-layer problem of the last ConstraintHandler (lazy)
-};
-
 // fb2_apply_assemble touches element matrices only where apply_local! changes them: the cells that own a prescribed dof.
 // They form a sub-grid (own connectivity, the parent's coordinates) with its own element assembly; all other cells go
 // through the fused kernel of the caller's assembler, restricted to the interior list.
@@ -78,6 +67,27 @@ __global__ void __launch_bounds__(256) k_ea_mul(const double* __restrict__ Kes, 
     }
     if (j < n) s0 = fma(__ldcs(K + (size_t)j * n), __ldg(x + cell_dofs[(size_t)j * ncells_pad + c]), s0);
     atomicAdd(y + cell_dofs[(size_t)i * ncells_pad + c], s0 + s1);
+}
+
+// diag[dof(c, i)] += Ke_c[i, i]: the diagonal of the operator (Jacobi preconditioner of the matrix-free CG)
+__global__ void k_ea_diag(const double* __restrict__ Kes, const int32_t* __restrict__ cell_dofs, int64_t ncells, int64_t ncells_pad, int n,
+                          double* __restrict__ diag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells * n) return;
+    const int64_t c = t / n;
+    const int i = (int)(t - c * n);
+    atomicAdd(diag + cell_dofs[(size_t)i * ncells_pad + c], Kes[(size_t)c * n * n + (size_t)i * n + i]);
+}
+
+// f[dof(c, i)] += fe_c[i]
+__global__ void k_ea_rhs(const double* __restrict__ fes, const int32_t* __restrict__ cell_dofs, int64_t ncells, int64_t ncells_pad, int n,
+                         double* __restrict__ f) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells * n) return;
+    const int64_t c = t / n;
+    const int i = (int)(t - c * n);
+    const double v = fes[t];
+    if (v != 0.0) atomicAdd(f + cell_dofs[(size_t)i * ncells_pad + c], v);
 }
 
 __device__ __forceinline__ int64_t ea_find(const int32_t* __restrict__ prescribed, int64_t np, int32_t d) {
@@ -229,6 +239,7 @@ extern "C" int fb2_ea_destroy(fb2_ea* ea) {
     if (ea->bpat) fb2_pattern_destroy(ea->bpat);
     if (ea->bdh) fb2_dh_destroy(ea->bdh);
     cudaFree(ea->d_ub);
+    cudaFree(ea->d_work);
     split_free(ea->split);
     delete ea;
     return FB2_OK;
@@ -303,6 +314,32 @@ extern "C" int fb2_ea_mul(fb2_ea* ea, const double* Kes_dev, const double* x_dev
     FB2_CUDA(cudaMemsetAsync(y_dev, 0, (size_t)ea->dh->ndofs * sizeof(double), ctx->stream));
     const int64_t tot = g->ncells * ea->n;
     k_ea_mul<<<nblocks(tot, 256), 256, 0, ctx->stream>>>(Kes_dev, x_dev, ea->dh->d_cell_dofs, g->ncells, g->ncells_pad, ea->n, y_dev);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+extern "C" int fb2_ea_diag(fb2_ea* ea, const double* Kes_dev, double* diag_dev) {
+    FB2_CHECK(ea && Kes_dev && diag_dev, FB2_ERR_BAD_ARG, "fb2_ea_diag: null argument");
+    fb2_grid* g = ea->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaMemsetAsync(diag_dev, 0, (size_t)ea->dh->ndofs * sizeof(double), ctx->stream));
+    const int64_t tot = g->ncells * ea->n;
+    k_ea_diag<<<nblocks(tot, 256), 256, 0, ctx->stream>>>(Kes_dev, ea->dh->d_cell_dofs, g->ncells, g->ncells_pad, ea->n, diag_dev);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    return FB2_OK;
+}
+
+extern "C" int fb2_ea_rhs(fb2_ea* ea, const double* fes_dev, double* f_dev) {
+    FB2_CHECK(ea && fes_dev && f_dev, FB2_ERR_BAD_ARG, "fb2_ea_rhs: null argument");
+    fb2_grid* g = ea->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)ea->dh->ndofs * sizeof(double), ctx->stream));
+    const int64_t tot = g->ncells * ea->n;
+    k_ea_rhs<<<nblocks(tot, 256), 256, 0, ctx->stream>>>(fes_dev, ea->dh->d_cell_dofs, g->ncells, g->ncells_pad, ea->n, f_dev);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;

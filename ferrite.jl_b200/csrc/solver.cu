@@ -254,33 +254,31 @@ extern "C" int fb2_csr_values(fb2_pattern* p, const double* nzval_csc_dev, doubl
     return FB2_OK;
 }
 
-extern "C" int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_dev, double* x_dev, double reltol, double abstol,
-                      int maxiter, int jacobi, int symmetric, int* iters, double* resnorm) {
-    FB2_CHECK(p && nzval_dev && b_dev && x_dev, FB2_ERR_BAD_ARG, "fb2_cg: null argument");
-    fb2_ctx* ctx = p->dh->grid->ctx;
-    FB2_NEED_DEVICE(ctx);
-    FB2_CHECK(maxiter >= 0 && reltol >= 0 && abstol >= 0, FB2_ERR_BAD_ARG, "fb2_cg: bad tolerance / iteration limit");
-    FB2_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = p->n;
+namespace {
+
+__global__ void k_reciprocal(double* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = d[i] != 0.0 ? 1.0 / d[i] : 1.0;
+}
+
+// Preconditioned CG on work vectors [r | z | p | Ap | dinv | partials]; A_times(v, out) applies the operator, fill_dinv (jacobi)
+// writes the inverse diagonal.  Stopping rule of IterativeSolvers.cg!: ||r|| <= max(reltol ||r0||, abstol).
+template <class Op, class Dinv>
+int cg_run(fb2_ctx* ctx, int64_t n, double** work, size_t* work_count, Op A_times, int jacobi, Dinv fill_dinv, const double* b_dev,
+           double* x_dev, double reltol, double abstol, int maxiter, int* iters, double* resnorm) {
     cudaStream_t st = ctx->stream;
     const size_t need = (size_t)5 * n + 3 * RB + 8;
-    if (p->work_count < need) {
-        cudaFree(p->d_work);
-        p->d_work = nullptr;
-        p->work_count = 0;
-        FB2_CUDA(cudaMalloc(&p->d_work, need * sizeof(double)));
-        p->work_count = need;
+    if (*work_count < need) {
+        cudaFree(*work);
+        *work = nullptr;
+        *work_count = 0;
+        FB2_CUDA(cudaMalloc(work, need * sizeof(double)));
+        *work_count = need;
     }
-    double *r = p->d_work, *z = r + n, *pp = z + n, *Ap = pp + n, *dinv = Ap + n, *part1 = dinv + n, *part2 = part1 + RB, *part3 = part2 + RB,
+    double *r = *work, *z = r + n, *pp = z + n, *Ap = pp + n, *dinv = Ap + n, *part1 = dinv + n, *part2 = part1 + RB, *part3 = part2 + RB,
            *sc = part3 + RB;
-    if (!symmetric) FB2_TRY(ensure_tperm(p));
-    auto A_times = [&](const double* v, double* out) -> int {
-        // K symmetric in value: K v = K^T v, the plain gather; otherwise through the transpose permutation
-        if (symmetric) return launch_gather<false>(p, nzval_dev, v, out);
-        return fb2_spmv(p, nzval_dev, v, out, 0);
-    };
     const int nb = (int)std::min<int64_t>(RB, std::max<int64_t>(1, (n + 255) / 256));
-    if (jacobi) { k_diag_inverse<<<nblk(n, 256), 256, 0, st>>>(p->d_diag, nzval_dev, n, dinv); ctx->launches++; }
+    if (jacobi) FB2_TRY(fill_dinv(dinv));
     const double* dptr = jacobi ? dinv : nullptr;
     FB2_TRY(A_times(x_dev, Ap));
     k_cg_init<<<nb, 256, 0, st>>>(b_dev, Ap, r, z, pp, dptr, n, part1, part2);
@@ -290,7 +288,7 @@ extern "C" int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_d
     FB2_CUDA(cudaMemcpyAsync(h, sc, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     FB2_CUDA(cudaStreamSynchronize(st));
     const double r0 = sqrt(h[3]);
-    const double target = std::max(reltol * r0, abstol);   // IterativeSolvers.cg!: ||r|| <= max(reltol ||r0||, abstol)
+    const double target = std::max(reltol * r0, abstol);
     double rn = r0;
     int it = 0;
     while (it < maxiter && rn > target) {
@@ -308,10 +306,54 @@ extern "C" int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_d
         if (!(h[4] > 0.0) && rn > target) {
             if (iters) *iters = it;
             if (resnorm) *resnorm = rn;
-            return fb2_fail(FB2_ERR_BAD_ARG, "fb2_cg: p'Ap = %g is not positive after %d iterations (matrix not SPD?)", h[4], it);
+            return fb2_fail(FB2_ERR_BAD_ARG, "cg: p'Ap = %g is not positive after %d iterations (matrix not SPD?)", h[4], it);
         }
     }
     if (iters) *iters = it;
     if (resnorm) *resnorm = rn;
     return fb2_check_device_error(ctx);
+}
+
+}  // namespace
+
+extern "C" int fb2_cg(fb2_pattern* p, const double* nzval_dev, const double* b_dev, double* x_dev, double reltol, double abstol,
+                      int maxiter, int jacobi, int symmetric, int* iters, double* resnorm) {
+    FB2_CHECK(p && nzval_dev && b_dev && x_dev, FB2_ERR_BAD_ARG, "fb2_cg: null argument");
+    fb2_ctx* ctx = p->dh->grid->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(maxiter >= 0 && reltol >= 0 && abstol >= 0, FB2_ERR_BAD_ARG, "fb2_cg: bad tolerance / iteration limit");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = p->n;
+    if (!symmetric) FB2_TRY(ensure_tperm(p));
+    auto A_times = [&](const double* v, double* out) -> int {
+        // K symmetric in value: K v = K^T v, the plain gather; otherwise through the transpose permutation
+        if (symmetric) return launch_gather<false>(p, nzval_dev, v, out);
+        return fb2_spmv(p, nzval_dev, v, out, 0);
+    };
+    auto fill_dinv = [&](double* dinv) -> int {
+        k_diag_inverse<<<nblk(n, 256), 256, 0, ctx->stream>>>(p->d_diag, nzval_dev, n, dinv);
+        ctx->launches++;
+        return FB2_OK;
+    };
+    return cg_run(ctx, n, &p->d_work, &p->work_count, A_times, jacobi, fill_dinv, b_dev, x_dev, reltol, abstol, maxiter, iters, resnorm);
+}
+
+// CG on the matrix-free operator of the element assembly: A p = sum_e P' Ke P p (fb2_ea_mul); no global matrix exists.
+// With Kes / fes after fb2_ea_apply_local the Dirichlet conditions are part of the operator (b = sum_e P' fe).
+extern "C" int fb2_ea_cg(fb2_ea* ea, const double* Kes_dev, const double* b_dev, double* x_dev, double reltol, double abstol,
+                         int maxiter, int jacobi, int* iters, double* resnorm) {
+    FB2_CHECK(ea && Kes_dev && b_dev && x_dev, FB2_ERR_BAD_ARG, "fb2_ea_cg: null argument");
+    fb2_ctx* ctx = ea->dh->grid->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(maxiter >= 0 && reltol >= 0 && abstol >= 0, FB2_ERR_BAD_ARG, "fb2_ea_cg: bad tolerance / iteration limit");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = ea->dh->ndofs;
+    auto A_times = [&](const double* v, double* out) -> int { return fb2_ea_mul(ea, Kes_dev, v, out); };
+    auto fill_dinv = [&](double* dinv) -> int {
+        FB2_TRY(fb2_ea_diag(ea, Kes_dev, dinv));
+        k_reciprocal<<<nblk(n, 256), 256, 0, ctx->stream>>>(dinv, n);
+        ctx->launches++;
+        return FB2_OK;
+    };
+    return cg_run(ctx, n, &ea->d_work, &ea->work_count, A_times, jacobi, fill_dinv, b_dev, x_dev, reltol, abstol, maxiter, iters, resnorm);
 }

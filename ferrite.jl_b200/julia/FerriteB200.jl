@@ -225,6 +225,26 @@ function mul_device!(y_dev::Ptr{Float64}, ea::ElementAssembly, Kes_dev::Ptr{Floa
     return y_dev
 end
 
+# f = sum_e P_e' fe and the diagonal of the operator
+function rhs_device!(f_dev::Ptr{Float64}, ea::ElementAssembly, fes_dev::Ptr{Float64})
+    @fb2 fb2_ea_rhs (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}) ea.h fes_dev f_dev
+    return f_dev
+end
+
+function diag_device!(d_dev::Ptr{Float64}, ea::ElementAssembly, Kes_dev::Ptr{Float64})
+    @fb2 fb2_ea_diag (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}) ea.h Kes_dev d_dev
+    return d_dev
+end
+
+# IterativeSolvers.cg!(x, A, b) with the matrix-free operator; returns (iterations, final residual norm)
+function cg_device!(x_dev::Ptr{Float64}, ea::ElementAssembly, Kes_dev::Ptr{Float64}, b_dev::Ptr{Float64};
+        reltol::Float64 = sqrt(eps(Float64)), abstol::Float64 = 0.0, maxiter::Int = ea.prob.ndofs, jacobi::Bool = false)
+    iters = Ref{Cint}(0)
+    res = Ref{Float64}(0.0)
+    @fb2 fb2_ea_cg (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cdouble, Cint, Cint, Ptr{Cint}, Ptr{Float64}) ea.h Kes_dev b_dev x_dev reltol abstol maxiter jacobi iters res
+    return Int(iters[]), res[]
+end
+
 # apply_local!(Ke, fe, celldofs(cell), ch; apply_zero) for every cell (src/Dofs/ConstraintHandler.jl:1750-1822)
 function apply_local_device!(Kes_dev::Ptr{Float64}, fes_dev::Ptr{Float64}, ea::ElementAssembly, ch::ConstraintHandler; apply_zero::Bool = false)
     c = Ref{Ptr{Cvoid}}(C_NULL)

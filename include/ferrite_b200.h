@@ -308,6 +308,14 @@ int fb2_ea_apply_local(fb2_ea* ea, fb2_ch* ch, double* Kes_dev, double* fes_dev,
  * fb2_ea_assemble + fb2_ea_apply_local + fb2_scatter_device into the caller's nzval / f */
 int fb2_apply_assemble(fb2_assembler* a, fb2_ea* ea, fb2_ch* ch, int element, const void* params, size_t params_bytes,
                        const double* u_dev, double* nzval_dev, double* f_dev, int applyzero, const fb2_asm_opts* opts);
+/* the global right-hand side of the stored element vectors: f = sum_e P_e' fe (f_dev: ndofs doubles, overwritten) */
+int fb2_ea_rhs(fb2_ea* ea, const double* fes_dev, double* f_dev);
+/* diagonal of the operator: diag[dof(c, i)] = sum over cells of Ke_c[i, i] (diag_dev: ndofs doubles, overwritten) */
+int fb2_ea_diag(fb2_ea* ea, const double* Kes_dev, double* diag_dev);
+/* fb2_cg on the matrix-free operator (no global matrix): the solver loop gpu_assembly.jl:287-304 is written for.  With
+ * Kes / fes after fb2_ea_apply_local the Dirichlet conditions are part of the operator; b = sum_e P_e' fe. */
+int fb2_ea_cg(fb2_ea* ea, const double* Kes_dev, const double* b_dev, double* x_dev, double reltol, double abstol, int maxiter,
+              int jacobi, int* iters, double* resnorm);
 int fb2_ea_destroy(fb2_ea* ea);
 
 /* ---- partitioned multi-GPU assembly (new capability; the reference is single-process) ------ */
