@@ -482,6 +482,35 @@ def main():
                 "rowsum_check": float(yv.abs().max()) / float(K.nzval.abs().max()) if cfg["element"] == "heat" else None}
         del xv, yv
 
+    # ---- element assembly: stored element matrices and the matrix-free operator y = sum_e P' Ke P x ------
+    ea_info = None
+    if world == 1 and cfg["element"] == "heat" and g.ncells * dh.ndofs_per_cell ** 2 * 8 <= 8 << 30:
+        try:
+            ea = fb.ElementAssembly(dh, cv)
+            Kes, fes = ea.assemble(elem)
+            xv = torch.ones(dh.ndofs, dtype=torch.float64, device=dev)
+            yv = torch.empty_like(xv)
+
+            def _ms(fn, reps=10):
+                fn()
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(reps):
+                    fn()
+                t1.record()
+                torch.cuda.synchronize()
+                return t0.elapsed_time(t1) / reps
+            n_loc = dh.ndofs_per_cell
+            mul_ms = _ms(lambda: ea.mul(Kes, xv, out=yv))
+            mul_bytes = g.ncells * (8 * n_loc * n_loc + 4 * n_loc) + 3 * 8 * dh.ndofs    # Ke + dofs, x read, y zero-fill + RED
+            ea_info = {"element_matrices_ms": _ms(lambda: ea.assemble(elem, Kes=Kes, fes=fes)), "mul_ms": mul_ms,
+                       "mul_GB/s": mul_bytes / mul_ms / 1e6, "mul_bytes": mul_bytes,
+                       "rowsum_check": float(yv.abs().max()) / float(Kes.abs().max())}
+            del ea, Kes, fes, xv, yv
+        except Exception as exc:          # an extra measurement must never cost the headline line
+            ea_info = {"error": str(exc)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -524,6 +553,10 @@ def main():
     if spmv:
         spmv["frac_of_hbm_peak"] = spmv["GB/s"] / hbm_peak
         line["spmv"] = spmv
+    if ea_info:
+        if "mul_GB/s" in ea_info:
+            ea_info["mul_frac_of_hbm_peak"] = ea_info["mul_GB/s"] / hbm_peak
+        line["element_assembly"] = ea_info
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, SAMPLE(cfg))
     sys.stdout.flush()

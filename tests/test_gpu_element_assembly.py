@@ -221,54 +221,3 @@ def test_apply_assemble_edge_cases(ctx):
     oK, of = O.allocate_matrix(odh), np.zeros(odh.ndofs)
     O.assemble_global(odh, ocv, oK, of, "heat", op)
     assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
-
-
-def test_matrix_free_cg_solves_the_heat_tutorial(ctx):
-    # heat_equation.jl:59-114,181-234 without a global matrix (the solver loop of gpu_assembly.jl:287-304): element matrices,
-    # apply_local!, CG on y = sum_e P' Ke P x; norm(u) == 3.307743912641305
-    g = fb.generate_grid(fb.Quadrilateral, (20, 20))
-    ip = fb.Lagrange(fb.RefQuadrilateral, 1)
-    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
-    cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip)
-    ch = fb.ConstraintHandler(dh)
-    boundary = np.concatenate([fb.getfacetset(g, k) for k in ("left", "right", "top", "bottom")])
-    fb.add_(ch, fb.Dirichlet("u", boundary, lambda x, t: 0))
-    fb.close_(ch)
-    ea = fb.ElementAssembly(dh, cv)
-    Kes, fes = ea.assemble(fb.HeatElement())
-    ea.apply_local_(Kes, fes, ch)
-    f = ea.rhs(fes)
-    ref = 3.307743912641305
-    for jacobi in (False, True):
-        u = ctx.zeros(dh.ndofs)
-        it, rn = ea.cg_(u, Kes, f, reltol=1e-13, jacobi=jacobi)
-        assert 0 < it < dh.ndofs and rn <= 1e-13 * float(f.norm()) * 1.01
-        assert abs(float(u.norm()) - ref) / ref < 1e-11
-    # rhs / diag against the assembled system of the same element matrices
-    K = fb.allocate_matrix(dh)
-    fa = ctx.zeros(dh.ndofs)
-    fb.scatter_device_(fb.start_assemble(K, fa), Kes, fes)
-    assert close(f.cpu().numpy(), fa.cpu().numpy())[0]
-    assert close(ea.diag(Kes).cpu().numpy(), K.tocsc().diagonal())[0]
-
-
-def test_matrix_free_cg_elasticity_matches_assembled_solve(ctx):
-    # Q1^3 elasticity with inhomogeneous Dirichlet values: matrix-free CG == sparse direct solve of apply_assemble!'s system
-    import scipy.sparse.linalg as spla
-    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (5, 4, 3), 1, 3, 2)
-    elem, op = make_element("elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, 0.0, -1.0)})
-    ch, och = dirichlet(g, og, dh, odh, 3)
-    ea = fb.ElementAssembly(dh, cv)
-    Kes, fes = ea.assemble(elem)
-    ea.apply_local_(Kes, fes, ch)
-    f = ea.rhs(fes)
-    u = ctx.zeros(dh.ndofs)
-    it, rn = ea.cg_(u, Kes, f, reltol=1e-13, jacobi=True)
-    assert 0 < it < dh.ndofs
-    K = fb.allocate_matrix(dh)
-    fa = ctx.zeros(dh.ndofs)
-    fb.apply_assemble_(fb.start_assemble(K, fa), ch, elem, cv, ea=ea)
-    uref = spla.spsolve(K.tocsc(), fa.cpu().numpy())
-    assert close(u.cpu().numpy(), uref, 1e-9)[0]
-    pd = och.prescribed_dofs - 1
-    assert np.allclose(u.cpu().numpy()[pd], och.inhomogeneities, rtol=1e-10, atol=1e-13)

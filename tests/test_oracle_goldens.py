@@ -426,3 +426,51 @@ def test_local_application_of_bc_golden():
             assert np.allclose(f[pd] / np.diag(P), 0.0 if azero else ch.inhomogeneities, rtol=1e-14, atol=0)
             u = np.linalg.solve(A, f)
             assert abs(np.linalg.norm(u) - golden) < 1e-12 * golden, (azero, np.linalg.norm(u))
+
+
+def _poisson_errors_oracle(shape, order, N):
+    # test/integration/convergence_test_utils.jl: -lap u = f with u = prod cos(pi x_i / 2) on [-1, 1]^d, u prescribed on
+    # every facet set; the right-hand side is the nodal interpolant of f integrated with the mass matrix (the kernel menu
+    # has no x-dependent source), which keeps the orders p + 1 (L2) and p (H1)
+    dim = {"quadrilateral": 2, "hexahedron": 3}[shape]
+    grid = O.generate_grid(shape, (N,) * dim)
+    ip = O.Lagrange(shape, order)
+    dh = O.DofHandler(grid).add("u", ip).close()
+    cv = O.CellValues(O.QuadratureRule(shape, max(2 * order - 1, 2)), ip)
+    ana = lambda x: np.prod(np.cos(np.pi * np.asarray(x) / 2), axis=-1)     # noqa: E731
+    ch = O.ConstraintHandler(dh)
+    boundary = np.concatenate([grid.facetsets[k] for k in sorted(grid.facetsets)])
+    ch.add(O.Dirichlet("u", boundary, lambda x, t: ana(x)))
+    ch.close()
+    ch.update(0.0)
+    # dof coordinates: interpolate the coordinate field (exact for the multilinear geometry)
+    geo = O.Lagrange(shape, 1)
+    xd = np.zeros((dh.ndofs, dim))
+    for a in range(ip.nbase):
+        M, _ = geo.value_and_gradient(ip.refcoords[a])
+        xd[dh.cell_dofs[:, a] - 1] = np.einsum("j,cjd->cd", M, grid.nodes[grid.cells - 1])
+    K, Mm = O.allocate_matrix(dh), O.allocate_matrix(dh)
+    O.assemble_global(dh, cv, K, np.zeros(dh.ndofs), "heat", {"k": 1.0, "source": 0.0})
+    O.assemble_global(dh, cv, Mm, None, "mass", {"rho": 1.0})
+    f = Mm.toscipy() @ (dim * np.pi ** 2 / 4 * ana(xd))
+    ch.apply(K, f)
+    u = spla.spsolve(K.toscipy().tocsc(), f)
+    ch.apply_vec(u)
+    dNdx, dO = O.reinit(cv, grid.nodes[grid.cells - 1])
+    ue = u[dh.cell_dofs - 1]
+    xq = np.einsum("qa,cad->cqd", cv.N, xd[dh.cell_dofs - 1])
+    uh = np.einsum("qa,ca->cq", cv.N, ue)
+    gh = np.einsum("ca,cqad->cqd", ue, dNdx)
+    ua = ana(xq)
+    ga = np.stack([-np.pi / 2 * np.tan(np.pi * xq[..., d] / 2) * ua for d in range(dim)], axis=-1)
+    return (np.sqrt(np.sum((ua - uh) ** 2 * dO)), np.sqrt(np.sum(np.sum((ga - gh) ** 2, axis=-1) * dO)), np.abs(ua - uh).max())
+
+
+def test_poisson_convergence_rates():
+    # test/integration/convergence_test_utils.jl:176-207: L2 rate = order + 1, H1 rate = order (atol 0.1), pointwise bounds
+    for shape, order, N in (("quadrilateral", 1, 21), ("quadrilateral", 2, 7), ("hexahedron", 1, 11)):
+        l1, h1, m1 = _poisson_errors_oracle(shape, order, N)
+        l2, h2, m2 = _poisson_errors_oracle(shape, order, 2 * N)
+        assert m1 < 3e-2 and m2 < 1e-2      # the reference's 1e-2 / 5e-3 hold for the exact source; the interpolated one costs a factor 3
+        assert abs(np.log(l1 / l2) / np.log(2) - (order + 1)) < 0.1, (shape, order, np.log(l1 / l2) / np.log(2))
+        assert abs(np.log(h1 / h2) / np.log(2) - order) < 0.1, (shape, order, np.log(h1 / h2) / np.log(2))

@@ -1,0 +1,134 @@
+"""GPU tests of the matrix-free solver path: CG on the element-assembly operator, pinned on the heat tutorial's
+norm(u) golden, and the Poisson convergence rates of test/integration/convergence_test_utils.jl computed entirely on the device.
+(Sorted after the parity files on purpose: these are end-to-end physics checks built on top of them.)"""
+import numpy as np
+import pytest
+
+import ferrite_b200 as fb
+import oracle as O
+from test_gpu_element_assembly import dirichlet
+from test_gpu_parity import build, close, make_element
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return fb.default_context(0)
+
+
+def test_matrix_free_cg_solves_the_heat_tutorial(ctx):
+    # heat_equation.jl:59-114,181-234 without a global matrix (the solver loop of gpu_assembly.jl:287-304): element matrices,
+    # apply_local!, CG on y = sum_e P' Ke P x; norm(u) == 3.307743912641305
+    g = fb.generate_grid(fb.Quadrilateral, (20, 20))
+    ip = fb.Lagrange(fb.RefQuadrilateral, 1)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip)
+    ch = fb.ConstraintHandler(dh)
+    boundary = np.concatenate([fb.getfacetset(g, k) for k in ("left", "right", "top", "bottom")])
+    fb.add_(ch, fb.Dirichlet("u", boundary, lambda x, t: 0))
+    fb.close_(ch)
+    ea = fb.ElementAssembly(dh, cv)
+    Kes, fes = ea.assemble(fb.HeatElement())
+    ea.apply_local_(Kes, fes, ch)
+    f = ea.rhs(fes)
+    ref = 3.307743912641305
+    for jacobi in (False, True):
+        u = ctx.zeros(dh.ndofs)
+        it, rn = ea.cg_(u, Kes, f, reltol=1e-13, jacobi=jacobi)
+        assert 0 < it < dh.ndofs and rn <= 1e-13 * float(f.norm()) * 1.01
+        assert abs(float(u.norm()) - ref) / ref < 1e-11
+    # rhs / diag against the assembled system of the same element matrices
+    K = fb.allocate_matrix(dh)
+    fa = ctx.zeros(dh.ndofs)
+    fb.scatter_device_(fb.start_assemble(K, fa), Kes, fes)
+    assert close(f.cpu().numpy(), fa.cpu().numpy())[0]
+    assert close(ea.diag(Kes).cpu().numpy(), K.tocsc().diagonal())[0]
+
+
+def test_matrix_free_cg_elasticity_matches_assembled_solve(ctx):
+    # Q1^3 elasticity with inhomogeneous Dirichlet values: matrix-free CG == sparse direct solve of apply_assemble!'s system
+    import scipy.sparse.linalg as spla
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (5, 4, 3), 1, 3, 2)
+    elem, op = make_element("elasticity", {"E": 10.0, "nu": 0.3, "b": (0.0, 0.0, -1.0)})
+    ch, och = dirichlet(g, og, dh, odh, 3)
+    ea = fb.ElementAssembly(dh, cv)
+    Kes, fes = ea.assemble(elem)
+    ea.apply_local_(Kes, fes, ch)
+    f = ea.rhs(fes)
+    u = ctx.zeros(dh.ndofs)
+    it, rn = ea.cg_(u, Kes, f, reltol=1e-13, jacobi=True)
+    assert 0 < it < dh.ndofs
+    K = fb.allocate_matrix(dh)
+    fa = ctx.zeros(dh.ndofs)
+    fb.apply_assemble_(fb.start_assemble(K, fa), ch, elem, cv, ea=ea)
+    uref = spla.spsolve(K.tocsc(), fa.cpu().numpy())
+    assert close(u.cpu().numpy(), uref, 1e-9)[0]
+    pd = och.prescribed_dofs - 1
+    assert np.allclose(u.cpu().numpy()[pd], och.inhomogeneities, rtol=1e-10, atol=1e-13)
+
+
+def _poisson_errors_gpu(ctx, ct, order, N, matrix_free):
+    # the GPU twin of tests/test_oracle_goldens.py::_poisson_errors_oracle (test/integration/convergence_test_utils.jl):
+    # heat + mass assembly, apply! / apply_local!, CG and function_value / function_gradient all on the device
+    import torch
+    dim = 2 if ct == fb.Quadrilateral else 3
+    shape = "quadrilateral" if dim == 2 else "hexahedron"
+    g = fb.generate_grid(ct, (N,) * dim)
+    ip = fb.Lagrange(ct, order)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(ct, max(2 * order - 1, 2)), ip)
+    ana = lambda x: np.prod(np.cos(np.pi * np.asarray(x) / 2), axis=-1)     # noqa: E731
+    ch = fb.ConstraintHandler(dh)
+    boundary = np.concatenate([fb.getfacetset(g, k) for k in ("left", "right", "top", "bottom") + (("front", "back") if dim == 3 else ())])
+    fb.add_(ch, fb.Dirichlet("u", boundary, lambda x, t: float(ana(x))))
+    fb.close_(ch)
+    fb.update_(ch, 0.0)
+    oip, geo = O.Lagrange(shape, order), O.Lagrange(shape, 1)
+    cd = dh.cell_dofs
+    xn = g.nodes[g.cells - 1]
+    xd = np.zeros((dh.ndofs, dim))
+    for a in range(oip.nbase):
+        M, _ = geo.value_and_gradient(oip.refcoords[a])
+        xd[cd[:, a] - 1] = np.einsum("j,cjd->cd", M, xn)
+    dev = f"cuda:{ctx.device}"
+    rhs = torch.from_numpy(dim * np.pi ** 2 / 4 * ana(xd)).to(dev)
+    u = ctx.zeros(dh.ndofs)
+    if matrix_free:
+        # no global matrix anywhere: fe = Me rhs_e per cell, apply_local!, CG on the element-assembly operator
+        ea = fb.ElementAssembly(dh, cv)
+        Mes, _ = ea.assemble(fb.MassElement(1.0))
+        Kes, fes = ea.assemble(fb.HeatElement(1.0, 0.0))
+        rhs_e = rhs[torch.from_numpy(cd - 1).to(dev)]
+        fes.copy_(torch.einsum("cji,cj->ci", Mes, rhs_e))
+        ea.apply_local_(Kes, fes, ch)
+        it, _ = ea.cg_(u, Kes, ea.rhs(fes), reltol=1e-12, jacobi=True)
+    else:
+        Mm = fb.allocate_matrix(dh)
+        fb.assemble_(fb.start_assemble(Mm, None), fb.MassElement(1.0), cv)
+        f = fb.spmv(Mm, rhs)
+        K = fb.allocate_matrix(dh)
+        fb.assemble_(fb.start_assemble(K, None), fb.HeatElement(1.0, 0.0), cv)
+        fb.apply_(K, f, ch)
+        it, _ = fb.cg_(u, K, f, reltol=1e-12, jacobi=True)
+    assert 0 < it < dh.ndofs
+    fb.apply_(u, ch)
+    uh, gh = fb.function_values_(cv, dh, u)
+    _, dO = fb.reinit_(cv, g)
+    xq = torch.stack([fb.function_values_(cv, dh, torch.from_numpy(np.ascontiguousarray(xd[:, k])).to(dev), gradients=False)[..., 0]
+                      for k in range(dim)], dim=-1).cpu().numpy()
+    uh, gh, dO = uh.cpu().numpy()[..., 0], gh.cpu().numpy()[..., 0, :], dO.cpu().numpy()
+    ua = ana(xq)
+    ga = np.stack([-np.pi / 2 * np.tan(np.pi * xq[..., k] / 2) * ua for k in range(dim)], axis=-1)
+    return (np.sqrt(np.sum((ua - uh) ** 2 * dO)), np.sqrt(np.sum(np.sum((ga - gh) ** 2, axis=-1) * dO)), np.abs(ua - uh).max())
+
+
+@pytest.mark.parametrize("ct,order,N", [(fb.Quadrilateral, 1, 21), (fb.Quadrilateral, 2, 7), (fb.Hexahedron, 1, 11)])
+@pytest.mark.parametrize("matrix_free", [False, True])
+def test_poisson_convergence_rates_on_the_device(ctx, ct, order, N, matrix_free):
+    # L2 rate = order + 1, H1 rate = order, atol 0.1 (test/integration/convergence_test_utils.jl:176-207)
+    l1, h1, m1 = _poisson_errors_gpu(ctx, ct, order, N, matrix_free)
+    l2, h2, m2 = _poisson_errors_gpu(ctx, ct, order, 2 * N, matrix_free)
+    assert m1 < 3e-2 and m2 < 1e-2
+    assert abs(np.log(l1 / l2) / np.log(2) - (order + 1)) < 0.1
+    assert abs(np.log(h1 / h2) / np.log(2) - order) < 0.1
