@@ -180,7 +180,7 @@ _PROTOS = {
 }
 DIST_EXCHANGE, DIST_HALO, DIST_OWN_ONLY = 0, 1, 2
 FACET_FLUX, FACET_TRACTION, FACET_NORMAL_TRACTION = 1, 2, 3
-ORDER_PERMUTATION, ORDER_FIELDWISE, ORDER_COMPONENTWISE = 0, 1, 2
+ORDER_PERMUTATION, ORDER_FIELDWISE, ORDER_COMPONENTWISE, ORDER_METIS = 0, 1, 2, 3
 
 lib.fb2_version.restype = C.c_char_p
 lib.fb2_version.argtypes = []

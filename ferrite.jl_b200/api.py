@@ -254,6 +254,13 @@ class DofOrder:
     class ComponentWise(FieldWise):
         kind = L.ORDER_COMPONENTWISE
 
+    class Metis(FieldWise):
+        """DofOrder.Ext{Metis}(): fill-reducing nested-dissection order (ext/FerriteMetis.jl:29-92)"""
+        kind = L.ORDER_METIS
+
+        def __init__(self):
+            self.target_blocks = None
+
 
 def renumber_(dh, *args):
     """renumber!(dh, order) / renumber!(dh, ch, order): order = a permutation vector (1-based, dof i becomes perm[i]),

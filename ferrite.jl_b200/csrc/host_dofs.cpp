@@ -164,6 +164,10 @@ extern "C" int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fi
     return FB2_OK;
 }
 
+// METIS as shipped with the CUDA toolkit (libmetis_static.a, 64-bit idx_t; see partition.cu)
+extern "C" int METIS_NodeND(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* options, int64_t* perm, int64_t* iperm);
+extern "C" int METIS_SetDefaultOptions(int64_t* options);
+
 // renumber!(dh, order): src/Dofs/DofRenumbering.jl:79-125 (apply), :167-246 (FieldWise / ComponentWise permutations).
 // kind 0: perm_in (1-based, dof i -> perm_in[i]); 1: FieldWise, 2: ComponentWise with optional target blocks (1-based block
 // per field / per component; nullptr = one block each in declaration order).  The permutation is returned in perm_out
@@ -220,6 +224,34 @@ extern "C" int fb2_dh_renumber(fb2_dh* dh, int kind, const int64_t* target_block
         for (int64_t d = 0; d < n; ++d) { FB2_CHECK(dofblock[d] >= 0, FB2_ERR_INTERNAL, "fb2_dh_renumber: dof %lld belongs to no cell", (long long)d + 1); start[dofblock[d] + 1]++; }
         for (int b = 0; b < nblocks; ++b) start[b + 1] += start[b];
         for (int64_t d = 0; d < n; ++d) perm[d] = start[dofblock[d]]++;
+    } else if (kind == 3) {
+        // DofOrder.Ext{Metis}() (ext/FerriteMetis.jl:29-92): fill-reducing nested dissection of the dof coupling graph (two
+        // dofs are adjacent when a cell holds both, no diagonal); new number of dof i = iperm[i]
+        std::vector<int64_t> cnt((size_t)n + 1, 0);
+        for (size_t i = 0; i < dh->cell_dofs.size(); ++i) cnt[dh->cell_dofs[i] + 1]++;
+        for (int64_t d = 0; d < n; ++d) cnt[d + 1] += cnt[d];
+        std::vector<int64_t> inc((size_t)cnt[n]), fill(cnt.begin(), cnt.end() - 1);   // dof -> cells
+        for (int64_t c = 0; c < nc; ++c)
+            for (int i = 0; i < ndpc; ++i) inc[fill[dh->cell_dofs[(size_t)c * ndpc + i]]++] = c;
+        std::vector<int64_t> xadj((size_t)n + 1, 0), adjncy, row;
+        for (int64_t d = 0; d < n; ++d) {
+            row.clear();
+            for (int64_t k = cnt[d]; k < cnt[d + 1]; ++k)
+                for (int i = 0; i < ndpc; ++i) {
+                    const int64_t e = dh->cell_dofs[(size_t)inc[k] * ndpc + i];
+                    if (e != d) row.push_back(e);
+                }
+            std::sort(row.begin(), row.end());
+            row.erase(std::unique(row.begin(), row.end()), row.end());
+            adjncy.insert(adjncy.end(), row.begin(), row.end());
+            xadj[d + 1] = (int64_t)adjncy.size();
+        }
+        int64_t nv = n, options[40];
+        METIS_SetDefaultOptions(options);
+        std::vector<int64_t> mperm((size_t)n), miperm((size_t)n);
+        const int mrc = METIS_NodeND(&nv, xadj.data(), adjncy.data(), nullptr, options, mperm.data(), miperm.data());
+        FB2_CHECK(mrc == 1, FB2_ERR_INTERNAL, "METIS_NodeND failed with status %d", mrc);
+        for (int64_t d = 0; d < n; ++d) perm[d] = miperm[d];
     } else {
         return fb2_fail(FB2_ERR_BAD_ARG, "fb2_dh_renumber: unknown order %d", kind);
     }

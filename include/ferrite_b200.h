@@ -143,9 +143,10 @@ int fb2_dh_from_host(fb2_grid* grid, int nfields, const fb2_field* fields, int64
                      int ndofs_per_cell, const int64_t* cell_dofs, fb2_dh** out);
 /* renumber!(dh, order): src/Dofs/DofRenumbering.jl:79-125,167-246.  order: 0 = the permutation perm_in (1-based, dof i
  * becomes perm_in[i]), FB2_ORDER_FIELDWISE / FB2_ORDER_COMPONENTWISE with optional 1-based target blocks (one per field /
- * per component; NULL = declaration order).  perm_out (nullable, ndofs entries) receives the permutation for
+ * per component; NULL = declaration order), FB2_ORDER_METIS = DofOrder.Ext{Metis}() (ext/FerriteMetis.jl:29-92: METIS_NodeND
+ * on the dof coupling graph, no coupling matrix).  perm_out (nullable, ndofs entries) receives the permutation for
  * fb2_ch_renumber.  Renumber before allocate_matrix: patterns and assemblers of the old numbering are stale. */
-enum { FB2_ORDER_PERMUTATION = 0, FB2_ORDER_FIELDWISE = 1, FB2_ORDER_COMPONENTWISE = 2 };
+enum { FB2_ORDER_PERMUTATION = 0, FB2_ORDER_FIELDWISE = 1, FB2_ORDER_COMPONENTWISE = 2, FB2_ORDER_METIS = 3 };
 int fb2_dh_renumber(fb2_dh* dh, int order, const int64_t* target_blocks, int ntargets, const int64_t* perm_in, int64_t* perm_out);
 int fb2_dh_info(fb2_dh* dh, int64_t* ndofs, int* ndofs_per_cell, int* nfields);
 /* celldofs!(dofs, dh, i) for all cells: ndofs_per_cell x ncells, 1-based (src/Dofs/DofHandler.jl:248-253) */

@@ -320,3 +320,38 @@ def test_element_assembly_needs_a_device(hctx):
     cv = fb.CellValues(fb.QuadratureRule(fb.RefQuadrilateral, 2), ip, ctx=hctx)
     with pytest.raises(fb.FB2Error):
         fb.ElementAssembly(dh, cv)
+
+
+def _factor_fill(cell_dofs, ndofs):
+    """nnz(L + U) of a sparse LU in the given numbering (no column reordering): the quantity DofOrder.Ext{Metis} reduces"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = cell_dofs.shape[1]
+    rows = np.repeat(cell_dofs[:, :, None], n, axis=2).ravel() - 1
+    cols = np.repeat(cell_dofs[:, None, :], n, axis=1).ravel() - 1
+    A = sp.csc_matrix((np.ones(len(rows)), (rows, cols)), shape=(ndofs, ndofs))
+    A = A + sp.identity(ndofs, format="csc") * (A.sum(axis=1).max() + 1.0)          # diagonally dominant: no pivoting
+    lu = spla.splu(A, permc_spec="NATURAL", diag_pivot_thresh=0.0, options={"SymmetricMode": True})
+    return lu.L.nnz + lu.U.nnz
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim", [(fb.Quadrilateral, (24, 24), 1, 1), (fb.Hexahedron, (8, 8, 8), 1, 1), (fb.Triangle, (10, 10), 2, 2)])
+def test_renumber_metis_reduces_fill(hctx, ct, nel, order, vdim):
+    # renumber!(dh, DofOrder.Ext{Metis}()) (ext/FerriteMetis.jl:29-92; the reference's test only runs it, test/test_dofs.jl:426-432)
+    g = fb.generate_grid(ct, nel, ctx=hctx)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, order) ** vdim))
+    cd0 = dh.cell_dofs.copy()
+    scramble = np.random.default_rng(3).permutation(dh.ndofs) + 1
+    fb.renumber_(dh, scramble)
+    fill_scrambled = _factor_fill(dh.cell_dofs, dh.ndofs)
+    perm = fb.renumber_(dh, fb.DofOrder.Metis())
+    assert sorted(perm.tolist()) == list(range(1, dh.ndofs + 1))
+    assert np.array_equal(dh.cell_dofs, perm[scramble[cd0 - 1] - 1])
+    fill_metis = _factor_fill(dh.cell_dofs, dh.ndofs)
+    fill_generated = _factor_fill(cd0, dh.ndofs)
+    assert fill_metis < 0.5 * fill_scrambled, (fill_metis, fill_scrambled)
+    assert fill_metis < 1.2 * fill_generated, (fill_metis, fill_generated)
+    # deterministic (default METIS seed): the same graph gives the same order
+    dh2 = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, order) ** vdim))
+    fb.renumber_(dh2, scramble)
+    assert np.array_equal(fb.renumber_(dh2, fb.DofOrder.Metis()), perm)
