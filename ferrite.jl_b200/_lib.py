@@ -146,11 +146,16 @@ _PROTOS = {
     "fb2_ea_rhs": [_p, _p, _p],
     "fb2_ea_cg": [_p, _p, _p, _p, C.c_double, C.c_double, C.c_int, C.c_int, _ip, _dp],
     "fb2_ea_destroy": [_p],
+    "fb2_rhsdata_create": [_p, _p, _p, _pp],
+    "fb2_rhsdata_info": [_p, _dp, _i64p, _i64p],
+    "fb2_apply_rhs": [_p, _p, _p, C.c_int],
+    "fb2_rhsdata_destroy": [_p],
     "fb2_assembler_destroy": [_p],
     "fb2_ch_create": [_p, _pp],
     "fb2_ch_add_dirichlet": [_p, C.c_int, C.c_int, C.c_int64, _i64p, C.c_int, _ip, _ip],
     "fb2_ch_close": [_p],
     "fb2_ch_from_host": [_p, C.c_int64, _i64p, _dp, _pp],
+    "fb2_ch_set_inhomogeneities": [_p, C.c_int64, _dp],
     "fb2_ch_bc_points": [_p, C.c_int, _i64p, _dp],
     "fb2_ch_bc_set_values": [_p, C.c_int, C.c_int64, _dp],
     "fb2_ch_info": [_p, _i64p],

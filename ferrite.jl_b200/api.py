@@ -735,6 +735,11 @@ class ConstraintHandler:
         L.call("fb2_ch_from_host", dh.h, len(p), _ptr(p, C.c_int64), _ptr(v, C.c_double), C.byref(ch.h))
         return ch
 
+    def set_inhomogeneities(self, values):
+        """update!(ch, t) in arrays-in mode: the reference's ch.inhomogeneities (order of prescribed_dofs)"""
+        v = _f64(values)
+        L.call("fb2_ch_set_inhomogeneities", self.h, len(v), _ptr(v, C.c_double))
+
     def _add(self, dbc):
         comps = dbc.components or []
         carr = (C.c_int * max(len(comps), 1))(*comps)
@@ -797,6 +802,32 @@ def apply_(K, f=None, ch=None, applyzero=False):
     L.call("fb2_apply", ch.h, K.h, C.c_void_p(K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None,
            1 if applyzero else 0, C.byref(m))
     return m.value
+
+
+class RHSData:
+    """get_rhs_data(ch, A) (src/Dofs/ConstraintHandler.jl:191-208): mean diagonal and prescribed columns of A before apply!"""
+
+    def __init__(self, ch, K):
+        self.ch, self.K = ch, K
+        self.h = C.c_void_p()
+        L.call("fb2_rhsdata_create", ch.h, K.h, C.c_void_p(K.nzval.data_ptr()), C.byref(self.h))
+        m, np_, ns = C.c_double(), C.c_int64(), C.c_int64()
+        L.call("fb2_rhsdata_info", self.h, C.byref(m), C.byref(np_), C.byref(ns))
+        self.m, self.nprescribed, self.nstored = m.value, np_.value, ns.value
+
+    def __del__(self):
+        if _destroy is not None:
+            _destroy(self, "fb2_rhsdata_destroy", _chain(self.K, "dh"))
+
+
+def get_rhs_data(ch, K):
+    return RHSData(ch, K)
+
+
+def apply_rhs_(data, f, ch, applyzero=False):
+    """apply_rhs!(data, f, ch, applyzero) (src/Dofs/ConstraintHandler.jl:217-240): boundary conditions onto a new right-hand side"""
+    L.call("fb2_apply_rhs", data.h, C.c_void_p(f.data_ptr()), ch.h, 1 if applyzero else 0)
+    return f
 
 
 def apply_zero_(K, f=None, ch=None):

@@ -116,6 +116,44 @@ __global__ void k_apply_vector(const int32_t* __restrict__ prescribed, const dou
     if (i < np) u[prescribed[i]] = applyzero ? 0.0 : inhom[i];
 }
 
+// RHSData (src/Dofs/ConstraintHandler.jl:191-208): lengths of the prescribed columns, then their rows / values
+__global__ void k_rhs_lengths(const int32_t* __restrict__ prescribed, int64_t np, const int64_t* __restrict__ colptr,
+                              int64_t* __restrict__ len) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) len[i] = colptr[prescribed[i] + 1] - colptr[prescribed[i]];
+}
+
+__global__ void k_rhs_copy(const int32_t* __restrict__ prescribed, int64_t np, const int64_t* __restrict__ colptr,
+                           const int32_t* __restrict__ rowval, const double* __restrict__ nzval, const int64_t* __restrict__ ptr,
+                           int32_t* __restrict__ rows, double* __restrict__ vals) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= np) return;
+    const int64_t b = colptr[prescribed[w]], e = colptr[prescribed[w] + 1], o = ptr[w];
+    for (int64_t k = b + lane; k < e; k += 32) {
+        rows[o + k - b] = rowval[k];
+        vals[o + k - b] = nzval[k];
+    }
+}
+
+// apply_rhs! first loop (:219-226): f[row] -= v * K[row, d] from the stored columns, warp per prescribed dof
+__global__ void k_rhs_columns(const double* __restrict__ inhom, int64_t np, const int64_t* __restrict__ ptr,
+                              const int32_t* __restrict__ rows, const double* __restrict__ vals, double* __restrict__ f) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= np) return;
+    const double v = inhom[w];
+    if (v == 0.0) return;
+    for (int64_t k = ptr[w] + lane; k < ptr[w + 1]; k += 32) atomicAdd(f + rows[k], -v * vals[k]);
+}
+
+// second loop (:227-237): f[pdof] = b * m
+__global__ void k_rhs_prescribed(const int32_t* __restrict__ prescribed, const double* __restrict__ inhom, int64_t np, double m,
+                                 double* __restrict__ f, int applyzero) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) f[prescribed[i]] = (applyzero ? 0.0 : inhom[i]) * m;
+}
+
 inline unsigned nblocks(int64_t total, int bs) { return (unsigned)((total + bs - 1) / bs); }
 
 void add_prescribed(fb2_ch* ch, int64_t dof) {
@@ -320,6 +358,17 @@ extern "C" int fb2_ch_renumber(fb2_ch* ch, const int64_t* perm) {
     return finish_close(ch);
 }
 
+// arrays-in mode of update!(ch, t): the reference's ch.inhomogeneities (order of ch.prescribed_dofs) after its own update!
+extern "C" int fb2_ch_set_inhomogeneities(fb2_ch* ch, int64_t n, const double* inhomogeneities) {
+    FB2_CHECK(ch && inhomogeneities, FB2_ERR_BAD_ARG, "fb2_ch_set_inhomogeneities: null argument");
+    FB2_CHECK(ch->closed, FB2_ERR_BAD_ARG, "fb2_ch_set_inhomogeneities: the ConstraintHandler is not closed");
+    FB2_CHECK(n == (int64_t)ch->prescribed.size(), FB2_ERR_BAD_ARG, "fb2_ch_set_inhomogeneities: %lld values for %lld prescribed dofs",
+              (long long)n, (long long)ch->prescribed.size());
+    ch->inhom.assign(inhomogeneities, inhomogeneities + n);
+    ch->inhom_dirty = true;
+    return FB2_OK;
+}
+
 extern "C" int fb2_ch_bc_points(fb2_ch* ch, int ibc, int64_t* npoints, double* x) {
     FB2_CHECK(ch && npoints && ibc >= 0 && ibc < (int)ch->bcs.size(), FB2_ERR_BAD_ARG, "fb2_ch_bc_points: bad argument");
     const DirichletBC& bc = ch->bcs[ibc];
@@ -386,6 +435,100 @@ extern "C" int fb2_apply(fb2_ch* ch, fb2_pattern* p, double* nzval_dev, double* 
         FB2_CUDA(cudaMemcpyAsync(meandiag, ch->d_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st));
         FB2_CUDA(cudaStreamSynchronize(st));
     }
+    return FB2_OK;
+}
+
+struct fb2_rhsdata {
+    fb2_ctx* ctx = nullptr;
+    int64_t n = 0, np = 0;
+    double m = 0.0;              // meandiag(A)
+    int64_t* d_ptr = nullptr;    // [np + 1]
+    int32_t* d_rows = nullptr;   // A[:, prescribed_dofs] as compact CSC
+    double* d_vals = nullptr;
+};
+
+extern "C" int fb2_rhsdata_destroy(fb2_rhsdata* r) {
+    if (!r) return FB2_OK;
+    cudaFree(r->d_ptr);
+    cudaFree(r->d_rows);
+    cudaFree(r->d_vals);
+    delete r;
+    return FB2_OK;
+}
+
+// get_rhs_data(ch, A): mean |diagonal| and the prescribed columns of the matrix as it is now (before apply!)
+extern "C" int fb2_rhsdata_create(fb2_ch* ch, fb2_pattern* p, const double* nzval_dev, fb2_rhsdata** out) {
+    FB2_CHECK(ch && p && nzval_dev && out, FB2_ERR_BAD_ARG, "fb2_rhsdata_create: null argument");
+    FB2_CHECK(ch->closed, FB2_ERR_BAD_ARG, "fb2_rhsdata_create: the ConstraintHandler is not closed");
+    FB2_CHECK(p->n == ch->dh->ndofs, FB2_ERR_BAD_ARG, "fb2_rhsdata_create: matrix size does not match the DofHandler");
+    fb2_ctx* ctx = ch->dh->grid->ctx;
+    FB2_NEED_DEVICE(ctx);
+    cudaStream_t st = ctx->stream;
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    fb2_rhsdata* r = new fb2_rhsdata();
+    r->ctx = ctx;
+    r->n = p->n;
+    r->np = (int64_t)ch->prescribed.size();
+    const int nb = (int)std::min<int64_t>(1024, (p->n + 255) / 256);
+    k_meandiag_partial<<<nb, 256, 0, st>>>(nzval_dev, p->d_diag, p->n, ch->d_scratch);
+    k_meandiag_final<<<1, 256, 0, st>>>(ch->d_scratch, nb, p->n);
+    ctx->launches += 2;
+    cudaError_t e = cudaMemcpyAsync(&r->m, ch->d_scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, st);
+    std::vector<int64_t> ptr((size_t)r->np + 1, 0);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_ptr, ptr.size() * sizeof(int64_t));
+    if (e == cudaSuccess && r->np > 0) {
+        k_rhs_lengths<<<nblocks(r->np, 256), 256, 0, st>>>(ch->d_prescribed, r->np, p->d_colptr, r->d_ptr);
+        ctx->launches++;
+        e = cudaMemcpyAsync(ptr.data() + 1, r->d_ptr, (size_t)r->np * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    for (int64_t i = 0; i < r->np; ++i) ptr[i + 1] += ptr[i];
+    const int64_t tot = ptr[r->np];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_ptr, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_rows, std::max<int64_t>(tot, 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&r->d_vals, std::max<int64_t>(tot, 1) * sizeof(double));
+    if (e == cudaSuccess && r->np > 0) {
+        k_rhs_copy<<<nblocks(r->np * 32, 256), 256, 0, st>>>(ch->d_prescribed, r->np, p->d_colptr, p->d_rowval, nzval_dev, r->d_ptr,
+                                                            r->d_rows, r->d_vals);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);   // ptr (host) is read by the copy above
+    if (e != cudaSuccess) {
+        fb2_rhsdata_destroy(r);
+        return fb2_fail(e == cudaErrorMemoryAllocation ? FB2_ERR_OOM : FB2_ERR_CUDA, "fb2_rhsdata_create: %s", cudaGetErrorString(e));
+    }
+    *out = r;
+    return FB2_OK;
+}
+
+extern "C" int fb2_rhsdata_info(fb2_rhsdata* r, double* meandiag, int64_t* nprescribed, int64_t* nstored) {
+    FB2_CHECK(r, FB2_ERR_BAD_ARG, "fb2_rhsdata_info: null handle");
+    if (meandiag) *meandiag = r->m;
+    if (nprescribed) *nprescribed = r->np;
+    if (nstored) {
+        FB2_CUDA(cudaMemcpy(nstored, r->d_ptr + r->np, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    return FB2_OK;
+}
+
+// apply_rhs!(data, f, ch, applyzero): the boundary conditions of the current update! on a new right-hand side, K untouched
+extern "C" int fb2_apply_rhs(fb2_rhsdata* r, double* f_dev, fb2_ch* ch, int applyzero) {
+    FB2_CHECK(r && f_dev && ch, FB2_ERR_BAD_ARG, "fb2_apply_rhs: null argument");
+    FB2_CHECK(ch->closed && (int64_t)ch->prescribed.size() == r->np && ch->dh->ndofs == r->n, FB2_ERR_BAD_ARG,
+              "fb2_apply_rhs: the ConstraintHandler does not match the RHSData");
+    fb2_ctx* ctx = ch->dh->grid->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_TRY(upload_inhom(ch));
+    if (r->np == 0) return FB2_OK;
+    if (!applyzero) {
+        k_rhs_columns<<<nblocks(r->np * 32, 256), 256, 0, ctx->stream>>>(ch->d_inhom, r->np, r->d_ptr, r->d_rows, r->d_vals, f_dev);
+        ctx->launches++;
+    }
+    k_rhs_prescribed<<<nblocks(r->np, 256), 256, 0, ctx->stream>>>(ch->d_prescribed, ch->d_inhom, r->np, r->m, f_dev, applyzero);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
     return FB2_OK;
 }
 

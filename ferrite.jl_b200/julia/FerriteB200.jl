@@ -164,6 +164,30 @@ function Ferrite.apply!(K::B200Matrix, ch::ConstraintHandler, nzval_dev::Ptr{Flo
     return m[]
 end
 
+# get_rhs_data(ch, A) / apply_rhs!(data, f, ch, applyzero) -- src/Dofs/ConstraintHandler.jl:191-240 (one factorisation, many steps)
+mutable struct B200RHSData
+    h::Ptr{Cvoid}
+    ch::Ptr{Cvoid}
+end
+
+function Ferrite.get_rhs_data(ch::ConstraintHandler, K::B200Matrix, nzval_dev::Ptr{Float64})
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_ch_from_host (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) K.prob.dh length(ch.prescribed_dofs) ch.prescribed_dofs ch.inhomogeneities c
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_rhsdata_create (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) c[] K.pattern nzval_dev r
+    return finalizer(B200RHSData(r[], c[])) do d
+        ccall((:fb2_rhsdata_destroy, LIB), Cint, (Ptr{Cvoid},), d.h)
+        ccall((:fb2_ch_destroy, LIB), Cint, (Ptr{Cvoid},), d.ch)
+    end
+end
+
+function Ferrite.apply_rhs!(data::B200RHSData, f_dev::Ptr{Float64}, ch::ConstraintHandler, applyzero::Bool = false)
+    # the inhomogeneities of the current update!(ch, t) travel as one small array
+    @fb2 fb2_ch_set_inhomogeneities (Ptr{Cvoid}, Int64, Ptr{Float64}) data.ch length(ch.inhomogeneities) ch.inhomogeneities
+    @fb2 fb2_apply_rhs (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Cint) data.h f_dev data.ch applyzero
+    return f_dev
+end
+
 # ---- Neumann / traction facet loop (hyperelasticity.jl:278-291) ------------------------------------------------------
 # `facetset` is a reference facet set (OrderedSet{FacetIndex}); kind: 1 flux (params q), 2 traction (params t),
 # 3 normal traction (params p: fe += p n N dGamma; the tutorial's `ge[i] -= (dui . tn n) dGamma` is p = -tn).

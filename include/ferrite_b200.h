@@ -222,6 +222,8 @@ int fb2_ch_close(fb2_ch* ch);
 /* arrays-in mode: adopt a closed reference ConstraintHandler (ch.prescribed_dofs sorted, ch.inhomogeneities),
  * src/Dofs/ConstraintHandler.jl:160-162 */
 int fb2_ch_from_host(fb2_dh* dh, int64_t n, const int64_t* prescribed_dofs, const double* inhomogeneities, fb2_ch** out);
+/* update!(ch, t) in arrays-in mode: the reference's ch.inhomogeneities after its own update! (src/Dofs/ConstraintHandler.jl:303-361) */
+int fb2_ch_set_inhomogeneities(fb2_ch* ch, int64_t n, const double* inhomogeneities);
 /* update!(ch, t) (src/Dofs/ConstraintHandler.jl:504-580) is split around the user's Julia function f(x,t):
  * fb2_ch_bc_points returns the dof locations x (sdim x npoints) of condition ibc in the reference's
  * evaluation order (BCValues, src/FEValues/FacetValues.jl:185-236); the caller evaluates f and hands the
@@ -237,6 +239,14 @@ int fb2_ch_export(fb2_ch* ch, int64_t* prescribed_dofs, double* inhomogeneities)
 int fb2_apply(fb2_ch* ch, fb2_pattern* p, double* nzval_dev, double* f_dev, int applyzero, double* meandiag);
 /* apply!(u, ch) / apply_zero!(u, ch): src/Dofs/ConstraintHandler.jl:686-700 */
 int fb2_apply_vector(fb2_ch* ch, double* u_dev, int applyzero);
+/* get_rhs_data(ch, A) / apply_rhs!(data, f, ch, applyzero): src/Dofs/ConstraintHandler.jl:191-240.  The mean diagonal and the
+ * prescribed columns of the matrix are captured BEFORE apply!; afterwards every new right-hand side gets the boundary
+ * conditions of the current update! without touching K (time stepping with one factorisation). */
+typedef struct fb2_rhsdata fb2_rhsdata;
+int fb2_rhsdata_create(fb2_ch* ch, fb2_pattern* p, const double* nzval_dev, fb2_rhsdata** out);
+int fb2_rhsdata_info(fb2_rhsdata* data, double* meandiag, int64_t* nprescribed, int64_t* nstored);
+int fb2_apply_rhs(fb2_rhsdata* data, double* f_dev, fb2_ch* ch, int applyzero);
+int fb2_rhsdata_destroy(fb2_rhsdata* data);
 int fb2_ch_destroy(fb2_ch* ch);
 
 /* reinit!(cv, cell) for a batch of cells outside the fused loop (post-processing): src/FEValues/CellValues.jl:122-140.

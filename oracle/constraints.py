@@ -14,7 +14,7 @@ import numpy as np
 
 from .interpolations import geometric_interpolation
 
-__all__ = ["Dirichlet", "ConstraintHandler", "apply_local", "apply_assemble"]
+__all__ = ["Dirichlet", "ConstraintHandler", "apply_local", "apply_assemble", "get_rhs_data", "apply_rhs"]
 
 
 class Dirichlet:
@@ -199,3 +199,28 @@ def apply_assemble(K, f, ch, dofs, Ke, fe, applyzero=False):
     from .assemble import assemble_cell
     apply_local(Ke, fe, dofs, ch, applyzero)
     assemble_cell(K, f, dofs, Ke, fe)
+
+
+def get_rhs_data(ch, K):
+    """get_rhs_data(ch, A) (src/Dofs/ConstraintHandler.jl:203-208): (meandiag(A), A[:, prescribed_dofs]) of the matrix as it is"""
+    n = K.n
+    cp = K.colptr - 1
+    diag_pos = K.lookup(np.arange(1, n + 1), np.arange(1, n + 1))
+    m = 0.0
+    for v in np.abs(np.where(diag_pos >= 0, K.nzval[np.maximum(diag_pos, 0)], 0.0)):
+        m += v
+    m /= n
+    cols = [(K.rowval[cp[d]:cp[d + 1]] - 1, K.nzval[cp[d]:cp[d + 1]].copy()) for d in ch.prescribed_dofs - 1]
+    return m, cols
+
+
+def apply_rhs(data, f, ch, applyzero=False):
+    """apply_rhs!(data, f, ch, applyzero) (:217-240) without the affine branch"""
+    m, cols = data
+    for i, (rows, vals) in enumerate(cols):
+        v = ch.inhomogeneities[i]
+        if not applyzero and v != 0:
+            np.subtract.at(f, rows, v * vals)
+    for i, d in enumerate(ch.prescribed_dofs - 1):
+        f[d] = (0.0 if applyzero else ch.inhomogeneities[i]) * m
+    return f

@@ -355,3 +355,13 @@ def test_renumber_metis_reduces_fill(hctx, ct, nel, order, vdim):
     dh2 = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, order) ** vdim))
     fb.renumber_(dh2, scramble)
     assert np.array_equal(fb.renumber_(dh2, fb.DofOrder.Metis()), perm)
+
+
+def test_set_inhomogeneities_arrays_in(hctx):
+    g = fb.generate_grid(fb.Quadrilateral, (3, 3), ctx=hctx)
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefQuadrilateral, 1)))
+    ch = fb.ConstraintHandler.from_arrays(dh, [1, 5, 9], [0.0, 0.0, 0.0])
+    ch.set_inhomogeneities([1.0, 2.5, -3.0])
+    assert list(ch.inhomogeneities) == [1.0, 2.5, -3.0]
+    with pytest.raises(fb.FB2Error):
+        ch.set_inhomogeneities([1.0, 2.0])

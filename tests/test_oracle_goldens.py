@@ -474,3 +474,30 @@ def test_poisson_convergence_rates():
         assert m1 < 3e-2 and m2 < 1e-2      # the reference's 1e-2 / 5e-3 hold for the exact source; the interpolated one costs a factor 3
         assert abs(np.log(l1 / l2) / np.log(2) - (order + 1)) < 0.1, (shape, order, np.log(l1 / l2) / np.log(2))
         assert abs(np.log(h1 / h2) / np.log(2) - order) < 0.1, (shape, order, np.log(h1 / h2) / np.log(2))
+
+
+def test_apply_rhs_golden():
+    # test/test_apply_rhs.jl:5-92: apply!(K, f, ch) and get_rhs_data + apply!(A, ch) + apply_rhs!(data, g, ch) give the same solve
+    grid = O.generate_grid("quadrilateral", (20, 20))
+    ip = O.Lagrange("quadrilateral", 1)
+    dh = O.DofHandler(grid).add("u", ip).close()
+    cv = O.CellValues(O.QuadratureRule("quadrilateral", 2), ip)
+    ch = O.ConstraintHandler(dh)
+    ch.add(O.Dirichlet("u", np.concatenate([grid.facetsets["left"], grid.facetsets["right"]]), lambda x, t: 0))
+    ch.add(O.Dirichlet("u", np.concatenate([grid.facetsets["top"], grid.facetsets["bottom"]]), lambda x, t: 2))
+    ch.close()
+    ch.update(0.0)
+    K, A = O.allocate_matrix(dh), O.allocate_matrix(dh)
+    f, g = np.zeros(dh.ndofs), np.zeros(dh.ndofs)
+    O.assemble_global(dh, cv, K, f, "heat")
+    O.assemble_global(dh, cv, A, g, "heat")
+    data = O.get_rhs_data(ch, A)
+    ch.apply(K, f)
+    ch.apply(A)
+    O.apply_rhs(data, g, ch)
+    assert np.array_equal(K.nzval, A.nzval)
+    assert np.allclose(f, g, rtol=1e-15, atol=1e-15)
+    u1 = spla.spsolve(K.toscipy().tocsc(), f)
+    u2 = spla.spsolve(A.toscipy().tocsc(), g)
+    assert np.allclose(u1, u2, rtol=1e-14, atol=0)
+    assert abs(u1[ch.prescribed_dofs - 1] - ch.inhomogeneities).max() < 1e-14

@@ -132,3 +132,48 @@ def test_poisson_convergence_rates_on_the_device(ctx, ct, order, N, matrix_free)
     assert m1 < 3e-2 and m2 < 1e-2
     assert abs(np.log(l1 / l2) / np.log(2) - (order + 1)) < 0.1
     assert abs(np.log(h1 / h2) / np.log(2) - order) < 0.1
+
+
+@pytest.mark.parametrize("applyzero", [False, True])
+def test_apply_rhs_matches_apply_and_oracle(ctx, applyzero):
+    # test/test_apply_rhs.jl:5-92 on the device, and parity of the right-hand side with the oracle's apply_rhs!
+    g, og, dh, odh, cv, ocv = build(fb.Quadrilateral, (20, 20), 1, 1, 2)
+    elem, op = make_element("heat", {})
+    ch, och = fb.ConstraintHandler(dh), O.ConstraintHandler(odh)
+    lr = ("left", "right")
+    tb = ("top", "bottom")
+    fb.add_(ch, fb.Dirichlet("u", np.concatenate([fb.getfacetset(g, k) for k in lr]), lambda x, t: 0))
+    fb.add_(ch, fb.Dirichlet("u", np.concatenate([fb.getfacetset(g, k) for k in tb]), lambda x, t: 2 + t * x[0]))
+    och.add(O.Dirichlet("u", np.concatenate([og.facetsets[k] for k in lr]), lambda x, t: 0))
+    och.add(O.Dirichlet("u", np.concatenate([og.facetsets[k] for k in tb]), lambda x, t: 2 + t * x[0]))
+    fb.close_(ch)
+    och.close()
+    fb.update_(ch, 0.0)
+    och.update(0.0)
+    K, A = fb.allocate_matrix(dh), fb.allocate_matrix(dh)
+    f, gv = ctx.zeros(dh.ndofs), ctx.zeros(dh.ndofs)
+    fb.assemble_(fb.start_assemble(K, f), elem, cv)
+    fb.assemble_(fb.start_assemble(A, gv), elem, cv)
+    data = fb.get_rhs_data(ch, A)
+    oA, og_ = O.allocate_matrix(odh), np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oA, og_, "heat", op)
+    odata = O.get_rhs_data(och, oA)
+    assert abs(data.m - odata[0]) <= 1e-13 * odata[0] and data.nprescribed == len(och.prescribed_dofs)
+    assert data.nstored == sum(len(r) for r, _ in odata[1])
+    fb.apply_(K, f, ch, applyzero=applyzero)
+    fb.apply_(A, None, ch)                      # apply!(A, ch): the matrix once
+    fb.apply_rhs_(data, gv, ch, applyzero=applyzero)
+    assert close(gv.cpu().numpy(), f.cpu().numpy())[0]
+    assert close(gv.cpu().numpy(), O.apply_rhs(odata, og_.copy(), och, applyzero=applyzero))[0]
+    assert np.array_equal(K.nzval.cpu().numpy(), A.nzval.cpu().numpy())
+    # next time step: new inhomogeneities on a fresh right-hand side, K untouched
+    fb.update_(ch, 1.5)
+    och.update(1.5)
+    g2 = ctx.zeros(dh.ndofs)
+    fb.assemble_(fb.start_assemble(fb.allocate_matrix(dh), g2), elem, cv)
+    fb.apply_rhs_(data, g2, ch, applyzero=applyzero)
+    assert close(g2.cpu().numpy(), O.apply_rhs(odata, og_.copy(), och, applyzero=applyzero))[0]
+    u = ctx.zeros(dh.ndofs)
+    fb.cg_(u, A, g2, reltol=1e-13, jacobi=True)
+    expect = np.zeros(len(och.prescribed_dofs)) if applyzero else och.inhomogeneities
+    assert np.allclose(u.cpu().numpy()[och.prescribed_dofs - 1], expect, rtol=1e-10, atol=1e-12)
