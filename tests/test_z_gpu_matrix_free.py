@@ -165,7 +165,7 @@ def test_apply_rhs_matches_apply_and_oracle(ctx, applyzero):
     fb.apply_rhs_(data, gv, ch, applyzero=applyzero)
     assert close(gv.cpu().numpy(), f.cpu().numpy())[0]
     assert close(gv.cpu().numpy(), O.apply_rhs(odata, og_.copy(), och, applyzero=applyzero))[0]
-    assert np.array_equal(K.nzval.cpu().numpy(), A.nzval.cpu().numpy())
+    assert close(K.nzval.cpu().numpy(), A.nzval.cpu().numpy())[0]        # two atomic assemblies: equal up to summation order
     # next time step: new inhomogeneities on a fresh right-hand side, K untouched
     fb.update_(ch, 1.5)
     och.update(1.5)
