@@ -119,6 +119,7 @@ _PROTOS = {
     "fb2_cellvalues_destroy": [_p],
     "fb2_function_values": [_p, _p, _p, _p, _p],
     "fb2_reinit_cells": [_p, _p, _i64p, C.c_int64, _p, _p],
+    "fb2_spatial_coordinates": [_p, _p, _i64p, C.c_int64, _p],
     "fb2_facetvalues_create": [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp],
     "fb2_facetvalues_info": [_p, _ip, _ip, _ip, _ip, _ip],
     "fb2_facetvalues_export": [_p, _dp, _dp, _dp],

@@ -426,6 +426,101 @@ def reinit_(cv, grid, cells=None):
     return dNdx, dO
 
 
+def spatial_coordinates_(cv, grid, cells=None):
+    """spatial_coordinate(cv, q, x) of every quadrature point of a batch of cells: CUDA tensor (n, nq, sdim)."""
+    torch = _torch()
+    n = grid.ncells if cells is None else len(cells)
+    x = torch.empty((n, cv.nq, grid.sdim), dtype=torch.float64, device=f"cuda:{grid.ctx.device}")
+    ids = None if cells is None else _i64(cells)
+    L.call("fb2_spatial_coordinates", cv.h, grid.h, _ptr(ids, C.c_int64) if ids is not None else None, n, C.c_void_p(x.data_ptr()))
+    grid.ctx.synchronize()
+    return x
+
+
+class ReinitCellValues:
+    """`cv` after reinit!(cv, cell) for a whole batch of cells: the accessors of src/FEValues/common_values.jl and CellValues.jl
+    (shape_value :138ff, shape_gradient, shape_symmetric_gradient, shape_divergence, getdetJdV, spatial_coordinate :363-372,
+    function_value / function_gradient :177-227) with 1-based q and i as in the reference.  Values that depend on the cell come
+    back as CUDA tensors whose first axis is the cell of the batch; they are views of the buffers fb2_reinit_cells and
+    fb2_spatial_coordinates filled on the device."""
+
+    def __init__(self, cv, grid, cells=None):
+        self.cv, self.grid, self.cells = cv, grid, cells
+        self.dNdx, self.detJdV = reinit_(cv, grid, cells)
+        self.N = _torch().from_numpy(cv.tables()["N"]).to(self.dNdx.device)      # (nq, nbase)
+        self._x = None
+
+    def getnquadpoints(self):
+        return self.cv.nq
+
+    def getnbasefunctions(self):
+        return self.cv.nbase_scalar * self.cv.vdim
+
+    def _split(self, i):
+        assert 1 <= i <= self.getnbasefunctions(), "base function index out of range"
+        return (i - 1) // self.cv.vdim, (i - 1) % self.cv.vdim
+
+    def shape_value(self, q, i):
+        """N_i(xi_q): a float for scalar interpolations, a (vdim,) tensor N_a e_c for vectorised ones (i = (a-1) vdim + c)"""
+        a, c = self._split(i)
+        v = self.N[q - 1, a]
+        if self.cv.vdim == 1:
+            return float(v)
+        out = _torch().zeros(self.cv.vdim, dtype=_torch().float64, device=self.N.device)
+        out[c] = v
+        return out
+
+    def shape_gradient(self, q, i):
+        """(n, dim) for scalar interpolations; (n, vdim, dim) with row c = grad N_a for vectorised ones"""
+        a, c = self._split(i)
+        g = self.dNdx[:, q - 1, a, :]
+        if self.cv.vdim == 1:
+            return g
+        out = _torch().zeros((g.shape[0], self.cv.vdim, g.shape[1]), dtype=g.dtype, device=g.device)
+        out[:, c, :] = g
+        return out
+
+    def shape_symmetric_gradient(self, q, i):
+        g = self.shape_gradient(q, i)
+        return 0.5 * (g + g.transpose(1, 2))
+
+    def shape_divergence(self, q, i):
+        a, c = self._split(i)
+        return self.dNdx[:, q - 1, a, c] if self.cv.vdim > 1 else self.dNdx[:, q - 1, a, :].sum(dim=1)
+
+    def getdetJdV(self, q):
+        return self.detJdV[:, q - 1]
+
+    def spatial_coordinate(self, q):
+        if self._x is None:
+            self._x = spatial_coordinates_(self.cv, self.grid, self.cells)
+        return self._x[:, q - 1, :]
+
+    def function_value(self, q, ue):
+        """ue: (n, ndofs_per_cell) cell-local dof values -> (n,) or (n, vdim)"""
+        u = ue.reshape(ue.shape[0], self.cv.nbase_scalar, self.cv.vdim)
+        v = _torch().einsum("a,nac->nc", self.N[q - 1], u)
+        return v[:, 0] if self.cv.vdim == 1 else v
+
+    def function_gradient(self, q, ue):
+        u = ue.reshape(ue.shape[0], self.cv.nbase_scalar, self.cv.vdim)
+        g = _torch().einsum("nac,nad->ncd", u, self.dNdx[:, q - 1])
+        return g[:, 0, :] if self.cv.vdim == 1 else g
+
+
+    def function_symmetric_gradient(self, q, ue):
+        g = self.function_gradient(q, ue)
+        return 0.5 * (g + g.transpose(1, 2))
+
+    def function_divergence(self, q, ue):
+        g = self.function_gradient(q, ue)
+        return g.sum(dim=1) if self.cv.vdim == 1 else g.diagonal(dim1=1, dim2=2).sum(dim=1)
+
+
+def reinit_batch(cv, grid, cells=None):
+    return ReinitCellValues(cv, grid, cells)
+
+
 def function_values_(cv, dh, u, gradients=True):
     """function_value(cv, q, ue) and function_gradient(cv, q, ue) at every quadrature point of every cell:
     CUDA tensors (ncells, nq, vdim) and (ncells, nq, vdim, dim)."""

@@ -386,6 +386,24 @@ __global__ void k_reinit_cells(const int32_t* __restrict__ conn, const double* _
         }
 }
 
+// spatial_coordinate(cv, q, x) (src/FEValues/common_values.jl:363-372): x_q = sum_j M_j(xi_q) x_j
+__global__ void k_spatial_coordinates(const int32_t* __restrict__ conn, const double* __restrict__ xyz, int64_t ncells_pad, int xstride,
+                                      int sdim, const int64_t* __restrict__ cells, int64_t n, const double* __restrict__ tab, int o_M,
+                                      int nq, int ngeo, double* __restrict__ x) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * nq) return;
+    const int64_t k = t / nq;
+    const int q = (int)(t - k * nq);
+    const int64_t cell = cells ? cells[k] - 1 : k;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < ngeo; ++j) {
+        const double M = tab[o_M + q * ngeo + j];
+        const double* xj = xyz + (size_t)conn[(size_t)j * ncells_pad + cell] * xstride;
+        for (int d = 0; d < sdim; ++d) s[d] = fma(M, xj[d], s[d]);
+    }
+    for (int d = 0; d < sdim; ++d) x[(size_t)t * sdim + d] = s[d];
+}
+
 // function_value / function_gradient of a dof vector at every quadrature point of every cell
 // (src/FEValues/common_values.jl:177-227): val[c] = sum_a N_a u_(a,c), grad[c][d] = sum_a u_(a,c) dN_a/dx_d
 template <int DIM>
@@ -479,6 +497,33 @@ static int ensure_cv_tables(fb2_cv* cv) {
     FB2_CUDA(cudaMalloc(&cv->d_tables, h.size() * sizeof(double)));
     FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     cv->tables_count = h.size();
+    return FB2_OK;
+}
+
+extern "C" int fb2_spatial_coordinates(fb2_cv* cv, fb2_grid* g, const int64_t* cells, int64_t n, double* x_dev) {
+    FB2_CHECK(cv && g && n >= 0, FB2_ERR_BAD_ARG, "fb2_spatial_coordinates: bad argument");
+    if (n == 0) return FB2_OK;
+    FB2_CHECK(x_dev, FB2_ERR_BAD_ARG, "fb2_spatial_coordinates: null output");
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CHECK(cv->celltype == g->celltype && cv->ngeo == g->nnpc, FB2_ERR_BAD_ARG, "fb2_spatial_coordinates: CellValues do not match the grid");
+    if (cells) for (int64_t k = 0; k < n; ++k) FB2_CHECK(cells[k] >= 1 && cells[k] <= g->ncells, FB2_ERR_BAD_ARG, "fb2_spatial_coordinates: cell %lld out of range", (long long)cells[k]);
+    else FB2_CHECK(n <= g->ncells, FB2_ERR_BAD_ARG, "fb2_spatial_coordinates: more cells than the grid has");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    FB2_TRY(ensure_cv_tables(cv));
+    const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
+    const int o_M = nq + nq * nb + nq * nb * rd;
+    int64_t* d_cells = nullptr;
+    if (cells) {
+        FB2_CUDA(cudaMalloc(&d_cells, n * sizeof(int64_t)));
+        FB2_CUDA(cudaMemcpyAsync(d_cells, cells, n * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    k_spatial_coordinates<<<(unsigned)((n * nq + 127) / 128), 128, 0, ctx->stream>>>(g->d_conn, g->d_xyz, g->ncells_pad, g->xstride, g->sdim,
+                                                                                     d_cells, n, cv->d_tables, o_M, nq, ng, x_dev);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (d_cells) { cudaStreamSynchronize(ctx->stream); cudaFree(d_cells); }
+    FB2_CUDA(e);
     return FB2_OK;
 }
 

@@ -254,6 +254,9 @@ int fb2_ch_destroy(fb2_ch* ch);
  * dNdx[cell][q][i][d] (rdim x n x nq per cell, column-major = cv.fun_values.dNdx) and detJdV[cell][q]. */
 int fb2_reinit_cells(fb2_cv* cv, fb2_grid* grid, const int64_t* cells, int64_t n, double* dNdx_dev, double* detJdV_dev);
 
+/* spatial_coordinate(cv, q, x) for a batch of cells (src/FEValues/common_values.jl:363-372): x_dev is n x nq x sdim.
+ * cells: 1-based ids, NULL = the first n cells. */
+int fb2_spatial_coordinates(fb2_cv* cv, fb2_grid* grid, const int64_t* cells, int64_t n, double* x_dev);
 /* function_value / function_gradient (src/FEValues/common_values.jl:177-227) of the dof vector u at every quadrature
  * point of every cell: values[cell][q][c] (vdim x nq per cell) and gradients[cell][q][c][d] (dim x vdim x nq per cell,
  * column-major); either output may be NULL. */

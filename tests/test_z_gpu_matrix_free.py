@@ -177,3 +177,53 @@ def test_apply_rhs_matches_apply_and_oracle(ctx, applyzero):
     fb.cg_(u, A, g2, reltol=1e-13, jacobi=True)
     expect = np.zeros(len(och.prescribed_dofs)) if applyzero else och.inhomogeneities
     assert np.allclose(u.cpu().numpy()[och.prescribed_dofs - 1], expect, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("ct,nel,order,vdim,qo", [
+    (fb.Hexahedron, (4, 3, 3), 1, 1, 2), (fb.Hexahedron, (3, 2, 2), 2, 3, 3), (fb.Tetrahedron, (3, 2, 2), 2, 3, 4),
+    (fb.Quadrilateral, (5, 4), 2, 1, 3), (fb.Triangle, (5, 4), 1, 2, 2),
+])
+def test_cellvalues_accessors_on_an_affine_field(ctx, ct, nel, order, vdim, qo):
+    # test/test_cellvalues.jl:54-98: a field that is affine in x is reproduced exactly by function_value / function_gradient /
+    # function_symmetric_gradient / function_divergence at spatial_coordinate(cv, q, x); volumes = sum detJdV
+    # (test/test_utils.jl:130-222); shape_value / shape_gradient / getdetJdV against the oracle's reinit!
+    import torch
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, vdim, qo)
+    dim = len(nel)
+    rv = fb.reinit_batch(cv, g)
+    dNdx, dO = O.reinit(ocv, og.nodes[og.cells - 1])
+    assert rv.getnquadpoints() == ocv.w.size and rv.getnbasefunctions() == odh.ndofs_per_cell
+    rng = np.random.default_rng(4)
+    V, G = rng.random(vdim), rng.random((vdim, dim))
+    # dof coordinates (interpolation of the multilinear geometry at the reference coordinates of the basis)
+    oip, geo = odh.field_ips[0].base, O.Lagrange(og.shape, 1)
+    xe = np.stack([np.einsum("j,cjd->cd", geo.value_and_gradient(oip.refcoords[a])[0], og.nodes[og.cells - 1])
+                   for a in range(oip.nbase)], axis=1)                        # (nc, nbase, dim)
+    ue = (np.einsum("vd,cad->cav", G, xe) + V).reshape(og.ncells, -1)
+    ue_t = torch.from_numpy(ue).to(f"cuda:{ctx.device}")
+    vol = 0.0
+    for q in range(1, rv.getnquadpoints() + 1):
+        xq = rv.spatial_coordinate(q).cpu().numpy()
+        assert close(xq, np.einsum("j,cjd->cd", ocv.M[q - 1], og.nodes[og.cells - 1]), 1e-14)[0]
+        assert close(rv.getdetJdV(q).cpu().numpy(), dO[:, q - 1], 1e-13)[0]
+        vol += float(rv.getdetJdV(q).sum())
+        val, grad = rv.function_value(q, ue_t).cpu().numpy(), rv.function_gradient(q, ue_t).cpu().numpy()
+        exact = np.einsum("vd,cd->cv", G, xq) + V
+        if vdim == 1:
+            assert np.allclose(val, exact[:, 0], rtol=1e-12, atol=1e-13) and np.allclose(grad, G[0], rtol=0, atol=1e-11)
+            assert np.allclose(rv.function_divergence(q, ue_t).cpu().numpy(), G[0].sum(), rtol=0, atol=1e-11)
+        else:
+            assert np.allclose(val, exact, rtol=1e-12, atol=1e-13) and np.allclose(grad, G, rtol=0, atol=1e-11)
+            assert np.allclose(rv.function_symmetric_gradient(q, ue_t).cpu().numpy(), 0.5 * (G + G.T), rtol=0, atol=1e-11)
+            assert np.allclose(rv.function_divergence(q, ue_t).cpu().numpy(), np.trace(G), rtol=0, atol=1e-11)
+        for i in (1, rv.getnbasefunctions()):
+            a, c = (i - 1) // vdim, (i - 1) % vdim
+            sg = rv.shape_gradient(q, i).cpu().numpy()
+            sv = rv.shape_value(q, i)
+            if vdim == 1:
+                assert sv == ocv.N[q - 1, a] and close(sg, dNdx[:, q - 1, a, :], 1e-13)[0]
+            else:
+                assert float(sv[c]) == ocv.N[q - 1, a] and float(sv.sum()) == ocv.N[q - 1, a]
+                assert close(sg[:, c, :], dNdx[:, q - 1, a, :], 1e-13)[0] and np.count_nonzero(np.delete(sg, c, axis=1)) == 0
+                assert close(rv.shape_divergence(q, i).cpu().numpy(), dNdx[:, q - 1, a, c], 1e-13)[0]
+    assert abs(vol - 2.0 ** dim) < 1e-12 * 2.0 ** dim
