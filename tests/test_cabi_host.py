@@ -365,3 +365,70 @@ def test_set_inhomogeneities_arrays_in(hctx):
     assert list(ch.inhomogeneities) == [1.0, 2.5, -3.0]
     with pytest.raises(fb.FB2Error):
         ch.set_inhomogeneities([1.0, 2.0])
+
+
+def _dof_locations_consistent(cells, nodes, cell_dofs, oip, geo, vdim):
+    """every global dof sits at one location and one component from whichever cell it is seen (test/test_dofs.jl:1117-1150)"""
+    loc = {}
+    for c, conn in enumerate(cells):
+        x = nodes[np.asarray(conn) - 1]
+        for a in range(oip.nbase):
+            M, _ = geo.value_and_gradient(oip.refcoords[a])
+            xd = M @ x
+            for k in range(vdim):
+                d = int(cell_dofs[c][a * vdim + k])
+                if d in loc:
+                    if not (np.allclose(loc[d][0], xd, atol=1e-12) and loc[d][1] == k):
+                        return False
+                else:
+                    loc[d] = (xd, k)
+    return True
+
+
+def test_shared_face_dofs_for_all_tetrahedron_orientations(hctx):
+    # test/test_dofs.jl:1099-1153 for Lagrange{RefTetrahedron, 2} (orders 3 and 4 are out of scope): 24 x 24 vertex orders
+    import itertools
+    nodes = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], dtype=float)
+    oip, geo = O.Lagrange("tetrahedron", 2), O.Lagrange("tetrahedron", 1)
+    for vdim, nshared in ((1, 6), (2, 12)):
+        for t1 in itertools.permutations((1, 2, 3, 4)):
+            for t2 in itertools.permutations((2, 3, 4, 5)):
+                g = fb.Grid.from_arrays(fb.Tetrahedron, [t1, t2], nodes, ctx=hctx)
+                dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefTetrahedron, 2) ** vdim))
+                cd = dh.cell_dofs
+                assert len(set(cd[0]) & set(cd[1])) == nshared and dh.ndofs == 2 * 10 * vdim - nshared
+                assert _dof_locations_consistent([t1, t2], nodes, cd, oip, geo, vdim), (t1, t2)
+                if vdim == 1:
+                    odh = O.DofHandler(O.Grid("tetrahedron", [t1, t2], nodes)).add("u", oip).close()
+                    assert np.array_equal(cd, odh.cell_dofs)
+
+
+def test_shared_face_dofs_for_all_hexahedron_orientations(hctx):
+    # test/test_dofs.jl:1156-1235 for Lagrange{RefHexahedron, 2}: the 24 proper rotations of both cells
+    import itertools
+    corner = [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)]
+    rotations = []
+    for cols in itertools.permutations(range(3)):
+        for s in itertools.product((-1, 1), repeat=3):
+            R = np.zeros((3, 3), dtype=int)
+            for r in range(3):
+                R[r, cols[r]] = s[r]
+            if round(np.linalg.det(R)) == 1:
+                rotations.append(tuple(corner.index(tuple(int(v) for v in R @ np.array(cn))) for cn in corner))
+    assert len(rotations) == 24
+    nodes = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1],
+                      [0, 0, 2], [1, 0, 2], [1, 1, 2], [0, 1, 2]], dtype=float)
+    bottom, top = (1, 2, 3, 4, 5, 6, 7, 8), (5, 6, 7, 8, 9, 10, 11, 12)
+    oip, geo = O.Lagrange("hexahedron", 2), O.Lagrange("hexahedron", 1)
+    for vdim, nshared in ((1, 9), (3, 27)):
+        for r1 in rotations:
+            for r2 in rotations:
+                h1, h2 = tuple(bottom[k] for k in r1), tuple(top[k] for k in r2)
+                g = fb.Grid.from_arrays(fb.Hexahedron, [h1, h2], nodes, ctx=hctx)
+                dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefHexahedron, 2) ** vdim))
+                cd = dh.cell_dofs
+                assert len(set(cd[0]) & set(cd[1])) == nshared and dh.ndofs == 2 * 27 * vdim - nshared
+                assert _dof_locations_consistent([h1, h2], nodes, cd, oip, geo, vdim), (h1, h2)
+                if vdim == 1:
+                    odh = O.DofHandler(O.Grid("hexahedron", [h1, h2], nodes)).add("u", oip).close()
+                    assert np.array_equal(cd, odh.cell_dofs)
