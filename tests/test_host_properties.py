@@ -94,3 +94,27 @@ def test_partitions_from_arbitrary_owner_arrays(p, nparts, seed):
                 ns, nfs, _, _ = parts[a].peer_counts(b)
                 _, _, nr, nfr = parts[b].peer_counts(a)
                 assert (ns, nfs) == (nr, nfr)
+
+
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(problems(), st.booleans(), st.data())
+def test_random_renumbering_matches_oracle(p, componentwise, data):
+    # renumber!(dh, DofOrder.FieldWise(blocks) / ComponentWise(blocks)) with random target blocks, then the inverse of the
+    # returned permutation restores the original numbering (src/Dofs/DofRenumbering.jl:79-125,167-246)
+    ct, nel, fields = p
+    g, dh, og, odh = build(ct, nel, fields)
+    cd0 = dh.cell_dofs.copy()
+    nslots = sum(v for _, v in fields) if componentwise else len(fields)
+    nblocks = data.draw(st.integers(1, nslots))
+    tb = data.draw(st.lists(st.integers(1, nblocks), min_size=nslots, max_size=nslots).filter(lambda b: set(b) == set(range(1, nblocks + 1))))
+    order = (fb.DofOrder.ComponentWise if componentwise else fb.DofOrder.FieldWise)(tb)
+    perm = fb.renumber_(dh, order)
+    operm = O.renumber_permutation(odh, "componentwise" if componentwise else "fieldwise", tb)
+    assert np.array_equal(perm, operm)
+    O.renumber(odh, operm)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    # block b holds a contiguous range, ordered by block
+    iperm = np.empty_like(perm)
+    iperm[perm - 1] = np.arange(1, dh.ndofs + 1)
+    fb.renumber_(dh, iperm)
+    assert np.array_equal(dh.cell_dofs, cd0)
