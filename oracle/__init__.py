@@ -31,3 +31,4 @@ from .element import *        # noqa: F401,F403
 from .assemble import *       # noqa: F401,F403
 from .constraints import *    # noqa: F401,F403
 from .facets import *         # noqa: F401,F403
+from .affine import *        # noqa: F401,F403

@@ -501,3 +501,60 @@ def test_apply_rhs_golden():
     u2 = spla.spsolve(A.toscipy().tocsc(), g)
     assert np.allclose(u1, u2, rtol=1e-14, atol=0)
     assert abs(u1[ch.prescribed_dofs - 1] - ch.inhomogeneities).max() < 1e-14
+
+
+def test_affine_constraints_golden():
+    # Groundwork for the next round (oracle only; the CUDA library has no affine constraints yet).
+    # test/test_constraints.jl:323-412: in-place apply! with condensation == the explicitly condensed system C'KC a_f = C'(f - Kg)
+    grid = O.generate_grid("line", (10,))
+    dh = O.DofHandler(grid).add("u", O.Lagrange("line", 1)).close()
+    n = dh.ndofs
+    # nonsymmetric matrix condensation (:330-341)
+    ch = O.AffineConstraintHandler(dh)
+    ch.add(O.AffineConstraint(1, [(3, 2.0)], 0.0))
+    ch.add(O.AffineConstraint(2, [(4, 3.0)], 0.0))
+    ch.close()
+    C, _ = ch.create_constraint_matrix()
+    K = O.dense_pattern(n)
+    K.nzval[:] = np.arange(1.0, n * n + 1)                 # reshape(1.0:(n^2), n, n), column-major like nzval
+    Kd = K.toscipy().toarray()
+    ch.apply(K)
+    fd = ch.free_dofs - 1
+    Cd = C.toarray()
+    assert np.array_equal(K.toscipy().toarray()[np.ix_(fd, fd)], Cd.T @ Kd @ Cd)
+    test_acs = [
+        [O.AffineConstraint(4, [(7, 1.0)], 0.0)],
+        [O.AffineConstraint(2, [(5, 1.0), (6, 2.0)], 1.0)],
+        [O.AffineConstraint(2, [(9, 1.0)], 0.0), O.AffineConstraint(3, [(9, 1.0)], 0.0)],
+        [O.AffineConstraint(2, [(7, 3.0), (8, 1.0)], -1.0), O.AffineConstraint(4, [(9, -1.0)], 2.0)],
+    ]
+    for acs in test_acs:
+        ch = O.AffineConstraintHandler(dh)
+        ch.add(O.Dirichlet("u", grid.facetsets["left"], lambda x, t: 0.0))
+        for ac in acs:
+            ch.add(ac)
+        ch.close()
+        ch.update(0.0)
+        C, g = ch.create_constraint_matrix()
+        C = C.toarray()
+        K = O.allocate_matrix_condensed(dh, ch)
+        f = np.zeros(n)
+        f[-1] = 1.0
+        for c in range(grid.ncells):
+            O.assemble_cell(K, None, dh.cell_dofs[c], 2.0 * np.array([[1.0, -1.0], [-1.0, 1.0]]))
+        Kd = K.toscipy().toarray()
+        aa = C @ np.linalg.solve((C.T @ Kd @ C), C.T @ (f - Kd @ g)) + g
+        ch.apply(K, f)
+        a = ch.apply_vec(np.linalg.solve(K.toscipy().toarray(), f))
+        assert np.allclose(a, aa, rtol=1e-12, atol=1e-13)
+        for ac in acs:                                         # the constraint holds in the solution
+            assert abs(a[ac.constrained_dof - 1] - (ac.b + sum(v * a[d - 1] for d, v in ac.entries))) < 1e-12
+    # error paths (:1417-1422)
+    ch = O.AffineConstraintHandler(dh)
+    ch.add(O.AffineConstraint(1, [(2, 1.0)], 0.0))
+    ch.add(O.AffineConstraint(2, [(3, 1.0)], 0.0))
+    try:
+        ch.close()
+        assert False, "nested constraints must be rejected"
+    except ValueError as e:
+        assert "nested affine constraints currently not supported" in str(e)
