@@ -4,7 +4,7 @@ Restates, for the next round's device implementation (DESIGN.md section 8, item 
   * `AffineConstraint(dof, [master => coeff, ...], b)` and `add!` / `close!` (src/Dofs/ConstraintHandler.jl:114-131, 303-361:
     sorted prescribed dofs, `dofcoefficients` aligned with them, nested constraints rejected),
   * `create_constraint_matrix` (:889-916): a = C a_f + g,
-  * the condensed sparsity pattern of `allocate_matrix(dh, ch)` (src/Dofs/sparsity_pattern.jl `_condense_sparsity_pattern!`:
+  * the condensed sparsity pattern of `allocate_matrix(dh, ch)` (src/Dofs/sparsity_pattern.jl:782-840 `_add_constraint_entries!`:
     entry (r, c) with r constrained adds (m, c) for the masters m of r, c constrained adds (r, m), both add (m1, m2)),
   * `apply!(K, f, ch)` with `_condense!` (:710-740, 809-868) and `apply!(u, ch)` (:686-700).
 Restriction of this restatement: master dofs must be unconstrained (the reference additionally allows Dirichlet-prescribed
@@ -152,12 +152,14 @@ def allocate_matrix_condensed(dh, ch):
     pairs = set(zip(K.rowval.tolist(), cols.tolist()))
     extra = set()
     for r, c in pairs:
-        cr, cc = ch._coeffs(r), ch._coeffs(c)
-        if cr and not cc:
-            extra.update((d, c) for d, _ in cr)
-        elif cc and not cr:
+        cr, cc = ch._coeffs(r), ch._coeffs(c)      # None: not affinely constrained (free or Dirichlet), sparsity_pattern.jl:794-832
+        if cr is None and cc is None:
+            continue
+        if cr is None:
             extra.update((r, d) for d, _ in cc)
-        elif cr and cc:
+        elif cc is None:
+            extra.update((d, c) for d, _ in cr)
+        else:
             extra.update((d1, d2) for d1, _ in cr for d2, _ in cc)
     return _csc_from_pairs(n, pairs | extra)
 

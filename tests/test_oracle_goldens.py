@@ -558,3 +558,32 @@ def test_affine_constraints_golden():
         assert False, "nested constraints must be rejected"
     except ValueError as e:
         assert "nested affine constraints currently not supported" in str(e)
+
+
+def test_condensed_pattern_equals_pattern_of_extended_cells():
+    # the pattern of allocate_matrix(dh, ch) is the pattern of allocate_matrix(dh) plus, per cell,
+    # ext x ext with ext = (cell dofs that are not affinely constrained) + (masters of the cell's affinely constrained dofs)
+    # -- what lets the incidence-based device builder produce it from one extra padded dof list per cell
+    rng = np.random.default_rng(7)
+    for shape, nel, order in (("quadrilateral", (5, 4), 1), ("triangle", (4, 4), 2), ("hexahedron", (3, 2, 2), 1)):
+        grid = O.generate_grid(shape, nel)
+        dh = O.DofHandler(grid).add("u", O.Lagrange(shape, order)).close()
+        n = dh.ndofs
+        slaves = rng.choice(np.arange(1, n + 1), size=max(3, n // 6), replace=False)
+        pool = np.setdiff1d(np.arange(1, n + 1), slaves)
+        ch = O.AffineConstraintHandler(dh)
+        for s in slaves:
+            masters = rng.choice(pool, size=rng.integers(0, 4), replace=False)
+            ch.add(O.AffineConstraint(int(s), [(int(m), float(rng.random() + 0.5)) for m in masters], float(rng.random())))
+        ch.close()
+        K = O.allocate_matrix_condensed(dh, ch)
+        K0 = O.allocate_matrix(dh)
+        pairs = set(zip(K0.rowval.tolist(), np.repeat(np.arange(1, n + 1), np.diff(K0.colptr)).tolist()))
+        for c in range(grid.ncells):
+            ext = []
+            for d in dh.cell_dofs[c]:
+                co = ch._coeffs(d)
+                ext += [int(d)] if co is None else [m for m, _ in co]
+            pairs.update((r, cc) for r in ext for cc in ext)
+        cols = np.repeat(np.arange(1, n + 1), np.diff(K.colptr))
+        assert pairs == set(zip(K.rowval.tolist(), cols.tolist())), shape
