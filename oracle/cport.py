@@ -32,7 +32,8 @@ def build(force=False):
     out_dir = os.path.join(_HERE, "_build")
     so = os.path.join(out_dir, "liboracle_cpu.so")
     tag = os.path.join(out_dir, "cpu.tag")
-    if not force and os.path.exists(so) and os.path.exists(tag) and open(tag).read() == _cpu_tag():
+    if (not force and os.path.exists(so) and os.path.exists(tag) and open(tag).read() == _cpu_tag()
+            and os.path.getmtime(so) >= os.path.getmtime(_SRC)):
         return so
     try:
         os.makedirs(out_dir, exist_ok=True)
@@ -55,6 +56,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.oracle_assemble.restype = C.c_int64
+        _lib.oracle_assemble_colored.restype = C.c_int64
         _lib.oracle_max_threads.restype = C.c_int
     return _lib
 
@@ -63,8 +65,33 @@ def max_threads():
     return lib().oracle_max_threads()
 
 
-def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0, u=None):
-    """Same contract as oracle.assemble_global, executed by the C port with `nthreads` OpenMP threads."""
+def structured_coloring(grid, nel):
+    """Colours of a generate_grid mesh such that no two cells of a colour share a node (create_coloring(grid),
+    src/Grid/coloring.jl:308-317, delivers such a colouring; any valid one serves the threaded loop): parity of the cell's
+    (i, j, k) for quadrilaterals / hexahedra, times the sub-cell index for the 2 triangles / 6 tetrahedra of a cube.
+    Returns (ncolors, color_ptr, color_cells) with 0-based int64 arrays; validity is checked."""
+    sub = {"quadrilateral": 1, "hexahedron": 1, "triangle": 2, "tetrahedron": 6}[grid.shape]
+    nel = tuple(nel)
+    c = np.arange(grid.ncells, dtype=np.int64)
+    cube, t = c // sub, c % sub
+    par, stride, mult = np.zeros_like(c), 1, 1
+    for nd in nel:
+        par += ((cube // stride) % nd % 2) * mult
+        stride *= nd
+        mult *= 2
+    color = par * sub + t
+    ncolors = int(color.max()) + 1
+    order = np.argsort(color, kind="stable").astype(np.int64)
+    ptr = np.concatenate([[0], np.cumsum(np.bincount(color, minlength=ncolors))]).astype(np.int64)
+    for k in range(ncolors):
+        nodes = grid.cells[order[ptr[k]:ptr[k + 1]]].ravel()
+        assert len(np.unique(nodes)) == len(nodes), "colouring is not valid for this grid"
+    return ncolors, ptr, order
+
+
+def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0, u=None, colors=None):
+    """Same contract as oracle.assemble_global, executed by the C port with `nthreads` OpenMP threads.
+    colors = (ncolors, color_ptr, color_cells): the coloured loop (plain adds) instead of the atomic one."""
     grid = dh.grid
     n = dh.ndofs_per_cell
     assert n == cv.nbase
@@ -95,12 +122,15 @@ def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0, u=None):
 
     def ptr(a, t):
         return a.ctypes.data_as(C.POINTER(t))
-    bad = lib().oracle_assemble(
+    nco, cptr, ccells = (0, None, None) if colors is None else colors
+    bad = lib().oracle_assemble_colored(
         C.c_int(eid), C.c_int(grid.sdim), C.c_int(cells.shape[1]), C.c_int(cv.base.nbase), C.c_int(cv.vdim), C.c_int(cv.nq),
         C.c_int64(grid.ncells), ptr(cells, C.c_int64), ptr(xyz, C.c_double), ptr(cd, C.c_int64),
         ptr(K.colptr, C.c_int64), ptr(K.rowval, C.c_int64), ptr(N, C.c_double), ptr(dN, C.c_double), ptr(dM, C.c_double),
         ptr(w, C.c_double), ptr(pv, C.c_double), ptr(uu, C.c_double) if uu is not None else None, ptr(K.nzval, C.c_double),
-        ptr(f, C.c_double) if f is not None else None, C.c_int(nthreads))
+        ptr(f, C.c_double) if f is not None else None, C.c_int(nthreads), C.c_int(nco),
+        ptr(np.ascontiguousarray(cptr, dtype=np.int64), C.c_int64) if nco else None,
+        ptr(np.ascontiguousarray(ccells, dtype=np.int64), C.c_int64) if nco else None)
     if bad:
         raise ArithmeticError(f"det(J) is not positive in cell {bad}")
     return K, f

@@ -59,13 +59,19 @@ static void sortperm(int n, const int64_t* dofs, int64_t* sorted, int* perm) {
 }
 
 /* element: 1 = heat (params: k, source), 3 = elasticity (params: lambda, mu, b[3]) ; returns 0 or the 1-based id of a bad cell */
-int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int nq, int64_t ncells, const int64_t* cells,
-                        const double* xyz, const int64_t* cell_dofs, const int64_t* colptr, const int64_t* rowval,
-                        const double* N, const double* dN, const double* dM, const double* w, const double* params,
-                        const double* u, double* nzval, double* f, int nthreads) {
+/* Coloured variant (docs/src/literate-howto/threaded_assembly.jl:330-377: colours one after the other, the cells of a colour in
+   parallel, plain adds): ncolors > 0, color_ptr[ncolors + 1] (0-based offsets) into color_cells (0-based cell ids).
+   ncolors == 0: all cells in one parallel sweep with atomic adds (the how-to's other scheme, :308-310). */
+int64_t oracle_assemble_colored(int element, int dim, int ngeo, int nbs, int vdim, int nq, int64_t ncells, const int64_t* cells,
+                                const double* xyz, const int64_t* cell_dofs, const int64_t* colptr, const int64_t* rowval,
+                                const double* N, const double* dN, const double* dM, const double* w, const double* params,
+                                const double* u, double* nzval, double* f, int nthreads, int ncolors, const int64_t* color_ptr,
+                                const int64_t* color_cells) {
     const int n = nbs * vdim;
     int64_t bad = 0;
     if (n > MAXN || ngeo > MAXG) return -1;
+    const int use_atomic = ncolors <= 0;
+    const int nphases = use_atomic ? 1 : ncolors;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -75,8 +81,11 @@ int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int n
         double fe[MAXN], g[MAXN * 3], x[MAXG * 3];
         int64_t dofs[MAXN], sorted[MAXN];
         int perm[MAXN];
+        for (int phase = 0; phase < nphases; ++phase) {
+        const int64_t i0 = use_atomic ? 0 : color_ptr[phase], i1 = use_atomic ? ncells : color_ptr[phase + 1];
 #pragma omp for schedule(static)
-        for (int64_t ci = 0; ci < ncells; ++ci) {
+        for (int64_t idx = i0; idx < i1; ++idx) {
+            const int64_t ci = use_atomic ? idx : color_cells[idx];
             /* reinit!(cc, i) */
             for (int j = 0; j < ngeo; ++j) {
                 int64_t node = cells[ci * ngeo + j] - 1;
@@ -192,8 +201,12 @@ int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int n
             /* assemble!(assembler, dofs, Ke, fe) */
             if (f)
                 for (int i = 0; i < n; ++i) {
+                    if (use_atomic) {
 #pragma omp atomic
-                    f[dofs[i] - 1] += fe[i];
+                        f[dofs[i] - 1] += fe[i];
+                    } else {
+                        f[dofs[i] - 1] += fe[i];
+                    }
                 }
             sortperm(n, dofs, sorted, perm);
             for (int c = 0; c < n; ++c) {
@@ -205,8 +218,12 @@ int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int n
                     if (row == sorted[r]) {
                         double v = Ke[perm[c] * n + perm[r]];
                         if (v != 0.0) {
+                            if (use_atomic) {
 #pragma omp atomic
-                            nzval[k] += v;
+                                nzval[k] += v;
+                            } else {
+                                nzval[k] += v;
+                            }
                         }
                         ++r;
                         if (r < n && sorted[r] == sorted[r - 1]) continue;  /* duplicate dof: same k again */
@@ -219,9 +236,18 @@ int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int n
                 }
             }
         }
+        }   /* phase: the implicit barrier of the omp for separates the colours */
         free(Ke);
     }
     return bad;
+}
+
+int64_t oracle_assemble(int element, int dim, int ngeo, int nbs, int vdim, int nq, int64_t ncells, const int64_t* cells,
+                        const double* xyz, const int64_t* cell_dofs, const int64_t* colptr, const int64_t* rowval,
+                        const double* N, const double* dN, const double* dM, const double* w, const double* params,
+                        const double* u, double* nzval, double* f, int nthreads) {
+    return oracle_assemble_colored(element, dim, ngeo, nbs, vdim, nq, ncells, cells, xyz, cell_dofs, colptr, rowval, N, dN, dM, w,
+                                   params, u, nzval, f, nthreads, 0, 0, 0);
 }
 
 int oracle_max_threads(void) {

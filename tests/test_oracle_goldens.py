@@ -587,3 +587,31 @@ def test_condensed_pattern_equals_pattern_of_extended_cells():
             pairs.update((r, cc) for r in ext for cc in ext)
         cols = np.repeat(np.arange(1, n + 1), np.diff(K.colptr))
         assert pairs == set(zip(K.rowval.tolist(), cols.tolist())), shape
+
+
+def test_c_port_coloured_scheme_matches_numpy_oracle():
+    # the coloured threading scheme of docs/src/literate-howto/threaded_assembly.jl:330-377 in the C port (CPU baseline):
+    # valid colourings for generate_grid meshes, same K and f as the sequential oracle, bitwise reproducible run to run
+    from oracle import cport
+    lam, mu = O.lame(200e9, 0.3)
+    cases = [("hexahedron", (7, 6, 5), 1, 1, 2, "heat", {"k": 2.0, "source": 3.0}),
+             ("hexahedron", (4, 3, 3), 2, 3, 3, "elasticity", {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)}),
+             ("tetrahedron", (3, 3, 2), 2, 1, 2, "heat", None), ("quadrilateral", (6, 5), 1, 1, 2, "heat", None),
+             ("triangle", (5, 4), 2, 1, 2, "heat", None)]
+    for shape, nel, order, vdim, qo, el, params in cases:
+        dim = len(nel)
+        grid = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * dim, (1,) * dim, 0.2)
+        ip = O.Lagrange(shape, order)
+        ip = ip ** vdim if vdim > 1 else ip
+        dh = O.DofHandler(grid).add("u", ip).close()
+        cv = O.CellValues(O.QuadratureRule(shape, qo), ip)
+        colors = cport.structured_coloring(grid, nel)
+        assert colors[0] == {"hexahedron": 8, "tetrahedron": 48, "quadrilateral": 4, "triangle": 8}[shape]
+        K0, K1, K2 = O.allocate_matrix(dh), O.allocate_matrix(dh), O.allocate_matrix(dh)
+        f0, f1, f2 = np.zeros(dh.ndofs), np.zeros(dh.ndofs), np.zeros(dh.ndofs)
+        O.assemble_global(dh, cv, K0, f0, el, params)
+        cport.assemble(dh, cv, K1, f1, el, params, nthreads=4, colors=colors)
+        cport.assemble(dh, cv, K2, f2, el, params, nthreads=2, colors=colors)
+        assert np.abs(K1.nzval - K0.nzval).max() <= 1e-13 * np.abs(K0.nzval).max()
+        assert np.abs(f1 - f0).max() <= 1e-13 * max(np.abs(f0).max(), 1e-300)
+        assert np.array_equal(K1.nzval, K2.nzval) and np.array_equal(f1, f2)      # threaded_assembly.jl:397-410
