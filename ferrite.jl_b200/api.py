@@ -192,7 +192,86 @@ def generate_grid(celltype, nel, left=None, right=None, ctx=None):
     return Grid(ctx, h)
 
 
+# local vertex ids (1-based) of the facets of every cell type, src/Grid/grid.jl:196-259 (reference_facets)
+_FACETS = {
+    Line: ((1,), (2,)),
+    Triangle: ((1, 2), (2, 3), (3, 1)),
+    Quadrilateral: ((1, 2), (2, 3), (3, 4), (4, 1)),
+    Tetrahedron: ((1, 3, 2), (1, 2, 4), (2, 3, 4), (1, 4, 3)),
+    Hexahedron: ((1, 4, 3, 2), (1, 2, 6, 5), (2, 3, 7, 6), (3, 4, 8, 7), (1, 5, 8, 4), (5, 6, 7, 8)),
+}
+
+
+def _user_sets(grid, kind):
+    if not hasattr(grid, "_sets"):
+        grid._sets = {"facet": {}, "node": {}, "cell": {}}
+    return grid._sets[kind]
+
+
+def _check_setname(sets, name):
+    if name in sets:
+        raise ValueError(f"There already exists a set with the name: {name}")      # src/Grid/utils.jl `_check_setname`
+
+
+def _passes(f, coords, all_):
+    vals = (bool(f(x)) for x in coords)
+    return all(vals) if all_ else any(vals)
+
+
+def addfacetset_(grid, name, f_or_pairs, all=True):
+    """addfacetset!(grid, name, set_or_predicate; all = true) (src/Grid/utils.jl:42-60,119-134): with a predicate f(x), every
+    (cell, local facet) whose vertex coordinates all (any) satisfy f, in lexicographic order; interior facets included."""
+    sets = _user_sets(grid, "facet")
+    _check_setname(sets, name)
+    if callable(f_or_pairs):
+        nodes, cells, out = grid.nodes, grid.cells, []
+        for ci in range(grid.ncells):
+            for fi, verts in enumerate(_FACETS[grid.celltype]):
+                if _passes(f_or_pairs, (nodes[cells[ci, v - 1] - 1] for v in verts), all):
+                    out.append((ci + 1, fi + 1))
+        pairs = np.asarray(out, dtype=np.int64).reshape(-1, 2)
+    else:
+        pairs = _i64(sorted(set(map(tuple, np.asarray(f_or_pairs, dtype=np.int64).reshape(-1, 2).tolist())))).reshape(-1, 2)
+    sets[name] = pairs
+    return grid
+
+
+def addnodeset_(grid, name, f_or_ids):
+    """addnodeset!(grid, name, ids_or_predicate) (src/Grid/utils.jl:29-40,201-207)"""
+    sets = _user_sets(grid, "node")
+    _check_setname(sets, name)
+    if callable(f_or_ids):
+        ids = [i + 1 for i, x in enumerate(grid.nodes) if f_or_ids(x)]
+    else:
+        ids = sorted(set(int(i) for i in f_or_ids))
+    sets[name] = _i64(ids)
+    return grid
+
+
+def addcellset_(grid, name, f_or_ids, all=True):
+    """addcellset!(grid, name, ids_or_predicate; all = true) (src/Grid/utils.jl:21-27,188-200)"""
+    sets = _user_sets(grid, "cell")
+    _check_setname(sets, name)
+    if callable(f_or_ids):
+        nodes, cells = grid.nodes, grid.cells
+        ids = [ci + 1 for ci in range(grid.ncells) if _passes(f_or_ids, (nodes[n - 1] for n in cells[ci]), all)]
+    else:
+        ids = sorted(set(int(i) for i in f_or_ids))
+    sets[name] = _i64(ids)
+    return grid
+
+
+def getnodeset(grid, name):
+    return _user_sets(grid, "node")[name]
+
+
+def getcellset(grid, name):
+    return _user_sets(grid, "cell")[name]
+
+
 def getfacetset(grid, name):
+    if name in _user_sets(grid, "facet"):
+        return _user_sets(grid, "facet")[name]
     n = C.c_int64()
     L.call("fb2_grid_facetset", grid.h, name.encode(), C.byref(n), None)
     out = np.empty((n.value, 2), dtype=np.int64)

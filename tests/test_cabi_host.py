@@ -432,3 +432,44 @@ def test_shared_face_dofs_for_all_hexahedron_orientations(hctx):
                 if vdim == 1:
                     odh = O.DofHandler(O.Grid("hexahedron", [h1, h2], nodes)).add("u", oip).close()
                     assert np.array_equal(cd, odh.cell_dofs)
+
+
+def test_grid_sets_by_predicate_and_by_list(hctx):
+    # addfacetset! / addnodeset! / addcellset! (src/Grid/utils.jl:21-60,119-134,188-207); literals of
+    # test/test_grid_dofhandler_vtk.jl:290-307 and test/test_constraints.jl:416
+    g = fb.generate_grid(fb.Hexahedron, (1, 1, 1), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), ctx=hctx)
+    fb.addcellset_(g, "cell_set", [1])
+    fb.addnodeset_(g, "node_set", [1])
+    fb.addfacetset_(g, "face_set", [(1, 1)])
+    fb.addfacetset_(g, "left_face", lambda x: np.isclose(x[0], 0.0))
+    assert 1 in fb.getnodeset(g, "node_set") and list(fb.getcellset(g, "cell_set")) == [1]
+    assert fb.getfacetset(g, "left_face").tolist() == [[1, 5]] and fb.getfacetset(g, "face_set").tolist() == [[1, 1]]
+    assert np.array_equal(fb.getfacetset(g, "left_face"), fb.getfacetset(g, "left"))
+    with pytest.raises(ValueError):
+        fb.addfacetset_(g, "left_face", [(1, 2)])
+    g = fb.generate_grid(fb.Line, (2,), ctx=hctx)
+    fb.addfacetset_(g, "center", lambda x: np.isclose(x[0], 0.0))
+    assert fb.getfacetset(g, "center").tolist() == [[1, 2], [2, 1]]
+    # the facet tables agree with the oracle's reference shapes, and the generated facet sets are what the predicates find
+    for ct, shape, nel in ((fb.Triangle, "triangle", (3, 2)), (fb.Quadrilateral, "quadrilateral", (3, 2)),
+                           (fb.Tetrahedron, "tetrahedron", (2, 2, 2)), (fb.Hexahedron, "hexahedron", (3, 2, 2))):
+        from ferrite_b200 import api
+        assert api._FACETS[ct] == O.REFSHAPES[shape].facets
+        g = fb.generate_grid(ct, nel, ctx=hctx)
+        fb.addfacetset_(g, "myleft", lambda x: np.isclose(x[0], -1.0))
+        fb.addfacetset_(g, "mytop", lambda x: np.isclose(x[len(nel) - 1], 1.0))
+        assert np.array_equal(fb.getfacetset(g, "myleft"), fb.getfacetset(g, "left"))
+        assert np.array_equal(fb.getfacetset(g, "mytop"), fb.getfacetset(g, "top"))
+        fb.addnodeset_(g, "corner", lambda x: np.allclose(x, -1.0))
+        assert list(fb.getnodeset(g, "corner")) == [1]
+        fb.addcellset_(g, "lower", lambda x: x[len(nel) - 1] <= 0.0)
+        fb.addcellset_(g, "touch", lambda x: x[len(nel) - 1] <= -1.0, all=False)
+        assert 0 < len(fb.getcellset(g, "lower")) < g.ncells and set(fb.getcellset(g, "lower")) <= set(fb.getcellset(g, "touch"))
+    # a Dirichlet condition on a predicate facet set equals the one on the generated set
+    dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(fb.RefHexahedron, 1)))
+    ch1, ch2 = fb.ConstraintHandler(dh), fb.ConstraintHandler(dh)
+    fb.add_(ch1, fb.Dirichlet("u", fb.getfacetset(g, "myleft"), lambda x, t: x[1]))
+    fb.add_(ch2, fb.Dirichlet("u", fb.getfacetset(g, "left"), lambda x, t: x[1]))
+    fb.close_(ch1)
+    fb.close_(ch2)
+    assert np.array_equal(ch1.prescribed_dofs, ch2.prescribed_dofs) and np.array_equal(ch1.inhomogeneities, ch2.inhomogeneities)
