@@ -4,9 +4,12 @@
 // one fused kernel per launch (or one per colour) that covers the reference's whole cell loop; see
 // assemble_kernels.cuh for the kernels and DESIGN.md for the per-kernel byte / flop accounting.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "assemble_kernels.cuh"
+#include "march_kernels.cuh"
 
 namespace {
 
@@ -200,6 +203,50 @@ int dispatch_neohooke(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, i
     return fb2_fail(FB2_ERR_UNSUPPORTED, "Neo-Hooke needs a 3-D cell with a 3-component field");
 }
 
+// fb2_hex8_heat hard-codes the tables of CellValues(QuadratureRule{RefHexahedron}(2), Lagrange{RefHexahedron,1}()): accept a
+// CellValues (library-made or arrays-in) only if its tables agree with them to rounding.
+bool cv_is_q1hex_gauss2(const fb2_cv* cv) {
+    if (cv->celltype != FB2_HEXAHEDRON || cv->nq != 8 || cv->nb != 8 || cv->ngeo != 8 || cv->rdim != 3) return false;
+    const double tol = 4e-15;
+    for (int q = 0; q < 8; ++q) {
+        const int qb[3] = {q & 1, (q >> 1) & 1, (q >> 2) & 1};
+        for (int i = 0; i < 8; ++i) {
+            const int sb[3] = {fb2_hx(i), fb2_hy(i), fb2_hz(i)};
+            double n[3], d[3];
+            for (int a = 0; a < 3; ++a) { n[a] = fb2_q1n(sb[a], qb[a]); d[a] = sb[a] ? 0.5 : -0.5; }
+            const double N = n[0] * n[1] * n[2];
+            const double dN[3] = {d[0] * n[1] * n[2], n[0] * d[1] * n[2], n[0] * n[1] * d[2]};
+            if (std::fabs(cv->N[q * 8 + i] - N) > tol || std::fabs(cv->M[q * 8 + i] - N) > tol) return false;
+            for (int a = 0; a < 3; ++a)
+                if (std::fabs(cv->dN[(q * 8 + i) * 3 + a] - dN[a]) > tol || std::fabs(cv->dM[(q * 8 + i) * 3 + a] - dN[a]) > tol) return false;
+        }
+    }
+    return true;
+}
+
+// The marching-tile kernel keeps one matrix-column copy per tile NODE, so it needs a numbering in which every grid node
+// carries exactly one dof of the (scalar, first-order) field -- true for close!(dh) and any renumber!, false for the
+// broken twin of the element-assembly path (element_assembly.cu), whose cells own private dofs.  Checked once per assembler.
+bool march_usable(fb2_assembler* a) {
+    if (a->march_state == 0) {
+        const fb2_dh* dh = a->dh;
+        const fb2_grid* g = dh->grid;
+        bool ok = dh->ndpc == 8 && g->nnpc == 8 && (int64_t)dh->cell_dofs.size() == g->ncells * 8;
+        if (ok) {
+            std::vector<int32_t> node_dof((size_t)g->nnodes, -1);
+            for (int64_t c = 0; c < g->ncells && ok; ++c)
+                for (int i = 0; i < 8; ++i) {
+                    int32_t& nd = node_dof[(size_t)g->cells[(size_t)c * 8 + i] - 1];
+                    const int32_t d = dh->cell_dofs[(size_t)c * 8 + i];
+                    if (nd < 0) nd = d;
+                    else if (nd != d) { ok = false; break; }
+                }
+        }
+        a->march_state = ok ? 1 : 2;
+    }
+    return a->march_state == 1;
+}
+
 // tile kernel (tiles.cu): whole grid, atomic mode only; falls back to the per-cell kernel when no schedule exists
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
 int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate) {
@@ -227,6 +274,46 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     }
     FB2_TRY(fb2_map_build_packed(a));
     A.map8 = reinterpret_cast<const uint4*>(a->d_map8);
+    // Default for Q1 hexahedra of generate_grid (atomic mode, whole layers): the marching-tile kernel (march_kernels.cuh).
+    // variant 30 forces the thread-per-cell kernel for comparison.
+    if constexpr (DIM == 3 && NGEO == 8 && NB == 8 && NQ == 8) {
+        fb2_grid* g = a->dh->grid;
+        const int64_t lay = g->nel[0] * g->nel[1];
+        if (atomic && (variant == 0 || variant == 31) && g->generated && g->celltype == FB2_HEXAHEDRON && A.cells == nullptr && A.ncount > 0 &&
+            A.cell_first % lay == 0 && A.ncount % lay == 0 && g->nel[0] < (1 << 28) && g->nel[1] < (1 << 28) && march_usable(a)) {
+            MarchArgs M;
+            M.nx = (int)g->nel[0];
+            M.ny = (int)g->nel[1];
+            M.z0 = (int)(A.cell_first / lay);
+            M.z1 = M.z0 + (int)(A.ncount / lay);
+            M.tiles_x = (M.nx + 7) / 8;
+            M.tiles_y = (M.ny + 3) / 4;
+            M.cap = (MARCH_PN * std::max(a->pat->max_col_len, 1) + 1) / 2 * 2;
+            M.overwrite = accumulate ? 0 : 1;
+            const size_t smem = fb2_march_smem(M.cap);
+            if (smem <= 100 * 1024) {
+                // chunk length: about a dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 4
+                // layers keep the share of first / last planes (REDs instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
+                const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 8;
+                const int nzl = M.z1 - M.z0;
+                const int64_t want = std::max<int64_t>(1, 12 * resident / tiles);
+                M.lz = (int)std::max<int64_t>(4, (nzl + want - 1) / want);
+                if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
+                const int nchunks = (nzl + M.lz - 1) / M.lz;
+                // variant 31: table-driven integration inside the marching kernel (A/B against the analytic element)
+                const bool analytic = ELEM == FB2_ELEM_HEAT && variant != 31 && cv_is_q1hex_gauss2(a->cv);
+                auto k = a->map_complete ? (analytic ? k_march_hex<ELEM, false, true> : k_march_hex<ELEM, false, false>)
+                                         : (analytic ? k_march_hex<ELEM, true, true> : k_march_hex<ELEM, true, false>);
+                FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                // eight single-warp CTAs per SM need 8 x 27 KB: ask for the full shared-memory carveout
+                FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                k<<<(unsigned)(tiles * nchunks), 32, smem, ctx->stream>>>(A, M);
+                ctx->launches++;
+                FB2_CUDA(cudaGetLastError());
+                return FB2_OK;
+            }
+        }
+    }
     // variant 6: launch over the warp list, which adds the y-merge through shared memory.  Measured on C2 it removes a
     // further ~20 % of the REDs but costs two CTA barriers and 12 % padding lanes (200 = 6*32 + 8): 2.78 ms vs 2.41 ms
     // with the x-merge alone, so it is not the default.
@@ -236,7 +323,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
         A.wcount = a->d_wcount;
         A.ncount = a->nwarps * 32;
     }
-    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic, variant, a->map_complete);
+    return launch_scalar<DIM, NGEO, NB, NQ, ELEM>(ctx, A, atomic, variant == 30 ? 0 : variant, a->map_complete);
 }
 
 template <int ELEM>

@@ -185,6 +185,8 @@ struct fb2_assembler {
     uint8_t* d_wcount = nullptr;   //   number of cells of the warp (0 for padding warps)
     int64_t nwarps = 0;
     bool map_complete = false;     // every (cell, i, j) has a pattern entry: unchecked scatter allowed
+    int march_state = 0;           // marching-tile kernel: 0 not checked, 1 usable (continuous Q1 numbering on a generated
+                                   // hexahedral grid: every grid node carries ONE dof), 2 not usable
     fb2_dh* dh = nullptr;
     fb2_pattern* pat = nullptr;
     fb2_cv* cv = nullptr;

@@ -165,7 +165,7 @@ def test_assembly_matches_oracle(ctx, case, scatter):
         ou = displacement(og, odh, vdim)
         u = torch.from_numpy(ou).to(f.device)
     O.assemble_global(odh, ocv, oK, of, kind, op, u=ou)
-    variants = [0, 1, 2, 5, 6, 7, 8, 9, 12] if kind in ("heat", "mass") else [0]   # 0 per-cell kernel (x face merge), 1 block kernel, 2 unrolled, 5 tile kernel, 6 x+y face merge
+    variants = [0, 1, 2, 5, 6, 7, 8, 9, 12, 30] if kind in ("heat", "mass") else [0]   # 0 default (marching tiles on generated Q1 hexahedra, else per-cell kernel), 30 per-cell kernel (x face merge), 1 block kernel, 2 unrolled, 5 tile kernel, 6 x+y face merge
     for variant in variants:
         a = fb.start_assemble(K, f, scatter=scatter)
         a.variant = variant
@@ -178,6 +178,68 @@ def test_assembly_matches_oracle(ctx, case, scatter):
         if kind != "mass":
             ok, nrm = close(f.cpu().numpy(), of)
             assert ok, f"f mismatch (variant {variant}): norm-wise {nrm:.3e}"
+
+
+@pytest.mark.parametrize("nel", [(8, 4, 3), (9, 5, 7), (17, 13, 11), (3, 2, 1), (24, 10, 9)])
+@pytest.mark.parametrize("lz", ["1", "3", ""])
+def test_marching_tile_kernel(ctx, nel, lz, monkeypatch):
+    """k_march_hex (default for generate_grid Q1 hexahedra): full / partial tiles, chunk lengths (FB2_MARCH_LZ), zero fill
+    (plain stores for tile-interior columns) and fillzero=false (REDs everywhere), against the oracle and the per-cell kernel."""
+    if lz:
+        monkeypatch.setenv("FB2_MARCH_LZ", lz)
+    else:
+        monkeypatch.delenv("FB2_MARCH_LZ", raising=False)
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, 1, 2, True)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, "heat", dict(k=1.7, source=0.3))
+    elem = fb.HeatElement(k=1.7, source=0.3)
+    a = fb.start_assemble(K, f)
+    K.nzval.fill_(55.0)
+    f.fill_(-3.0)
+    fb.assemble_(a, elem, cv)
+    fb.finish_assemble(a)
+    nz, fv = K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()
+    assert close(nz, oK.nzval)[0] and close(fv, of)[0]
+    a2 = fb.start_assemble(K, f, fillzero=False)     # accumulate onto the first result
+    fb.assemble_(a2, elem, cv)
+    fb.finish_assemble(a2)
+    assert close(K.nzval.cpu().numpy(), 2 * oK.nzval)[0] and close(f.cpu().numpy(), 2 * of)[0]
+    a3 = fb.start_assemble(K, f)
+    a3.variant = 30                                   # thread-per-cell kernel
+    fb.assemble_(a3, elem, cv)
+    fb.finish_assemble(a3)
+    assert close(K.nzval.cpu().numpy(), nz)[0] and close(f.cpu().numpy(), fv)[0]
+
+
+def test_marching_tile_kernel_after_renumbering_and_detj_error(ctx):
+    """the accumulator window follows the global column layout, so any dof numbering works; det(J) <= 0 is reported"""
+    nel = (10, 9, 6)
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, 1, 2, True)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(dh.ndofs) + 1
+    fb.renumber_(dh, perm)
+    O.renumber(odh, perm)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK, of, "heat")
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, fb.HeatElement(), cv)
+    fb.finish_assemble(a)
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
+    xyz = g.nodes.copy()
+    xyz[:, 0] *= -1.0                                 # mirrored cells: det(J) < 0 everywhere
+    g.set_coordinates(xyz)
+    with pytest.raises(fb.DetJNotPositive):
+        a = fb.start_assemble(K, f)
+        fb.assemble_(a, fb.HeatElement(), cv)
+        fb.finish_assemble(a)
 
 
 def test_colored_is_bitwise_reproducible_and_coloring_valid(ctx):
