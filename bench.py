@@ -30,6 +30,9 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (celltype, nel, order, vdim, qr_order, element, B_min bytes/cell, F_min flop/cell)
+    "c1": dict(cell="quad", nel=(100, 100), order=1, vdim=1, qr=2, element="heat", bmin=126.0, fmin=0.45e3,
+               label="heat Q1 quad 100^2 (BASELINE.json configs[0], the reference's CPU tutorial path; 10 000 cells: "
+                     "launch-latency bound, report the time, not the roofline)"),
     "c2": dict(cell="hex", nel=(200, 200, 200), order=1, vdim=1, qr=2, element="heat", bmin=314.0, fmin=4.3e3,
                label="heat Q1 hex 200^3 (BASELINE.json configs[1]), perturbed nodes"),
     "c2s": dict(cell="hex", nel=(64, 64, 64), order=1, vdim=1, qr=2, element="heat", bmin=314.0, fmin=4.3e3,
@@ -127,13 +130,16 @@ def SAMPLE(cfg):
     """bounded CPU sample (cubes per direction) of a configuration"""
     if cfg["element"] == "neohooke":
         return (24, 24, 24)
+    if len(cfg["nel"]) == 2:
+        return tuple(cfg["nel"])
     return (64, 64, 64) if cfg["order"] == 1 else (16, 16, 16)
 
 
 def oracle_problem(cfg, nel):
     import oracle as O
-    shape = "tetrahedron" if cfg.get("cell") == "tet" else "hexahedron"
-    og = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * 3, (1,) * 3, 0.2)
+    shape = {"tet": "tetrahedron", "quad": "quadrilateral"}.get(cfg.get("cell"), "hexahedron")
+    dim = len(nel)
+    og = O.perturb_grid(O.generate_grid(shape, nel), nel, (-1,) * dim, (1,) * dim, 0.2)
     ip = O.Lagrange(shape, cfg["order"])
     ip = ip ** cfg["vdim"] if cfg["vdim"] > 1 else ip
     dh = O.DofHandler(og).add("u", ip).close()
@@ -283,7 +289,9 @@ def main():
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's communicator / transport lines go to stderr (fd 1 is redirected above), so the driver can see them
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
@@ -294,7 +302,7 @@ def main():
     # ---- set-up (not timed): grid, dofs, pattern, map all resident in HBM ------------------------------
     t_setup = time.perf_counter()
     nel = cfg["nel"]
-    ct = fb.Tetrahedron if cfg["cell"] == "tet" else fb.Hexahedron
+    ct = {"tet": fb.Tetrahedron, "quad": fb.Quadrilateral}.get(cfg["cell"], fb.Hexahedron)
     ip = fb.Lagrange(ct, cfg["order"]) ** cfg["vdim"]
     cv = fb.CellValues(fb.QuadratureRule(ct, cfg["qr"]), ip)
     if cfg["element"] == "heat":
@@ -308,7 +316,7 @@ def main():
     if world == 1:
         g = fb.generate_grid(ct, nel).perturb(0.2)
         dh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
-        ncells_total, volume = g.ncells, 8.0
+        ncells_total, volume = g.ncells, 2.0 ** len(nel)
     else:
         # weak scaling: every GPU owns one block of `nel` cells of a px*py*pz times larger box; every rank derives
         # the global numbering (host), its own + halo cells and the interface exchange lists
@@ -325,8 +333,13 @@ def main():
     if cfg["element"] == "neohooke":
         # a deterministic small displacement state (|grad u| ~ 0.03, det F > 0); the work per cell does not depend on it
         u_state = (1e-3 * torch.sin(0.37 * torch.arange(dh.ndofs, dtype=torch.float64))).to(dev)
-    a = fb.start_assemble(K, f, scatter=args.scatter)
-    a.variant = args.variant
+    def new_assembler(f_vec=f, fillzero=True):
+        """start_assemble(K, f): zero fill pending for the next assemble call (the native assembler is cached on K)"""
+        asm = fb.start_assemble(K, f_vec, fillzero=fillzero, scatter=args.scatter)
+        asm.variant = args.variant
+        return asm
+
+    a = new_assembler()
     if part is not None:
         part.bind(a, cv)
         if args.dist_mode == "exchange":
@@ -334,11 +347,11 @@ def main():
             dist.broadcast_object_list(ids, src=0)
             fb.comm_init(ctx, ids[0], world, rank)
 
-    def step(asm):
+    def step(asm=None):
+        """one full assembly: start_assemble (zero fill) + the cell loop [+ interface exchange]"""
         if part is None:
-            fb.assemble_(asm, elem, cv, u=u_state)
+            fb.assemble_(new_assembler(), elem, cv, u=u_state)
         else:
-            part._asm = asm
             part.assemble_(elem, mode=args.dist_mode)
 
     step(a)
@@ -428,9 +441,7 @@ def main():
         ctx.synchronize()
 
     # ---- dominant kernel alone (no zero fill, no exchange) for the roofline -----------------------------------
-    a_nz = fb.start_assemble(K, f, fillzero=False, scatter=args.scatter)
-    a_nz.variant = args.variant
-    a_nz._h = a._h          # reuse the same native assembler (map)
+    a_nz = new_assembler(fillzero=False)
     kreps = max(3, min(args.steps, 10))
     fb.assemble_(a_nz, elem, cv, u=u_state)
     torch.cuda.synchronize()
@@ -441,7 +452,6 @@ def main():
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / kreps
-    a_nz._h = {}
     step(a)       # restore K, f (the accumulating launches above added on top)
     ctx.synchronize()
     fsum_dev = float(f.sum())
@@ -453,9 +463,6 @@ def main():
         nz_host = torch.empty(K.nnz, dtype=torch.float64).pin_memory()
         f_host = torch.empty(dh.ndofs, dtype=torch.float64).pin_memory()
         nz_np, f_np = nz_host.numpy(), f_host.numpy()
-        a_h = fb.start_assemble(K, f if part is not None else None, scatter=args.scatter)
-        a_h.variant = args.variant
-        a_h._h = a._h
         esteps = max(2, min(args.steps, 5))
 
         xyz_np = xyz_host.numpy()
@@ -465,10 +472,10 @@ def main():
             if part is None:
                 # H2D of this step's coordinates, assembly and D2H of nzval + f, pipelined over 8 slabs of cells
                 # (synchronises before returning)
-                fb.assemble_host_streamed(a_h, elem, cv, nz_np, f_np, xyz=xyz_np, u=u_np)
+                fb.assemble_host_streamed(new_assembler(None), elem, cv, nz_np, f_np, xyz=xyz_np, u=u_np)
             else:
                 g.upload_coordinates_async(xyz_host)          # H2D: this step's input
-                step(a_h)
+                step()
                 nz_host.copy_(K.nzval, non_blocking=True)     # D2H of this rank's owned columns / dofs
                 f_host.copy_(f, non_blocking=True)
                 torch.cuda.synchronize()
@@ -480,7 +487,6 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
-        a_h._h = {}
         e2e = {"value": ncells_total * esteps / dt, "unit": "cells/s",
                "h2d_bytes_per_step": int(sum_over_ranks(float(g.nnodes * g.sdim * 8))),
                "d2h_bytes_per_step": int(sum_over_ranks(float((K.nnz + dh.ndofs) * 8))), "steps": esteps,

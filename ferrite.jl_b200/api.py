@@ -416,6 +416,7 @@ class B200Matrix:
         self.n, self.nnz = n.value, nnz.value
         self.nzval = dh.grid.ctx.zeros(self.nnz)
         self._colptr = self._rowval = None
+        self._asm = {}       # native assemblers of this matrix, one per CellValues: id(cv) -> (handle, cv)
 
     def _export(self):
         if self._colptr is None:
@@ -440,6 +441,14 @@ class B200Matrix:
 
     def __del__(self):
         if _destroy is not None:      # module globals are already gone at interpreter shutdown
+            try:
+                alive = getattr(self, "h", None) and all(getattr(p, "h", None) for p in _chain(self, "dh"))
+                for h, _ in getattr(self, "_asm", {}).values():
+                    if alive:
+                        L.lib.fb2_assembler_destroy(h)
+                self._asm = {}
+            except Exception:
+                pass
             _destroy(self, "fb2_pattern_destroy", _chain(self, "dh"))
 
 
@@ -708,24 +717,32 @@ class NeoHookeElement(ElasticityElement):
 
 # ---- assembler ------------------------------------------------------------------------------------------------------
 class Assembler:
+    """The assembler start_assemble returns.  The native assembler (the cell-local -> nzval map, src/assembler.jl:347-457) is
+    cached on the matrix per CellValues, so calling start_assemble before every assembly -- as the reference does -- is free.
+    `fillzero` is consumed by the first assemble_ / scatter_ call: start_assemble zeroes K and f ONCE (src/assembler.jl:
+    287-291), every later call on the same assembler adds onto the result."""
+
     def __init__(self, K, f, fillzero=True, scatter="atomic"):
         self.K, self.f = K, f
         self.fillzero = fillzero
         self.scatter = scatter
         self.variant = 0
-        self._h = {}
 
     def _handle(self, cv):
+        cache = self.K._asm
         key = id(cv)
-        if key not in self._h:
+        if key not in cache:
             h = C.c_void_p()
             L.call("fb2_assembler_create", self.K.dh.h, self.K.h, cv.h if cv is not None else None, C.byref(h))
-            self._h[key] = (h, cv)
-        return self._h[key][0]
+            cache[key] = (h, cv)
+        return cache[key][0]
 
     def _opts(self):
-        return L.AsmOpts(1 if self.fillzero else 0, L.SCATTER_COLORED if self.scatter == "colored" else L.SCATTER_ATOMIC,
-                         self.variant, 0)
+        """options of the next native call; the pending zero fill is handed to that call and cleared"""
+        o = L.AsmOpts(1 if self.fillzero else 0, L.SCATTER_COLORED if self.scatter == "colored" else L.SCATTER_ATOMIC,
+                      self.variant, 0)
+        self.fillzero = False
+        return o
 
     def coloring(self, cv=None):
         h = self._handle(cv)
@@ -734,19 +751,11 @@ class Assembler:
         L.call("fb2_assembler_coloring", h, C.byref(nc), _ptr(col, C.c_int32))
         return nc.value, col
 
-    def __del__(self):
-        try:
-            alive = all(getattr(p, "h", None) for p in [self.K] + _chain(self.K, "dh"))
-            for h, _ in self._h.values():
-                if alive:
-                    L.lib.fb2_assembler_destroy(h)
-            self._h = {}
-        except Exception:
-            pass
-
 
 def start_assemble(K, f=None, fillzero=True, scatter="atomic"):
-    """start_assemble(K, f; fillzero) -- the zero fill happens inside the next assemble_ call."""
+    """start_assemble(K, f; fillzero): K.nzval and f are zeroed once -- the fill is fused into the FIRST assemble_ call on the
+    returned assembler (nothing may read K in between); later assemble_ calls on the same assembler accumulate, like
+    repeated assemble! calls of the reference."""
     return Assembler(K, f, fillzero, scatter)
 
 
@@ -1089,6 +1098,7 @@ class Partition:
         return dict(send_rows=a[0], send_cols=a[1], recv_rows=a[2], recv_cols=a[3], send_f=a[4], recv_f=a[5])
 
     def bind(self, assembler, cv):
+        assembler._accumulate = not assembler.fillzero
         self._asm = assembler
         self._cv = cv
         L.call("fb2_partition_bind", self.h, assembler._handle(cv))
@@ -1109,7 +1119,10 @@ class Partition:
         """assemble! for this rank: mode 'exchange' (own cells + NCCL interface exchange, needs comm_init) or
         'halo' (own + halo cells, no communication); the local K / f then hold the final owned columns / dofs."""
         a = self._asm
-        opts = a._opts()
+        # one call = start_assemble + the cell loop + exchange: the local K / f are zero-filled every time unless the bound
+        # assembler was created with fillzero=False
+        opts = L.AsmOpts(0 if getattr(a, "_accumulate", False) else 1,
+                         L.SCATTER_COLORED if a.scatter == "colored" else L.SCATTER_ATOMIC, a.variant, 0)
         L.call("fb2_assemble_distributed", a._handle(self._cv), self.h,
                {"halo": L.DIST_HALO, "exchange": L.DIST_EXCHANGE, "own": L.DIST_OWN_ONLY}[mode],
                element.elem_id, C.byref(element.params), C.sizeof(element.params),

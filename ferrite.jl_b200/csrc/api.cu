@@ -1,4 +1,5 @@
 // Context, CellValues and assembler entry points of the C ABI (see include/ferrite_b200.h).
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -22,6 +23,11 @@ int fb2_fail(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+uint64_t fb2_next_uid() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
 }
 
 extern "C" const char* fb2_version(void) { return "ferrite_b200 0.1.0 (sm_100a)"; }
@@ -146,6 +152,7 @@ extern "C" int fb2_cellvalues_create(fb2_ctx* ctx, int celltype, int qr_order, i
     FB2_CHECK(fb2_lagrange(celltype, geo_order, &geo), FB2_ERR_UNSUPPORTED, "CellValues: geometric order %d not supported", geo_order);
     FB2_CHECK(vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "CellValues: vdim must be 1..3");
     fb2_cv* cv = new fb2_cv();
+    cv->uid = fb2_next_uid();
     cv->ctx = ctx;
     cv->celltype = celltype;
     cv->rdim = ip.rdim;
@@ -180,6 +187,7 @@ extern "C" int fb2_cellvalues_from_tables(fb2_ctx* ctx, int celltype, int nq, in
     FB2_CHECK(rd > 0, FB2_ERR_BAD_ARG, "fb2_cellvalues_from_tables: unknown cell type %d", celltype);
     FB2_CHECK(nq >= 1 && n >= 1 && ngeo >= 1 && vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "fb2_cellvalues_from_tables: bad sizes");
     fb2_cv* cv = new fb2_cv();
+    cv->uid = fb2_next_uid();
     cv->ctx = ctx;
     cv->celltype = celltype;
     cv->rdim = rd;
@@ -225,7 +233,6 @@ extern "C" int fb2_cellvalues_export(fb2_cv* cv, double* N, double* dNdxi, doubl
 
 extern "C" int fb2_cellvalues_destroy(fb2_cv* cv) {
     if (!cv) return FB2_OK;
-    if (cv->ctx && cv->ctx->const_tables_owner == cv) cv->ctx->const_tables_owner = nullptr;
     if (cv->d_tables) cudaFree(cv->d_tables);
     delete cv;
     return FB2_OK;
@@ -242,6 +249,10 @@ extern "C" int fb2_assembler_create(fb2_dh* dh, fb2_pattern* p, fb2_cv* cv, fb2_
                   "fb2_assembler_create: the element must cover all %d dofs of a cell (CellValues has %d)", dh->ndpc, cv->nb * cv->vdim);
         FB2_CHECK(cv->ngeo == dh->grid->nnpc, FB2_ERR_BAD_ARG, "fb2_assembler_create: geometric interpolation has %d nodes, cells have %d", cv->ngeo, dh->grid->nnpc);
         FB2_CHECK(cv->rdim == dh->grid->sdim, FB2_ERR_UNSUPPORTED, "embedded elements (rdim %d in sdim %d) are not supported", cv->rdim, dh->grid->sdim);
+        // kernels, zero fills and table uploads all run on the GRID's context (stream); a CellValues made on another
+        // context of the same device is fine, one made for another device is not
+        FB2_CHECK(cv->ctx == nullptr || cv->ctx->device == dh->grid->ctx->device, FB2_ERR_BAD_ARG,
+                  "fb2_assembler_create: the CellValues live on device %d, the grid on device %d", cv->ctx->device, dh->grid->ctx->device);
     }
     fb2_assembler* a = new fb2_assembler();
     a->dh = dh;
@@ -422,6 +433,7 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     cudaSetDevice(a->dh->grid->ctx->device);
     cudaFree(a->d_map);
     cudaFree(a->d_map8);
+    cudaFree(a->d_mapb);
     cudaFree(a->d_mapc);
     cudaFree(a->d_dofc);
     cudaFree(a->d_basec);

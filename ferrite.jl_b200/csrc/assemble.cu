@@ -13,9 +13,13 @@
 
 namespace {
 
+// c_tab is one module-global array per DEVICE, whatever the number of contexts on it: the owner is tracked per device
+// (by the CellValues' never-reused uid), not per context.
+uint64_t g_const_tables_uid[64] = {};
+
 int upload_tables(fb2_assembler* a, AsmArgs* A) {
     fb2_cv* cv = a->cv;
-    fb2_ctx* ctx = cv->ctx;
+    fb2_ctx* ctx = a->dh->grid->ctx;   // everything of an assembly runs on the grid's context / stream
     const int nq = cv->nq, nb = cv->nb, ng = cv->ngeo, rd = cv->rdim;
     A->nq = nq;
     A->o_w = 0;
@@ -27,7 +31,8 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
     // tables larger than the constant bank (e.g. Q2 hexahedra with a 4x4x4 rule) are served from the global copy alone:
     // only the thread-per-cell kernels read c_tab, and those shapes are handled by the CTA kernels anyway
     A->const_ok = total <= FB2_TAB_MAX;
-    if (ctx->const_tables_owner != cv || cv->d_tables == nullptr) {
+    uint64_t& owner = g_const_tables_uid[ctx->device & 63];
+    if (owner != cv->uid || cv->d_tables == nullptr) {
         std::vector<double> h(total);
         memcpy(h.data() + A->o_w, cv->w.data(), sizeof(double) * nq);
         memcpy(h.data() + A->o_N, cv->N.data(), sizeof(double) * nq * nb);
@@ -38,7 +43,7 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
         if (A->const_ok) {
             FB2_CUDA(cudaMemcpyToSymbolAsync(c_tab, h.data(), sizeof(double) * total, 0, cudaMemcpyHostToDevice, ctx->stream));
             FB2_CUDA(cudaStreamSynchronize(ctx->stream));
-            ctx->const_tables_owner = cv;
+            owner = cv->uid;
         }
         if (cv->d_tables == nullptr) {   // global copy: the CTA kernels index the tables per lane, which a constant bank serialises
             FB2_CUDA(cudaMalloc(&cv->d_tables, sizeof(double) * total));
@@ -288,12 +293,15 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
             M.z1 = M.z0 + (int)(A.ncount / lay);
             M.tiles_x = (M.nx + 7) / 8;
             M.tiles_y = (M.ny + 3) / 4;
-            M.cap = (MARCH_PN * std::max(a->pat->max_col_len, 1) + 1) / 2 * 2;
+            M.cap = fb2_march_cap(std::max(a->pat->max_col_len, 1));
             M.overwrite = accumulate ? 0 : 1;
             const size_t smem = fb2_march_smem(M.cap);
-            if (smem <= 100 * 1024) {
+            // the bulk (TMA) flush needs 16-byte aligned matrix storage and columns short enough for the byte-packed map
+            if (smem <= 100 * 1024 && M.cap < 65536 && a->pat->max_col_len < 255 && (reinterpret_cast<uintptr_t>(A.nzval) & 15) == 0) {
+                FB2_TRY(fb2_map_build_bytes(a));
+                M.mapb = a->d_mapb;
                 // chunk length: about a dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 4
-                // layers keep the share of first / last planes (REDs instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
+                // layers keep the share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
                 const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 8;
                 const int nzl = M.z1 - M.z0;
                 const int64_t want = std::max<int64_t>(1, 12 * resident / tiles);
@@ -305,7 +313,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 auto k = a->map_complete ? (analytic ? k_march_hex<ELEM, false, true> : k_march_hex<ELEM, false, false>)
                                          : (analytic ? k_march_hex<ELEM, true, true> : k_march_hex<ELEM, true, false>);
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                // eight single-warp CTAs per SM need 8 x 27 KB: ask for the full shared-memory carveout
+                // eight single-warp CTAs per SM need 8 x 28 KB: ask for the full shared-memory carveout
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 k<<<(unsigned)(tiles * nchunks), 32, smem, ctx->stream>>>(A, M);
                 ctx->launches++;
@@ -479,7 +487,7 @@ int fb2_coloring_build(fb2_assembler* a) {
 
 static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, int variant, int accumulate) {
     fb2_cv* cv = a->cv;
-    fb2_ctx* ctx = cv->ctx;
+    fb2_ctx* ctx = a->dh->grid->ctx;
     const int ct = cv->celltype, nbs = cv->nb, vdim = cv->vdim;
     int rc = FB2_OK;
     switch (element) {

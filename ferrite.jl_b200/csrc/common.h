@@ -79,6 +79,7 @@ std::vector<std::vector<int>> fb2_boundarydof_indices(const LagrangeInfo& ip, in
 bool fb2_quadrature(int celltype, int order, std::vector<double>* w, std::vector<double>* pts);
 
 // ---- objects --------------------------------------------------------------------------------
+uint64_t fb2_next_uid();   // process-wide, starts at 1, never repeats (api.cu)
 struct fb2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -87,7 +88,6 @@ struct fb2_ctx {
     int64_t launches = 0;
     int* d_errflag = nullptr;   // [0] = code, [1] = cell id
     int* h_errflag = nullptr;   // pinned
-    const void* const_tables_owner = nullptr;  // fb2_cv whose tables are currently in __constant__ memory
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     // copy streams + events of the streamed host-buffer entry point (lazy)
@@ -149,6 +149,7 @@ struct fb2_pattern {
 
 struct fb2_cv {
     fb2_ctx* ctx = nullptr;
+    uint64_t uid = 0;             // never reused: identifies the tables resident in the device's __constant__ bank
     int celltype = 0;
     int rdim = 0, nq = 0, nb = 0, vdim = 1, ngeo = 0;
     int ip_order = 0, geo_order = 0, qr_order = 0;
@@ -195,6 +196,7 @@ struct fb2_assembler {
     uint16_t* d_mapc = nullptr;    // cell-major copy for k_cell_blocks: [ncells][ceil8(n*n)] (lazy)
     int32_t* d_dofc = nullptr;     // cell-major dofs for the CTA kernels: [ncells][n] (built with d_mapc)
     int64_t* d_basec = nullptr;    //   and their column bases colptr[dof]
+    uint8_t* d_mapb = nullptr;     // byte-packed copy for the marching-tile kernel: [ceil(n*n/16)][ncells_pad][16] (lazy)
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     // colouring (lazy)
     int ncolors = 0;
@@ -259,6 +261,7 @@ int fb2_pattern_build_device(fb2_pattern* p);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
 int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);
+int fb2_map_build_bytes(fb2_assembler* a);
 int fb2_map_build_cellmajor(fb2_assembler* a);
 int fb2_tiles_build(fb2_assembler* a, int TC);
 int fb2_warplist_build(fb2_assembler* a);

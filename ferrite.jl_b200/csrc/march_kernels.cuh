@@ -4,8 +4,7 @@
 // What limits the thread-per-cell kernels on B200 (scripts/micro/red_micro.cu, profiles/r02_red_micro.txt): FP64 REDs whose
 // 32 lanes land in 32 different sectors run at 120-160 G elements/s chip-wide, coalesced plain stores at 760 G/s, and one
 // Q1 hexahedron needs 50 such REDs after the x-face merge -- 8 M cells x 50 = 2.5 ms of RED time against 1.2 ms of FP64
-// work.  The way out is to sum the 8 cell contributions of an entry ON CHIP and to write finished matrix columns with
-// coalesced stores:
+// work.  The way out is to sum the 8 cell contributions of an entry ON CHIP and to write finished matrix columns in bulk:
 //
 //   * a warp owns a tile of 8 x 4 cells in (x, y) and marches through the layers z = zb .. ze-1 of its chunk, one cell per
 //     lane and layer (the same reinit! + element routine as k_cell_scalar: src/FEValues/CellValues.jl:122-140,
@@ -15,11 +14,13 @@
 //     assemble! indexes it, so any dof numbering works, src/assembler.jl:347-457).  Lanes add their Ke entries with plain
 //     shared-memory read-modify-writes, ordered in batches such that no two lanes of one instruction hit the same entry
 //     (local pairs (i, j) with the same node offset alias across cells, pairs with different offsets never do);
-//   * after layer z the columns of node plane z are final inside the tile: columns of tile-interior nodes have received
-//     every contribution they will ever get and are written once with coalesced plain stores (216 contiguous bytes per
-//     column; no zero fill and no read-for-ownership needed for them); columns on the tile faces, and the first and last
-//     plane of a chunk, are shared with neighbouring warps and go out as REDs (12.75 per cell instead of 50, and those
-//     are coalesced along the column as well);
+//   * after layer z the columns of node plane z are final inside the tile.  They leave the SM through the TMA engine:
+//     the seven tile-interior columns of a tile row are one contiguous piece of nzval (1.5 KB) that has received every
+//     contribution it will ever get -- ONE bulk copy shared -> global (cp.async.bulk, no zero fill and no read-for-ownership
+//     needed); the columns of the tile faces (shared with the neighbouring tiles) and the first / last plane of a chunk go
+//     out as bulk reduce-adds (cp.reduce.async.bulk.add.f64).  15 bulk operations per layer replace 1600 per-lane REDs; the
+//     copies of the columns are placed at the parity of their global position so that both ends are 16-byte aligned;
+//   * node coordinates and dofs of the next node plane are prefetched (cp.async) while a layer is integrated;
 //   * no CTA barrier anywhere: one warp per CTA, so the FP64 phase of one warp overlaps the shared-memory and store
 //     phases of the others.
 #pragma once
@@ -29,17 +30,22 @@ struct MarchArgs {
     int z0, z1;            // layers [z0, z1) of this launch
     int tiles_x, tiles_y;  // tiles of 8 x 4 cells per layer
     int lz;                // layers per chunk (one warp marches through one chunk of one tile)
-    int cap;               // accumulator doubles per node plane: 45 x (longest matrix column), even
+    int cap;               // accumulator doubles per node plane: 45 x (longest matrix column) + 48 parity pads, even
     int overwrite;         // 1: nzval / f were zero-filled for this launch and nobody else adds to tile-interior columns
-                           //    => they are written with plain stores; 0: everything is added with REDs
+                           //    => they are written with plain (bulk) stores; 0: everything is added
+    const uint8_t* mapb;   // byte-packed offset map (fb2_map_build_bytes)
 };
 
 constexpr int MARCH_PN = 45;   // nodes of a tile plane (9 x 5)
 constexpr int MARCH_PS = 48;   // padded
 
+__host__ __device__ inline int fb2_march_cap(int max_col_len) { return (MARCH_PN * max_col_len + MARCH_PS + 1) / 2 * 2; }
+// doubles: [2][cap] matrix window | [2][PS] load vector | [32] dummies | [2][PS][4] node coordinates; then colptr[dof] (int64),
+// dof (int), column start (uint16) and length (uint8) per window plane and tile node; then the staged offset map (4 x 16 bytes
+// per lane).  27.2 KB for Q1 hexahedra: eight single-warp CTAs per SM.
 __host__ __device__ inline size_t fb2_march_smem(int cap) {
-    return sizeof(double) * (2 * (size_t)cap + 2 * MARCH_PS + 32) + sizeof(int64_t) * 2 * MARCH_PS + sizeof(int) * 4 * MARCH_PS +
-           sizeof(uint4) * 8 * 32;
+    return sizeof(double) * (2 * (size_t)cap + 2 * MARCH_PS + 32 + 2 * MARCH_PS * 4) + sizeof(int64_t) * 2 * MARCH_PS +
+           sizeof(int) * (2 * MARCH_PS + 8) + sizeof(uint16_t) * 2 * MARCH_PS + sizeof(uint8_t) * 2 * MARCH_PS + sizeof(uint4) * 4 * 32;
 }
 
 // local node positions of the 8-node hexahedron (src/Grid/grid_generators.jl:170-178)
@@ -66,6 +72,17 @@ __host__ __device__ constexpr MarchBatches fb2_march_batches() {
     return r;
 }
 
+// ---- TMA bulk operations (1-D, shared::cta -> global), tracked by the issuing thread's bulk async-group -------------------
+__device__ __forceinline__ void fb2_bulk_store(double* gdst, const double* ssrc, int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fb2_bulk_red_add(double* gdst, const double* ssrc, int bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fb2_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fb2_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fb2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Set-up of a node plane of the tile, first half: every lane publishes the dofs of the four nodes of its cell that lie in
 // the plane and the column extents of tile nodes `lane` and `lane + 32` are requested.
 __device__ __forceinline__ void fb2_march_plane_issue(int* s_dof, const int64_t* __restrict__ colptr, int lane, int tn0, bool inside,
@@ -86,8 +103,13 @@ __device__ __forceinline__ void fb2_march_plane_issue(int* s_dof, const int64_t*
     if (dB >= 0) { bB = __ldg(colptr + dB); lenB = (int)(__ldg(colptr + dB + 1) - bB); }
 }
 
-// second half: exclusive scan of the column lengths = start of every column copy inside the plane's accumulator
-__device__ __forceinline__ void fb2_march_plane_finish(int* s_cs, int64_t* s_gb, int lane, int64_t bA, int64_t bB, int lenA, int lenB) {
+// Second half: position of every column copy inside the plane's accumulator = exclusive scan of the column lengths plus
+// parity pads, such that copy and global column start at the same parity (entry index mod 2): with 16-byte aligned bases
+// the bulk operations of the flush then see 16-byte aligned addresses on both sides after peeling at most one entry.  Columns
+// that are adjacent in nzval stay adjacent in the accumulator (no pad between them).  *rowok: bit b = the seven interior
+// columns of tile row b are one contiguous piece of nzval.
+__device__ __forceinline__ void fb2_march_plane_finish(uint16_t* s_cs, uint8_t* s_len, int64_t* s_gb, int* s_rowok, int lane, int64_t bA, int64_t bB,
+                                                       int lenA, int lenB) {
     const unsigned full = 0xffffffffu;
     int sA = lenA, sB = lenB;
 #pragma unroll
@@ -96,61 +118,94 @@ __device__ __forceinline__ void fb2_march_plane_finish(int* s_cs, int64_t* s_gb,
         if (lane >= o) { sA += t; sB += u; }
     }
     const int totA = __shfl_sync(full, sA, 31);
-    s_cs[lane] = sA - lenA;
+    const int csA = sA - lenA, csB = totA + sB - lenB;
+    // parity mismatch of the unpadded layout, pad where it changes
+    const int tA = (csA + (int)bA) & 1, tB = (csB + (int)bB) & 1;
+    const int tA31 = __shfl_sync(full, tA, 31);
+    int pvA = __shfl_up_sync(full, tA, 1), pvB = __shfl_up_sync(full, tB, 1);
+    if (lane == 0) { pvA = 0; pvB = tA31; }
+    int pA = tA ^ pvA, pB = tB ^ pvB;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(full, pA, o), u = __shfl_up_sync(full, pB, o);
+        if (lane >= o) { pA += t; pB += u; }
+    }
+    const int totP = __shfl_sync(full, pA, 31);
+    s_cs[lane] = (uint16_t)(csA + pA);
+    s_len[lane] = (uint8_t)lenA;
     s_gb[lane] = bA;
-    if (lane < MARCH_PS - 32) {   // entries 45..47 have length 0, so s_cs[45] is the total
-        s_cs[lane + 32] = totA + sB - lenB;
+    if (lane < MARCH_PS - 32) {
+        s_cs[lane + 32] = (uint16_t)(csB + totP + pB);
+        s_len[lane + 32] = (uint8_t)lenB;
         s_gb[lane + 32] = bB;
+    }
+    // contiguity of neighbouring columns: column n + 1 starts where column n ends
+    int64_t nbA = __shfl_down_sync(full, bA, 1);
+    const int64_t nbB = __shfl_down_sync(full, bB, 1), bB0 = __shfl_sync(full, bB, 0);
+    if (lane == 31) nbA = bB0;
+    const unsigned mA = __ballot_sync(full, lenA > 0 && nbA == bA + lenA), mB = __ballot_sync(full, lenB > 0 && nbB == bB + lenB);
+    if (lane == 0) {
+        const unsigned long long m = (unsigned long long)mA | ((unsigned long long)mB << 32);
+        int ok = 0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b)
+            if (((m >> (9 * b + 1)) & 0x3Full) == 0x3Full) ok |= 1 << b;
+        *s_rowok = ok;
     }
     __syncwarp();
 }
 
-// FP64 RED that skips exact zeros without a branch (entries of a face column this tile never touched stay untouched)
-__device__ __forceinline__ void fb2_red_nz(double* p, double v) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f64 p, %1, 0d0000000000000000;\n\t@p red.global.add.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v) : "memory");
-}
-
-// entries [c0, c1) of a plane accumulator -> nzval[g0 + (e - c0)], plain stores or REDs; the accumulator is zeroed for reuse
+// One piece of a finished plane: columns n0 .. n0 + cnt - 1 (adjacent in nzval and in the accumulator) -> global memory,
+// as a bulk copy (STORE) or a bulk reduce-add, after peeling a leading / trailing entry where the piece starts / ends on
+// an odd entry.  Called by ONE lane per piece.
 template <bool STORE>
-__device__ __forceinline__ void fb2_march_flush_run(double* __restrict__ acc, double* __restrict__ nzval, int c0, int c1, int64_t g0, int lane) {
-    double* g = nzval + (g0 - c0);
-    for (int e = c0 + lane; e < c1; e += 32) {
-        const double v = acc[e];
-        acc[e] = 0.0;
-        if (STORE) g[e] = v;
-        else fb2_red_nz(g + e, v);
+__device__ __forceinline__ void fb2_march_emit(double* __restrict__ nzval, const double* acc, const uint16_t* s_cs, const uint8_t* s_len, const int64_t* s_gb,
+                                               int n0, int cnt) {
+    const int c0 = s_cs[n0];
+    int total = (int)s_cs[n0 + cnt - 1] + (int)s_len[n0 + cnt - 1] - c0;
+    if (total <= 0) return;
+    const int64_t g0 = s_gb[n0];
+    double* g = nzval + g0;
+    const double* a = acc + c0;
+    if (g0 & 1) {
+        if (STORE) g[0] = a[0]; else atomicAdd(g, a[0]);
+        ++g; ++a; --total;
+    }
+    const int body = total & ~1;
+    if (body) {
+        if (STORE) fb2_bulk_store(g, a, body * 8); else fb2_bulk_red_add(g, a, body * 8);
+    }
+    if (total & 1) {
+        if (STORE) g[body] = a[body]; else atomicAdd(g + body, a[body]);
     }
 }
 
-// Write a finished node plane out (and zero its accumulator for reuse).  Tile-interior columns (a = 1..7, b = 1..3) have
-// every contribution they will ever get: plain stores unless `redall`; the columns of the tile faces are shared with
-// the neighbouring tiles: REDs.  The columns of the seven interior nodes of a tile row are one contiguous run of nzval
-// whenever their dofs are consecutive (the reference's numbering away from the grid boundary): six fully coalesced
-// requests instead of seven column-sized ones; other numberings take the column-by-column path.
-__device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, double* acc, double* sf, const int* s_cs, const int64_t* s_gb,
-                                                const int* s_dof, int lane, bool redall, bool with_f) {
-    const unsigned full = 0xffffffffu;
-#pragma unroll 1
-    for (int b = 0; b < 5; ++b) {
-        const int r0 = b * 9;
-        const bool st = !redall && b >= 1 && b <= 3;
-        bool okc = true;
-        if (lane < 6) {
-            const int n = r0 + 1 + lane;
-            okc = s_gb[n + 1] == s_gb[n] + (s_cs[n + 1] - s_cs[n]);
+// Write a finished node plane out.  Lane s < 15 takes piece s: tile row b = s / 3, part 0 / 2 = the face columns a = 0 / 8
+// (reduce-add: shared with the neighbouring tiles), part 1 = the interior columns a = 1..7 (copy unless `redall` or the row
+// is a tile face, b = 0 / 4).  Rows whose interior columns are not contiguous in nzval (irregular numbering) are written
+// column by column by lanes 16..22.  The accumulator is NOT zeroed here: the bulk operations read it asynchronously;
+// fb2_bulk_wait_read + a zero fill precede its next use.
+__device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, const double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
+                                                const int64_t* s_gb, const int* s_dof, int rowok, int lane, bool redall, bool with_f) {
+    fb2_fence_async_smem();   // the read-modify-writes of this warp (generic proxy) -> visible to the bulk engine (async proxy)
+    __syncwarp();
+    if (lane < 15) {
+        const int b = lane / 3, part = lane - 3 * b, r0 = 9 * b;
+        if (part == 0) fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0, 1);
+        else if (part == 2) fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 8, 1);
+        else if ((rowok >> b) & 1) {
+            if (!redall && b >= 1 && b <= 3) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 1, 7);
+            else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 1, 7);
         }
-        if (__all_sync(full, okc)) {
-            fb2_march_flush_run<false>(acc, A.nzval, s_cs[r0], s_cs[r0 + 1], s_gb[r0], lane);
-            if (st) fb2_march_flush_run<true>(acc, A.nzval, s_cs[r0 + 1], s_cs[r0 + 8], s_gb[r0 + 1], lane);
-            else fb2_march_flush_run<false>(acc, A.nzval, s_cs[r0 + 1], s_cs[r0 + 8], s_gb[r0 + 1], lane);
-            fb2_march_flush_run<false>(acc, A.nzval, s_cs[r0 + 8], s_cs[r0 + 9], s_gb[r0 + 8], lane);
-        } else {
-#pragma unroll 1
-            for (int a = 0; a < 9; ++a) {
-                if (st && a >= 1 && a <= 7) fb2_march_flush_run<true>(acc, A.nzval, s_cs[r0 + a], s_cs[r0 + a + 1], s_gb[r0 + a], lane);
-                else fb2_march_flush_run<false>(acc, A.nzval, s_cs[r0 + a], s_cs[r0 + a + 1], s_gb[r0 + a], lane);
-            }
+        fb2_bulk_commit();
+    } else if (lane >= 16 && lane < 23 && rowok != 31) {
+        for (int b = 0; b < 5; ++b) {
+            if ((rowok >> b) & 1) continue;
+            const int n = 9 * b + 1 + (lane - 16);
+            if (!redall && b >= 1 && b <= 3) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, n, 1);
+            else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, n, 1);
         }
+        fb2_bulk_commit();
     }
     if (with_f) {
 #pragma unroll
@@ -162,7 +217,7 @@ __device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, double* acc, d
                 sf[n] = 0.0;
                 const int a = n % 9, b = n / 9;
                 if (!redall && a >= 1 && a <= 7 && b >= 1 && b <= 3) A.f[d] = v;
-                else fb2_red_nz(A.f + d, v);
+                else if (v != 0.0) atomicAdd(A.f + d, v);
             }
         }
     }
@@ -179,7 +234,7 @@ __device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, double* acc, d
 //   * grad N_i = dN_i/dxi . adj(J) / det: the division by det is folded into the weight (dOmega / det^2);
 //   * constant functions are in the kernel of the operator, so Ke_ii = -sum_{j != i} Ke_ij: only the 28 strict upper
 //     entries are accumulated;
-//   * all shape-function values are compile-time constants (no table loads).
+//   * the shape-function values are two constants (no table loads).
 // Point q = qx + 2 qy + 4 qz sits at ((2 qx - 1) g, (2 qy - 1) g, (2 qz - 1) g), g = 1/sqrt(3) (src/Quadrature/
 // quadrature.jl:96-104: first coordinate fastest, points ascending); w[q] comes from the CellValues.
 // ------------------------------------------------------------------------------------------------------------------------
@@ -188,92 +243,100 @@ __host__ __device__ constexpr double fb2_q1n(int s, int p) {   // 1-D linear sha
 }
 __host__ __device__ constexpr int fb2_hexnode(int sx, int sy, int sz) { return sz * 4 + (sy ? (sx ? 2 : 3) : (sx ? 1 : 0)); }
 
+// The loop over (qy, qz) is ROLLED (four iterations of a body that handles the two points qx = 0, 1): the fully unrolled
+// body is 35 KB of SASS, and with eight independent warps per SM at different places of it the instruction fetch stalls
+// cost more (29 % of all stall samples, profiles/r02_prof_c2_march_c.txt) than the shared sub-expressions save.
 __device__ __forceinline__ bool fb2_hex8_heat(const double (&x)[8][3], const double* __restrict__ tw, double (&Ke)[36], double (&fe)[8]) {
+    constexpr double NA = fb2_q1n(0, 0), NB = fb2_q1n(1, 0);   // shape function of the near / far node of a Gauss point
 #pragma unroll
     for (int e = 0; e < 36; ++e) Ke[e] = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) fe[i] = 0.0;
     bool bad = false;
-    double dz[2][2][3];   // (x(sx,sy,1) - x(sx,sy,0)) / 2
-#pragma unroll
-    for (int sx = 0; sx < 2; ++sx)
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        const int qy = it & 1, qz = it >> 1;
+        const double ny[2] = {qy ? NB : NA, qy ? NA : NB}, nz[2] = {qz ? NB : NA, qz ? NA : NB};
+        double w[2][2], hw[2][2];       // ny nz and half of it
 #pragma unroll
         for (int sy = 0; sy < 2; ++sy)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) dz[sx][sy][c] = 0.5 * (x[fb2_hexnode(sx, sy, 1)][c] - x[fb2_hexnode(sx, sy, 0)][c]);
-#pragma unroll
-    for (int qz = 0; qz < 2; ++qz) {
-        double xz[2][2][3];   // position interpolated along z
+            for (int sz = 0; sz < 2; ++sz) { w[sy][sz] = ny[sy] * nz[sz]; hw[sy][sz] = 0.5 * w[sy][sz]; }
+        const double hny[2] = {0.5 * ny[0], 0.5 * ny[1]}, hnz[2] = {0.5 * nz[0], 0.5 * nz[1]};
+        // the x-line through the two points: its end points P[sx], and d x / d eta, d x / d zeta at the ends
+        double P[2][3], Dy[2][3], Dz[2][3];
 #pragma unroll
         for (int sx = 0; sx < 2; ++sx)
 #pragma unroll
-            for (int sy = 0; sy < 2; ++sy)
+            for (int c = 0; c < 3; ++c) {
+                const double x00 = x[fb2_hexnode(sx, 0, 0)][c], x10 = x[fb2_hexnode(sx, 1, 0)][c];
+                const double x01 = x[fb2_hexnode(sx, 0, 1)][c], x11 = x[fb2_hexnode(sx, 1, 1)][c];
+                P[sx][c] = fma(w[1][1], x11, fma(w[0][1], x01, fma(w[1][0], x10, w[0][0] * x00)));
+                Dy[sx][c] = fma(hnz[1], x11 - x01, hnz[0] * (x10 - x00));
+                Dz[sx][c] = fma(hny[1], x11 - x10, hny[0] * (x01 - x00));
+            }
+        double J[3][3];       // J[a][b] = d x_a / d xi_b
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    xz[sx][sy][c] = fma(x[fb2_hexnode(sx, sy, 1)][c], fb2_q1n(1, qz), x[fb2_hexnode(sx, sy, 0)][c] * fb2_q1n(0, qz));
+        for (int c = 0; c < 3; ++c) J[c][0] = 0.5 * (P[1][c] - P[0][c]);
 #pragma unroll
-        for (int qy = 0; qy < 2; ++qy) {
-            double J[3][3];       // J[a][b] = d x_a / d xi_b
-            double dy[2][3], dzy[2][3];
+        for (int qx = 0; qx < 2; ++qx) {
+            const int q = qx + 2 * it;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double p0 = fma(xz[0][1][c], fb2_q1n(1, qy), xz[0][0][c] * fb2_q1n(0, qy));
-                const double p1 = fma(xz[1][1][c], fb2_q1n(1, qy), xz[1][0][c] * fb2_q1n(0, qy));
-                J[c][0] = 0.5 * (p1 - p0);
-#pragma unroll
-                for (int sx = 0; sx < 2; ++sx) {
-                    dy[sx][c] = xz[sx][1][c] - xz[sx][0][c];
-                    dzy[sx][c] = fma(dz[sx][1][c], fb2_q1n(1, qy), dz[sx][0][c] * fb2_q1n(0, qy));
-                }
+                J[c][1] = fma(Dy[1][c], fb2_q1n(1, qx), Dy[0][c] * fb2_q1n(0, qx));
+                J[c][2] = fma(Dz[1][c], fb2_q1n(1, qx), Dz[0][c] * fb2_q1n(0, qx));
             }
+            // adjugate (= det * inverse) and determinant
+            double Aj[3][3];
+            Aj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+            Aj[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+            Aj[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+            const double det = J[0][0] * Aj[0][0] + J[0][1] * Aj[1][0] + J[0][2] * Aj[2][0];
+            Aj[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+            Aj[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+            Aj[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+            Aj[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+            Aj[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+            Aj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+            bad |= !(det > 0.0);
+            const double wq = tw[q];
+            const double dO = det * wq;
+            const double sc = wq / det;     // dOmega / det^2: the gradients below are det * grad N
+            // det * grad N_i = dN_i/dxi . adj(J) with dN_i/dxi = (sgn_x ny nz / 2, nx sgn_y nz / 2, nx ny sgn_z / 2):
+            //   g_i = sgn_x U[sy][sz] + nx(sx) V[sy][sz],  U = (ny nz / 2) Aj[0][:],  V = sgn_y (nz / 2) Aj[1][:] + sgn_z (ny / 2) Aj[2][:]
+            double A1[2][3], A2[2][3];
 #pragma unroll
-            for (int qx = 0; qx < 2; ++qx) {
-                const int q = qx + 2 * qy + 4 * qz;
+            for (int s = 0; s < 2; ++s)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    J[c][1] = fma(dy[1][c], 0.5 * fb2_q1n(1, qx), dy[0][c] * (0.5 * fb2_q1n(0, qx)));
-                    J[c][2] = fma(dzy[1][c], fb2_q1n(1, qx), dzy[0][c] * fb2_q1n(0, qx));
-                }
-                // adjugate (= det * inverse) and determinant
-                double Aj[3][3];
-                Aj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
-                Aj[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
-                Aj[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
-                const double det = J[0][0] * Aj[0][0] + J[0][1] * Aj[1][0] + J[0][2] * Aj[2][0];
-                Aj[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
-                Aj[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
-                Aj[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
-                Aj[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]);
-                Aj[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
-                Aj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-                bad |= !(det > 0.0);
-                const double w = tw[q];
-                const double dO = det * w;
-                const double sc = w / det;     // dOmega / det^2: the gradients below are det * grad N
-                double g[8][3], gs[8][3];
+                for (int b = 0; b < 3; ++b) { A1[s][b] = hnz[s] * Aj[1][b]; A2[s][b] = hny[s] * Aj[2][b]; }
+            double g[8][3], gs[8][3];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int sx = fb2_hx(i), sy = fb2_hy(i), sz = fb2_hz(i);
-                    const double d0 = (sx ? 0.5 : -0.5) * fb2_q1n(sy, qy) * fb2_q1n(sz, qz);
-                    const double d1 = fb2_q1n(sx, qx) * (sy ? 0.5 : -0.5) * fb2_q1n(sz, qz);
-                    const double d2 = fb2_q1n(sx, qx) * fb2_q1n(sy, qy) * (sz ? 0.5 : -0.5);
+            for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                for (int sz = 0; sz < 2; ++sz) {
+                    const int i0 = fb2_hexnode(0, sy, sz), i1 = fb2_hexnode(1, sy, sz);
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
-                        g[i][b] = fma(d2, Aj[2][b], fma(d1, Aj[1][b], d0 * Aj[0][b]));
-                        gs[i][b] = g[i][b] * sc;
+                        const double U = hw[sy][sz] * Aj[0][b];
+                        const double V = (sy ? A1[sz][b] : -A1[sz][b]) + (sz ? A2[sy][b] : -A2[sy][b]);
+                        g[i0][b] = fma(fb2_q1n(0, qx), V, -U);
+                        g[i1][b] = fma(fb2_q1n(1, qx), V, U);
+                        gs[i0][b] = g[i0][b] * sc;
+                        gs[i1][b] = g[i1][b] * sc;
                     }
-                    fe[i] = fma(fb2_q1n(sx, qx) * fb2_q1n(sy, qy) * fb2_q1n(sz, qz), dO, fe[i]);
+                    const double wd = w[sy][sz] * dO;
+                    fe[i0] = fma(fb2_q1n(0, qx), wd, fe[i0]);
+                    fe[i1] = fma(fb2_q1n(1, qx), wd, fe[i1]);
                 }
 #pragma unroll
-                for (int j = 1; j < 8; ++j)
+            for (int j = 1; j < 8; ++j)
 #pragma unroll
-                    for (int i = 0; i < j; ++i) {
-                        double s = Ke[j * (j + 1) / 2 + i];
+                for (int i = 0; i < j; ++i) {
+                    double s = Ke[j * (j + 1) / 2 + i];
 #pragma unroll
-                        for (int b = 0; b < 3; ++b) s = fma(g[i][b], gs[j][b], s);
-                        Ke[j * (j + 1) / 2 + i] = s;
-                    }
-            }
+                    for (int b = 0; b < 3; ++b) s = fma(g[i][b], gs[j][b], s);
+                    Ke[j * (j + 1) / 2 + i] = s;
+                }
         }
     }
     // diagonal from the zero row sums
@@ -292,14 +355,18 @@ template <int ELEM, bool CHECK, bool ANALYTIC>
 __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const MarchArgs M) {
     constexpr int PS = MARCH_PS;
     constexpr MarchBatches MB = fb2_march_batches();
+    static_assert(fb2_march_batches().nbatch == 8, "one load-vector entry rides along with every batch");
     extern __shared__ __align__(16) unsigned char smraw[];
     const int cap = M.cap;
     double* s_acc = reinterpret_cast<double*>(smraw);                   // [2][cap] matrix window | [2][PS] load vector | [32] dummies
     const int o_f = 2 * cap, o_dummy = o_f + 2 * PS;
-    int64_t* s_gb = reinterpret_cast<int64_t*>(s_acc + o_dummy + 32);   // [2][PS] colptr[dof] of the tile nodes
-    int* s_cs = reinterpret_cast<int*>(s_gb + 2 * PS);                  // [2][PS] start of the node's column copy
-    int* s_dof = s_cs + 2 * PS;                                         // [2][PS] dof of the tile node, -1 = no such node
-    uint4* s_map = reinterpret_cast<uint4*>(s_dof + 2 * PS);            // [8][32] packed offset map of the lane's cell
+    double* s_xw = s_acc + o_dummy + 32;                                // [2][PS][4] node coordinates of two node planes
+    int64_t* s_gb = reinterpret_cast<int64_t*>(s_xw + 2 * PS * 4);      // [2][PS] colptr[dof] of the tile nodes
+    int* s_dof = reinterpret_cast<int*>(s_gb + 2 * PS);                 // [2][PS] dof of the tile node, -1 = no such node
+    int* s_rowok = s_dof + 2 * PS;                                      // [2] (+6 pad) contiguity bits of the tile rows
+    uint16_t* s_cs = reinterpret_cast<uint16_t*>(s_rowok + 8);          // [2][PS] start of the node's column copy
+    uint8_t* s_len = reinterpret_cast<uint8_t*>(s_cs + 2 * PS);         // [2][PS] its length
+    uint4* s_map = reinterpret_cast<uint4*>(s_len + 2 * PS);            // [4][32] byte-packed offset map of the lane's cell
 
     const int lane = threadIdx.x;
     const int lx = lane & 7, ly = lane >> 3;
@@ -318,50 +385,97 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     const bool with_f = A.f != nullptr && ELEM == FB2_ELEM_HEAT;
     const double kscale = A.p[0], fscale = A.p[1];
 
+    // grid nodes of tile nodes `lane` and `lane + 32` (generate_grid numbers the nodes x fastest, then y, then z:
+    // src/Grid/grid_generators.jl:550-559); -1 = outside the grid
+    const int64_t nlay = (int64_t)(M.nx + 1) * (M.ny + 1);
+    int64_t nodeA, nodeB;
+    {
+        const int aA = lane % 9, bA_ = lane / 9, nB = lane + 32, aB = nB % 9, bB_ = nB / 9;
+        const int gxA = tx * 8 + aA, gyA = ty * 4 + bA_, gxB = tx * 8 + aB, gyB = ty * 4 + bB_;
+        nodeA = (gxA <= M.nx && gyA <= M.ny) ? gxA + (int64_t)(M.nx + 1) * gyA : -1;
+        nodeB = (nB < MARCH_PN && gxB <= M.nx && gyB <= M.ny) ? gxB + (int64_t)(M.nx + 1) * gyB : -1;
+    }
+    auto fetch_plane_xyz = [&](int zp, int slot) {   // node plane zp -> window slot (cp.async, 32 bytes per node)
+        double* dst = s_xw + (size_t)slot * PS * 4;
+        if (nodeA >= 0) {
+            const double* src = A.xyz + 4 * (nodeA + nlay * zp);
+            fb2_cp_async16(dst + 4 * lane, src);
+            fb2_cp_async16(dst + 4 * lane + 2, src + 2);
+        }
+        if (nodeB >= 0) {
+            const double* src = A.xyz + 4 * (nodeB + nlay * zp);
+            fb2_cp_async16(dst + 4 * (lane + 32), src);
+            fb2_cp_async16(dst + 4 * (lane + 32) + 2, src + 2);
+        }
+    };
+
     for (int i = lane; i < o_dummy + 32; i += 32) s_acc[i] = 0.0;
+    // cp.async groups, in issue order: [coordinates of the first two node planes], then per layer [offset map of the
+    // layer's cell], [coordinates of node plane z + 2]; "wait_group 1" = everything but the newest group has landed
+    fetch_plane_xyz(zb, 0);
+    fetch_plane_xyz(zb + 1, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    int dnext[4];   // dofs of the top nodes of the next layer's cell (prefetched one layer ahead)
     {   // bottom plane of the first layer
         const int64_t cell = cxy + lay * zb;
         int d[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) d[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell);
         int64_t bA, bB;
         int lenA, lenB;
         fb2_march_plane_issue(s_dof, A.colptr, lane, tn0, inside, d[0], d[1], d[2], d[3], bA, bB, lenA, lenB);
-        fb2_march_plane_finish(s_cs, s_gb, lane, bA, bB, lenA, lenB);
+        fb2_march_plane_finish(s_cs, s_len, s_gb, s_rowok, lane, bA, bB, lenA, lenB);
     }
 
     for (int z = zb; z < ze; ++z) {
         const int pb = (z - zb) & 1, pt = pb ^ 1;   // window planes holding the node planes z and z + 1
         const int64_t cell = cxy + lay * z;
-        double x[8][3];
-        {
-            int node[8];
+        // offset map of this layer's cell and set-up of the top plane: requested now, needed after the integration
 #pragma unroll
-            for (int j = 0; j < 8; ++j) node[j] = __ldg(A.conn + (size_t)j * np + cell);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) fb2_load_x<3>(A.xyz, node[j], x[j]);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) fb2_cp_async16(&s_map[k * 32 + lane], A.map8 + (size_t)k * np + cell);
+        for (int k = 0; k < 4; ++k) fb2_cp_async16(&s_map[k * 32 + lane], M.mapb + ((size_t)k * np + cell) * 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         int64_t bA, bB;
         int lenA, lenB;
-        {
-            int d[4];
+        fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, inside, dnext[0], dnext[1], dnext[2], dnext[3], bA, bB, lenA, lenB);
+        if (z + 1 < ze) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell);
-            fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, inside, d[0], d[1], d[2], d[3], bA, bB, lenA, lenB);
+            for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell + lay);
         }
+        // node coordinates: both planes were requested at least one layer ago
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the offset map just requested
+        __syncwarp();
+        double x[8][3];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double* xs = s_xw + ((size_t)(fb2_hz(j) ? pt : pb) * PS + tn0 + fb2_hy(j) * 9 + fb2_hx(j)) * 4;
+            const double2 v = *reinterpret_cast<const double2*>(xs);
+            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = xs[2];
+        }
+        __syncwarp();
+        if (z + 1 < ze) fetch_plane_xyz(z + 2, pb);   // the slot of node plane z is free now
+        asm volatile("cp.async.commit_group;" ::: "memory");
         double Ke[36], fe[8];
         bool bad;
         if constexpr (ANALYTIC && ELEM == FB2_ELEM_HEAT) bad = fb2_hex8_heat(x, c_tab + A.o_w, Ke, fe);
         else bad = fb2_scalar_element<3, 8, 8, 8, ELEM, true, false>(A, x, Ke, fe);
         if (bad && inside) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
         const bool act = inside && !bad;
-        fb2_march_plane_finish(s_cs + pt * PS, s_gb + pt * PS, lane, bA, bB, lenA, lenB);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        uint4 mp[8];   // mp[j] = offsets of rows 0..7 inside column j
+        fb2_march_plane_finish(s_cs + pt * PS, s_len + pt * PS, s_gb + pt * PS, s_rowok + pt, lane, bA, bB, lenA, lenB);
+        // the window plane that now becomes the top plane was flushed one layer ago: wait until the bulk engine has read
+        // it, then clear it
+        fb2_bulk_wait_read();
+        __syncwarp();
+        {
+            double2* zp = reinterpret_cast<double2*>(s_acc + (size_t)pt * cap);
+            for (int i = lane; i < cap / 2; i += 32) zp[i] = make_double2(0.0, 0.0);
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // the offset map (the newest group may be the coordinate prefetch)
+        __syncwarp();
+        uint4 mp[4];   // mp[k] = offsets of entries 16 k .. 16 k + 15 (columns 2 k and 2 k + 1), one byte each
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mp[k] = act ? s_map[k * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 0; k < 4; ++k) mp[k] = act ? s_map[k * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
         int cb[8];     // start of the copy of column j inside s_acc; inactive lanes add into their private dummy
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -379,10 +493,10 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 #pragma unroll
             for (int e = 0; e < 64; ++e) {
                 if (MB.b[e] != b) continue;
-                const int i = e & 7, j = e >> 3;
-                const unsigned w32 = (i >> 1) == 0 ? mp[j].x : ((i >> 1) == 1 ? mp[j].y : ((i >> 1) == 2 ? mp[j].z : mp[j].w));
-                const unsigned off = (i & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
-                const int sl = (CHECK && off == 0xFFFFu) ? o_dummy + lane : cb[j] + (int)off;
+                const int j = e >> 3;
+                const unsigned w32 = ((e >> 2) & 3) == 0 ? mp[e >> 4].x : (((e >> 2) & 3) == 1 ? mp[e >> 4].y : (((e >> 2) & 3) == 2 ? mp[e >> 4].z : mp[e >> 4].w));
+                const unsigned off = (w32 >> (8 * (e & 3))) & 0xFFu;
+                const int sl = (CHECK && off == 0xFFu) ? o_dummy + lane : cb[j] + (int)off;
                 t[e] = s_acc[sl];
             }
             if (with_f) {   // load-vector entry of local node b rides along (entries of one local node never alias)
@@ -394,12 +508,11 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
             for (int e = 0; e < 64; ++e) {
                 if (MB.b[e] != b) continue;
                 const int i = e & 7, j = e >> 3;
-                const unsigned w32 = (i >> 1) == 0 ? mp[j].x : ((i >> 1) == 1 ? mp[j].y : ((i >> 1) == 2 ? mp[j].z : mp[j].w));
-                const unsigned off = (i & 1) ? (w32 >> 16) : (w32 & 0xFFFFu);
+                const unsigned w32 = ((e >> 2) & 3) == 0 ? mp[e >> 4].x : (((e >> 2) & 3) == 1 ? mp[e >> 4].y : (((e >> 2) & 3) == 2 ? mp[e >> 4].z : mp[e >> 4].w));
+                const unsigned off = (w32 >> (8 * (e & 3))) & 0xFFu;
                 const double v = i <= j ? Ke[j * (j + 1) / 2 + i] : Ke[i * (i + 1) / 2 + j];
-                if (CHECK && off == 0xFFFFu) {   // a non-zero aimed at a missing pattern entry is an error (src/assembler.jl:459-467)
+                if (CHECK && off == 0xFFu) {   // a non-zero aimed at a missing pattern entry is an error (src/assembler.jl:459-467)
                     if (v != 0.0 && act) missing = true;
-                    s_acc[o_dummy + lane] = 0.0;
                 } else {
                     s_acc[cb[j] + (int)off] = t[e] + v;
                 }
@@ -408,9 +521,11 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
             __syncwarp();
         }
         if (CHECK && missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
-        fb2_march_flush(A, s_acc + pb * cap, s_acc + o_f + pb * PS, s_cs + pb * PS, s_gb + pb * PS, s_dof + pb * PS, lane,
-                        z == zb || !M.overwrite, with_f);
+        fb2_march_flush(A, s_acc + (size_t)pb * cap, s_acc + o_f + pb * PS, s_cs + pb * PS, s_len + pb * PS, s_gb + pb * PS, s_dof + pb * PS,
+                        s_rowok[pb], lane, z == zb || !M.overwrite, with_f);
     }
     const int pl = (ze - zb) & 1;   // the top plane of the chunk is shared with the chunk above
-    fb2_march_flush(A, s_acc + pl * cap, s_acc + o_f + pl * PS, s_cs + pl * PS, s_gb + pl * PS, s_dof + pl * PS, lane, true, with_f);
+    fb2_march_flush(A, s_acc + (size_t)pl * cap, s_acc + o_f + pl * PS, s_cs + pl * PS, s_len + pl * PS, s_gb + pl * PS, s_dof + pl * PS,
+                    s_rowok[pl], lane, true, with_f);
+    fb2_bulk_wait_read();   // shared memory must outlive the bulk reads
 }

@@ -160,6 +160,21 @@ __global__ void k_pack_map(const uint16_t* __restrict__ map, int64_t ncells_pad,
     map8[t] = e < nn ? map[(size_t)e * ncells_pad + c] : (uint16_t)0xFFFF;
 }
 
+// Byte-packed variant for the marching-tile kernel (columns of at most 254 entries): 16 offsets per 16-byte chunk, chunk k
+// of cell c at mapb[(k * ncells_pad + c) * 16 ..], 0xFF = no such pattern entry.
+__global__ void k_pack_map_bytes(const uint16_t* __restrict__ map, int64_t ncells_pad, int nn, int nchunks, uint8_t* __restrict__ mapb) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nchunks * 16 * ncells_pad;
+    if (t >= total) return;
+    int s = (int)(t & 15);
+    int64_t r = t >> 4;
+    int64_t c = r % ncells_pad;
+    int k = (int)(r / ncells_pad);
+    int e = k * 16 + s;
+    const unsigned v = e < nn ? map[(size_t)e * ncells_pad + c] : 0xFFFFu;
+    mapb[t] = v >= 0xFFu ? (uint8_t)0xFF : (uint8_t)v;
+}
+
 // Cell-major variant for k_cell_blocks: the n*n offsets of one cell are contiguous (padded to a multiple of 8
 // entries), so a CTA stages a cell's block with 16-byte cp.async copies.
 __global__ void k_cellmajor_map(const uint16_t* __restrict__ map, int64_t ncells, int64_t ncells_pad, int nn, int stride,
@@ -435,6 +450,22 @@ int fb2_map_build_packed(fb2_assembler* a) {
     const int64_t total = (int64_t)nchunks * 8 * g->ncells_pad;
     FB2_CUDA(cudaMalloc(&a->d_map8, total * sizeof(uint16_t)));
     k_pack_map<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells_pad, nn, nchunks, a->d_map8);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FB2_OK;
+}
+
+int fb2_map_build_bytes(fb2_assembler* a) {
+    if (a->d_mapb) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CHECK(a->pat->max_col_len < 255, FB2_ERR_UNSUPPORTED, "byte-packed offset map needs columns shorter than 255 entries");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int nn = a->n * a->n, nchunks = (nn + 15) / 16;
+    const int64_t total = (int64_t)nchunks * 16 * g->ncells_pad;
+    FB2_CUDA(cudaMalloc(&a->d_mapb, total));
+    k_pack_map_bytes<<<nblocks(total, 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells_pad, nn, nchunks, a->d_mapb);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     FB2_CUDA(cudaStreamSynchronize(ctx->stream));

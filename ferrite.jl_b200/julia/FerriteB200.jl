@@ -128,10 +128,13 @@ struct fb2_asm_opts
     reserved::Cint
 end
 
-struct B200Assembler <: Ferrite.AbstractAssembler
+# `fillzero` is a pending flag: start_assemble zeroes K and f ONCE (src/assembler.jl:287-291); the fill is fused into the
+# first assemble! on this assembler and cleared, later assemble! calls add onto the result like the reference's.
+mutable struct B200Assembler <: Ferrite.AbstractAssembler
     K::B200Matrix
     fillzero::Bool
 end
+take_fillzero!(a::B200Assembler) = (z = a.fillzero; a.fillzero = false; z)
 
 # start_assemble(K, f; fillzero) -- src/assembler.jl:287-291
 Ferrite.start_assemble(K::B200Matrix; fillzero::Bool = true) = B200Assembler(K, fillzero)
@@ -144,7 +147,7 @@ The whole `for cell in CellIterator(dh) ... assemble!(assembler, celldofs(cell),
 """
 function Ferrite.assemble!(a::B200Assembler, element; u::Union{Nothing, Vector{Float64}} = nothing)
     K = a.K
-    opts = Ref(fb2_asm_opts(a.fillzero, 0, 0, 0))
+    opts = Ref(fb2_asm_opts(take_fillzero!(a), 0, 0, 0))
     params = Ref(element)
     GC.@preserve params opts begin
         @fb2 fb2_assemble_host (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{fb2_asm_opts}) K.assembler elem_id(element) params sizeof(element) (u === nothing ? C_NULL : pointer(u)) K.host.nzval K.f opts
@@ -292,7 +295,7 @@ function Ferrite.apply_assemble!(a::B200Assembler, ea::ElementAssembly, ch::Cons
         u_dev::Ptr{Float64} = Ptr{Float64}(C_NULL), apply_zero::Bool = false)
     c = Ref{Ptr{Cvoid}}(C_NULL)
     @fb2 fb2_ch_from_host (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}) ea.prob.dh length(ch.prescribed_dofs) ch.prescribed_dofs ch.inhomogeneities c
-    opts = Ref(fb2_asm_opts(a.fillzero, 0, 0, 0))
+    opts = Ref(fb2_asm_opts(take_fillzero!(a), 0, 0, 0))
     params = Ref(element)
     GC.@preserve params opts begin
         @fb2 fb2_apply_assemble (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Csize_t, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{fb2_asm_opts}) a.K.assembler ea.h c[] elem_id(element) params sizeof(element) u_dev nzval_dev f_dev apply_zero opts

@@ -27,7 +27,7 @@ ids = [fb.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 fb.comm_init(ctx, ids[0], world, rank)
 part._asm = a
-modes = {"local_all_cells": lambda: fb.assemble_(a, elem, cv), "own": lambda: part.assemble_(elem, mode="own"),
+modes = {"local_all_cells": lambda: fb.assemble_(fb.start_assemble(K, f), elem, cv), "own": lambda: part.assemble_(elem, mode="own"),
          "halo": lambda: part.assemble_(elem, mode="halo"), "exchange": lambda: part.assemble_(elem, mode="exchange")}
 out = {}
 for name, fn in modes.items():

@@ -18,13 +18,13 @@ def t(fn, n=4):
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 out = {}
 def plain():
-    g.upload_coordinates_async(xyz); fb.assemble_host(a, elem, cv, nz.numpy(), f.numpy())
+    g.upload_coordinates_async(xyz); fb.assemble_host(fb.start_assemble(K, None), elem, cv, nz.numpy(), f.numpy())
 out["plain_upload+assemble_host"] = t(plain)
-out["assemble_host_only"] = t(lambda: fb.assemble_host(a, elem, cv, nz.numpy(), f.numpy()))
+out["assemble_host_only"] = t(lambda: fb.assemble_host(fb.start_assemble(K, None), elem, cv, nz.numpy(), f.numpy()))
 for ns in (1, 2, 4, 8, 16):
     os.environ["FB2_HOST_SLABS"] = str(ns)
-    out[f"streamed_noxyz_{ns}"] = t(lambda: fb.assemble_host_streamed(a, elem, cv, nz.numpy(), f.numpy()))
-    out[f"streamed_xyz_{ns}"] = t(lambda: fb.assemble_host_streamed(a, elem, cv, nz.numpy(), f.numpy(), xyz=xyz.numpy()))
+    out[f"streamed_noxyz_{ns}"] = t(lambda: fb.assemble_host_streamed(fb.start_assemble(K, None), elem, cv, nz.numpy(), f.numpy()))
+    out[f"streamed_xyz_{ns}"] = t(lambda: fb.assemble_host_streamed(fb.start_assemble(K, None), elem, cv, nz.numpy(), f.numpy(), xyz=xyz.numpy()))
 # raw copies
 d = torch.empty(K.nnz, dtype=torch.float64, device="cuda")
 out["raw_d2h_nzval"] = t(lambda: nz.copy_(d, non_blocking=True))

@@ -187,7 +187,7 @@ def test_apply_assemble_split_cache_follows_update_and_coordinates(ctx):
     och.update(2.0)
     og.nodes[:] = og.nodes * np.array([1.0, 1.1, 0.9]) + 0.05
     g.set_coordinates(og.nodes)
-    fb.apply_assemble_(a, ch, elem, cv, ea=ea)
+    fb.apply_assemble_(fb.start_assemble(K, f), ch, elem, cv, ea=ea)
     oK, of = _oracle_apply_assemble(og, odh, ocv, och, "heat", op)
     assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
     # another ConstraintHandler through the same ElementAssembly
@@ -196,7 +196,7 @@ def test_apply_assemble_split_cache_follows_update_and_coordinates(ctx):
     och2.add(O.Dirichlet("u", og.facetsets["top"], lambda x, t: 2.0 + x[0]))
     fb.close_(ch2)
     och2.close()
-    fb.apply_assemble_(a, ch2, elem, cv, ea=ea, applyzero=True)
+    fb.apply_assemble_(fb.start_assemble(K, f), ch2, elem, cv, ea=ea, applyzero=True)
     oK, of = _oracle_apply_assemble(og, odh, ocv, och2, "heat", op, applyzero=True)
     assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
     # fillzero = false accumulates

@@ -256,6 +256,7 @@ def test_colored_is_bitwise_reproducible_and_coloring_valid(ctx):
         assert len(np.unique(nodes)) == len(nodes)
     runs = []
     for _ in range(3):
+        a = fb.start_assemble(K, f, scatter="colored")
         fb.assemble_(a, fb.HeatElement(), cv)
         fb.finish_assemble(a)
         runs.append((K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()))
@@ -276,6 +277,23 @@ def test_fillzero_false_accumulates(ctx, nel):
     fb.assemble_(a2, fb.HeatElement(), cv)
     fb.finish_assemble(a2)
     assert np.allclose(K.nzval.cpu().numpy(), 2 * once.cpu().numpy(), rtol=1e-14)
+
+
+def test_two_passes_on_one_assembler_accumulate(ctx):
+    """start_assemble zeroes K and f once; assemble! calls on the returned assembler add up (src/assembler.jl:287-291,
+    322-331): a = start_assemble(K, f); heat pass; mass pass  ==  K_heat + K_mass."""
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (9, 6, 5), 1, 1, 2)
+    K, f = fb.allocate_matrix(dh), ctx.zeros(dh.ndofs)
+    oK1, oK2, of1 = O.allocate_matrix(odh), O.allocate_matrix(odh), np.zeros(odh.ndofs)
+    O.assemble_global(odh, ocv, oK1, of1, "heat", dict(k=2.0, source=3.0))
+    O.assemble_global(odh, ocv, oK2, None, "mass", dict(rho=0.5))
+    K.nzval.fill_(9.0)
+    f.fill_(9.0)
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, fb.HeatElement(k=2.0, source=3.0), cv)
+    fb.assemble_(a, fb.MassElement(rho=0.5), cv)
+    fb.finish_assemble(a)
+    assert close(K.nzval.cpu().numpy(), oK1.nzval + oK2.nzval)[0] and close(f.cpu().numpy(), of1)[0]
 
 
 def test_host_buffer_entry_point(ctx):
@@ -429,9 +447,11 @@ def test_missing_entry_and_zero_skip(ctx):
     Ke[:, 0, 0] = Ke[:, 1, 1] = 1.0
     fb.scatter_(a, Ke)
     assert np.allclose(K.nzval.cpu().numpy(), [1, 2, 2, 1])
+    fb.scatter_(a, Ke)                      # a second assemble! on the same assembler adds (start_assemble zeroes once)
+    assert np.allclose(K.nzval.cpu().numpy(), [2, 4, 4, 2])
     Ke[1, 0, 1] = 5.0
     with pytest.raises(fb.MissingPatternEntry):
-        fb.scatter_(a, Ke)
+        fb.scatter_(fb.start_assemble(K, None), Ke)
 
 
 @pytest.mark.parametrize("nel", [(3, 3, 3), (12, 10, 9)])   # per-cell kernel / tile kernel
@@ -771,16 +791,15 @@ def test_streamed_host_path_matches_plain_host_path(ctx, ct, nel, order, vdim, k
     u = 0.01 * np.sin(np.arange(dh.ndofs, dtype=np.float64)) if kind == "neohooke" else None
     nz1, f1 = np.empty(K.nnz), np.empty(dh.ndofs)
     nz2, f2 = np.full(K.nnz, np.nan), np.full(dh.ndofs, np.nan)
-    a = fb.start_assemble(K, None)
-    fb.assemble_host(a, elem, cv, nz1, f1, u=u)
-    fb.assemble_host_streamed(a, elem, cv, nz2, f2, u=u)
+    fb.assemble_host(fb.start_assemble(K, None), elem, cv, nz1, f1, u=u)
+    fb.assemble_host_streamed(fb.start_assemble(K, None), elem, cv, nz2, f2, u=u)
     assert np.array_equal(np.isnan(nz2), np.zeros(K.nnz, bool))
     assert close(nz2, nz1, 1e-13)[0] and close(f2, f1, 1e-13)[0]
     # new coordinates travel with the call
     xyz = np.ascontiguousarray(g.nodes * 1.25)
-    fb.assemble_host_streamed(a, elem, cv, nz2, f2, u=u, xyz=xyz)
+    fb.assemble_host_streamed(fb.start_assemble(K, None), elem, cv, nz2, f2, u=u, xyz=xyz)
     g.upload_coordinates_async(xyz)
-    fb.assemble_host(a, elem, cv, nz1, f1, u=u)
+    fb.assemble_host(fb.start_assemble(K, None), elem, cv, nz1, f1, u=u)
     assert close(nz2, nz1, 1e-13)[0] and close(f2, f1, 1e-13)[0]
 
 
@@ -1021,6 +1040,63 @@ def test_renumbered_problem_matches_oracle(ctx, ct, nel, order, vdim, qo, kind, 
         assert ok, (scatter, nrm)
     fb.apply_(K, f, ch)
     och.apply(oK, of)
+    ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+    assert ok, nrm
+    ok, nrm = close(f.cpu().numpy(), of)
+    assert ok, nrm
+
+
+def test_config_c1_quad_100x100_entrywise_with_apply(ctx):
+    """BASELINE.json configs[0] at its full size: heat equation, Q1 on generate_grid(Quadrilateral, (100, 100)) with the
+    tutorial's homogeneous Dirichlet condition on all four facet sets (heat_equation.jl:59-114): numbering and pattern
+    bit-exact, K / f entry-wise before and after apply!, and the solution of the constrained system."""
+    nel = (100, 100)
+    g, og, dh, odh, cv, ocv = build(fb.Quadrilateral, nel, 1, 1, 2, perturb=False)
+    assert g.ncells == 10000 and dh.ndofs == 10201
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    K, oK = fb.allocate_matrix(dh), O.allocate_matrix(odh)
+    assert K.nnz == 90601
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f, of = ctx.zeros(dh.ndofs), np.zeros(odh.ndofs)
+    fb.assemble_(fb.start_assemble(K, f), fb.HeatElement(), cv)
+    O.assemble_global(odh, ocv, oK, of, "heat")
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
+    ch, och = fb.ConstraintHandler(dh), O.ConstraintHandler(odh)
+    union = np.concatenate([fb.getfacetset(g, s) for s in ("left", "right", "top", "bottom")])
+    ounion = np.concatenate([og.facetsets[s] for s in ("left", "right", "top", "bottom")])
+    fb.add_(ch, fb.Dirichlet("u", union, lambda x, t: 0.0))
+    och.add(O.Dirichlet("u", ounion, lambda x, t: 0.0))
+    fb.close_(ch)
+    och.close()
+    fb.update_(ch, 0.0)
+    och.update(0.0)
+    assert np.array_equal(ch.prescribed_dofs, och.prescribed_dofs) and len(ch.prescribed_dofs) == 400
+    fb.apply_(K, f, ch)
+    och.apply(oK, of)
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
+    u = spla.spsolve(K.tocsc(), f.cpu().numpy())
+    ou = spla.spsolve(oK.toscipy().tocsc(), of)
+    assert np.linalg.norm(u - ou) <= 1e-10 * np.linalg.norm(ou)
+
+
+@pytest.mark.parametrize("kind,nel,vdim", [("heat", (64, 64, 64), 1), ("elasticity", (32, 32, 32), 3), ("heat", (96, 40, 72), 1)])
+def test_large_entrywise_against_the_c_port(ctx, kind, nel, vdim):
+    """Entry-wise nzval / f at sizes the numpy oracle does not reach: the C restatement of the reference loop
+    (oracle/cpu_assemble.c, itself checked against the numpy oracle in tests/test_oracle_goldens.py) is the checker.
+    64^3 Q1 heat (262 144 cells: many tiles, chunks and waves of the marching kernel) and 32^3 Q1^3 elasticity."""
+    from oracle import cport
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, vdim, 2, True)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    K, oK = fb.allocate_matrix(dh), O.allocate_matrix(odh)
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
+    f, of = ctx.zeros(dh.ndofs), np.zeros(odh.ndofs)
+    if kind == "heat":
+        elem, op = fb.HeatElement(k=1.3, source=0.7), dict(k=1.3, source=0.7)
+    else:
+        lam, mu = O.lame(200e9, 0.3)
+        elem, op = fb.ElasticityElement(lam=lam, mu=mu, b=(0.1, 0.2, -1.0)), {"lambda": lam, "mu": mu, "b": (0.1, 0.2, -1.0)}
+    cport.assemble(odh, ocv, oK, of, kind, op, nthreads=1)      # one thread: the reference's serial summation order
+    fb.assemble_(fb.start_assemble(K, f), elem, cv)
     ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
     assert ok, nrm
     ok, nrm = close(f.cpu().numpy(), of)
