@@ -86,7 +86,7 @@ __device__ __forceinline__ void fb2_fence_async_smem() { asm volatile("fence.pro
 // Set-up of a node plane of the tile, first half: every lane publishes the dofs of the four nodes of its cell that lie in
 // the plane and the column extents of tile nodes `lane` and `lane + 32` are requested.
 __device__ __forceinline__ void fb2_march_plane_issue(int* s_dof, const int64_t* __restrict__ colptr, int lane, int tn0, bool inside,
-                                                      int d0, int d1, int d2, int d3, int64_t& bA, int64_t& bB, int& lenA, int& lenB) {
+                                                      int d0, int d1, int d2, int d3, int64_t& bA, int64_t& bB, int64_t& eA, int64_t& eB) {
     s_dof[lane] = -1;
     if (lane < MARCH_PS - 32) s_dof[lane + 32] = -1;
     __syncwarp();
@@ -98,9 +98,9 @@ __device__ __forceinline__ void fb2_march_plane_issue(int* s_dof, const int64_t*
     }
     __syncwarp();
     const int dA = s_dof[lane], dB = lane < MARCH_PS - 32 ? s_dof[lane + 32] : -1;
-    bA = 0; bB = 0; lenA = 0; lenB = 0;
-    if (dA >= 0) { bA = __ldg(colptr + dA); lenA = (int)(__ldg(colptr + dA + 1) - bA); }
-    if (dB >= 0) { bB = __ldg(colptr + dB); lenB = (int)(__ldg(colptr + dB + 1) - bB); }
+    bA = 0; bB = 0; eA = 0; eB = 0;
+    if (dA >= 0) { bA = __ldg(colptr + dA); eA = __ldg(colptr + dA + 1); }
+    if (dB >= 0) { bB = __ldg(colptr + dB); eB = __ldg(colptr + dB + 1); }
 }
 
 // Second half: position of every column copy inside the plane's accumulator = exclusive scan of the column lengths plus
@@ -109,8 +109,12 @@ __device__ __forceinline__ void fb2_march_plane_issue(int* s_dof, const int64_t*
 // that are adjacent in nzval stay adjacent in the accumulator (no pad between them).  *rowok: bit b = the seven interior
 // columns of tile row b are one contiguous piece of nzval.
 __device__ __forceinline__ void fb2_march_plane_finish(uint16_t* s_cs, uint8_t* s_len, int64_t* s_gb, int* s_rowok, int lane, int64_t bA, int64_t bB,
-                                                       int lenA, int lenB) {
+                                                       int64_t eA, int64_t eB) {
     const unsigned full = 0xffffffffu;
+    // the four colptr values were requested before the integration; this empty statement keeps every consumer (starting
+    // with the subtractions below) behind it, so the warp does not stall on them before it has work to hide the latency
+    asm volatile("" : "+l"(bA), "+l"(bB), "+l"(eA), "+l"(eB));
+    const int lenA = (int)(eA - bA), lenB = (int)(eB - bB);
     int sA = lenA, sB = lenB;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -246,38 +250,56 @@ __host__ __device__ constexpr int fb2_hexnode(int sx, int sy, int sz) { return s
 // The loop over (qy, qz) is ROLLED (four iterations of a body that handles the two points qx = 0, 1): the fully unrolled
 // body is 35 KB of SASS, and with eight independent warps per SM at different places of it the instruction fetch stalls
 // cost more (29 % of all stall samples, profiles/r02_prof_c2_march_c.txt) than the shared sub-expressions save.
-__device__ __forceinline__ bool fb2_hex8_heat(const double (&x)[8][3], const double* __restrict__ tw, double (&Ke)[36], double (&fe)[8]) {
+// The node coordinates are read from the shared-memory window inside the loop (xs[j] = the lane's node j, 32 bytes apart
+// in z-pairs) instead of living in 48 registers next to the 72 of Ke / fe.
+__device__ __forceinline__ bool fb2_hex8_heat(const double* const (&xs)[8], const double* __restrict__ tw, double (&Ke)[36], double (&fe)[8]) {
     constexpr double NA = fb2_q1n(0, 0), NB = fb2_q1n(1, 0);   // shape function of the near / far node of a Gauss point
 #pragma unroll
     for (int e = 0; e < 36; ++e) Ke[e] = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) fe[i] = 0.0;
     bool bad = false;
+    // All factors 1/2 of the linear shape-function derivatives are dropped: with Jt = 2 J one has adj(Jt) = 4 adj(J) and
+    // det(Jt) = 8 det(J), so grad N_i = (sgn_x ny nz, nx sgn_y nz, nx ny sgn_z) . adj(Jt) / det(Jt) and dOmega = det(Jt) w / 8.
 #pragma unroll 1
     for (int it = 0; it < 4; ++it) {
         const int qy = it & 1, qz = it >> 1;
         const double ny[2] = {qy ? NB : NA, qy ? NA : NB}, nz[2] = {qz ? NB : NA, qz ? NA : NB};
-        double w[2][2], hw[2][2];       // ny nz and half of it
+        double w[2][2];       // ny nz
 #pragma unroll
         for (int sy = 0; sy < 2; ++sy)
 #pragma unroll
-            for (int sz = 0; sz < 2; ++sz) { w[sy][sz] = ny[sy] * nz[sz]; hw[sy][sz] = 0.5 * w[sy][sz]; }
-        const double hny[2] = {0.5 * ny[0], 0.5 * ny[1]}, hnz[2] = {0.5 * nz[0], 0.5 * nz[1]};
-        // the x-line through the two points: its end points P[sx], and d x / d eta, d x / d zeta at the ends
-        double P[2][3], Dy[2][3], Dz[2][3];
+            for (int sz = 0; sz < 2; ++sz) w[sy][sz] = ny[sy] * nz[sz];
+        // the x-line through the two points: Jt[:][0] = difference of its end points; 2 d x / d eta, 2 d x / d zeta at the ends
+        double J[3][3], Dy[2][3], Dz[2][3];
+        {
+            double x[8][3];
 #pragma unroll
-        for (int sx = 0; sx < 2; ++sx)
+            for (int j = 0; j < 8; ++j) {
+#ifdef FB2_HEX8_XSMEM   // volatile: re-read in every iteration, not hoisted back into 48 registers
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(xs[j]);
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[j][0]), "=d"(x[j][1]) : "r"(sa));
+                asm volatile("ld.shared.f64 %0, [%1+16];" : "=d"(x[j][2]) : "r"(sa));
+#else
+                const double2 v = *reinterpret_cast<const double2*>(xs[j]);
+                x[j][0] = v.x; x[j][1] = v.y; x[j][2] = xs[j][2];
+#endif
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double x00 = x[fb2_hexnode(sx, 0, 0)][c], x10 = x[fb2_hexnode(sx, 1, 0)][c];
-                const double x01 = x[fb2_hexnode(sx, 0, 1)][c], x11 = x[fb2_hexnode(sx, 1, 1)][c];
-                P[sx][c] = fma(w[1][1], x11, fma(w[0][1], x01, fma(w[1][0], x10, w[0][0] * x00)));
-                Dy[sx][c] = fma(hnz[1], x11 - x01, hnz[0] * (x10 - x00));
-                Dz[sx][c] = fma(hny[1], x11 - x10, hny[0] * (x01 - x00));
-            }
-        double J[3][3];       // J[a][b] = d x_a / d xi_b
 #pragma unroll
-        for (int c = 0; c < 3; ++c) J[c][0] = 0.5 * (P[1][c] - P[0][c]);
+                for (int sx = 0; sx < 2; ++sx) {
+                    const double x00 = x[fb2_hexnode(sx, 0, 0)][c], x10 = x[fb2_hexnode(sx, 1, 0)][c];
+                    const double x01 = x[fb2_hexnode(sx, 0, 1)][c], x11 = x[fb2_hexnode(sx, 1, 1)][c];
+                    Dy[sx][c] = fma(nz[1], x11 - x01, nz[0] * (x10 - x00));
+                    Dz[sx][c] = fma(ny[1], x11 - x10, ny[0] * (x01 - x00));
+                }
+                J[c][0] = fma(w[1][1], x[fb2_hexnode(1, 1, 1)][c] - x[fb2_hexnode(0, 1, 1)][c],
+                              fma(w[0][1], x[fb2_hexnode(1, 0, 1)][c] - x[fb2_hexnode(0, 0, 1)][c],
+                                  fma(w[1][0], x[fb2_hexnode(1, 1, 0)][c] - x[fb2_hexnode(0, 1, 0)][c],
+                                      w[0][0] * (x[fb2_hexnode(1, 0, 0)][c] - x[fb2_hexnode(0, 0, 0)][c]))));
+            }
+        }
 #pragma unroll
         for (int qx = 0; qx < 2; ++qx) {
             const int q = qx + 2 * it;
@@ -286,7 +308,7 @@ __device__ __forceinline__ bool fb2_hex8_heat(const double (&x)[8][3], const dou
                 J[c][1] = fma(Dy[1][c], fb2_q1n(1, qx), Dy[0][c] * fb2_q1n(0, qx));
                 J[c][2] = fma(Dz[1][c], fb2_q1n(1, qx), Dz[0][c] * fb2_q1n(0, qx));
             }
-            // adjugate (= det * inverse) and determinant
+            // adjugate (= det * inverse) and determinant of Jt
             double Aj[3][3];
             Aj[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
             Aj[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
@@ -299,16 +321,21 @@ __device__ __forceinline__ bool fb2_hex8_heat(const double (&x)[8][3], const dou
             Aj[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
             Aj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
             bad |= !(det > 0.0);
-            const double wq = tw[q];
-            const double dO = det * wq;
-            const double sc = wq / det;     // dOmega / det^2: the gradients below are det * grad N
-            // det * grad N_i = dN_i/dxi . adj(J) with dN_i/dxi = (sgn_x ny nz / 2, nx sgn_y nz / 2, nx ny sgn_z / 2):
-            //   g_i = sgn_x U[sy][sz] + nx(sx) V[sy][sz],  U = (ny nz / 2) Aj[0][:],  V = sgn_y (nz / 2) Aj[1][:] + sgn_z (ny / 2) Aj[2][:]
+            const double w8 = 0.125 * tw[q];
+            const double dO = det * w8;
+            // dOmega / det(Jt)^2 (the gradients below are det(Jt) * grad N): reciprocal by two Newton steps on the hardware
+            // approximation (2^-20 -> 2^-40 -> below rounding; det is a cell volume, far from the subnormal range)
+            double rc;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(det));
+            rc = fma(fma(-det, rc, 1.0), rc, rc);
+            rc = fma(fma(-det, rc, 1.0), rc, rc);
+            const double sc = w8 * rc;
+            //   g_i = sgn_x U[sy][sz] + nx(sx) V[sy][sz],  U = ny nz Aj[0][:],  V = sgn_y nz Aj[1][:] + sgn_z ny Aj[2][:]
             double A1[2][3], A2[2][3];
 #pragma unroll
             for (int s = 0; s < 2; ++s)
 #pragma unroll
-                for (int b = 0; b < 3; ++b) { A1[s][b] = hnz[s] * Aj[1][b]; A2[s][b] = hny[s] * Aj[2][b]; }
+                for (int b = 0; b < 3; ++b) { A1[s][b] = nz[s] * Aj[1][b]; A2[s][b] = ny[s] * Aj[2][b]; }
             double g[8][3], gs[8][3];
 #pragma unroll
             for (int sy = 0; sy < 2; ++sy)
@@ -317,7 +344,7 @@ __device__ __forceinline__ bool fb2_hex8_heat(const double (&x)[8][3], const dou
                     const int i0 = fb2_hexnode(0, sy, sz), i1 = fb2_hexnode(1, sy, sz);
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
-                        const double U = hw[sy][sz] * Aj[0][b];
+                        const double U = w[sy][sz] * Aj[0][b];
                         const double V = (sy ? A1[sz][b] : -A1[sz][b]) + (sz ? A2[sy][b] : -A2[sy][b]);
                         g[i0][b] = fma(fb2_q1n(0, qx), V, -U);
                         g[i1][b] = fma(fb2_q1n(1, qx), V, U);
@@ -411,7 +438,8 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 
     for (int i = lane; i < o_dummy + 32; i += 32) s_acc[i] = 0.0;
     // cp.async groups, in issue order: [coordinates of the first two node planes], then per layer [offset map of the
-    // layer's cell], [coordinates of node plane z + 2]; "wait_group 1" = everything but the newest group has landed
+    // layer's cell] before and [coordinates of node plane z + 2] after the integration; "wait_group 1" = everything but the
+    // newest group has landed
     fetch_plane_xyz(zb, 0);
     fetch_plane_xyz(zb + 1, 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -423,10 +451,9 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         for (int i = 0; i < 4; ++i) d[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell);
-        int64_t bA, bB;
-        int lenA, lenB;
-        fb2_march_plane_issue(s_dof, A.colptr, lane, tn0, inside, d[0], d[1], d[2], d[3], bA, bB, lenA, lenB);
-        fb2_march_plane_finish(s_cs, s_len, s_gb, s_rowok, lane, bA, bB, lenA, lenB);
+        int64_t bA, bB, eA, eB;
+        fb2_march_plane_issue(s_dof, A.colptr, lane, tn0, inside, d[0], d[1], d[2], d[3], bA, bB, eA, eB);
+        fb2_march_plane_finish(s_cs, s_len, s_gb, s_rowok, lane, bA, bB, eA, eB);
     }
 
     for (int z = zb; z < ze; ++z) {
@@ -436,9 +463,8 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 #pragma unroll
         for (int k = 0; k < 4; ++k) fb2_cp_async16(&s_map[k * 32 + lane], M.mapb + ((size_t)k * np + cell) * 16);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        int64_t bA, bB;
-        int lenA, lenB;
-        fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, inside, dnext[0], dnext[1], dnext[2], dnext[3], bA, bB, lenA, lenB);
+        int64_t bA, bB, eA, eB;
+        fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, inside, dnext[0], dnext[1], dnext[2], dnext[3], bA, bB, eA, eB);
         if (z + 1 < ze) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell + lay);
@@ -446,23 +472,29 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         // node coordinates: both planes were requested at least one layer ago
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the offset map just requested
         __syncwarp();
-        double x[8][3];
+        const double* xs[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double* xs = s_xw + ((size_t)(fb2_hz(j) ? pt : pb) * PS + tn0 + fb2_hy(j) * 9 + fb2_hx(j)) * 4;
-            const double2 v = *reinterpret_cast<const double2*>(xs);
-            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = xs[2];
-        }
-        __syncwarp();
-        if (z + 1 < ze) fetch_plane_xyz(z + 2, pb);   // the slot of node plane z is free now
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (int j = 0; j < 8; ++j) xs[j] = s_xw + ((size_t)(fb2_hz(j) ? pt : pb) * PS + tn0 + fb2_hy(j) * 9 + fb2_hx(j)) * 4;
         double Ke[36], fe[8];
         bool bad;
-        if constexpr (ANALYTIC && ELEM == FB2_ELEM_HEAT) bad = fb2_hex8_heat(x, c_tab + A.o_w, Ke, fe);
-        else bad = fb2_scalar_element<3, 8, 8, 8, ELEM, true, false>(A, x, Ke, fe);
+        if constexpr (ANALYTIC && ELEM == FB2_ELEM_HEAT) {
+            bad = fb2_hex8_heat(xs, c_tab + A.o_w, Ke, fe);
+        } else {
+            double x[8][3];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double2 v = *reinterpret_cast<const double2*>(xs[j]);
+                x[j][0] = v.x; x[j][1] = v.y; x[j][2] = xs[j][2];
+            }
+            bad = fb2_scalar_element<3, 8, 8, 8, ELEM, true, false>(A, x, Ke, fe);
+        }
         if (bad && inside) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
         const bool act = inside && !bad;
-        fb2_march_plane_finish(s_cs + pt * PS, s_len + pt * PS, s_gb + pt * PS, s_rowok + pt, lane, bA, bB, lenA, lenB);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // the offset map
+        __syncwarp();
+        if (z + 1 < ze) fetch_plane_xyz(z + 2, pb);   // the slot of node plane z is free now; lands during the flush
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        fb2_march_plane_finish(s_cs + pt * PS, s_len + pt * PS, s_gb + pt * PS, s_rowok + pt, lane, bA, bB, eA, eB);
         // the window plane that now becomes the top plane was flushed one layer ago: wait until the bulk engine has read
         // it, then clear it
         fb2_bulk_wait_read();
@@ -471,8 +503,6 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
             double2* zp = reinterpret_cast<double2*>(s_acc + (size_t)pt * cap);
             for (int i = lane; i < cap / 2; i += 32) zp[i] = make_double2(0.0, 0.0);
         }
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // the offset map (the newest group may be the coordinate prefetch)
-        __syncwarp();
         uint4 mp[4];   // mp[k] = offsets of entries 16 k .. 16 k + 15 (columns 2 k and 2 k + 1), one byte each
 #pragma unroll
         for (int k = 0; k < 4; ++k) mp[k] = act ? s_map[k * 32 + lane] : make_uint4(0u, 0u, 0u, 0u);
