@@ -8,10 +8,22 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cub/cub.cuh>
+
 #include "assemble_kernels.cuh"
 #include "march_kernels.cuh"
 
 namespace {
+
+// the zero fill of nzval that start_assemble owes, for every kernel that does not fuse it
+int pay_zero_fill(fb2_assembler* a, AsmArgs& A) {
+    if (A.zero_pending) {
+        FB2_CUDA(cudaMemsetAsync(A.nzval, 0, (size_t)a->pat->nnz * sizeof(double), a->dh->grid->ctx->stream));
+        A.zero_pending = 0;
+    }
+    return FB2_OK;
+}
+
 
 // c_tab is one module-global array per DEVICE, whatever the number of contexts on it: the owner is tracked per device
 // (by the CellValues' never-reused uid), not per context.
@@ -252,6 +264,46 @@ bool march_usable(fb2_assembler* a) {
     return a->march_state == 1;
 }
 
+// Columns the marching-tile kernel adds to with reduce-adds (see k_march_mark), as a sorted device list; cached per chunk length.
+int march_zero_list(fb2_assembler* a, int lz) {
+    if (a->d_march_zcols && a->march_zlz == lz) return FB2_OK;
+    const fb2_dh* dh = a->dh;
+    const fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nx = (int)g->nel[0], ny = (int)g->nel[1], nz = (int)g->nel[2];
+    const int64_t nn = (int64_t)(nx + 1) * (ny + 1) * (nz + 1), nd = dh->ndofs;
+    cudaFree(a->d_march_zcols);
+    a->d_march_zcols = nullptr;
+    uint8_t* d_flag = nullptr;
+    int32_t* d_out = nullptr;
+    int64_t* d_num = nullptr;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int64_t num = 0;
+    cudaError_t e = cudaMalloc(&d_flag, (size_t)nd);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)nd * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, (size_t)nd, st);
+    if (e == cudaSuccess) {
+        k_march_mark<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dh->d_cell_dofs, g->ncells_pad, nx, ny, nz, lz, d_flag);
+        cub::CountingInputIterator<int32_t> ids(0);
+        e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, d_flag, d_out, d_num, (int)nd, st);
+        if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes);
+        if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, ids, d_flag, d_out, d_num, (int)nd, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&num, d_num, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_march_zcols, std::max<size_t>((size_t)num, 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(a->d_march_zcols, d_out, (size_t)num * sizeof(int32_t), cudaMemcpyDeviceToDevice);
+    cudaFree(d_flag); cudaFree(d_out); cudaFree(d_num); cudaFree(d_tmp);
+    if (e != cudaSuccess) return fb2_fail(FB2_ERR_CUDA, "march_zero_list: %s", cudaGetErrorString(e));
+    ctx->launches += 2;
+    a->march_zlz = lz;
+    a->march_nzcols = num;
+    return FB2_OK;
+}
+
 // tile kernel (tiles.cu): whole grid, atomic mode only; falls back to the per-cell kernel when no schedule exists
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
 int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate) {
@@ -315,6 +367,22 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 // eight single-warp CTAs per SM need 8 x 28 KB: ask for the full shared-memory carveout
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                // start_assemble's zero fill of nzval, if still owed.  Only the columns that receive reduce-adds need it
+                // (38 % of nzval on C2), but zeroing those 3.1 M separate columns (FB2_MARCH_ZSEL=1, k_zero_columns) takes as
+                // long as one memset over everything (0.23 vs 0.24 ms, profiles/r02_launches_c2.csv), so the memset stays.
+                if (A.zero_pending) {
+                    const char* ez = getenv("FB2_MARCH_ZSEL");
+                    if (ez && atoi(ez) == 1 && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
+                        FB2_TRY(march_zero_list(a, M.lz));
+                        if (a->march_nzcols > 0)
+                            k_zero_columns<<<(unsigned)((a->march_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_march_zcols, a->march_nzcols,
+                                                                                                          a->pat->d_colptr, A.nzval);
+                        ctx->launches++;
+                    } else {
+                        FB2_CUDA(cudaMemsetAsync(A.nzval, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+                    }
+                    A.zero_pending = 0;
+                }
                 k<<<(unsigned)(tiles * nchunks), 32, smem, ctx->stream>>>(A, M);
                 ctx->launches++;
                 FB2_CUDA(cudaGetLastError());
@@ -322,6 +390,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
             }
         }
     }
+    FB2_TRY(pay_zero_fill(a, A));   // the marching-tile kernel was not applicable
     // variant 6: launch over the warp list, which adds the y-merge through shared memory.  Measured on C2 it removes a
     // further ~20 % of the REDs but costs two CTA barriers and 12 % padding lanes (200 = 6*32 + 8): 2.78 ms vs 2.41 ms
     // with the x-merge alone, so it is not the default.
@@ -490,6 +559,10 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
     fb2_ctx* ctx = a->dh->grid->ctx;
     const int ct = cv->celltype, nbs = cv->nb, vdim = cv->vdim;
     int rc = FB2_OK;
+    // only the marching-tile kernel (Q1 hexahedra, heat / mass, default variant) takes the fill over
+    const bool may_fuse = (element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS) && (variant == 0 || variant == 31) && atomic &&
+                          ct == FB2_HEXAHEDRON && nbs == 8 && cv->nq == 8 && vdim == 1;
+    if (!may_fuse) FB2_TRY(pay_zero_fill(a, A));
     switch (element) {
         case FB2_ELEM_HEAT:
             FB2_CHECK(vdim == 1, FB2_ERR_BAD_ARG, "the heat element needs a scalar field");
@@ -615,7 +688,10 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
         }
     }
     if (o.fillzero) {
-        FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+        // the fill of nzval is owed to the kernel launch below (launch_one pays it with a memset unless the kernel fuses it)
+        const bool subset_now = a->d_cells != nullptr || a->ncells_active > 0;
+        if (o.scatter_mode == FB2_SCATTER_COLORED || subset_now) FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+        else A.zero_pending = 1;
         if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)dh->ndofs * sizeof(double), ctx->stream));
     }
     if (o.scatter_mode == FB2_SCATTER_COLORED) {
@@ -633,7 +709,7 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     const bool subset = a->d_cells != nullptr || a->ncells_active > 0;
     A.cell_first = subset && !a->d_cells ? a->cell_first : 0;
     A.ncount = subset ? a->ncells_active : g->ncells;
-    if (A.ncount == 0) return FB2_OK;
+    if (A.ncount == 0) return pay_zero_fill(a, A);
     return launch_one(a, A, element, true, o.variant, !o.fillzero);
 }
 

@@ -48,6 +48,7 @@ struct AsmArgs {
     int* errflag;
     double p[6];  // element parameters
     int nq;
+    int zero_pending;      // host only: start_assemble's zero fill of nzval is still owed (a kernel that fuses it clears this)
     const double* tab;     // the c_tab contents in global memory (per-lane indexed reads)
     bool const_ok;         // the tables fit (and are) in c_tab
     // table offsets into c_tab / tab (in doubles)

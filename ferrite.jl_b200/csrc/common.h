@@ -186,6 +186,11 @@ struct fb2_assembler {
     uint8_t* d_wcount = nullptr;   //   number of cells of the warp (0 for padding warps)
     int64_t nwarps = 0;
     bool map_complete = false;     // every (cell, i, j) has a pattern entry: unchecked scatter allowed
+    // selective zero fill of the marching-tile kernel (lazy): sorted list of the columns that receive reduce-adds, for the
+    // chunk length it was built for
+    int march_zlz = 0;
+    int64_t march_nzcols = 0;
+    int32_t* d_march_zcols = nullptr;
     int march_state = 0;           // marching-tile kernel: 0 not checked, 1 usable (continuous Q1 numbering on a generated
                                    // hexahedral grid: every grid node carries ONE dof), 2 not usable
     fb2_dh* dh = nullptr;

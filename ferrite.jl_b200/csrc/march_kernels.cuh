@@ -559,3 +559,42 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
                     s_rowok[pl], lane, true, with_f);
     fb2_bulk_wait_read();   // shared memory must outlive the bulk reads
 }
+
+// ---- selective zero fill -----------------------------------------------------------------------------------------------------
+// With `overwrite` the marching kernel writes the columns of tile-interior nodes with plain stores, so start_assemble's
+// zero fill (src/assembler.jl:287-291) is only needed for the columns that receive reduce-adds: nodes on tile faces
+// (x % 8 == 0 or y % 4 == 0) and the node planes where two chunks meet -- 38 % of nzval on C2 instead of all of it.
+// k_march_mark flags those columns (thread per grid node, same predicate as fb2_march_flush); the flagged dofs are
+// compacted into a sorted list once per assembler; k_zero_columns (warp per listed column) runs in front of every launch.
+__global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, int nx, int ny, int nz, int lz, uint8_t* __restrict__ flag) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nn = (int64_t)(nx + 1) * (ny + 1) * (nz + 1);
+    if (t >= nn) return;
+    const int x = (int)(t % (nx + 1)), y = (int)((t / (nx + 1)) % (ny + 1)), p = (int)(t / ((int64_t)(nx + 1) * (ny + 1)));
+    const bool need = (x % 8 == 0) || (y % 4 == 0) || (p % lz == 0) || p == nz;
+    if (!need) return;
+    // the node is corner (sx, sy, sz) of the cell below / left of it (clamped to the grid)
+    const int cx = min(x, nx - 1), cy = min(y, ny - 1), cz = min(p, nz - 1);
+    const int ln = fb2_hexnode(x - cx, y - cy, p - cz);
+    const int64_t cell = cx + (int64_t)nx * (cy + (int64_t)ny * cz);
+    flag[cell_dofs[(size_t)ln * np + cell]] = 1;
+}
+
+// a warp takes 32 listed columns: one lane per column fetches its extent (two dependent loads for 32 columns instead of
+// two per column), then the whole warp zeroes them one after the other
+__global__ void k_zero_columns(const int32_t* __restrict__ cols, int64_t n, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t i = w * 32 + lane;
+    int64_t b = 0, e = 0;
+    if (i < n) {
+        const int c = __ldg(cols + i);
+        b = __ldg(colptr + c);
+        e = __ldg(colptr + c + 1);
+    }
+    const int m = (int)min((int64_t)32, n - w * 32);
+    for (int k = 0; k < m; ++k) {
+        const int64_t bk = __shfl_sync(0xffffffffu, b, k), ek = __shfl_sync(0xffffffffu, e, k);
+        for (int64_t p = bk + lane; p < ek; p += 32) nzval[p] = 0.0;
+    }
+}
