@@ -244,6 +244,109 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def nccl_vs_oracle_check(fb, ctx, dist, world, rank, per_rank=24):
+    """N > 1, before the timing: a small heat problem (per_rank^3 cells per GPU) assembled through the real NCCL exchange
+    path, owned columns gathered on rank 0 and compared entry by entry with the serial oracle (the C restatement of the
+    reference loop; the oracle is the checker here, outside every timed region).  Returns {nccl_vs_oracle_nz_err, _f_err,
+    nccl_vs_oracle_pattern_exact} on rank 0, {} elsewhere."""
+    import numpy as np
+    dims = block_dims(world)
+    nel = tuple(per_rank * d for d in dims)
+    hctx = fb.Context(-1)
+    gg = fb.generate_grid(fb.Hexahedron, nel, ctx=hctx).perturb(0.2)
+    ip = fb.Lagrange(fb.Hexahedron, 1)
+    gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(fb.Hexahedron, 2), ip)
+    part = fb.Partition(gdh, world, rank, dims)
+    g, dh = part.local_problem(ctx)
+    K = fb.allocate_matrix(dh)
+    f = ctx.zeros(dh.ndofs)
+    part.bind(fb.start_assemble(K, f), cv)
+    elem = fb.HeatElement(1.5, 0.7)
+    for _ in range(2):                      # twice: zero fill + exchange must be repeatable
+        part.assemble_(elem, mode="exchange")
+    ctx.synchronize()
+    trip = part.owned_triplets(K, f)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(trip, gathered, dst=0)
+    out = {}
+    if rank == 0:
+        import oracle as O
+        from oracle import cport
+        og = O.perturb_grid(O.generate_grid("hexahedron", nel), nel, (-1.0,) * 3, (1.0,) * 3, 0.2)
+        oip = O.Lagrange("hexahedron", 1)
+        odh = O.DofHandler(og).add("u", oip).close()
+        oK = O.allocate_matrix(odh)
+        of = np.zeros(odh.ndofs)
+        cport.assemble(odh, O.CellValues(O.QuadratureRule("hexahedron", 2), oip), oK, of, "heat", {"k": 1.5, "source": 0.7}, nthreads=1)
+        rows = np.concatenate([t[0] for t in gathered])
+        cols = np.concatenate([t[1] for t in gathered])
+        vals = np.concatenate([t[2] for t in gathered])
+        fd = np.concatenate([t[3] for t in gathered])
+        fv = np.concatenate([t[4] for t in gathered])
+        o = np.lexsort((rows, cols))
+        ocols = np.repeat(np.arange(odh.ndofs), np.diff(oK.colptr))
+        exact = bool(len(rows) == oK.nnz and np.array_equal(rows[o], oK.rowval) and np.array_equal(cols[o] - 1, ocols)
+                     and len(np.unique(fd)) == odh.ndofs == len(fd))
+        out = {"nccl_vs_oracle_pattern_exact": exact,
+               "nccl_vs_oracle_nz_err": float(np.abs(vals[o] - oK.nzval).max() / np.abs(oK.nzval).max()) if exact else None,
+               "nccl_vs_oracle_f_err": float(np.abs(fv[np.argsort(fd)] - of).max() / np.abs(of).max()) if exact else None,
+               "nccl_vs_oracle_problem": f"heat Q1 hex {'x'.join(map(str, nel))}, {world} ranks, exchange mode"}
+    dist.barrier()
+    del part, K, f, g, dh
+    return out
+
+
+def config4_strong(fb, ctx, dist, torch, world, rank, dev, steps, nel_total=(320, 320, 320)):
+    """BASELINE.json configs[4]: Q1^3 linear elasticity on 320^3 cells in total, partitioned over the N ranks (strong
+    scaling: the global problem is fixed), NCCL exchange of the interface columns.  Returns the record on rank 0."""
+    import time as _t
+    rec = {"workload": f"linear elasticity Q1^3 hex {'x'.join(map(str, nel_total))} in total (BASELINE.json configs[4]), "
+                       f"block partition over {world} ranks", "scaling": "strong"}
+    try:
+        t0 = _t.perf_counter()
+        dims = block_dims(world)
+        hctx = fb.Context(-1)
+        ip = fb.Lagrange(fb.Hexahedron, 1) ** 3
+        cv = fb.CellValues(fb.QuadratureRule(fb.Hexahedron, 2), ip)
+        gg = fb.generate_grid(fb.Hexahedron, nel_total, ctx=hctx).perturb(0.2)
+        gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+        part = fb.Partition(gdh, world, rank, dims)
+        g, dh = part.local_problem(ctx)
+        ncells = gg.ncells
+        del gdh, gg
+        K = fb.allocate_matrix(dh)
+        f = ctx.zeros(dh.ndofs)
+        part.bind(fb.start_assemble(K, f), cv)
+        elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+        for _ in range(2):
+            part.assemble_(elem, mode="exchange")
+        torch.cuda.synchronize()
+        rec["setup_s"] = round(_t.perf_counter() - t0, 1)
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            part.assemble_(elem, mode="exchange")
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fz = torch.tensor([float(f[2::3].sum())], dtype=torch.float64, device=dev)
+        dist.all_reduce(fz, op=dist.ReduceOp.SUM)
+        rec.update({"ms_per_step": float(t.item()), "cells_per_s": ncells / (float(t.item()) * 1e-3), "cells": ncells,
+                    "nnz_rank0": K.nnz, "steps": steps, "sum_fz_plus_volume": abs(float(fz.item()) + 8.0)})
+        del part, K, f
+    except Exception as exc:                 # an extra record must never cost the headline line
+        rec["error"] = str(exc)[:300]
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+    torch.cuda.empty_cache()
+    return rec
+
+
 def block_dims(n):
     """px, py, pz with px*py*pz == n, as cubic as possible (2 -> 2x1x1, 4 -> 2x2x1, 8 -> 2x2x2)."""
     dims = [1, 1, 1]
@@ -270,6 +373,7 @@ def main():
                     help="N>1: own cells + NCCL interface exchange, or own+halo cells without communication")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="N>1: skip the extra strong-scaling record of BASELINE.json configs[4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     cfg = CONFIGS[args.config]
@@ -298,6 +402,13 @@ def main():
     bind_to_gpu_numa_node(local_rank)
     ctx = fb.default_context(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    nccl_check = {}
+    if world > 1:
+        # the library's own NCCL communicator (interface exchange); created once, used by every partitioned problem below
+        ids = [fb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        fb.comm_init(ctx, ids[0], world, rank)
+        nccl_check = nccl_vs_oracle_check(fb, ctx, dist, world, rank)
 
     # ---- set-up (not timed): grid, dofs, pattern, map all resident in HBM ------------------------------
     t_setup = time.perf_counter()
@@ -342,10 +453,6 @@ def main():
     a = new_assembler()
     if part is not None:
         part.bind(a, cv)
-        if args.dist_mode == "exchange":
-            ids = [fb.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            fb.comm_init(ctx, ids[0], world, rank)
 
     def step(asm=None):
         """one full assembly: start_assemble (zero fill) + the cell loop [+ interface exchange]"""
@@ -540,6 +647,13 @@ def main():
         except Exception as exc:          # an extra measurement must never cost the headline line
             ea_info = {"error": str(exc)[:200]}
 
+    ndofs0, nnz0, gcells0 = dh.ndofs, K.nnz, g.ncells
+    config4 = None
+    if world > 1 and args.config == "c2" and not args.no_config4:
+        # free the headline problem first: configs[4] needs most of the 180 GB at N = 2
+        del a, a_nz, K, f, part
+        torch.cuda.empty_cache()
+        config4 = config4_strong(fb, ctx, dist, torch, world, rank, dev, steps=max(3, min(args.steps, 5)))
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -547,7 +661,7 @@ def main():
         return
     hbm_peak, peak_src = load_peaks()
     fp64_peak = ctx.measure_fp64_peak()
-    cells_per_s_kernel = g.ncells / (kernel_ms * 1e-3)
+    cells_per_s_kernel = gcells0 / (kernel_ms * 1e-3)
     achieved = cfg["bmin"] * cells_per_s_kernel / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -555,7 +669,7 @@ def main():
         traffic = json.load(open(tp)).get(args.config)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms, "bytes_per_cell": cfg["bmin"],
-                "kernel_cells": g.ncells,
+                "kernel_cells": gcells0,
                 "fp64": {"achieved_tflops": cfg["fmin"] * cells_per_s_kernel / 1e12, "peak_tflops": fp64_peak,
                          "frac": cfg["fmin"] * cells_per_s_kernel / 1e12 / fp64_peak if fp64_peak else None,
                          "flop_per_cell": cfg["fmin"], "peak_source": "FMA microbenchmark in this run"}}
@@ -570,11 +684,14 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["label"] + ("" if world == 1 else f" per GPU, {ncells_total} cells in total"),
-                   "cells": ncells_total, "ndofs_rank0": dh.ndofs, "nnz_rank0": K.nnz, "scatter": args.scatter,
+                   "cells": ncells_total, "ndofs_rank0": ndofs0, "nnz_rank0": nnz0, "scatter": args.scatter,
                    "l2": "inputs+outputs (>= 3 GB per GPU) exceed the 126 MB L2; no flush needed", "setup_s": round(t_setup, 2),
                    "parallelism": par},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "checks": checks,
     }
+    line["checks"].update(nccl_check)
+    if config4:
+        line["config4"] = config4
     if e2e:
         line["e2e"] = e2e
     if apply_info:

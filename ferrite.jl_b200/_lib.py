@@ -192,6 +192,8 @@ lib.fb2_version.restype = C.c_char_p
 lib.fb2_version.argtypes = []
 lib.fb2_last_error.restype = C.c_char_p
 lib.fb2_last_error.argtypes = []
+lib.fb2_last_kernel.restype = C.c_char_p
+lib.fb2_last_kernel.argtypes = []
 for _name, _args in _PROTOS.items():
     _f = getattr(lib, _name)
     _f.argtypes = _args

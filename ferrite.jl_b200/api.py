@@ -882,6 +882,11 @@ def apply_assemble_(assembler, ch, element, cv, u=None, applyzero=False, ea=None
     return ea
 
 
+def last_kernel():
+    """name of the kernel family the last assemble call launched for the cell loop (k_march_hex, k_cell_scalar, ...)"""
+    return L.lib.fb2_last_kernel().decode()
+
+
 def finish_assemble(assembler):
     assembler.K.dh.grid.ctx.synchronize()
     return assembler.K, assembler.f

@@ -13,6 +13,9 @@
 #include "assemble_kernels.cuh"
 #include "march_kernels.cuh"
 
+const char* g_fb2_last_kernel = "";
+extern "C" const char* fb2_last_kernel(void) { return g_fb2_last_kernel; }
+
 namespace {
 
 // the zero fill of nzval that start_assemble owes, for every kernel that does not fuse it
@@ -105,6 +108,7 @@ int launch_scalar(fb2_ctx* ctx, const AsmArgs& A, bool atomic, int variant = 0, 
     else if (atomic) k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, true, 1, ROLL><<<grid, bs, 0, ctx->stream>>>(A);
     else k_cell_scalar<DIM, NGEO, NB, NQ, ELEM, false><<<grid, bs, 0, ctx->stream>>>(A);
     ctx->launches++;
+    g_fb2_last_kernel = "k_cell_scalar";
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;
 }
@@ -142,6 +146,7 @@ int launch_blocks(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
         FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
         k<<<grid, bs, L.total, ctx->stream>>>(A, cells);
     }
+    g_fb2_last_kernel = "k_cell_blocks";
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;
@@ -168,6 +173,7 @@ int launch_syrk(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic) {
         FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, S::NTHR, smem, ctx->stream>>>(A);
     }
+    g_fb2_last_kernel = "k_cell_syrk";
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     return FB2_OK;
@@ -323,6 +329,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 auto k = k_tile_scalar<DIM, NGEO, NB, NQ, ELEM, TC, 2>;
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 k<<<(unsigned)S->ntiles, TC, smem, ctx->stream>>>(A, T);
+                g_fb2_last_kernel = "k_tile_scalar";
                 ctx->launches++;
                 FB2_CUDA(cudaGetLastError());
                 return FB2_OK;
@@ -335,14 +342,23 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
     // variant 30 forces the thread-per-cell kernel for comparison.
     if constexpr (DIM == 3 && NGEO == 8 && NB == 8 && NQ == 8) {
         fb2_grid* g = a->dh->grid;
-        const int64_t lay = g->nel[0] * g->nel[1];
-        if (atomic && (variant == 0 || variant == 31) && g->generated && g->celltype == FB2_HEXAHEDRON && A.cells == nullptr && A.ncount > 0 &&
-            A.cell_first % lay == 0 && A.ncount % lay == 0 && g->nel[0] < (1 << 28) && g->nel[1] < (1 << 28) && march_usable(a)) {
+        // structured view: generate_grid order (cells x fastest; any whole-layer range), or a box with a cell map (the local
+        // grid of a block partition; any range of cell ids)
+        const bool gen = g->generated && g->celltype == FB2_HEXAHEDRON;
+        const bool boxed = !gen && g->structured && g->d_sv_cellmap != nullptr;
+        const int64_t* snel = gen ? g->nel : g->sv_nel;
+        const int64_t lay = (gen || boxed) ? snel[0] * snel[1] : 1;
+        const bool range_ok = gen ? (A.cell_first % lay == 0 && A.ncount % lay == 0) : boxed;
+        if (atomic && (variant == 0 || variant == 31) && (gen || boxed) && A.cells == nullptr && A.ncount > 0 && range_ok &&
+            snel[0] < (1 << 28) && snel[1] < (1 << 28) && march_usable(a)) {
             MarchArgs M;
-            M.nx = (int)g->nel[0];
-            M.ny = (int)g->nel[1];
-            M.z0 = (int)(A.cell_first / lay);
-            M.z1 = M.z0 + (int)(A.ncount / lay);
+            M.nx = (int)snel[0];
+            M.ny = (int)snel[1];
+            M.z0 = gen ? (int)(A.cell_first / lay) : 0;
+            M.z1 = gen ? M.z0 + (int)(A.ncount / lay) : (int)snel[2];
+            M.cellmap = gen ? nullptr : g->d_sv_cellmap;
+            M.cell_lo = gen ? 0 : A.cell_first;
+            M.cell_hi = gen ? g->ncells : A.cell_first + A.ncount;
             M.tiles_x = (M.nx + 7) / 8;
             M.tiles_y = (M.ny + 3) / 4;
             M.cap = fb2_march_cap(std::max(a->pat->max_col_len, 1));
@@ -372,7 +388,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 // long as one memset over everything (0.23 vs 0.24 ms, profiles/r02_launches_c2.csv), so the memset stays.
                 if (A.zero_pending) {
                     const char* ez = getenv("FB2_MARCH_ZSEL");
-                    if (ez && atoi(ez) == 1 && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
+                    if (ez && atoi(ez) == 1 && gen && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
                         FB2_TRY(march_zero_list(a, M.lz));
                         if (a->march_nzcols > 0)
                             k_zero_columns<<<(unsigned)((a->march_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_march_zcols, a->march_nzcols,
@@ -384,6 +400,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                     A.zero_pending = 0;
                 }
                 k<<<(unsigned)(tiles * nchunks), 32, smem, ctx->stream>>>(A, M);
+                g_fb2_last_kernel = "k_march_hex";
                 ctx->launches++;
                 FB2_CUDA(cudaGetLastError());
                 return FB2_OK;
@@ -501,6 +518,17 @@ int fb2_warplist_build(fb2_assembler* a) {
     FB2_CUDA(cudaMemcpy(a->d_wfirst, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     FB2_CUDA(cudaMemcpy(a->d_wcount, count.data(), count.size(), cudaMemcpyHostToDevice));
     return FB2_OK;
+}
+
+bool fb2_march_applicable(fb2_assembler* a, int element, const fb2_asm_opts* opts) {
+    const fb2_cv* cv = a->cv;
+    const fb2_grid* g = a->dh->grid;
+    if (!cv || !(element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS)) return false;
+    if (opts && (opts->scatter_mode != FB2_SCATTER_ATOMIC || !(opts->variant == 0 || opts->variant == 31))) return false;
+    if (cv->celltype != FB2_HEXAHEDRON || cv->nb != 8 || cv->nq != 8 || cv->vdim != 1 || cv->ngeo != 8) return false;
+    const bool gen = g->generated && g->celltype == FB2_HEXAHEDRON, boxed = !gen && g->structured && g->d_sv_cellmap != nullptr;
+    if (!(gen || boxed) || a->pat->max_col_len >= 255) return false;
+    return march_usable(a);
 }
 
 int fb2_check_device_error(fb2_ctx* ctx) {

@@ -113,6 +113,13 @@ struct fb2_grid {
     double* d_xyz = nullptr;      // [nnodes][xstride]
     double* d_xyz_stage = nullptr;  // staging buffer of fb2_grid_upload_coordinates_async
     int xstride = 0;              // 4 for sdim 3, 2 for sdim 2, 1 for sdim 1
+    // structured view of a hexahedral grid that is NOT stored in generate_grid order (the local grid of a block partition:
+    // cells ordered [interface | interior | halo]): the cells form a box of sv_nel cells, box position -> cell id in
+    // sv_cellmap (-1 = no such cell), and node (a, b, c) of the box has the id a + (sv_nel[0]+1) (b + (sv_nel[1]+1) c).
+    bool structured = false;
+    int64_t sv_nel[3] = {0, 0, 0};
+    std::vector<int32_t> sv_cellmap;
+    int32_t* d_sv_cellmap = nullptr;
 };
 int fb2_grid_upload(fb2_grid* g);
 int fb2_grid_upload_xyz(fb2_grid* g);
@@ -273,5 +280,8 @@ int fb2_warplist_build(fb2_assembler* a);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,
                         double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 int fb2_check_device_error(fb2_ctx* ctx);
+// the marching-tile kernel (march_kernels.cuh) will take `element` on this assembler (structured hexahedral grid, continuous
+// Q1 numbering, atomic scatter, default variant)
+bool fb2_march_applicable(fb2_assembler* a, int element, const fb2_asm_opts* opts);
 int fb2_coloring_build(fb2_assembler* a);
 int fb2_ch_sync_device(fb2_ch* ch);      // upload the inhomogeneities if update! changed them

@@ -283,6 +283,7 @@ extern "C" int fb2_grid_destroy(fb2_grid* g) {
         cudaFree(g->d_conn);
         cudaFree(g->d_xyz);
         cudaFree(g->d_xyz_stage);
+        cudaFree(g->d_sv_cellmap);
     }
     delete g;
     return FB2_OK;

@@ -34,6 +34,11 @@ struct MarchArgs {
     int overwrite;         // 1: nzval / f were zero-filled for this launch and nobody else adds to tile-interior columns
                            //    => they are written with plain (bulk) stores; 0: everything is added
     const uint8_t* mapb;   // byte-packed offset map (fb2_map_build_bytes)
+    // cell of box position (x, y, z): x + nx (y + ny z) for grids in generate_grid order (cellmap == nullptr), else
+    // cellmap[that] (-1 = no cell there).  Only cells with cell_lo <= id < cell_hi are assembled by this launch (the own cells
+    // of a partition, a slab of the streamed host path, ...); the others count as absent.
+    const int32_t* cellmap;
+    int64_t cell_lo, cell_hi;
 };
 
 constexpr int MARCH_PN = 45;   // nodes of a tile plane (9 x 5)
@@ -408,6 +413,22 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     const int64_t cxy = (int64_t)min(cx, M.nx - 1) + (int64_t)M.nx * min(cy, M.ny - 1);
     const int64_t lay = (int64_t)M.nx * M.ny;
     const int64_t np = A.ncells_pad;
+    // id of the lane's cell in layer z, -1 if there is none or it is not part of this launch
+    auto cell_at = [&](int z) -> int64_t {
+        if (!inside || z >= M.z1) return -1;
+        const int64_t c = M.cellmap ? (int64_t)__ldg(M.cellmap + cxy + lay * z) : cxy + lay * z;
+        return (c >= M.cell_lo && c < M.cell_hi) ? c : -1;
+    };
+    // dofs of the lane's four corners of node plane zp + 1: from the cell below it (layer zp) if present, else from the
+    // cell above it -- a node plane between an assembled and an absent layer still needs its column copies
+    auto plane_dofs = [&](int64_t cbelow, int64_t cabove, int (&d)[4]) -> bool {
+        const int64_t c = cbelow >= 0 ? cbelow : cabove;
+        const int base = cbelow >= 0 ? 4 : 0;
+        if (c < 0) return false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = __ldg(A.cell_dofs + (size_t)(base + i) * np + c);
+        return true;
+    };
     const int tn0 = ly * 9 + lx;                    // tile node of the cell's corner (0, 0)
     const bool with_f = A.f != nullptr && ELEM == FB2_ELEM_HEAT;
     const double kscale = A.p[0], fscale = A.p[1];
@@ -443,32 +464,33 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     fetch_plane_xyz(zb, 0);
     fetch_plane_xyz(zb + 1, 1);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    int dnext[4];   // dofs of the top nodes of the next layer's cell (prefetched one layer ahead)
-    {   // bottom plane of the first layer
-        const int64_t cell = cxy + lay * zb;
-        int d[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = __ldg(A.cell_dofs + (size_t)i * np + cell);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell);
+    // cells of the lane in layers z, z + 1, z + 2 (looked up ahead of their use), dofs of node plane z + 1 (prefetched one
+    // layer ahead) and whether the lane has any
+    int64_t c0 = cell_at(zb), c1 = zb + 1 < ze ? cell_at(zb + 1) : -1, c2 = zb + 2 < ze ? cell_at(zb + 2) : -1;
+    int dnext[4] = {0, 0, 0, 0};
+    bool pubnext;
+    {   // bottom plane of the first layer (the cells below it belong to another chunk)
+        int d[4] = {0, 0, 0, 0};
+        const bool pub = plane_dofs(-1, c0, d);
+        pubnext = plane_dofs(c0, c1, dnext);
         int64_t bA, bB, eA, eB;
-        fb2_march_plane_issue(s_dof, A.colptr, lane, tn0, inside, d[0], d[1], d[2], d[3], bA, bB, eA, eB);
+        fb2_march_plane_issue(s_dof, A.colptr, lane, tn0, pub, d[0], d[1], d[2], d[3], bA, bB, eA, eB);
         fb2_march_plane_finish(s_cs, s_len, s_gb, s_rowok, lane, bA, bB, eA, eB);
     }
+    const int64_t csafe = M.cell_lo;   // a valid cell for the loads of lanes without one
 
     for (int z = zb; z < ze; ++z) {
         const int pb = (z - zb) & 1, pt = pb ^ 1;   // window planes holding the node planes z and z + 1
-        const int64_t cell = cxy + lay * z;
+        const bool have = c0 >= 0;
+        const int64_t cell = have ? c0 : csafe;
+        const int64_t c3 = z + 3 < ze ? cell_at(z + 3) : -1;
         // offset map of this layer's cell and set-up of the top plane: requested now, needed after the integration
 #pragma unroll
         for (int k = 0; k < 4; ++k) fb2_cp_async16(&s_map[k * 32 + lane], M.mapb + ((size_t)k * np + cell) * 16);
         asm volatile("cp.async.commit_group;" ::: "memory");
         int64_t bA, bB, eA, eB;
-        fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, inside, dnext[0], dnext[1], dnext[2], dnext[3], bA, bB, eA, eB);
-        if (z + 1 < ze) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dnext[i] = __ldg(A.cell_dofs + (size_t)(4 + i) * np + cell + lay);
-        }
+        fb2_march_plane_issue(s_dof + pt * PS, A.colptr, lane, tn0, pubnext, dnext[0], dnext[1], dnext[2], dnext[3], bA, bB, eA, eB);
+        pubnext = plane_dofs(c1, c2, dnext);   // node plane z + 2, used by the next iteration
         // node coordinates: both planes were requested at least one layer ago
         asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the offset map just requested
         __syncwarp();
@@ -488,8 +510,8 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
             }
             bad = fb2_scalar_element<3, 8, 8, 8, ELEM, true, false>(A, x, Ke, fe);
         }
-        if (bad && inside) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
-        const bool act = inside && !bad;
+        if (bad && have) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
+        const bool act = have && !bad;
         asm volatile("cp.async.wait_group 0;" ::: "memory");   // the offset map
         __syncwarp();
         if (z + 1 < ze) fetch_plane_xyz(z + 2, pb);   // the slot of node plane z is free now; lands during the flush
@@ -553,6 +575,7 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         if (CHECK && missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
         fb2_march_flush(A, s_acc + (size_t)pb * cap, s_acc + o_f + pb * PS, s_cs + pb * PS, s_len + pb * PS, s_gb + pb * PS, s_dof + pb * PS,
                         s_rowok[pb], lane, z == zb || !M.overwrite, with_f);
+        c0 = c1; c1 = c2; c2 = c3;
     }
     const int pl = (ze - zb) & 1;   // the top plane of the chunk is shared with the chunk above
     fb2_march_flush(A, s_acc + (size_t)pl * cap, s_acc + o_f + pl * PS, s_cs + pl * PS, s_len + pl * PS, s_gb + pl * PS, s_dof + pl * PS,

@@ -17,6 +17,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 
 #include "common.h"
@@ -111,6 +113,39 @@ __global__ void k_unpack_add(const int64_t* __restrict__ pos, int64_t nnz, const
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < nnz) nzval[pos[t]] += in[t];               // positions are unique within one peer list
     else if (t < nnz + nf && f) f[fd[t - nnz]] += in[t];
+}
+
+// All peers in one launch: segment p = [nz values | f values] of the exchange with one peer.  An owned entry can receive
+// partial sums from several peers, so the fused unpack adds with REDs.
+struct XSeg {
+    const int64_t* pos;
+    const int32_t* fd;
+    double* buf;
+    int64_t nnz, nf, start;   // start = first thread of the segment
+};
+constexpr int XSEG_MAX = 64;
+struct XSegs { XSeg s[XSEG_MAX]; int n; int64_t total; };
+
+__global__ void k_pack_all(const XSegs S, const double* __restrict__ nzval, const double* __restrict__ f) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.total) return;
+    int k = 0;
+    while (k + 1 < S.n && t >= S.s[k + 1].start) ++k;
+    const XSeg& sg = S.s[k];
+    const int64_t i = t - sg.start;
+    sg.buf[i] = i < sg.nnz ? nzval[sg.pos[i]] : (f ? f[sg.fd[i - sg.nnz]] : 0.0);
+}
+
+__global__ void k_unpack_all(const XSegs S, double* __restrict__ nzval, double* __restrict__ f) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S.total) return;
+    int k = 0;
+    while (k + 1 < S.n && t >= S.s[k + 1].start) ++k;
+    const XSeg& sg = S.s[k];
+    const int64_t i = t - sg.start;
+    const double v = sg.buf[i];
+    if (i < sg.nnz) atomicAdd(nzval + sg.pos[i], v);
+    else if (f) atomicAdd(f + sg.fd[i - sg.nnz], v);
 }
 
 __global__ void k_mask_unowned(const int32_t* __restrict__ unowned, int64_t n, const int64_t* __restrict__ colptr,
@@ -345,11 +380,55 @@ extern "C" int fb2_partition_export(fb2_part* P, int64_t* cells_global, uint8_t*
     return FB2_OK;
 }
 
+// Structured view of the local grid of a block partition of a generate_grid hexahedral mesh: own + halo cells fill a box,
+// and the local node numbering (ascending global ids) is the box's own x-fastest numbering.  Both facts are VERIFIED here
+// cell by cell; if either fails the grid simply has no structured view (the generic kernels are used).
+static void attach_structured_view(const fb2_part* P, fb2_grid* lg) {
+    const fb2_grid* g = P->gdh->grid;
+    if (!g->generated || g->celltype != FB2_HEXAHEDRON) return;
+    const int64_t nx = g->nel[0], ny = g->nel[1];
+    const int64_t nl = (int64_t)P->cells_global.size();
+    int64_t lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {-1, -1, -1};
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int64_t ijk[3] = {c % nx, (c / nx) % ny, c / (nx * ny)};
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], ijk[d]); hi[d] = std::max(hi[d], ijk[d]); }
+    }
+    const int64_t L[3] = {hi[0] - lo[0] + 1, hi[1] - lo[1] + 1, hi[2] - lo[2] + 1};
+    if (L[0] * L[1] * L[2] > (int64_t)1 << 30) return;
+    if ((int64_t)P->l2g_node.size() != (L[0] + 1) * (L[1] + 1) * (L[2] + 1)) return;   // the node set is not the full box
+    std::vector<int32_t> map((size_t)(L[0] * L[1] * L[2]), -1);
+    static const int hx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, hy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, hz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int64_t b[3] = {c % nx - lo[0], (c / nx) % ny - lo[1], c / (nx * ny) - lo[2]};
+        map[(size_t)(b[0] + L[0] * (b[1] + L[1] * b[2]))] = (int32_t)l;
+        for (int v = 0; v < 8; ++v) {
+            const int64_t expect = (b[0] + hx[v]) + (L[0] + 1) * ((b[1] + hy[v]) + (L[1] + 1) * (b[2] + hz[v]));
+            if (P->lcells[(size_t)l * 8 + v] - 1 != expect) return;
+        }
+    }
+    if (lg->ctx->device >= 0) {
+        if (cudaSetDevice(lg->ctx->device) != cudaSuccess) return;
+        if (cudaMalloc(&lg->d_sv_cellmap, map.size() * sizeof(int32_t)) != cudaSuccess) { lg->d_sv_cellmap = nullptr; return; }
+        if (cudaMemcpy(lg->d_sv_cellmap, map.data(), map.size() * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(lg->d_sv_cellmap);
+            lg->d_sv_cellmap = nullptr;
+            return;
+        }
+    }
+    for (int d = 0; d < 3; ++d) lg->sv_nel[d] = L[d];
+    lg->sv_cellmap.swap(map);
+    lg->structured = true;
+}
+
 extern "C" int fb2_partition_local_grid(fb2_part* P, fb2_ctx* ctx, fb2_grid** out) {
     FB2_CHECK(P && ctx && out, FB2_ERR_BAD_ARG, "fb2_partition_local_grid: null argument");
     fb2_grid* g = P->gdh->grid;
-    return fb2_grid_from_host(ctx, g->celltype, (int64_t)P->cells_global.size(), (int64_t)P->l2g_node.size(), g->sdim,
-                              P->lcells.data(), P->lxyz.data(), out);
+    FB2_TRY(fb2_grid_from_host(ctx, g->celltype, (int64_t)P->cells_global.size(), (int64_t)P->l2g_node.size(), g->sdim,
+                               P->lcells.data(), P->lxyz.data(), out));
+    attach_structured_view(P, *out);
+    return FB2_OK;
 }
 
 extern "C" int fb2_partition_local_dh(fb2_part* P, fb2_grid* local_grid, fb2_dh** out) {
@@ -579,7 +658,33 @@ extern "C" int fb2_partition_exchange(fb2_part* P, double* nzval_dev, double* f_
     fb2_ctx* ctx = P->bound->dh->grid->ctx;
     FB2_CHECK(ctx->nccl_comm, FB2_ERR_NCCL, "fb2_partition_exchange: call fb2_comm_init_rank first");
     FB2_CHECK(ctx->nranks == P->nparts && ctx->rank == P->rank, FB2_ERR_BAD_ARG, "fb2_partition_exchange: communicator and partition disagree");
-    for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_pack(P, p, nzval_dev, f_dev, nullptr));
+    // pack for every peer in one launch (<= XSEG_MAX peers; more fall back to one launch per peer)
+    XSegs SS, RS;
+    SS.n = RS.n = 0;
+    SS.total = RS.total = 0;
+    bool fused = true;
+    for (int p = 0; p < P->nparts && fused; ++p) {
+        PeerPlan& pp = P->peers[p];
+        const int64_t ns = (int64_t)(pp.send_rows.size() + pp.send_f.size()), nr = (int64_t)(pp.recv_rows.size() + pp.recv_f.size());
+        if (ns) {
+            if (SS.n == XSEG_MAX) { fused = false; break; }
+            SS.s[SS.n++] = XSeg{pp.d_send_pos, pp.d_send_f, pp.d_sendbuf, (int64_t)pp.send_rows.size(), (int64_t)pp.send_f.size(), SS.total};
+            SS.total += ns;
+        }
+        if (nr) {
+            if (RS.n == XSEG_MAX) { fused = false; break; }
+            RS.s[RS.n++] = XSeg{pp.d_recv_pos, pp.d_recv_f, pp.d_recvbuf, (int64_t)pp.recv_rows.size(), (int64_t)pp.recv_f.size(), RS.total};
+            RS.total += nr;
+        }
+    }
+    if (fused) {
+        if (SS.total) {
+            k_pack_all<<<nblk(SS.total, 256), 256, 0, ctx->stream>>>(SS, nzval_dev, f_dev);
+            ctx->launches++;
+        }
+    } else {
+        for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_pack(P, p, nzval_dev, f_dev, nullptr));
+    }
     FB2_NCCL(g_nccl.GroupStart());
     for (int p = 0; p < P->nparts; ++p) {
         PeerPlan& pp = P->peers[p];
@@ -588,7 +693,15 @@ extern "C" int fb2_partition_exchange(fb2_part* P, double* nzval_dev, double* f_
         if (nr) FB2_NCCL(g_nccl.Recv(pp.d_recvbuf, nr, /*ncclFloat64*/ 8, p, ctx->nccl_comm, ctx->stream));
     }
     FB2_NCCL(g_nccl.GroupEnd());
-    for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_unpack_add(P, p, nullptr, nzval_dev, f_dev));
+    if (fused) {
+        if (RS.total) {
+            k_unpack_all<<<nblk(RS.total, 256), 256, 0, ctx->stream>>>(RS, nzval_dev, f_dev);
+            ctx->launches++;
+        }
+        FB2_CUDA(cudaGetLastError());
+    } else {
+        for (int p = 0; p < P->nparts; ++p) FB2_TRY(fb2_partition_unpack_add(P, p, nullptr, nzval_dev, f_dev));
+    }
     return FB2_OK;
 }
 
@@ -599,7 +712,10 @@ extern "C" int fb2_assemble_distributed(fb2_assembler* a, fb2_part* P, int mode,
     FB2_CHECK(mode == FB2_DIST_EXCHANGE || mode == FB2_DIST_HALO || mode == FB2_DIST_OWN_ONLY, FB2_ERR_BAD_ARG,
               "fb2_assemble_distributed: unknown mode %d", mode);
     fb2_ctx* ctx = a->dh->grid->ctx;
-    if (mode == FB2_DIST_EXCHANGE && P->nparts > 1 && P->n_iface > 0 && P->n_iface < P->ncells_own && ctx->nccl_comm) {
+    // The marching-tile kernel sweeps the whole box of local cells in one launch (interface and interior cells are not
+    // separate ranges of its tiles), so with it the exchange follows the assembly on the same stream.
+    const bool marching = fb2_march_applicable(a, element, opts);
+    if (!marching && mode == FB2_DIST_EXCHANGE && P->nparts > 1 && P->n_iface > 0 && P->n_iface < P->ncells_own && ctx->nccl_comm) {
         // interface cells first; their exchange (pack, NCCL send/recv, unpack, mask) runs on the second stream while the
         // interior cells are assembled.  Interior cells touch no entry of an exchanged row or column, so the two never
         // write the same address.

@@ -199,6 +199,10 @@ int fb2_assemble_host(fb2_assembler* a, int element, const void* params, size_t 
  * Host buffers should be pinned (cudaHostRegister / CUDA.pin) for the copies to overlap. */
 int fb2_assemble_host_streamed(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* xyz_host,
                                const double* u_host, double* nzval_host, double* f_host, const fb2_asm_opts* opts);
+/* name of the kernel family the last fb2_assemble* call on this thread's process launched for the cell loop ("k_march_hex",
+ * "k_cell_scalar", "k_cell_syrk", "k_cell_blocks", "k_tile_scalar", ...): lets tests and benchmarks state WHICH hand-written
+ * kernel produced a number (no reference counterpart) */
+const char* fb2_last_kernel(void);
 /* create_coloring(grid): number of colours and, optionally, the colour of every cell (0-based colour ids) */
 int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color);
 /* scatter-only entry: assemble!(assembler, dofs, Ke, fe) for a batch of precomputed element matrices

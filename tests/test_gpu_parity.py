@@ -201,6 +201,7 @@ def test_marching_tile_kernel(ctx, nel, lz, monkeypatch):
     f.fill_(-3.0)
     fb.assemble_(a, elem, cv)
     fb.finish_assemble(a)
+    assert fb.last_kernel() == "k_march_hex"
     nz, fv = K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()
     assert close(nz, oK.nzval)[0] and close(fv, of)[0]
     a2 = fb.start_assemble(K, f, fillzero=False)     # accumulate onto the first result
@@ -211,6 +212,7 @@ def test_marching_tile_kernel(ctx, nel, lz, monkeypatch):
     a3.variant = 30                                   # thread-per-cell kernel
     fb.assemble_(a3, elem, cv)
     fb.finish_assemble(a3)
+    assert fb.last_kernel() == "k_cell_scalar"
     assert close(K.nzval.cpu().numpy(), nz)[0] and close(f.cpu().numpy(), fv)[0]
 
 
@@ -533,6 +535,7 @@ def test_full_size_properties_c2_scaled(ctx):
 @pytest.mark.parametrize("mode", ["halo", "own"])
 @pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,p,nparts", [
     (fb.Hexahedron, (6, 5, 4), 1, 1, 2, "heat", {"k": 1.0, "source": 1.0}, 4),
+    (fb.Hexahedron, (19, 11, 10), 1, 1, 2, "heat", {"k": 1.3, "source": 0.6}, 8),
     (fb.Hexahedron, (4, 4, 4), 1, 3, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 8),
     (fb.Hexahedron, (3, 3, 2), 2, 3, 3, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 2),
     (fb.Tetrahedron, (3, 2, 2), 2, 1, 2, "heat", {}, 3),
@@ -561,6 +564,8 @@ def test_partitioned_assembly_matches_serial_oracle(ctx, mode, ct, nel, order, v
         a = fb.start_assemble(K, f)
         pt.bind(a, cv)
         pt.assemble_(elem, mode=mode)
+        if kind == "heat" and ct == fb.Hexahedron:      # block partition of a generated grid: structured view + cell map
+            assert fb.last_kernel() == "k_march_hex"
         st.append((lg, ldh, K, f, a))
     if mode == "own":
         for r, pt in enumerate(parts):
