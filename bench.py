@@ -653,7 +653,8 @@ def main():
         # free the headline problem first: configs[4] needs most of the 180 GB at N = 2
         del a, a_nz, K, f, part
         torch.cuda.empty_cache()
-        config4 = config4_strong(fb, ctx, dist, torch, world, rank, dev, steps=max(3, min(args.steps, 5)))
+        c4n = int(os.environ.get("FB2_C4_NEL", "320"))      # debugging knob: a smaller total size
+        config4 = config4_strong(fb, ctx, dist, torch, world, rank, dev, steps=max(3, min(args.steps, 5)), nel_total=(c4n,) * 3)
     if rank != 0:
         if world > 1:
             dist.barrier()

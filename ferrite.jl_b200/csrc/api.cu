@@ -249,10 +249,11 @@ extern "C" int fb2_assembler_create(fb2_dh* dh, fb2_pattern* p, fb2_cv* cv, fb2_
                   "fb2_assembler_create: the element must cover all %d dofs of a cell (CellValues has %d)", dh->ndpc, cv->nb * cv->vdim);
         FB2_CHECK(cv->ngeo == dh->grid->nnpc, FB2_ERR_BAD_ARG, "fb2_assembler_create: geometric interpolation has %d nodes, cells have %d", cv->ngeo, dh->grid->nnpc);
         FB2_CHECK(cv->rdim == dh->grid->sdim, FB2_ERR_UNSUPPORTED, "embedded elements (rdim %d in sdim %d) are not supported", cv->rdim, dh->grid->sdim);
-        // kernels, zero fills and table uploads all run on the GRID's context (stream); a CellValues made on another
-        // context of the same device is fine, one made for another device is not
-        FB2_CHECK(cv->ctx == nullptr || cv->ctx->device == dh->grid->ctx->device, FB2_ERR_BAD_ARG,
-                  "fb2_assembler_create: the CellValues live on device %d, the grid on device %d", cv->ctx->device, dh->grid->ctx->device);
+        // kernels, zero fills and table uploads all run on the GRID's context (stream), whatever context the CellValues were
+        // created on; their device copy belongs to the first device that uses them
+        FB2_CHECK(cv->tables_device < 0 || cv->tables_device == dh->grid->ctx->device, FB2_ERR_BAD_ARG,
+                  "fb2_assembler_create: these CellValues are already in use on device %d, the grid lives on device %d (create one CellValues per device)",
+                  cv->tables_device, dh->grid->ctx->device);
     }
     fb2_assembler* a = new fb2_assembler();
     a->dh = dh;

@@ -63,6 +63,7 @@ int upload_tables(fb2_assembler* a, AsmArgs* A) {
         if (cv->d_tables == nullptr) {   // global copy: the CTA kernels index the tables per lane, which a constant bank serialises
             FB2_CUDA(cudaMalloc(&cv->d_tables, sizeof(double) * total));
             FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), sizeof(double) * total, cudaMemcpyHostToDevice));
+            cv->tables_device = ctx->device;
             cv->tables_count = total;
         }
     }
@@ -231,6 +232,8 @@ int dispatch_neohooke(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, i
 bool cv_is_q1hex_gauss2(const fb2_cv* cv) {
     if (cv->celltype != FB2_HEXAHEDRON || cv->nq != 8 || cv->nb != 8 || cv->ngeo != 8 || cv->rdim != 3) return false;
     const double tol = 4e-15;
+    for (int q = 1; q < 8; ++q)
+        if (cv->w[q] != cv->w[0]) return false;     // the analytic element takes one weight
     for (int q = 0; q < 8; ++q) {
         const int qb[3] = {q & 1, (q >> 1) & 1, (q >> 2) & 1};
         for (int i = 0; i < 8; ++i) {
@@ -378,6 +381,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 const int nchunks = (nzl + M.lz - 1) / M.lz;
                 // variant 31: table-driven integration inside the marching kernel (A/B against the analytic element)
                 const bool analytic = ELEM == FB2_ELEM_HEAT && variant != 31 && cv_is_q1hex_gauss2(a->cv);
+                if (analytic) A.p[2] = 0.125 * a->cv->w[0];   // the common quadrature weight / 8 (see fb2_hex8_heat)
                 auto k = a->map_complete ? (analytic ? k_march_hex<ELEM, false, true> : k_march_hex<ELEM, false, false>)
                                          : (analytic ? k_march_hex<ELEM, true, true> : k_march_hex<ELEM, true, false>);
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

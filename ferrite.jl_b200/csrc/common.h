@@ -163,6 +163,7 @@ struct fb2_cv {
     // host tables, q-major: N[q][i], dN[q][i][d], M[q][j], dM[q][j][d], w[q], pts[q][d]
     std::vector<double> N, dN, M, dM, w, pts;
     double* d_tables = nullptr;   // packed [w | N | dN | M | dM] on the device
+    int tables_device = -1;       // device that holds d_tables (the first one that used this CellValues); -1 = none yet
     size_t tables_count = 0;
 };
 

@@ -466,6 +466,7 @@ extern "C" int fb2_reinit_cells(fb2_cv* cv, fb2_grid* g, const int64_t* cells, i
         memcpy(h.data() + o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
         FB2_CUDA(cudaMalloc(&cv->d_tables, h.size() * sizeof(double)));
         FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        cv->tables_device = ctx->device;
         cv->tables_count = h.size();
     }
     int64_t* d_cells = nullptr;
@@ -496,6 +497,7 @@ static int ensure_cv_tables(fb2_cv* cv) {
     memcpy(h.data() + o_dM, cv->dM.data(), sizeof(double) * nq * ng * rd);
     FB2_CUDA(cudaMalloc(&cv->d_tables, h.size() * sizeof(double)));
     FB2_CUDA(cudaMemcpy(cv->d_tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    { int dev = -1; cudaGetDevice(&dev); cv->tables_device = dev; }
     cv->tables_count = h.size();
     return FB2_OK;
 }

@@ -245,7 +245,7 @@ __device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, const double* 
 //     entries are accumulated;
 //   * the shape-function values are two constants (no table loads).
 // Point q = qx + 2 qy + 4 qz sits at ((2 qx - 1) g, (2 qy - 1) g, (2 qz - 1) g), g = 1/sqrt(3) (src/Quadrature/
-// quadrature.jl:96-104: first coordinate fastest, points ascending); w[q] comes from the CellValues.
+// quadrature.jl:96-104: first coordinate fastest, points ascending); the common weight comes from the CellValues.
 // ------------------------------------------------------------------------------------------------------------------------
 __host__ __device__ constexpr double fb2_q1n(int s, int p) {   // 1-D linear shape function of node s at Gauss point p
     return s == p ? 0.5 * (1.0 + 0.5773502691896257) : 0.5 * (1.0 - 0.5773502691896257);
@@ -257,7 +257,7 @@ __host__ __device__ constexpr int fb2_hexnode(int sx, int sy, int sz) { return s
 // cost more (29 % of all stall samples, profiles/r02_prof_c2_march_c.txt) than the shared sub-expressions save.
 // The node coordinates are read from the shared-memory window inside the loop (xs[j] = the lane's node j, 32 bytes apart
 // in z-pairs) instead of living in 48 registers next to the 72 of Ke / fe.
-__device__ __forceinline__ bool fb2_hex8_heat(const double* const (&xs)[8], const double* __restrict__ tw, double (&Ke)[36], double (&fe)[8]) {
+__device__ __forceinline__ bool fb2_hex8_heat(const double* const (&xs)[8], const double w8, double (&Ke)[36], double (&fe)[8]) {
     constexpr double NA = fb2_q1n(0, 0), NB = fb2_q1n(1, 0);   // shape function of the near / far node of a Gauss point
 #pragma unroll
     for (int e = 0; e < 36; ++e) Ke[e] = 0.0;
@@ -307,7 +307,6 @@ __device__ __forceinline__ bool fb2_hex8_heat(const double* const (&xs)[8], cons
         }
 #pragma unroll
         for (int qx = 0; qx < 2; ++qx) {
-            const int q = qx + 2 * it;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 J[c][1] = fma(Dy[1][c], fb2_q1n(1, qx), Dy[0][c] * fb2_q1n(0, qx));
@@ -326,8 +325,7 @@ __device__ __forceinline__ bool fb2_hex8_heat(const double* const (&xs)[8], cons
             Aj[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
             Aj[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
             bad |= !(det > 0.0);
-            const double w8 = 0.125 * tw[q];
-            const double dO = det * w8;
+            const double dO = det * w8;     // w8 = w_q / 8; the eight weights of the 2 x 2 x 2 rule are equal (checked on the host)
             // dOmega / det(Jt)^2 (the gradients below are det(Jt) * grad N): reciprocal by two Newton steps on the hardware
             // approximation (2^-20 -> 2^-40 -> below rounding; det is a cell volume, far from the subnormal range)
             double rc;
@@ -413,12 +411,13 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     const int64_t cxy = (int64_t)min(cx, M.nx - 1) + (int64_t)M.nx * min(cy, M.ny - 1);
     const int64_t lay = (int64_t)M.nx * M.ny;
     const int64_t np = A.ncells_pad;
-    // id of the lane's cell in layer z, -1 if there is none or it is not part of this launch
-    auto cell_at = [&](int z) -> int64_t {
-        if (!inside || z >= M.z1) return -1;
-        const int64_t c = M.cellmap ? (int64_t)__ldg(M.cellmap + cxy + lay * z) : cxy + lay * z;
-        return (c >= M.cell_lo && c < M.cell_hi) ? c : -1;
+    // id of the lane's cell in layer z: the raw look-up (-1 = no cell / no such layer) and, separately, the test whether it
+    // belongs to this launch -- the test is applied when the id is USED, layers after the look-up was issued
+    auto raw_cell = [&](int z) -> int64_t {
+        if (!inside || z >= ze) return -1;
+        return M.cellmap ? (int64_t)__ldg(M.cellmap + cxy + lay * z) : cxy + lay * z;
     };
+    auto own = [&](int64_t c) -> int64_t { return (c >= M.cell_lo && c < M.cell_hi) ? c : -1; };
     // dofs of the lane's four corners of node plane zp + 1: from the cell below it (layer zp) if present, else from the
     // cell above it -- a node plane between an assembled and an absent layer still needs its column copies
     auto plane_dofs = [&](int64_t cbelow, int64_t cabove, int (&d)[4]) -> bool {
@@ -457,6 +456,17 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         }
     };
 
+    if (M.cellmap) {   // a tile of a partition-local box may hold halo cells only: nothing to do for this launch
+        bool any = false;
+        for (int z = zb; z < ze; z += 8) {   // eight independent look-ups per round trip
+            int64_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = raw_cell(z + k);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) any |= own(v[k]) >= 0;
+        }
+        if (!__any_sync(0xffffffffu, any)) return;
+    }
     for (int i = lane; i < o_dummy + 32; i += 32) s_acc[i] = 0.0;
     // cp.async groups, in issue order: [coordinates of the first two node planes], then per layer [offset map of the
     // layer's cell] before and [coordinates of node plane z + 2] after the integration; "wait_group 1" = everything but the
@@ -466,7 +476,8 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     asm volatile("cp.async.commit_group;" ::: "memory");
     // cells of the lane in layers z, z + 1, z + 2 (looked up ahead of their use), dofs of node plane z + 1 (prefetched one
     // layer ahead) and whether the lane has any
-    int64_t c0 = cell_at(zb), c1 = zb + 1 < ze ? cell_at(zb + 1) : -1, c2 = zb + 2 < ze ? cell_at(zb + 2) : -1;
+    int64_t c0 = own(raw_cell(zb)), c1 = own(raw_cell(zb + 1)), c2 = own(raw_cell(zb + 2));
+    int64_t r3 = raw_cell(zb + 3);   // raw: its test waits until it becomes c2
     int dnext[4] = {0, 0, 0, 0};
     bool pubnext;
     {   // bottom plane of the first layer (the cells below it belong to another chunk)
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         const int pb = (z - zb) & 1, pt = pb ^ 1;   // window planes holding the node planes z and z + 1
         const bool have = c0 >= 0;
         const int64_t cell = have ? c0 : csafe;
-        const int64_t c3 = z + 3 < ze ? cell_at(z + 3) : -1;
+        const int64_t r4 = raw_cell(z + 4);
         // offset map of this layer's cell and set-up of the top plane: requested now, needed after the integration
 #pragma unroll
         for (int k = 0; k < 4; ++k) fb2_cp_async16(&s_map[k * 32 + lane], M.mapb + ((size_t)k * np + cell) * 16);
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         double Ke[36], fe[8];
         bool bad;
         if constexpr (ANALYTIC && ELEM == FB2_ELEM_HEAT) {
-            bad = fb2_hex8_heat(xs, c_tab + A.o_w, Ke, fe);
+            bad = fb2_hex8_heat(xs, A.p[2], Ke, fe);
         } else {
             double x[8][3];
 #pragma unroll
@@ -575,7 +586,7 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
         if (CHECK && missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
         fb2_march_flush(A, s_acc + (size_t)pb * cap, s_acc + o_f + pb * PS, s_cs + pb * PS, s_len + pb * PS, s_gb + pb * PS, s_dof + pb * PS,
                         s_rowok[pb], lane, z == zb || !M.overwrite, with_f);
-        c0 = c1; c1 = c2; c2 = c3;
+        c0 = c1; c1 = c2; c2 = own(r3); r3 = r4;
     }
     const int pl = (ze - zb) & 1;   // the top plane of the chunk is shared with the chunk above
     fb2_march_flush(A, s_acc + (size_t)pl * cap, s_acc + o_f + pl * PS, s_cs + pl * PS, s_len + pl * PS, s_gb + pl * PS, s_dof + pl * PS,
