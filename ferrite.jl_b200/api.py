@@ -361,7 +361,7 @@ def renumber_(dh, *args):
 
 
 def add_(obj, *args):
-    """add!(dh, name, ip)  or  add!(ch, dbc)"""
+    """add!(dh, name, ip)  or  add!(ch, Dirichlet / AffineConstraint / PeriodicDirichlet)"""
     if isinstance(obj, DofHandler):
         name, ip = args
         assert obj.h is None, "DofHandler already closed"
@@ -370,6 +370,10 @@ def add_(obj, *args):
         obj.field_ips.append(ip)
         return obj
     if isinstance(obj, ConstraintHandler):
+        if isinstance(args[0], AffineConstraint):
+            return obj._add_affine(args[0])
+        if isinstance(args[0], PeriodicDirichlet):
+            return obj._add_periodic(args[0])
         return obj._add(args[0])
     raise TypeError(type(obj))
 
@@ -452,10 +456,15 @@ class B200Matrix:
             _destroy(self, "fb2_pattern_destroy", _chain(self, "dh"))
 
 
-def allocate_matrix(dh, colptr=None, rowval=None):
-    """allocate_matrix(dh) (pattern built on the device); with colptr/rowval: adopt the reference's pattern."""
+def allocate_matrix(dh, colptr=None, rowval=None, ch=None):
+    """allocate_matrix(dh) (pattern built on the device); allocate_matrix(dh, ch=ch): the condensed pattern for a closed
+    ConstraintHandler with affine / periodic constraints; with colptr/rowval: adopt the reference's pattern."""
     h = C.c_void_p()
-    if colptr is None:
+    if isinstance(colptr, ConstraintHandler):
+        ch, colptr = colptr, None
+    if ch is not None:
+        L.call("fb2_pattern_create_condensed", dh.h, ch.h, C.byref(h))
+    elif colptr is None:
         L.call("fb2_pattern_create", dh.h, C.byref(h))
     else:
         cp, rv = _i64(colptr), _i64(rowval)
@@ -939,6 +948,33 @@ class ConstraintHandler:
         self.dbcs.append((ibc.value, dbc, ncomp))
         return self
 
+    def _add_affine(self, ac):
+        m = _i64([d for d, _ in ac.entries])
+        v = _f64([c for _, c in ac.entries])
+        L.call("fb2_ch_add_affine", self.h, int(ac.constrained_dof), len(m), _ptr(m, C.c_int64) if len(m) else None,
+               _ptr(v, C.c_double) if len(m) else None, float(ac.b))
+        return self
+
+    def _add_periodic(self, pd):
+        mset, iset = _i64(pd.face_map[0]), _i64(pd.face_map[1])
+        comps = pd.components or []
+        carr = (C.c_int * max(len(comps), 1))(*comps)
+        L.call("fb2_ch_add_periodic", self.h, self.dh.field_names.index(pd.field), mset.shape[0], _ptr(mset, C.c_int64),
+               iset.shape[0], _ptr(iset, C.c_int64), len(comps), carr)
+        return self
+
+    @property
+    def dofcoefficients(self):
+        """ch.dofcoefficients: per prescribed dof None or [(master, coeff), ...] (1-based masters)"""
+        n, nt = C.c_int64(), C.c_int64()
+        L.call("fb2_ch_info", self.h, C.byref(n))
+        L.call("fb2_ch_affine_export", self.h, C.byref(nt), None, None, None)
+        ptr, m, v = np.empty(n.value + 1, dtype=np.int64), np.empty(nt.value, dtype=np.int64), np.empty(nt.value)
+        L.call("fb2_ch_affine_export", self.h, C.byref(nt), _ptr(ptr, C.c_int64), _ptr(m, C.c_int64) if nt.value else None,
+               _ptr(v, C.c_double) if nt.value else None)
+        return [list(zip(m[ptr[i]:ptr[i + 1]].tolist(), v[ptr[i]:ptr[i + 1]].tolist())) if ptr[i + 1] > ptr[i] else None
+                for i in range(n.value)]
+
     def _close(self):
         L.call("fb2_ch_close", self.h)
         self.closed = True
@@ -964,6 +1000,30 @@ class ConstraintHandler:
     def __del__(self):
         if _destroy is not None:      # module globals are already gone at interpreter shutdown
             _destroy(self, "fb2_ch_destroy", _chain(self, "dh"))
+
+
+class AffineConstraint:
+    """AffineConstraint(constrained_dof, [master => coeff, ...], b): u_dof = sum coeff u_master + b
+    (src/Dofs/ConstraintHandler.jl:114-131); entries = [(master_dof, coeff), ...], dofs 1-based"""
+
+    def __init__(self, constrained_dof, entries, b=0.0):
+        self.constrained_dof, self.entries, self.b = int(constrained_dof), [(int(d), float(c)) for d, c in entries], float(b)
+
+
+def collect_periodic_facets(grid, mset, iset):
+    """collect_periodic_facets(grid, mirror_set, image_set) for facet sets that are translates of each other: the pair of
+    facet sets; the dof pairing (by position) happens in add!(ch, PeriodicDirichlet(...))."""
+    m = getfacetset(grid, mset) if isinstance(mset, str) else mset
+    i = getfacetset(grid, iset) if isinstance(iset, str) else iset
+    return (_i64(m), _i64(i))
+
+
+class PeriodicDirichlet:
+    """PeriodicDirichlet(field, face_map[, components]): the dofs on the mirror facets are constrained to those on the image
+    facets, u_mirror = u_image (src/Dofs/ConstraintHandler.jl:1032-1300)"""
+
+    def __init__(self, field, face_map, components=None):
+        self.field, self.face_map, self.components = field, face_map, list(components) if components else None
 
 
 def update_(ch, t=0.0):

@@ -253,6 +253,21 @@ struct fb2_ch {
     uint8_t* d_isconstrained = nullptr;
     double* d_scratch = nullptr;             // reduction scratch
     bool inhom_dirty = true;
+    // AffineConstraint(dof, [master => coeff, ...], b) (src/Dofs/ConstraintHandler.jl:114-131): u_dof = sum coeff u_master + b.
+    // Host: per constrained dof (0-based) its masters / coefficients / b, in insertion order of the masters; after close!
+    // aff_ptr / aff_dof / aff_coef are aligned with `prescribed` (dofcoefficients of the reference, empty = none).
+    struct Affine { std::vector<int64_t> masters; std::vector<double> coefs; double b = 0.0; };
+    std::map<int64_t, Affine> affine;
+    std::vector<uint8_t> aff_is;             // per prescribed dof: constrained by an AffineConstraint (possibly without masters)
+    std::vector<int32_t> aff_ptr, aff_dof;
+    std::vector<double> aff_coef;
+    bool has_affine = false;                 // some constrained dof has masters
+    int32_t* d_aff_ptr = nullptr;            // [np + 1]
+    int32_t* d_aff_dof = nullptr;
+    double* d_aff_coef = nullptr;
+    int32_t* d_aff_of = nullptr;             // [ndofs] index into prescribed of a dof constrained by an AffineConstraint, else -1
+    int32_t* d_aff_list = nullptr;           // indices into prescribed of the dofs with masters
+    int64_t n_aff = 0;
 };
 
 // element assembly (element_assembly.cu)
@@ -271,6 +286,8 @@ struct fb2_ea {
 
 // ---- device-side helpers implemented in .cu files ------------------------------------------
 int fb2_pattern_build_device(fb2_pattern* p);
+// same builder on an explicit table of (pseudo-)cells: d_cell_dofs is SoA [ndpc][ncells_pad]
+int fb2_pattern_build_device_from(fb2_pattern* p, const int32_t* d_cell_dofs, int64_t ncells, int64_t ncells_pad, int ndpc);
 int fb2_pattern_finalize(fb2_pattern* p);   // diag index, max col len
 int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);

@@ -348,6 +348,7 @@ extern "C" int fb2_ea_rhs(fb2_ea* ea, const double* fes_dev, double* f_dev) {
 extern "C" int fb2_ea_apply_local(fb2_ea* ea, fb2_ch* ch, double* Kes_dev, double* fes_dev, int applyzero) {
     FB2_CHECK(ea && ch && Kes_dev, FB2_ERR_BAD_ARG, "fb2_ea_apply_local: null argument");
     FB2_CHECK(ch->closed, FB2_ERR_BAD_ARG, "fb2_ea_apply_local: the ConstraintHandler is not closed");
+    FB2_CHECK(!ch->has_affine, FB2_ERR_UNSUPPORTED, "fb2_ea_apply_local: affine constraints need the global apply! (`_condense_local!` is not implemented)");
     FB2_CHECK(ch->dh == ea->dh || ch->dh->ndofs == ea->dh->ndofs, FB2_ERR_BAD_ARG,
               "fb2_ea_apply_local: the ConstraintHandler belongs to another DofHandler");
     fb2_grid* g = ea->dh->grid;

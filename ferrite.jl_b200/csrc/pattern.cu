@@ -11,6 +11,8 @@
 // The map built by fb2_map_build replaces the per-cell sort + merge walk of _assemble_inner!
 // (src/assembler.jl:347-457): for every cell and local (i, j) it stores the offset of row dof_i inside
 // column dof_j as a uint16, so the scatter is nzval[colptr[dof_j] + off] += Ke[i, j].
+#include <algorithm>
+#include <climits>
 #include <cub/cub.cuh>
 
 #include "common.h"
@@ -234,14 +236,18 @@ int fb2_pattern_finalize(fb2_pattern* p) {
 }
 
 int fb2_pattern_build_device(fb2_pattern* p) {
+    return fb2_pattern_build_device_from(p, p->dh->d_cell_dofs, p->dh->grid->ncells, p->dh->grid->ncells_pad, p->dh->ndpc);
+}
+
+int fb2_pattern_build_device_from(fb2_pattern* p, const int32_t* d_cell_dofs, int64_t ncells, int64_t ncells_pad, int ndpc) {
     fb2_dh* dh = p->dh;
     fb2_grid* g = dh->grid;
     fb2_ctx* ctx = g->ctx;
     cudaStream_t st = ctx->stream;
     FB2_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = dh->ndofs, ncells = g->ncells;
-    const int ndpc = dh->ndpc;
+    const int64_t n = dh->ndofs;
     const int64_t ninc = ncells * ndpc;
+    FB2_CHECK(ninc < (int64_t)INT_MAX, FB2_ERR_UNSUPPORTED, "pattern build: %lld cell-dof incidences exceed the 32-bit counters of the builder", (long long)ninc);
     p->n = n;
 
     int *d_cnt = nullptr, *d_cursor = nullptr;
@@ -270,7 +276,7 @@ int fb2_pattern_build_device(fb2_pattern* p) {
     P_CUDA(cudaMalloc(&d_d2c, ninc * sizeof(int32_t)));
     P_CUDA(cudaMemsetAsync(d_cnt, 0, (n + 1) * sizeof(int), st));
     P_CUDA(cudaMemsetAsync(d_cursor, 0, (n + 1) * sizeof(int), st));
-    k_count_incidence<<<nblocks(ninc, 256), 256, 0, st>>>(dh->d_cell_dofs, ncells, g->ncells_pad, ndpc, d_cnt);
+    k_count_incidence<<<nblocks(ninc, 256), 256, 0, st>>>(d_cell_dofs, ncells, ncells_pad, ndpc, d_cnt);
     ctx->launches++;
     // dof -> cells offsets (exclusive scan over n+1 entries; the last count is 0)
     P_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_ptr, n + 1, st));
@@ -296,7 +302,7 @@ int fb2_pattern_build_device(fb2_pattern* p) {
         cudaFree(d_maxdeg);
         P_CUDA(e);
     }
-    k_fill_incidence<<<nblocks(ninc, 256), 256, 0, st>>>(dh->d_cell_dofs, ncells, g->ncells_pad, ndpc, d_ptr, d_cursor, d_d2c);
+    k_fill_incidence<<<nblocks(ninc, 256), 256, 0, st>>>(d_cell_dofs, ncells, ncells_pad, ndpc, d_ptr, d_cursor, d_d2c);
     ctx->launches++;
 
     int cap = 32;
@@ -312,7 +318,7 @@ int fb2_pattern_build_device(fb2_pattern* p) {
     P_CUDA(cudaFuncSetAttribute(k_pattern_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)std::min<int64_t>((n + warps - 1) / warps, (int64_t)ctx->sm_count * 32);
     P_CUDA(cudaMemsetAsync(d_colcount, 0, (n + 1) * sizeof(int64_t), st));
-    k_pattern_columns<false><<<grid, warps * 32, smem, st>>>(dh->d_cell_dofs, g->ncells_pad, ndpc, n, d_ptr, d_d2c, cap,
+    k_pattern_columns<false><<<grid, warps * 32, smem, st>>>(d_cell_dofs, ncells_pad, ndpc, n, d_ptr, d_d2c, cap,
                                                              d_colcount, nullptr, nullptr, nullptr);
     ctx->launches++;
     P_CUDA(cudaMalloc(&p->d_colptr, (n + 1) * sizeof(int64_t)));
@@ -324,7 +330,7 @@ int fb2_pattern_build_device(fb2_pattern* p) {
     p->nnz = nnz;
     P_CUDA(cudaMalloc(&p->d_rowval, nnz * sizeof(int32_t)));
     P_CUDA(cudaMalloc(&p->d_diag, n * sizeof(int64_t)));
-    k_pattern_columns<true><<<grid, warps * 32, smem, st>>>(dh->d_cell_dofs, g->ncells_pad, ndpc, n, d_ptr, d_d2c, cap,
+    k_pattern_columns<true><<<grid, warps * 32, smem, st>>>(d_cell_dofs, ncells_pad, ndpc, n, d_ptr, d_d2c, cap,
                                                             nullptr, p->d_colptr, p->d_rowval, p->d_diag);
     ctx->launches++;
     P_CUDA(cudaGetLastError());
@@ -342,6 +348,67 @@ extern "C" int fb2_pattern_create(fb2_dh* dh, fb2_pattern** out) {
     fb2_pattern* p = new fb2_pattern();
     p->dh = dh;
     int rc = fb2_pattern_build_device(p);
+    if (rc != FB2_OK) { fb2_pattern_destroy(p); return rc; }
+    *out = p;
+    return FB2_OK;
+}
+
+// allocate_matrix(dh, ch): the pattern of allocate_matrix(dh) plus the entries `_condense!` writes (src/Dofs/sparsity_pattern.jl:
+// 782-844 `_add_constraint_entries!`).  Those are, per cell, ext x ext with ext = (cell dofs that are not affinely constrained)
+// + (masters of the cell's affinely constrained dofs) -- tests/test_oracle_goldens.py checks this identity against the
+// reference's rule -- so the device builder runs unchanged on a table of pseudo-cells: the cells themselves plus one padded
+// `ext` list for every cell that holds an affinely constrained dof (duplicates inside a list are harmless for a set union).
+extern "C" int fb2_pattern_create_condensed(fb2_dh* dh, fb2_ch* ch, fb2_pattern** out) {
+    FB2_CHECK(dh && ch && out, FB2_ERR_BAD_ARG, "fb2_pattern_create_condensed: null argument");
+    FB2_CHECK(ch->closed && ch->dh == dh, FB2_ERR_BAD_ARG, "fb2_pattern_create_condensed: the ConstraintHandler must be closed and belong to this DofHandler");
+    if (!ch->has_affine) return fb2_pattern_create(dh, out);
+    fb2_grid* g = dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_NEED_DEVICE(ctx);
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int ndpc = dh->ndpc;
+    const int64_t nc = g->ncells;
+    std::vector<std::vector<int32_t>> ext;
+    size_t W = (size_t)ndpc;
+    for (int64_t c = 0; c < nc; ++c) {
+        const int32_t* cd = &dh->cell_dofs[(size_t)c * ndpc];
+        bool any = false;
+        for (int i = 0; i < ndpc && !any; ++i) {
+            const int32_t ip = ch->dofmap[cd[i]];
+            any = ip >= 0 && ch->aff_ptr[ip + 1] > ch->aff_ptr[ip];
+        }
+        if (!any) continue;
+        std::vector<int32_t> e;
+        for (int i = 0; i < ndpc; ++i) {
+            const int32_t ip = ch->dofmap[cd[i]];
+            if (ip >= 0 && ch->aff_is[ip]) {      // an AffineConstraint (even one without masters) is replaced by its masters
+                for (int t = ch->aff_ptr[ip]; t < ch->aff_ptr[ip + 1]; ++t) e.push_back(ch->aff_dof[t]);
+            } else {
+                e.push_back(cd[i]);
+            }
+        }
+        std::sort(e.begin(), e.end());
+        e.erase(std::unique(e.begin(), e.end()), e.end());
+        if (e.empty()) continue;
+        W = std::max(W, e.size());
+        ext.push_back(std::move(e));
+    }
+    const int64_t ntot = nc + (int64_t)ext.size(), npad = (ntot + 31) / 32 * 32;
+    std::vector<int32_t> tab((size_t)W * npad, 0);
+    for (int64_t c = 0; c < nc; ++c) {
+        const int32_t* cd = &dh->cell_dofs[(size_t)c * ndpc];
+        for (size_t i = 0; i < W; ++i) tab[i * npad + c] = cd[i < (size_t)ndpc ? i : 0];
+    }
+    for (size_t k = 0; k < ext.size(); ++k)
+        for (size_t i = 0; i < W; ++i) tab[i * npad + nc + k] = ext[k][i < ext[k].size() ? i : 0];
+    int32_t* d_tab = nullptr;
+    FB2_CUDA(cudaMalloc(&d_tab, tab.size() * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_tab); return fb2_fail(FB2_ERR_CUDA, "fb2_pattern_create_condensed: %s", cudaGetErrorString(e)); }
+    fb2_pattern* p = new fb2_pattern();
+    p->dh = dh;
+    int rc = fb2_pattern_build_device_from(p, d_tab, ntot, npad, (int)W);
+    cudaFree(d_tab);
     if (rc != FB2_OK) { fb2_pattern_destroy(p); return rc; }
     *out = p;
     return FB2_OK;

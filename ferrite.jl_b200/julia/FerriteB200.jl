@@ -167,6 +167,29 @@ function Ferrite.apply!(K::B200Matrix, ch::ConstraintHandler, nzval_dev::Ptr{Flo
     return m[]
 end
 
+# A closed reference ConstraintHandler WITH affine / periodic constraints (ch.dofcoefficients, src/Dofs/ConstraintHandler.jl:160-165):
+# rebuilt natively from its own fields -- Dirichlet dofs as value-only constraints, affine ones with their masters -- so that
+# apply! runs `_condense!` on the device and allocate_matrix(dh, ch) returns the condensed pattern.
+function native_constraints(dh_native::Ptr{Cvoid}, ch::ConstraintHandler)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_ch_create (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) dh_native c
+    for (i, dof) in pairs(ch.prescribed_dofs)
+        coeffs = ch.dofcoefficients[i]
+        masters = coeffs === nothing ? Int64[] : Int64[first(p) for p in coeffs]
+        vals = coeffs === nothing ? Float64[] : Float64[last(p) for p in coeffs]
+        @fb2 fb2_ch_add_affine (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Float64}, Float64) c[] dof length(masters) masters vals ch.inhomogeneities[i]
+    end
+    @fb2 fb2_ch_close (Ptr{Cvoid},) c[]
+    return c[]
+end
+
+# allocate_matrix(dh, ch) -- src/Dofs/sparsity_pattern.jl:628-645 with `_add_constraint_entries!` :782-844
+function condensed_pattern(dh_native::Ptr{Cvoid}, ch_native::Ptr{Cvoid})
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    @fb2 fb2_pattern_create_condensed (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}) dh_native ch_native p
+    return p[]
+end
+
 # get_rhs_data(ch, A) / apply_rhs!(data, f, ch, applyzero) -- src/Dofs/ConstraintHandler.jl:191-240 (one factorisation, many steps)
 mutable struct B200RHSData
     h::Ptr{Cvoid}

@@ -161,6 +161,9 @@ int fb2_dh_destroy(fb2_dh* dh);
 int fb2_pattern_create(fb2_dh* dh, fb2_pattern** out);
 /* arrays-in mode: adopt K.colptr (n+1) / K.rowval (nnz), 1-based */
 int fb2_pattern_from_host(fb2_dh* dh, const int64_t* colptr, const int64_t* rowval, fb2_pattern** out);
+/* allocate_matrix(dh, ch): the condensed pattern for a ConstraintHandler with affine / periodic constraints, i.e. the entries of
+ * allocate_matrix(dh) plus those `_condense!` writes into (src/Dofs/sparsity_pattern.jl:782-844); built on the device */
+int fb2_pattern_create_condensed(fb2_dh* dh, fb2_ch* ch, fb2_pattern** out);
 int fb2_pattern_info(fb2_pattern* p, int64_t* n, int64_t* nnz);
 int fb2_pattern_export(fb2_pattern* p, int64_t* colptr, int64_t* rowval);
 int fb2_pattern_destroy(fb2_pattern* p);
@@ -221,6 +224,22 @@ int fb2_ch_create(fb2_dh* dh, fb2_ch** out);
  * components: 1-based, sorted; ncomponents = 0 means all. Returns the index of the condition in *ibc. */
 int fb2_ch_add_dirichlet(fb2_ch* ch, int field, int kind, int64_t n, const int64_t* entities, int ncomponents,
                          const int* components, int* ibc);
+/* add!(ch, AffineConstraint(dof, [master => coeff, ...], b)): u_dof = sum coeff u_master + b (src/Dofs/ConstraintHandler.jl:114-131,
+ * 383-401).  dof / masters 1-based; n = 0 prescribes the value b.  close! rejects nested constraints ("nested affine constraints
+ * currently not supported", :338-361); restriction of this library: masters must be unconstrained dofs.  fb2_apply then runs
+ * add_inhomogeneities!, `_condense!` (:782-867) and the row / column zeroing on the device; fb2_apply_vector sets
+ * u_dof = sum coeff u_master + b (:686-700).  Use fb2_pattern_create_condensed for the matrix. */
+int fb2_ch_add_affine(fb2_ch* ch, int64_t dof, int n, const int64_t* masters, const double* coefs, double b);
+/* add!(ch, PeriodicDirichlet(field, collect_periodic_facets(grid, mirror_set, image_set), components)) for facet sets that are
+ * translates of each other (src/Dofs/ConstraintHandler.jl:1032-1300): the dofs on the mirror facets are constrained to the dofs
+ * at the matching positions of the image facets (u_mirror = u_image, :1046-1047), as affine constraints; pairs = 2 x n
+ * (cell, local facet), 1-based; ncomponents = 0 means all */
+int fb2_ch_add_periodic(fb2_ch* ch, int field, int64_t n_mirror, const int64_t* mirror_pairs, int64_t n_image,
+                        const int64_t* image_pairs, int ncomponents, const int* components);
+/* ch.dofcoefficients of the closed handler, aligned with ch.prescribed_dofs (src/Dofs/ConstraintHandler.jl:160-165): ptr
+ * (nprescribed + 1 offsets, 0-based), masters (1-based), coefs; *ntotal receives the number of (master, coeff) pairs; any
+ * output pointer may be NULL */
+int fb2_ch_affine_export(fb2_ch* ch, int64_t* ntotal, int64_t* ptr, int64_t* masters, double* coefs);
 /* close!(ch): src/Dofs/ConstraintHandler.jl:303-361 (sorts prescribed dofs, builds isconstrained) */
 int fb2_ch_close(fb2_ch* ch);
 /* arrays-in mode: adopt a closed reference ConstraintHandler (ch.prescribed_dofs sorted, ch.inhomogeneities),
