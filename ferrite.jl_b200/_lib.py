@@ -30,7 +30,7 @@ class MissingPatternEntry(FB2Error):
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_DETJ, ERR_MISSING, ERR_UNSUPPORTED, ERR_NCCL, ERR_INTERNAL = range(9)
 LINE, TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON = 1, 2, 3, 4, 5
-ELEM_HEAT, ELEM_MASS, ELEM_ELASTICITY, ELEM_NEOHOOKE = 1, 2, 3, 4
+ELEM_HEAT, ELEM_MASS, ELEM_ELASTICITY, ELEM_NEOHOOKE, ELEM_ELASTICITY_GENERAL = 1, 2, 3, 4, 5
 SCATTER_ATOMIC, SCATTER_COLORED = 0, 1
 BC_FACET, BC_FACE, BC_EDGE, BC_VERTEX, BC_NODE = 0, 1, 2, 3, 4
 
@@ -49,6 +49,10 @@ class MassParams(C.Structure):
 
 class ElasticityParams(C.Structure):
     _fields_ = [("lam", C.c_double), ("mu", C.c_double), ("b", C.c_double * 3)]
+
+
+class ElasticityGeneralParams(C.Structure):
+    _fields_ = [("C", C.c_double * 81), ("b", C.c_double * 3)]
 
 
 class AsmOpts(C.Structure):

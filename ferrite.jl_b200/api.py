@@ -719,6 +719,22 @@ class ElasticityElement:
         self.params = L.ElasticityParams(float(lam), float(mu), (C.c_double * 3)(*b))
 
 
+class GeneralElasticityElement:
+    """Ke = int grad(dN_i) : C : grad(N_j) for any stiffness tensor C with minor symmetries (orthotropic, anisotropic, ...),
+    fe = int Ni . b -- the element routine as the reference writes it (linear_elasticity.jl:266-281, benchmark/helper.jl:249-262).
+    C: (dim, dim, dim, dim) array = SymmetricTensor{4, dim}.  ElasticityElement is the isotropic fast path."""
+    elem_id = L.ELEM_ELASTICITY_GENERAL
+
+    def __init__(self, C4, b=(0.0, 0.0, 0.0)):
+        C4 = np.asarray(C4, dtype=np.float64)
+        d = C4.shape[0]
+        assert C4.shape == (d,) * 4 and d in (2, 3)
+        full = np.zeros((3, 3, 3, 3))
+        full[:d, :d, :d, :d] = C4
+        b = tuple(b) + (0.0,) * (3 - len(b))
+        self.params = L.ElasticityGeneralParams((C.c_double * 81)(*full.ravel()), (C.c_double * 3)(*b))
+
+
 class NeoHookeElement(ElasticityElement):
     """tangent + residual of the compressible Neo-Hooke model (hyperelasticity.jl:162-176,241-276)"""
     elem_id = L.ELEM_NEOHOOKE

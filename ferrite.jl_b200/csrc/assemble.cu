@@ -611,6 +611,9 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
                 if (handled) return rc;
             }
             return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(a, ctx, A, atomic, ct, nbs, vdim);
+        case FB2_ELEM_ELASTICITY_GENERAL:
+            FB2_CHECK(vdim == cv->rdim, FB2_ERR_BAD_ARG, "the elasticity element needs a vector field with as many components as space dimensions");
+            return dispatch_blocks<FB2_ELEM_ELASTICITY_GENERAL, 1>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_NEOHOOKE:
             FB2_CHECK(A.u != nullptr, FB2_ERR_BAD_ARG, "the Neo-Hooke element needs the current solution u");
             return dispatch_neohooke(a, ctx, A, atomic, ct, nbs, vdim);
@@ -659,6 +662,27 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
             FB2_CHECK(params && params_bytes == sizeof(p), FB2_ERR_BAD_ARG, "elasticity params: expected %zu bytes", sizeof(p));
             memcpy(&p, params, sizeof(p));
             A.p[0] = p.lambda; A.p[1] = p.mu; A.p[2] = p.b[0]; A.p[3] = p.b[1]; A.p[4] = p.b[2];
+            break;
+        }
+        case FB2_ELEM_ELASTICITY_GENERAL: {
+            fb2_elasticity_general_params p;
+            FB2_CHECK(params && params_bytes == sizeof(p), FB2_ERR_BAD_ARG, "general elasticity params: expected %zu bytes", sizeof(p));
+            memcpy(&p, params, sizeof(p));
+            // minor symmetries C_ijkl = C_jikl = C_ijlk (SymmetricTensor{4}); the kernel relies on them
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    for (int k = 0; k < 3; ++k)
+                        for (int l = 0; l < 3; ++l) {
+                            const double c = p.C[((i * 3 + j) * 3 + k) * 3 + l];
+                            const double tol = 1e-12 * (std::fabs(c) + 1e-300);
+                            FB2_CHECK(std::fabs(c - p.C[((j * 3 + i) * 3 + k) * 3 + l]) <= tol && std::fabs(c - p.C[((i * 3 + j) * 3 + l) * 3 + k]) <= tol,
+                                      FB2_ERR_BAD_ARG, "general elasticity: C lacks the minor symmetries at (%d,%d,%d,%d)", i + 1, j + 1, k + 1, l + 1);
+                        }
+            if (!a->d_cmat) FB2_CUDA(cudaMalloc(&a->d_cmat, 81 * sizeof(double)));
+            FB2_CUDA(cudaMemcpyAsync(a->d_cmat, p.C, 81 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            FB2_CUDA(cudaStreamSynchronize(ctx->stream));   // p lives on this stack frame
+            A.cmat = a->d_cmat;
+            A.p[2] = p.b[0]; A.p[3] = p.b[1]; A.p[4] = p.b[2];
             break;
         }
         default: return fb2_fail(FB2_ERR_BAD_ARG, "unknown element id %d", element);

@@ -48,6 +48,7 @@ struct AsmArgs {
     int* errflag;
     double p[6];  // element parameters
     int nq;
+    const double* cmat;    // FB2_ELEM_ELASTICITY_GENERAL: the 81 entries of C on the device
     int zero_pending;      // host only: start_assemble's zero fill of nzval is still owed (a kernel that fuses it clears this)
     const double* tab;     // the c_tab contents in global memory (per-lane indexed reads)
     bool const_ok;         // the tables fit (and are) in c_tab
@@ -938,6 +939,37 @@ __global__ void __launch_bounds__(ELEM == FB2_ELEM_NEOHOOKE ? 192 : 256, 2) k_ce
                         for (int c = 0; c < VDIM; ++c)
 #pragma unroll
                             for (int d = 0; d < VDIM; ++d) acc[t][c][d] = fma(ga[c], gb[d], acc[t][c][d]);
+                    }
+                }
+            } else if (ELEM == FB2_ELEM_ELASTICITY_GENERAL) {
+                // K_ab[c][d] = sum_{j,n} g_a[j] C[c][j][d][n] g_b[n] dOmega for any stiffness tensor (the isotropic special case
+                // is k_cell_syrk); C is read through the L1 (81 doubles shared by all threads)
+#pragma unroll
+                for (int c = 0; c < VDIM; ++c) fa[c] = fma(Na, A.p[2 + c], fa[c]);
+                double h[VDIM][VDIM][DIM];
+#pragma unroll
+                for (int c = 0; c < VDIM; ++c)
+#pragma unroll
+                    for (int d = 0; d < VDIM; ++d)
+#pragma unroll
+                        for (int n = 0; n < DIM; ++n) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int j = 0; j < DIM; ++j) s = fma(ga[j], __ldg(A.cmat + ((c * 3 + j) * 3 + d) * 3 + n), s);
+                            h[c][d][n] = s;
+                        }
+#pragma unroll
+                for (int t = 0; t < TB; ++t) {
+                    if (b0 + t < NBS) {
+#pragma unroll
+                        for (int c = 0; c < VDIM; ++c)
+#pragma unroll
+                            for (int d = 0; d < VDIM; ++d) {
+                                double v = acc[t][c][d];
+#pragma unroll
+                                for (int n = 0; n < DIM; ++n) v = fma(h[c][d][n], gq[(b0 + t) * DIM + n], v);
+                                acc[t][c][d] = v;
+                            }
                     }
                 }
             } else {  // neo-hooke: K_ab[c][d] = sum_{j,n} ga[j] A[c][j][d][n] gb[n]   (dOmega is inside A and P)

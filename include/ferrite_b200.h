@@ -55,7 +55,11 @@ enum {
     FB2_ELEM_HEAT = 1,       /* Ke = int k grad(Ni).grad(Nj), fe = int s Ni; heat_equation.jl:143-164 */
     FB2_ELEM_MASS = 2,       /* Ke = int rho Ni.Nj, fe = 0 */
     FB2_ELEM_ELASTICITY = 3, /* Ke = int eps_i:C:eps_j (isotropic C), fe = int Ni.b; threaded_assembly.jl:105-119 */
-    FB2_ELEM_NEOHOOKE = 4    /* tangent + residual of Psi = mu/2(Ic-3-2lnJ)+lam/2(J-1)^2; hyperelasticity.jl:162-176,241-276 */
+    FB2_ELEM_NEOHOOKE = 4,   /* tangent + residual of Psi = mu/2(Ic-3-2lnJ)+lam/2(J-1)^2; hyperelasticity.jl:162-176,241-276 */
+    FB2_ELEM_ELASTICITY_GENERAL = 5 /* Ke = int grad(dN_i) : C : grad(N_j) for ANY stiffness tensor C with minor symmetries
+                                       (orthotropic, fully anisotropic, ...), fe = int Ni.b: the routine as the reference
+                                       writes it, linear_elasticity.jl:266-281, benchmark/helper.jl:249-262.  The isotropic
+                                       FB2_ELEM_ELASTICITY (tensor-core SYRK) is the fast special case. */
 };
 
 /* scatter strategies (src/assembler.jl:174-231 `atomic` flag; threaded_assembly.jl:232-265 colouring) */
@@ -70,6 +74,8 @@ typedef struct { int order; int vdim; } fb2_field; /* Lagrange{refshape(cell), o
 typedef struct { double k; double source; } fb2_heat_params;
 typedef struct { double rho; } fb2_mass_params;
 typedef struct { double lambda; double mu; double b[3]; } fb2_elasticity_params; /* also for FB2_ELEM_NEOHOOKE */
+/* C[((i*3 + j)*3 + k)*3 + l] = C_ijkl (SymmetricTensor{4,dim}, dim = 2 uses the indices < 2), body force b */
+typedef struct { double C[81]; double b[3]; } fb2_elasticity_general_params;
 
 typedef struct {
     int fillzero;     /* start_assemble(K, f; fillzero) src/assembler.jl:287-291 */

@@ -19,7 +19,7 @@ import numpy as np
 from .interpolations import geometric_interpolation
 
 __all__ = ["CellValues", "reinit", "element_heat", "element_mass", "element_elasticity",
-           "element_neohooke", "lame", "ELEMENTS", "DetJError"]
+           "element_neohooke", "element_elasticity_general", "isotropic_stiffness", "lame", "ELEMENTS", "DetJError"]
 
 
 class DetJError(ArithmeticError):
@@ -145,6 +145,30 @@ def element_elasticity(cv, x, params=None, u=None):
     return Ke, fe
 
 
+def element_elasticity_general(cv, x, params=None, u=None):
+    """Linear elasticity with an arbitrary 4th-order stiffness C (the routine of docs/src/literate-tutorials/
+    linear_elasticity.jl:266-281 / benchmark/helper.jl:249-262: Ke[I,J] += (grad(dN_I) : C : grad^sym(N_J)) dOmega; with the minor
+    symmetries of a SymmetricTensor{4} the symmetric part is implied): Ke[(a,c),(b,d)] = int g_a[j] C[c,j,d,n] g_b[n],
+    fe[(a,c)] = int N_a b_c.   params = {'C': (dim,dim,dim,dim) array, 'b'}"""
+    p = dict(b=None)
+    p.update(params or {})
+    v = cv.vdim
+    C = np.asarray(p["C"], dtype=np.float64)
+    assert C.shape == (v, v, v, v)
+    b = np.zeros(v) if p["b"] is None else np.asarray(p["b"], dtype=np.float64)
+    dNdx, dOm = reinit(cv, x)
+    nb = cv.base.nbase
+    Ke = np.einsum("cqaj,ejdn,cqbn,cq->caebd", dNdx, C, dNdx, dOm).reshape(x.shape[0], nb * v, nb * v)
+    fe = np.einsum("qa,cq,e->cae", cv.N, dOm, b).reshape(x.shape[0], nb * v)
+    return Ke, fe
+
+
+def isotropic_stiffness(lam, mu, dim=3):
+    """C_ijkl = lam d_ij d_kl + mu (d_ik d_jl + d_il d_jk)"""
+    d = np.eye(dim)
+    return lam * np.einsum("ij,kl->ijkl", d, d) + mu * (np.einsum("ik,jl->ijkl", d, d) + np.einsum("il,jk->ijkl", d, d))
+
+
 def _inv3_sym(C):
     det, inv = _det_inv(C)
     return det, inv
@@ -185,5 +209,6 @@ ELEMENTS = {
     "heat": element_heat,
     "mass": element_mass,
     "elasticity": element_elasticity,
+    "elasticity_general": element_elasticity_general,
     "neohooke": element_neohooke,
 }

@@ -1106,3 +1106,44 @@ def test_large_entrywise_against_the_c_port(ctx, kind, nel, vdim):
     assert ok, nrm
     ok, nrm = close(f.cpu().numpy(), of)
     assert ok, nrm
+
+
+@pytest.mark.parametrize("ct,nel,order,qo", [(fb.Hexahedron, (5, 4, 3), 1, 2), (fb.Hexahedron, (3, 2, 2), 2, 3), (fb.Tetrahedron, (3, 3, 2), 2, 4),
+                                              (fb.Quadrilateral, (7, 5), 1, 2), (fb.Triangle, (5, 4), 2, 3)])
+def test_general_stiffness_tensor_elasticity(ctx, ct, nel, order, qo):
+    """FB2_ELEM_ELASTICITY_GENERAL: any SymmetricTensor{4} C (linear_elasticity.jl:266-281, benchmark/helper.jl:249-262).  An
+    orthotropic C against the oracle's einsum restatement, and the isotropic C must reproduce the tensor-core SYRK element."""
+    dim = len(nel)
+    g, og, dh, odh, cv, ocv = build(ct, nel, order, dim, qo)
+    rng = np.random.default_rng(3)
+    # orthotropic: random symmetric positive definite 6x6 (3x3 in 2-D) Voigt matrix with the orthotropic zero pattern
+    voigt = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)] if dim == 3 else [(0, 0), (1, 1), (0, 1)]
+    nv = len(voigt)
+    D = np.zeros((nv, nv))
+    A = rng.random((dim, dim)) + dim * np.eye(dim)
+    D[:dim, :dim] = A @ A.T
+    D[dim:, dim:] = np.diag(rng.random(nv - dim) + 0.5)
+    C4 = np.zeros((dim,) * 4)
+    for I, (i, j) in enumerate(voigt):
+        for J, (k, l) in enumerate(voigt):
+            for (a, b_) in {(i, j), (j, i)}:
+                for (c, d) in {(k, l), (l, k)}:
+                    C4[a, b_, c, d] = D[I, J]
+    bf = (0.3, -1.0, 0.5)[:dim]
+    K, oK = fb.allocate_matrix(dh), O.allocate_matrix(odh)
+    f, of = ctx.zeros(dh.ndofs), np.zeros(odh.ndofs)
+    fb.assemble_(fb.start_assemble(K, f), fb.GeneralElasticityElement(C4, bf), cv)
+    O.assemble_global(odh, ocv, oK, of, "elasticity_general", {"C": C4, "b": bf})
+    ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
+    assert ok, nrm
+    assert close(f.cpu().numpy(), of)[0]
+    # isotropic C == ElasticityElement
+    lam, mu = O.lame(10.0, 0.3)
+    fb.assemble_(fb.start_assemble(K, f), fb.GeneralElasticityElement(O.isotropic_stiffness(lam, mu, dim), bf), cv)
+    nz_general = K.nzval.cpu().numpy().copy()
+    fb.assemble_(fb.start_assemble(K, f), fb.ElasticityElement(lam=lam, mu=mu, b=bf), cv)
+    assert close(nz_general, K.nzval.cpu().numpy(), 1e-12)[0]
+    with pytest.raises(fb.FB2Error, match="minor symmetries"):
+        bad = C4.copy()
+        bad[0, 1, 0, 0] += 1.0
+        fb.assemble_(fb.start_assemble(K, f), fb.GeneralElasticityElement(bad, bf), cv)
