@@ -163,6 +163,7 @@ _PROTOS = {
     "fb2_ch_set_inhomogeneities": [_p, C.c_int64, _dp],
     "fb2_ch_bc_points": [_p, C.c_int, _i64p, _dp],
     "fb2_ch_bc_set_values": [_p, C.c_int, C.c_int64, _dp],
+    "fb2_assemble_mixed_up": [_p, _p, _p, C.c_int, C.c_int, C.c_double, C.c_double, _p, _p, C.POINTER(AsmOpts)],
     "fb2_ch_add_affine": [_p, C.c_int64, C.c_int, _i64p, _dp, C.c_double],
     "fb2_ch_add_periodic": [_p, C.c_int, C.c_int64, _i64p, C.c_int64, _i64p, C.c_int, _ip],
     "fb2_ch_affine_export": [_p, _i64p, _i64p, _i64p, _dp],

@@ -182,7 +182,18 @@ class Grid:
             _destroy(self, "fb2_grid_destroy", (getattr(self, "ctx", None),))
 
 
-def generate_grid(celltype, nel, left=None, right=None, ctx=None):
+def generate_grid(celltype, nel, left=None, right=None, ctx=None, corners=None):
+    """generate_grid(CellType, nel, left, right) or, for quadrilaterals / triangles, generate_grid(CellType, nel, corners) with
+    the four corner points (src/Grid/grid_generators.jl:78-112,383-417: nodes = bilinear map of the unit grid onto the corners)"""
+    if corners is not None:
+        assert celltype in (Quadrilateral, Triangle) and left is None and right is None
+        g = generate_grid(celltype, nel, ctx=ctx)
+        xi = g.nodes                                    # the generated nodes on [-1, 1]^2 are the reference coordinates
+        c = _f64(corners)
+        M = np.stack([(1 - xi[:, 0]) * (1 - xi[:, 1]), (1 + xi[:, 0]) * (1 - xi[:, 1]), (1 + xi[:, 0]) * (1 + xi[:, 1]),
+                      (1 - xi[:, 0]) * (1 + xi[:, 1])], axis=1) / 4.0
+        g.set_coordinates(M @ c)
+        return g
     ctx = ctx or default_context()
     nel = _i64(nel)
     lp = _ptr(_f64(left), C.c_double) if left is not None else None
@@ -740,6 +751,19 @@ class NeoHookeElement(ElasticityElement):
     elem_id = L.ELEM_NEOHOOKE
 
 
+class MultiFieldCellValues:
+    """MultiFieldCellValues(qr, (u = ip_u, p = ip_p)) (src/FEValues/CellValues.jl:229-298): several interpolations evaluated on one
+    quadrature rule and one geometric mapping; the fields are attributes like `cellvalues.u` / `cellvalues.p`."""
+
+    def __init__(self, qr, ip_geo=None, ctx=None, **fields):
+        self.qr, self.names = qr, list(fields)
+        for name, ip in fields.items():
+            setattr(self, name, CellValues(qr, ip, ip_geo, ctx=ctx))
+
+    def __getitem__(self, name):
+        return getattr(self, name)
+
+
 # ---- assembler ------------------------------------------------------------------------------------------------------
 class Assembler:
     """The assembler start_assemble returns.  The native assembler (the cell-local -> nzval map, src/assembler.jl:347-457) is
@@ -792,6 +816,20 @@ def assemble_(assembler, element, cv, u=None):
     L.call("fb2_assemble", h, element.elem_id, C.byref(element.params), C.sizeof(element.params),
            C.c_void_p(u.data_ptr()) if u is not None else None,
            C.c_void_p(assembler.K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
+    return assembler
+
+
+def assemble_mixed_up_(assembler, cellvalues, G, K_bulk, u="u", p="p"):
+    """The cell loop of the incompressible-elasticity tutorial (assemble_up!, incompressible_elasticity.jl:266-293) for a
+    two-field DofHandler: cellvalues = MultiFieldCellValues(qr, u=ip_u, p=ip_p); K_bulk may be inf.  The traction term is added
+    with assemble_facets_ afterwards."""
+    dh = assembler.K.dh
+    h = assembler._handle(None)
+    opts = assembler._opts()
+    f = assembler.f
+    invK = 0.0 if np.isinf(K_bulk) else 1.0 / float(K_bulk)
+    L.call("fb2_assemble_mixed_up", h, cellvalues[u].h, cellvalues[p].h, dh.field_names.index(u), dh.field_names.index(p), float(G),
+           invK, C.c_void_p(assembler.K.nzval.data_ptr()), C.c_void_p(f.data_ptr()) if f is not None else None, C.byref(opts))
     return assembler
 
 

@@ -270,7 +270,10 @@ extern "C" int fb2_assemble_facets(fb2_dh* dh, fb2_fv* fv, fb2_fset* set, int ki
     FB2_CHECK(set->grid == g, FB2_ERR_BAD_ARG, "fb2_assemble_facets: the facet set belongs to another grid");
     FB2_CHECK(fv->celltype == g->celltype && fv->rdim == g->sdim, FB2_ERR_BAD_ARG, "fb2_assemble_facets: FacetValues do not match the grid");
     FB2_CHECK(fv->ngeo == g->nnpc && fv->ngeo <= 8, FB2_ERR_UNSUPPORTED, "fb2_assemble_facets: geometric interpolation must match the cell's nodes");
-    FB2_CHECK(dh->fields.size() == 1 && dh->ndpc == fv->nb * fv->vdim, FB2_ERR_BAD_ARG, "fb2_assemble_facets: FacetValues must cover the (single) field");
+    // the FacetValues integrate the FIRST field of the DofHandler (local dofs 0 .. nb*vdim-1); further fields (e.g. the pressure
+    // of a mixed u-p problem, incompressible_elasticity.jl:295-309) take no part in the surface term
+    FB2_CHECK(!dh->fields.empty() && dh->ips[0].nbase * dh->fields[0].vdim == fv->nb * fv->vdim, FB2_ERR_BAD_ARG,
+              "fb2_assemble_facets: FacetValues must cover the first field of the DofHandler");
     FB2_CHECK(kind == FB2_FACET_FLUX || kind == FB2_FACET_TRACTION || kind == FB2_FACET_NORMAL_TRACTION, FB2_ERR_BAD_ARG,
               "fb2_assemble_facets: unknown kind %d", kind);
     const int need = kind == FB2_FACET_TRACTION ? fv->vdim : 1;

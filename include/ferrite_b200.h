@@ -212,6 +212,15 @@ int fb2_assemble_host_streamed(fb2_assembler* a, int element, const void* params
  * "k_cell_scalar", "k_cell_syrk", "k_cell_blocks", "k_tile_scalar", ...): lets tests and benchmarks state WHICH hand-written
  * kernel produced a number (no reference counterpart) */
 const char* fb2_last_kernel(void);
+/* MultiFieldCellValues(qr, (u = ip_u, p = ip_p)) + the mixed u-p element of the incompressible-elasticity tutorial
+ * (src/FEValues/CellValues.jl:229-298; docs/src/literate-tutorials/incompressible_elasticity.jl:266-311): cv_u / cv_p are the
+ * CellValues of the two fields on ONE quadrature rule and geometric interpolation (checked); `a` = fb2_assembler_create(dh,
+ * pattern, NULL) of the two-field DofHandler; field_u / field_p = field indices in add! order.  Integrates K_uu = int 2G
+ * dev3d(eps_i):dev3d(eps_j), K_pu = -int psi_i div phi_j, K_pp = -int psi_i psi_j / K (inv_bulk = 1/K, 0 for the
+ * incompressible limit) and scatters with assemble! semantics.  f_dev (nullable) is only zero-filled; the traction term
+ * comes from fb2_assemble_facets on the displacement field. */
+int fb2_assemble_mixed_up(fb2_assembler* a, fb2_cv* cv_u, fb2_cv* cv_p, int field_u, int field_p, double shear_G, double inv_bulk,
+                          double* nzval_dev, double* f_dev, const fb2_asm_opts* opts);
 /* create_coloring(grid): number of colours and, optionally, the colour of every cell (0-based colour ids) */
 int fb2_assembler_coloring(fb2_assembler* a, int* ncolors, int32_t* cell_color);
 /* scatter-only entry: assemble!(assembler, dofs, Ke, fe) for a batch of precomputed element matrices

@@ -32,3 +32,4 @@ from .assemble import *       # noqa: F401,F403
 from .constraints import *    # noqa: F401,F403
 from .facets import *         # noqa: F401,F403
 from .affine import *        # noqa: F401,F403
+from .mixed import *         # noqa: F401,F403

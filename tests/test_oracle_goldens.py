@@ -615,3 +615,39 @@ def test_c_port_coloured_scheme_matches_numpy_oracle():
         assert np.abs(K1.nzval - K0.nzval).max() <= 1e-13 * np.abs(K0.nzval).max()
         assert np.abs(f1 - f0).max() <= 1e-13 * max(np.abs(f0).max(), 1e-300)
         assert np.array_equal(K1.nzval, K2.nzval) and np.array_equal(f1, f2)      # threaded_assembly.jl:397-410
+
+
+def _cook_problem(n=50):
+    """the quadratic / linear problem of incompressible_elasticity.jl:386-446 with the oracle: (K, f, ch, dh)"""
+    g = O.cook_grid(n, n)
+    ipu, ipp = O.Lagrange("triangle", 2) ** 2, O.Lagrange("triangle", 1)
+    dh = O.DofHandler(g).add("u", ipu).add("p", ipp).close()
+    qr = O.QuadratureRule("triangle", 3)
+    cvu, cvp = O.CellValues(qr, ipu), O.CellValues(qr, ipp)
+    nu_ = 0.5
+    G = 1.0 / (2 * (1 + nu_))
+    K = O.allocate_matrix(dh)
+    O.assemble_up(dh, cvu, cvp, K, G, 0.0)              # K = Emod nu / (3 (1 - 2 nu)) = Inf: 1 / K = 0
+    f = np.zeros(dh.ndofs)
+    fv = O.FacetValues(O.FacetQuadratureRule("triangle", 3), ipu)
+    nuu = ipu.nbase
+    pairs = g.facetsets["traction"]
+    for facet in np.unique(pairs[:, 1]):
+        cells = pairs[pairs[:, 1] == facet, 0] - 1
+        fe = O.facet_element(fv, g.nodes[g.cells[cells] - 1], int(facet), "traction", (0.0, 1.0 / 16.0))
+        np.add.at(f, dh.cell_dofs[cells][:, :nuu] - 1, fe)
+    ch = O.ConstraintHandler(dh)
+    ch.add(O.Dirichlet("u", g.facetsets["clamped"], lambda x, t: [0.0, 0.0], [1, 2]))
+    ch.close()
+    ch.update(0.0)
+    return g, dh, K, f, ch, (cvu, cvp, G)
+
+
+def test_incompressible_elasticity_tutorial_golden():
+    # docs/src/literate-tutorials/incompressible_elasticity.jl:477: norm(u2) = 919.1284143115702 -- pins the two-field dof
+    # numbering, MultiFieldCellValues (both fields on one rule), the mixed u-p element, the traction facet term and apply!
+    import scipy.sparse.linalg as spla
+    g, dh, K, f, ch, _ = _cook_problem(50)
+    ch.apply(K, f)
+    u = spla.spsolve(K.toscipy().tocsc(), f)
+    assert abs(np.linalg.norm(u) - 919.1284143115702) <= 1e-8 * 919.1284143115702
