@@ -219,9 +219,21 @@ def _user_sets(grid, kind):
     return grid._sets[kind]
 
 
-def _check_setname(sets, name):
-    if name in sets:
-        raise ValueError(f"There already exists a set with the name: {name}")      # src/Grid/utils.jl `_check_setname`
+def _check_setname(sets, name, grid=None):
+    """src/Grid/utils.jl `_check_setname`: user sets AND, for facet sets, the sets generate_grid created ("left", "top", ...)"""
+    taken = name in sets
+    if not taken and grid is not None:
+        n = C.c_int64()
+        taken = L.lib.fb2_grid_facetset(grid.h, name.encode(), C.byref(n), None) == 0
+    if taken:
+        raise ValueError(f"There already exists a set with the name: {name}")
+
+
+def _warn_emptyset(items, name):
+    """src/Grid/utils.jl `_warn_emptyset`"""
+    if len(items) == 0:
+        import warnings
+        warnings.warn(f"no entities added to the set with name {name}")
 
 
 def _passes(f, coords, all_):
@@ -233,7 +245,7 @@ def addfacetset_(grid, name, f_or_pairs, all=True):
     """addfacetset!(grid, name, set_or_predicate; all = true) (src/Grid/utils.jl:42-60,119-134): with a predicate f(x), every
     (cell, local facet) whose vertex coordinates all (any) satisfy f, in lexicographic order; interior facets included."""
     sets = _user_sets(grid, "facet")
-    _check_setname(sets, name)
+    _check_setname(sets, name, grid)
     if callable(f_or_pairs):
         nodes, cells, out = grid.nodes, grid.cells, []
         for ci in range(grid.ncells):
@@ -243,6 +255,7 @@ def addfacetset_(grid, name, f_or_pairs, all=True):
         pairs = np.asarray(out, dtype=np.int64).reshape(-1, 2)
     else:
         pairs = _i64(sorted(set(map(tuple, np.asarray(f_or_pairs, dtype=np.int64).reshape(-1, 2).tolist())))).reshape(-1, 2)
+    _warn_emptyset(pairs, name)
     sets[name] = pairs
     return grid
 

@@ -132,6 +132,7 @@ struct fb2_dh {
     int ndpc = 0;
     std::vector<int32_t> cell_dofs;  // host, ndpc x ncells, 0-based
     int32_t* d_cell_dofs = nullptr;  // SoA [ndpc][ncells_pad], 0-based
+    uint64_t generation = 0;         // bumped by renumber!: caches derived from cell_dofs compare it
     int field_offset(int f) const {
         int o = 0;
         for (int i = 0; i < f; ++i) o += ips[i].nbase * fields[i].vdim;

@@ -22,6 +22,7 @@ struct EaSplit {
     const fb2_ch* ch = nullptr;    // cache key: handle, number of prescribed dofs, checksum of the dof list
     size_t np = 0;
     uint64_t sig = 0;
+    uint64_t dh_generation = 0;    // numbering the split was built for (renumber! invalidates it)
     int64_t ninterior = 0, nboundary = 0;
     int32_t* d_interior = nullptr; // cells without a prescribed dof, ascending
     fb2_grid* sgrid = nullptr;     // boundary cells; d_xyz aliases the parent's coordinates (follows coordinate updates)
@@ -163,13 +164,14 @@ static uint64_t ch_signature(const fb2_ch* ch) {
 static int split_build(fb2_ea* ea, fb2_assembler* a, fb2_ch* ch) {
     EaSplit* sp = ea->split;
     const uint64_t sig = ch_signature(ch);
-    if (sp && sp->ch == ch && sp->np == ch->prescribed.size() && sp->sig == sig && sp->pat == a->pat) return FB2_OK;
+    if (sp && sp->ch == ch && sp->np == ch->prescribed.size() && sp->sig == sig && sp->pat == a->pat && sp->dh_generation == a->dh->generation) return FB2_OK;
     split_free(sp);
     ea->split = nullptr;
     sp = new EaSplit();
     sp->ch = ch;
     sp->np = ch->prescribed.size();
     sp->sig = sig;
+    sp->dh_generation = a->dh->generation;
     sp->pat = a->pat;
     fb2_dh* dh = ea->dh;
     fb2_grid* g = dh->grid;

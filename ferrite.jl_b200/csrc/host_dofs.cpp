@@ -257,6 +257,7 @@ extern "C" int fb2_dh_renumber(fb2_dh* dh, int kind, const int64_t* target_block
     }
     for (size_t i = 0; i < dh->cell_dofs.size(); ++i) dh->cell_dofs[i] = (int32_t)perm[dh->cell_dofs[i]];
     if (dh->d_cell_dofs) { cudaFree(dh->d_cell_dofs); dh->d_cell_dofs = nullptr; }
+    dh->generation++;
     FB2_TRY(upload_cell_dofs(dh));
     if (perm_out) for (int64_t i = 0; i < n; ++i) perm_out[i] = perm[i] + 1;
     return FB2_OK;

@@ -501,19 +501,22 @@ extern "C" int fb2_partition_bind(fb2_part* P, fb2_assembler* a) {
             }
             if (n == 0) continue;
             int32_t *d_r = nullptr, *d_c = nullptr;
-            FB2_CUDA(cudaMalloc(&d_r, n * sizeof(int32_t)));
-            FB2_CUDA(cudaMalloc(&d_c, n * sizeof(int32_t)));
-            FB2_CUDA(cudaMalloc(d_pos, n * sizeof(int64_t)));
-            FB2_CUDA(cudaMemcpyAsync(d_r, rows.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            FB2_CUDA(cudaMemcpyAsync(d_c, cols.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            k_lookup_pos<<<nblk((int64_t)n, 256), 256, 0, st>>>(d_r, d_c, (int64_t)n, a->pat->d_colptr, a->pat->d_rowval, *d_pos);
-            ctx->launches++;
-            // every listed entry must exist in the local pattern
             std::vector<int64_t> h(n);
-            FB2_CUDA(cudaMemcpyAsync(h.data(), *d_pos, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            FB2_CUDA(cudaStreamSynchronize(st));
-            cudaFree(d_r);
+            cudaError_t e = cudaMalloc(&d_r, n * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMalloc(&d_c, n * sizeof(int32_t));
+            if (e == cudaSuccess) e = cudaMalloc(d_pos, n * sizeof(int64_t));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, rows.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, cols.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) {
+                k_lookup_pos<<<nblk((int64_t)n, 256), 256, 0, st>>>(d_r, d_c, (int64_t)n, a->pat->d_colptr, a->pat->d_rowval, *d_pos);
+                ctx->launches++;
+                // every listed entry must exist in the local pattern
+                e = cudaMemcpyAsync(h.data(), *d_pos, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(d_r);     // the temporaries go on every path
             cudaFree(d_c);
+            FB2_CHECK(e == cudaSuccess, e == cudaErrorMemoryAllocation ? FB2_ERR_OOM : FB2_ERR_CUDA, "fb2_partition_bind: %s", cudaGetErrorString(e));
             for (size_t t = 0; t < n; ++t)
                 FB2_CHECK(h[t] >= 0, FB2_ERR_INTERNAL, "fb2_partition_bind: exchange entry missing in the local pattern (peer %d)", p);
         }

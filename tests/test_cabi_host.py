@@ -473,3 +473,18 @@ def test_grid_sets_by_predicate_and_by_list(hctx):
     fb.close_(ch1)
     fb.close_(ch2)
     assert np.array_equal(ch1.prescribed_dofs, ch2.prescribed_dofs) and np.array_equal(ch1.inhomogeneities, ch2.inhomogeneities)
+
+
+def test_addfacetset_name_collision_with_generated_sets_and_empty_warning():
+    """src/Grid/utils.jl `_check_setname` / `_warn_emptyset`: a generated facet set name is taken; an empty set warns"""
+    import warnings
+    hctx = fb.Context(-1)
+    g = fb.generate_grid(fb.Quadrilateral, (3, 2), ctx=hctx)
+    with pytest.raises(ValueError, match="There already exists a set with the name"):
+        fb.addfacetset_(g, "left", lambda x: x[0] < -0.99)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        fb.addfacetset_(g, "nothing", lambda x: x[0] > 5.0)
+    assert any("no entities added" in str(x.message) for x in w)
+    fb.addfacetset_(g, "mine", lambda x: x[0] < -0.99)
+    assert np.array_equal(fb.getfacetset(g, "mine"), fb.getfacetset(g, "left"))
