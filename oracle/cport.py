@@ -13,6 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "cpu_assemble.c")
+_SRC2 = os.path.join(_HERE, "cpu_setup.c")
 _lib = None
 
 
@@ -33,7 +34,7 @@ def build(force=False):
     so = os.path.join(out_dir, "liboracle_cpu.so")
     tag = os.path.join(out_dir, "cpu.tag")
     if (not force and os.path.exists(so) and os.path.exists(tag) and open(tag).read() == _cpu_tag()
-            and os.path.getmtime(so) >= os.path.getmtime(_SRC)):
+            and os.path.getmtime(so) >= max(os.path.getmtime(_SRC), os.path.getmtime(_SRC2))):
         return so
     try:
         os.makedirs(out_dir, exist_ok=True)
@@ -44,7 +45,7 @@ def build(force=False):
         out_dir = tempfile.mkdtemp(prefix="oracle_cpu_")
         so = os.path.join(out_dir, "liboracle_cpu.so")
         tag = os.path.join(out_dir, "cpu.tag")
-    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", so, _SRC, "-lm"]
+    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", so, _SRC, _SRC2, "-lm"]
     subprocess.run(cmd, check=True)
     with open(tag, "w") as fh:
         fh.write(_cpu_tag())
@@ -134,3 +135,38 @@ def assemble(dh, cv, K, f, element="heat", params=None, nthreads=0, u=None, colo
     if bad:
         raise ArithmeticError(f"det(J) is not positive in cell {bad}")
     return K, f
+
+
+class _Plain:
+    """attribute bag standing in for the numpy oracle's Grid / DofHandler / CSC in assemble()"""
+
+
+def hex_q1_problem(nel, vdim=1, left=(-1.0, -1.0, -1.0), right=(1.0, 1.0, 1.0), amplitude=0.2):
+    """(grid, dh, K) of generate_grid(Hexahedron, nel) + perturbation + close! of one Q1 field with `vdim` components +
+    allocate_matrix, set up by the C restatement (oracle/cpu_setup.c): same arrays as the numpy oracle produces, in seconds
+    at 200^3.  The returned objects carry exactly the attributes assemble() reads."""
+    nx, ny, nz = (int(n) for n in nel)
+    L = lib()
+    sizes = [C.c_int64() for _ in range(4)]
+    L.oracle_hex_q1_sizes(C.c_int64(nx), C.c_int64(ny), C.c_int64(nz), C.c_int(vdim), *[C.byref(s) for s in sizes])
+    nn, nc, nd, nnz = (s.value for s in sizes)
+    cells = np.empty((nc, 8), dtype=np.int64)
+    xyz = np.empty((nn, 3), dtype=np.float64)
+    cd = np.empty((nc, 8 * vdim), dtype=np.int64)
+    colptr = np.empty(nd + 1, dtype=np.int64)
+    rowval = np.empty(nnz, dtype=np.int64)
+    lo, hi = np.asarray(left, dtype=np.float64), np.asarray(right, dtype=np.float64)
+
+    def ptr(a, t):
+        return a.ctypes.data_as(C.POINTER(t))
+    L.oracle_hex_q1_setup.restype = C.c_int
+    rc = L.oracle_hex_q1_setup(C.c_int64(nx), C.c_int64(ny), C.c_int64(nz), ptr(lo, C.c_double), ptr(hi, C.c_double), C.c_double(amplitude),
+                               C.c_int(vdim), ptr(cells, C.c_int64), ptr(xyz, C.c_double), ptr(cd, C.c_int64), ptr(colptr, C.c_int64),
+                               ptr(rowval, C.c_int64))
+    if rc != 0:
+        raise RuntimeError(f"oracle_hex_q1_setup failed ({rc})")
+    grid, dh, K = _Plain(), _Plain(), _Plain()
+    grid.cells, grid.nodes, grid.ncells, grid.nnodes, grid.sdim, grid.shape = cells, xyz, nc, nn, 3, "hexahedron"
+    dh.grid, dh.cell_dofs, dh.ndofs, dh.ndofs_per_cell = grid, cd, nd, 8 * vdim
+    K.n, K.nnz, K.colptr, K.rowval, K.nzval = nd, nnz, colptr, rowval, np.zeros(nnz)
+    return grid, dh, K

@@ -5,6 +5,7 @@ Every expected value below is a literal taken from the reference's tests/docs
 trusted for parity checks of the CUDA path because these pass.
 """
 import numpy as np
+import pytest
 import scipy.sparse.linalg as spla
 
 import oracle as O
@@ -651,3 +652,18 @@ def test_incompressible_elasticity_tutorial_golden():
     ch.apply(K, f)
     u = spla.spsolve(K.toscipy().tocsc(), f)
     assert abs(np.linalg.norm(u) - 919.1284143115702) <= 1e-8 * 919.1284143115702
+
+
+@pytest.mark.parametrize("nel,vdim", [((5, 4, 3), 1), ((3, 4, 5), 3), ((1, 1, 1), 1), ((7, 2, 6), 2)])
+def test_c_setup_matches_numpy_oracle(nel, vdim):
+    # oracle/cpu_setup.c (the set-up of the full-size CPU reference arm) against the numpy oracle: nodes, cells, dofs, pattern
+    from oracle import cport
+    g, dh, K = cport.hex_q1_problem(nel, vdim)
+    og = O.perturb_grid(O.generate_grid("hexahedron", nel), nel, (-1.0,) * 3, (1.0,) * 3, 0.2)
+    ip = O.Lagrange("hexahedron", 1)
+    ip = ip ** vdim if vdim > 1 else ip
+    odh = O.DofHandler(og).add("u", ip).close()
+    oK = O.allocate_matrix(odh)
+    assert np.array_equal(g.cells, og.cells) and np.allclose(g.nodes, og.nodes, rtol=0, atol=1e-15)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs) and dh.ndofs == odh.ndofs
+    assert np.array_equal(K.colptr, oK.colptr) and np.array_equal(K.rowval, oK.rowval)
