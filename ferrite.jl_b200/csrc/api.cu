@@ -435,6 +435,7 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     cudaFree(a->d_map);
     cudaFree(a->d_map8);
     cudaFree(a->d_mapb);
+    cudaFree(a->d_mapv);
     cudaFree(a->d_cmat);
     cudaFree(a->d_march_zcols);
     cudaFree(a->d_mapc);

@@ -12,6 +12,7 @@
 
 #include "assemble_kernels.cuh"
 #include "march_kernels.cuh"
+#include "march_vec_kernels.cuh"
 
 const char* g_fb2_last_kernel = "";
 extern "C" const char* fb2_last_kernel(void) { return g_fb2_last_kernel; }
@@ -313,6 +314,95 @@ int march_zero_list(fb2_assembler* a, int lz) {
     return FB2_OK;
 }
 
+// k_march_vec keeps three matrix-column copies per tile NODE: it needs a numbering in which every grid node carries the three
+// dofs of one first-order vector field, the same in every cell around it (true for close!(dh) and any renumber!, false for
+// the broken twin of the element-assembly path).  Checked once per assembler.
+bool marchv_usable(fb2_assembler* a) {
+    if (a->marchv_state == 0) {
+        const fb2_dh* dh = a->dh;
+        const fb2_grid* g = dh->grid;
+        bool ok = dh->ndpc == 24 && g->nnpc == 8 && dh->fields.size() == 1 && dh->fields[0].vdim == 3 &&
+                  (int64_t)dh->cell_dofs.size() == g->ncells * 24;
+        if (ok) {
+            std::vector<int32_t> node_dof((size_t)g->nnodes * 3, -1);
+            for (int64_t c = 0; c < g->ncells && ok; ++c)
+                for (int i = 0; i < 24; ++i) {
+                    int32_t& nd = node_dof[((size_t)g->cells[(size_t)c * 8 + i / 3] - 1) * 3 + i % 3];
+                    const int32_t d = dh->cell_dofs[(size_t)c * 24 + i];
+                    if (nd < 0) nd = d;
+                    else if (nd != d) { ok = false; break; }
+                }
+        }
+        a->marchv_state = ok ? 1 : 2;
+    }
+    return a->marchv_state == 1;
+}
+
+// conditions of k_march_vec that do not depend on the launch: element tables, structured grid, column length, numbering
+bool marchv_static_ok(fb2_assembler* a) {
+    const fb2_grid* g = a->dh->grid;
+    const fb2_cv* cv = a->cv;
+    if (!cv || cv->vdim != 3 || !cv_is_q1hex_gauss2(cv)) return false;
+    const bool gen = g->generated && g->celltype == FB2_HEXAHEDRON;
+    const bool boxed = !gen && g->structured && g->d_sv_cellmap != nullptr;
+    if (!(gen || boxed)) return false;
+    const int64_t* snel = gen ? g->nel : g->sv_nel;
+    if (snel[0] >= (1 << 28) || snel[1] >= (1 << 28) || a->pat->max_col_len >= 255) return false;
+    if (fb2_mvec_smem(fb2_mvec_cap(std::max(a->pat->max_col_len, 1))) > 113 * 1024) return false;
+    return marchv_usable(a);
+}
+
+// Isotropic elasticity on trilinear hexahedra of a structured grid: the marching-tile kernel k_march_vec.  *handled = false
+// when it does not apply (the caller falls back to k_cell_syrk).
+int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bool* handled) {
+    *handled = false;
+    fb2_grid* g = a->dh->grid;
+    const fb2_cv* cv = a->cv;
+    if (!marchv_static_ok(a)) return FB2_OK;
+    const bool gen = g->generated && g->celltype == FB2_HEXAHEDRON;
+    if (A.cells != nullptr || A.ncount <= 0) return FB2_OK;
+    const int64_t* snel = gen ? g->nel : g->sv_nel;
+    const int64_t lay = snel[0] * snel[1];
+    if (gen && !(A.cell_first % lay == 0 && A.ncount % lay == 0)) return FB2_OK;
+    if ((reinterpret_cast<uintptr_t>(A.nzval) & 15) != 0) return FB2_OK;   // the bulk (TMA) flush needs 16-byte aligned matrix storage
+    MarchArgs M;
+    memset(&M, 0, sizeof(M));
+    M.nx = (int)snel[0];
+    M.ny = (int)snel[1];
+    M.z0 = gen ? (int)(A.cell_first / lay) : 0;
+    M.z1 = gen ? M.z0 + (int)(A.ncount / lay) : (int)snel[2];
+    M.cellmap = gen ? nullptr : g->d_sv_cellmap;
+    M.cell_lo = gen ? 0 : A.cell_first;
+    M.cell_hi = gen ? g->ncells : A.cell_first + A.ncount;
+    M.tiles_x = (M.nx + 3) / 4;
+    M.tiles_y = (M.ny + 3) / 4;
+    M.cap = fb2_mvec_cap(std::max(a->pat->max_col_len, 1));
+    M.overwrite = accumulate ? 0 : 1;
+    const size_t smem = fb2_mvec_smem(M.cap);
+    if (smem > 113 * 1024 || M.cap >= 65536) return FB2_OK;
+    FB2_TRY(fb2_map_build_vec(a));
+    M.mapv = a->d_mapv;
+    // chunk length: about eight CTAs per resident slot keep the tail of the launch short; chunks of >= 8 layers keep the
+    // share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
+    const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 2;
+    const int nzl = M.z1 - M.z0;
+    const int64_t want = std::max<int64_t>(1, 8 * resident / tiles);
+    M.lz = (int)std::max<int64_t>(8, (nzl + want - 1) / want);
+    if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
+    const int nchunks = (nzl + M.lz - 1) / M.lz;
+    A.p[5] = 0.125 * cv->w[0];   // the common quadrature weight / 8
+    auto k = a->map_complete ? k_march_vec<false> : k_march_vec<true>;
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    FB2_TRY(pay_zero_fill(a, A));
+    k<<<(unsigned)(tiles * nchunks), 128, smem, ctx->stream>>>(A, M);
+    g_fb2_last_kernel = "k_march_vec";
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    *handled = true;
+    return FB2_OK;
+}
+
 // tile kernel (tiles.cu): whole grid, atomic mode only; falls back to the per-cell kernel when no schedule exists
 template <int DIM, int NGEO, int NB, int NQ, int ELEM>
 int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomic, int variant, int accumulate) {
@@ -524,9 +614,26 @@ int fb2_warplist_build(fb2_assembler* a) {
     return FB2_OK;
 }
 
+int fb2_map_build_vec(fb2_assembler* a) {
+    if (a->d_mapv) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    FB2_CHECK(a->n == 24 && a->pat->max_col_len < 255, FB2_ERR_UNSUPPORTED, "lane-major byte map: 24 dofs per cell and columns shorter than 255 entries");
+    FB2_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total = g->ncells * 160;
+    FB2_CUDA(cudaMalloc(&a->d_mapv, std::max<int64_t>(total, 1) * sizeof(uint32_t)));
+    k_pack_map_vec<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(a->d_map, g->ncells, g->ncells_pad, a->d_mapv);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    FB2_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FB2_OK;
+}
+
 bool fb2_march_applicable(fb2_assembler* a, int element, const fb2_asm_opts* opts) {
     const fb2_cv* cv = a->cv;
     const fb2_grid* g = a->dh->grid;
+    if (cv && element == FB2_ELEM_ELASTICITY)
+        return !(opts && (opts->scatter_mode != FB2_SCATTER_ATOMIC || opts->variant != 0)) && marchv_static_ok(a);
     if (!cv || !(element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS)) return false;
     if (opts && (opts->scatter_mode != FB2_SCATTER_ATOMIC || !(opts->variant == 0 || opts->variant == 31))) return false;
     if (cv->celltype != FB2_HEXAHEDRON || cv->nb != 8 || cv->nq != 8 || cv->vdim != 1 || cv->ngeo != 8) return false;
@@ -605,6 +712,11 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
             if (variant != 1 && try_scalar<FB2_ELEM_MASS>(a, ctx, A, atomic, variant, accumulate, ct, nbs, cv->nq, &rc)) return rc;
             return dispatch_blocks<FB2_ELEM_MASS, 0>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY:
+            if (variant == 0 && atomic) {   // structured trilinear hexahedra: the marching-tile kernel (variant 32 = without it)
+                bool handled = false;
+                rc = try_march_vec(a, ctx, A, accumulate, &handled);
+                if (rc != FB2_OK || handled) return rc;
+            }
             if (variant != 1) {   // variant 1: the DFMA block kernel
                 bool handled = false;
                 rc = dispatch_syrk(a, ctx, A, atomic, ct, nbs, vdim, &handled);

@@ -213,6 +213,9 @@ struct fb2_assembler {
     double* d_cmat = nullptr;      // stiffness tensor of FB2_ELEM_ELASTICITY_GENERAL (81 doubles, lazy)
     uint8_t* d_mapb = nullptr;     // byte-packed copy for the marching-tile kernel: [ceil(n*n/16)][ncells_pad][16] (lazy)
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
+    uint32_t* d_mapv = nullptr;    // lane-major byte map of k_march_vec: [ncells][5][32] words (lazy)
+    int marchv_state = 0;          // k_march_vec: 0 not checked, 1 usable (every grid node carries the three dofs of ONE vector
+                                   // field, the same in all its cells), 2 not usable
     // colouring (lazy)
     int ncolors = 0;
     std::vector<int32_t> cell_color;
@@ -295,6 +298,7 @@ int fb2_map_build(fb2_assembler* a);
 int fb2_map_build_packed(fb2_assembler* a);
 int fb2_map_build_bytes(fb2_assembler* a);
 int fb2_map_build_cellmajor(fb2_assembler* a);
+int fb2_map_build_vec(fb2_assembler* a);
 int fb2_tiles_build(fb2_assembler* a, int TC);
 int fb2_warplist_build(fb2_assembler* a);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,

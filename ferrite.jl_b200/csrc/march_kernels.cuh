@@ -34,6 +34,7 @@ struct MarchArgs {
     int overwrite;         // 1: nzval / f were zero-filled for this launch and nobody else adds to tile-interior columns
                            //    => they are written with plain (bulk) stores; 0: everything is added
     const uint8_t* mapb;   // byte-packed offset map (fb2_map_build_bytes)
+    const uint32_t* mapv;  // lane-major byte map of k_march_vec (fb2_map_build_vec)
     // cell of box position (x, y, z): x + nx (y + ny z) for grids in generate_grid order (cellmap == nullptr), else
     // cellmap[that] (-1 = no cell there).  Only cells with cell_lo <= id < cell_hi are assembled by this launch (the own cells
     // of a partition, a slab of the streamed host path, ...); the others count as absent.

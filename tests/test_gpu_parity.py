@@ -244,6 +244,99 @@ def test_marching_tile_kernel_after_renumbering_and_detj_error(ctx):
         fb.finish_assemble(a)
 
 
+@pytest.mark.parametrize("nel", [(4, 4, 2), (9, 6, 5), (13, 7, 11), (3, 2, 1), (17, 10, 9)])
+@pytest.mark.parametrize("lz", ["1", "3", ""])
+def test_marching_tile_kernel_elasticity(ctx, nel, lz, monkeypatch):
+    """k_march_vec (default for isotropic elasticity on generate_grid Q1 hexahedra, BASELINE.json configs[4]'s element): full /
+    partial tiles, chunk lengths, zero fill (bulk stores for tile-interior columns) and fillzero=false (reduce-adds everywhere),
+    against the oracle and the warp-per-cell kernel."""
+    if lz:
+        monkeypatch.setenv("FB2_MARCH_LZ", lz)
+    else:
+        monkeypatch.delenv("FB2_MARCH_LZ", raising=False)
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, 3, 2, True)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    lam, mu = O.lame(10.0, 0.3)
+    b = (0.1, 0.2, -1.0)
+    O.assemble_global(odh, ocv, oK, of, "elasticity", {"lambda": lam, "mu": mu, "b": b})
+    elem = fb.ElasticityElement(lam=lam, mu=mu, b=b)
+    a = fb.start_assemble(K, f)
+    K.nzval.fill_(55.0)
+    f.fill_(-3.0)
+    fb.assemble_(a, elem, cv)
+    fb.finish_assemble(a)
+    assert fb.last_kernel() == "k_march_vec"
+    nz, fv = K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()
+    ok, nrm = close(nz, oK.nzval)
+    assert ok, f"nzval mismatch: norm-wise {nrm:.3e}"
+    ok, nrm = close(fv, of)
+    assert ok, f"f mismatch: norm-wise {nrm:.3e}"
+    a2 = fb.start_assemble(K, f, fillzero=False)     # accumulate onto the first result
+    fb.assemble_(a2, elem, cv)
+    fb.finish_assemble(a2)
+    assert close(K.nzval.cpu().numpy(), 2 * oK.nzval)[0] and close(f.cpu().numpy(), 2 * of)[0]
+    a3 = fb.start_assemble(K, f)
+    a3.variant = 32                                   # warp-per-cell kernel
+    fb.assemble_(a3, elem, cv)
+    fb.finish_assemble(a3)
+    assert fb.last_kernel() == "k_cell_syrk"
+    assert close(K.nzval.cpu().numpy(), nz)[0] and close(f.cpu().numpy(), fv)[0]
+    a4 = fb.start_assemble(K, None)                   # K only
+    fb.assemble_(a4, elem, cv)
+    fb.finish_assemble(a4)
+    assert fb.last_kernel() == "k_march_vec"
+    assert close(K.nzval.cpu().numpy(), nz, 1e-13)[0]
+
+
+def test_marching_tile_kernel_elasticity_after_renumbering_and_detj_error(ctx):
+    """the window follows the global column layout (three columns per node, wherever the numbering puts them); det(J) <= 0 is
+    reported"""
+    nel = (7, 9, 6)
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, 3, 2, True)
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(dh.ndofs) + 1
+    fb.renumber_(dh, perm)
+    O.renumber(odh, perm)
+    assert np.array_equal(dh.cell_dofs, odh.cell_dofs)
+    K = fb.allocate_matrix(dh)
+    oK = O.allocate_matrix(odh)
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    lam, mu = O.lame(200e9, 0.3)
+    O.assemble_global(odh, ocv, oK, of, "elasticity", {"lambda": lam, "mu": mu, "b": (0.0, 0.0, -1.0)})
+    elem = fb.ElasticityElement(lam=lam, mu=mu, b=(0.0, 0.0, -1.0))
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, elem, cv)
+    fb.finish_assemble(a)
+    assert fb.last_kernel() == "k_march_vec"
+    assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
+    # a component-wise numbering: the three columns of a node are far apart in nzval
+    fb.renumber_(dh, fb.DofOrder.ComponentWise())
+    K2 = fb.allocate_matrix(dh)
+    f2 = ctx.zeros(dh.ndofs)
+    a = fb.start_assemble(K2, f2)
+    fb.assemble_(a, elem, cv)
+    fb.finish_assemble(a)
+    assert fb.last_kernel() == "k_march_vec"
+    nz2, fv2 = K2.nzval.cpu().numpy().copy(), f2.cpu().numpy().copy()
+    a = fb.start_assemble(K2, f2)
+    a.variant = 32
+    fb.assemble_(a, elem, cv)
+    fb.finish_assemble(a)
+    assert fb.last_kernel() == "k_cell_syrk"
+    assert close(nz2, K2.nzval.cpu().numpy())[0] and close(fv2, f2.cpu().numpy())[0]
+    xyz = g.nodes.copy()
+    xyz[:, 0] *= -1.0                                 # mirrored cells: det(J) < 0 everywhere
+    g.set_coordinates(xyz)
+    with pytest.raises(fb.DetJNotPositive):
+        a = fb.start_assemble(K2, f2)
+        fb.assemble_(a, elem, cv)
+        fb.finish_assemble(a)
+
+
 def test_colored_is_bitwise_reproducible_and_coloring_valid(ctx):
     g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (7, 6, 5), 1, 1, 2)
     K = fb.allocate_matrix(dh)
