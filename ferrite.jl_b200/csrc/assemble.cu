@@ -391,7 +391,12 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
     if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
     const int nchunks = (nzl + M.lz - 1) / M.lz;
     A.p[5] = 0.125 * cv->w[0];   // the common quadrature weight / 8
-    auto k = a->map_complete ? k_march_vec<false> : k_march_vec<true>;
+    if (const char* e = getenv("FB2_MVEC_DBG")) M.dbg = atoi(e);
+    // FB2_MVEC_FLUSH=thread: flush with coalesced per-thread stores / REDs instead of the TMA engine (A/B measurement)
+    const char* ef = getenv("FB2_MVEC_FLUSH");
+    const bool tmaf = !(ef && strcmp(ef, "thread") == 0);
+    auto k = tmaf ? (a->map_complete ? k_march_vec<false, true> : k_march_vec<true, true>)
+                  : (a->map_complete ? k_march_vec<false, false> : k_march_vec<true, false>);
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     FB2_TRY(pay_zero_fill(a, A));

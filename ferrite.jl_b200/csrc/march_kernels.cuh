@@ -35,6 +35,7 @@ struct MarchArgs {
                            //    => they are written with plain (bulk) stores; 0: everything is added
     const uint8_t* mapb;   // byte-packed offset map (fb2_map_build_bytes)
     const uint32_t* mapv;  // lane-major byte map of k_march_vec (fb2_map_build_vec)
+    int dbg;               // measurement only (FB2_MVEC_DBG, results are wrong): 1 every piece as a bulk store, 2 no flush, 3 every piece as a reduce-add
     // cell of box position (x, y, z): x + nx (y + ny z) for grids in generate_grid order (cellmap == nullptr), else
     // cellmap[that] (-1 = no cell there).  Only cells with cell_lo <= id < cell_hi are assembled by this launch (the own cells
     // of a partition, a slab of the streamed host path, ...); the others count as absent.

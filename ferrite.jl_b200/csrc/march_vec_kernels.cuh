@@ -106,21 +106,100 @@ __device__ __forceinline__ void fb2_mvec_scan(const int64_t* s_gb, const uint8_t
         const unsigned m = __ballot_sync(full, len[s] > 0 && k + 1 < MV_NC && nb == gb[s] + len[s]);
         if (lane == 0) s_adj[s] = m;
     }
+    if (lane == 0) s_adj[3] = 0u;
 }
 
-// Write a finished node plane out (after fence.proxy.async + CTA barrier).  Thread p < 15 takes piece p: tile row b = p / 3,
-// part 0 / 2 = the columns of the face nodes a = 0 / 4 (reduce-add: shared with the neighbouring tiles), part 1 = the nine
-// columns of the interior nodes a = 1..3 (bulk store unless `redall` or the row is a tile face).  A piece whose columns are
-// not contiguous in nzval (irregular numbering) is written column by column.
-__device__ __forceinline__ void fb2_mvec_flush(const AsmArgs& A, const double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
-                                               const int64_t* s_gb, const int* s_dof, const unsigned* s_adj, int tid, bool redall, bool with_f) {
-    if (tid < 15) {
-        const int b = tid / 3, part = tid - 3 * b;
+// One run of a finished plane (adjacent in nzval and in the window) -> global memory, by one warp: plain stores (STORE) or
+// REDs, two entries per lane and instruction after peeling a leading / trailing entry where the run starts / ends on an odd
+// entry (window copy and global column start at the same parity).  The window is cleared on the way.
+template <bool STORE>
+__device__ __forceinline__ void fb2_mvec_run(double* __restrict__ nzval, double* acc, int c0, int total, int64_t g0, int lane) {
+    if (total <= 0) return;
+    double* g = nzval + g0;
+    double* a = acc + c0;
+    int i0 = 0;
+    if (g0 & 1) {
+        if (lane == 0) {
+            const double v = a[0];
+            a[0] = 0.0;
+            if (STORE) g[0] = v; else atomicAdd(g, v);
+        }
+        i0 = 1;
+    }
+    const int body = (total - i0) & ~1;
+    for (int i = i0 + 2 * lane; i < i0 + body; i += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(a + i);
+        *reinterpret_cast<double2*>(a + i) = make_double2(0.0, 0.0);
+        if (STORE) *reinterpret_cast<double2*>(g + i) = v;
+        else { atomicAdd(g + i, v.x); atomicAdd(g + i + 1, v.y); }
+    }
+    if (((total - i0) & 1) && lane == 0) {
+        const double v = a[i0 + body];
+        a[i0 + body] = 0.0;
+        if (STORE) g[i0 + body] = v; else atomicAdd(g + i0 + body, v);
+    }
+}
+
+// Write a finished node plane out and clear its window (after the CTA barrier behind the last update).  The unit of work is
+// a tile node (its three columns: one run of nzval in the usual numberings, else column by column): warp w takes the units
+// w, w + 4, ...; units 0..8 are the tile-interior nodes -- their columns have received every contribution they will ever get
+// and are written with plain coalesced stores unless `redall` --, units 9..24 the nodes on the tile faces, which are shared
+// with the neighbouring tiles and go out as coalesced REDs (fire and forget: unlike a TMA reduce they do not hold the window
+// until the L2 has taken them, 2300 cycles per layer in profiles/r02_prof_c5_march_a.txt).
+__device__ __forceinline__ void fb2_mvec_flush(const AsmArgs& A, double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
+                                               const int64_t* s_gb, int* s_dof, const unsigned* s_adj, int tid, bool redall, bool with_f) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int u = warp; u < MV_PN; u += 4) {
+        int n;
+        if (u < 9) n = 5 * (1 + u / 3) + 1 + u % 3;
+        else {
+            const int j = u - 9;
+            n = j < 5 ? j : (j < 10 ? 15 + j : (j < 13 ? 5 * (j - 9) : 5 * (j - 12) + 4));
+        }
+        const bool store = !redall && u < 9;
+        const int k0 = 3 * n;
+        const unsigned bits = (unsigned)((((unsigned long long)s_adj[k0 >> 5] | ((unsigned long long)s_adj[(k0 >> 5) + 1] << 32)) >> (k0 & 31)) & 3ull);
+        if (bits == 3u) {
+            const int c0 = s_cs[k0], total = (int)s_cs[k0 + 2] + (int)s_len[k0 + 2] - c0;
+            if (store) fb2_mvec_run<true>(A.nzval, acc, c0, total, s_gb[k0], lane);
+            else fb2_mvec_run<false>(A.nzval, acc, c0, total, s_gb[k0], lane);
+        } else {
+            for (int k = k0; k < k0 + 3; ++k) {
+                if (store) fb2_mvec_run<true>(A.nzval, acc, s_cs[k], s_len[k], s_gb[k], lane);
+                else fb2_mvec_run<false>(A.nzval, acc, s_cs[k], s_len[k], s_gb[k], lane);
+            }
+        }
+    }
+    if (tid < MV_NC) {
+        const int d = s_dof[tid];
+        s_dof[tid] = -1;   // the slot is set up for another node plane two layers from now
+        if (with_f && d >= 0) {
+            const double v = sf[tid];
+            sf[tid] = 0.0;
+            const int n = tid / 3, a = n % 5, b = n / 5;
+            if (!redall && a >= 1 && a <= 3 && b >= 1 && b <= 3) A.f[d] = v;
+            else if (v != 0.0) atomicAdd(A.f + d, v);
+        }
+    }
+}
+
+// The same through the TMA engine (template flag TMAF of the kernel; after fence.proxy.async + CTA barrier): one thread
+// takes piece p < 15: tile row b = p / 3, part 0 / 2 = the columns of the face nodes a = 0 / 4 (bulk reduce-add), part 1 = the nine
+// columns of the interior nodes a = 1..3 (bulk store unless `redall` or the row is a tile face).  A piece whose columns are not
+// contiguous in nzval is written column by column.  The window is NOT cleared: the bulk operations read it asynchronously,
+// fb2_bulk_wait_read + a zero fill precede its next use.
+__device__ __forceinline__ void fb2_mvec_flush_tma(const AsmArgs& A, const double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
+                                                   const int64_t* s_gb, int* s_dof, const unsigned* s_adj, int tid, bool redall, bool with_f, int dbg) {
+    // piece p = 4 * lane + warp on lanes 0..3 of every warp: a bulk operation takes its operands from uniform registers, so a
+    // warp issues the pieces of its lanes one after the other -- four per warp instead of fifteen on one warp
+    const int p = 4 * (tid & 31) + (tid >> 5);
+    if ((tid & 31) < 4 && p < 15 && dbg != 2) {
+        const int b = p / 3, part = p - 3 * b;
         const int n0 = (5 * b + (part == 0 ? 0 : (part == 1 ? 1 : 4))) * 3, cnt = part == 1 ? 9 : 3;
-        const bool store = !redall && part == 1 && b >= 1 && b <= 3;
+        const bool store = dbg == 1 || (dbg != 3 && !redall && part == 1 && b >= 1 && b <= 3);
         const int wd = n0 >> 5, sh = n0 & 31;
-        const unsigned long long bits = ((unsigned long long)s_adj[wd] | ((unsigned long long)(wd < 2 ? s_adj[wd + 1] : 0u) << 32)) >> sh;
         const unsigned long long need = (1ull << (cnt - 1)) - 1ull;
+        const unsigned long long bits = ((unsigned long long)s_adj[wd] | ((unsigned long long)s_adj[wd + 1] << 32)) >> sh;
         if ((bits & need) == need) {
             if (store) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, n0, cnt);
             else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, n0, cnt);
@@ -132,12 +211,14 @@ __device__ __forceinline__ void fb2_mvec_flush(const AsmArgs& A, const double* a
         }
         fb2_bulk_commit();
     }
-    if (with_f && tid < MV_NC) {
-        const int d = s_dof[tid];
-        if (d >= 0) {
-            const double v = sf[tid];
-            sf[tid] = 0.0;
-            const int n = tid / 3, a = n % 5, b = n / 5;
+    const int col = 127 - tid;   // the per-column chores sit on the upper warps
+    if (col < MV_NC) {
+        const int d = s_dof[col];
+        s_dof[col] = -1;   // the slot is set up for another node plane two layers from now
+        if (with_f && d >= 0) {
+            const double v = sf[col];
+            sf[col] = 0.0;
+            const int n = col / 3, a = n % 5, b = n / 5;
             if (!redall && a >= 1 && a <= 3 && b >= 1 && b <= 3) A.f[d] = v;
             else if (v != 0.0) atomicAdd(A.f + d, v);
         }
@@ -146,7 +227,7 @@ __device__ __forceinline__ void fb2_mvec_flush(const AsmArgs& A, const double* a
 
 // A.p: [0] lambda, [1] mu, [2..4] body force, [5] w / 8 (the common weight of the 2 x 2 x 2 Gauss rule; the host checks that
 // the CellValues holds the tables of QuadratureRule{RefHexahedron}(2) + Lagrange{RefHexahedron,1}).
-template <bool CHECK>
+template <bool CHECK, bool TMAF>
 __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const MarchArgs M) {
     constexpr int CS = MV_CS;
     constexpr double NA = fb2_q1n(0, 0), NB = fb2_q1n(1, 0);   // 1-D shape function of the near / far node of a Gauss point
@@ -259,16 +340,16 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
     int64_t cbeg = 0, cend = 0;
     auto step_colptr = [&](int slot) {
         cbeg = 0; cend = 0;
-        if (tid < MV_NC) {
-            const int d = s_dof[slot * CS + tid];
+        if (127 - tid < MV_NC) {
+            const int d = s_dof[slot * CS + 127 - tid];
             if (d >= 0) { cbeg = __ldg(A.colptr + d); cend = __ldg(A.colptr + d + 1); }
         }
     };
     auto step_store = [&](int slot) {
         asm volatile("" : "+l"(cbeg), "+l"(cend));   // keeps the consumers of the two loads behind the integration
-        if (tid < MV_NC) {
-            s_gb[slot * CS + tid] = cbeg;
-            s_len[slot * CS + tid] = (uint8_t)(cend - cbeg);
+        if (127 - tid < MV_NC) {
+            s_gb[slot * CS + 127 - tid] = cbeg;
+            s_len[slot * CS + 127 - tid] = (uint8_t)(cend - cbeg);
         }
     };
     {   // node planes zb (cells above only: the layer below belongs to another chunk) and zb + 1
@@ -293,6 +374,14 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
+    unsigned mpn[5] = {0u, 0u, 0u, 0u, 0u};   // offset words of the cell of the next sub-step
+    {
+        const int64_t celln = __shfl_sync(full, c0, (2 * warp) & 3);
+        if (celln >= 0) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) mpn[k] = __ldg(M.mapv + ((size_t)celln * 5 + k) * 32 + lane);
+        }
+    }
     for (int z = zb; z < ze; ++z) {
         const int rel = z - zb;
         const int pb = rel & 1, pt = pb ^ 1;                                   // window planes of node planes z and z + 1
@@ -309,14 +398,22 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
             const bool have = cell >= 0;
             // set-up of node plane z + 2, the part of this interval that has to precede the integration
             if (ss == 1) step_colptr(s2);
-            if (ss == 3 && warp == 0) fb2_mvec_scan(s_gb + s2 * CS, s_len + s2 * CS, s_cs + s2 * CS, s_adj + s2 * 4, lane);
-            unsigned mp[5] = {0u, 0u, 0u, 0u, 0u};
+            if (ss == 3 && warp == 1) fb2_mvec_scan(s_gb + s2 * CS, s_len + s2 * CS, s_cs + s2 * CS, s_adj + s2 * 4, lane);
+            // offset words of this sub-step's cell (requested one sub-step ago) and request of the next cell's
+            unsigned mp[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) mp[k] = mpn[k];
+            {
+                const int64_t celln = ss < 3 ? __shfl_sync(full, c0, (ss + 1 + 2 * warp) & 3) : __shfl_sync(full, c1, (2 * warp) & 3);
+                if (celln >= 0) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) mpn[k] = __ldg(M.mapv + ((size_t)celln * 5 + k) * 32 + lane);
+                }
+            }
             double acc[3][3][2];
             double fpart = 0.0;
             bool bad = false;
             if (have) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) mp[k] = __ldg(M.mapv + ((size_t)cell * 5 + k) * 32 + lane);
                 // ---- geometry: X[sx][sy][sz][c] -------------------------------------------------------------------------------------
                 const int tn0 = y * 5 + warp;
                 double X[2][2][2][3];
@@ -388,26 +485,23 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
                         fb2_dmma884(acc[c][d], gw[0][c], g[0][d]);
                         fb2_dmma884(acc[c][d], gw[1][c], g[1][d]);
                     }
-                // the offset words were requested before the integration; their consumers stay behind it
-                asm volatile("" : "+r"(mp[0]), "+r"(mp[1]), "+r"(mp[2]), "+r"(mp[3]), "+r"(mp[4]));
                 bad = __any_sync(full, bad);
                 if (bad && lane == 0) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
             }
             // set-up of node plane z + 2, the parts that may follow the integration
             if (ss == 2) step_store(s2);
             if (ss == 0) {
-                // the window plane that becomes node plane z + 1 was flushed one layer ago: wait until the bulk engine has read
-                // it, then clear it; meanwhile the dof table of node plane z + 2 is reset and filled
-                if (tid < 15) fb2_bulk_wait_read();
-                if (tid < CS) s_dof[s2 * CS + tid] = -1;
-                __syncthreads();
-                {
+                // the flush of node plane z - 1 (which cleared the window plane that now becomes node plane z + 1 and reset the
+                // dof table of its set-up slot) is behind every warp; the dofs of node plane z + 2 go into that slot
+                if (TMAF) {   // the bulk engine has read the window plane: clear it
+                    if (lane < 4) fb2_bulk_wait_read();
+                    __syncthreads();
                     double2* zp = reinterpret_cast<double2*>(s_acc + (size_t)pt * cap);
                     for (int i = tid; i < cap / 2; i += 128) zp[i] = make_double2(0.0, 0.0);
                 }
+                __syncthreads();
                 publish(s_dof + s2 * CS, pubnext, dnext);
                 pubnext = plane_dofs(c2, c3, dnext);   // node plane z + 3
-                __syncthreads();
             }
             // ---- Ke = lambda H + mu H^T + mu tr(H) I into the window ---------------------------------------------------------------
             if (have && !bad) {
@@ -461,19 +555,27 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
                 }
             }
             if (ss == 3) {
-                fb2_fence_async_smem();   // the read-modify-writes (generic proxy) -> visible to the bulk engine
+                if (TMAF) fb2_fence_async_smem();   // the read-modify-writes (generic proxy) -> visible to the bulk engine
                 asm volatile("cp.async.wait_group 0;" ::: "memory");   // coordinates of node plane z + 2
             }
             __syncthreads();
         }
-        fb2_mvec_flush(A, s_acc + (size_t)pb * cap, s_f + pb * CS, s_cs + sb * CS, s_len + sb * CS, s_gb + sb * CS, s_dof + sb * CS, s_adj + sb * 4,
-                       tid, z == zb || !M.overwrite, with_f);
+        if (TMAF)
+            fb2_mvec_flush_tma(A, s_acc + (size_t)pb * cap, s_f + pb * CS, s_cs + sb * CS, s_len + sb * CS, s_gb + sb * CS, s_dof + sb * CS, s_adj + sb * 4,
+                               tid, z == zb || !M.overwrite, with_f, M.dbg);
+        else
+            fb2_mvec_flush(A, s_acc + (size_t)pb * cap, s_f + pb * CS, s_cs + sb * CS, s_len + sb * CS, s_gb + sb * CS, s_dof + sb * CS, s_adj + sb * 4,
+                           tid, z == zb || !M.overwrite, with_f);
         c0 = c1; c1 = c2; c2 = c3; c3 = own(r4); r4 = r5;
     }
     {   // the top plane of the chunk is shared with the chunk above
         const int rel = ze - zb, pl = rel & 1, sl = rel % 3;
-        fb2_mvec_flush(A, s_acc + (size_t)pl * cap, s_f + pl * CS, s_cs + sl * CS, s_len + sl * CS, s_gb + sl * CS, s_dof + sl * CS, s_adj + sl * 4, tid,
-                       true, with_f);
+        if (TMAF)
+            fb2_mvec_flush_tma(A, s_acc + (size_t)pl * cap, s_f + pl * CS, s_cs + sl * CS, s_len + sl * CS, s_gb + sl * CS, s_dof + sl * CS, s_adj + sl * 4,
+                               tid, true, with_f, M.dbg);
+        else
+            fb2_mvec_flush(A, s_acc + (size_t)pl * cap, s_f + pl * CS, s_cs + sl * CS, s_len + sl * CS, s_gb + sl * CS, s_dof + sl * CS, s_adj + sl * 4, tid,
+                           true, with_f);
     }
-    if (tid < 15) fb2_bulk_wait_read();   // shared memory must outlive the bulk reads
+    if (TMAF && lane < 4) fb2_bulk_wait_read();   // shared memory must outlive the bulk reads
 }
