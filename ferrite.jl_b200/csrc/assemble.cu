@@ -382,11 +382,11 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
     if (smem > 113 * 1024 || M.cap >= 65536) return FB2_OK;
     FB2_TRY(fb2_map_build_vec(a));
     M.mapv = a->d_mapv;
-    // chunk length: about eight CTAs per resident slot keep the tail of the launch short; chunks of >= 8 layers keep the
+    // chunk length: about two dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 8 layers keep the
     // share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
     const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 2;
     const int nzl = M.z1 - M.z0;
-    const int64_t want = std::max<int64_t>(1, 8 * resident / tiles);
+    const int64_t want = std::max<int64_t>(1, (24 * resident + tiles - 1) / tiles);
     M.lz = (int)std::max<int64_t>(8, (nzl + want - 1) / want);
     if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
     const int nchunks = (nzl + M.lz - 1) / M.lz;

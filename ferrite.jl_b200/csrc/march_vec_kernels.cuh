@@ -32,7 +32,14 @@ constexpr int MV_PN = 25;   // nodes of a tile plane (5 x 5)
 constexpr int MV_NC = 75;   // matrix columns of a tile plane
 constexpr int MV_CS = 76;   // padded
 
-__host__ __device__ inline int fb2_mvec_cap(int max_col_len) { return (MV_NC * max_col_len + MV_CS + 1) / 2 * 2; }
+// Doubles per window plane: the 75 column copies, up to 76 parity pads and up to 4 x 14 row pads (fb2_mvec_scan), rounded up
+// to 12 mod 16.  The residues matter: in the window updates of the kernel the 16 lanes of a half-warp hit the rows of four
+// nodes (offsets {0, 3, 9, 12} + const inside a column) in the columns of four nodes that lie 0 / R +- 243 / P / P + R +- 243
+// doubles apart (R = distance of two tile rows, P = of the two planes).  The four groups of four 8-byte banks overlap at
+// most pairwise iff 7 + R and 5 + P (mod 16) are in {1, 2, 5, 8, 11, 14, 15}; the dense layout (R = 1215, P = 6152) gave
+// three- to four-fold conflicts on every access (profiles/r02_prof_c5_march_d.txt: 85 conflicts per cell; grids with an even
+// number of nodes per row ran 25 % slower than those with an odd one).
+__host__ __device__ inline int fb2_mvec_cap(int max_col_len) { return (MV_NC * max_col_len + MV_CS + 56 + 3) / 16 * 16 + 12; }
 // doubles: [2][cap] matrix window | [2][CS] load vector | [3][PN][4] node coordinates; int64 [3][CS] colptr[dof]; int [3][CS] dof;
 // unsigned [3][4] adjacency bits; uint16 [3][CS] start of the column copy; uint8 [3][CS] its length.  106 KB for 81-entry
 // columns: two CTAs per SM.
@@ -107,6 +114,33 @@ __device__ __forceinline__ void fb2_mvec_scan(const int64_t* s_gb, const uint8_t
         if (lane == 0) s_adj[s] = m;
     }
     if (lane == 0) s_adj[3] = 0u;
+    __syncwarp();
+    // row pads (see fb2_mvec_cap): shift tile row b >= 1 by an even amount such that its distance to row b - 1 becomes
+    // 1, 7, 11 (odd distances) or 4, 8, 10, 14 (even ones) mod 16; every lane derives the four shifts
+    int start[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) start[b] = s_cs[15 * b];
+    int shift[5];
+    shift[0] = 0;
+#pragma unroll
+    for (int b = 1; b < 5; ++b) {
+        const int d = (start[b] - start[b - 1]) & 15;
+        // smallest even x with (d + x) mod 16 in the allowed set of d's parity
+        int x;
+        if (d & 1) x = d <= 1 ? 1 - d : (d <= 7 ? 7 - d : (d <= 11 ? 11 - d : 17 - d));
+        else x = d <= 4 ? 4 - d : (d <= 8 ? 8 - d : (d <= 10 ? 10 - d : (d <= 14 ? 14 - d : 20 - d)));
+        shift[b] = shift[b - 1] + x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const int k = lane + 32 * s;
+        if (k < MV_NC) {
+            const int b = k / 15;
+            const int sh = b == 0 ? 0 : (b == 1 ? shift[1] : (b == 2 ? shift[2] : (b == 3 ? shift[3] : shift[4])));
+            s_cs[k] = (uint16_t)(s_cs[k] + sh);
+        }
+    }
 }
 
 // One run of a finished plane (adjacent in nzval and in the window) -> global memory, by one warp: plain stores (STORE) or
@@ -485,6 +519,10 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
                         fb2_dmma884(acc[c][d], gw[0][c], g[0][d]);
                         fb2_dmma884(acc[c][d], gw[1][c], g[1][d]);
                     }
+                if (with_f) {   // fe[(a, c)] = b_c sum_q N_a dOmega: the four lanes of a row hold the four pairs of points
+                    fpart += __shfl_xor_sync(full, fpart, 1);
+                    fpart += __shfl_xor_sync(full, fpart, 2);
+                }
                 bad = __any_sync(full, bad);
                 if (bad && lane == 0) fb2_flag_error(A.errflag, FB2_ERR_DETJ_NOT_POSITIVE, cell);
             }
@@ -544,15 +582,7 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
                 for (int tt = 0; tt < 18; ++tt)
                     if (!CHECK || sl[tt] >= 0) s_acc[sl[tt]] = t[tt] + v[tt];
                 if (CHECK && missing) fb2_flag_error(A.errflag, FB2_ERR_MISSING_PATTERN_ENTRY, cell);
-                if (with_f) {   // fe[(a, c)] = b_c sum_q N_a dOmega: the four lanes of a row hold the four pairs of points
-                    double fs = fpart;
-                    fs += __shfl_xor_sync(full, fs, 1);
-                    fs += __shfl_xor_sync(full, fs, 2);
-                    if (kr < 3) {
-                        const int tna = tn0 + msy * 5 + msx;
-                        s_f[(msz ? pt : pb) * CS + tna * 3 + kr] += bforce * fs;
-                    }
-                }
+                if (with_f && kr < 3) s_f[(msz ? pt : pb) * CS + (tn0 + msy * 5 + msx) * 3 + kr] += bforce * fpart;
             }
             if (ss == 3) {
                 if (TMAF) fb2_fence_async_smem();   // the read-modify-writes (generic proxy) -> visible to the bulk engine

@@ -8,10 +8,12 @@ from bench import block_dims
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 rank = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 ctx = fb.default_context(0)
-nel = (200, 200, 200)
-ip = fb.Lagrange(fb.RefHexahedron, 1)
+kind = os.environ.get("PL_KIND", "heat")                       # heat | elasticity
+n1 = int(os.environ.get("PL_NEL", "200"))                      # cells per rank and direction
+nel = (n1, n1, n1)
+ip = fb.Lagrange(fb.RefHexahedron, 1) ** (3 if kind == "elasticity" else 1)
 cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, 2), ip)
-elem = fb.HeatElement(1.0, 1.0)
+elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0)) if kind == "elasticity" else fb.HeatElement(1.0, 1.0)
 dims = block_dims(world)
 gg = fb.generate_grid(fb.Hexahedron, tuple(n * d for n, d in zip(nel, dims)), ctx=fb.Context(-1)).perturb(0.2)
 gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
@@ -38,4 +40,10 @@ out["all_cells_step"] = timed(lambda: fb.assemble_(fb.start_assemble(K, f), elem
 out["own_step"] = timed(lambda: part.assemble_(elem, mode="own"))
 out["halo_step"] = timed(lambda: part.assemble_(elem, mode="halo"))
 out["kernel"] = fb.last_kernel()
+a._accumulate = True
+out["own_accumulate"] = timed(lambda: part.assemble_(elem, mode="own"))
+a._accumulate = False
+a.variant = 32 if kind == "elasticity" else 30
+out["own_step_percell_kernel"] = timed(lambda: part.assemble_(elem, mode="own"))
+out["kernel2"] = fb.last_kernel()
 print(json.dumps(out))

@@ -630,6 +630,7 @@ def test_full_size_properties_c2_scaled(ctx):
     (fb.Hexahedron, (6, 5, 4), 1, 1, 2, "heat", {"k": 1.0, "source": 1.0}, 4),
     (fb.Hexahedron, (19, 11, 10), 1, 1, 2, "heat", {"k": 1.3, "source": 0.6}, 8),
     (fb.Hexahedron, (4, 4, 4), 1, 3, 2, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 8),
+    (fb.Hexahedron, (11, 9, 10), 1, 3, 2, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.3, 0.0, -1.0)}, 8),
     (fb.Hexahedron, (3, 3, 2), 2, 3, 3, "elasticity", {"E": 200e9, "nu": 0.3, "b": (0.0, 0.0, -1.0)}, 2),
     (fb.Tetrahedron, (3, 2, 2), 2, 1, 2, "heat", {}, 3),
 ])
@@ -659,6 +660,8 @@ def test_partitioned_assembly_matches_serial_oracle(ctx, mode, ct, nel, order, v
         pt.assemble_(elem, mode=mode)
         if kind == "heat" and ct == fb.Hexahedron:      # block partition of a generated grid: structured view + cell map
             assert fb.last_kernel() == "k_march_hex"
+        if kind == "elasticity" and ct == fb.Hexahedron and order == 1:
+            assert fb.last_kernel() == "k_march_vec"
         st.append((lg, ldh, K, f, a))
     if mode == "own":
         for r, pt in enumerate(parts):
