@@ -624,6 +624,18 @@ def main():
                "h2d_bytes_per_step": int(sum_over_ranks(float(g.nnodes * g.sdim * 8))),
                "d2h_bytes_per_step": int(sum_over_ranks(float((K.nnz + dh.ndofs) * 8))), "steps": esteps,
                "checksum_ok": bool(abs(float(f_host.sum()) - fsum_dev) <= 1e-9 * max(1.0, abs(fsum_dev)))}
+        if world > 1:
+            # the ceiling of this path on this box: the same D2H copy alone, all ranks at once (the step is D2H-bound: the
+            # copy of nzval is >= 85 % of its bytes), worst rank
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                nz_host.copy_(K.nzval, non_blocking=True)
+                torch.cuda.synchronize()
+            dt_raw = max_over_ranks(time.perf_counter() - t0) / 2
+            e2e["d2h_alone_GBps_per_gpu"] = round(K.nnz * 8 / dt_raw / 1e9, 1)
+            e2e["d2h_in_step_GBps_per_gpu"] = round((K.nnz + dh.ndofs) * 8 * esteps / dt / 1e9, 1)
+            e2e["cpu_affinity"] = len(os.sched_getaffinity(0))
 
     # ---- the consumer of K: y = K x on the assembled matrix, an HBM-bound gather ------------------------
     spmv = None

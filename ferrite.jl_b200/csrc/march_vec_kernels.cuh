@@ -23,9 +23,16 @@
 //   * after layer z the columns of node plane z are final inside the tile: the nine columns of the three tile-interior nodes
 //     of a tile row are one contiguous 5.8 KB piece of nzval -> one cp.async.bulk store; columns of nodes on the tile faces
 //     and on the first / last plane of a chunk are shared with other CTAs -> cp.reduce.async.bulk.add.f64.  15 bulk
-//     operations per layer and CTA replace 9 216 REDs;
+//     operations per layer and CTA replace 9 216 REDs.  A bulk operation takes its operands from uniform registers, so the
+//     pieces of the lanes of one warp are issued one after the other: the 15 pieces sit on lanes 0..3 of the four warps;
 //   * the set-up of node plane z + 2 (dofs, colptr extents, scan of the column copies) is spread over the sub-steps of
-//     layer z, one step per barrier interval, with the loads issued one interval before their use.
+//     layer z, one step per barrier interval, with the loads issued one interval before their use; the offset-map words of a
+//     cell are requested one sub-step ahead;
+//   * the window layout is padded against shared-memory bank conflicts (fb2_mvec_cap).
+// Measured on one B200 (128^3 cells, profiles/r02_prof_c5_march_*.txt): 3.8 ms against 5.05 ms for k_cell_syrk; what is left
+// is latency: two CTAs (eight warps) per SM is all that 2 x 104 KB of window and 232 registers allow, no unit is busier than
+// 42 % (shared-memory wavefronts), FP64 pipe 23 %, DRAM 23 %.  A flush by coalesced per-thread stores / REDs with fused
+// clearing of the window (FB2_MVEC_FLUSH=thread) costs 26 % more instructions and runs at 4.5 ms.
 #pragma once
 
 constexpr int MV_PN = 25;   // nodes of a tile plane (5 x 5)
@@ -511,14 +518,18 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
                     fpart = fma(ax * ay * nzm, dO, fpart);
                 }
                 // ---- contraction on the FP64 tensor cores: acc[c][d][e] = H_cd[a = mc][b = 2 kr + e] ---------------------------------
+                // (the two k-steps of a tile depend on each other through the accumulator: nine independent DMMAs, then nine more)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         acc[c][d][0] = 0.0; acc[c][d][1] = 0.0;
                         fb2_dmma884(acc[c][d], gw[0][c], g[0][d]);
-                        fb2_dmma884(acc[c][d], gw[1][c], g[1][d]);
                     }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) fb2_dmma884(acc[c][d], gw[1][c], g[1][d]);
                 if (with_f) {   // fe[(a, c)] = b_c sum_q N_a dOmega: the four lanes of a row hold the four pairs of points
                     fpart += __shfl_xor_sync(full, fpart, 1);
                     fpart += __shfl_xor_sync(full, fpart, 2);

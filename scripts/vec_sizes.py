@@ -1,12 +1,13 @@
-"""k_march_vec on generated grids of several sizes (python scripts/vec_sizes.py 128x128x128 129x128x128 ...): ms per launch"""
+"""k_march_vec / k_march_hex (VS_KIND=heat) on generated grids of several sizes (python scripts/vec_sizes.py 128x128x128 129x128x128 ...): ms per launch"""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import ferrite_b200 as fb
 ctx = fb.default_context(0)
-ip = fb.Lagrange(fb.RefHexahedron, 1) ** 3
+kind = os.environ.get("VS_KIND", "elasticity")
+ip = fb.Lagrange(fb.RefHexahedron, 1) ** (3 if kind == "elasticity" else 1)
 cv = fb.CellValues(fb.QuadratureRule(fb.RefHexahedron, 2), ip)
-elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0))
+elem = fb.ElasticityElement(E=200e9, nu=0.3, b=(0.0, 0.0, -1.0)) if kind == "elasticity" else fb.HeatElement(1.0, 1.0)
 for spec in sys.argv[1:]:
     nel = tuple(int(v) for v in spec.split("x"))
     g = fb.generate_grid(fb.Hexahedron, nel).perturb(0.2)
