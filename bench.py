@@ -43,9 +43,13 @@ CONFIGS = {
                    label="linear elasticity Q1^3 hex, 160^3 cells per GPU (BASELINE.json configs[4]: 320^3 cells on 8 GPUs)"),
     "c3": dict(cell="hex", nel=(48, 48, 48), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
                label="linear elasticity Q2^3 hex 48^3 (BASELINE.json configs[2] at 1/8 size)"),
-    "c4": dict(cell="tet", nel=(48, 48, 48), order=2, vdim=3, qr=4, element="neohooke", bmin=7.0e3, fmin=0.25e6,
+    # bytes: 349 stored entries per cell (nnz / ncells of this mesh) written once = 2.79 kB, + dofs 120 + conn 16 + u, f, x 80;
+    # flops per quadrature point (11 of them): grad u 90 FMA, constitutive law + dP/dF ~400, residual 30 x 3, tangent
+    # 30 x 27 + 900 x 3 (exploiting that grad(delta u_i) has one non-zero row; the reference's dense tensor contractions
+    # perform 10.8 kFMA per point = 0.24 MFLOP per cell): 4.1 kFMA x 11 x 2 = 0.09 MFLOP
+    "c4": dict(cell="tet", nel=(48, 48, 48), order=2, vdim=3, qr=4, element="neohooke", bmin=3.0e3, fmin=0.09e6,
                label="Neo-Hooke tangent + residual, P2^3 tetrahedra, generate_grid(Tetrahedron, 48^3) = 663552 cells "
-                     "(BASELINE.json configs[3]); bytes/flops per cell are estimates (30x30 Ke, 11-point rule)"),
+                     "(BASELINE.json configs[3])"),
     "c3full": dict(cell="hex", nel=(96, 96, 96), order=2, vdim=3, qr=3, element="elasticity", bmin=37.6e3, fmin=0.48e6,
                    label="linear elasticity Q2^3 hex 96^3 (BASELINE.json configs[2], full size: nnz = 4.09e9 > 2^32)"),
 }
