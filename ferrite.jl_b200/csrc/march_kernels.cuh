@@ -150,7 +150,8 @@ __device__ __forceinline__ void fb2_march_plane_finish(uint16_t* s_cs, uint8_t* 
         s_len[lane + 32] = (uint8_t)lenB;
         s_gb[lane + 32] = bB;
     }
-    // contiguity of neighbouring columns: column n + 1 starts where column n ends
+    // contiguity of neighbouring columns: column n + 1 starts where column n ends (bits 0..4 of *rowok: the seven interior
+    // columns of tile row b are contiguous; bits 8..12: all nine are)
     int64_t nbA = __shfl_down_sync(full, bA, 1);
     const int64_t nbB = __shfl_down_sync(full, bB, 1), bB0 = __shfl_sync(full, bB, 0);
     if (lane == 31) nbA = bB0;
@@ -159,8 +160,10 @@ __device__ __forceinline__ void fb2_march_plane_finish(uint16_t* s_cs, uint8_t* 
         const unsigned long long m = (unsigned long long)mA | ((unsigned long long)mB << 32);
         int ok = 0;
 #pragma unroll
-        for (int b = 0; b < 5; ++b)
+        for (int b = 0; b < 5; ++b) {
             if (((m >> (9 * b + 1)) & 0x3Full) == 0x3Full) ok |= 1 << b;
+            if (((m >> (9 * b)) & 0xFFull) == 0xFFull) ok |= 256 << b;   // all nine columns of the row are one piece of nzval
+        }
         *s_rowok = ok;
     }
     __syncwarp();
@@ -191,25 +194,56 @@ __device__ __forceinline__ void fb2_march_emit(double* __restrict__ nzval, const
     }
 }
 
-// Write a finished node plane out.  Lane s < 15 takes piece s: tile row b = s / 3, part 0 / 2 = the face columns a = 0 / 8
-// (reduce-add: shared with the neighbouring tiles), part 1 = the interior columns a = 1..7 (copy unless `redall` or the row
-// is a tile face, b = 0 / 4).  Rows whose interior columns are not contiguous in nzval (irregular numbering) are written
-// column by column by lanes 16..22.  The accumulator is NOT zeroed here: the bulk operations read it asynchronously;
-// fb2_bulk_wait_read + a zero fill precede its next use.
+// The same for the pieces of all lanes of a warp at once (total = 0: the lane has none).  One call site per kind of bulk
+// operation: a bulk operation takes its operands from uniform registers, so ptxas wraps every site in a loop that elects
+// one lane at a time -- with the fifteen pieces of a plane spread over the eleven inlined sites of fb2_march_emit's branches
+// the flush was 11 % of the kernel's instructions and 20 % of its stall samples (profiles/r02_prof_c2_final.txt).
+__device__ __forceinline__ void fb2_march_emit_piece(double* g, const double* a, int total, bool store) {
+    const int head = (total > 0 && (reinterpret_cast<uintptr_t>(g) & 8)) ? 1 : 0;   // nzval is 16-byte aligned: odd entry index
+    const int rem = total - head;
+    const int body = rem & ~1;
+    if (head) {
+        if (store) g[0] = a[0]; else atomicAdd(g, a[0]);
+    }
+    if (rem & 1) {
+        if (store) g[head + body] = a[head + body]; else atomicAdd(g + head + body, a[head + body]);
+    }
+    if (body > 0 && store) fb2_bulk_store(g + head, a + head, body * 8);
+    if (body > 0 && !store) fb2_bulk_red_add(g + head, a + head, body * 8);
+}
+
+// Write a finished node plane out.  Lane s < 15 takes piece s of tile row b = s / 3: part 0 / 2 = the face columns a = 0 / 8
+// (reduce-add: shared with the neighbouring tiles), part 1 = the interior columns a = 1..7 (bulk store unless `redall` or the
+// row is a tile face, b = 0 / 4); a row that is reduce-added as a whole and contiguous in nzval is ONE piece (part 0).
+// Rows whose interior columns are not contiguous in nzval (irregular numbering) are written column by column by lanes
+// 16..22.  The accumulator is NOT zeroed here: the bulk operations read it asynchronously; fb2_bulk_wait_read + a zero fill
+// precede its next use.
 __device__ __forceinline__ void fb2_march_flush(const AsmArgs& A, const double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
                                                 const int64_t* s_gb, const int* s_dof, int rowok, int lane, bool redall, bool with_f) {
     fb2_fence_async_smem();   // the read-modify-writes of this warp (generic proxy) -> visible to the bulk engine (async proxy)
     __syncwarp();
-    if (lane < 15) {
+    {
         const int b = lane / 3, part = lane - 3 * b, r0 = 9 * b;
-        if (part == 0) fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0, 1);
-        else if (part == 2) fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 8, 1);
-        else if ((rowok >> b) & 1) {
-            if (!redall && b >= 1 && b <= 3) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 1, 7);
-            else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, r0 + 1, 7);
+        const bool rowred = redall || b == 0 || b == 4;
+        const bool whole = rowred && ((rowok >> (8 + b)) & 1);
+        int n0 = r0, cnt = 0;
+        if (lane < 15) {
+            if (whole) cnt = part == 0 ? 9 : 0;
+            else if (part == 0) cnt = 1;
+            else if (part == 2) { n0 = r0 + 8; cnt = 1; }
+            else if ((rowok >> b) & 1) { n0 = r0 + 1; cnt = 7; }
         }
-        fb2_bulk_commit();
-    } else if (lane >= 16 && lane < 23 && rowok != 31) {
+        int total = 0, c0 = 0;
+        int64_t g0 = 0;
+        if (cnt > 0) {
+            c0 = s_cs[n0];
+            total = (int)s_cs[n0 + cnt - 1] + (int)s_len[n0 + cnt - 1] - c0;
+            g0 = s_gb[n0];
+        }
+        fb2_march_emit_piece(A.nzval + g0, acc + c0, total, !rowred && part == 1);
+        if (lane < 15) fb2_bulk_commit();
+    }
+    if (lane >= 16 && lane < 23 && (rowok & 31) != 31) {
         for (int b = 0; b < 5; ++b) {
             if ((rowok >> b) & 1) continue;
             const int n = 9 * b + 1 + (lane - 16);

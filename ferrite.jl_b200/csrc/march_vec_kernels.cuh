@@ -232,26 +232,46 @@ __device__ __forceinline__ void fb2_mvec_flush(const AsmArgs& A, double* acc, do
 __device__ __forceinline__ void fb2_mvec_flush_tma(const AsmArgs& A, const double* acc, double* sf, const uint16_t* s_cs, const uint8_t* s_len,
                                                    const int64_t* s_gb, int* s_dof, const unsigned* s_adj, int tid, bool redall, bool with_f, int dbg) {
     // piece p = 4 * lane + warp on lanes 0..3 of every warp: a bulk operation takes its operands from uniform registers, so a
-    // warp issues the pieces of its lanes one after the other -- four per warp instead of fifteen on one warp
+    // warp issues the pieces of its lanes one after the other -- four per warp instead of fifteen on one warp.  A tile row
+    // that is reduce-added as a whole and contiguous in nzval is one piece (part 0).
     const int p = 4 * (tid & 31) + (tid >> 5);
-    if ((tid & 31) < 4 && p < 15 && dbg != 2) {
-        const int b = p / 3, part = p - 3 * b;
-        const int n0 = (5 * b + (part == 0 ? 0 : (part == 1 ? 1 : 4))) * 3, cnt = part == 1 ? 9 : 3;
-        const bool store = dbg == 1 || (dbg != 3 && !redall && part == 1 && b >= 1 && b <= 3);
-        const int wd = n0 >> 5, sh = n0 & 31;
-        const unsigned long long need = (1ull << (cnt - 1)) - 1ull;
+    const bool mine = (tid & 31) < 4 && p < 15 && dbg != 2;
+    const int b = p / 3, part = p - 3 * b;
+    const bool rowred = redall || b == 0 || b == 4;
+    auto contiguous = [&](int k0, int n) -> bool {   // columns k0 .. k0 + n - 1 follow each other in nzval
+        const int wd = k0 >> 5, sh = k0 & 31;
         const unsigned long long bits = ((unsigned long long)s_adj[wd] | ((unsigned long long)s_adj[wd + 1] << 32)) >> sh;
-        if ((bits & need) == need) {
-            if (store) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, n0, cnt);
-            else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, n0, cnt);
-        } else {
-            for (int k = 0; k < cnt; ++k) {
-                if (store) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, n0 + k, 1);
-                else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, n0 + k, 1);
-            }
+        const unsigned long long need = (1ull << (n - 1)) - 1ull;
+        return (bits & need) == need;
+    };
+    int n0 = 15 * b, cnt = 0;
+    bool percol = false;
+    if (mine) {
+        if (rowred && dbg != 1 && contiguous(15 * b, 15)) cnt = part == 0 ? 15 : 0;
+        else {
+            n0 = 15 * b + (part == 0 ? 0 : (part == 1 ? 3 : 12));
+            cnt = part == 1 ? 9 : 3;
+            if (!contiguous(n0, cnt)) percol = true;
         }
-        fb2_bulk_commit();
     }
+    const bool store = dbg == 1 || (dbg != 3 && !rowred && part == 1);
+    {
+        int total = 0, c0 = 0;
+        int64_t g0 = 0;
+        if (cnt > 0 && !percol) {
+            c0 = s_cs[n0];
+            total = (int)s_cs[n0 + cnt - 1] + (int)s_len[n0 + cnt - 1] - c0;
+            g0 = s_gb[n0];
+        }
+        fb2_march_emit_piece(A.nzval + g0, acc + c0, total, store);
+    }
+    if (percol) {   // irregular numbering
+        for (int k = 0; k < cnt; ++k) {
+            if (store) fb2_march_emit<true>(A.nzval, acc, s_cs, s_len, s_gb, n0 + k, 1);
+            else fb2_march_emit<false>(A.nzval, acc, s_cs, s_len, s_gb, n0 + k, 1);
+        }
+    }
+    if (mine) fb2_bulk_commit();
     const int col = 127 - tid;   // the per-column chores sit on the upper warps
     if (col < MV_NC) {
         const int d = s_dof[col];
