@@ -275,7 +275,7 @@ bool march_usable(fb2_assembler* a) {
 }
 
 // Columns the marching-tile kernel adds to with reduce-adds (see k_march_mark), as a sorted device list; cached per chunk length.
-int march_zero_list(fb2_assembler* a, int lz) {
+int march_zero_list(fb2_assembler* a, int lz, int tx = 8, int ty = 4, int vdim = 1) {
     if (a->d_march_zcols && a->march_zlz == lz) return FB2_OK;
     const fb2_dh* dh = a->dh;
     const fb2_grid* g = dh->grid;
@@ -296,7 +296,7 @@ int march_zero_list(fb2_assembler* a, int lz) {
     if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, (size_t)nd, st);
     if (e == cudaSuccess) {
-        k_march_mark<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dh->d_cell_dofs, g->ncells_pad, nx, ny, nz, lz, d_flag);
+        k_march_mark<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dh->d_cell_dofs, g->ncells_pad, nx, ny, nz, lz, tx, ty, vdim, d_flag);
         cub::CountingInputIterator<int32_t> ids(0);
         e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, d_flag, d_out, d_num, (int)nd, st);
         if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes);
@@ -399,7 +399,22 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
                   : (a->map_complete ? k_march_vec<false, false> : k_march_vec<true, false>);
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    FB2_TRY(pay_zero_fill(a, A));
+    // start_assemble's zero fill of nzval, if still owed: only the columns that receive reduce-adds need it (nodes on tile
+    // faces and on the planes where two chunks meet, 47 % of nzval at 128^3); with three columns = 1.9 KB per node the
+    // column-wise fill beats the memset over everything here (FB2_MARCH_ZSEL=0 keeps the memset)
+    if (A.zero_pending) {
+        const char* ez = getenv("FB2_MARCH_ZSEL");
+        if (!(ez && atoi(ez) == 0) && gen && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
+            FB2_TRY(march_zero_list(a, M.lz, 4, 4, 3));
+            if (a->march_nzcols > 0)
+                k_zero_columns<<<(unsigned)((a->march_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_march_zcols, a->march_nzcols,
+                                                                                              a->pat->d_colptr, A.nzval);
+            ctx->launches++;
+            A.zero_pending = 0;
+        } else {
+            FB2_TRY(pay_zero_fill(a, A));
+        }
+    }
     k<<<(unsigned)(tiles * nchunks), 128, smem, ctx->stream>>>(A, M);
     g_fb2_last_kernel = "k_march_vec";
     ctx->launches++;
@@ -704,8 +719,9 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
     const int ct = cv->celltype, nbs = cv->nb, vdim = cv->vdim;
     int rc = FB2_OK;
     // only the marching-tile kernel (Q1 hexahedra, heat / mass, default variant) takes the fill over
-    const bool may_fuse = (element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS) && (variant == 0 || variant == 31) && atomic &&
-                          ct == FB2_HEXAHEDRON && nbs == 8 && cv->nq == 8 && vdim == 1;
+    const bool may_fuse = atomic && ct == FB2_HEXAHEDRON && nbs == 8 && cv->nq == 8 &&
+                          (((element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS) && (variant == 0 || variant == 31) && vdim == 1) ||
+                           (element == FB2_ELEM_ELASTICITY && variant == 0 && vdim == 3));
     if (!may_fuse) FB2_TRY(pay_zero_fill(a, A));
     switch (element) {
         case FB2_ELEM_HEAT:
@@ -722,6 +738,7 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
                 rc = try_march_vec(a, ctx, A, accumulate, &handled);
                 if (rc != FB2_OK || handled) return rc;
             }
+            FB2_TRY(pay_zero_fill(a, A));   // the marching-tile kernel was not applicable
             if (variant != 1) {   // variant 1: the DFMA block kernel
                 bool handled = false;
                 rc = dispatch_syrk(a, ctx, A, atomic, ct, nbs, vdim, &handled);

@@ -636,18 +636,19 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 // (x % 8 == 0 or y % 4 == 0) and the node planes where two chunks meet -- 38 % of nzval on C2 instead of all of it.
 // k_march_mark flags those columns (thread per grid node, same predicate as fb2_march_flush); the flagged dofs are
 // compacted into a sorted list once per assembler; k_zero_columns (warp per listed column) runs in front of every launch.
-__global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, int nx, int ny, int nz, int lz, uint8_t* __restrict__ flag) {
+__global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, int nx, int ny, int nz, int lz, int tx, int ty, int vdim,
+                             uint8_t* __restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nn = (int64_t)(nx + 1) * (ny + 1) * (nz + 1);
     if (t >= nn) return;
     const int x = (int)(t % (nx + 1)), y = (int)((t / (nx + 1)) % (ny + 1)), p = (int)(t / ((int64_t)(nx + 1) * (ny + 1)));
-    const bool need = (x % 8 == 0) || (y % 4 == 0) || (p % lz == 0) || p == nz;
+    const bool need = (x % tx == 0) || (y % ty == 0) || (p % lz == 0) || p == nz;   // tiles of tx x ty cells, chunks of lz layers
     if (!need) return;
     // the node is corner (sx, sy, sz) of the cell below / left of it (clamped to the grid)
     const int cx = min(x, nx - 1), cy = min(y, ny - 1), cz = min(p, nz - 1);
     const int ln = fb2_hexnode(x - cx, y - cy, p - cz);
     const int64_t cell = cx + (int64_t)nx * (cy + (int64_t)ny * cz);
-    flag[cell_dofs[(size_t)ln * np + cell]] = 1;
+    for (int c = 0; c < vdim; ++c) flag[cell_dofs[(size_t)(ln * vdim + c) * np + cell]] = 1;
 }
 
 // a warp takes 32 listed columns: one lane per column fetches its extent (two dependent loads for 32 columns instead of

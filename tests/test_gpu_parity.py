@@ -549,6 +549,55 @@ def test_missing_entry_and_zero_skip(ctx):
         fb.scatter_(fb.start_assemble(K, None), Ke)
 
 
+@pytest.mark.parametrize("vdim", [1, 3])
+def test_marching_kernels_on_an_incomplete_pattern(ctx, vdim):
+    """assemble! on a pattern that lacks entries (src/assembler.jl:459-467) through the marching-tile kernels (their CHECK
+    instantiations): zeros aimed at missing entries are skipped, a non-zero is an error"""
+    g, og, dh, odh, cv, ocv = build(fb.Hexahedron, (9, 6, 5), 1, vdim, 2, True)
+    K0 = fb.allocate_matrix(dh)
+    colptr, rowval = K0.colptr.copy(), K0.rowval.copy()
+    # drop the first strictly-lower entry of three interior columns
+    drop = []
+    for col in (dh.ndofs // 3, dh.ndofs // 2, dh.ndofs - 7):
+        lo, hi = colptr[col] - 1, colptr[col + 1] - 1
+        below = [p for p in range(lo, hi) if rowval[p] > col + 1]
+        drop.append(below[0])
+    keep = np.ones(len(rowval), bool)
+    keep[drop] = False
+    counts = np.diff(colptr).copy()
+    for p in drop:
+        counts[np.searchsorted(colptr - 1, p, side="right") - 1] -= 1
+    colptr2 = np.concatenate(([1], 1 + np.cumsum(counts)))
+    K = fb.allocate_matrix(dh, colptr2, rowval[keep])
+    f = ctx.zeros(dh.ndofs)
+    of = np.zeros(odh.ndofs)
+    oK = O.allocate_matrix(odh)
+    kernel = "k_march_hex" if vdim == 1 else "k_march_vec"
+    if vdim == 1:
+        zero, full = fb.HeatElement(k=0.0, source=0.7), fb.HeatElement(k=1.0, source=0.7)
+        O.assemble_global(odh, ocv, oK, of, "heat", dict(k=0.0, source=0.7))
+    else:
+        zero, full = fb.ElasticityElement(lam=0.0, mu=0.0, b=(0.1, 0.2, -1.0)), fb.ElasticityElement(lam=1.0, mu=0.5, b=(0.1, 0.2, -1.0))
+        O.assemble_global(odh, ocv, oK, of, "elasticity", {"lambda": 0.0, "mu": 0.0, "b": (0.1, 0.2, -1.0)})
+    K.nzval.fill_(3.0)
+    a = fb.start_assemble(K, f)
+    fb.assemble_(a, zero, cv)
+    fb.finish_assemble(a)                              # every element matrix is exactly zero: nothing to complain about
+    assert fb.last_kernel() == kernel
+    assert float(K.nzval.abs().max()) == 0.0 and close(f.cpu().numpy(), of)[0]
+    with pytest.raises(fb.MissingPatternEntry):
+        a = fb.start_assemble(K, f)
+        fb.assemble_(a, full, cv)
+        fb.finish_assemble(a)
+    assert fb.last_kernel() == kernel
+    # the same matrix entries as on the complete pattern wherever the entry exists
+    ctx.synchronize()
+    a = fb.start_assemble(K0, f)
+    fb.assemble_(a, full, cv)
+    fb.finish_assemble(a)
+    assert close(K.nzval.cpu().numpy(), K0.nzval.cpu().numpy()[keep])[0]
+
+
 @pytest.mark.parametrize("nel", [(3, 3, 3), (12, 10, 9)])   # per-cell kernel / tile kernel
 def test_detj_not_positive_is_reported(ctx, nel):
     og = O.generate_grid("hexahedron", nel)
