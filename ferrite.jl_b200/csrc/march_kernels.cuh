@@ -651,21 +651,36 @@ __global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, 
     for (int c = 0; c < vdim; ++c) flag[cell_dofs[(size_t)(ln * vdim + c) * np + cell]] = 1;
 }
 
-// a warp takes 32 listed columns: one lane per column fetches its extent (two dependent loads for 32 columns instead of
-// two per column), then the whole warp zeroes them one after the other
+// A warp takes 32 listed columns: one lane per column fetches its extent (two dependent loads for 32 columns instead of two
+// per column); listed columns that follow each other in nzval (the node rows of tile faces in y, the node planes between
+// chunks) are merged into runs, and the whole warp zeroes one run after the other with 16-byte stores.
 __global__ void k_zero_columns(const int32_t* __restrict__ cols, int64_t n, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
+    const unsigned full = 0xffffffffu;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int64_t i = w * 32 + lane;
+    if (w * 32 >= n) return;
     int64_t b = 0, e = 0;
     if (i < n) {
         const int c = __ldg(cols + i);
         b = __ldg(colptr + c);
         e = __ldg(colptr + c + 1);
     }
-    const int m = (int)min((int64_t)32, n - w * 32);
-    for (int k = 0; k < m; ++k) {
-        const int64_t bk = __shfl_sync(0xffffffffu, b, k), ek = __shfl_sync(0xffffffffu, e, k);
-        for (int64_t p = bk + lane; p < ek; p += 32) nzval[p] = 0.0;
+    const int64_t pe = __shfl_up_sync(full, e, 1);
+    unsigned heads = __ballot_sync(full, i < n && (lane == 0 || b != pe));
+    while (heads) {
+        const int s = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const int t = (heads ? __ffs(heads) - 1 : (int)min((int64_t)32, n - w * 32)) - 1;   // last column of the run
+        int64_t rb = __shfl_sync(full, b, s);
+        const int64_t re = __shfl_sync(full, e, t);
+        if (rb >= re) continue;
+        if (rb & 1) {   // nzval is 16-byte aligned (checked by the caller): peel to an even entry
+            if (lane == 0) nzval[rb] = 0.0;
+            ++rb;
+        }
+        const int64_t body = (re - rb) & ~(int64_t)1;
+        for (int64_t p = rb + 2 * lane; p < rb + body; p += 64) *reinterpret_cast<double2*>(nzval + p) = make_double2(0.0, 0.0);
+        if (((re - rb) & 1) && lane == 0) nzval[re - 1] = 0.0;
     }
 }
