@@ -465,6 +465,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
         if (atomic && (variant == 0 || variant == 31) && (gen || boxed) && A.cells == nullptr && A.ncount > 0 && range_ok &&
             snel[0] < (1 << 28) && snel[1] < (1 << 28) && march_usable(a)) {
             MarchArgs M;
+            memset(&M, 0, sizeof(M));
             M.nx = (int)snel[0];
             M.ny = (int)snel[1];
             M.z0 = gen ? (int)(A.cell_first / lay) : 0;
@@ -488,7 +489,23 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 const int64_t want = std::max<int64_t>(1, 12 * resident / tiles);
                 M.lz = (int)std::max<int64_t>(4, (nzl + want - 1) / want);
                 if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
-                const int nchunks = (nzl + M.lz - 1) / M.lz;
+                int nchunks = (nzl + M.lz - 1) / M.lz;
+                M.nfull = nchunks;
+                M.lt = M.lz;
+                // CTAs of equal length run in synchronised waves, and the last, partly filled wave costs a whole chunk time
+                // (4 % of the launch on a 201 x 200 x 200 box: 10.56 waves of 20 layers): the last ~15 % of the layers are cut
+                // into chunks of a third of the length.  Not with the column-wise zero fill, whose list assumes uniform chunks.
+                const char* ezs = getenv("FB2_MARCH_ZSEL");
+                if (!getenv("FB2_MARCH_LZ") && !(ezs && atoi(ezs) == 1) && nchunks >= 4 && M.lz >= 12) {
+                    M.nfull = std::max(1, (int)(0.85 * nzl / M.lz));
+                    M.lt = std::max(4, M.lz / 3);
+                    nchunks = M.nfull + (nzl - M.nfull * M.lz + M.lt - 1) / M.lt;
+                }
+                if (const char* e = getenv("FB2_MARCH_LT")) {   // tests: force short chunks behind the first half of the full ones
+                    M.nfull = std::max(1, ((nzl + M.lz - 1) / M.lz) / 2);
+                    M.lt = std::min(M.lz, std::max(1, atoi(e)));
+                    nchunks = M.nfull + (std::max(0, nzl - M.nfull * M.lz) + M.lt - 1) / M.lt;
+                }
                 // variant 31: table-driven integration inside the marching kernel (A/B against the analytic element)
                 const bool analytic = ELEM == FB2_ELEM_HEAT && variant != 31 && cv_is_q1hex_gauss2(a->cv);
                 if (analytic) A.p[2] = 0.125 * a->cv->w[0];   // the common quadrature weight / 8 (see fb2_hex8_heat)

@@ -30,6 +30,8 @@ struct MarchArgs {
     int z0, z1;            // layers [z0, z1) of this launch
     int tiles_x, tiles_y;  // tiles of 8 x 4 cells per layer
     int lz;                // layers per chunk (one warp marches through one chunk of one tile)
+    int nfull, lt;         // k_march_hex: the first nfull chunks have lz layers, the chunks after them lt <= lz (short chunks at the
+                           // end of the launch keep its tail short: CTAs are dispatched in chunk order)
     int cap;               // accumulator doubles per node plane: 45 x (longest matrix column) + 48 parity pads, even
     int overwrite;         // 1: nzval / f were zero-filled for this launch and nobody else adds to tile-interior columns
                            //    => they are written with plain (bulk) stores; 0: everything is added
@@ -440,7 +442,8 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
     const int tx = bid % M.tiles_x;
     bid /= M.tiles_x;
     const int ty = bid % M.tiles_y, ch = bid / M.tiles_y;
-    const int zb = M.z0 + ch * M.lz, ze = min(M.z1, zb + M.lz);
+    const int zb = ch < M.nfull ? M.z0 + ch * M.lz : M.z0 + M.nfull * M.lz + (ch - M.nfull) * M.lt;
+    const int ze = min(M.z1, zb + (ch < M.nfull ? M.lz : M.lt));
     if (zb >= ze) return;
     const int cx = tx * 8 + lx, cy = ty * 4 + ly;
     const bool inside = cx < M.nx && cy < M.ny;     // lanes outside the grid redo a valid cell and add nothing

@@ -181,12 +181,15 @@ def test_assembly_matches_oracle(ctx, case, scatter):
 
 
 @pytest.mark.parametrize("nel", [(8, 4, 3), (9, 5, 7), (17, 13, 11), (3, 2, 1), (24, 10, 9)])
-@pytest.mark.parametrize("lz", ["1", "3", ""])
+@pytest.mark.parametrize("lz", ["1", "3", "", "3,1", "4,2"])
 def test_marching_tile_kernel(ctx, nel, lz, monkeypatch):
     """k_march_hex (default for generate_grid Q1 hexahedra): full / partial tiles, chunk lengths (FB2_MARCH_LZ), zero fill
     (plain stores for tile-interior columns) and fillzero=false (REDs everywhere), against the oracle and the per-cell kernel."""
+    monkeypatch.delenv("FB2_MARCH_LT", raising=False)
     if lz:
-        monkeypatch.setenv("FB2_MARCH_LZ", lz)
+        monkeypatch.setenv("FB2_MARCH_LZ", lz.split(",")[0])
+        if "," in lz:                                     # short chunks at the end of the launch (tail of the big launches)
+            monkeypatch.setenv("FB2_MARCH_LT", lz.split(",")[1])
     else:
         monkeypatch.delenv("FB2_MARCH_LZ", raising=False)
     g, og, dh, odh, cv, ocv = build(fb.Hexahedron, nel, 1, 1, 2, True)
