@@ -338,6 +338,44 @@ bool marchv_usable(fb2_assembler* a) {
     return a->marchv_state == 1;
 }
 
+// CTA lists of a split marching launch on a partition-local box (see fb2_assembler::march_part): list 0 = the CTAs (tile x
+// chunk) that hold an interface cell, list 1 = the other CTAs with own cells.  Built on the host from the cell map.
+int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y, int nchunks, int64_t ncells_own) {
+    const fb2_grid* g = a->dh->grid;
+    const int64_t key[8] = {M.lz, M.nfull, M.lt, tile_x, tile_y, a->march_iface, ncells_own, nchunks};
+    if (a->d_cta_list[0] && memcmp(key, a->cta_key, sizeof(key)) == 0) return FB2_OK;
+    FB2_CHECK(g->structured && !g->sv_cellmap.empty(), FB2_ERR_INTERNAL, "march_cta_lists: the grid has no cell map");
+    const int64_t nx = g->sv_nel[0], ny = g->sv_nel[1], nz = g->sv_nel[2];
+    const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y;
+    std::vector<uint8_t> flag((size_t)(tiles * nchunks), 0);
+    for (int64_t z = 0; z < nz; ++z) {
+        const int64_t zr = z - M.z0;
+        const int64_t ch = M.nfull > 0 && zr >= (int64_t)M.nfull * M.lz ? M.nfull + (zr - (int64_t)M.nfull * M.lz) / M.lt : zr / M.lz;
+        if (zr < 0 || ch >= nchunks) continue;
+        for (int64_t y = 0; y < ny; ++y)
+            for (int64_t x = 0; x < nx; ++x) {
+                const int32_t c = g->sv_cellmap[(size_t)(x + nx * (y + ny * z))];
+                if (c < 0 || c >= ncells_own) continue;
+                uint8_t& fl = flag[(size_t)(ch * tiles + (y / tile_y) * M.tiles_x + x / tile_x)];
+                fl |= c < a->march_iface ? 3 : 1;
+            }
+    }
+    std::vector<int32_t> list[2];
+    for (size_t i = 0; i < flag.size(); ++i) {
+        if (flag[i] & 2) list[0].push_back((int32_t)i);
+        else if (flag[i] & 1) list[1].push_back((int32_t)i);
+    }
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(a->d_cta_list[k]);
+        a->d_cta_list[k] = nullptr;
+        FB2_CUDA(cudaMalloc(&a->d_cta_list[k], std::max<size_t>(list[k].size(), 1) * sizeof(int32_t)));
+        FB2_CUDA(cudaMemcpy(a->d_cta_list[k], list[k].data(), list[k].size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        a->cta_count[k] = (int64_t)list[k].size();
+    }
+    memcpy(a->cta_key, key, sizeof(key));
+    return FB2_OK;
+}
+
 // conditions of k_march_vec that do not depend on the launch: element tables, structured grid, column length, numbering
 bool marchv_static_ok(fb2_assembler* a) {
     const fb2_grid* g = a->dh->grid;
@@ -415,7 +453,15 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
             FB2_TRY(pay_zero_fill(a, A));
         }
     }
-    k<<<(unsigned)(tiles * nchunks), 128, smem, ctx->stream>>>(A, M);
+    int64_t nctas = tiles * nchunks;
+    if (a->march_part != 0 && !gen) {   // split launch of the partitioned exchange path
+        M.nfull = 0;
+        M.lt = M.lz;
+        FB2_TRY(march_cta_lists(a, M, 4, 4, nchunks, A.cell_first + A.ncount));
+        M.ctalist = a->d_cta_list[a->march_part - 1];
+        nctas = a->cta_count[a->march_part - 1];
+    }
+    if (nctas > 0) k<<<(unsigned)nctas, 128, smem, ctx->stream>>>(A, M);
     g_fb2_last_kernel = "k_march_vec";
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
@@ -530,7 +576,13 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                     }
                     A.zero_pending = 0;
                 }
-                k<<<(unsigned)(tiles * nchunks), 32, smem, ctx->stream>>>(A, M);
+                int64_t nctas = tiles * nchunks;
+                if (a->march_part != 0 && !gen) {   // split launch of the partitioned exchange path
+                    FB2_TRY(march_cta_lists(a, M, 8, 4, nchunks, A.cell_first + A.ncount));
+                    M.ctalist = a->d_cta_list[a->march_part - 1];
+                    nctas = a->cta_count[a->march_part - 1];
+                }
+                if (nctas > 0) k<<<(unsigned)nctas, 32, smem, ctx->stream>>>(A, M);
                 g_fb2_last_kernel = "k_march_hex";
                 ctx->launches++;
                 FB2_CUDA(cudaGetLastError());
@@ -917,7 +969,9 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
     A.cell_first = subset && !a->d_cells ? a->cell_first : 0;
     A.ncount = subset ? a->ncells_active : g->ncells;
     if (A.ncount == 0) return pay_zero_fill(a, A);
-    return launch_one(a, A, element, true, o.variant, !o.fillzero);
+    // split marching launch (fb2_assemble_distributed): the caller paid the zero fill in front of both parts
+    const int accumulate = a->march_part != 0 ? (a->march_overwrite ? 0 : 1) : !o.fillzero;
+    return launch_one(a, A, element, true, o.variant, accumulate);
 }
 
 // assemble!(a, celldofs(cell), Ke, fe) for every cell from device-resident element matrices (the layout of fb2_ea_assemble:

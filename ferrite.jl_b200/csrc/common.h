@@ -214,6 +214,15 @@ struct fb2_assembler {
     uint8_t* d_mapb = nullptr;     // byte-packed copy for the marching-tile kernel: [ceil(n*n/16)][ncells_pad][16] (lazy)
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     uint32_t* d_mapv = nullptr;    // lane-major byte map of k_march_vec: [ncells][5][32] words (lazy)
+    // Marching kernels on a partition-local grid, exchange mode: the CTAs (tile x chunk) that hold interface cells are launched
+    // first (march_part = 1), the others (2) run while the interface columns are exchanged; 0 = one launch over all CTAs.
+    // The two CTA lists are cached for the chunk structure / tile size they were built for.
+    int march_part = 0;
+    int march_overwrite = 0;       // part 2: nzval was zero-filled in front of part 1 (plain stores for tile-interior columns allowed)
+    int64_t march_iface = 0;       // cells [0, march_iface) of the local grid are the interface cells
+    int32_t* d_cta_list[2] = {nullptr, nullptr};
+    int64_t cta_count[2] = {0, 0};
+    int64_t cta_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int marchv_state = 0;          // k_march_vec: 0 not checked, 1 usable (every grid node carries the three dofs of ONE vector
                                    // field, the same in all its cells), 2 not usable
     // colouring (lazy)

@@ -37,6 +37,7 @@ struct MarchArgs {
                            //    => they are written with plain (bulk) stores; 0: everything is added
     const uint8_t* mapb;   // byte-packed offset map (fb2_map_build_bytes)
     const uint32_t* mapv;  // lane-major byte map of k_march_vec (fb2_map_build_vec)
+    const int32_t* ctalist; // optional: CTA blockIdx.x works on tile x chunk number ctalist[blockIdx.x] (launch over a subset)
     int dbg;               // measurement only (FB2_MVEC_DBG, results are wrong): 1 every piece as a bulk store, 2 no flush, 3 every piece as a reduce-add
     // cell of box position (x, y, z): x + nx (y + ny z) for grids in generate_grid order (cellmap == nullptr), else
     // cellmap[that] (-1 = no cell there).  Only cells with cell_lo <= id < cell_hi are assembled by this launch (the own cells
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 
     const int lane = threadIdx.x;
     const int lx = lane & 7, ly = lane >> 3;
-    int bid = blockIdx.x;
+    int bid = M.ctalist ? __ldg(M.ctalist + blockIdx.x) : (int)blockIdx.x;
     const int tx = bid % M.tiles_x;
     bid /= M.tiles_x;
     const int ty = bid % M.tiles_y, ch = bid / M.tiles_y;

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
 
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int bid = blockIdx.x;
+    int bid = M.ctalist ? __ldg(M.ctalist + blockIdx.x) : (int)blockIdx.x;
     const int tx = bid % M.tiles_x;
     bid /= M.tiles_x;
     const int ty = bid % M.tiles_y, ch = bid / M.tiles_y;

@@ -749,6 +749,57 @@ extern "C" int fb2_assemble_distributed(fb2_assembler* a, fb2_part* P, int mode,
         FB2_CUDA(cudaStreamWaitEvent(ctx->stream, P->ev_done, 0));
         return FB2_OK;
     }
+    // Marching kernels, exchange mode: the CTAs (tile x chunk) that hold interface cells run first; their columns are then
+    // complete on this rank, and pack / NCCL / unpack-add / mask run on the second stream while the other CTAs assemble
+    // (those touch no exchanged row or column).  FB2_MARCH_SPLIT=0 keeps the exchange behind ONE launch; FB2_MARCH_SPLIT=2
+    // splits the launch in every mode (tests of the CTA lists without a communicator).
+    const char* esplit = getenv("FB2_MARCH_SPLIT");
+    const int split_env = esplit ? atoi(esplit) : 1;
+    const bool can_split = marching && P->n_iface > 0 && P->n_iface < P->ncells_own && a->dh->grid->structured && !a->dh->grid->generated;
+    if (can_split && ((mode == FB2_DIST_EXCHANGE && P->nparts > 1 && ctx->nccl_comm && split_env != 0) || (split_env == 2 && mode != FB2_DIST_HALO))) {
+        fb2_asm_opts o = {1, FB2_SCATTER_ATOMIC, 0, 0};
+        if (opts) o = *opts;
+        const bool exchange = mode == FB2_DIST_EXCHANGE && P->nparts > 1 && ctx->nccl_comm;
+        // start_assemble's zero fill, then both parts may write tile-interior columns with plain stores
+        if (o.fillzero) {
+            FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+            if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)a->dh->ndofs * sizeof(double), ctx->stream));
+        }
+        a->march_overwrite = o.fillzero ? 1 : 0;
+        o.fillzero = 0;
+        a->cell_first = 0;
+        a->ncells_active = P->ncells_own;
+        a->march_iface = P->n_iface;
+        // part 1 (few CTAs) and the exchange behind it run on the second, high-priority stream NEXT TO part 2: launched one
+        // after the other on one stream, the small launch would leave most SMs idle for the length of a chunk
+        cudaStream_t main_stream = ctx->stream;
+        if (exchange) {
+            cudaEventRecord(P->ev_iface, main_stream);
+            cudaStreamWaitEvent(P->xstream, P->ev_iface, 0);
+            ctx->stream = P->xstream;
+        }
+        a->march_part = 1;
+        int rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, &o);
+        if (rc == FB2_OK && exchange) {
+            rc = fb2_partition_exchange(P, nzval_dev, f_dev);
+            if (rc == FB2_OK) rc = fb2_partition_mask_unowned(P, nzval_dev, f_dev);
+            if (rc == FB2_OK) cudaEventRecord(P->ev_done, P->xstream);
+        }
+        ctx->stream = main_stream;
+        if (rc == FB2_OK) {
+            a->march_part = 2;
+            rc = fb2_launch_assemble(a, element, params, params_bytes, u_dev, nzval_dev, f_dev, &o);
+        }
+        a->march_part = 0;
+        a->ncells_active = 0;
+        FB2_TRY(rc);
+        if (exchange) {
+            FB2_CUDA(cudaStreamWaitEvent(ctx->stream, P->ev_done, 0));
+            return FB2_OK;
+        }
+        if (mode == FB2_DIST_OWN_ONLY) return FB2_OK;
+        return fb2_partition_mask_unowned(P, nzval_dev, f_dev);
+    }
     if (mode != FB2_DIST_HALO) {   // own cells = local cells [0, ncells_own)
         a->cell_first = 0;
         a->ncells_active = P->ncells_own;

@@ -22,9 +22,14 @@ def main():
     torch.cuda.set_device(lr)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{lr}"))
     ctx = fb.default_context(lr)
-    if kind == "heat":
-        ct, nel, order, vdim, qo = fb.Hexahedron, (12, 9, 7), 1, 1, 2
+    if kind in ("heat", "heat_big"):
+        # heat_big: several tiles and chunks per rank, so that the split launch of the marching kernel has both parts
+        ct, nel, order, vdim, qo = fb.Hexahedron, ((12, 9, 7) if kind == "heat" else (40, 22, 26)), 1, 1, 2
         elem, oel, op = fb.HeatElement(1.5, 0.7), "heat", {"k": 1.5, "source": 0.7}
+    elif kind == "elasticity_q1":                 # k_march_vec on the cell-map path
+        ct, nel, order, vdim, qo = fb.Hexahedron, (22, 13, 20), 1, 3, 2
+        lam, mu = 10.0 * 0.3 / (1.3 * 0.4), 10.0 / 2.6
+        elem, oel, op = fb.ElasticityElement(lam=lam, mu=mu, b=(0.1, 0.2, -1.0)), "elasticity", {"lambda": lam, "mu": mu, "b": (0.1, 0.2, -1.0)}
     else:
         ct, nel, order, vdim, qo = fb.Hexahedron, (5, 4, 6), 2, 3, 3
         lam, mu = 10.0 * 0.3 / (1.3 * 0.4), 10.0 / 2.6

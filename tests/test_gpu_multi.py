@@ -17,7 +17,7 @@ def _ngpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("kind", ["heat", "elasticity"])
+@pytest.mark.parametrize("kind", ["heat", "heat_big", "elasticity", "elasticity_q1"])
 def test_nccl_exchange_matches_serial_oracle(tmp_path, kind):
     n = _ngpus()
     if n < 2:

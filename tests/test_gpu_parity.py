@@ -746,6 +746,46 @@ def test_partitioned_assembly_matches_serial_oracle(ctx, mode, ct, nel, order, v
     assert ok, nrm
 
 
+@pytest.mark.parametrize("nel,vdim,kind,p", [
+    ((19, 11, 10), 1, "heat", {"k": 1.3, "source": 0.6}),
+    ((21, 18, 13), 1, "heat", {"k": 1.0, "source": 1.0}),
+    ((11, 9, 10), 3, "elasticity", {"E": 10.0, "nu": 0.3, "b": (0.3, 0.0, -1.0)}),
+])
+def test_split_marching_launch_of_the_exchange_path(ctx, nel, vdim, kind, p, monkeypatch):
+    """exchange mode launches the CTAs with interface cells first and the others while the interface columns travel
+    (fb2_assemble_distributed); FB2_MARCH_SPLIT=2 runs the same two launches without a communicator: every rank's local
+    K, f must equal the single-launch result"""
+    hctx = fb.Context(-1)
+    ct = fb.Hexahedron
+    gg = fb.generate_grid(ct, nel, ctx=hctx).perturb(0.2)
+    ip = fb.Lagrange(ct, 1) ** vdim
+    gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+    cv = fb.CellValues(fb.QuadratureRule(ct, 2), ip)
+    elem, _ = make_element(kind, p)
+    for lz in ("", "2"):
+        if lz:
+            monkeypatch.setenv("FB2_MARCH_LZ", lz)
+        else:
+            monkeypatch.delenv("FB2_MARCH_LZ", raising=False)
+        for r in range(8):
+            pt = fb.Partition(gdh, 8, r)
+            lg, ldh = pt.local_problem(ctx)
+            K = fb.allocate_matrix(ldh)
+            f = ctx.zeros(ldh.ndofs)
+            a = fb.start_assemble(K, f)
+            pt.bind(a, cv)
+            monkeypatch.setenv("FB2_MARCH_SPLIT", "0")
+            K.nzval.fill_(7.0)
+            pt.assemble_(elem, mode="own")
+            assert fb.last_kernel() == ("k_march_hex" if vdim == 1 else "k_march_vec")
+            nz0, f0 = K.nzval.cpu().numpy().copy(), f.cpu().numpy().copy()
+            monkeypatch.setenv("FB2_MARCH_SPLIT", "2")
+            K.nzval.fill_(-5.0)
+            f.fill_(3.0)
+            pt.assemble_(elem, mode="own")
+            assert close(K.nzval.cpu().numpy(), nz0, 1e-13)[0] and close(f.cpu().numpy(), f0, 1e-13)[0], (r, lz)
+
+
 # ---- facet loop (SURVEY 8f-1): FacetValues + Neumann / traction term ------------------------------------------------
 @pytest.mark.parametrize("ct,nel,order,vdim,qo,kind,params,sets", [
     (fb.Hexahedron, (4, 3, 3), 1, 3, 2, "normal_traction", -0.1, ("top", "bottom", "front", "back")),
