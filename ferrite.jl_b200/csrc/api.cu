@@ -438,6 +438,7 @@ extern "C" int fb2_assembler_destroy(fb2_assembler* a) {
     cudaFree(a->d_mapv);
     cudaFree(a->d_cta_list[0]);
     cudaFree(a->d_cta_list[1]);
+    cudaFree(a->d_box_zcols);
     cudaFree(a->d_cmat);
     cudaFree(a->d_march_zcols);
     cudaFree(a->d_mapc);

@@ -340,9 +340,19 @@ bool marchv_usable(fb2_assembler* a) {
 
 // CTA lists of a split marching launch on a partition-local box (see fb2_assembler::march_part): list 0 = the CTAs (tile x
 // chunk) that hold an interface cell, list 1 = the other CTAs with own cells.  Built on the host from the cell map.
-int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y, int nchunks, int64_t ncells_own) {
+// chunk length of k_march_vec: about two dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 8
+// layers keep the share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
+void marchv_plan(const fb2_ctx* ctx, int tiles_x, int tiles_y, int nzl, int* lz, int* nchunks) {
+    const int64_t tiles = (int64_t)tiles_x * tiles_y, resident = (int64_t)ctx->sm_count * 2;
+    const int64_t want = std::max<int64_t>(1, (24 * resident + tiles - 1) / tiles);
+    *lz = (int)std::max<int64_t>(8, (nzl + want - 1) / want);
+    if (const char* e = getenv("FB2_MARCH_LZ")) *lz = std::max(1, atoi(e));
+    *nchunks = (nzl + *lz - 1) / *lz;
+}
+
+int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y, int nchunks, int64_t ncells_own, bool zero_list = false) {
     const fb2_grid* g = a->dh->grid;
-    const int64_t key[8] = {M.lz, M.nfull, M.lt, tile_x, tile_y, a->march_iface, ncells_own, nchunks};
+    const int64_t key[8] = {M.lz, M.nfull, M.lt, tile_x, tile_y, a->march_iface, ncells_own, nchunks + (zero_list ? ((int64_t)1 << 32) : 0)};
     if (a->d_cta_list[0] && memcmp(key, a->cta_key, sizeof(key)) == 0) return FB2_OK;
     FB2_CHECK(g->structured && !g->sv_cellmap.empty(), FB2_ERR_INTERNAL, "march_cta_lists: the grid has no cell map");
     const int64_t nx = g->sv_nel[0], ny = g->sv_nel[1], nz = g->sv_nel[2];
@@ -371,6 +381,47 @@ int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y
         FB2_CUDA(cudaMalloc(&a->d_cta_list[k], std::max<size_t>(list[k].size(), 1) * sizeof(int32_t)));
         FB2_CUDA(cudaMemcpy(a->d_cta_list[k], list[k].data(), list[k].size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         a->cta_count[k] = (int64_t)list[k].size();
+    }
+    // Columns that need start_assemble's zero fill when tile-interior columns are written with plain stores (three dofs per
+    // node, k_march_vec): every node that is NOT strictly inside a CTA (tile x chunk) with own cells -- nodes on tile faces,
+    // on the planes between chunks, and the nodes of regions without own cells (nobody writes their columns).
+    cudaFree(a->d_box_zcols);
+    a->d_box_zcols = nullptr;
+    a->box_nzcols = -1;
+    if (zero_list && a->dh->ndpc == 24) {
+        const fb2_dh* dh = a->dh;
+        std::vector<int32_t> zc;
+        for (int64_t z = 0; z <= nz; ++z) {
+            const int64_t zr = z - M.z0;
+            // strictly between the first and the last node plane of a chunk
+            const bool zin = zr > 0 && zr < M.z1 - M.z0 && zr % M.lz != 0;
+            for (int64_t y = 0; y <= ny; ++y)
+                for (int64_t x = 0; x <= nx; ++x) {
+                    // the node's dofs from any local cell around it; written by a plain store iff the node is strictly inside
+                    // a tile and a chunk and an own cell touches it (the kernel then holds a copy of its columns)
+                    int32_t cany = -1;
+                    int lnany = 0;
+                    bool own_touch = false;
+                    for (int dz = 0; dz < 2; ++dz)
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int64_t cx = x - dx, cy = y - dy, cz = z - dz;
+                                if (cx < 0 || cy < 0 || cz < 0 || cx >= nx || cy >= ny || cz >= nz) continue;
+                                const int32_t c = g->sv_cellmap[(size_t)(cx + nx * (cy + ny * cz))];
+                                if (c < 0) continue;
+                                if (cany < 0) { cany = c; lnany = fb2_hexnode(dx, dy, dz); }
+                                if (c < ncells_own) own_touch = true;
+                            }
+                    if (cany < 0) continue;
+                    const bool stored = zin && own_touch && x % tile_x != 0 && y % tile_y != 0;
+                    if (stored) continue;
+                    for (int k = 0; k < 3; ++k) zc.push_back(dh->cell_dofs[(size_t)cany * 24 + lnany * 3 + k]);
+                }
+        }
+        std::sort(zc.begin(), zc.end());
+        FB2_CUDA(cudaMalloc(&a->d_box_zcols, std::max<size_t>(zc.size(), 1) * sizeof(int32_t)));
+        FB2_CUDA(cudaMemcpy(a->d_box_zcols, zc.data(), zc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        a->box_nzcols = (int64_t)zc.size();
     }
     memcpy(a->cta_key, key, sizeof(key));
     return FB2_OK;
@@ -420,14 +471,9 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
     if (smem > 113 * 1024 || M.cap >= 65536) return FB2_OK;
     FB2_TRY(fb2_map_build_vec(a));
     M.mapv = a->d_mapv;
-    // chunk length: about two dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 8 layers keep the
-    // share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
-    const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 2;
-    const int nzl = M.z1 - M.z0;
-    const int64_t want = std::max<int64_t>(1, (24 * resident + tiles - 1) / tiles);
-    M.lz = (int)std::max<int64_t>(8, (nzl + want - 1) / want);
-    if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
-    const int nchunks = (nzl + M.lz - 1) / M.lz;
+    const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y;
+    int nchunks = 1;
+    marchv_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &nchunks);
     A.p[5] = 0.125 * cv->w[0];   // the common quadrature weight / 8
     if (const char* e = getenv("FB2_MVEC_DBG")) M.dbg = atoi(e);
     // FB2_MVEC_FLUSH=thread: flush with coalesced per-thread stores / REDs instead of the TMA engine (A/B measurement)
@@ -457,7 +503,7 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
     if (a->march_part != 0 && !gen) {   // split launch of the partitioned exchange path
         M.nfull = 0;
         M.lt = M.lz;
-        FB2_TRY(march_cta_lists(a, M, 4, 4, nchunks, A.cell_first + A.ncount));
+        FB2_TRY(march_cta_lists(a, M, 4, 4, nchunks, A.cell_first + A.ncount, true));
         M.ctalist = a->d_cta_list[a->march_part - 1];
         nctas = a->cta_count[a->march_part - 1];
     }
@@ -700,6 +746,35 @@ int fb2_warplist_build(fb2_assembler* a) {
     FB2_CUDA(cudaMalloc(&a->d_wcount, count.size()));
     FB2_CUDA(cudaMemcpy(a->d_wfirst, first.data(), first.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     FB2_CUDA(cudaMemcpy(a->d_wcount, count.data(), count.size(), cudaMemcpyHostToDevice));
+    return FB2_OK;
+}
+
+int fb2_march_split_zero_fill(fb2_assembler* a, int element, int64_t ncells_own, double* nzval_dev, bool* done) {
+    *done = false;
+    const char* ez = getenv("FB2_MARCH_ZSEL");
+    if (element != FB2_ELEM_ELASTICITY || (ez && atoi(ez) == 0) || !marchv_static_ok(a)) return FB2_OK;
+    fb2_grid* g = a->dh->grid;
+    fb2_ctx* ctx = g->ctx;
+    if (g->generated || !g->structured || a->dh->ndofs >= (int64_t)1 << 31 || (reinterpret_cast<uintptr_t>(nzval_dev) & 15) != 0) return FB2_OK;
+    // the same tiles and chunks as try_march_vec will use for the own cells of the box
+    MarchArgs M;
+    memset(&M, 0, sizeof(M));
+    M.nx = (int)g->sv_nel[0];
+    M.ny = (int)g->sv_nel[1];
+    M.z0 = 0;
+    M.z1 = (int)g->sv_nel[2];
+    M.tiles_x = (M.nx + 3) / 4;
+    M.tiles_y = (M.ny + 3) / 4;
+    int nchunks = 1;
+    marchv_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &nchunks);
+    M.lt = M.lz;
+    FB2_TRY(march_cta_lists(a, M, 4, 4, nchunks, ncells_own, true));
+    if (a->box_nzcols < 0) return FB2_OK;
+    if (a->box_nzcols > 0)
+        k_zero_columns<<<(unsigned)((a->box_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_box_zcols, a->box_nzcols, a->pat->d_colptr, nzval_dev);
+    ctx->launches++;
+    FB2_CUDA(cudaGetLastError());
+    *done = true;
     return FB2_OK;
 }
 

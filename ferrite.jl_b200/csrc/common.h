@@ -221,6 +221,8 @@ struct fb2_assembler {
     int march_overwrite = 0;       // part 2: nzval was zero-filled in front of part 1 (plain stores for tile-interior columns allowed)
     int64_t march_iface = 0;       // cells [0, march_iface) of the local grid are the interface cells
     int32_t* d_cta_list[2] = {nullptr, nullptr};
+    int32_t* d_box_zcols = nullptr;   // k_march_vec on a partition-local box: columns that need start_assemble's zero fill (see
+    int64_t box_nzcols = -1;          // fb2_march_split_zero_fill), built with the CTA lists; -1 = none
     int64_t cta_count[2] = {0, 0};
     int64_t cta_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int marchv_state = 0;          // k_march_vec: 0 not checked, 1 usable (every grid node carries the three dofs of ONE vector
@@ -308,6 +310,9 @@ int fb2_map_build_packed(fb2_assembler* a);
 int fb2_map_build_bytes(fb2_assembler* a);
 int fb2_map_build_cellmajor(fb2_assembler* a);
 int fb2_map_build_vec(fb2_assembler* a);
+// zero fill of nzval in front of a split marching launch (fb2_assemble_distributed): column-wise where the kernel allows it
+// (*done = true), else the caller runs a memset
+int fb2_march_split_zero_fill(fb2_assembler* a, int element, int64_t ncells_own, double* nzval_dev, bool* done);
 int fb2_tiles_build(fb2_assembler* a, int TC);
 int fb2_warplist_build(fb2_assembler* a);
 int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_t params_bytes, const double* u_dev,

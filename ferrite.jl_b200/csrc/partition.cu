@@ -761,8 +761,11 @@ extern "C" int fb2_assemble_distributed(fb2_assembler* a, fb2_part* P, int mode,
         if (opts) o = *opts;
         const bool exchange = mode == FB2_DIST_EXCHANGE && P->nparts > 1 && ctx->nccl_comm;
         // start_assemble's zero fill, then both parts may write tile-interior columns with plain stores
+        a->march_iface = P->n_iface;
         if (o.fillzero) {
-            FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
+            bool done = false;   // column-wise where the kernel writes the other columns with plain stores
+            FB2_TRY(fb2_march_split_zero_fill(a, element, P->ncells_own, nzval_dev, &done));
+            if (!done) FB2_CUDA(cudaMemsetAsync(nzval_dev, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
             if (f_dev) FB2_CUDA(cudaMemsetAsync(f_dev, 0, (size_t)a->dh->ndofs * sizeof(double), ctx->stream));
         }
         a->march_overwrite = o.fillzero ? 1 : 0;

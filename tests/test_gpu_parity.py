@@ -1272,7 +1272,8 @@ def test_config_c1_quad_100x100_entrywise_with_apply(ctx):
     assert np.linalg.norm(u - ou) <= 1e-10 * np.linalg.norm(ou)
 
 
-@pytest.mark.parametrize("kind,nel,vdim", [("heat", (64, 64, 64), 1), ("elasticity", (32, 32, 32), 3), ("heat", (96, 40, 72), 1)])
+@pytest.mark.parametrize("kind,nel,vdim", [("heat", (64, 64, 64), 1), ("elasticity", (32, 32, 32), 3), ("heat", (96, 40, 72), 1),
+                                           ("elasticity", (45, 38, 41), 3)])
 def test_large_entrywise_against_the_c_port(ctx, kind, nel, vdim):
     """Entry-wise nzval / f at sizes the numpy oracle does not reach: the C restatement of the reference loop
     (oracle/cpu_assemble.c, itself checked against the numpy oracle in tests/test_oracle_goldens.py) is the checker.
