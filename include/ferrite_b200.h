@@ -83,8 +83,10 @@ typedef struct {
     int variant;      /* 0 = default kernel for the element.  >0 = measured alternatives, all parity-tested:
                          1 DFMA block kernel, 2 unrolled quadrature loop, 4 branch-free scatter, 5 tile kernel,
                          6 x+y face merge, 7 no sector pairing, 8 warp-specialised groups, 9 coordinates in shared
-                         memory, 12 zero fill overlapped with the assembly; 20 / 21 are measurement-only (wrong results):
-                         integration without scatter / scatter without integration */
+                         memory, 12 zero fill overlapped with the assembly; 30 / 32 the thread-per-cell / warp-per-cell kernel
+                         where a marching-tile kernel (k_march_hex / k_march_vec) is the default, 31 table-driven integration
+                         inside k_march_hex; 20 / 21 are measurement-only (wrong results): integration without scatter /
+                         scatter without integration */
     int reserved;
 } fb2_asm_opts;
 
