@@ -443,7 +443,7 @@ bool marchv_static_ok(fb2_assembler* a) {
 
 // Isotropic elasticity on trilinear hexahedra of a structured grid: the marching-tile kernel k_march_vec.  *handled = false
 // when it does not apply (the caller falls back to k_cell_syrk).
-int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bool* handled) {
+int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bool* handled, bool general = false) {
     *handled = false;
     fb2_grid* g = a->dh->grid;
     const fb2_cv* cv = a->cv;
@@ -479,8 +479,11 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
     // FB2_MVEC_FLUSH=thread: flush with coalesced per-thread stores / REDs instead of the TMA engine (A/B measurement)
     const char* ef = getenv("FB2_MVEC_FLUSH");
     const bool tmaf = !(ef && strcmp(ef, "thread") == 0);
-    auto k = tmaf ? (a->map_complete ? k_march_vec<false, true> : k_march_vec<true, true>)
-                  : (a->map_complete ? k_march_vec<false, false> : k_march_vec<true, false>);
+    auto k = general ? (a->map_complete ? k_march_vec<false, true, true> : k_march_vec<true, true, true>)
+             : tmaf  ? (a->map_complete ? k_march_vec<false, true, false> : k_march_vec<true, true, false>)
+                     : (a->map_complete ? k_march_vec<false, false, false> : k_march_vec<true, false, false>);
+    MarchCmat CM;
+    memcpy(CM.c, a->h_cmat, sizeof(CM.c));
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // start_assemble's zero fill of nzval, if still owed: only the columns that receive reduce-adds need it (nodes on tile
@@ -507,7 +510,7 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
         M.ctalist = a->d_cta_list[a->march_part - 1];
         nctas = a->cta_count[a->march_part - 1];
     }
-    if (nctas > 0) k<<<(unsigned)nctas, 128, smem, ctx->stream>>>(A, M);
+    if (nctas > 0) k<<<(unsigned)nctas, 128, smem, ctx->stream>>>(A, M, CM);
     g_fb2_last_kernel = "k_march_vec";
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
@@ -752,7 +755,7 @@ int fb2_warplist_build(fb2_assembler* a) {
 int fb2_march_split_zero_fill(fb2_assembler* a, int element, int64_t ncells_own, double* nzval_dev, bool* done) {
     *done = false;
     const char* ez = getenv("FB2_MARCH_ZSEL");
-    if (element != FB2_ELEM_ELASTICITY || (ez && atoi(ez) == 0) || !marchv_static_ok(a)) return FB2_OK;
+    if ((element != FB2_ELEM_ELASTICITY && element != FB2_ELEM_ELASTICITY_GENERAL) || (ez && atoi(ez) == 0) || !marchv_static_ok(a)) return FB2_OK;
     fb2_grid* g = a->dh->grid;
     fb2_ctx* ctx = g->ctx;
     if (g->generated || !g->structured || a->dh->ndofs >= (int64_t)1 << 31 || (reinterpret_cast<uintptr_t>(nzval_dev) & 15) != 0) return FB2_OK;
@@ -796,7 +799,7 @@ int fb2_map_build_vec(fb2_assembler* a) {
 bool fb2_march_applicable(fb2_assembler* a, int element, const fb2_asm_opts* opts) {
     const fb2_cv* cv = a->cv;
     const fb2_grid* g = a->dh->grid;
-    if (cv && element == FB2_ELEM_ELASTICITY)
+    if (cv && (element == FB2_ELEM_ELASTICITY || element == FB2_ELEM_ELASTICITY_GENERAL))
         return !(opts && (opts->scatter_mode != FB2_SCATTER_ATOMIC || opts->variant != 0)) && marchv_static_ok(a);
     if (!cv || !(element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS)) return false;
     if (opts && (opts->scatter_mode != FB2_SCATTER_ATOMIC || !(opts->variant == 0 || opts->variant == 31))) return false;
@@ -865,7 +868,7 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
     // only the marching-tile kernel (Q1 hexahedra, heat / mass, default variant) takes the fill over
     const bool may_fuse = atomic && ct == FB2_HEXAHEDRON && nbs == 8 && cv->nq == 8 &&
                           (((element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS) && (variant == 0 || variant == 31) && vdim == 1) ||
-                           (element == FB2_ELEM_ELASTICITY && variant == 0 && vdim == 3));
+                           ((element == FB2_ELEM_ELASTICITY || element == FB2_ELEM_ELASTICITY_GENERAL) && variant == 0 && vdim == 3));
     if (!may_fuse) FB2_TRY(pay_zero_fill(a, A));
     switch (element) {
         case FB2_ELEM_HEAT:
@@ -891,6 +894,12 @@ static int launch_one(fb2_assembler* a, AsmArgs& A, int element, bool atomic, in
             return dispatch_blocks<FB2_ELEM_ELASTICITY, 1>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_ELASTICITY_GENERAL:
             FB2_CHECK(vdim == cv->rdim, FB2_ERR_BAD_ARG, "the elasticity element needs a vector field with as many components as space dimensions");
+            if (variant == 0 && atomic) {   // structured trilinear hexahedra: the marching-tile kernel with C as an argument
+                bool handled = false;
+                rc = try_march_vec(a, ctx, A, accumulate, &handled, true);
+                if (rc != FB2_OK || handled) return rc;
+            }
+            FB2_TRY(pay_zero_fill(a, A));
             return dispatch_blocks<FB2_ELEM_ELASTICITY_GENERAL, 1>(a, ctx, A, atomic, ct, nbs, vdim);
         case FB2_ELEM_NEOHOOKE:
             FB2_CHECK(A.u != nullptr, FB2_ERR_BAD_ARG, "the Neo-Hooke element needs the current solution u");
@@ -957,6 +966,7 @@ int fb2_launch_assemble(fb2_assembler* a, int element, const void* params, size_
                                       FB2_ERR_BAD_ARG, "general elasticity: C lacks the minor symmetries at (%d,%d,%d,%d)", i + 1, j + 1, k + 1, l + 1);
                         }
             if (!a->d_cmat) FB2_CUDA(cudaMalloc(&a->d_cmat, 81 * sizeof(double)));
+            memcpy(a->h_cmat, p.C, sizeof(a->h_cmat));
             FB2_CUDA(cudaMemcpyAsync(a->d_cmat, p.C, 81 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             FB2_CUDA(cudaStreamSynchronize(ctx->stream));   // p lives on this stack frame
             A.cmat = a->d_cmat;

@@ -211,6 +211,7 @@ struct fb2_assembler {
     int32_t* d_dofc = nullptr;     // cell-major dofs for the CTA kernels: [ncells][n] (built with d_mapc)
     int64_t* d_basec = nullptr;    //   and their column bases colptr[dof]
     double* d_cmat = nullptr;      // stiffness tensor of FB2_ELEM_ELASTICITY_GENERAL (81 doubles, lazy)
+    double h_cmat[81] = {};        //   and its host copy (k_march_vec takes it as a kernel argument)
     uint8_t* d_mapb = nullptr;     // byte-packed copy for the marching-tile kernel: [ceil(n*n/16)][ncells_pad][16] (lazy)
     uint16_t* d_map8 = nullptr;    // packed copy for the thread-per-cell kernels: [ceil(n*n/8)][ncells_pad][8] (lazy)
     uint32_t* d_mapv = nullptr;    // lane-major byte map of k_march_vec: [ncells][5][32] words (lazy)

@@ -288,8 +288,12 @@ __device__ __forceinline__ void fb2_mvec_flush_tma(const AsmArgs& A, const doubl
 
 // A.p: [0] lambda, [1] mu, [2..4] body force, [5] w / 8 (the common weight of the 2 x 2 x 2 Gauss rule; the host checks that
 // the CellValues holds the tables of QuadratureRule{RefHexahedron}(2) + Lagrange{RefHexahedron,1}).
-template <bool CHECK, bool TMAF>
-__global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const MarchArgs M) {
+// GENERAL: any stiffness tensor with the minor symmetries (FB2_ELEM_ELASTICITY_GENERAL, linear_elasticity.jl:266-281):
+// Ke[(a,c),(b,d)] = sum_qs C[c][q][d][s] H_ab[q][s], still lane-local; C travels as a kernel argument (constant bank operands).
+struct MarchCmat { double c[81]; };
+
+template <bool CHECK, bool TMAF, bool GENERAL>
+__global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const MarchArgs M, const MarchCmat CM) {
     constexpr int CS = MV_CS;
     constexpr double NA = fb2_q1n(0, 0), NB = fb2_q1n(1, 0);   // 1-D shape function of the near / far node of a Gauss point
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -596,8 +600,17 @@ __global__ void __launch_bounds__(128, 2) k_march_vec(const AsmArgs A, const Mar
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             const int tt = (bs * 3 + d) * 3 + c;
-                            double val = fma(lam, acc[c][d][bs], mu * acc[d][c][bs]);
-                            if (c == d) val += mtr;
+                            double val;
+                            if constexpr (GENERAL) {
+                                val = 0.0;
+#pragma unroll
+                                for (int q = 0; q < 3; ++q)
+#pragma unroll
+                                    for (int r = 0; r < 3; ++r) val = fma(CM.c[((c * 3 + q) * 3 + d) * 3 + r], acc[q][r][bs], val);
+                            } else {
+                                val = fma(lam, acc[c][d][bs], mu * acc[d][c][bs]);
+                                if (c == d) val += mtr;
+                            }
                             v[tt] = val;
                             const unsigned off = (mp[tt >> 2] >> (8 * (tt & 3))) & 0xFFu;
                             sl[tt] = cb[bs][d] + (int)off;

@@ -1297,8 +1297,8 @@ def test_large_entrywise_against_the_c_port(ctx, kind, nel, vdim):
     assert ok, nrm
 
 
-@pytest.mark.parametrize("ct,nel,order,qo", [(fb.Hexahedron, (5, 4, 3), 1, 2), (fb.Hexahedron, (3, 2, 2), 2, 3), (fb.Tetrahedron, (3, 3, 2), 2, 4),
-                                              (fb.Quadrilateral, (7, 5), 1, 2), (fb.Triangle, (5, 4), 2, 3)])
+@pytest.mark.parametrize("ct,nel,order,qo", [(fb.Hexahedron, (5, 4, 3), 1, 2), (fb.Hexahedron, (13, 9, 10), 1, 2), (fb.Hexahedron, (3, 2, 2), 2, 3),
+                                              (fb.Tetrahedron, (3, 3, 2), 2, 4), (fb.Quadrilateral, (7, 5), 1, 2), (fb.Triangle, (5, 4), 2, 3)])
 def test_general_stiffness_tensor_elasticity(ctx, ct, nel, order, qo):
     """FB2_ELEM_ELASTICITY_GENERAL: any SymmetricTensor{4} C (linear_elasticity.jl:266-281, benchmark/helper.jl:249-262).  An
     orthotropic C against the oracle's einsum restatement, and the isotropic C must reproduce the tensor-core SYRK element."""
@@ -1322,10 +1322,18 @@ def test_general_stiffness_tensor_elasticity(ctx, ct, nel, order, qo):
     K, oK = fb.allocate_matrix(dh), O.allocate_matrix(odh)
     f, of = ctx.zeros(dh.ndofs), np.zeros(odh.ndofs)
     fb.assemble_(fb.start_assemble(K, f), fb.GeneralElasticityElement(C4, bf), cv)
+    if ct == fb.Hexahedron and order == 1:       # structured trilinear hexahedra: the marching-tile kernel takes C as an argument
+        assert fb.last_kernel() == "k_march_vec"
     O.assemble_global(odh, ocv, oK, of, "elasticity_general", {"C": C4, "b": bf})
     ok, nrm = close(K.nzval.cpu().numpy(), oK.nzval)
     assert ok, nrm
     assert close(f.cpu().numpy(), of)[0]
+    if ct == fb.Hexahedron and order == 1:       # and the block kernel gives the same matrix
+        a1 = fb.start_assemble(K, f)
+        a1.variant = 1
+        fb.assemble_(a1, fb.GeneralElasticityElement(C4, bf), cv)
+        assert fb.last_kernel() == "k_cell_blocks"
+        assert close(K.nzval.cpu().numpy(), oK.nzval)[0] and close(f.cpu().numpy(), of)[0]
     # isotropic C == ElasticityElement
     lam, mu = O.lame(10.0, 0.3)
     fb.assemble_(fb.start_assemble(K, f), fb.GeneralElasticityElement(O.isotropic_stiffness(lam, mu, dim), bf), cv)
