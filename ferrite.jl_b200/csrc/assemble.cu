@@ -275,8 +275,9 @@ bool march_usable(fb2_assembler* a) {
 }
 
 // Columns the marching-tile kernel adds to with reduce-adds (see k_march_mark), as a sorted device list; cached per chunk length.
-int march_zero_list(fb2_assembler* a, int lz, int tx = 8, int ty = 4, int vdim = 1) {
-    if (a->d_march_zcols && a->march_zlz == lz) return FB2_OK;
+int march_zero_list(fb2_assembler* a, int lz, int tx = 8, int ty = 4, int vdim = 1, int nfull = 1 << 30, int lt = 1) {
+    const int zkey = lz + 1024 * lt + (nfull < 1024 ? nfull << 20 : 0);
+    if (a->d_march_zcols && a->march_zlz == zkey) return FB2_OK;
     const fb2_dh* dh = a->dh;
     const fb2_grid* g = dh->grid;
     fb2_ctx* ctx = g->ctx;
@@ -296,7 +297,7 @@ int march_zero_list(fb2_assembler* a, int lz, int tx = 8, int ty = 4, int vdim =
     if (e == cudaSuccess) e = cudaMalloc(&d_num, sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_flag, 0, (size_t)nd, st);
     if (e == cudaSuccess) {
-        k_march_mark<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dh->d_cell_dofs, g->ncells_pad, nx, ny, nz, lz, tx, ty, vdim, d_flag);
+        k_march_mark<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(dh->d_cell_dofs, g->ncells_pad, nx, ny, nz, lz, std::min(nfull, nz / std::max(lz, 1) + 1), lt, tx, ty, vdim, d_flag);
         cub::CountingInputIterator<int32_t> ids(0);
         e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, d_flag, d_out, d_num, (int)nd, st);
         if (e == cudaSuccess) e = cudaMalloc(&d_tmp, tmp_bytes);
@@ -309,7 +310,7 @@ int march_zero_list(fb2_assembler* a, int lz, int tx = 8, int ty = 4, int vdim =
     cudaFree(d_flag); cudaFree(d_out); cudaFree(d_num); cudaFree(d_tmp);
     if (e != cudaSuccess) return fb2_fail(FB2_ERR_CUDA, "march_zero_list: %s", cudaGetErrorString(e));
     ctx->launches += 2;
-    a->march_zlz = lz;
+    a->march_zlz = zkey;
     a->march_nzcols = num;
     return FB2_OK;
 }
@@ -340,6 +341,31 @@ bool marchv_usable(fb2_assembler* a) {
 
 // CTA lists of a split marching launch on a partition-local box (see fb2_assembler::march_part): list 0 = the CTAs (tile x
 // chunk) that hold an interface cell, list 1 = the other CTAs with own cells.  Built on the host from the cell map.
+// Chunks of k_march_hex: about a dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 4 layers keep the
+// share of first / last planes (reduce-adds instead of stores) small (FB2_MARCH_LZ overrides).  CTAs of equal length run in
+// synchronised waves, and the last, partly filled wave costs a whole chunk time (4 % of the launch on a 201 x 200 x 200 box:
+// 10.56 waves of 20 layers): the last ~15 % of the layers are cut into chunks of a third of the length (first nfull chunks:
+// lz layers, then lt).  FB2_MARCH_LT (tests) forces short chunks behind the first half of the full ones.
+void marchh_plan(const fb2_ctx* ctx, int tiles_x, int tiles_y, int nzl, int* lz, int* nfull, int* lt, int* nchunks) {
+    const int64_t tiles = (int64_t)tiles_x * tiles_y, resident = (int64_t)ctx->sm_count * 8;
+    const int64_t want = std::max<int64_t>(1, 12 * resident / tiles);
+    *lz = (int)std::max<int64_t>(4, (nzl + want - 1) / want);
+    if (const char* e = getenv("FB2_MARCH_LZ")) *lz = std::max(1, atoi(e));
+    *nchunks = (nzl + *lz - 1) / *lz;
+    *nfull = *nchunks;
+    *lt = *lz;
+    if (!getenv("FB2_MARCH_LZ") && *nchunks >= 4 && *lz >= 12) {
+        *nfull = std::max(1, (int)(0.85 * nzl / *lz));
+        *lt = std::max(4, *lz / 3);
+        *nchunks = *nfull + (nzl - *nfull * *lz + *lt - 1) / *lt;
+    }
+    if (const char* e = getenv("FB2_MARCH_LT")) {
+        *nfull = std::max(1, ((nzl + *lz - 1) / *lz) / 2);
+        *lt = std::min(*lz, std::max(1, atoi(e)));
+        *nchunks = *nfull + (std::max(0, nzl - *nfull * *lz) + *lt - 1) / *lt;
+    }
+}
+
 // chunk length of k_march_vec: about two dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 8
 // layers keep the share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
 void marchv_plan(const fb2_ctx* ctx, int tiles_x, int tiles_y, int nzl, int* lz, int* nchunks) {
@@ -388,13 +414,15 @@ int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y
     cudaFree(a->d_box_zcols);
     a->d_box_zcols = nullptr;
     a->box_nzcols = -1;
-    if (zero_list && a->dh->ndpc == 24) {
+    if (zero_list && (a->dh->ndpc == 24 || a->dh->ndpc == 8)) {
+        const int vd = a->dh->ndpc / 8;
         const fb2_dh* dh = a->dh;
         std::vector<int32_t> zc;
         for (int64_t z = 0; z <= nz; ++z) {
             const int64_t zr = z - M.z0;
             // strictly between the first and the last node plane of a chunk
-            const bool zin = zr > 0 && zr < M.z1 - M.z0 && zr % M.lz != 0;
+            const int64_t zt = zr - (int64_t)M.nfull * M.lz;
+            const bool zin = zr > 0 && zr < M.z1 - M.z0 && ((M.nfull <= 0 || zt <= 0) ? zr % M.lz != 0 : zt % M.lt != 0);
             for (int64_t y = 0; y <= ny; ++y)
                 for (int64_t x = 0; x <= nx; ++x) {
                     // the node's dofs from any local cell around it; written by a plain store iff the node is strictly inside
@@ -415,7 +443,7 @@ int march_cta_lists(fb2_assembler* a, const MarchArgs& M, int tile_x, int tile_y
                     if (cany < 0) continue;
                     const bool stored = zin && own_touch && x % tile_x != 0 && y % tile_y != 0;
                     if (stored) continue;
-                    for (int k = 0; k < 3; ++k) zc.push_back(dh->cell_dofs[(size_t)cany * 24 + lnany * 3 + k]);
+                    for (int k = 0; k < vd; ++k) zc.push_back(dh->cell_dofs[(size_t)cany * 8 * vd + lnany * vd + k]);
                 }
         }
         std::sort(zc.begin(), zc.end());
@@ -495,7 +523,7 @@ int try_march_vec(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, int accumulate, bo
             FB2_TRY(march_zero_list(a, M.lz, 4, 4, 3));
             if (a->march_nzcols > 0)
                 k_zero_columns<<<(unsigned)((a->march_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_march_zcols, a->march_nzcols,
-                                                                                              a->pat->d_colptr, A.nzval);
+                                                                                              a->pat->d_colptr, A.nzval, a->pat->nnz);
             ctx->launches++;
             A.zero_pending = 0;
         } else {
@@ -577,30 +605,9 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
             if (smem <= 100 * 1024 && M.cap < 65536 && a->pat->max_col_len < 255 && (reinterpret_cast<uintptr_t>(A.nzval) & 15) == 0) {
                 FB2_TRY(fb2_map_build_bytes(a));
                 M.mapb = a->d_mapb;
-                // chunk length: about a dozen CTAs per resident slot keep the tail of the launch short; chunks of >= 4
-                // layers keep the share of first / last planes (reduce-adds instead of stores) small.  FB2_MARCH_LZ overrides (tuning).
-                const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y, resident = (int64_t)ctx->sm_count * 8;
-                const int nzl = M.z1 - M.z0;
-                const int64_t want = std::max<int64_t>(1, 12 * resident / tiles);
-                M.lz = (int)std::max<int64_t>(4, (nzl + want - 1) / want);
-                if (const char* e = getenv("FB2_MARCH_LZ")) M.lz = std::max(1, atoi(e));
-                int nchunks = (nzl + M.lz - 1) / M.lz;
-                M.nfull = nchunks;
-                M.lt = M.lz;
-                // CTAs of equal length run in synchronised waves, and the last, partly filled wave costs a whole chunk time
-                // (4 % of the launch on a 201 x 200 x 200 box: 10.56 waves of 20 layers): the last ~15 % of the layers are cut
-                // into chunks of a third of the length.  Not with the column-wise zero fill, whose list assumes uniform chunks.
-                const char* ezs = getenv("FB2_MARCH_ZSEL");
-                if (!getenv("FB2_MARCH_LZ") && !(ezs && atoi(ezs) == 1) && nchunks >= 4 && M.lz >= 12) {
-                    M.nfull = std::max(1, (int)(0.85 * nzl / M.lz));
-                    M.lt = std::max(4, M.lz / 3);
-                    nchunks = M.nfull + (nzl - M.nfull * M.lz + M.lt - 1) / M.lt;
-                }
-                if (const char* e = getenv("FB2_MARCH_LT")) {   // tests: force short chunks behind the first half of the full ones
-                    M.nfull = std::max(1, ((nzl + M.lz - 1) / M.lz) / 2);
-                    M.lt = std::min(M.lz, std::max(1, atoi(e)));
-                    nchunks = M.nfull + (std::max(0, nzl - M.nfull * M.lz) + M.lt - 1) / M.lt;
-                }
+                const int64_t tiles = (int64_t)M.tiles_x * M.tiles_y;
+                int nchunks = 1;
+                marchh_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &M.nfull, &M.lt, &nchunks);
                 // variant 31: table-driven integration inside the marching kernel (A/B against the analytic element)
                 const bool analytic = ELEM == FB2_ELEM_HEAT && variant != 31 && cv_is_q1hex_gauss2(a->cv);
                 if (analytic) A.p[2] = 0.125 * a->cv->w[0];   // the common quadrature weight / 8 (see fb2_hex8_heat)
@@ -610,15 +617,16 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 // eight single-warp CTAs per SM need 8 x 28 KB: ask for the full shared-memory carveout
                 FB2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 // start_assemble's zero fill of nzval, if still owed.  Only the columns that receive reduce-adds need it
-                // (38 % of nzval on C2), but zeroing those 3.1 M separate columns (FB2_MARCH_ZSEL=1, k_zero_columns) takes as
-                // long as one memset over everything (0.23 vs 0.24 ms, profiles/r02_launches_c2.csv), so the memset stays.
+                // (38 % of nzval on C2: nodes on tile faces and on the planes between chunks).  Zeroed column by column this
+                // took as long as the memset over everything (0.28 vs 0.30 ms); as runs of adjacent columns rounded to whole
+                // 32-byte sectors (k_zero_columns) it takes 0.22 ms: C2 step 1.93 -> 1.85 ms.  FB2_MARCH_ZSEL=0 keeps the memset.
                 if (A.zero_pending) {
                     const char* ez = getenv("FB2_MARCH_ZSEL");
-                    if (ez && atoi(ez) == 1 && gen && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
-                        FB2_TRY(march_zero_list(a, M.lz));
+                    if (!(ez && atoi(ez) == 0) && gen && M.z0 == 0 && M.z1 == g->nel[2] && a->dh->ndofs < (int64_t)1 << 31) {
+                        FB2_TRY(march_zero_list(a, M.lz, 8, 4, 1, M.nfull, M.lt));
                         if (a->march_nzcols > 0)
                             k_zero_columns<<<(unsigned)((a->march_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_march_zcols, a->march_nzcols,
-                                                                                                          a->pat->d_colptr, A.nzval);
+                                                                                                          a->pat->d_colptr, A.nzval, a->pat->nnz);
                         ctx->launches++;
                     } else {
                         FB2_CUDA(cudaMemsetAsync(A.nzval, 0, (size_t)a->pat->nnz * sizeof(double), ctx->stream));
@@ -627,7 +635,7 @@ int launch_tiles_or_cells(fb2_assembler* a, fb2_ctx* ctx, AsmArgs& A, bool atomi
                 }
                 int64_t nctas = tiles * nchunks;
                 if (a->march_part != 0 && !gen) {   // split launch of the partitioned exchange path
-                    FB2_TRY(march_cta_lists(a, M, 8, 4, nchunks, A.cell_first + A.ncount));
+                    FB2_TRY(march_cta_lists(a, M, 8, 4, nchunks, A.cell_first + A.ncount, true));
                     M.ctalist = a->d_cta_list[a->march_part - 1];
                     nctas = a->cta_count[a->march_part - 1];
                 }
@@ -755,26 +763,31 @@ int fb2_warplist_build(fb2_assembler* a) {
 int fb2_march_split_zero_fill(fb2_assembler* a, int element, int64_t ncells_own, double* nzval_dev, bool* done) {
     *done = false;
     const char* ez = getenv("FB2_MARCH_ZSEL");
-    if ((element != FB2_ELEM_ELASTICITY && element != FB2_ELEM_ELASTICITY_GENERAL) || (ez && atoi(ez) == 0) || !marchv_static_ok(a)) return FB2_OK;
+    if (ez && atoi(ez) == 0) return FB2_OK;
+    const bool vec = element == FB2_ELEM_ELASTICITY || element == FB2_ELEM_ELASTICITY_GENERAL;
+    const bool scalar = element == FB2_ELEM_HEAT || element == FB2_ELEM_MASS;
+    if (vec ? !marchv_static_ok(a) : !(scalar && fb2_march_applicable(a, element, nullptr))) return FB2_OK;
     fb2_grid* g = a->dh->grid;
     fb2_ctx* ctx = g->ctx;
     if (g->generated || !g->structured || a->dh->ndofs >= (int64_t)1 << 31 || (reinterpret_cast<uintptr_t>(nzval_dev) & 15) != 0) return FB2_OK;
-    // the same tiles and chunks as try_march_vec will use for the own cells of the box
+    // the same tiles and chunks as the launch will use for the own cells of the box
     MarchArgs M;
     memset(&M, 0, sizeof(M));
     M.nx = (int)g->sv_nel[0];
     M.ny = (int)g->sv_nel[1];
     M.z0 = 0;
     M.z1 = (int)g->sv_nel[2];
-    M.tiles_x = (M.nx + 3) / 4;
-    M.tiles_y = (M.ny + 3) / 4;
+    const int tx = vec ? 4 : 8, ty = 4;
+    M.tiles_x = (M.nx + tx - 1) / tx;
+    M.tiles_y = (M.ny + ty - 1) / ty;
     int nchunks = 1;
-    marchv_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &nchunks);
-    M.lt = M.lz;
-    FB2_TRY(march_cta_lists(a, M, 4, 4, nchunks, ncells_own, true));
+    if (vec) { marchv_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &nchunks); M.lt = M.lz; }
+    else marchh_plan(ctx, M.tiles_x, M.tiles_y, M.z1 - M.z0, &M.lz, &M.nfull, &M.lt, &nchunks);
+    FB2_TRY(march_cta_lists(a, M, tx, ty, nchunks, ncells_own, true));
     if (a->box_nzcols < 0) return FB2_OK;
     if (a->box_nzcols > 0)
-        k_zero_columns<<<(unsigned)((a->box_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_box_zcols, a->box_nzcols, a->pat->d_colptr, nzval_dev);
+        k_zero_columns<<<(unsigned)((a->box_nzcols + 255) / 256), 256, 0, ctx->stream>>>(a->d_box_zcols, a->box_nzcols, a->pat->d_colptr, nzval_dev,
+                                                                                     a->pat->nnz);
     ctx->launches++;
     FB2_CUDA(cudaGetLastError());
     *done = true;

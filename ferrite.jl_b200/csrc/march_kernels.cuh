@@ -640,13 +640,15 @@ __global__ void __launch_bounds__(32, 8) k_march_hex(const AsmArgs A, const Marc
 // (x % 8 == 0 or y % 4 == 0) and the node planes where two chunks meet -- 38 % of nzval on C2 instead of all of it.
 // k_march_mark flags those columns (thread per grid node, same predicate as fb2_march_flush); the flagged dofs are
 // compacted into a sorted list once per assembler; k_zero_columns (warp per listed column) runs in front of every launch.
-__global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, int nx, int ny, int nz, int lz, int tx, int ty, int vdim,
-                             uint8_t* __restrict__ flag) {
+__global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, int nx, int ny, int nz, int lz, int nfull, int lt, int tx, int ty,
+                             int vdim, uint8_t* __restrict__ flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nn = (int64_t)(nx + 1) * (ny + 1) * (nz + 1);
     if (t >= nn) return;
     const int x = (int)(t % (nx + 1)), y = (int)((t / (nx + 1)) % (ny + 1)), p = (int)(t / ((int64_t)(nx + 1) * (ny + 1)));
-    const bool need = (x % tx == 0) || (y % ty == 0) || (p % lz == 0) || p == nz;   // tiles of tx x ty cells, chunks of lz layers
+    // tiles of tx x ty cells; chunks of lz layers, behind the first nfull of them chunks of lt layers
+    const int pt = p - nfull * lz;
+    const bool need = (x % tx == 0) || (y % ty == 0) || (pt <= 0 ? p % lz == 0 : pt % lt == 0) || p == nz;
     if (!need) return;
     // the node is corner (sx, sy, sz) of the cell below / left of it (clamped to the grid)
     const int cx = min(x, nx - 1), cy = min(y, ny - 1), cz = min(p, nz - 1);
@@ -658,7 +660,7 @@ __global__ void k_march_mark(const int32_t* __restrict__ cell_dofs, int64_t np, 
 // A warp takes 32 listed columns: one lane per column fetches its extent (two dependent loads for 32 columns instead of two
 // per column); listed columns that follow each other in nzval (the node rows of tile faces in y, the node planes between
 // chunks) are merged into runs, and the whole warp zeroes one run after the other with 16-byte stores.
-__global__ void k_zero_columns(const int32_t* __restrict__ cols, int64_t n, const int64_t* __restrict__ colptr, double* __restrict__ nzval) {
+__global__ void k_zero_columns(const int32_t* __restrict__ cols, int64_t n, const int64_t* __restrict__ colptr, double* __restrict__ nzval, int64_t nnz) {
     const unsigned full = 0xffffffffu;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -677,12 +679,14 @@ __global__ void k_zero_columns(const int32_t* __restrict__ cols, int64_t n, cons
         heads &= heads - 1;
         const int t = (heads ? __ffs(heads) - 1 : (int)min((int64_t)32, n - w * 32)) - 1;   // last column of the run
         int64_t rb = __shfl_sync(full, b, s);
-        const int64_t re = __shfl_sync(full, e, t);
+        int64_t re = __shfl_sync(full, e, t);
         if (rb >= re) continue;
-        if (rb & 1) {   // nzval is 16-byte aligned (checked by the caller): peel to an even entry
-            if (lane == 0) nzval[rb] = 0.0;
-            ++rb;
-        }
+        // Whole 32-byte sectors (nzval is 16-byte aligned and comes from cudaMalloc / a torch tensor: 32-byte aligned in
+        // practice, else the 16-byte stores below still work): a partly written sector costs the L2 a read from DRAM before
+        // it can be written back.  The few entries of neighbouring columns this touches are either listed themselves or
+        // belong to columns the marching kernel writes completely afterwards (that is what makes them unlisted).
+        rb &= ~(int64_t)3;
+        re = min((re + 3) & ~(int64_t)3, nnz);
         const int64_t body = (re - rb) & ~(int64_t)1;
         for (int64_t p = rb + 2 * lane; p < rb + body; p += 64) *reinterpret_cast<double2*>(nzval + p) = make_double2(0.0, 0.0);
         if (((re - rb) & 1) && lane == 0) nzval[re - 1] = 0.0;
