@@ -122,6 +122,7 @@ struct fb2_grid {
     int32_t* d_sv_cellmap = nullptr;
 };
 int fb2_grid_upload(fb2_grid* g);
+int fb2_host_threads();   // threads for the independent host loops of the set-up (host_grid.cpp)
 int fb2_grid_upload_xyz(fb2_grid* g);
 
 struct fb2_dh {

@@ -8,6 +8,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <thread>
+
+#include <sched.h>
 
 #include "common.h"
 
@@ -85,6 +89,19 @@ static void sort_pairs(std::vector<int64_t>& v) {
     for (size_t i = 0; i < p.size(); ++i) { v[2 * i] = p[i].first; v[2 * i + 1] = p[i].second; }
 }
 
+// Threads for the embarrassingly parallel host loops of the set-up (independent iterations: results do not depend on the
+// count).  torchrun exports OMP_NUM_THREADS=1 for every rank, so the count is taken from the CPUs this process may run on,
+// shared between the ranks of the node: FB2_HOST_THREADS overrides.
+int fb2_host_threads() {
+    if (const char* e = getenv("FB2_HOST_THREADS")) return std::max(1, atoi(e));
+    int ncpu = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) ncpu = CPU_COUNT(&set);
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return std::max(1, std::min(8, ncpu / ranks));
+}
+
 extern "C" int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel, const double* left, const double* right,
                                  fb2_grid** out) {
     FB2_CHECK(ctx && nel && out, FB2_ERR_BAD_ARG, "fb2_grid_generate: null argument");
@@ -124,6 +141,8 @@ extern "C" int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel,
     // nodes: xi = 2(idx-1)/(nn-1) - 1, x = sum_i M_i(xi) corner_i, first index fastest (:550-559)
     g->xyz.resize((size_t)nnodes * dim);
     const double scale = dim == 1 ? 2.0 : (dim == 2 ? 4.0 : 8.0);
+    const int nthreads = fb2_host_threads();
+#pragma omp parallel for collapse(2) schedule(static) num_threads(nthreads)
     for (int64_t k = 0; k < nn[2]; ++k)
         for (int64_t j = 0; j < nn[1]; ++j)
             for (int64_t i = 0; i < nn[0]; ++i) {
@@ -182,14 +201,29 @@ extern "C" int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel,
         g->ncells = tet ? 6 * ncube : ncube;
         g->cells.resize((size_t)g->ncells * g->nnpc);
         static const int split[6][4] = {{1, 2, 4, 8}, {1, 5, 2, 8}, {2, 3, 4, 8}, {2, 7, 3, 8}, {2, 5, 6, 8}, {2, 6, 7, 8}};
+        bool hex_filled = false;
+        if (!tet) {   // connectivity in parallel; the facet sets (boundary cells only) in the serial sweep below
+#pragma omp parallel for collapse(2) schedule(static) num_threads(nthreads)
+            for (int64_t k = 0; k < n[2]; ++k)
+                for (int64_t j = 0; j < n[1]; ++j)
+                    for (int64_t i = 0; i < n[0]; ++i) {
+                        int64_t* p = &g->cells[(size_t)(i + n[0] * (j + n[1] * k)) * 8];
+                        p[0] = node(i, j, k); p[1] = node(i + 1, j, k); p[2] = node(i + 1, j + 1, k); p[3] = node(i, j + 1, k);
+                        p[4] = node(i, j, k + 1); p[5] = node(i + 1, j, k + 1); p[6] = node(i + 1, j + 1, k + 1); p[7] = node(i, j + 1, k + 1);
+                    }
+            hex_filled = true;
+        }
         for (int64_t k = 0; k < n[2]; ++k)
             for (int64_t j = 0; j < n[1]; ++j)
                 for (int64_t i = 0; i < n[0]; ++i) {
+                    // hexahedra: only boundary cells are left to do (their facet sets); jump over the interior of the row
+                    if (hex_filled && i == 1 && n[0] > 2 && k > 0 && k < n[2] - 1 && j > 0 && j < n[1] - 1) i = n[0] - 1;
                     int64_t c = i + n[0] * (j + n[1] * k);
                     int64_t v[8] = {node(i, j, k),     node(i + 1, j, k),     node(i + 1, j + 1, k),     node(i, j + 1, k),
                                     node(i, j, k + 1), node(i + 1, j, k + 1), node(i + 1, j + 1, k + 1), node(i, j + 1, k + 1)};
                     if (!tet) {
-                        memcpy(&g->cells[(size_t)c * 8], v, sizeof(v));
+                        if (!hex_filled) memcpy(&g->cells[(size_t)c * 8], v, sizeof(v));
+                        if (!(k == 0 || j == 0 || i == 0 || i == n[0] - 1 || j == n[1] - 1 || k == n[2] - 1)) continue;
                         if (k == 0) push(fs["bottom"], c + 1, 1);
                         if (j == 0) push(fs["front"], c + 1, 2);
                         if (i == n[0] - 1) push(fs["right"], c + 1, 3);
@@ -230,6 +264,8 @@ extern "C" int fb2_grid_perturb(fb2_grid* g, double amplitude) {
     FB2_CHECK(g->generated, FB2_ERR_BAD_ARG, "fb2_grid_perturb: only for grids made by fb2_grid_generate");
     const int dim = g->sdim;
     int64_t nn[3] = {g->nel[0] + 1, dim > 1 ? g->nel[1] + 1 : 1, dim > 2 ? g->nel[2] + 1 : 1};
+    const int nthreads = fb2_host_threads();
+#pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t id = 0; id < g->nnodes; ++id) {
         int64_t r = id, idx[3];
         for (int d = 0; d < dim; ++d) { idx[d] = r % nn[d]; r /= nn[d]; }

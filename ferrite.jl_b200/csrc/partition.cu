@@ -239,35 +239,38 @@ static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* d
         }
         const int64_t nx = g->nel[0], ny = g->nel[1], nz = dim > 2 ? g->nel[2] : 1;
         const int per = (g->celltype == FB2_TRIANGLE) ? 2 : (g->celltype == FB2_TETRAHEDRON ? 6 : 1);
-        for (int64_t c = 0; c < ncells; ++c) {
-            int64_t cube = c / per;
-            int64_t i = cube % nx, j = (cube / nx) % ny, k = cube / (nx * ny);
-            int b = block_of(i, nx, P->dims[0]) + P->dims[0] * (block_of(j, ny, P->dims[1]) + P->dims[1] * (dim > 2 ? block_of(k, nz, P->dims[2]) : 0));
-            owner[c] = b;
-        }
+        // block of every cube, swept in storage order (no division per cell)
+        std::vector<int> bx((size_t)nx), by((size_t)ny), bz((size_t)nz);
+        for (int64_t i = 0; i < nx; ++i) bx[i] = block_of(i, nx, P->dims[0]);
+        for (int64_t j = 0; j < ny; ++j) by[j] = block_of(j, ny, P->dims[1]);
+        for (int64_t k = 0; k < nz; ++k) bz[k] = dim > 2 ? block_of(k, nz, P->dims[2]) : 0;
+        const int nth = fb2_host_threads();
+#pragma omp parallel for collapse(2) schedule(static) num_threads(nth)
+        for (int64_t k = 0; k < nz; ++k)
+            for (int64_t j = 0; j < ny; ++j) {
+                const int bjk = P->dims[0] * (by[j] + P->dims[1] * bz[k]);
+                int32_t* o = &owner[(size_t)(nx * (j + ny * k)) * per];
+                for (int64_t i = 0; i < nx; ++i)
+                    for (int t = 0; t < per; ++t) o[i * per + t] = bx[i] + bjk;
+            }
     } else {
         P->dims[0] = nparts;
         for (int64_t c = 0; c < ncells; ++c) owner[c] = block_of(c, ncells, nparts);
     }
     // ---- dof -> rank: lowest rank among the cells touching the dof ---------------------------------------------
-    std::vector<int32_t> gdof_owner((size_t)gdh->ndofs, nparts);
+    std::vector<int32_t> gdof_owner((size_t)gdh->ndofs, nparts), gdof_maxowner((size_t)gdh->ndofs, -1);
     for (int64_t c = 0; c < ncells; ++c) {
         const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
         const int32_t o = owner[c];
-        for (int i = 0; i < ndpc; ++i)
+        for (int i = 0; i < ndpc; ++i) {
             if (o < gdof_owner[cd[i]]) gdof_owner[cd[i]] = o;
+            if (o > gdof_maxowner[cd[i]]) gdof_maxowner[cd[i]] = o;
+        }
     }
     // ---- local cells: own + every cell touching an owned dof ------------------------------------------------------
     // Order: [own cells touching an exchanged dof | other own cells | halo cells], each by ascending global id.  A dof is
     // exchanged when cells of more than one rank touch it.  Contiguous ranges let the kernels run without an index list,
     // and the interface cells can be assembled first so that their exchange overlaps the interior.
-    std::vector<int32_t> gdof_maxowner((size_t)gdh->ndofs, -1);
-    for (int64_t c = 0; c < ncells; ++c) {
-        const int32_t* cd = &gdh->cell_dofs[(size_t)c * ndpc];
-        const int32_t o = owner[c];
-        for (int i = 0; i < ndpc; ++i)
-            if (o > gdof_maxowner[cd[i]]) gdof_maxowner[cd[i]] = o;
-    }
     {
         std::vector<int64_t> iface, inner, halo;
         for (int64_t c = 0; c < ncells; ++c) {
@@ -310,14 +313,18 @@ static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* d
         }
     P->lcells.resize((size_t)nl * nnpc);
     P->lcell_dofs.resize((size_t)nl * ndpc);
+    const int nthl = fb2_host_threads();
+#pragma omp parallel for schedule(static) num_threads(nthl)
     for (int64_t l = 0; l < nl; ++l) {
         const int64_t c = P->cells_global[l];
         for (int k = 0; k < nnpc; ++k) P->lcells[(size_t)l * nnpc + k] = g2l_node[g->cells[(size_t)c * nnpc + k] - 1] + 1;
         for (int i = 0; i < ndpc; ++i) P->lcell_dofs[(size_t)l * ndpc + i] = g2l_dof[gdh->cell_dofs[(size_t)c * ndpc + i]] + 1;
     }
     P->lxyz.resize(P->l2g_node.size() * sdim);
-    for (size_t n = 0; n < P->l2g_node.size(); ++n)
-        for (int d = 0; d < sdim; ++d) P->lxyz[n * sdim + d] = g->xyz[(size_t)P->l2g_node[n] * sdim + d];
+    const int64_t nln = (int64_t)P->l2g_node.size();
+#pragma omp parallel for schedule(static) num_threads(nthl)
+    for (int64_t n = 0; n < nln; ++n)
+        for (int d = 0; d < sdim; ++d) P->lxyz[(size_t)n * sdim + d] = g->xyz[(size_t)P->l2g_node[n] * sdim + d];
     // ---- exchange lists -----------------------------------------------------------------------------------------------
     P->peers.resize(nparts);
     std::vector<std::vector<uint64_t>> send_k(nparts), recv_k(nparts), send_fk(nparts), recv_fk(nparts);
