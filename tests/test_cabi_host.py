@@ -55,6 +55,25 @@ def test_generate_grid_matches_oracle(hctx, ct, nel, left, right):
         assert np.array_equal(fb.getfacetset(g, name), pairs), name
 
 
+@pytest.mark.parametrize("ct,nel", [(fb.Hexahedron, (23, 17, 9)), (fb.Hexahedron, (2, 1, 3)), (fb.Tetrahedron, (5, 4, 3)), (fb.Quadrilateral, (31, 7))])
+def test_host_setup_does_not_depend_on_the_thread_count(hctx, ct, nel, monkeypatch):
+    """the independent host loops of the set-up (nodes, connectivity, perturbation, partition arrays) run on several threads
+    (FB2_HOST_THREADS): grid, facet sets and partition plan must be identical for 1 and 5 threads"""
+    out = []
+    for threads in ("1", "5"):
+        monkeypatch.setenv("FB2_HOST_THREADS", threads)
+        g = fb.generate_grid(ct, nel, ctx=hctx).perturb(0.15)
+        dh = fb.close_(fb.add_(fb.DofHandler(g), "u", fb.Lagrange(ct, 1)))
+        part = fb.Partition(dh, 4, 1)
+        out.append((g.cells.copy(), g.nodes.copy(), {k: np.asarray(fb.getfacetset(g, k)).copy() for k in ("left", "right")},
+                    part.l2g_dof.copy(), part.dof_owner.copy(), part.cells_global.copy(),
+                    (part.ncells_local, part.ncells_own, part.nnodes_local, part.ndofs_local, part.ndofs_owned)))
+    a, b = out
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert all(np.array_equal(a[2][k], b[2][k]) for k in a[2])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5]) and a[6] == b[6]
+
+
 def test_perturb_matches_oracle(hctx):
     nel, left, right = (4, 3, 5), (0.0, 0.0, 0.0), (1.0, 2.0, 3.0)
     g = fb.generate_grid(fb.Hexahedron, nel, left, right, ctx=hctx).perturb(0.2)
