@@ -339,12 +339,16 @@ def config4_strong(fb, ctx, dist, torch, world, rank, dev, steps, nel_total=(320
         hctx = fb.Context(-1)
         ip = fb.Lagrange(fb.Hexahedron, 1) ** 3
         cv = fb.CellValues(fb.QuadratureRule(fb.Hexahedron, 2), ip)
-        gg = fb.generate_grid(fb.Hexahedron, nel_total, ctx=hctx).perturb(0.2)
-        gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
-        part = fb.Partition(gdh, world, rank, dims)
+        if not os.environ.get("FB2_BENCH_GLOBAL_SETUP"):
+            part = fb.Partition.generated(nel_total, ip, world, rank, dims, perturb=0.2, host_ctx=hctx)   # rank-local set-up
+            ncells = int(nel_total[0] * nel_total[1] * nel_total[2])
+        else:
+            gg = fb.generate_grid(fb.Hexahedron, nel_total, ctx=hctx).perturb(0.2)
+            gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+            part = fb.Partition(gdh, world, rank, dims)
+            ncells = gg.ncells
+            del gdh, gg
         g, dh = part.local_problem(ctx)
-        ncells = gg.ncells
-        del gdh, gg
         K = fb.allocate_matrix(dh)
         f = ctx.zeros(dh.ndofs)
         part.bind(fb.start_assemble(K, f), cv)
@@ -464,11 +468,19 @@ def main():
         dims = block_dims(world)
         gnel = tuple(n * d for n, d in zip(nel, dims))
         hctx = fb.Context(-1)
-        gg = fb.generate_grid(fb.Hexahedron, gnel, tuple(-float(d) for d in dims), tuple(float(d) for d in dims), ctx=hctx).perturb(0.2)
-        gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
-        part = fb.Partition(gdh, world, rank, dims)
+        gleft, gright = tuple(-float(d) for d in dims), tuple(float(d) for d in dims)
+        if cfg["cell"] == "hex" and cfg["order"] == 1 and not os.environ.get("FB2_BENCH_GLOBAL_SETUP"):
+            # rank-local set-up: the same plan as Partition(close!(DofHandler(generate_grid(...).perturb(0.2))), world, rank, dims)
+            # from closed forms, without the global grid / DofHandler (tests/test_partition_host.py compares the two)
+            part = fb.Partition.generated(gnel, ip, world, rank, dims, left=gleft, right=gright, perturb=0.2, host_ctx=hctx)
+            ncells_total = int(gnel[0] * gnel[1] * gnel[2])
+        else:
+            gg = fb.generate_grid(fb.Hexahedron, gnel, gleft, gright, ctx=hctx).perturb(0.2)
+            gdh = fb.close_(fb.add_(fb.DofHandler(gg), "u", ip))
+            part = fb.Partition(gdh, world, rank, dims)
+            ncells_total = gg.ncells
         g, dh = part.local_problem(ctx)
-        ncells_total, volume = gg.ncells, 8.0 * world
+        volume = 8.0 * world
     K = fb.allocate_matrix(dh)
     f = ctx.zeros(dh.ndofs)
     if cfg["element"] == "neohooke":

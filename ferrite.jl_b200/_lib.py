@@ -176,6 +176,7 @@ _PROTOS = {
     "fb2_partition_create": [_p, C.c_int, C.c_int, _ip, _pp],
     "fb2_partition_create_from_owners": [_p, C.c_int, C.c_int, _i32p, _pp],
     "fb2_partition_create_metis": [_p, C.c_int, C.c_int, _pp],
+    "fb2_partition_create_generated": [_p, _i64p, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, _ip, _pp],
     "fb2_partition_info": [_p, _i64p, _i64p, _i64p, _i64p, _i64p],
     "fb2_partition_export": [_p, _i64p, C.POINTER(C.c_uint8), _i64p, _i64p, _i32p],
     "fb2_partition_local_grid": [_p, _p, _pp],

@@ -1194,6 +1194,31 @@ class Partition:
         else:
             darr = (C.c_int * 3)(*(list(dims) + [1, 1, 1])[:3]) if dims is not None else None
             L.call("fb2_partition_create", gdh.h, self.nparts, self.rank, darr, C.byref(self.h))
+        self._field_names, self._field_ips = list(gdh.field_names), list(gdh.field_ips)
+        self._export()
+
+    @classmethod
+    def generated(cls, nel, ip, nparts, rank, dims=None, left=None, right=None, perturb=0.0, name="u", host_ctx=None):
+        """The plan Partition(close!(DofHandler(generate_grid(Hexahedron, nel, left, right).perturb(perturb)) + field `name` =
+        Lagrange{RefHexahedron,1}^vdim), nparts, rank, dims) would give, built rank-locally from closed forms: no global grid,
+        no global DofHandler (fb2_partition_create_generated)."""
+        assert ip.refshape == Hexahedron and ip.order == 1
+        self = cls.__new__(cls)
+        self.gdh, self.nparts, self.rank = None, int(nparts), int(rank)
+        self._hctx = host_ctx or Context(-1)
+        self.h = C.c_void_p()
+        nel = _i64(nel)
+        lp = _ptr(_f64(left), C.c_double) if left is not None else None
+        rp = _ptr(_f64(right), C.c_double) if right is not None else None
+        darr = (C.c_int * 3)(*(list(dims) + [1, 1, 1])[:3]) if dims is not None else None
+        L.call("fb2_partition_create_generated", self._hctx.h, _ptr(nel, C.c_int64), lp, rp, float(perturb), int(ip.vdim),
+               self.nparts, self.rank, darr, C.byref(self.h))
+        self.ncells_global = int(nel[0] * nel[1] * nel[2])
+        self._field_names, self._field_ips = [name], [ip]
+        self._export()
+        return self
+
+    def _export(self):
         v = [C.c_int64() for _ in range(5)]
         L.call("fb2_partition_info", self.h, *[C.byref(x) for x in v])
         self.ncells_local, self.ncells_own, self.nnodes_local, self.ndofs_local, self.ndofs_owned = (x.value for x in v)
@@ -1213,7 +1238,7 @@ class Partition:
         grid = Grid(ctx, gh)
         L.call("fb2_partition_local_dh", self.h, grid.h, C.byref(dhh))
         dh = DofHandler(grid)
-        dh.field_names, dh.field_ips = list(self.gdh.field_names), list(self.gdh.field_ips)
+        dh.field_names, dh.field_ips = list(self._field_names), list(self._field_ips)
         dh.h = dhh
         dh._info()
         return grid, dh
@@ -1276,7 +1301,7 @@ class Partition:
 
     def __del__(self):
         if _destroy is not None:      # module globals are already gone at interpreter shutdown
-            _destroy(self, "fb2_partition_destroy", _chain(self, "gdh"))
+            _destroy(self, "fb2_partition_destroy", list(_chain(self, "gdh")) + ([self._hctx] if getattr(self, "_hctx", None) is not None else []))
 
 
 def comm_unique_id():

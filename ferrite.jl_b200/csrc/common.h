@@ -123,6 +123,10 @@ struct fb2_grid {
 };
 int fb2_grid_upload(fb2_grid* g);
 int fb2_host_threads();   // threads for the independent host loops of the set-up (host_grid.cpp)
+// node coordinates of generate_grid / perturb, one definition for fb2_grid_generate and the rank-local set-up (host_grid.cpp)
+void fb2_generated_corners(int dim, const double* lo, const double* hi, int* nc, double* refcoords, double* corner);
+void fb2_generated_node(int dim, const int64_t* nn, int nc, const double* refcoords, const double* corner, const int64_t* idx, double* x);
+double fb2_perturb_delta(int64_t id, int d, double amplitude, double h);
 int fb2_grid_upload_xyz(fb2_grid* g);
 
 struct fb2_dh {

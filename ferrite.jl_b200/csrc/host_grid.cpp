@@ -102,6 +102,42 @@ int fb2_host_threads() {
     return std::max(1, std::min(8, ncpu / ranks));
 }
 
+// Node (idx) of generate_grid: xi = 2 idx / (nn - 1) - 1, x = sum_c M_c(xi) corner_c with the multilinear shape functions of the
+// hypercube (src/Grid/grid_generators.jl:550-578).  ONE definition, also called by the rank-local set-up of partition.cu, so
+// that both produce the same bits.  refcoords: [nc][3], corner: [8][3].
+void fb2_generated_node(int dim, const int64_t* nn, int nc, const double* refcoords, const double* corner, const int64_t* idx, double* x) {
+    const double scale = dim == 1 ? 2.0 : (dim == 2 ? 4.0 : 8.0);
+    double xi[3];
+    for (int d = 0; d < dim; ++d) xi[d] = 2.0 * (double)idx[d] / (double)(nn[d] - 1) - 1.0;
+    x[0] = x[1] = x[2] = 0.0;
+    for (int c = 0; c < nc; ++c) {
+        double M = 1.0;
+        for (int d = 0; d < dim; ++d) M = M * (refcoords[c * 3 + d] > 0 ? (1 + xi[d]) : (1 - xi[d]));
+        M = M / scale;
+        for (int d = 0; d < dim; ++d) x[d] += M * corner[c * 3 + d];
+    }
+}
+
+// corners of the box in the vertex order of the linear hypercube (_extrema_to_corners :565-578)
+void fb2_generated_corners(int dim, const double* lo, const double* hi, int* nc, double* refcoords, double* corner) {
+    LagrangeInfo cube;
+    fb2_lagrange(dim == 1 ? FB2_LINE : (dim == 2 ? FB2_QUADRILATERAL : FB2_HEXAHEDRON), 1, &cube);
+    *nc = cube.nbase;
+    for (int i = 0; i < cube.nbase; ++i)
+        for (int d = 0; d < 3; ++d) {
+            refcoords[i * 3 + d] = cube.refcoords[i][d];
+            corner[i * 3 + d] = 0.0;
+            if (d < dim) {
+                double dxi = cube.refcoords[i][d] - (-1.0);
+                corner[i * 3 + d] = lo[d] + ((hi[d] - lo[d]) / 2.0) * dxi;
+            }
+        }
+}
+
+static inline double hash01(uint64_t id, uint64_t salt);
+// displacement of fb2_grid_perturb for component d of global node id (0-based); interior nodes only (the caller checks)
+double fb2_perturb_delta(int64_t id, int d, double amplitude, double h);
+
 extern "C" int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel, const double* left, const double* right,
                                  fb2_grid** out) {
     FB2_CHECK(ctx && nel && out, FB2_ERR_BAD_ARG, "fb2_grid_generate: null argument");
@@ -128,35 +164,20 @@ extern "C" int fb2_grid_generate(fb2_ctx* ctx, int celltype, const int64_t* nel,
     g->generated = true;
     for (int d = 0; d < 3; ++d) { g->nel[d] = n[d]; g->left[d] = lo[d]; g->right[d] = hi[d]; }
 
-    // corners of the box, in the vertex order of the linear hypercube (_extrema_to_corners :565-578)
-    LagrangeInfo cube;
-    fb2_lagrange(dim == 1 ? FB2_LINE : (dim == 2 ? FB2_QUADRILATERAL : FB2_HEXAHEDRON), 1, &cube);
-    const int nc = cube.nbase;
-    double corner[8][3];
-    for (int i = 0; i < nc; ++i)
-        for (int d = 0; d < dim; ++d) {
-            double dxi = cube.refcoords[i][d] - (-1.0);
-            corner[i][d] = lo[d] + ((hi[d] - lo[d]) / 2.0) * dxi;
-        }
+    int nc = 0;
+    double refc[8 * 3], corner[8 * 3];
+    fb2_generated_corners(dim, lo, hi, &nc, refc, corner);
     // nodes: xi = 2(idx-1)/(nn-1) - 1, x = sum_i M_i(xi) corner_i, first index fastest (:550-559)
     g->xyz.resize((size_t)nnodes * dim);
-    const double scale = dim == 1 ? 2.0 : (dim == 2 ? 4.0 : 8.0);
     const int nthreads = fb2_host_threads();
 #pragma omp parallel for collapse(2) schedule(static) num_threads(nthreads)
     for (int64_t k = 0; k < nn[2]; ++k)
         for (int64_t j = 0; j < nn[1]; ++j)
             for (int64_t i = 0; i < nn[0]; ++i) {
-                int64_t id = i + nn[0] * (j + nn[1] * k);
-                int64_t idx[3] = {i, j, k};
-                double xi[3];
-                for (int d = 0; d < dim; ++d) xi[d] = 2.0 * (double)idx[d] / (double)(nn[d] - 1) - 1.0;
-                double x[3] = {0, 0, 0};
-                for (int c = 0; c < nc; ++c) {
-                    double M = 1.0;
-                    for (int d = 0; d < dim; ++d) M = M * (cube.refcoords[c][d] > 0 ? (1 + xi[d]) : (1 - xi[d]));
-                    M = M / scale;
-                    for (int d = 0; d < dim; ++d) x[d] += M * corner[c][d];
-                }
+                const int64_t id = i + nn[0] * (j + nn[1] * k);
+                const int64_t idx[3] = {i, j, k};
+                double x[3];
+                fb2_generated_node(dim, nn, nc, refc, corner, idx, x);
                 for (int d = 0; d < dim; ++d) g->xyz[(size_t)id * dim + d] = x[d];
             }
     auto node = [&](int64_t i, int64_t j, int64_t k) { return 1 + i + nn[0] * (j + nn[1] * k); };
@@ -259,6 +280,8 @@ static inline double hash01(uint64_t id, uint64_t salt) {
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
+double fb2_perturb_delta(int64_t id, int d, double amplitude, double h) { return amplitude * h * (hash01((uint64_t)id + 1, (uint64_t)d) - 0.5); }
+
 extern "C" int fb2_grid_perturb(fb2_grid* g, double amplitude) {
     FB2_CHECK(g, FB2_ERR_BAD_ARG, "fb2_grid_perturb: null grid");
     FB2_CHECK(g->generated, FB2_ERR_BAD_ARG, "fb2_grid_perturb: only for grids made by fb2_grid_generate");
@@ -274,7 +297,7 @@ extern "C" int fb2_grid_perturb(fb2_grid* g, double amplitude) {
         if (!interior) continue;
         for (int d = 0; d < dim; ++d) {
             double h = (g->right[d] - g->left[d]) / (double)g->nel[d];
-            g->xyz[(size_t)id * dim + d] += amplitude * h * (hash01((uint64_t)id + 1, (uint64_t)d) - 0.5);
+            g->xyz[(size_t)id * dim + d] += fb2_perturb_delta(id, d, amplitude, h);
         }
     }
     return fb2_grid_upload_xyz(g);

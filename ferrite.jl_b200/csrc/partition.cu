@@ -36,6 +36,7 @@ struct PeerPlan {
 
 struct fb2_part {
     fb2_dh* gdh = nullptr;
+    bool owns_global = false;   // gdh (+ its grid) is the metadata-only global problem of fb2_partition_create_generated
     int nparts = 1, rank = 0;
     int dims[3] = {1, 1, 1};
     std::vector<int64_t> cells_global;   // local cells (own + halo), ascending global id (0-based)
@@ -365,6 +366,266 @@ static int partition_create_impl(fb2_dh* gdh, int nparts, int rank, const int* d
     return FB2_OK;
 }
 
+// ---- rank-local set-up of a block partition of generate_grid(Hexahedron, nel) -------------------------------------------------
+// fb2_partition_create needs the global grid and DofHandler on every rank (N = 8, 400^3 cells: 14 s per rank, nearly all of
+// it global sweeps).  For the case the benchmarks use -- first-order hexahedra of generate_grid, one Lagrange field of order
+// 1, px x py x pz blocks -- everything the plan holds has a closed form, so a rank can build its part directly:
+//   * close!(dh) numbers dofs by first appearance in the cell sweep (src/Dofs/DofHandler.jl:576-738): node (i, j, k) first
+//     appears in cell (max(i-1,0), max(j-1,0), max(k-1,0)), a cell (a, b, c) introduces (1 + [a=0]) (1 + [b=0]) (1 + [c=0]) nodes
+//     in local vertex order, hence  rank(node) = #nodes introduced by earlier cells + position among the new nodes of its cell
+//     (fb2_gen_node_rank), dofs vdim * rank + component;
+//   * the owner of a dof = lowest rank of a cell touching it = block of that first cell; cells touching an owned dof = the block
+//     extended by one cell on its high sides;
+//   * node coordinates: the same function as fb2_grid_generate + fb2_grid_perturb (global node id in the hash).
+// The result is array-for-array what fb2_partition_create derives from the global problem (tests/test_partition_host.py);
+// the global grid / DofHandler the plan refers to hold metadata only.
+namespace {
+// sort on `nth` threads: sorted chunks, then pairwise merges
+template <class T, class Cmp>
+void fb2_psort(std::vector<T>& v, int nth, Cmp cmp) {
+    const size_t n = v.size();
+    if (nth <= 1 || n < ((size_t)1 << 16)) { std::sort(v.begin(), v.end(), cmp); return; }
+    std::vector<size_t> b((size_t)nth + 1);
+    for (int k = 0; k <= nth; ++k) b[k] = n * (size_t)k / (size_t)nth;
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+    for (int k = 0; k < nth; ++k) std::sort(v.begin() + b[k], v.begin() + b[k + 1], cmp);
+    for (int w = 1; w < nth; w *= 2) {
+#pragma omp parallel for schedule(static, 1) num_threads(nth)
+        for (int k = 0; k < nth; k += 2 * w)
+            if (k + w < nth) std::inplace_merge(v.begin() + b[k], v.begin() + b[k + w], v.begin() + b[std::min(k + 2 * w, nth)], cmp);
+    }
+}
+inline int64_t gen_F(int64_t m) { return m + (m > 0 ? 1 : 0); }   // nodes (per direction) introduced by cell columns < m
+inline int64_t gen_f(int64_t m) { return m == 0 ? 2 : 1; }
+int64_t fb2_gen_node_rank(int64_t i, int64_t j, int64_t k, int64_t nx, int64_t ny) {
+    static const int LV[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    const int64_t a = std::max<int64_t>(i - 1, 0), b = std::max<int64_t>(j - 1, 0), c = std::max<int64_t>(k - 1, 0);
+    int64_t r = gen_F(c) * (ny + 1) * (nx + 1) + gen_f(c) * gen_F(b) * (nx + 1) + gen_f(c) * gen_f(b) * gen_F(a);
+    for (int v = 0; v < 8; ++v) {
+        const int da = LV[v][0], db = LV[v][1], dc = LV[v][2];
+        if (a + da == i && b + db == j && c + dc == k) break;
+        if ((da == 1 || a == 0) && (db == 1 || b == 0) && (dc == 1 || c == 0)) ++r;
+    }
+    return r;
+}
+}  // namespace
+
+extern "C" int fb2_partition_create_generated(fb2_ctx* hctx, const int64_t* nel, const double* left, const double* right, double perturb,
+                                              int vdim, int nparts, int rank, const int* dims_in, fb2_part** out) {
+    FB2_CHECK(hctx && nel && out, FB2_ERR_BAD_ARG, "fb2_partition_create_generated: null argument");
+    FB2_CHECK(nparts >= 1 && rank >= 0 && rank < nparts && vdim >= 1 && vdim <= 3, FB2_ERR_BAD_ARG, "fb2_partition_create_generated: bad nparts / rank / vdim");
+    const int64_t nx = nel[0], ny = nel[1], nz = nel[2];
+    FB2_CHECK(nx >= 1 && ny >= 1 && nz >= 1, FB2_ERR_BAD_ARG, "fb2_partition_create_generated: nel < 1");
+    const int64_t nnodes = (nx + 1) * (ny + 1) * (nz + 1);
+    FB2_CHECK(nnodes * vdim < (int64_t)2147483647, FB2_ERR_UNSUPPORTED, "more than 2^31-1 global dofs");
+    // ---- the global problem, metadata only ----------------------------------------------------------------------------------
+    fb2_grid* g = new fb2_grid();
+    g->ctx = hctx;
+    g->celltype = FB2_HEXAHEDRON;
+    g->sdim = 3;
+    g->nnpc = 8;
+    g->generated = true;
+    g->ncells = nx * ny * nz;
+    g->nnodes = nnodes;
+    double lo[3] = {-1, -1, -1}, hi[3] = {1, 1, 1};
+    for (int d = 0; d < 3; ++d) {
+        if (left) lo[d] = left[d];
+        if (right) hi[d] = right[d];
+        g->nel[d] = nel[d]; g->left[d] = lo[d]; g->right[d] = hi[d];
+    }
+    fb2_dh* gdh = new fb2_dh();
+    gdh->grid = g;
+    fb2_field fld = {1, vdim};
+    LagrangeInfo ip;
+    fb2_lagrange(FB2_HEXAHEDRON, 1, &ip);
+    gdh->fields.push_back(fld);
+    gdh->ips.push_back(ip);
+    gdh->ndpc = 8 * vdim;
+    gdh->ndofs = nnodes * vdim;
+    fb2_part* P = new fb2_part();
+    P->gdh = gdh;
+    P->owns_global = true;
+    P->nparts = nparts;
+    P->rank = rank;
+    if (dims_in) { for (int d = 0; d < 3; ++d) P->dims[d] = dims_in[d]; }
+    else default_dims(nparts, g->nel, 3, P->dims);
+    if ((int64_t)P->dims[0] * P->dims[1] * P->dims[2] != nparts) {
+        fb2_partition_destroy(P);
+        return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create: block layout does not multiply to nparts");
+    }
+    const int px = P->dims[0], py = P->dims[1];
+    std::vector<int> bx((size_t)nx), by((size_t)ny), bz((size_t)nz);
+    for (int64_t i = 0; i < nx; ++i) bx[i] = block_of(i, nx, P->dims[0]);
+    for (int64_t j = 0; j < ny; ++j) by[j] = block_of(j, ny, P->dims[1]);
+    for (int64_t k = 0; k < nz; ++k) bz[k] = block_of(k, nz, P->dims[2]);
+    auto cell_owner = [&](int64_t i, int64_t j, int64_t k) { return bx[i] + px * (by[j] + py * bz[k]); };
+    // owner of a node's dofs = lowest / highest rank among the cells around it
+    auto node_owner = [&](int64_t i, int64_t j, int64_t k) { return cell_owner(std::max<int64_t>(i - 1, 0), std::max<int64_t>(j - 1, 0), std::max<int64_t>(k - 1, 0)); };
+    auto node_maxowner = [&](int64_t i, int64_t j, int64_t k) { return cell_owner(std::min(i, nx - 1), std::min(j, ny - 1), std::min(k, nz - 1)); };
+    // my block and the box of local cells (block + one cell on the high sides)
+    const int rb[3] = {rank % px, (rank / px) % py, rank / (px * py)};
+    const int64_t n3[3] = {nx, ny, nz};
+    int64_t blo[3], bhi[3], ehi[3];
+    for (int d = 0; d < 3; ++d) {
+        blo[d] = ((int64_t)rb[d] * n3[d]) / P->dims[d];
+        bhi[d] = ((int64_t)(rb[d] + 1) * n3[d]) / P->dims[d];
+        ehi[d] = std::min(bhi[d] + 1, n3[d]);
+    }
+    if (blo[0] >= bhi[0] || blo[1] >= bhi[1] || blo[2] >= bhi[2]) {
+        fb2_partition_destroy(P);
+        return fb2_fail(FB2_ERR_BAD_ARG, "fb2_partition_create: rank %d owns no cells", rank);
+    }
+    static const int HV[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    // ---- local cells: [own, touching an exchanged dof | other own | halo], each by ascending global id ------------------------
+    {
+        std::vector<int64_t> iface, inner, halo;
+        for (int64_t k = blo[2]; k < ehi[2]; ++k)
+            for (int64_t j = blo[1]; j < ehi[1]; ++j)
+                for (int64_t i = blo[0]; i < ehi[0]; ++i) {
+                    const int64_t c = i + nx * (j + ny * k);
+                    if (i < bhi[0] && j < bhi[1] && k < bhi[2]) {
+                        bool x = false;
+                        for (int v = 0; v < 8 && !x; ++v)
+                            x = node_owner(i + HV[v][0], j + HV[v][1], k + HV[v][2]) != node_maxowner(i + HV[v][0], j + HV[v][1], k + HV[v][2]);
+                        (x ? iface : inner).push_back(c);
+                    } else {
+                        bool touch = false;
+                        for (int v = 0; v < 8 && !touch; ++v) touch = node_owner(i + HV[v][0], j + HV[v][1], k + HV[v][2]) == rank;
+                        if (touch) halo.push_back(c);
+                    }
+                }
+        P->n_iface = (int64_t)iface.size();
+        P->ncells_own = (int64_t)(iface.size() + inner.size());
+        P->cells_global = iface;
+        P->cells_global.insert(P->cells_global.end(), inner.begin(), inner.end());
+        P->cells_global.insert(P->cells_global.end(), halo.begin(), halo.end());
+        P->cell_is_own.assign(P->cells_global.size(), 0);
+        std::fill(P->cell_is_own.begin(), P->cell_is_own.begin() + P->ncells_own, 1);
+    }
+    const int64_t nl = (int64_t)P->cells_global.size();
+    // ---- local nodes: the nodes of the local cells, ascending global id; a node marked by the cells that use it ------------------
+    const int64_t L1[3] = {ehi[0] - blo[0] + 1, ehi[1] - blo[1] + 1, ehi[2] - blo[2] + 1};   // nodes of the box per direction
+    const int64_t nbox = L1[0] * L1[1] * L1[2];
+    std::vector<int32_t> box2l((size_t)nbox, -1);
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int64_t i = c % nx - blo[0], j = (c / nx) % ny - blo[1], k = c / (nx * ny) - blo[2];
+        for (int v = 0; v < 8; ++v) box2l[(size_t)((i + HV[v][0]) + L1[0] * ((j + HV[v][1]) + L1[1] * (k + HV[v][2])))] = 0;
+    }
+    struct NodeRec { int64_t gdof0; int32_t lnode; int32_t owner; };
+    std::vector<NodeRec> recs;
+    for (int64_t bk = 0; bk < L1[2]; ++bk)
+        for (int64_t bj = 0; bj < L1[1]; ++bj)
+            for (int64_t bi = 0; bi < L1[0]; ++bi) {
+                int32_t& m = box2l[(size_t)(bi + L1[0] * (bj + L1[1] * bk))];
+                if (m != 0) continue;
+                const int64_t i = bi + blo[0], j = bj + blo[1], k = bk + blo[2];
+                m = (int32_t)P->l2g_node.size();
+                P->l2g_node.push_back(i + (nx + 1) * (j + (ny + 1) * k));
+                recs.push_back(NodeRec{(int64_t)vdim * fb2_gen_node_rank(i, j, k, nx, ny), m, (int32_t)node_owner(i, j, k)});
+            }
+    const int64_t nln = (int64_t)P->l2g_node.size();
+    // ---- local dofs: ascending global dof id -----------------------------------------------------------------------------------------
+    const int nth = fb2_host_threads();
+    fb2_psort(recs, nth, [](const NodeRec& a, const NodeRec& b) { return a.gdof0 < b.gdof0; });
+    std::vector<int32_t> node_dof0((size_t)nln);   // first local dof (0-based) of a local node
+    P->l2g_dof.reserve((size_t)nln * vdim);
+    P->dof_owner.reserve((size_t)nln * vdim);
+    for (int64_t r = 0; r < nln; ++r) {
+        node_dof0[recs[r].lnode] = (int32_t)(r * vdim);
+        for (int t = 0; t < vdim; ++t) {
+            P->l2g_dof.push_back(recs[r].gdof0 + t);
+            P->dof_owner.push_back(recs[r].owner);
+            P->ndofs_owned += recs[r].owner == rank ? 1 : 0;
+        }
+    }
+    // ---- local arrays ------------------------------------------------------------------------------------------------------------------
+    const int ndpc = 8 * vdim;
+    P->lcells.resize((size_t)nl * 8);
+    P->lcell_dofs.resize((size_t)nl * ndpc);
+#pragma omp parallel for schedule(static) num_threads(nth)
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int64_t i = c % nx - blo[0], j = (c / nx) % ny - blo[1], k = c / (nx * ny) - blo[2];
+        for (int v = 0; v < 8; ++v) {
+            const int32_t ln = box2l[(size_t)((i + HV[v][0]) + L1[0] * ((j + HV[v][1]) + L1[1] * (k + HV[v][2])))];
+            P->lcells[(size_t)l * 8 + v] = ln + 1;
+            for (int t = 0; t < vdim; ++t) P->lcell_dofs[(size_t)l * ndpc + v * vdim + t] = node_dof0[ln] + t + 1;
+        }
+    }
+    P->lxyz.resize((size_t)nln * 3);
+    {
+        int nc = 0;
+        double refc[8 * 3], corner[8 * 3];
+        fb2_generated_corners(3, lo, hi, &nc, refc, corner);
+        const int64_t nn[3] = {nx + 1, ny + 1, nz + 1};
+#pragma omp parallel for schedule(static) num_threads(nth)
+        for (int64_t n = 0; n < nln; ++n) {
+            const int64_t id = P->l2g_node[n];
+            const int64_t idx[3] = {id % nn[0], (id / nn[0]) % nn[1], id / (nn[0] * nn[1])};
+            double x[3];
+            fb2_generated_node(3, nn, nc, refc, corner, idx, x);
+            const bool interior = idx[0] > 0 && idx[0] < nn[0] - 1 && idx[1] > 0 && idx[1] < nn[1] - 1 && idx[2] > 0 && idx[2] < nn[2] - 1;
+            if (perturb != 0.0 && interior)
+                for (int d = 0; d < 3; ++d) x[d] += fb2_perturb_delta(id, d, perturb, (hi[d] - lo[d]) / (double)n3[d]);
+            for (int d = 0; d < 3; ++d) P->lxyz[(size_t)n * 3 + d] = x[d];
+        }
+    }
+    // ---- exchange lists (as in partition_create_impl, with local look-ups) --------------------------------------------------------------------
+    P->peers.resize(nparts);
+    std::vector<std::vector<uint64_t>> send_k(nparts), recv_k(nparts), send_fk(nparts), recv_fk(nparts);
+    for (int64_t l = 0; l < nl; ++l) {
+        const int64_t c = P->cells_global[l];
+        const int64_t ci = c % nx, cj = (c / nx) % ny, ck = c / (nx * ny);
+        int64_t cd[24];
+        int own[24];
+        for (int v = 0; v < 8; ++v) {
+            const int32_t ln = P->lcell_dofs[(size_t)l * ndpc + v * vdim] - 1;   // first local dof of the node
+            for (int t = 0; t < vdim; ++t) {
+                cd[v * vdim + t] = P->l2g_dof[ln + t];
+                own[v * vdim + t] = P->dof_owner[ln + t];
+            }
+        }
+        if (P->cell_is_own[l]) {
+            for (int j = 0; j < ndpc; ++j) {
+                const int o = own[j];
+                if (o == rank) continue;
+                send_fk[o].push_back((uint64_t)cd[j]);
+                for (int i = 0; i < ndpc; ++i) send_k[o].push_back(((uint64_t)cd[j] << 32) | (uint32_t)cd[i]);
+            }
+        } else {
+            const int s = cell_owner(ci, cj, ck);
+            for (int j = 0; j < ndpc; ++j) {
+                if (own[j] != rank) continue;
+                recv_fk[s].push_back((uint64_t)cd[j]);
+                for (int i = 0; i < ndpc; ++i) recv_k[s].push_back(((uint64_t)cd[j] << 32) | (uint32_t)cd[i]);
+            }
+        }
+    }
+    auto uniq = [&](std::vector<uint64_t>& v) {
+        fb2_psort(v, nth, [](uint64_t a, uint64_t b) { return a < b; });
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    };
+    auto g2l = [&](uint64_t gd) { return (int32_t)(std::lower_bound(P->l2g_dof.begin(), P->l2g_dof.end(), (int64_t)gd) - P->l2g_dof.begin()); };
+    for (int p = 0; p < nparts; ++p) {
+        uniq(send_k[p]); uniq(recv_k[p]); uniq(send_fk[p]); uniq(recv_fk[p]);
+        PeerPlan& pp = P->peers[p];
+        const int64_t ns = (int64_t)send_k[p].size(), nr = (int64_t)recv_k[p].size();
+        pp.send_cols.resize((size_t)ns); pp.send_rows.resize((size_t)ns);
+        pp.recv_cols.resize((size_t)nr); pp.recv_rows.resize((size_t)nr);
+#pragma omp parallel for schedule(static) num_threads(nth)
+        for (int64_t q = 0; q < ns; ++q) { pp.send_cols[q] = g2l(send_k[p][q] >> 32); pp.send_rows[q] = g2l(send_k[p][q] & 0xffffffffu); }
+#pragma omp parallel for schedule(static) num_threads(nth)
+        for (int64_t q = 0; q < nr; ++q) { pp.recv_cols[q] = g2l(recv_k[p][q] >> 32); pp.recv_rows[q] = g2l(recv_k[p][q] & 0xffffffffu); }
+        for (uint64_t k : send_fk[p]) pp.send_f.push_back(g2l(k));
+        for (uint64_t k : recv_fk[p]) pp.recv_f.push_back(g2l(k));
+        std::vector<uint64_t>().swap(send_k[p]);
+        std::vector<uint64_t>().swap(recv_k[p]);
+    }
+    *out = P;
+    return FB2_OK;
+}
+
 extern "C" int fb2_partition_info(fb2_part* P, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
                                   int64_t* ndofs_local, int64_t* ndofs_owned) {
     FB2_CHECK(P, FB2_ERR_BAD_ARG, "fb2_partition_info: null handle");
@@ -587,6 +848,7 @@ extern "C" int fb2_partition_destroy(fb2_part* P) {
     if (!P) return FB2_OK;
     // the bound assembler may already be gone (host languages finalise in any order): use the saved device id
     if (P->bound) { cudaSetDevice(P->bound_device); free_binding(P); }
+    if (P->owns_global && P->gdh) { delete P->gdh->grid; delete P->gdh; }
     delete P;
     return FB2_OK;
 }

@@ -390,6 +390,13 @@ int fb2_partition_create(fb2_dh* dh, int nparts, int rank, const int* dims, fb2_
 int fb2_partition_create_from_owners(fb2_dh* dh, int nparts, int rank, const int32_t* cell_owner, fb2_part** out);
 /* cell -> rank from METIS_PartMeshDual (the CUDA toolkit's libmetis_static.a, linked statically): general grids */
 int fb2_partition_create_metis(fb2_dh* dh, int nparts, int rank, fb2_part** out);
+/* The same plan as fb2_partition_create for generate_grid(Hexahedron, nel, left, right) [+ fb2_grid_perturb(perturb)] with one
+   Lagrange field of order 1 and `vdim` components, built WITHOUT the global grid and DofHandler: close!'s first-appearance
+   numbering (src/Dofs/DofHandler.jl:576-738), ownership and node coordinates have closed forms on that grid, so every rank
+   derives its part directly (set-up time independent of the number of ranks).  `host_ctx`: a host-only context that owns the
+   metadata-only global problem the plan refers to.  dims: px, py, pz or NULL. */
+int fb2_partition_create_generated(fb2_ctx* host_ctx, const int64_t* nel, const double* left, const double* right, double perturb,
+                                   int vdim, int nparts, int rank, const int* dims, fb2_part** out);
 int fb2_partition_info(fb2_part* part, int64_t* ncells_local, int64_t* ncells_own, int64_t* nnodes_local,
                        int64_t* ndofs_local, int64_t* ndofs_owned);
 /* global ids (1-based) of the local cells / nodes / dofs, own-cell flags, owner rank of each local dof */

@@ -218,3 +218,37 @@ def test_metis_partition_covers_the_grid_and_is_balanced():
         assert sizes.min() > 0 and sizes.max() <= 1.3 * g.ncells / nparts + 2
         owned = np.concatenate([p.l2g_dof[p.dof_owner == p.rank] for p in parts])
         assert len(owned) == dh.ndofs == len(np.unique(owned))
+
+
+@pytest.mark.parametrize("nel,nparts,dims,vdim,pert", [
+    ((5, 4, 3), 2, None, 1, 0.2), ((6, 5, 4), 4, (2, 2, 1), 3, 0.2), ((7, 6, 5), 8, (2, 2, 2), 1, 0.0), ((9, 3, 2), 3, (3, 1, 1), 2, 0.1),
+    ((3, 3, 3), 1, None, 1, 0.2), ((2, 2, 2), 8, (2, 2, 2), 1, 0.2), ((5, 7, 6), 6, (1, 2, 3), 1, 0.2), ((64, 48, 48), 2, None, 1, 0.2),
+])
+def test_rank_local_setup_equals_the_plan_from_the_global_problem(nel, nparts, dims, vdim, pert, monkeypatch):
+    """fb2_partition_create_generated (closed forms for close!'s numbering, ownership and the node coordinates of generate_grid
+    + perturb; no global grid, no global DofHandler) against fb2_partition_create on the global problem: every array of the
+    plan, the exchange lists of every peer and the local grid / DofHandler must be identical."""
+    monkeypatch.setenv("FB2_HOST_THREADS", "3")      # the threaded sort / translate paths
+    h = fb.Context(-1)
+    g = fb.generate_grid(fb.Hexahedron, nel, ctx=h)
+    if pert:
+        g.perturb(pert)
+    ip = fb.Lagrange(fb.Hexahedron, 1) ** vdim
+    gdh = fb.close_(fb.add_(fb.DofHandler(g), "u", ip))
+
+    def plan(pt):
+        d = dict(cells=pt.cells_global, own=pt.cell_is_own, l2gn=pt.l2g_node, l2gd=pt.l2g_dof, downer=pt.dof_owner,
+                 info=np.array([pt.ncells_local, pt.ncells_own, pt.nnodes_local, pt.ndofs_local, pt.ndofs_owned]))
+        for o in range(pt.nparts):
+            d["counts%d" % o] = np.array(pt.peer_counts(o))
+            for k, v in pt.peer_lists(o).items():
+                d["%s%d" % (k, o)] = v
+        lg, ldh = pt.local_problem(h)
+        d["lcells"], d["lxyz"], d["ldofs"] = lg.cells, lg.nodes, np.asarray(ldh.cell_dofs)
+        return d
+
+    for r in range(nparts):
+        a = plan(fb.Partition(gdh, nparts, r, dims))
+        b = plan(fb.Partition.generated(nel, ip, nparts, r, dims, perturb=pert, host_ctx=h))
+        for k in a:
+            assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), (r, k)
