@@ -339,4 +339,14 @@ function partition_plan(global_dh_handle::Ptr{Cvoid}, nparts::Integer, rank::Int
     return p[]
 end
 
+# the same plan for generate_grid(Hexahedron, nel, left, right) [+ perturbation] with one Lagrange{RefHexahedron,1}()^vdim field,
+# built rank-locally (no global grid / DofHandler): px, py, pz blocks
+function partition_plan_generated(host_ctx::Ptr{Cvoid}, nel::NTuple{3, Int}, left::Vec{3, Float64}, right::Vec{3, Float64}, vdim::Integer,
+        nparts::Integer, rank::Integer, dims::NTuple{3, Int}; perturb::Float64 = 0.0)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    n, l, r, d = Int64[nel...], Float64[left...], Float64[right...], Cint[dims...]
+    @fb2 fb2_partition_create_generated (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Cint, Cint, Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}) host_ctx n l r perturb vdim nparts rank d p
+    return p[]
+end
+
 end # module
